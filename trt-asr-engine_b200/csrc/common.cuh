@@ -1,0 +1,85 @@
+// common.cuh -- shared helpers for the sm_100a kernels of libparakeet_trt (B200-native build).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+namespace pkb {
+
+// ---- model constants (published Parakeet-TDT-0.6B-v3 architecture; contract.json:54-66,161-215) ----
+constexpr int kNMels = 128;
+constexpr int kDModel = 1024;
+constexpr int kHeads = 8;
+constexpr int kDHead = 128;
+constexpr int kFF = 4096;
+constexpr int kConvK = 9;
+constexpr int kSubCh = 256;
+constexpr int kCacheS = 256;     // last_channel_cache_size
+constexpr int kRingCap = 288;    // physical ring capacity: 256 cached + up to 32 rows of the running chunk
+constexpr int kTimeCtx = 4;      // conv time cache columns
+constexpr int kCacheDrop = 3;
+constexpr int kValidOut = 3;
+constexpr int kDropPre = 2;
+constexpr int kVocab = 8193;     // token head incl. blank
+constexpr int kBlank = 8192;
+constexpr int kNDur = 5;
+constexpr int kJointOut = kVocab + kNDur;  // 8198
+constexpr int kPredH = 640;
+constexpr int kPredL = 2;
+constexpr int kJointH = 640;
+constexpr int kMaxSymbols = 8;
+constexpr int kMaxTq = 30;       // T<=256 frames per push -> 32 tokens -> 30 after drop
+constexpr int kPosRows = kCacheS + 2 * kMaxTq;  // relative positions -(kMaxTq-1) .. 256+kMaxTq-1 (padded)
+constexpr int kPosNeg = kMaxTq - 1;             // table row of relative position r is (r + kPosNeg)
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define PKB_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      throw ::pkb::CudaError(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " + \
+                             __FILE__ + ":" + std::to_string(__LINE__));                        \
+  } while (0)
+
+#define PKB_CHECK(cond, msg)                                                     \
+  do {                                                                           \
+    if (!(cond)) throw std::runtime_error(std::string("check failed: ") + (msg)); \
+  } while (0)
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_as_float(((uint32_t)b) << 16); }
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+// Split an f32 into bf16 hi + bf16 lo (hi = rn(x), lo = rn(x - hi)): hi+lo carries ~16 mantissa bits.
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+// Store one GEMM-A-operand element.  Activations feeding a GEMM are bf16 [rows, lda]; in split ("precise") mode a
+// second plane lo_off elements further holds the bf16 low parts (lo_off == 0: plain bf16).
+__device__ __forceinline__ void store_act(__nv_bfloat16* A, size_t row, int lda, int col, float v, long long lo_off) {
+  __nv_bfloat16 hi, lo;
+  split_bf16(v, hi, lo);
+  A[row * (size_t)lda + col] = hi;
+  if (lo_off) A[row * (size_t)lda + col + lo_off] = lo;
+}
+#endif
+
+}  // namespace pkb

@@ -1,0 +1,59 @@
+// dec_kernels.cuh -- device-side state and kernels of the batched TDT greedy decode (see dec_kernels.cu).
+#pragma once
+#include "common.cuh"
+#include "enc_kernels.cuh"
+
+namespace pkb {
+
+constexpr int kMaxStepsPerChunk = 32;   // >= valid_out_len * max_symbols (3*8 = 24 joint evaluations per chunk)
+
+struct DecodeDev {
+  int B = 0;
+  int max_symbols = kMaxSymbols;
+  int punct_suppress = 1;
+  float blank_penalty = 0.0f;
+  // per entry (this step)
+  const int* slot = nullptr;      // [B]
+  const int* row_off = nullptr;   // [B+1] packed-row prefix (encoder rows of entry e start at row_off[e])
+  const int* t_enc = nullptr;     // [B] frames to decode = min(qlen, valid_out_len)
+  int* t_cur = nullptr;           // [B]
+  int* n_sym = nullptr;           // [B]
+  int* active = nullptr;          // [B]
+  int* emit_tok = nullptr;        // [B] token emitted in this iteration or -1
+  int* pred_rowmap = nullptr;     // [B] slot if emitted else -1 (row map of the pred-projection epilogue)
+  int* n_steps = nullptr;         // [B]
+  int* steps = nullptr;           // [B][kMaxStepsPerChunk][3] = (time_idx, token, duration)
+  int* n_active = nullptr;        // scalar: entries still active after the last select
+  int* m_pred = nullptr;          // scalar: B if any entry emitted in this iteration else 0 (device-side GEMM M)
+  // tensors
+  const float* enc_proj = nullptr;   // [M,640]  joint.enc(enc) + bias
+  float* pred_proj = nullptr;        // [slots,640] joint.pred(g) + bias (cached per stream, refreshed on emission)
+  const float* logits = nullptr;     // [B,8198]
+  const float* gates = nullptr;      // [B,2560]
+  const __nv_bfloat16* embed = nullptr;  // [8193,640]
+  const unsigned* punct_bits = nullptr;  // [ceil(8193/32)]
+  // per slot state
+  float* pred_h = nullptr;        // [slots][2][640]
+  float* pred_c = nullptr;
+  float* pred_g = nullptr;        // [slots][640]
+  int* n_emitted = nullptr;       // [slots] tokens emitted so far in the utterance
+  int* y_id = nullptr;            // [slots] last emitted / primed token
+  // GEMM operands
+  ActOut act_hidden{};            // [B,640]
+  ActOut act_pred{};              // [B,1280]
+  ActOut act_g{};                 // [B,640]
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+#endif
+
+void launch_decode_begin(const DecodeDev& d, cudaStream_t st);
+void launch_decode_iter_reset(const DecodeDev& d, cudaStream_t st);
+void launch_joint_hidden(const DecodeDev& d, cudaStream_t st);
+void launch_tdt_select(const DecodeDev& d, cudaStream_t st);
+void launch_pred_input(const DecodeDev& d, cudaStream_t st);
+void launch_lstm_cell(const DecodeDev& d, int layer, cudaStream_t st);
+void launch_force_token(const DecodeDev& d, const int* d_toks, cudaStream_t st);
+
+}  // namespace pkb

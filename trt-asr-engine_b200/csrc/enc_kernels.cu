@@ -1,0 +1,469 @@
+// enc_kernels.cu -- see enc_kernels.cuh.
+//
+// Semantics restated from NeMo 2.6.0 (ConformerEncoder.forward_for_export, reached by the reference through
+// /root/reference/tools/export_onnx/export.py:343-375; tensor contract contracts/parakeet-tdt-0.6b-v3.contract.json:97-159):
+//   * ConvSubsampling dw_striding: conv0+ReLU, 2x(depthwise s2 + pointwise + ReLU), flatten (c*16+f), Linear
+//   * RelPositionMultiHeadAttention over concat(cache, x); rel_shift == table row (Tk-Tq+i)-j; masked keys excluded
+//   * CausalConv1D with a 4-column time cache, cache_drop_size 3
+// B200-first differences from the exported graph: K/V are projected once and kept in per-stream ring buffers (the
+// exported graph re-projects all 256 cached rows every chunk), linear_pos(pos_emb) is precomputed per layer,
+// and the FIFO caches are rings addressed by a per-stream head, so carry-over costs O(new rows).
+#include "enc_kernels.cuh"
+
+namespace pkb {
+
+__device__ __forceinline__ int find_entry(const int* __restrict__ prefix, int B, int idx) {
+  int lo = 0, hi = B - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (prefix[mid] <= idx) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// ------------------------------------------------------------------------------------------------ rows
+__global__ void build_rows_kernel(BatchDev b) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < b.M) {
+    const int e = find_entry(b.row_off, b.B, i);
+    b.row_entry[i] = e;
+    b.row_pos[i] = i - b.row_off[e];
+  }
+  if (i < b.sumT3) {
+    const int e = find_entry(b.off3, b.B, i);
+    const int t3 = i - b.off3[e];
+    b.rowmap3[i] = (t3 >= kDropPre && t3 - kDropPre < b.Tq[e]) ? b.row_off[e] + t3 - kDropPre : -1;
+  }
+}
+void launch_build_rows(const BatchDev& b, cudaStream_t st) {
+  const int n = b.M > b.sumT3 ? b.M : b.sumT3;
+  if (n <= 0) return;
+  build_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(b);
+  PKB_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------ subsampling stage 1
+// One CTA per (entry, t2).  7 input rows -> conv0 (3 rows x 64 x 32ch at a time, in smem) -> depthwise -> 32 x 256 outputs.
+__global__ void __launch_bounds__(256)
+subsample_stage1_kernel(BatchDev b, const float* __restrict__ feat_ring, int ring_cap, SubsampleWeights w, ActOut a1) {
+  __shared__ float s_in[7][kNMels + 2];        // [row][f+1], zero padded
+  __shared__ float s_y0[3][66][33];            // [t1 row][f1+1][c] (+1 pad column against bank conflicts)
+  const int g = blockIdx.x;
+  const int e = find_entry(b.off2, b.B, g);
+  const int t2 = g - b.off2[e];
+  const int T = b.T[e], T1 = b.T1[e];
+  const float* ring = feat_ring + (size_t)b.slot[e] * ring_cap * kNMels;
+  const int f0 = b.f0[e];
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < 7 * (kNMels + 2); i += 256) {
+    const int r = i / (kNMels + 2), fp = i % (kNMels + 2);
+    const int t = 4 * t2 - 3 + r, f = fp - 1;
+    float v = 0.0f;
+    if (t >= 0 && t < T && f >= 0 && f < kNMels) v = ring[(size_t)((f0 + t) % ring_cap) * kNMels + f];
+    s_in[r][fp] = v;
+  }
+  const int c_l = tid & 31, fgrp = tid >> 5;   // channel within group, 8 f-groups
+  for (int cg = 0; cg < kSubCh / 32; ++cg) {
+    const int c = cg * 32 + c_l;
+    float k0[9], k2[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { k0[i] = w.w0[c * 9 + i]; k2[i] = w.w2[c * 9 + i]; }
+    const float bias0 = w.b0[c], bias2 = w.b2[c];
+    __syncthreads();   // s_in ready (first iteration) / previous s_y0 consumers done
+    // conv0 + ReLU for t1 = 2*t2-1 .. 2*t2+1
+#pragma unroll
+    for (int r1 = 0; r1 < 3; ++r1) {
+      const int t1 = 2 * t2 - 1 + r1;
+      const bool row_ok = t1 >= 0 && t1 < T1;
+      for (int i = 0; i < 8; ++i) {
+        const int f1 = fgrp + 8 * i;
+        float acc = 0.0f;
+        if (row_ok) {
+          acc = bias0;
+#pragma unroll
+          for (int dt = 0; dt < 3; ++dt)
+#pragma unroll
+            for (int df = 0; df < 3; ++df)
+              acc = fmaf(k0[dt * 3 + df], s_in[2 * r1 + dt][2 * f1 + df], acc);   // input row 2*t1-1+dt == local 2*r1+dt
+          acc = fmaxf(acc, 0.0f);
+        }
+        s_y0[r1][f1 + 1][c_l] = acc;
+      }
+      if (tid < 64) { s_y0[r1][(tid >> 5) * 65][c_l] = 0.0f; }   // f1 = -1 and f1 = 64 padding columns
+    }
+    __syncthreads();
+    // depthwise conv.2 (3x3, s2, p1): f2 = fgrp + 8*i
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int f2 = fgrp + 8 * i;
+      float acc = bias2;
+#pragma unroll
+      for (int dt = 0; dt < 3; ++dt)
+#pragma unroll
+        for (int df = 0; df < 3; ++df)
+          acc = fmaf(k2[dt * 3 + df], s_y0[dt][2 * f2 + df][c_l], acc);            // y0 col 2*f2-1+df == padded 2*f2+df
+      store_act(a1.ptr, (size_t)g * 32 + f2, a1.lda, c, acc, a1.lo_off);
+    }
+  }
+}
+void launch_subsample_stage1(const BatchDev& b, const float* feat_ring, int ring_cap, const SubsampleWeights& w, ActOut a1,
+                             cudaStream_t st) {
+  if (b.sumT2 <= 0) return;
+  subsample_stage1_kernel<<<b.sumT2, 256, 0, st>>>(b, feat_ring, ring_cap, w, a1);
+  PKB_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------ subsampling stage 2
+// One CTA per (entry, t3); thread == channel (256), loop over 16 output frequency bins.
+__global__ void __launch_bounds__(256)
+subsample_stage2_kernel(BatchDev b, const float* __restrict__ y1, SubsampleWeights w, ActOut a2) {
+  const int g = blockIdx.x;
+  const int e = find_entry(b.off3, b.B, g);
+  const int t3 = g - b.off3[e];
+  const int T2 = b.T2[e];
+  const int c = threadIdx.x;
+  float k[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) k[i] = w.w5[c * 9 + i];
+  const float bias = w.b5[c];
+  const float* base = y1 + (size_t)b.off2[e] * 32 * kSubCh;   // [T2][32][256]
+  for (int f3 = 0; f3 < 16; ++f3) {
+    float acc = bias;
+#pragma unroll
+    for (int dt = 0; dt < 3; ++dt) {
+      const int t2 = 2 * t3 - 1 + dt;
+      if (t2 < 0 || t2 >= T2) continue;
+#pragma unroll
+      for (int df = 0; df < 3; ++df) {
+        const int f2 = 2 * f3 - 1 + df;
+        if (f2 < 0 || f2 >= 32) continue;
+        acc = fmaf(k[dt * 3 + df], base[((size_t)t2 * 32 + f2) * kSubCh + c], acc);
+      }
+    }
+    store_act(a2.ptr, (size_t)g * 16 + f3, a2.lda, c, acc, a2.lo_off);
+  }
+}
+void launch_subsample_stage2(const BatchDev& b, const float* y1, const SubsampleWeights& w, ActOut a2, cudaStream_t st) {
+  if (b.sumT3 <= 0) return;
+  subsample_stage2_kernel<<<b.sumT3, 256, 0, st>>>(b, y1, w, a2);
+  PKB_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+__device__ __forceinline__ void ln_row(float (&v)[32], const float* __restrict__ g, const float* __restrict__ bta, int lane) {
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.0f / kDModel);
+  float q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+  const float var = warp_sum(q) * (1.0f / kDModel);
+  const float inv = 1.0f / sqrtf(var + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int col = i * 128 + lane * 4;
+    const float4 gg = *reinterpret_cast<const float4*>(g + col);
+    const float4 bb = *reinterpret_cast<const float4*>(bta + col);
+    v[4 * i + 0] = (v[4 * i + 0] - mean) * inv * gg.x + bb.x;
+    v[4 * i + 1] = (v[4 * i + 1] - mean) * inv * gg.y + bb.y;
+    v[4 * i + 2] = (v[4 * i + 2] - mean) * inv * gg.z + bb.z;
+    v[4 * i + 3] = (v[4 * i + 3] - mean) * inv * gg.w + bb.w;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+layernorm_kernel(float* __restrict__ x, int M, const float* __restrict__ g1, const float* __restrict__ b1,
+                 const float* __restrict__ g2, const float* __restrict__ b2, int write_x, ActOut a, AcacheOut ac, int has_ac) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float v[32];
+  float* xr = x + (size_t)row * kDModel;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 t = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+  ln_row(v, g1, b1, lane);
+  if (has_ac) {
+    const int e = ac.row_entry[row];
+    const int phys = (ac.entry_head[e] + kCacheS + ac.row_pos[row]) % kRingCap;
+    const size_t base = ((size_t)ac.entry_slot[e] * kRingCap + phys) * kDModel;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int col = i * 128 + lane * 4;
+      if (ac.is_f32) {
+        *reinterpret_cast<float4*>((float*)ac.ring + base + col) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      } else {
+        __nv_bfloat16* r = (__nv_bfloat16*)ac.ring + base + col;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r[j] = __float2bfloat16_rn(v[4 * i + j]);
+      }
+    }
+  }
+  if (write_x) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      *reinterpret_cast<float4*>(xr + i * 128 + lane * 4) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    if (g2 != nullptr) ln_row(v, g2, b2, lane);
+  }
+  if (a.ptr == nullptr) return;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) store_act(a.ptr, row, a.lda, i * 128 + lane * 4 + j, v[4 * i + j], a.lo_off);
+}
+void launch_layernorm(float* x, int M, const float* g1, const float* b1, const float* g2, const float* b2, int write_x, ActOut a,
+                      const AcacheOut* ac, cudaStream_t st) {
+  if (M <= 0) return;
+  AcacheOut z{};
+  layernorm_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, M, g1, b1, g2, b2, write_x, a, ac ? *ac : z, ac != nullptr);
+  PKB_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------ attention
+// One CTA (128 threads) per (entry, head).
+//   phase A1: thread == key column j (coalesced over the K^T ring):  ac[i][j] = (q_i + u) . k_j
+//   phase A2: thread == relative-position column:                      G[i][r]  = (q_i + v) . p_r
+//   phase B : scores[i][j] = (ac[i][j] + G[i][(256+i-j)+kPosNeg]) / sqrt(128), masked softmax (one warp per query row)
+//   phase C : thread == head dim d (coalesced over the V ring rows):   ctx[i][d] = sum_j p[i][j] v_j[d]
+constexpr int kQG = 6;   // queries processed together in registers (steady-state Tq)
+
+template <typename KV> __device__ __forceinline__ float ld_kv(const KV* p);
+template <> __device__ __forceinline__ float ld_kv<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ld_kv<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename KV>
+__global__ void __launch_bounds__(128)
+attention_kernel(BatchDev b, AttnArgs a) {
+  extern __shared__ float smem[];
+  const int e = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+  const int Tq = b.Tq[e], qlen = b.qlen[e], len = b.len[e], head = b.head[e], slot = b.slot[e];
+  const int row0 = b.row_off[e];
+  const int Tk = kCacheS + Tq;
+  const int npos = Tk + Tq - 1;                 // relative positions -(Tq-1) .. Tk-1
+  float* s_qu = smem;                           // [Tq][128]
+  float* s_qv = s_qu + Tq * kDHead;             // [Tq][128]
+  float* s_sc = s_qv + Tq * kDHead;             // [Tq][kRingCap]   scores / probabilities
+  float* s_g = s_sc + Tq * kRingCap;            // [Tq][kPosRows]   position scores
+
+  for (int i = tid; i < Tq * kDHead; i += 128) {
+    const int qi = i >> 7, d = i & 127;
+    const float qv = a.q[(size_t)(row0 + qi) * kDModel + h * kDHead + d];
+    s_qu[i] = qv + a.bias_u[h * kDHead + d];
+    s_qv[i] = qv + a.bias_v[h * kDHead + d];
+  }
+  __syncthreads();
+
+  const KV* kt = reinterpret_cast<const KV*>(a.kring) + ((size_t)slot * kHeads + h) * kDHead * kRingCap;
+  const KV* pt = reinterpret_cast<const KV*>(a.ppos_t) + (size_t)h * kDHead * kPosRows;
+  const int r_lo = kPosNeg - (Tq - 1);          // first table row used
+  for (int q0 = 0; q0 < Tq; q0 += kQG) {
+    const int nq = min(kQG, Tq - q0);
+    for (int j = kCacheS - len + tid; j < kCacheS + qlen; j += 128) {       // A1 (valid keys only)
+      const int phys = (head + j) % kRingCap;
+      float acc[kQG];
+#pragma unroll
+      for (int i = 0; i < kQG; ++i) acc[i] = 0.0f;
+      for (int d = 0; d < kDHead; ++d) {
+        const float kv = ld_kv<KV>(kt + (size_t)d * kRingCap + phys);
+#pragma unroll
+        for (int i = 0; i < kQG; ++i)
+          if (i < nq) acc[i] = fmaf(s_qu[(q0 + i) * kDHead + d], kv, acc[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < kQG; ++i)
+        if (i < nq) s_sc[(q0 + i) * kRingCap + j] = acc[i];
+    }
+    for (int c = tid; c < npos; c += 128) {     // A2
+      const int r = r_lo + c;
+      float acc[kQG];
+#pragma unroll
+      for (int i = 0; i < kQG; ++i) acc[i] = 0.0f;
+      for (int d = 0; d < kDHead; ++d) {
+        const float pv = ld_kv<KV>(pt + (size_t)d * kPosRows + r);
+#pragma unroll
+        for (int i = 0; i < kQG; ++i)
+          if (i < nq) acc[i] = fmaf(s_qv[(q0 + i) * kDHead + d], pv, acc[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < kQG; ++i)
+        if (i < nq) s_g[(q0 + i) * kPosRows + r] = acc[i];
+    }
+  }
+  __syncthreads();
+
+  // phase B: masked softmax; key j valid iff (j >= 256-len for cached rows) or (j-256 < qlen for new rows)
+  const float scale = 0.08838834764831845f;     // 1/sqrt(128)
+  const int warp = tid >> 5, lane = tid & 31;
+  const int j_lo = kCacheS - len, j_hi = kCacheS + qlen;
+  for (int i = warp; i < Tq; i += 4) {
+    float mx = -INFINITY;
+    for (int j = j_lo + lane; j < j_hi; j += 32) {
+      const float s = (s_sc[i * kRingCap + j] + s_g[i * kPosRows + (kCacheS + i - j) + kPosNeg]) * scale;
+      s_sc[i * kRingCap + j] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float sum = 0.0f;
+    for (int j = j_lo + lane; j < j_hi; j += 32) {
+      const float p = __expf(s_sc[i * kRingCap + j] - mx);
+      s_sc[i * kRingCap + j] = p;
+      sum += p;
+    }
+    sum = warp_sum(sum);
+    const float inv = (i < qlen && sum > 0.0f) ? 1.0f / sum : 0.0f;   // padded query rows are fully masked -> zeros
+    for (int j = j_lo + lane; j < j_hi; j += 32) s_sc[i * kRingCap + j] *= inv;
+  }
+  __syncthreads();
+
+  // phase C
+  const KV* vr = reinterpret_cast<const KV*>(a.vring) + (size_t)slot * kRingCap * kDModel + h * kDHead + tid;
+  for (int q0 = 0; q0 < Tq; q0 += kQG) {
+    const int nq = min(kQG, Tq - q0);
+    float acc[kQG];
+#pragma unroll
+    for (int i = 0; i < kQG; ++i) acc[i] = 0.0f;
+    for (int j = j_lo; j < j_hi; ++j) {
+      const int phys = (head + j) % kRingCap;
+      const float vv = ld_kv<KV>(vr + (size_t)phys * kDModel);
+#pragma unroll
+      for (int i = 0; i < kQG; ++i)
+        if (i < nq) acc[i] = fmaf(s_sc[(q0 + i) * kRingCap + j], vv, acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < kQG; ++i)
+      if (i < nq) store_act(a.ctx.ptr, row0 + q0 + i, a.ctx.lda, h * kDHead + tid, acc[i], a.ctx.lo_off);
+  }
+}
+void launch_attention(const BatchDev& b, const AttnArgs& a, cudaStream_t st) {
+  if (b.B <= 0) return;
+  const size_t smem = (size_t)b.max_Tq * (2 * kDHead + kRingCap + kPosRows) * sizeof(float);
+  static size_t attr_set[2] = {0, 0};
+  if (smem > 48 * 1024 && attr_set[a.kv_f32] < smem) {
+    if (a.kv_f32) PKB_CUDA(cudaFuncSetAttribute(attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else PKB_CUDA(cudaFuncSetAttribute(attention_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[a.kv_f32] = smem;
+  }
+  if (a.kv_f32) attention_kernel<float><<<dim3(b.B, kHeads), 128, smem, st>>>(b, a);
+  else attention_kernel<__nv_bfloat16><<<dim3(b.B, kHeads), 128, smem, st>>>(b, a);
+  PKB_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------ conv module middle
+// One CTA per (entry, 256-channel group); thread == channel.
+__global__ void __launch_bounds__(256)
+dwconv_kernel(BatchDev b, DwConvArgs a) {
+  const int e = blockIdx.x, ch = blockIdx.y * 256 + threadIdx.x;
+  const int Tq = b.Tq[e], qlen = b.qlen[e], row0 = b.row_off[e];
+  float* cache = a.cache_tm + (size_t)b.slot[e] * a.slot_stride + (size_t)ch * kTimeCtx;
+  float w[kConvK];
+#pragma unroll
+  for (int i = 0; i < kConvK; ++i) w[i] = a.w[ch * kConvK + i];
+  const float bias = a.bias[ch];
+  // ext = [cache(4) | c(Tq, zero past qlen: pad_mask) | 0 0 0 0]; sliding window of 9
+  const float4 cv = *reinterpret_cast<const float4*>(cache);
+  float win[kConvK];
+  win[0] = cv.x; win[1] = cv.y; win[2] = cv.z; win[3] = cv.w;
+#pragma unroll
+  for (int i = 4; i < kConvK; ++i) {
+    const int t = i - 4;
+    win[i] = (t < Tq && t < qlen) ? a.c[(size_t)(row0 + t) * kDModel + ch] : 0.0f;
+  }
+  // new cache = ext[Tq+1 .. Tq+5)   (new_x[:-3][-4:], cache_drop_size 3)
+  float nc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = Tq + 1 + i;                 // index into ext
+    float v = 0.0f;
+    if (idx < 4) v = idx == 0 ? cv.x : idx == 1 ? cv.y : idx == 2 ? cv.z : cv.w;
+    else if (idx - 4 < Tq) v = (idx - 4 < qlen) ? a.c[(size_t)(row0 + idx - 4) * kDModel + ch] : 0.0f;
+    nc[i] = v;
+  }
+  for (int t = 0; t < Tq; ++t) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kConvK; ++i) acc = fmaf(w[i], win[i], acc);
+    acc += bias;
+    store_act(a.out.ptr, row0 + t, a.out.lda, ch, silu(acc), a.out.lo_off);
+#pragma unroll
+    for (int i = 0; i < kConvK - 1; ++i) win[i] = win[i + 1];
+    const int tn = t + 5;                       // next ext index t+1+8 -> c index t+5
+    win[kConvK - 1] = (tn < Tq && tn < qlen) ? a.c[(size_t)(row0 + tn) * kDModel + ch] : 0.0f;
+  }
+  *reinterpret_cast<float4*>(cache) = make_float4(nc[0], nc[1], nc[2], nc[3]);
+}
+void launch_dwconv(const BatchDev& b, const DwConvArgs& a, cudaStream_t st) {
+  if (b.B <= 0) return;
+  dwconv_kernel<<<dim3(b.B, kDModel / 256), 256, 0, st>>>(b, a);
+  PKB_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------ output
+__global__ void __launch_bounds__(256)
+gather_output_kernel(BatchDev b, const float* __restrict__ x, float* __restrict__ enc_out) {
+  const int e = blockIdx.x;
+  const int row0 = b.row_off[e], Tq = b.Tq[e];
+  for (int i = threadIdx.x; i < kDModel * kValidOut; i += 256) {
+    const int d = i / kValidOut, t = i % kValidOut;
+    enc_out[(size_t)e * kDModel * kValidOut + i] = t < Tq ? x[(size_t)(row0 + t) * kDModel + d] : 0.0f;
+  }
+}
+void launch_gather_output(const BatchDev& b, const float* x, float* enc_out, cudaStream_t st) {
+  if (b.B <= 0) return;
+  gather_output_kernel<<<b.B, 256, 0, st>>>(b, x, enc_out);
+  PKB_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------ import / export
+__global__ void __launch_bounds__(256)
+acache_to_act_kernel(const void* __restrict__ acache, int is_f32, const int* __restrict__ slots, const int* __restrict__ heads,
+                     ActOut a) {
+  const int e = blockIdx.y, j = blockIdx.x;     // logical cache row j of entry e
+  const int phys = (heads[e] + j) % kRingCap;
+  const size_t src = ((size_t)slots[e] * kRingCap + phys) * kDModel;
+  for (int c = threadIdx.x; c < kDModel; c += 256) {
+    const float v = is_f32 ? ((const float*)acache)[src + c] : __bfloat162float(((const __nv_bfloat16*)acache)[src + c]);
+    store_act(a.ptr, (size_t)e * kCacheS + j, a.lda, c, v, a.lo_off);
+  }
+}
+void launch_acache_to_act(const void* acache_layer, int is_f32, const int* slots, const int* heads, int n, ActOut a, cudaStream_t st) {
+  if (n <= 0) return;
+  acache_to_act_kernel<<<dim3(kCacheS, n), 256, 0, st>>>(acache_layer, is_f32, slots, heads, a);
+  PKB_CUDA(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(256)
+acache_copy_kernel(void* __restrict__ acache, int is_f32, const int* __restrict__ slots, const int* __restrict__ heads,
+                   float* __restrict__ ext, long long ext_entry_stride, int to_ring) {
+  const int e = blockIdx.y, j = blockIdx.x;
+  const int phys = (heads[e] + j) % kRingCap;
+  const size_t r = ((size_t)slots[e] * kRingCap + phys) * kDModel;
+  float* x = ext + (size_t)e * ext_entry_stride + (size_t)j * kDModel;
+  for (int c = threadIdx.x; c < kDModel; c += 256) {
+    if (to_ring) {
+      if (is_f32) ((float*)acache)[r + c] = x[c];
+      else ((__nv_bfloat16*)acache)[r + c] = __float2bfloat16_rn(x[c]);
+    } else {
+      x[c] = is_f32 ? ((const float*)acache)[r + c] : __bfloat162float(((const __nv_bfloat16*)acache)[r + c]);
+    }
+  }
+}
+void launch_acache_import(void* acache_layer, int is_f32, const int* slots, const int* heads, int n, const float* src,
+                          long long src_entry_stride, cudaStream_t st) {
+  if (n <= 0) return;
+  acache_copy_kernel<<<dim3(kCacheS, n), 256, 0, st>>>(acache_layer, is_f32, slots, heads, const_cast<float*>(src),
+                                                        src_entry_stride, 1);
+  PKB_CUDA(cudaGetLastError());
+}
+void launch_acache_export(const void* acache_layer, int is_f32, const int* slots, const int* heads, int n, float* dst,
+                          long long dst_entry_stride, cudaStream_t st) {
+  if (n <= 0) return;
+  acache_copy_kernel<<<dim3(kCacheS, n), 256, 0, st>>>(const_cast<void*>(acache_layer), is_f32, slots, heads, dst,
+                                                        dst_entry_stride, 0);
+  PKB_CUDA(cudaGetLastError());
+}
+
+}  // namespace pkb

@@ -1,0 +1,98 @@
+// enc_kernels.cuh -- non-GEMM kernels of the cache-aware FastConformer chunk (piece 2) and the per-stream
+// cache carry-over (piece 4).  See enc_kernels.cu for the mapping of each kernel.
+#pragma once
+#include "common.cuh"
+
+namespace pkb {
+
+// Per-step batch descriptor.  One "entry" = one stream advancing by one chunk in this batched step.
+// All arrays live in one device int buffer, written by a single H2D copy per step (see Engine::upload_batch).
+struct BatchDev {
+  int B = 0;          // entries
+  int M = 0;          // packed encoder rows = sum Tq
+  int sumT2 = 0, sumT3 = 0;
+  int max_Tq = 0;
+  const int* slot = nullptr;    // [B] state slot of the stream
+  const int* T = nullptr;       // [B] input feature frames of this chunk
+  const int* f0 = nullptr;      // [B] absolute index of the chunk's first frame in the stream's feature ring
+  const int* T1 = nullptr;      // [B] frames after conv0 ((T-1)/2+1)
+  const int* T2 = nullptr;      // [B] after dw1
+  const int* T3 = nullptr;      // [B] after dw2 (pre-encode tokens)
+  const int* Tq = nullptr;      // [B] T3 - drop_extra_pre_encoded
+  const int* qlen = nullptr;    // [B] valid new tokens (length after subsampling - 2, clamped to [0,Tq])
+  const int* len = nullptr;     // [B] cache_last_channel_len on entry
+  const int* head = nullptr;    // [B] physical ring index of logical cache position 0
+  const int* off2 = nullptr;    // [B+1] prefix sums of T2
+  const int* off3 = nullptr;    // [B+1] prefix sums of T3
+  const int* row_off = nullptr; // [B+1] prefix sums of Tq
+  int* row_entry = nullptr;     // [M]
+  int* row_pos = nullptr;       // [M]
+  int* rowmap3 = nullptr;       // [sumT3] -> packed row or -1 (dropped pre-encode token)
+};
+
+struct SubsampleWeights {
+  const float* w0; const float* b0;   // conv.0  [256,1,3,3], [256]
+  const float* w2; const float* b2;   // conv.2  depthwise
+  const float* w5; const float* b5;   // conv.5  depthwise
+};
+
+struct ActOut {             // destination of a GEMM-A operand (bf16 hi plane [+ lo plane])
+  __nv_bfloat16* ptr;
+  int lda;
+  long long lo_off;
+};
+
+void launch_build_rows(const BatchDev& b, cudaStream_t st);
+
+// conv0(1->256,3x3,s2,p1)+ReLU fused with depthwise conv.2 (3x3,s2,p1): feature ring -> A1 [sumT2*32, 256]
+void launch_subsample_stage1(const BatchDev& b, const float* feat_ring, int ring_cap, const SubsampleWeights& w, ActOut a1,
+                             cudaStream_t st);
+// depthwise conv.5 over y1 f32 [sumT2*32, 256] (channels-last) -> A2 [sumT3*16, 256]
+void launch_subsample_stage2(const BatchDev& b, const float* y1, const SubsampleWeights& w, ActOut a2, cudaStream_t st);
+
+// LayerNorm over rows of x f32 [M,1024] (one warp per row, eps 1e-5).
+//  write_x == 0:  A <- LN1(x)
+//  write_x == 1:  x <- LN1(x) in place; A <- (g2 ? LN2(x) : x) if A.ptr   (norm_out fused with the next layer's
+//                 norm_feed_forward1; after the last layer A is the joint's encoder-projection operand)
+//  acache != null: LN1(x) rows are also stored in the contract cache ring (cache_last_channel, pre-projection)
+struct AcacheOut { void* ring; int is_f32; const int* row_entry; const int* row_pos; const int* entry_slot; const int* entry_head; };
+void launch_layernorm(float* x, int M, const float* g1, const float* b1, const float* g2, const float* b2, int write_x, ActOut a,
+                      const AcacheOut* ac, cudaStream_t st);
+
+// Relative-position multi-head attention over [ring cache (256) || new rows (Tq)] for every (entry, head).
+struct AttnArgs {
+  const float* q;          // [M,1024] f32
+  const void* kring;       // this layer's K^T ring
+  const void* vring;       // this layer's V ring
+  const void* ppos_t;      // this layer's projected position table, transposed [head][d][kPosRows]
+  int kv_f32;              // element type of the three above (1: f32, 0: bf16)
+  const float* bias_u;     // [8,128]
+  const float* bias_v;
+  ActOut ctx;              // [M,1024]
+};
+void launch_attention(const BatchDev& b, const AttnArgs& a, cudaStream_t st);
+
+// Conv-module middle: depthwise k=9 over [time cache(4) | c(Tq) | 0000], folded BatchNorm, SiLU; updates the time cache.
+struct DwConvArgs {
+  const float* c;          // post-GLU activations f32 [M,1024]
+  float* cache_tm;         // this layer's time cache [slot][1024][4]  (stride between slots passed separately)
+  long long slot_stride;   // floats between consecutive slots of cache_tm
+  const float* w;          // [1024,9] depthwise weights with BN scale folded in
+  const float* bias;       // [1024] folded BN offset
+  ActOut out;              // [M,1024]
+};
+void launch_dwconv(const BatchDev& b, const DwConvArgs& a, cudaStream_t st);
+
+// encoder_output [B,1024,valid] <- first `valid_out` rows of each entry (transposed), zero-filled past qlen
+void launch_gather_output(const BatchDev& b, const float* x, float* enc_out /*[B,1024,3]*/, cudaStream_t st);
+
+// ---- state import/export at the contract layouts (cache carry-over across the C ABI) ----
+// acache ring rows (logical 0..255) -> bf16 hi/lo operand rows, for re-projecting K/V after an import
+void launch_acache_to_act(const void* acache_layer, int is_f32, const int* slots, const int* heads, int n, ActOut a, cudaStream_t st);
+// contract cache_last_channel [n,L,256,1024] f32 (host layout, on device) <-> acache rings
+void launch_acache_import(void* acache_layer, int is_f32, const int* slots, const int* heads, int n, const float* src,
+                          long long src_entry_stride, cudaStream_t st);
+void launch_acache_export(const void* acache_layer, int is_f32, const int* slots, const int* heads, int n, float* dst,
+                          long long dst_entry_stride, cudaStream_t st);
+
+}  // namespace pkb

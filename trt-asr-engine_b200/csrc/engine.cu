@@ -1,0 +1,1113 @@
+// engine.cu -- see engine.h.  Host orchestration of the batched streaming step.
+#include "engine.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <fstream>
+
+namespace pkb {
+
+namespace {
+
+template <typename T>
+T* dev_alloc(size_t n) {
+  T* p = nullptr;
+  if (n == 0) n = 1;
+  PKB_CUDA(cudaMalloc(&p, n * sizeof(T)));
+  return p;
+}
+template <typename T>
+T* dev_upload(const std::vector<T>& v) {
+  T* p = dev_alloc<T>(v.size());
+  if (!v.empty()) PKB_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return p;
+}
+
+inline int sub_len(int L) { return L <= 0 ? 0 : (L - 1) / 2 + 1; }   // floor((L + 2 - 3)/2) + 1, calc_length of dw_striding
+
+struct GemmW {
+  __nv_bfloat16* w = nullptr;
+  int N = 0, K = 0;
+  TensorMap map;
+};
+
+struct ActBuf {
+  __nv_bfloat16* ptr = nullptr;
+  int rows_cap = 0, K = 0;
+  long long lo_off = 0;
+  TensorMap map;
+  ActOut out() const { return ActOut{ptr, K, lo_off}; }
+};
+
+struct LayerW {
+  float *n_ff1_g, *n_ff1_b, *n_att_g, *n_att_b, *n_conv_g, *n_conv_b, *n_ff2_g, *n_ff2_b, *n_out_g, *n_out_b;
+  GemmW ff1_1, ff1_2, qkv, kv, out, pw1, pw2, ff2_1, ff2_2;
+  float *dw_w, *dw_b, *bias_u, *bias_v;
+  void* ppos_t;
+};
+
+// ---- small utility kernels ----
+__global__ void f32_to_act_kernel(const float* __restrict__ src, long long src_row_stride, long long src_col_stride, int rows,
+                                  int cols, ActOut a) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * cols) return;
+  const int r = (int)(i / cols), c = (int)(i % cols);
+  store_act(a.ptr, r, a.lda, c, src[r * src_row_stride + c * src_col_stride], a.lo_off);
+}
+// hidden[(b*T + t)*U + u] = relu(E[b*T+t] + P[b*U+u])
+__global__ void joint_hidden_grid_kernel(const float* __restrict__ E, const float* __restrict__ P, int T, int U, ActOut a) {
+  const int row = blockIdx.x;
+  const int u = row % U, bt = row / U, b = bt / T;
+  for (int c = threadIdx.x; c < kJointH; c += blockDim.x)
+    store_act(a.ptr, row, a.lda, c, fmaxf(E[(size_t)bt * kJointH + c] + P[((size_t)b * U + u) * kJointH + c], 0.0f), a.lo_off);
+}
+// P^T[h][d][r] <- P[r][h*128+d]
+__global__ void ppos_transpose_kernel(const float* __restrict__ P, void* __restrict__ out, int is_f32) {
+  const int r = blockIdx.x;
+  for (int c = threadIdx.x; c < kDModel; c += blockDim.x) {
+    const size_t o = (size_t)c * kPosRows + r;   // c == h*128+d
+    const float v = P[(size_t)r * kDModel + c];
+    if (is_f32) ((float*)out)[o] = v; else ((__nv_bfloat16*)out)[o] = __float2bfloat16_rn(v);
+  }
+}
+__global__ void fill_import_rows_kernel(int* row_entry, int* row_pos, int n_rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows) return;
+  row_entry[i] = i / kCacheS;
+  row_pos[i] = (i % kCacheS) - kCacheS;   // logical cache position j -> ring index head + 256 + (j - 256)
+}
+
+bool is_special_piece(const std::string& s) {
+  if (s == "<blank>" || s == "<pad>" || s == "<unk>") return true;
+  return !s.empty() && s.front() == '<' && s.back() == '>';
+}
+bool starts_with_sp_marker(const std::string& s) {
+  return s.size() >= 3 && (unsigned char)s[0] == 0xE2 && (unsigned char)s[1] == 0x96 && (unsigned char)s[2] == 0x81;
+}
+// punctuation-only piece (semantics of /root/reference/cpp/src/tokenizer.cpp:59-84)
+bool piece_is_punct_only(const std::string& s) {
+  if (is_special_piece(s)) return false;
+  size_t i = starts_with_sp_marker(s) ? 3 : 0;
+  if (i >= s.size()) return false;
+  bool non_space = false;
+  for (; i < s.size(); ++i) {
+    const unsigned char c = (unsigned char)s[i];
+    if (isalnum(c)) return false;
+    if (!isspace(c)) non_space = true;
+  }
+  return non_space;
+}
+
+}  // namespace
+
+// ================================================================================================
+struct Engine::Stream {
+  bool open = false;
+  int slot = 0;
+  long long frames_written = 0;          // frames ever written to the feature ring
+  std::deque<Entry> pending;             // explicit chunks (legacy ABI granularity)
+  bool audio_mode = false;
+  std::vector<float> audio;              // samples not yet turned into frames
+  long long sched_chunk = 0;             // index of the next scheduled chunk (audio mode)
+  bool has_norm = false;
+  int cache_len = 0;
+  int head = 0;
+  long long chunks = 0;
+  std::vector<int> tokens;
+  ChunkResult last;
+};
+
+struct Engine::Impl {
+  Frontend frontend;
+  // weights
+  SubsampleWeights sub{};
+  GemmW sub_pw1, sub_pw2, sub_out;
+  float *sub_pw1_b = nullptr, *sub_pw2_b = nullptr, *sub_out_b = nullptr;
+  std::vector<LayerW> layers;
+  GemmW joint_enc, joint_pred, joint_out, lstm[2];
+  float *joint_enc_b = nullptr, *joint_pred_b = nullptr, *joint_out_b = nullptr, *lstm_b[2] = {nullptr, nullptr};
+  __nv_bfloat16* embed = nullptr;
+  unsigned* punct_bits = nullptr;
+  // per-slot state
+  void *kring = nullptr, *vring = nullptr, *acache = nullptr;
+  size_t ring_layer_elems = 0;           // elements per layer in each ring (slots * 288 * 1024)
+  float* cache_tm = nullptr;             // [slots][L][1024][4]
+  float* feat_ring = nullptr;            // [slots][kFeatRing][128]
+  float* norm_stats = nullptr;           // [slots][2][128]
+  float *pred_h = nullptr, *pred_c = nullptr, *pred_g = nullptr, *pred_proj = nullptr;
+  int *n_emitted = nullptr, *y_id = nullptr;
+  // work buffers
+  int Mcap = 0, Bcap = 0, T3cap = 0, T2cap = 0;
+  ActBuf a_sub1, a_sub2, a_sub3, a_ln, a_ff, a_hid, a_pred, a_g, a_imp, a_pos;
+  float *x = nullptr, *q = nullptr, *cglu = nullptr, *y1 = nullptr, *enc_proj = nullptr, *logits = nullptr, *gates = nullptr,
+        *enc_out = nullptr, *ppos_tmp = nullptr, *scratch_f32 = nullptr;
+  size_t scratch_f32_elems = 0;
+  int* batch_ints = nullptr;             // device: entry arrays + prefixes
+  int* batch_ints_host = nullptr;        // pinned
+  int *row_entry = nullptr, *row_pos = nullptr, *rowmap3 = nullptr;
+  int *imp_row_entry = nullptr, *imp_row_pos = nullptr;
+  // decode buffers
+  int *t_cur = nullptr, *n_sym = nullptr, *active = nullptr, *emit_tok = nullptr, *pred_rowmap = nullptr, *n_steps = nullptr,
+      *steps = nullptr, *counters = nullptr, *force_toks = nullptr;
+  int* res_host = nullptr;               // pinned: [Bcap] n_steps + [Bcap*32*3] steps
+  int* counters_host = nullptr;          // pinned [2]
+  // frontend staging
+  float* audio_dev = nullptr;
+  float* audio_host = nullptr;           // pinned
+  size_t audio_cap = 0;
+  FrontSegment* segs_dev = nullptr;
+  FrontSegment* segs_host = nullptr;
+  int* fprefix_dev = nullptr;
+  int* fprefix_host = nullptr;
+  float* feat_stage_dev = nullptr;       // [128*256] legacy push staging
+  float* feat_stage_host = nullptr;
+};
+
+constexpr int kFeatRing = 512;           // frames kept per stream (5.12 s)
+constexpr int kFramesPerPass = 64;       // frontend frames per stream per step (bounds the pinned audio staging)
+constexpr int kNumBatchFields = 11;
+
+// ================================================================================================
+Engine::Engine(const EngineOptions& opt) : opt_(opt) {
+  PKB_CHECK(opt_.max_streams >= 1, "max_streams must be >= 1");
+  PKB_CUDA(cudaSetDevice(opt_.device_id));
+  cudaDeviceProp prop;
+  PKB_CUDA(cudaGetDeviceProperties(&prop, opt_.device_id));
+  sm_count_ = prop.multiProcessorCount;
+  PKB_CHECK(prop.major == 10, "this library is built for sm_100a (B200) only; found compute capability " +
+                                  std::to_string(prop.major) + "." + std::to_string(prop.minor));
+  PKB_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+  im_.reset(new Impl());
+  // vocab
+  {
+    std::ifstream f(opt_.model_dir + "/vocab.txt");
+    PKB_CHECK((bool)f, "cannot open " + opt_.model_dir + "/vocab.txt");
+    std::string line;
+    while (std::getline(f, line)) {
+      if (!line.empty() && line.back() == '\r') line.pop_back();
+      vocab_.push_back(line);
+    }
+    PKB_CHECK(!vocab_.empty() && (int)vocab_.size() <= kVocab, "vocab.txt must have 1..8193 lines");
+    punct_bits_.assign((kVocab + 31) / 32, 0u);
+    for (size_t i = 0; i < vocab_.size(); ++i) {
+      if (vocab_[i] == "<|startoftranscript|>") tok_start_ = (int)i;
+      if (vocab_[i] == "<|en|>") tok_lang_ = (int)i;
+      if (piece_is_punct_only(vocab_[i])) punct_bits_[i >> 5] |= 1u << (i & 31);
+    }
+  }
+  load_weights();
+  alloc_state();
+  streams_.resize(opt_.max_streams);
+  for (int i = 0; i < opt_.max_streams; ++i) {
+    streams_[i].reset(new Stream());
+    streams_[i]->slot = i;
+  }
+  PKB_CUDA(cudaStreamSynchronize(st_));
+}
+
+Engine::~Engine() {
+  // process teardown frees device memory; explicit frees are skipped on purpose (one engine per process lifetime
+  // in every caller), but the stream is destroyed so that a leaked engine does not keep work queued.
+  if (st_) {
+    cudaStreamSynchronize(st_);
+    cudaStreamDestroy(st_);
+  }
+}
+
+void Engine::synchronize() { PKB_CUDA(cudaStreamSynchronize(st_)); }
+
+// ------------------------------------------------------------------------------------------------ weights
+static GemmW upload_gemm_w(const std::vector<uint16_t>& bits, int N, int K) {
+  GemmW g;
+  g.N = N;
+  g.K = K;
+  PKB_CHECK((size_t)N * K == bits.size(), "weight shape mismatch");
+  // pad rows to a multiple of 128 so that every 128-row TMA box lies inside the allocation
+  const size_t rows_pad = ((size_t)N + 127) / 128 * 128;
+  g.w = dev_alloc<__nv_bfloat16>(rows_pad * K);
+  PKB_CUDA(cudaMemset(g.w, 0, rows_pad * K * 2));
+  PKB_CUDA(cudaMemcpy(g.w, bits.data(), bits.size() * 2, cudaMemcpyHostToDevice));
+  make_tensor_map_2d(&g.map, g.w, rows_pad, K, K, 128);
+  return g;
+}
+
+static ActBuf make_act(int rows_cap, int K, bool split) {
+  ActBuf a;
+  a.rows_cap = (rows_cap + 127) / 128 * 128;
+  a.K = K;
+  const size_t plane = (size_t)a.rows_cap * K;
+  a.ptr = dev_alloc<__nv_bfloat16>(plane * (split ? 2 : 1));
+  PKB_CUDA(cudaMemset(a.ptr, 0, plane * (split ? 2 : 1) * 2));
+  a.lo_off = split ? (long long)plane : 0;
+  make_tensor_map_2d(&a.map, a.ptr, (uint64_t)a.rows_cap * (split ? 2 : 1), K, K, 128);
+  return a;
+}
+
+void Engine::load_weights() {
+  WeightsFile wf(opt_.model_dir + "/weights.bin");
+  L_ = (int)wf.cfg("n_layers");
+  PKB_CHECK(wf.cfg("d_model") == kDModel && wf.cfg("n_heads") == kHeads && wf.cfg("ff_dim") == kFF &&
+                wf.cfg("conv_kernel") == kConvK && wf.cfg("sub_channels") == kSubCh && wf.cfg("feat_in") == kNMels &&
+                wf.cfg("vocab") == kVocab && wf.cfg("n_dur") == kNDur && wf.cfg("pred_hidden") == kPredH &&
+                wf.cfg("pred_layers") == kPredL && wf.cfg("joint_hidden") == kJointH && wf.cfg("cache_size") == kCacheS &&
+                wf.cfg("time_ctx") == kTimeCtx && wf.cfg("cache_drop") == kCacheDrop && wf.cfg("valid_out_len") == kValidOut &&
+                wf.cfg("drop_extra_pre_encoded") == kDropPre,
+            "weights.bin architecture constants do not match this build (Parakeet-TDT-0.6B-v3 shapes are compiled in)");
+  Impl& im = *im_;
+  const std::string pe = "encoder.pre_encode.";
+  im.sub.w0 = dev_upload(wf.f32(pe + "conv.0.weight"));
+  im.sub.b0 = dev_upload(wf.f32(pe + "conv.0.bias"));
+  im.sub.w2 = dev_upload(wf.f32(pe + "conv.2.weight"));
+  im.sub.b2 = dev_upload(wf.f32(pe + "conv.2.bias"));
+  im.sub.w5 = dev_upload(wf.f32(pe + "conv.5.weight"));
+  im.sub.b5 = dev_upload(wf.f32(pe + "conv.5.bias"));
+  im.sub_pw1 = upload_gemm_w(wf.bf16(pe + "conv.3.weight"), kSubCh, kSubCh);
+  im.sub_pw1_b = dev_upload(wf.f32(pe + "conv.3.bias"));
+  im.sub_pw2 = upload_gemm_w(wf.bf16(pe + "conv.6.weight"), kSubCh, kSubCh);
+  im.sub_pw2_b = dev_upload(wf.f32(pe + "conv.6.bias"));
+  {
+    // Linear(4096 -> 1024): NeMo flattens [C=256, F=16] channel-major (c*16+f); our operand rows are (f*256+c)
+    std::vector<uint16_t> w = wf.bf16(pe + "out.weight"), p(w.size());
+    for (int n = 0; n < kDModel; ++n)
+      for (int c = 0; c < kSubCh; ++c)
+        for (int f = 0; f < 16; ++f) p[(size_t)n * 4096 + f * kSubCh + c] = w[(size_t)n * 4096 + c * 16 + f];
+    im.sub_out = upload_gemm_w(p, kDModel, 4096);
+    im.sub_out_b = dev_upload(wf.f32(pe + "out.bias"));
+  }
+  im.layers.resize(L_);
+  for (int l = 0; l < L_; ++l) {
+    const std::string p = "encoder.layers." + std::to_string(l) + ".";
+    LayerW& w = im.layers[l];
+    w.n_ff1_g = dev_upload(wf.f32(p + "norm_feed_forward1.weight")); w.n_ff1_b = dev_upload(wf.f32(p + "norm_feed_forward1.bias"));
+    w.n_att_g = dev_upload(wf.f32(p + "norm_self_att.weight"));      w.n_att_b = dev_upload(wf.f32(p + "norm_self_att.bias"));
+    w.n_conv_g = dev_upload(wf.f32(p + "norm_conv.weight"));         w.n_conv_b = dev_upload(wf.f32(p + "norm_conv.bias"));
+    w.n_ff2_g = dev_upload(wf.f32(p + "norm_feed_forward2.weight")); w.n_ff2_b = dev_upload(wf.f32(p + "norm_feed_forward2.bias"));
+    w.n_out_g = dev_upload(wf.f32(p + "norm_out.weight"));           w.n_out_b = dev_upload(wf.f32(p + "norm_out.bias"));
+    w.ff1_1 = upload_gemm_w(wf.bf16(p + "feed_forward1.linear1.weight"), kFF, kDModel);
+    w.ff1_2 = upload_gemm_w(wf.bf16(p + "feed_forward1.linear2.weight"), kDModel, kFF);
+    w.ff2_1 = upload_gemm_w(wf.bf16(p + "feed_forward2.linear1.weight"), kFF, kDModel);
+    w.ff2_2 = upload_gemm_w(wf.bf16(p + "feed_forward2.linear2.weight"), kDModel, kFF);
+    {
+      std::vector<uint16_t> qkv = wf.bf16(p + "self_attn.linear_q.weight");
+      std::vector<uint16_t> k = wf.bf16(p + "self_attn.linear_k.weight"), v = wf.bf16(p + "self_attn.linear_v.weight");
+      qkv.insert(qkv.end(), k.begin(), k.end());
+      qkv.insert(qkv.end(), v.begin(), v.end());
+      w.qkv = upload_gemm_w(qkv, 3 * kDModel, kDModel);
+      w.kv.w = w.qkv.w + (size_t)kDModel * kDModel;   // rows [1024,3072): re-projection of imported caches
+      w.kv.N = 2 * kDModel;
+      w.kv.K = kDModel;
+      make_tensor_map_2d(&w.kv.map, w.kv.w, 2 * kDModel, kDModel, kDModel, 128);
+    }
+    w.out = upload_gemm_w(wf.bf16(p + "self_attn.linear_out.weight"), kDModel, kDModel);
+    {
+      // pointwise_conv1 [2048,1024,1]: interleave (value j, gate j) rows so the GLU pairs adjacent accumulator columns
+      std::vector<uint16_t> s = wf.bf16(p + "conv.pointwise_conv1.weight"), d(s.size());
+      for (int j = 0; j < kDModel; ++j) {
+        memcpy(&d[(size_t)(2 * j) * kDModel], &s[(size_t)j * kDModel], kDModel * 2);
+        memcpy(&d[(size_t)(2 * j + 1) * kDModel], &s[(size_t)(j + kDModel) * kDModel], kDModel * 2);
+      }
+      w.pw1 = upload_gemm_w(d, 2 * kDModel, kDModel);
+    }
+    w.pw2 = upload_gemm_w(wf.bf16(p + "conv.pointwise_conv2.weight"), kDModel, kDModel);
+    {
+      // fold eval-mode BatchNorm1d into the depthwise kernel: y = dw*s + (beta - mean*s), s = gamma/sqrt(var+eps)
+      std::vector<float> dw = wf.f32(p + "conv.depthwise_conv.weight"), g = wf.f32(p + "conv.batch_norm.weight"),
+                         b = wf.f32(p + "conv.batch_norm.bias"), mu = wf.f32(p + "conv.batch_norm.running_mean"),
+                         var = wf.f32(p + "conv.batch_norm.running_var");
+      std::vector<float> off(kDModel);
+      for (int c = 0; c < kDModel; ++c) {
+        const float s = g[c] / sqrtf(var[c] + 1e-5f);
+        for (int k = 0; k < kConvK; ++k) dw[(size_t)c * kConvK + k] *= s;
+        off[c] = b[c] - mu[c] * s;
+      }
+      w.dw_w = dev_upload(dw);
+      w.dw_b = dev_upload(off);
+    }
+    w.bias_u = dev_upload(wf.f32(p + "self_attn.pos_bias_u"));
+    w.bias_v = dev_upload(wf.f32(p + "self_attn.pos_bias_v"));
+    w.ppos_t = nullptr;   // filled in alloc_state (needs work buffers)
+  }
+  // predictor
+  {
+    std::vector<uint16_t> emb = wf.bf16("decoder.prediction.embed.weight");
+    PKB_CHECK(emb.size() == (size_t)kVocab * kPredH, "embedding shape");
+    im.embed = reinterpret_cast<__nv_bfloat16*>(dev_upload(emb));
+    for (int l = 0; l < kPredL; ++l) {
+      const std::string p = "decoder.prediction.dec_rnn.lstm.";
+      std::vector<uint16_t> ih = wf.bf16(p + "weight_ih_l" + std::to_string(l)), hh = wf.bf16(p + "weight_hh_l" + std::to_string(l));
+      std::vector<uint16_t> cat((size_t)4 * kPredH * 2 * kPredH);
+      for (int n = 0; n < 4 * kPredH; ++n) {
+        memcpy(&cat[(size_t)n * 2 * kPredH], &ih[(size_t)n * kPredH], kPredH * 2);
+        memcpy(&cat[(size_t)n * 2 * kPredH + kPredH], &hh[(size_t)n * kPredH], kPredH * 2);
+      }
+      im.lstm[l] = upload_gemm_w(cat, 4 * kPredH, 2 * kPredH);
+      std::vector<float> bi = wf.f32(p + "bias_ih_l" + std::to_string(l)), bh = wf.f32(p + "bias_hh_l" + std::to_string(l));
+      for (size_t i = 0; i < bi.size(); ++i) bi[i] += bh[i];
+      im.lstm_b[l] = dev_upload(bi);
+    }
+  }
+  im.joint_enc = upload_gemm_w(wf.bf16("joint.enc.weight"), kJointH, kDModel);
+  im.joint_enc_b = dev_upload(wf.f32("joint.enc.bias"));
+  im.joint_pred = upload_gemm_w(wf.bf16("joint.pred.weight"), kJointH, kPredH);
+  im.joint_pred_b = dev_upload(wf.f32("joint.pred.bias"));
+  im.joint_out = upload_gemm_w(wf.bf16("joint.joint_net.2.weight"), kJointOut, kJointH);
+  im.joint_out_b = dev_upload(wf.f32("joint.joint_net.2.bias"));
+  im.punct_bits = dev_upload(punct_bits_);
+  // keep the (host) linear_pos weights for alloc_state via a second open: cheap, mmap
+}
+
+// ------------------------------------------------------------------------------------------------ state / buffers
+void Engine::alloc_state() {
+  Impl& im = *im_;
+  const bool split = opt_.precision == 1;
+  const size_t S = (size_t)opt_.max_streams;
+  const size_t kv_elem = split ? 4 : 2;
+  im.ring_layer_elems = S * kRingCap * kDModel;
+  PKB_CUDA(cudaMalloc(&im.kring, im.ring_layer_elems * L_ * kv_elem));
+  PKB_CUDA(cudaMalloc(&im.vring, im.ring_layer_elems * L_ * kv_elem));
+  PKB_CUDA(cudaMemsetAsync(im.kring, 0, im.ring_layer_elems * L_ * kv_elem, st_));
+  PKB_CUDA(cudaMemsetAsync(im.vring, 0, im.ring_layer_elems * L_ * kv_elem, st_));
+  if (opt_.contract_cache) {
+    PKB_CUDA(cudaMalloc(&im.acache, im.ring_layer_elems * L_ * kv_elem));
+    PKB_CUDA(cudaMemsetAsync(im.acache, 0, im.ring_layer_elems * L_ * kv_elem, st_));
+  }
+  im.cache_tm = dev_alloc<float>(S * L_ * kDModel * kTimeCtx);
+  im.feat_ring = dev_alloc<float>(S * kFeatRing * kNMels);
+  im.norm_stats = dev_alloc<float>(S * 2 * kNMels);
+  im.pred_h = dev_alloc<float>(S * kPredL * kPredH);
+  im.pred_c = dev_alloc<float>(S * kPredL * kPredH);
+  im.pred_g = dev_alloc<float>(S * kPredH);
+  im.pred_proj = dev_alloc<float>(S * kJointH);
+  im.n_emitted = dev_alloc<int>(S);
+  im.y_id = dev_alloc<int>(S);
+  PKB_CUDA(cudaMemsetAsync(im.cache_tm, 0, S * L_ * kDModel * kTimeCtx * 4, st_));
+  PKB_CUDA(cudaMemsetAsync(im.pred_h, 0, S * kPredL * kPredH * 4, st_));
+  PKB_CUDA(cudaMemsetAsync(im.pred_c, 0, S * kPredL * kPredH * 4, st_));
+  PKB_CUDA(cudaMemsetAsync(im.pred_g, 0, S * kPredH * 4, st_));
+  PKB_CUDA(cudaMemsetAsync(im.pred_proj, 0, S * kJointH * 4, st_));
+  PKB_CUDA(cudaMemsetAsync(im.n_emitted, 0, S * 4, st_));
+  PKB_CUDA(cudaMemsetAsync(im.y_id, 0, S * 4, st_));
+
+  im.Bcap = opt_.max_streams;
+  im.Mcap = opt_.max_rows > 0 ? opt_.max_rows : std::max(64, 8 * opt_.max_streams);
+  im.Mcap = std::max(im.Mcap, kMaxTq + 2);
+  im.T3cap = im.Mcap + kDropPre * im.Bcap;
+  im.T2cap = 2 * im.T3cap + im.Bcap;
+  const int rows_dec = std::max(im.Bcap, 64);
+  im.a_sub1 = make_act(im.T2cap * 32, kSubCh, split);
+  im.a_sub2 = make_act(im.T3cap * 16, kSubCh, split);
+  im.a_sub3 = make_act(im.T3cap, 16 * kSubCh, split);
+  im.a_ln = make_act(std::max(im.Mcap, rows_dec), kDModel, split);
+  im.a_ff = make_act(im.Mcap, kFF, split);
+  im.a_hid = make_act(rows_dec, kJointH, split);
+  im.a_pred = make_act(rows_dec, 2 * kPredH, split);
+  im.a_g = make_act(rows_dec, kPredH, split);
+  im.a_imp = make_act(kCacheS, kDModel, split);
+  im.a_pos = make_act(kPosRows, kDModel, true);
+  im.x = dev_alloc<float>((size_t)im.Mcap * kDModel);
+  im.q = dev_alloc<float>((size_t)im.Mcap * kDModel);
+  im.cglu = dev_alloc<float>((size_t)im.Mcap * kDModel);
+  im.y1 = dev_alloc<float>((size_t)im.T2cap * 32 * kSubCh);
+  im.enc_proj = dev_alloc<float>((size_t)std::max(im.Mcap, rows_dec) * kJointH);
+  im.logits = dev_alloc<float>((size_t)rows_dec * kJointOut);
+  im.gates = dev_alloc<float>((size_t)rows_dec * 4 * kPredH);
+  im.enc_out = dev_alloc<float>((size_t)im.Bcap * kDModel * kValidOut);
+  im.ppos_tmp = dev_alloc<float>((size_t)kPosRows * kDModel);
+  im.scratch_f32_elems = (size_t)L_ * kCacheS * kDModel;     // one stream's contract cache (import / export staging)
+  im.scratch_f32 = dev_alloc<float>(im.scratch_f32_elems);
+  const size_t nints = (size_t)kNumBatchFields * im.Bcap + 3 * (im.Bcap + 1);
+  im.batch_ints = dev_alloc<int>(nints);
+  PKB_CUDA(cudaMallocHost(&im.batch_ints_host, nints * sizeof(int)));
+  im.row_entry = dev_alloc<int>(im.Mcap);
+  im.row_pos = dev_alloc<int>(im.Mcap);
+  im.rowmap3 = dev_alloc<int>(im.T3cap);
+  im.imp_row_entry = dev_alloc<int>(kCacheS);
+  im.imp_row_pos = dev_alloc<int>(kCacheS);
+  fill_import_rows_kernel<<<1, kCacheS, 0, st_>>>(im.imp_row_entry, im.imp_row_pos, kCacheS);
+  im.t_cur = dev_alloc<int>(im.Bcap); im.n_sym = dev_alloc<int>(im.Bcap); im.active = dev_alloc<int>(im.Bcap);
+  im.emit_tok = dev_alloc<int>(im.Bcap); im.pred_rowmap = dev_alloc<int>(im.Bcap);
+  im.n_steps = dev_alloc<int>((size_t)im.Bcap * (1 + kMaxStepsPerChunk * 3));
+  im.steps = im.n_steps + im.Bcap;
+  im.counters = dev_alloc<int>(2);
+  im.force_toks = dev_alloc<int>(im.Bcap);
+  PKB_CUDA(cudaMallocHost(&im.res_host, (size_t)im.Bcap * (1 + kMaxStepsPerChunk * 3) * sizeof(int)));
+  PKB_CUDA(cudaMallocHost(&im.counters_host, 2 * sizeof(int)));
+  // frontend staging: up to kFeatRing frames of audio per stream per pass
+  im.audio_cap = (size_t)im.Bcap * (kFramesPerPass * 160 + 400 + 2) + 1024;
+  im.audio_dev = dev_alloc<float>(im.audio_cap);
+  PKB_CUDA(cudaMallocHost(&im.audio_host, im.audio_cap * sizeof(float)));
+  im.segs_dev = dev_alloc<FrontSegment>(im.Bcap);
+  PKB_CUDA(cudaMallocHost(&im.segs_host, (size_t)im.Bcap * sizeof(FrontSegment)));
+  im.fprefix_dev = dev_alloc<int>(im.Bcap + 1);
+  PKB_CUDA(cudaMallocHost(&im.fprefix_host, (size_t)(im.Bcap + 1) * sizeof(int)));
+  im.feat_stage_dev = dev_alloc<float>((size_t)kNMels * 256);
+  PKB_CUDA(cudaMallocHost(&im.feat_stage_host, (size_t)kNMels * 256 * sizeof(float)));
+
+  // ---- projected relative-position table per layer:  P_l[r] = linear_pos_l(pe[r]),  r in [-kPosNeg, kPosRows-kPosNeg)
+  // pe[r][2i] = sin(r * div_i), pe[r][2i+1] = cos(r * div_i), div_i = exp(-(ln 1e4) * 2i / d_model)   (NeMo RelPositionalEncoding)
+  {
+    std::vector<float> pe((size_t)kPosRows * kDModel);
+    for (int idx = 0; idx < kPosRows; ++idx) {
+      const float r = (float)(idx - kPosNeg);
+      for (int i = 0; i < kDModel / 2; ++i) {
+        const float div = expf((float)(2 * i) * -(logf(10000.0f) / (float)kDModel));
+        pe[(size_t)idx * kDModel + 2 * i] = sinf(r * div);
+        pe[(size_t)idx * kDModel + 2 * i + 1] = cosf(r * div);
+      }
+    }
+    float* pe_dev = dev_upload(pe);
+    const long long n = (long long)kPosRows * kDModel;
+    f32_to_act_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st_>>>(pe_dev, kDModel, 1, kPosRows, kDModel, im.a_pos.out());
+    WeightsFile wf(opt_.model_dir + "/weights.bin");
+    for (int l = 0; l < L_; ++l) {
+      GemmW wp = upload_gemm_w(wf.bf16("encoder.layers." + std::to_string(l) + ".self_attn.linear_pos.weight"), kDModel, kDModel);
+      GemmArgs g;
+      g.A = im.a_pos.ptr; g.lda = kDModel; g.a_lo_off = im.a_pos.lo_off;
+      g.W = wp.w; g.M = kPosRows; g.N = kDModel; g.K = kDModel;
+      g.epi.mode = EPI_F32; g.epi.out_f32 = im.ppos_tmp; g.epi.ldo = kDModel;
+      gemm_simt(g, st_);
+      PKB_CUDA(cudaMalloc(&im.layers[l].ppos_t, (size_t)kPosRows * kDModel * kv_elem));
+      ppos_transpose_kernel<<<kPosRows, 256, 0, st_>>>(im.ppos_tmp, im.layers[l].ppos_t, split ? 1 : 0);
+      PKB_CUDA(cudaStreamSynchronize(st_));
+      cudaFree(wp.w);
+    }
+    cudaFree(pe_dev);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ streams
+int Engine::open_stream() {
+  for (int i = 0; i < (int)streams_.size(); ++i)
+    if (!streams_[i]->open) {
+      streams_[i]->open = true;
+      reset_stream(i);
+      return i;
+    }
+  throw std::runtime_error("no free stream slot (max_streams=" + std::to_string(opt_.max_streams) + ")");
+}
+
+void Engine::close_stream(int sid) {
+  PKB_CHECK(sid >= 0 && sid < (int)streams_.size(), "bad stream id");
+  streams_[sid]->open = false;
+}
+
+void Engine::reset_stream(int sid) {
+  PKB_CHECK(sid >= 0 && sid < (int)streams_.size() && streams_[sid]->open, "bad stream id");
+  Stream& s = *streams_[sid];
+  Impl& im = *im_;
+  s.frames_written = 0; s.pending.clear(); s.audio.clear(); s.audio_mode = false; s.sched_chunk = 0; s.has_norm = false;
+  s.cache_len = 0; s.head = 0; s.chunks = 0; s.tokens.clear(); s.last = ChunkResult();
+  const size_t slot = (size_t)s.slot;
+  PKB_CUDA(cudaMemsetAsync(im.cache_tm + slot * L_ * kDModel * kTimeCtx, 0, (size_t)L_ * kDModel * kTimeCtx * 4, st_));
+  PKB_CUDA(cudaMemsetAsync(im.pred_h + slot * kPredL * kPredH, 0, kPredL * kPredH * 4, st_));
+  PKB_CUDA(cudaMemsetAsync(im.pred_c + slot * kPredL * kPredH, 0, kPredL * kPredH * 4, st_));
+  PKB_CUDA(cudaMemsetAsync(im.pred_g + slot * kPredH, 0, kPredH * 4, st_));
+  PKB_CUDA(cudaMemsetAsync(im.n_emitted + slot, 0, 4, st_));
+  prime_streams({sid});
+}
+
+bool Engine::has_pending(int sid) const {
+  const Stream& s = *streams_[sid];
+  return s.open && (!s.pending.empty() || !s.audio.empty());
+}
+const std::vector<int>& Engine::tokens(int sid) const { return streams_[sid]->tokens; }
+const ChunkResult& Engine::last_chunk(int sid) const { return streams_[sid]->last; }
+int Engine::cache_len(int sid) const { return streams_[sid]->cache_len; }
+long long Engine::chunks_done(int sid) const { return streams_[sid]->chunks; }
+
+std::string Engine::detokenize(const std::vector<int>& ids) const {
+  // SentencePiece-style join (semantics of /root/reference/cpp/src/tokenizer.cpp:32-57)
+  std::string out;
+  for (int id : ids) {
+    if (id < 0 || id >= (int)vocab_.size()) continue;
+    const std::string& t = vocab_[id];
+    if (is_special_piece(t)) continue;
+    if (starts_with_sp_marker(t)) {
+      if (!out.empty() && out.back() != ' ') out.push_back(' ');
+      out.append(t, 3, std::string::npos);
+    } else {
+      out.append(t);
+    }
+  }
+  size_t i = 0;
+  while (i < out.size() && out[i] == ' ') ++i;
+  return out.substr(i);
+}
+
+// ------------------------------------------------------------------------------------------------ input queues
+void Engine::queue_features(int sid, const float* feats, int T) {
+  PKB_CHECK(sid >= 0 && sid < (int)streams_.size() && streams_[sid]->open, "bad stream id");
+  PKB_CHECK(T >= 1 && T <= 256, "queue_features: 1 <= T <= 256 frames per chunk");
+  Stream& s = *streams_[sid];
+  Impl& im = *im_;
+  PKB_CHECK(!s.audio_mode, "stream is in audio mode");
+  PKB_CHECK(s.pending.empty() || s.frames_written - s.pending.front().f0 + T <= kFeatRing, "feature ring full: call step() first");
+  PKB_CUDA(cudaStreamSynchronize(st_));   // staging buffer reuse
+  memcpy(im.feat_stage_host, feats, (size_t)kNMels * T * sizeof(float));
+  PKB_CUDA(cudaMemcpyAsync(im.feat_stage_dev, im.feat_stage_host, (size_t)kNMels * T * sizeof(float), cudaMemcpyHostToDevice, st_));
+  im.frontend.bins_to_frames(im.feat_stage_dev, T, im.feat_ring + (size_t)s.slot * kFeatRing * kNMels, kFeatRing,
+                             (int)(s.frames_written % kFeatRing), st_);
+  ++launches_;
+  s.pending.push_back(Entry{sid, (int)(s.frames_written % kFeatRing), T});
+  s.frames_written += T;
+}
+
+void Engine::queue_audio(int sid, const float* pcm, size_t n) {
+  PKB_CHECK(sid >= 0 && sid < (int)streams_.size() && streams_[sid]->open, "bad stream id");
+  Stream& s = *streams_[sid];
+  PKB_CHECK(s.audio_mode || s.frames_written == 0, "stream already received features; reset it before pushing audio");
+  s.audio_mode = true;
+  s.audio.insert(s.audio.end(), pcm, pcm + n);
+}
+
+void Engine::set_feature_norm(int sid, const float* mean128, const float* std128) {
+  PKB_CHECK(sid >= 0 && sid < (int)streams_.size() && streams_[sid]->open, "bad stream id");
+  Stream& s = *streams_[sid];
+  if (!mean128 || !std128) { s.has_norm = false; return; }
+  float* dst = im_->norm_stats + (size_t)s.slot * 2 * kNMels;
+  PKB_CUDA(cudaMemcpy(dst, mean128, kNMels * 4, cudaMemcpyHostToDevice));
+  PKB_CUDA(cudaMemcpy(dst + kNMels, std128, kNMels * 4, cudaMemcpyHostToDevice));
+  s.has_norm = true;
+}
+
+// audio -> feature rings for every stream in audio mode (one launch), then cut chunks by the schedule
+void Engine::frontend_pass() {
+  Impl& im = *im_;
+  int n_segs = 0, total_frames = 0;
+  size_t apos = 0;
+  std::vector<std::pair<int, int>> done;   // (sid, frames)
+  for (int sid = 0; sid < (int)streams_.size(); ++sid) {
+    Stream& s = *streams_[sid];
+    if (!s.open || !s.audio_mode || s.audio.size() < 400) continue;
+    int frames = (int)((s.audio.size() - 400) / 160 + 1);
+    // do not overrun the ring: frames not yet consumed by the schedule must stay resident
+    const long long next_start = s.sched_chunk == 0 ? 0 : 17 + 24 * (s.sched_chunk - 1);
+    const long long keep_from = std::max(0LL, next_start - 9);
+    const long long room = kFeatRing - (s.frames_written - keep_from);
+    if (room <= 0) continue;
+    frames = (int)std::min<long long>(std::min(frames, kFramesPerPass), room);
+    const size_t nsamp = (size_t)(frames - 1) * 160 + 400;
+    if (apos & 1) ++apos;
+    PKB_CHECK(apos + nsamp <= im.audio_cap, "audio staging overflow");
+    memcpy(im.audio_host + apos, s.audio.data(), nsamp * sizeof(float));
+    FrontSegment& sg = im.segs_host[n_segs];
+    sg.audio_off = (long long)apos;
+    sg.out_off = (long long)s.slot * kFeatRing * kNMels;
+    sg.out_stride = kNMels;
+    sg.ring_cap = kFeatRing;
+    sg.frame0 = (int)(s.frames_written % kFeatRing);
+    sg.norm_off = s.has_norm ? s.slot * 2 * kNMels : -1;
+    im.fprefix_host[n_segs] = total_frames;
+    total_frames += frames;
+    apos += nsamp;
+    ++n_segs;
+    done.emplace_back(sid, frames);
+  }
+  if (n_segs == 0) return;
+  im.fprefix_host[n_segs] = total_frames;
+  PKB_CUDA(cudaMemcpyAsync(im.audio_dev, im.audio_host, apos * sizeof(float), cudaMemcpyHostToDevice, st_));
+  PKB_CUDA(cudaMemcpyAsync(im.segs_dev, im.segs_host, n_segs * sizeof(FrontSegment), cudaMemcpyHostToDevice, st_));
+  PKB_CUDA(cudaMemcpyAsync(im.fprefix_dev, im.fprefix_host, (n_segs + 1) * sizeof(int), cudaMemcpyHostToDevice, st_));
+  im.frontend.logmel(im.audio_dev, im.segs_dev, im.fprefix_dev, n_segs, total_frames, im.feat_ring, im.norm_stats, sm_count_, st_);
+  ++launches_;
+  PKB_CUDA(cudaStreamSynchronize(st_));    // staging is reused by the next pass
+  for (auto& d : done) {
+    Stream& s = *streams_[d.first];
+    s.audio.erase(s.audio.begin(), s.audio.begin() + (size_t)d.second * 160);
+    s.frames_written += d.second;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ batching
+BatchDev Engine::upload_batch(const std::vector<Entry>& entries) {
+  Impl& im = *im_;
+  const int B = (int)entries.size();
+  PKB_CHECK(B <= im.Bcap, "batch larger than max_streams");
+  int* h = im.batch_ints_host;
+  const int C = im.Bcap;
+  int *slot = h, *T = h + C, *f0 = h + 2 * C, *T1 = h + 3 * C, *T2 = h + 4 * C, *T3 = h + 5 * C, *Tq = h + 6 * C, *qlen = h + 7 * C,
+      *len = h + 8 * C, *head = h + 9 * C, *tenc = h + 10 * C;
+  int* off2 = h + kNumBatchFields * C;
+  int* off3 = off2 + (C + 1);
+  int* roff = off3 + (C + 1);
+  BatchDev b;
+  b.B = B;
+  off2[0] = off3[0] = roff[0] = 0;
+  for (int i = 0; i < B; ++i) {
+    const Stream& s = *streams_[entries[i].sid];
+    slot[i] = s.slot;
+    T[i] = entries[i].T;
+    f0[i] = entries[i].f0;
+    T1[i] = sub_len(T[i]);
+    T2[i] = sub_len(T1[i]);
+    T3[i] = sub_len(T2[i]);
+    Tq[i] = T3[i] - kDropPre;
+    PKB_CHECK(Tq[i] >= kCacheDrop && Tq[i] <= kMaxTq, "chunk must hold 33..256 feature frames (got " + std::to_string(T[i]) + ")");
+    qlen[i] = Tq[i];
+    len[i] = s.cache_len;
+    head[i] = s.head;
+    tenc[i] = std::min(qlen[i], kValidOut);
+    off2[i + 1] = off2[i] + T2[i];
+    off3[i + 1] = off3[i] + T3[i];
+    roff[i + 1] = roff[i] + Tq[i];
+    b.max_Tq = std::max(b.max_Tq, Tq[i]);
+  }
+  b.M = roff[B]; b.sumT2 = off2[B]; b.sumT3 = off3[B];
+  PKB_CHECK(b.M <= im.Mcap && b.sumT3 <= im.T3cap && b.sumT2 <= im.T2cap, "batch exceeds row capacity");
+  const size_t nints = (size_t)kNumBatchFields * C + 3 * (C + 1);
+  PKB_CUDA(cudaMemcpyAsync(im.batch_ints, h, nints * sizeof(int), cudaMemcpyHostToDevice, st_));
+  int* d = im.batch_ints;
+  b.slot = d; b.T = d + C; b.f0 = d + 2 * C; b.T1 = d + 3 * C; b.T2 = d + 4 * C; b.T3 = d + 5 * C; b.Tq = d + 6 * C;
+  b.qlen = d + 7 * C; b.len = d + 8 * C; b.head = d + 9 * C;
+  b.off2 = d + kNumBatchFields * C; b.off3 = b.off2 + (C + 1); b.row_off = b.off3 + (C + 1);
+  b.row_entry = im.row_entry; b.row_pos = im.row_pos; b.rowmap3 = im.rowmap3;
+  return b;
+}
+
+// GEMM on an activation buffer and a weight, choosing the backend
+static void run_gemm(Engine* eng, const EngineOptions& opt, cudaStream_t st, long long* launches, const ActBuf& a, int lda_override,
+                     const GemmW& w, int M, const int* M_dev, const EpiParams& epi) {
+  (void)eng;
+  GemmArgs g;
+  g.A = a.ptr;
+  g.lda = lda_override > 0 ? lda_override : a.K;
+  g.a_lo_off = a.lo_off;
+  g.W = w.w;
+  g.M = M; g.N = w.N; g.K = w.K;
+  g.M_dev = M_dev;
+  g.epi = epi;
+  ++*launches;
+  const bool want_tc = opt.gemm_backend == 2 || (opt.gemm_backend == 0 && M > 16);
+  if (want_tc && lda_override <= 0 && gemm_tc_supported(g)) gemm_tc(g, a.map, w.map, st);
+  else gemm_simt(g, st);
+}
+#define RUN_GEMM(a, w, M, Mdev, epi) run_gemm(this, opt_, st_, &launches_, a, 0, w, M, Mdev, epi)
+
+void Engine::run_encoder(const BatchDev& b) {
+  Impl& im = *im_;
+  const bool split = opt_.precision == 1;
+  launch_build_rows(b, st_); ++launches_;
+  // ---- pre-encode ----
+  launch_subsample_stage1(b, im.feat_ring, kFeatRing, im.sub, im.a_sub1.out(), st_); ++launches_;
+  { EpiParams e; e.mode = EPI_BIAS_RELU_F32; e.out_f32 = im.y1; e.ldo = kSubCh; e.bias = im.sub_pw1_b;
+    RUN_GEMM(im.a_sub1, im.sub_pw1, b.sumT2 * 32, nullptr, e); }
+  launch_subsample_stage2(b, im.y1, im.sub, im.a_sub2.out(), st_); ++launches_;
+  { EpiParams e; e.mode = EPI_BIAS_RELU_ACT; e.out_act = im.a_sub3.ptr; e.lda_out = kSubCh; e.lo_off_out = im.a_sub3.lo_off;
+    e.bias = im.sub_pw2_b;
+    RUN_GEMM(im.a_sub2, im.sub_pw2, b.sumT3 * 16, nullptr, e); }
+  { EpiParams e; e.mode = EPI_BIAS_ROWMAP_F32; e.out_f32 = im.x; e.ldo = kDModel; e.bias = im.sub_out_b; e.row_map = b.rowmap3;
+    RUN_GEMM(im.a_sub3, im.sub_out, b.sumT3, nullptr, e); }
+  // ---- conformer layers ----
+  const int M = b.M;
+  launch_layernorm(im.x, M, im.layers[0].n_ff1_g, im.layers[0].n_ff1_b, nullptr, nullptr, 0, im.a_ln.out(), nullptr, st_); ++launches_;
+  const size_t kv_elem = split ? 4 : 2;
+  for (int l = 0; l < L_; ++l) {
+    const LayerW& w = im.layers[l];
+    char* kr = (char*)im.kring + (size_t)l * im.ring_layer_elems * kv_elem;
+    char* vr = (char*)im.vring + (size_t)l * im.ring_layer_elems * kv_elem;
+    // FFN 1 (half-step residual)
+    { EpiParams e; e.mode = EPI_SILU_ACT; e.out_act = im.a_ff.ptr; e.lda_out = kFF; e.lo_off_out = im.a_ff.lo_off;
+      RUN_GEMM(im.a_ln, w.ff1_1, M, nullptr, e); }
+    { EpiParams e; e.mode = EPI_RESADD_F32; e.out_f32 = im.x; e.ldo = kDModel; e.scale = 0.5f;
+      RUN_GEMM(im.a_ff, w.ff1_2, M, nullptr, e); }
+    // self-attention
+    AcacheOut ac{};
+    if (im.acache) {
+      ac.ring = (char*)im.acache + (size_t)l * im.ring_layer_elems * kv_elem; ac.is_f32 = split ? 1 : 0;
+      ac.row_entry = b.row_entry; ac.row_pos = b.row_pos; ac.entry_slot = b.slot; ac.entry_head = b.head;
+    }
+    launch_layernorm(im.x, M, w.n_att_g, w.n_att_b, nullptr, nullptr, 0, im.a_ln.out(), im.acache ? &ac : nullptr, st_); ++launches_;
+    { EpiParams e; e.mode = EPI_QKV; e.out_f32 = im.q; e.ldo = kDModel; e.row_entry = b.row_entry; e.row_pos = b.row_pos;
+      e.entry_slot = b.slot; e.entry_head = b.head; e.kring = kr; e.vring = vr; e.kv_f32 = split ? 1 : 0;
+      RUN_GEMM(im.a_ln, w.qkv, M, nullptr, e); }
+    { AttnArgs a; a.q = im.q; a.kring = kr; a.vring = vr; a.ppos_t = w.ppos_t; a.kv_f32 = split ? 1 : 0; a.bias_u = w.bias_u;
+      a.bias_v = w.bias_v; a.ctx = im.a_ln.out();
+      launch_attention(b, a, st_); ++launches_; }
+    { EpiParams e; e.mode = EPI_RESADD_F32; e.out_f32 = im.x; e.ldo = kDModel; e.scale = 1.0f;
+      RUN_GEMM(im.a_ln, w.out, M, nullptr, e); }
+    // convolution module
+    launch_layernorm(im.x, M, w.n_conv_g, w.n_conv_b, nullptr, nullptr, 0, im.a_ln.out(), nullptr, st_); ++launches_;
+    { EpiParams e; e.mode = EPI_GLU_F32; e.out_f32 = im.cglu; e.ldo = kDModel;
+      RUN_GEMM(im.a_ln, w.pw1, M, nullptr, e); }
+    { DwConvArgs a; a.c = im.cglu; a.cache_tm = im.cache_tm + (size_t)l * kDModel * kTimeCtx; a.slot_stride = (long long)L_ * kDModel * kTimeCtx;
+      a.w = w.dw_w; a.bias = w.dw_b; a.out = im.a_ln.out();
+      launch_dwconv(b, a, st_); ++launches_; }
+    { EpiParams e; e.mode = EPI_RESADD_F32; e.out_f32 = im.x; e.ldo = kDModel; e.scale = 1.0f;
+      RUN_GEMM(im.a_ln, w.pw2, M, nullptr, e); }
+    // FFN 2
+    launch_layernorm(im.x, M, w.n_ff2_g, w.n_ff2_b, nullptr, nullptr, 0, im.a_ln.out(), nullptr, st_); ++launches_;
+    { EpiParams e; e.mode = EPI_SILU_ACT; e.out_act = im.a_ff.ptr; e.lda_out = kFF; e.lo_off_out = im.a_ff.lo_off;
+      RUN_GEMM(im.a_ln, w.ff2_1, M, nullptr, e); }
+    { EpiParams e; e.mode = EPI_RESADD_F32; e.out_f32 = im.x; e.ldo = kDModel; e.scale = 0.5f;
+      RUN_GEMM(im.a_ff, w.ff2_2, M, nullptr, e); }
+    // norm_out (+ next layer's norm_feed_forward1; after the last layer: operand of the joint's encoder projection)
+    const bool last = l + 1 == L_;
+    launch_layernorm(im.x, M, w.n_out_g, w.n_out_b, last ? nullptr : im.layers[l + 1].n_ff1_g, last ? nullptr : im.layers[l + 1].n_ff1_b,
+                     1, im.a_ln.out(), nullptr, st_); ++launches_;
+  }
+  launch_gather_output(b, im.x, im.enc_out, st_); ++launches_;
+}
+
+void Engine::run_predictor_pass(const DecodeDev& d) {
+  Impl& im = *im_;
+  launch_pred_input(d, st_); ++launches_;
+  { EpiParams e; e.mode = EPI_BIAS_F32; e.out_f32 = im.gates; e.ldo = 4 * kPredH; e.bias = im.lstm_b[0];
+    RUN_GEMM(im.a_pred, im.lstm[0], d.B, d.m_pred, e); }
+  launch_lstm_cell(d, 0, st_); ++launches_;
+  { EpiParams e; e.mode = EPI_BIAS_F32; e.out_f32 = im.gates; e.ldo = 4 * kPredH; e.bias = im.lstm_b[1];
+    RUN_GEMM(im.a_pred, im.lstm[1], d.B, d.m_pred, e); }
+  launch_lstm_cell(d, 1, st_); ++launches_;
+  { EpiParams e; e.mode = EPI_BIAS_ROWMAP_F32; e.out_f32 = im.pred_proj; e.ldo = kJointH; e.bias = im.joint_pred_b; e.row_map = d.pred_rowmap;
+    RUN_GEMM(im.a_g, im.joint_pred, d.B, d.m_pred, e); }
+}
+
+static DecodeDev make_decode_dev(Engine::Impl& im, const EngineOptions& opt, int B, const int* slot, const int* row_off, const int* t_enc);
+
+void Engine::run_decode(const BatchDev& b, const std::vector<Entry>& entries) {
+  Impl& im = *im_;
+  (void)entries;
+  // joint encoder projection for every packed row: E = joint.enc(x) + bias
+  { EpiParams e; e.mode = EPI_BIAS_F32; e.out_f32 = im.enc_proj; e.ldo = kJointH; e.bias = im.joint_enc_b;
+    RUN_GEMM(im.a_ln, im.joint_enc, b.M, nullptr, e); }
+  DecodeDev d = make_decode_dev(im, opt_, b.B, b.slot, b.row_off, im.batch_ints + 10 * im.Bcap);
+  launch_decode_begin(d, st_); ++launches_;
+  const int max_iters = kValidOut * (kMaxSymbols + 1) + 2;
+  for (int it = 0; it < max_iters; ++it) {
+    launch_decode_iter_reset(d, st_); ++launches_;
+    launch_joint_hidden(d, st_); ++launches_;
+    { EpiParams e; e.mode = EPI_BIAS_F32; e.out_f32 = im.logits; e.ldo = kJointOut; e.bias = im.joint_out_b;
+      RUN_GEMM(im.a_hid, im.joint_out, b.B, nullptr, e); }
+    launch_tdt_select(d, st_); ++launches_;
+    PKB_CUDA(cudaMemcpyAsync(im.counters_host, im.counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, st_));
+    run_predictor_pass(d);
+    PKB_CUDA(cudaStreamSynchronize(st_));
+    if (im.counters_host[0] == 0) break;
+  }
+}
+
+static DecodeDev make_decode_dev(Engine::Impl& im, const EngineOptions& opt, int B, const int* slot, const int* row_off, const int* t_enc) {
+  DecodeDev d;
+  d.B = B; d.max_symbols = kMaxSymbols; d.punct_suppress = opt.punct_suppress; d.blank_penalty = opt.blank_penalty;
+  d.slot = slot; d.row_off = row_off; d.t_enc = t_enc;
+  d.t_cur = im.t_cur; d.n_sym = im.n_sym; d.active = im.active; d.emit_tok = im.emit_tok; d.pred_rowmap = im.pred_rowmap;
+  d.n_steps = im.n_steps; d.steps = im.steps; d.n_active = im.counters; d.m_pred = im.counters + 1;
+  d.enc_proj = im.enc_proj; d.pred_proj = im.pred_proj; d.logits = im.logits; d.gates = im.gates; d.embed = im.embed;
+  d.punct_bits = im.punct_bits; d.pred_h = im.pred_h; d.pred_c = im.pred_c; d.pred_g = im.pred_g; d.n_emitted = im.n_emitted;
+  d.y_id = im.y_id; d.act_hidden = im.a_hid.out(); d.act_pred = im.a_pred.out(); d.act_g = im.a_g.out();
+  return d;
+}
+
+// reset_utterance priming (parakeet_trt.cpp:1886-1942): predictor on <|startoftranscript|> then <|en|>; blank if neither exists
+void Engine::prime_streams(const std::vector<int>& sids) {
+  Impl& im = *im_;
+  const int B = (int)sids.size();
+  if (B == 0) return;
+  PKB_CHECK(B <= im.Bcap, "too many streams to prime");
+  PKB_CUDA(cudaStreamSynchronize(st_));
+  int* h = im.batch_ints_host;
+  for (int i = 0; i < B; ++i) h[i] = streams_[sids[i]]->slot;
+  PKB_CUDA(cudaMemcpyAsync(im.batch_ints, h, B * sizeof(int), cudaMemcpyHostToDevice, st_));
+  DecodeDev d = make_decode_dev(im, opt_, B, im.batch_ints, nullptr, nullptr);
+  std::vector<int> seq;
+  if (tok_start_ >= 0) seq.push_back(tok_start_);
+  if (tok_lang_ >= 0) seq.push_back(tok_lang_);
+  if (seq.empty()) seq.push_back(kBlank);
+  for (int tok : seq) {
+    PKB_CUDA(cudaStreamSynchronize(st_));
+    for (int i = 0; i < B; ++i) im.res_host[i] = tok;
+    PKB_CUDA(cudaMemcpyAsync(im.force_toks, im.res_host, B * sizeof(int), cudaMemcpyHostToDevice, st_));
+    launch_decode_iter_reset(d, st_); ++launches_;
+    launch_force_token(d, im.force_toks, st_); ++launches_;
+    run_predictor_pass(d);
+  }
+  // y_id = last primed token
+  std::vector<int> y(B, seq.back());
+  for (int i = 0; i < B; ++i)
+    PKB_CUDA(cudaMemcpyAsync(im.y_id + streams_[sids[i]]->slot, &y[i], sizeof(int), cudaMemcpyHostToDevice, st_));
+  PKB_CUDA(cudaStreamSynchronize(st_));
+}
+
+void Engine::run_batch(const std::vector<Entry>& entries, float* enc_out_host) {
+  Impl& im = *im_;
+  if (entries.empty()) return;
+  const BatchDev b = upload_batch(entries);
+  run_encoder(b);
+  const bool decode = enc_out_host == nullptr;
+  if (decode) {
+    run_decode(b, entries);
+    PKB_CUDA(cudaMemcpyAsync(im.res_host, im.n_steps, (size_t)im.Bcap * (1 + kMaxStepsPerChunk * 3) * sizeof(int),
+                             cudaMemcpyDeviceToHost, st_));
+  } else {
+    PKB_CUDA(cudaMemcpyAsync(enc_out_host, im.enc_out, (size_t)b.B * kDModel * kValidOut * sizeof(float), cudaMemcpyDeviceToHost, st_));
+  }
+  PKB_CUDA(cudaStreamSynchronize(st_));
+  const int* h = im.batch_ints_host;
+  const int C = im.Bcap;
+  for (int i = 0; i < b.B; ++i) {
+    Stream& s = *streams_[entries[i].sid];
+    const int Tq = h[6 * C + i];
+    const int keep = Tq - kCacheDrop;
+    s.last = ChunkResult();
+    s.last.encoded_len = h[10 * C + i];
+    if (decode) {
+      const int n = std::min(im.res_host[i], kMaxStepsPerChunk);
+      const int* st = im.res_host + C + (size_t)i * kMaxStepsPerChunk * 3;
+      for (int k = 0; k < n; ++k) {
+        s.last.steps.push_back(StepRecord{st[3 * k], st[3 * k + 1], st[3 * k + 2]});
+        if (st[3 * k + 1] != kBlank) s.tokens.push_back(st[3 * k + 1]);
+      }
+    }
+    s.cache_len = std::min(s.cache_len + keep, kCacheS);     // clamp(len + cache_keep_size, max=cache_len)
+    s.head = (s.head + keep) % kRingCap;
+    s.last.cache_len_out = s.cache_len;
+    s.chunks += 1;
+  }
+}
+
+int Engine::step() {
+  frontend_pass();
+  Impl& im = *im_;
+  int total = 0;
+  std::vector<Entry> batch;
+  int rows = 0, t3 = 0, t2 = 0;
+  auto flush = [&]() {
+    if (batch.empty()) return;
+    run_batch(batch, nullptr);
+    total += (int)batch.size();
+    batch.clear();
+    rows = t3 = t2 = 0;
+  };
+  for (int sid = 0; sid < (int)streams_.size(); ++sid) {
+    Stream& s = *streams_[sid];
+    if (!s.open) continue;
+    Entry e{sid, 0, 0};
+    bool have = false;
+    if (s.audio_mode) {
+      // streaming_encoder_reference.py:522-550: chunk 0 = [0,41); chunk k = [start-9, start+48), start = 17 + 24(k-1)
+      const long long start = s.sched_chunk == 0 ? 0 : 17 + 24 * (s.sched_chunk - 1);
+      const long long lo = s.sched_chunk == 0 ? 0 : start - 9;
+      const long long hi = start + (s.sched_chunk == 0 ? 41 : 48);
+      if (s.frames_written >= hi) {
+        e.f0 = (int)(lo % kFeatRing);
+        e.T = (int)(hi - lo);
+        have = true;
+      }
+    } else if (!s.pending.empty()) {
+      e = s.pending.front();
+      have = true;
+    }
+    if (!have) continue;
+    const int T3 = sub_len(sub_len(sub_len(e.T)));
+    const int T2 = sub_len(sub_len(e.T));
+    if (rows + T3 - kDropPre > im.Mcap || t3 + T3 > im.T3cap || t2 + T2 > im.T2cap) flush();
+    batch.push_back(e);
+    rows += T3 - kDropPre; t3 += T3; t2 += T2;
+    if (s.audio_mode) s.sched_chunk += 1; else s.pending.pop_front();
+  }
+  flush();
+  return total;
+}
+
+// ================================================================================================ tensor-level entry points
+void Engine::import_state(int sid, const float* cache_ch, long long, const float* cache_tm, int cache_len) {
+  Impl& im = *im_;
+  PKB_CHECK(im.acache != nullptr, "state import needs contract_cache=1");
+  PKB_CHECK(cache_len >= 0 && cache_len <= kCacheS, "cache_last_channel_len out of range");
+  Stream& s = *streams_[sid];
+  const bool split = opt_.precision == 1;
+  const size_t kv_elem = split ? 4 : 2;
+  s.cache_len = cache_len;
+  s.head = 0;
+  int hv[2] = {s.slot, 0};
+  int* meta = dev_alloc<int>(2);
+  PKB_CUDA(cudaMemcpyAsync(meta, hv, sizeof(hv), cudaMemcpyHostToDevice, st_));
+  PKB_CUDA(cudaMemcpyAsync(im.scratch_f32, cache_ch, im.scratch_f32_elems * 4, cudaMemcpyHostToDevice, st_));
+  PKB_CUDA(cudaMemcpyAsync(im.cache_tm + (size_t)s.slot * L_ * kDModel * kTimeCtx, cache_tm, (size_t)L_ * kDModel * kTimeCtx * 4,
+                           cudaMemcpyHostToDevice, st_));
+  for (int l = 0; l < L_; ++l) {
+    char* ac = (char*)im.acache + (size_t)l * im.ring_layer_elems * kv_elem;
+    launch_acache_import(ac, split, meta, meta + 1, 1, im.scratch_f32 + (size_t)l * kCacheS * kDModel, 0, st_); ++launches_;
+    launch_acache_to_act(ac, split, meta, meta + 1, 1, im.a_imp.out(), st_); ++launches_;
+    EpiParams e; e.mode = EPI_QKV; e.n_off = kDModel; e.row_entry = im.imp_row_entry; e.row_pos = im.imp_row_pos;
+    e.entry_slot = meta; e.entry_head = meta + 1;
+    e.kring = (char*)im.kring + (size_t)l * im.ring_layer_elems * kv_elem;
+    e.vring = (char*)im.vring + (size_t)l * im.ring_layer_elems * kv_elem;
+    e.kv_f32 = split;
+    RUN_GEMM(im.a_imp, im.layers[l].kv, kCacheS, nullptr, e);
+  }
+  PKB_CUDA(cudaStreamSynchronize(st_));
+  cudaFree(meta);
+}
+
+void Engine::export_state(int sid, float* cache_ch, float* cache_tm) {
+  Impl& im = *im_;
+  PKB_CHECK(im.acache != nullptr, "state export needs contract_cache=1");
+  Stream& s = *streams_[sid];
+  const bool split = opt_.precision == 1;
+  const size_t kv_elem = split ? 4 : 2;
+  int hv[2] = {s.slot, s.head};
+  int* meta = dev_alloc<int>(2);
+  PKB_CUDA(cudaMemcpyAsync(meta, hv, sizeof(hv), cudaMemcpyHostToDevice, st_));
+  for (int l = 0; l < L_; ++l) {
+    const char* ac = (const char*)im.acache + (size_t)l * im.ring_layer_elems * kv_elem;
+    launch_acache_export(ac, split, meta, meta + 1, 1, im.scratch_f32 + (size_t)l * kCacheS * kDModel, 0, st_); ++launches_;
+  }
+  PKB_CUDA(cudaMemcpyAsync(cache_ch, im.scratch_f32, im.scratch_f32_elems * 4, cudaMemcpyDeviceToHost, st_));
+  PKB_CUDA(cudaMemcpyAsync(cache_tm, im.cache_tm + (size_t)s.slot * L_ * kDModel * kTimeCtx, (size_t)L_ * kDModel * kTimeCtx * 4,
+                           cudaMemcpyDeviceToHost, st_));
+  PKB_CUDA(cudaStreamSynchronize(st_));
+  cudaFree(meta);
+  // rows that were never filled are zeros in the contract cache (zero-initialised FIFO)
+  const int invalid = kCacheS - s.cache_len;
+  for (int l = 0; l < L_; ++l) memset(cache_ch + (size_t)l * kCacheS * kDModel, 0, (size_t)invalid * kDModel * 4);
+}
+
+void Engine::encoder_streaming_step(int B, int T, const float* audio_signal, const int64_t* length, const float* cache_last_channel,
+                                    const float* cache_last_time, const int64_t* cache_last_channel_len, float* encoder_output,
+                                    int64_t* encoded_lengths, float* cache_last_channel_out, float* cache_last_time_out,
+                                    int64_t* cache_last_channel_len_out) {
+  PKB_CHECK(B >= 1 && B <= opt_.max_streams, "encoder_streaming_step: B exceeds max_streams");
+  const size_t ch_stride = (size_t)L_ * kCacheS * kDModel, tm_stride = (size_t)L_ * kDModel * kTimeCtx;
+  std::vector<int> sids;
+  std::vector<Entry> entries;
+  for (int i = 0; i < B; ++i) {
+    PKB_CHECK(length[i] == T, "encoder_streaming_step: length must equal T for every stream");
+    const int sid = open_stream();
+    sids.push_back(sid);
+    import_state(sid, cache_last_channel + i * ch_stride, 0, cache_last_time + i * tm_stride, (int)cache_last_channel_len[i]);
+    queue_features(sid, audio_signal + (size_t)i * kNMels * T, T);
+    entries.push_back(streams_[sid]->pending.front());
+    streams_[sid]->pending.pop_front();
+  }
+  run_batch(entries, encoder_output);
+  for (int i = 0; i < B; ++i) {
+    Stream& s = *streams_[sids[i]];
+    encoded_lengths[i] = s.last.encoded_len;
+    cache_last_channel_len_out[i] = s.cache_len;
+    export_state(sids[i], cache_last_channel_out + i * ch_stride, cache_last_time_out + i * tm_stride);
+    close_stream(sids[i]);
+  }
+}
+
+void Engine::predictor_step(int B, const int64_t* y, const float* h, const float* c, float* g, float* h_out, float* c_out) {
+  Impl& im = *im_;
+  PKB_CHECK(B >= 1 && B <= opt_.max_streams, "predictor_step: B exceeds max_streams");
+  std::vector<int> sids;
+  for (int i = 0; i < B; ++i) sids.push_back(open_stream());
+  PKB_CUDA(cudaStreamSynchronize(st_));
+  std::vector<float> hb(kPredL * kPredH), cb(kPredL * kPredH);
+  for (int i = 0; i < B; ++i) {
+    for (int l = 0; l < kPredL; ++l) {   // contract layout [2,B,640] -> slot layout [2][640]
+      memcpy(&hb[l * kPredH], h + ((size_t)l * B + i) * kPredH, kPredH * 4);
+      memcpy(&cb[l * kPredH], c + ((size_t)l * B + i) * kPredH, kPredH * 4);
+    }
+    const size_t slot = streams_[sids[i]]->slot;
+    PKB_CUDA(cudaMemcpy(im.pred_h + slot * kPredL * kPredH, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice));
+    PKB_CUDA(cudaMemcpy(im.pred_c + slot * kPredL * kPredH, cb.data(), cb.size() * 4, cudaMemcpyHostToDevice));
+    im.batch_ints_host[i] = (int)slot;
+    im.res_host[i] = (int)y[i];
+  }
+  PKB_CUDA(cudaMemcpyAsync(im.batch_ints, im.batch_ints_host, B * sizeof(int), cudaMemcpyHostToDevice, st_));
+  PKB_CUDA(cudaMemcpyAsync(im.force_toks, im.res_host, B * sizeof(int), cudaMemcpyHostToDevice, st_));
+  DecodeDev d = make_decode_dev(im, opt_, B, im.batch_ints, nullptr, nullptr);
+  launch_decode_iter_reset(d, st_); ++launches_;
+  launch_force_token(d, im.force_toks, st_); ++launches_;
+  run_predictor_pass(d);
+  PKB_CUDA(cudaStreamSynchronize(st_));
+  for (int i = 0; i < B; ++i) {
+    const size_t slot = streams_[sids[i]]->slot;
+    PKB_CUDA(cudaMemcpy(hb.data(), im.pred_h + slot * kPredL * kPredH, hb.size() * 4, cudaMemcpyDeviceToHost));
+    PKB_CUDA(cudaMemcpy(cb.data(), im.pred_c + slot * kPredL * kPredH, cb.size() * 4, cudaMemcpyDeviceToHost));
+    for (int l = 0; l < kPredL; ++l) {
+      memcpy(h_out + ((size_t)l * B + i) * kPredH, &hb[l * kPredH], kPredH * 4);
+      memcpy(c_out + ((size_t)l * B + i) * kPredH, &cb[l * kPredH], kPredH * 4);
+    }
+    PKB_CUDA(cudaMemcpy(g + (size_t)i * kPredH, im.pred_g + slot * kPredH, kPredH * 4, cudaMemcpyDeviceToHost));  // [B,640,1]
+    close_stream(sids[i]);
+  }
+}
+
+void Engine::joint_step(int B, int T, int U, const float* enc, const float* pred, float* out) {
+  Impl& im = *im_;
+  const int rows = B * T * U;
+  PKB_CHECK(B >= 1 && B * T <= im.a_ln.rows_cap && B * U <= im.a_g.rows_cap && rows <= im.a_hid.rows_cap,
+            "joint_step: B*T*U exceeds the decode row capacity (raise max_streams)");
+  PKB_CUDA(cudaStreamSynchronize(st_));
+  float* d_enc = dev_upload(std::vector<float>(enc, enc + (size_t)B * kDModel * T));
+  float* d_pred = dev_upload(std::vector<float>(pred, pred + (size_t)B * kPredH * U));
+  float* d_P = dev_alloc<float>((size_t)B * U * kJointH);
+  // enc [B,1024,T] -> operand rows (b*T+t): row stride within b is 1 (t), col stride T
+  for (int b = 0; b < B; ++b) {
+    ActOut a = im.a_ln.out(); a.ptr += (size_t)b * T * a.lda;
+    f32_to_act_kernel<<<(T * kDModel + 255) / 256, 256, 0, st_>>>(d_enc + (size_t)b * kDModel * T, 1, T, T, kDModel, a);
+    ActOut p = im.a_g.out(); p.ptr += (size_t)b * U * p.lda;
+    f32_to_act_kernel<<<(U * kPredH + 255) / 256, 256, 0, st_>>>(d_pred + (size_t)b * kPredH * U, 1, U, U, kPredH, p);
+    launches_ += 2;
+  }
+  { EpiParams e; e.mode = EPI_BIAS_F32; e.out_f32 = im.enc_proj; e.ldo = kJointH; e.bias = im.joint_enc_b;
+    RUN_GEMM(im.a_ln, im.joint_enc, B * T, nullptr, e); }
+  { EpiParams e; e.mode = EPI_BIAS_F32; e.out_f32 = d_P; e.ldo = kJointH; e.bias = im.joint_pred_b;
+    RUN_GEMM(im.a_g, im.joint_pred, B * U, nullptr, e); }
+  joint_hidden_grid_kernel<<<rows, 128, 0, st_>>>(im.enc_proj, d_P, T, U, im.a_hid.out()); ++launches_;
+  { EpiParams e; e.mode = EPI_BIAS_F32; e.out_f32 = im.logits; e.ldo = kJointOut; e.bias = im.joint_out_b;
+    RUN_GEMM(im.a_hid, im.joint_out, rows, nullptr, e); }
+  PKB_CUDA(cudaMemcpyAsync(out, im.logits, (size_t)rows * kJointOut * 4, cudaMemcpyDeviceToHost, st_));
+  PKB_CUDA(cudaStreamSynchronize(st_));
+  cudaFree(d_enc); cudaFree(d_pred); cudaFree(d_P);
+}
+
+size_t Engine::logmel(const float* pcm, size_t n, float* out, int per_feature_norm) {
+  Impl& im = *im_;
+  if (n < 400) return 0;
+  const size_t T = (n - 400) / 160 + 1;
+  PKB_CHECK(T < (1u << 30), "clip too long");
+  float* d_audio = dev_alloc<float>(n);
+  float* d_out = dev_alloc<float>(T * kNMels);
+  float* d_stats = dev_alloc<float>(2 * kNMels);
+  PKB_CUDA(cudaMemcpyAsync(d_audio, pcm, n * 4, cudaMemcpyHostToDevice, st_));
+  FrontSegment sg{0, 0, kNMels, 0, 0, -1};
+  int prefix[2] = {0, (int)T}, frames = (int)T;
+  FrontSegment* d_seg = dev_alloc<FrontSegment>(1);
+  int* d_prefix = dev_alloc<int>(3);
+  PKB_CUDA(cudaMemcpyAsync(d_seg, &sg, sizeof(sg), cudaMemcpyHostToDevice, st_));
+  PKB_CUDA(cudaMemcpyAsync(d_prefix, prefix, sizeof(prefix), cudaMemcpyHostToDevice, st_));
+  PKB_CUDA(cudaMemcpyAsync(d_prefix + 2, &frames, sizeof(int), cudaMemcpyHostToDevice, st_));
+  im.frontend.logmel(d_audio, d_seg, d_prefix, 1, (int)T, d_out, nullptr, sm_count_, st_); ++launches_;
+  if (per_feature_norm) {
+    im.frontend.per_feature_stats(d_out, d_seg, d_prefix + 2, 1, d_stats, st_); ++launches_;
+    im.frontend.apply_norm(d_out, d_seg, d_prefix + 2, 1, (int)T, d_stats, st_); ++launches_;
+  }
+  PKB_CUDA(cudaMemcpyAsync(out, d_out, T * kNMels * 4, cudaMemcpyDeviceToHost, st_));
+  PKB_CUDA(cudaStreamSynchronize(st_));
+  cudaFree(d_audio); cudaFree(d_out); cudaFree(d_stats); cudaFree(d_seg); cudaFree(d_prefix);
+  return T;
+}
+
+void Engine::gemm_test(int backend, int M, int N, int K, const float* A, const uint16_t* W_bits, float* C, int epi_silu) {
+  const bool split = opt_.precision == 1;
+  PKB_CUDA(cudaStreamSynchronize(st_));
+  ActBuf a = make_act(M, K, split);
+  GemmW w = upload_gemm_w(std::vector<uint16_t>(W_bits, W_bits + (size_t)N * K), N, K);
+  float* d_A = dev_upload(std::vector<float>(A, A + (size_t)M * K));
+  float* d_C = dev_alloc<float>((size_t)M * N);
+  const long long n = (long long)M * K;
+  f32_to_act_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st_>>>(d_A, K, 1, M, K, a.out());
+  GemmArgs g;
+  g.A = a.ptr; g.lda = K; g.a_lo_off = a.lo_off; g.W = w.w; g.M = M; g.N = N; g.K = K;
+  g.epi.mode = EPI_F32; g.epi.out_f32 = d_C; g.epi.ldo = N;
+  (void)epi_silu;
+  if (backend == 1) {
+    PKB_CHECK(gemm_tc_supported(g), "gemm_test: shape not supported by the tensor-core backend");
+    gemm_tc(g, a.map, w.map, st_);
+  } else {
+    gemm_simt(g, st_);
+  }
+  ++launches_;
+  PKB_CUDA(cudaMemcpyAsync(C, d_C, (size_t)M * N * 4, cudaMemcpyDeviceToHost, st_));
+  PKB_CUDA(cudaStreamSynchronize(st_));
+  cudaFree(a.ptr); cudaFree(w.w); cudaFree(d_A); cudaFree(d_C);
+}
+
+}  // namespace pkb

@@ -1,0 +1,117 @@
+// engine.h -- per-GPU batched streaming engine behind the C ABI.
+//
+// The reference drives one stream per session through three TensorRT engines with the decode loop on the host
+// (/root/reference/cpp/src/parakeet_trt.cpp:1557-1665, 1967-3858).  Here one Engine owns the weights of one GPU and a table of
+// stream slots; `step()` advances every stream that has a pending chunk in ONE batched pass
+// (frontend -> FastConformer chunk -> TDT decode), and the legacy `ParakeetSession` is a one-stream view of it.
+#pragma once
+#include <deque>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "dec_kernels.cuh"
+#include "enc_kernels.cuh"
+#include "frontend.h"
+#include "gemm.h"
+#include "weights_file.h"
+
+namespace pkb {
+
+struct EngineOptions {
+  std::string model_dir;
+  int device_id = 0;
+  int max_streams = 1;
+  int precision = 0;        // 0 = bf16 operands (fast); 1 = split bf16 hi+lo operands, f32 K/V rings (fp32-grade)
+  int gemm_backend = 0;     // 0 = auto (tcgen05 for M > 16, weight-streaming SIMT below); 1 = SIMT only; 2 = tcgen05 always
+  int contract_cache = 1;   // keep the pre-projection cache_last_channel ring (needed by state export)
+  int punct_suppress = 1;   // PARAKEET_DISABLE_PUNCT_SUPPRESSION inverse
+  float blank_penalty = 0.0f;
+  int max_rows = 0;         // packed encoder rows per batched pass (0: max(64, 8*max_streams))
+};
+
+struct StepRecord { int time_idx, token, duration; };
+
+struct ChunkResult {          // what one chunk of one stream produced
+  std::vector<StepRecord> steps;
+  int cache_len_out = 0;
+  int encoded_len = 0;
+};
+
+class Engine {
+ public:
+  explicit Engine(const EngineOptions& opt);
+  ~Engine();
+  Engine(const Engine&) = delete;
+
+  int open_stream();                       // -> stream id, or throws when the table is full
+  void close_stream(int sid);
+  void reset_stream(int sid);              // zero caches + predictor state, prime with <|startoftranscript|>, <|en|>
+
+  // Legacy-ABI granularity: these T frames ([128,T] bins-major, host) form exactly one encoder chunk.
+  void queue_features(int sid, const float* feats_bins_major, int T);
+  // Audio granularity: buffered; step() runs the GPU frontend and cuts chunks by the 41/57-frame schedule
+  // (tools/verify_nemo/streaming_encoder_reference.py:522-550).
+  void queue_audio(int sid, const float* pcm, size_t n);
+  void set_feature_norm(int sid, const float* mean128, const float* std128);   // nullptrs: none
+
+  // Advance every stream that has a pending chunk by one chunk.  Returns the number of chunks processed.
+  int step();
+  bool has_pending(int sid) const;
+
+  const std::vector<int>& tokens(int sid) const;
+  const ChunkResult& last_chunk(int sid) const;
+  int cache_len(int sid) const;
+  long long chunks_done(int sid) const;
+
+  // ---- tensor-level entry points at the contract layouts (host pointers) ----
+  void encoder_streaming_step(int B, int T, const float* audio_signal, const int64_t* length, const float* cache_last_channel,
+                              const float* cache_last_time, const int64_t* cache_last_channel_len, float* encoder_output,
+                              int64_t* encoded_lengths, float* cache_last_channel_out, float* cache_last_time_out,
+                              int64_t* cache_last_channel_len_out);
+  void predictor_step(int B, const int64_t* y, const float* h, const float* c, float* g, float* h_out, float* c_out);
+  void joint_step(int B, int T, int U, const float* enc, const float* pred, float* out);
+  // GPU frontend on host buffers: pcm[n] -> frames-major [T,128]; per_feature_norm applies utterance mean/std
+  size_t logmel(const float* pcm, size_t n, float* out_frames_major, int per_feature_norm);
+  // standalone GEMM for validation of the tensor-core backend: C = A(f32, split or rounded per precision) * W^T
+  void gemm_test(int backend, int M, int N, int K, const float* A, const uint16_t* W_bf16, float* C, int epi_silu);
+
+  const EngineOptions& options() const { return opt_; }
+  int n_layers() const { return L_; }
+  const std::vector<std::string>& vocab() const { return vocab_; }
+  std::string detokenize(const std::vector<int>& ids) const;
+  long long kernel_launches() const { return launches_; }
+  int sm_count() const { return sm_count_; }
+  cudaStream_t stream() const { return st_; }
+  void synchronize();
+
+  struct Stream;
+  struct Impl;
+  struct Entry { int sid; int f0; int T; };
+
+ private:
+  void load_weights();
+  void alloc_state();
+  void run_batch(const std::vector<Entry>& entries, float* enc_out_host /*optional [B,1024,3]*/);
+  void run_encoder(const BatchDev& b);
+  void run_decode(const BatchDev& b, const std::vector<Entry>& entries);
+  void run_predictor_pass(const DecodeDev& d);
+  void frontend_pass();
+  void prime_streams(const std::vector<int>& sids);
+  void import_state(int sid, const float* cache_ch, long long ch_stride_unused, const float* cache_tm, int cache_len);
+  void export_state(int sid, float* cache_ch, float* cache_tm);
+  BatchDev upload_batch(const std::vector<Entry>& entries);
+
+  EngineOptions opt_;
+  int L_ = 0;
+  int sm_count_ = 148;
+  cudaStream_t st_ = nullptr;
+  std::unique_ptr<Impl> im_;
+  std::vector<std::unique_ptr<Stream>> streams_;
+  std::vector<std::string> vocab_;
+  std::vector<unsigned> punct_bits_;
+  int tok_start_ = -1, tok_lang_ = -1;
+  long long launches_ = 0;
+};
+
+}  // namespace pkb
