@@ -55,5 +55,6 @@ def test_linearity_property_at_scale(eng):
     pcm = 0.25 * synth_clip(60.0, 77)
     a, b = eng.logmel(pcm), eng.logmel(2 * pcm)
     assert a.shape == (5998, 128)
-    d = (b - a)[:, 1:]
-    assert np.max(np.abs(d - np.log(4.0))) < 2e-3
+    loud = a > -4.0         # where the mel energy dwarfs the 1e-5 floor inside ln(E + 1e-5)
+    assert loud.mean() > 0.5
+    assert np.max(np.abs((b - a)[loud] - np.log(4.0))) < 1e-3

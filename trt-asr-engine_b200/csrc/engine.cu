@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <fstream>
 
 namespace pkb {
@@ -228,18 +229,21 @@ static GemmW upload_gemm_w(const std::vector<uint16_t>& bits, int N, int K) {
   const size_t rows_pad = ((size_t)N + 127) / 128 * 128;
   g.w = dev_alloc<__nv_bfloat16>(rows_pad * K);
   PKB_CUDA(cudaMemset(g.w, 0, rows_pad * K * 2));
-  PKB_CUDA(cudaMemcpy(g.w, bits.data(), bits.size() * 2, cudaMemcpyHostToDevice));
+  PKB_CUDA(cudaMemcpy(g.w, bits.data(), bits.size() * 2, cudaMemcpyHostToDevice));   // synchronous: both are complete on return
+  PKB_CUDA(cudaDeviceSynchronize());
   make_tensor_map_2d(&g.map, g.w, rows_pad, K, K, 128);
   return g;
 }
 
-static ActBuf make_act(int rows_cap, int K, bool split) {
+// NOTE: the engine stream is non-blocking, so legacy-default-stream memsets would NOT be ordered against it; every
+// device-side initialisation below is therefore issued on the engine stream itself.
+static ActBuf make_act(int rows_cap, int K, bool split, cudaStream_t st) {
   ActBuf a;
   a.rows_cap = (rows_cap + 127) / 128 * 128;
   a.K = K;
   const size_t plane = (size_t)a.rows_cap * K;
   a.ptr = dev_alloc<__nv_bfloat16>(plane * (split ? 2 : 1));
-  PKB_CUDA(cudaMemset(a.ptr, 0, plane * (split ? 2 : 1) * 2));
+  PKB_CUDA(cudaMemsetAsync(a.ptr, 0, plane * (split ? 2 : 1) * 2, st));
   a.lo_off = split ? (long long)plane : 0;
   make_tensor_map_2d(&a.map, a.ptr, (uint64_t)a.rows_cap * (split ? 2 : 1), K, K, 128);
   return a;
@@ -396,16 +400,16 @@ void Engine::alloc_state() {
   im.T3cap = im.Mcap + kDropPre * im.Bcap;
   im.T2cap = 2 * im.T3cap + im.Bcap;
   const int rows_dec = std::max(im.Bcap, 64);
-  im.a_sub1 = make_act(im.T2cap * 32, kSubCh, split);
-  im.a_sub2 = make_act(im.T3cap * 16, kSubCh, split);
-  im.a_sub3 = make_act(im.T3cap, 16 * kSubCh, split);
-  im.a_ln = make_act(std::max(im.Mcap, rows_dec), kDModel, split);
-  im.a_ff = make_act(im.Mcap, kFF, split);
-  im.a_hid = make_act(rows_dec, kJointH, split);
-  im.a_pred = make_act(rows_dec, 2 * kPredH, split);
-  im.a_g = make_act(rows_dec, kPredH, split);
-  im.a_imp = make_act(kCacheS, kDModel, split);
-  im.a_pos = make_act(kPosRows, kDModel, true);
+  im.a_sub1 = make_act(im.T2cap * 32, kSubCh, split, st_);
+  im.a_sub2 = make_act(im.T3cap * 16, kSubCh, split, st_);
+  im.a_sub3 = make_act(im.T3cap, 16 * kSubCh, split, st_);
+  im.a_ln = make_act(std::max(im.Mcap, rows_dec), kDModel, split, st_);
+  im.a_ff = make_act(im.Mcap, kFF, split, st_);
+  im.a_hid = make_act(rows_dec, kJointH, split, st_);
+  im.a_pred = make_act(rows_dec, 2 * kPredH, split, st_);
+  im.a_g = make_act(rows_dec, kPredH, split, st_);
+  im.a_imp = make_act(kCacheS, kDModel, split, st_);
+  im.a_pos = make_act(kPosRows, kDModel, true, st_);
   im.x = dev_alloc<float>((size_t)im.Mcap * kDModel);
   im.q = dev_alloc<float>((size_t)im.Mcap * kDModel);
   im.cglu = dev_alloc<float>((size_t)im.Mcap * kDModel);
@@ -667,6 +671,12 @@ BatchDev Engine::upload_batch(const std::vector<Entry>& entries) {
 }
 
 // GEMM on an activation buffer and a weight, choosing the backend
+static int g_tc_site = 0;        // bring-up aid: PARAKEET_B200_TC_MASK disables the tensor-core path per call-site group
+static int tc_mask() {
+  static int m = -2;
+  if (m == -2) { const char* v = getenv("PARAKEET_B200_TC_MASK"); m = v ? atoi(v) : -1; }
+  return m;
+}
 static void run_gemm(Engine* eng, const EngineOptions& opt, cudaStream_t st, long long* launches, const ActBuf& a, int lda_override,
                      const GemmW& w, int M, const int* M_dev, const EpiParams& epi) {
   (void)eng;
@@ -679,7 +689,8 @@ static void run_gemm(Engine* eng, const EngineOptions& opt, cudaStream_t st, lon
   g.M_dev = M_dev;
   g.epi = epi;
   ++*launches;
-  const bool want_tc = opt.gemm_backend == 2 || (opt.gemm_backend == 0 && M > 16);
+  bool want_tc = opt.gemm_backend == 2 || (opt.gemm_backend == 0 && M > 16);
+  if (tc_mask() >= 0 && !(tc_mask() & g_tc_site)) want_tc = false;
   if (want_tc && lda_override <= 0 && gemm_tc_supported(g)) gemm_tc(g, a.map, w.map, st);
   else gemm_simt(g, st);
 }
@@ -691,15 +702,19 @@ void Engine::run_encoder(const BatchDev& b) {
   launch_build_rows(b, st_); ++launches_;
   // ---- pre-encode ----
   launch_subsample_stage1(b, im.feat_ring, kFeatRing, im.sub, im.a_sub1.out(), st_); ++launches_;
+  g_tc_site = 1;
   { EpiParams e; e.mode = EPI_BIAS_RELU_F32; e.out_f32 = im.y1; e.ldo = kSubCh; e.bias = im.sub_pw1_b;
     RUN_GEMM(im.a_sub1, im.sub_pw1, b.sumT2 * 32, nullptr, e); }
   launch_subsample_stage2(b, im.y1, im.sub, im.a_sub2.out(), st_); ++launches_;
+  g_tc_site = 2;
   { EpiParams e; e.mode = EPI_BIAS_RELU_ACT; e.out_act = im.a_sub3.ptr; e.lda_out = kSubCh; e.lo_off_out = im.a_sub3.lo_off;
     e.bias = im.sub_pw2_b;
     RUN_GEMM(im.a_sub2, im.sub_pw2, b.sumT3 * 16, nullptr, e); }
+  g_tc_site = 4;
   { EpiParams e; e.mode = EPI_BIAS_ROWMAP_F32; e.out_f32 = im.x; e.ldo = kDModel; e.bias = im.sub_out_b; e.row_map = b.rowmap3;
     RUN_GEMM(im.a_sub3, im.sub_out, b.sumT3, nullptr, e); }
   // ---- conformer layers ----
+  g_tc_site = 8;
   const int M = b.M;
   launch_layernorm(im.x, M, im.layers[0].n_ff1_g, im.layers[0].n_ff1_b, nullptr, nullptr, 0, im.a_ln.out(), nullptr, st_); ++launches_;
   const size_t kv_elem = split ? 4 : 2;
@@ -708,8 +723,10 @@ void Engine::run_encoder(const BatchDev& b) {
     char* kr = (char*)im.kring + (size_t)l * im.ring_layer_elems * kv_elem;
     char* vr = (char*)im.vring + (size_t)l * im.ring_layer_elems * kv_elem;
     // FFN 1 (half-step residual)
+    g_tc_site = 64;
     { EpiParams e; e.mode = EPI_SILU_ACT; e.out_act = im.a_ff.ptr; e.lda_out = kFF; e.lo_off_out = im.a_ff.lo_off;
       RUN_GEMM(im.a_ln, w.ff1_1, M, nullptr, e); }
+    g_tc_site = 128;
     { EpiParams e; e.mode = EPI_RESADD_F32; e.out_f32 = im.x; e.ldo = kDModel; e.scale = 0.5f;
       RUN_GEMM(im.a_ff, w.ff1_2, M, nullptr, e); }
     // self-attention
@@ -719,27 +736,33 @@ void Engine::run_encoder(const BatchDev& b) {
       ac.row_entry = b.row_entry; ac.row_pos = b.row_pos; ac.entry_slot = b.slot; ac.entry_head = b.head;
     }
     launch_layernorm(im.x, M, w.n_att_g, w.n_att_b, nullptr, nullptr, 0, im.a_ln.out(), im.acache ? &ac : nullptr, st_); ++launches_;
+    g_tc_site = 256;
     { EpiParams e; e.mode = EPI_QKV; e.out_f32 = im.q; e.ldo = kDModel; e.row_entry = b.row_entry; e.row_pos = b.row_pos;
       e.entry_slot = b.slot; e.entry_head = b.head; e.kring = kr; e.vring = vr; e.kv_f32 = split ? 1 : 0;
       RUN_GEMM(im.a_ln, w.qkv, M, nullptr, e); }
     { AttnArgs a; a.q = im.q; a.kring = kr; a.vring = vr; a.ppos_t = w.ppos_t; a.kv_f32 = split ? 1 : 0; a.bias_u = w.bias_u;
       a.bias_v = w.bias_v; a.ctx = im.a_ln.out();
       launch_attention(b, a, st_); ++launches_; }
+    g_tc_site = 512;
     { EpiParams e; e.mode = EPI_RESADD_F32; e.out_f32 = im.x; e.ldo = kDModel; e.scale = 1.0f;
       RUN_GEMM(im.a_ln, w.out, M, nullptr, e); }
     // convolution module
     launch_layernorm(im.x, M, w.n_conv_g, w.n_conv_b, nullptr, nullptr, 0, im.a_ln.out(), nullptr, st_); ++launches_;
+    g_tc_site = 1024;
     { EpiParams e; e.mode = EPI_GLU_F32; e.out_f32 = im.cglu; e.ldo = kDModel;
       RUN_GEMM(im.a_ln, w.pw1, M, nullptr, e); }
     { DwConvArgs a; a.c = im.cglu; a.cache_tm = im.cache_tm + (size_t)l * kDModel * kTimeCtx; a.slot_stride = (long long)L_ * kDModel * kTimeCtx;
       a.w = w.dw_w; a.bias = w.dw_b; a.out = im.a_ln.out();
       launch_dwconv(b, a, st_); ++launches_; }
+    g_tc_site = 2048;
     { EpiParams e; e.mode = EPI_RESADD_F32; e.out_f32 = im.x; e.ldo = kDModel; e.scale = 1.0f;
       RUN_GEMM(im.a_ln, w.pw2, M, nullptr, e); }
     // FFN 2
     launch_layernorm(im.x, M, w.n_ff2_g, w.n_ff2_b, nullptr, nullptr, 0, im.a_ln.out(), nullptr, st_); ++launches_;
+    g_tc_site = 64;
     { EpiParams e; e.mode = EPI_SILU_ACT; e.out_act = im.a_ff.ptr; e.lda_out = kFF; e.lo_off_out = im.a_ff.lo_off;
       RUN_GEMM(im.a_ln, w.ff2_1, M, nullptr, e); }
+    g_tc_site = 128;
     { EpiParams e; e.mode = EPI_RESADD_F32; e.out_f32 = im.x; e.ldo = kDModel; e.scale = 0.5f;
       RUN_GEMM(im.a_ff, w.ff2_2, M, nullptr, e); }
     // norm_out (+ next layer's norm_feed_forward1; after the last layer: operand of the joint's encoder projection)
@@ -769,6 +792,7 @@ void Engine::run_decode(const BatchDev& b, const std::vector<Entry>& entries) {
   Impl& im = *im_;
   (void)entries;
   // joint encoder projection for every packed row: E = joint.enc(x) + bias
+  g_tc_site = 16;
   { EpiParams e; e.mode = EPI_BIAS_F32; e.out_f32 = im.enc_proj; e.ldo = kJointH; e.bias = im.joint_enc_b;
     RUN_GEMM(im.a_ln, im.joint_enc, b.M, nullptr, e); }
   DecodeDev d = make_decode_dev(im, opt_, b.B, b.slot, b.row_off, im.batch_ints + 10 * im.Bcap);
@@ -930,6 +954,7 @@ void Engine::import_state(int sid, const float* cache_ch, long long, const float
     char* ac = (char*)im.acache + (size_t)l * im.ring_layer_elems * kv_elem;
     launch_acache_import(ac, split, meta, meta + 1, 1, im.scratch_f32 + (size_t)l * kCacheS * kDModel, 0, st_); ++launches_;
     launch_acache_to_act(ac, split, meta, meta + 1, 1, im.a_imp.out(), st_); ++launches_;
+    g_tc_site = 32;
     EpiParams e; e.mode = EPI_QKV; e.n_off = kDModel; e.row_entry = im.imp_row_entry; e.row_pos = im.imp_row_pos;
     e.entry_slot = meta; e.entry_head = meta + 1;
     e.kring = (char*)im.kring + (size_t)l * im.ring_layer_elems * kv_elem;
@@ -1088,7 +1113,7 @@ size_t Engine::logmel(const float* pcm, size_t n, float* out, int per_feature_no
 void Engine::gemm_test(int backend, int M, int N, int K, const float* A, const uint16_t* W_bits, float* C, int epi_silu) {
   const bool split = opt_.precision == 1;
   PKB_CUDA(cudaStreamSynchronize(st_));
-  ActBuf a = make_act(M, K, split);
+  ActBuf a = make_act(M, K, split, st_);
   GemmW w = upload_gemm_w(std::vector<uint16_t>(W_bits, W_bits + (size_t)N * K), N, K);
   float* d_A = dev_upload(std::vector<float>(A, A + (size_t)M * K));
   float* d_C = dev_alloc<float>((size_t)M * N);

@@ -41,7 +41,7 @@ def main():
         z = eng.logmel(np.zeros(16000, np.float32))
         print("  zeros exact:", bool(np.all(z == np.float32(np.log(np.float32(1e-5))))), z[0, 0])
     elif sec == "gemm":
-        for M, N, K in [(6, 1024, 1024), (130, 640, 640), (300, 1024, 4096), (64, 8198, 640)]:
+        for M, N, K in [(96, 256, 256), (352, 256, 256), (256, 2048, 1024), (6, 1024, 1024), (300, 1024, 4096), (64, 8198, 640)]:
             rng = np.random.default_rng(1)
             A = rng.standard_normal((M, K)).astype(np.float32)
             Wb = f32_to_bf16_bits(rng.standard_normal((N, K)).astype(np.float32) / np.sqrt(K)).reshape(N, K)
