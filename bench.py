@@ -1,0 +1,357 @@
+#!/usr/bin/env python3
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config: RTFx (audio s / wall s) at 1024 concurrent streams.
+
+One "step" = every stream advances by one cache-aware chunk (24 new 10-ms frames = 0.24 s of audio per stream):
+batched push of 3840 samples per stream -> GPU log-mel frontend -> FastConformer chunk (57-frame slice, 256-step cache)
+-> TDT greedy decode -> cache carry-over.  Streams are sharded over the ranks (stream i -> rank i mod N), no collective
+on the data path; the only cross-rank traffic is the barrier + max-reduce of the timing.
+
+  value : whole-job RTFx with the audio already resident in HBM (pkb_engine_push_audio_batch_device + pkb_engine_step),
+          device-timed with CUDA events on the engine's stream, max over ranks.
+  e2e   : the same through the host-facing C ABI call (pkb_engine_push_audio_batch from pinned host memory + step; the
+          step ends with the D2H read of every stream's decode trace), wall-clock between device syncs, max over ranks.
+  roofline    : the dominant kernel (tcgen05 GEMM): algorithmic 2*M*N*K per launch / its CUDA-event duration, vs the
+                measured sustained bf16 peak of MEASURED_PEAKS.json.
+  cpu_baseline: the CPU oracle (C restatement of rust/features + PyTorch restatement of the NeMo modules the reference's
+                ORT-CPU runner executes) on the box's host cores, on a bounded sample of the same workload.
+`--impl reference` times that CPU path alone (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "trt-asr-engine_b200")
+for p in (PKG, os.path.join(PKG, "tools")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+SAMPLES_PER_STEP = 3840          # shift of 24 feature frames (contract.json:263-266)
+AUDIO_S_PER_STEP = 0.24
+N_CLIPS = 32
+METRIC = "RTFx (audio s / wall s) @1024 streams"
+
+
+def shard(n_streams: int, rank: int, world: int):
+    """stream i -> rank i mod world; no data-path collective."""
+    return [i for i in range(n_streams) if i % world == rank]
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0))), float(d.get("hbm_gbs", 6650.0)), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+                for n, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU path (oracle)
+def cpu_path_rtfx(model_dir: str, n_streams: int, n_chunks: int, warm_chunks: int = 1):
+    """The reference's CPU path restated: C log-mel (all host threads) + PyTorch-CPU streaming encoder + greedy TDT.
+    Returns (rtfx, cores, wall_s, audio_s).  Only the checker is executed here -- never the product."""
+    import ctypes
+
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from model_ref import DecodeState, ModelRef, prime, streaming_schedule, tdt_greedy_chunk
+    from synth_audio import synth_clip
+    so = os.path.join(ROOT, "oracle", "_build", "libfeatures_ref.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "_build/libfeatures_ref.so"], stdout=subprocess.DEVNULL)
+    fr = ctypes.CDLL(so)
+    fr.fr_num_frames.restype = ctypes.c_size_t
+    fr.fr_num_frames.argtypes = [ctypes.c_size_t]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m = ModelRef(model_dir)
+    total = warm_chunks + n_chunks
+    sched = streaming_schedule(total)
+    n_samp = (sched[-1][1] - 1) * 160 + 400
+    clips = [synth_clip(n_samp / 16000.0 + 0.1, 1000 + i)[:n_samp] for i in range(n_streams)]
+    states = []
+    for _ in range(n_streams):
+        st = DecodeState(m)
+        prime(m, st)
+        states.append(st)
+    cc, ct, cl = m.initial_cache(n_streams)
+    feats = np.zeros((n_streams, sched[-1][1], 128), np.float32)
+    done_frames = 0
+    t0 = None
+    for k, (b, e) in enumerate(sched):
+        if k == warm_chunks:
+            t0 = time.perf_counter()
+        # frontend for the frames this chunk needs that are not computed yet (streaming, like the GPU path)
+        if e > done_frames:
+            for i in range(n_streams):
+                seg = np.ascontiguousarray(clips[i][done_frames * 160:(e - 1) * 160 + 400])
+                fr.fr_logmel(seg.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(seg.size),
+                             feats[i, done_frames:e].ctypes.data_as(ctypes.c_void_p), ctypes.c_int(cores))
+            done_frames = e
+        x = torch.from_numpy(np.ascontiguousarray(feats[:, b:e].transpose(0, 2, 1)))
+        enc, el, cc, ct, cl = m.stream_step(x, torch.full((n_streams,), e - b, dtype=torch.int64), cc, ct, cl)
+        for i in range(n_streams):
+            tdt_greedy_chunk(m, states[i], enc[i:i + 1], int(el[i]))
+    wall = time.perf_counter() - t0
+    audio_s = n_streams * n_chunks * AUDIO_S_PER_STEP
+    return audio_s / wall, cores, wall, audio_s
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    from make_synthetic_model import ensure_model
+    model = ensure_model(os.path.join(ROOT, "models", f"synth{args.layers}"), n_layers=args.layers, seed=0)
+    n_streams = args.ref_streams
+    rtfx, cores, wall, audio_s = cpu_path_rtfx(model, n_streams, args.steps, max(args.warmup, 1))
+    sample = f"{n_streams} streams x {args.steps} chunks ({audio_s:.2f} s audio) after {max(args.warmup,1)} warm-up chunk(s)"
+    line = {"impl": "reference", "metric": METRIC, "value": rtfx, "unit": "x real time", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "streaming chunk step (57-frame slice, cache 256) + TDT greedy, CPU restatement of rust/features + "
+                                   "NeMo modules behind the ORT-CPU runner", "model": f"parakeet-tdt-0.6b-v3 synthetic weights, {args.layers} layers",
+                       "streams": n_streams},
+            "cpu_baseline": {"value": rtfx, "unit": "x real time", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rtfx, "unit": "x real time", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- GPU path
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--streams", type=int, default=1024, help="total concurrent streams over all ranks")
+    ap.add_argument("--layers", type=int, default=24)
+    ap.add_argument("--precision", type=int, default=int(os.environ.get("PKB_BENCH_PRECISION", "0")),
+                    help="0 = bf16 operands, 1 = split bf16 hi+lo (fp32-grade)")
+    ap.add_argument("--ref-streams", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+
+    import binding
+    from make_synthetic_model import ensure_model
+    from synth_audio import synth_clip
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    model = os.path.join(ROOT, "models", f"synth{args.layers}")
+    if rank == 0:
+        ensure_model(model, n_layers=args.layers, seed=0)
+    if world > 1:
+        dist.barrier()
+    if not os.path.exists(binding.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+
+    mine = shard(args.streams, rank, world)
+    n = len(mine)
+    eng = binding.Engine(model, device_id=local_rank, max_streams=n, precision=args.precision, max_rows=8 * n)
+    sids = np.array([eng.open() for _ in mine], np.int32)
+
+    prof_steps = 2
+    total_pushes = 2 + args.warmup + args.steps + 2 + args.steps + prof_steps   # prefill, warm-up, timed(value), warm, timed(e2e), profile
+    clip_len = total_pushes * SAMPLES_PER_STEP + 16000
+    clips = np.stack([synth_clip(clip_len / 16000.0 + 0.01, 1000 + c)[:clip_len] for c in range(N_CLIPS)])
+    phase = np.array([(i * 977) % 12000 for i in mine])
+    clip_of = np.array([i % N_CLIPS for i in mine])
+
+    def host_step_audio(k: int) -> np.ndarray:
+        idx = phase[:, None] + k * SAMPLES_PER_STEP + np.arange(SAMPLES_PER_STEP)[None, :]
+        return clips[clip_of[:, None], idx]
+
+    host = torch.empty((total_pushes, n, SAMPLES_PER_STEP), dtype=torch.float32).pin_memory()
+    for k in range(total_pushes):
+        host[k] = torch.from_numpy(host_step_audio(k))
+    dev = host.cuda(non_blocking=False)
+    torch.cuda.synchronize()
+    step_bytes = n * SAMPLES_PER_STEP * 4
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cursor = [0]
+
+    def do_step(resident: bool):
+        k = cursor[0]
+        cursor[0] += 1
+        if resident:
+            eng.push_audio_batch_device(sids, dev[k].data_ptr(), SAMPLES_PER_STEP, SAMPLES_PER_STEP)
+        else:
+            eng.push_audio_batch(sids, host[k].data_ptr(), SAMPLES_PER_STEP, SAMPLES_PER_STEP)
+        return eng.step()
+
+    # prefill: 2 pushes = 46 frames >= the 41 frames of chunk 0; afterwards every push yields exactly one chunk per stream
+    eng.push_audio_batch_device(sids, dev[0].data_ptr(), SAMPLES_PER_STEP, SAMPLES_PER_STEP)
+    cursor[0] = 1
+    assert do_step(True) == n, "prefill did not produce chunk 0 for every stream"
+    for _ in range(args.warmup):
+        assert do_step(True) == n
+
+    # ---- timed region 1: audio resident in HBM, CUDA events on the engine stream
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = eng.kernel_launches()
+    e0 = eng.event_record()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        do_step(True)
+    e1 = eng.event_record()
+    dev_ms = eng.event_elapsed_ms(e0, e1)
+    barrier()
+    wall_resident = time.perf_counter() - t0
+    launches = eng.kernel_launches() - launches0
+    clocks = sampler.stop()
+
+    # ---- timed region 2: end to end from pinned host memory through the C ABI (H2D + step + D2H of the decode traces)
+    for _ in range(2):
+        do_step(False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        do_step(False)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    # ---- per-launch timing of the dominant kernel (tcgen05 GEMM) for the roofline
+    eng.profile_enable(True)
+    for _ in range(prof_steps):
+        do_step(True)
+    gemm_ms, gemm_flops, gemm_launches = eng.profile_read()
+    eng.profile_enable(False)
+
+    n_tokens = sum(len(eng.tokens(int(s))) for s in sids[: min(n, 64)])
+    t = torch.tensor([dev_ms / 1e3, e2e_s, wall_resident], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_s, e2e_max, wall_max = (float(x) for x in t.tolist())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    audio_s = args.streams * args.steps * AUDIO_S_PER_STEP
+    peak_tf, peak_hbm, peak_src = load_peaks()
+    achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": audio_s / dev_s, "unit": "x real time", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == 0 else "bf16x2 (split hi+lo operands, fp32-grade)", "data": "synthetic",
+        "config": {"workload": f"{args.streams} concurrent streams sharded over {world} GPU(s) (stream i -> rank i mod N), cache-aware "
+                               "streaming chunk step (57-frame slice, cache 256, 24-frame shift) + TDT greedy decode, GPU log-mel frontend",
+                   "model": f"parakeet-tdt-0.6b-v3 architecture, seeded random weights, {args.layers} layers",
+                   "streams_per_gpu": n, "audio_s_per_step": args.streams * AUDIO_S_PER_STEP, "precision": args.precision,
+                   "l2_policy": "working set per step (1.2 GB weights + 29 MB K/V per stream) exceeds the 126 MB L2; no flush needed",
+                   "wall_ms_per_step_resident": 1e3 * wall_max / args.steps, "tokens_emitted_first_64_streams": n_tokens},
+        "clocks": clocks,
+        "e2e": {"value": audio_s / e2e_max, "unit": "x real time", "h2d_bytes_per_step": step_bytes * world,
+                "d2h_bytes_per_step": n * 97 * 4 * world},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                     "traffic": None, "kernel": "gemm_tc_kernel (tcgen05/TMA/TMEM)", "launches_timed": int(gemm_launches),
+                     "peak_source": f"{peak_src} sustained bf16 (MEASURED_PEAKS.json)"},
+    }
+    if not args.no_latency and world == 1:
+        line["latency_1stream"] = latency_one_stream(binding, model, args.precision, clips[0])
+    if not args.no_cpu_baseline and world == 1:
+        rtfx, cores, wall, a_s = cpu_path_rtfx(model, args.ref_streams, 16, 1)
+        line["cpu_baseline"] = {"value": rtfx, "unit": "x real time", "cores": cores, "kind": "port",
+                                "sample": f"{args.ref_streams} streams x 16 chunks ({a_s:.2f} s audio), {wall:.1f} s of CPU work, "
+                                          "C restatement of rust/features + PyTorch-CPU restatement of the NeMo modules (not the Rust/ORT binaries)"}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def latency_one_stream(binding, model, precision, clip):
+    """BASELINE config 2: one stream, per-chunk latency (push of 0.24 s of audio -> tokens on the host), p50 / p95."""
+    eng = binding.Engine(model, max_streams=1, precision=precision)
+    sid = np.array([eng.open()], np.int32)
+    buf = np.ascontiguousarray(clip[: 64 * SAMPLES_PER_STEP])
+    eng.push_audio_batch(sid, buf[:SAMPLES_PER_STEP].ctypes.data, SAMPLES_PER_STEP, SAMPLES_PER_STEP)
+    lat = []
+    for k in range(1, 60):
+        seg = buf[k * SAMPLES_PER_STEP:(k + 1) * SAMPLES_PER_STEP]
+        t0 = time.perf_counter()
+        eng.push_audio_batch(sid, seg.ctypes.data, SAMPLES_PER_STEP, SAMPLES_PER_STEP)
+        eng.step()
+        lat.append(1e3 * (time.perf_counter() - t0))
+    lat = np.array(lat[8:])
+    eng.close()
+    return {"p50_ms": float(np.percentile(lat, 50)), "p95_ms": float(np.percentile(lat, 95)), "chunks": int(lat.size)}
+
+
+if __name__ == "__main__":
+    main()

@@ -65,9 +65,24 @@ int32_t pkb_stream_push_features(PkbEngine* engine, int32_t stream, const float*
 int32_t pkb_stream_push_audio(PkbEngine* engine, int32_t stream, const float* pcm, size_t n);
 /* per-feature normalisation applied by the GPU frontend: (x - mean[m]) / std[m]; NULLs switch it off */
 int32_t pkb_stream_set_feature_norm(PkbEngine* engine, int32_t stream, const float* mean128, const float* std128);
+/* Batched push: `count` (<= 8192) samples for each of n streams; row i starts at pcm + i*stride floats.  Host memory
+ * (pinned memory is copied without a bounce) or, for the _device variant, device memory (e.g. audio already decoded on the
+ * GPU).  One H2D copy + one kernel for the whole batch -- the call a multi-stream server makes once per tick. */
+int32_t pkb_engine_push_audio_batch(PkbEngine* engine, int32_t n, const int32_t* streams, const float* pcm, int64_t stride,
+                                    int32_t count);
+int32_t pkb_engine_push_audio_batch_device(PkbEngine* engine, int32_t n, const int32_t* streams, const float* d_pcm,
+                                           int64_t stride, int32_t count);
 /* advance every stream with a pending chunk by one chunk; returns the number of chunks processed */
 int32_t pkb_engine_step(PkbEngine* engine);
 int32_t pkb_stream_has_pending(PkbEngine* engine, int32_t stream);
+
+/* ---- measurement hooks ---- */
+/* CUDA events recorded on the engine's own stream (device-side timing of a region of steps) */
+int32_t pkb_engine_event_record(PkbEngine* engine);                            /* -> event id */
+double pkb_engine_event_elapsed_ms(PkbEngine* engine, int32_t ev_a, int32_t ev_b);
+/* per-launch CUDA-event timing of the tcgen05 GEMM kernel: enable, run steps, read sum(ms), sum(flops), launches */
+int32_t pkb_engine_profile_enable(PkbEngine* engine, int32_t on);
+int32_t pkb_engine_profile_read(PkbEngine* engine, double* ms, double* flops, int64_t* launches);
 
 /* ---- results ---- */
 int32_t pkb_stream_num_tokens(PkbEngine* engine, int32_t stream);
@@ -77,6 +92,18 @@ int32_t pkb_stream_cache_len(PkbEngine* engine, int32_t stream);                
 int64_t pkb_stream_chunks_done(PkbEngine* engine, int32_t stream);
 int32_t pkb_stream_text(PkbEngine* engine, int32_t stream, char* out, int32_t cap);           /* detokenised transcript so far */
 int32_t pkb_detokenize(PkbEngine* engine, const int32_t* ids, int32_t n, char* out, int32_t cap);
+
+/* ---- per-stream state across the ABI (cache carry-over made explicit: checkpoint, migration, functional-mode parity) ----
+ * One stream's encoder caches in the contract layout: cache_last_channel [L,256,1024] (valid region = the last
+ * cache_len rows), cache_last_time [L,1024,4]; predictor state h,c [2,640], g [640] (+ tokens emitted so far, last token).
+ * Needs contract_cache = 1. */
+int32_t pkb_stream_import_state(PkbEngine* engine, int32_t stream, const float* cache_last_channel, const float* cache_last_time,
+                                int32_t cache_last_channel_len);
+int32_t pkb_stream_export_state(PkbEngine* engine, int32_t stream, float* cache_last_channel, float* cache_last_time,
+                                int32_t* cache_last_channel_len);
+int32_t pkb_stream_set_decoder_state(PkbEngine* engine, int32_t stream, const float* h, const float* c, const float* g,
+                                     int32_t n_emitted, int32_t y_id);
+int32_t pkb_stream_get_decoder_state(PkbEngine* engine, int32_t stream, float* h, float* c, float* g);
 
 /* ---- tensor-level calls, contract layouts, HOST pointers ---- */
 /* encoder_streaming: audio_signal [B,128,T] f32, length [B] i64 (must equal T), cache_last_channel [B,L,256,1024],

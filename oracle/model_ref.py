@@ -313,7 +313,8 @@ def prime(model: ModelRef, st: DecodeState) -> None:
 
 
 def tdt_greedy_chunk(model: ModelRef, st: DecodeState, enc_out: torch.Tensor, t_enc: int,
-                     max_symbols: int = 8, punct_suppression: bool = True) -> List[Tuple[int, int, int, int]]:
+                     max_symbols: int = 8, punct_suppression: bool = True,
+                     margins: Optional[list] = None) -> List[Tuple[int, int, int, int]]:
     """Greedy TDT over one chunk's encoder frames; mutates st.  Returns the per-step trace
     [(time_idx, best_tok, duration, advance)].  Follows parakeet_trt.cpp:2914-3676 / tdt_trace.py:277-353:
     first-max-wins argmax (strict '>'), blank+dur0 -> advance 1, non-blank -> predictor step,
@@ -331,6 +332,10 @@ def tdt_greedy_chunk(model: ModelRef, st: DecodeState, enc_out: torch.Tensor, t_
             if punct_suppression and not st.tokens and model.is_punct_only(tok):
                 tok = model.blank
             d = dur_values[int(torch.argmax(logits[V:V + model.n_dur]))]
+            if margins is not None:     # top-2 gaps of both heads: how far this decision is from flipping
+                t2 = torch.topk(logits[:V], 2).values
+                d2 = torch.topk(logits[V:V + model.n_dur], 2).values
+                margins.append((float(t2[0] - t2[1]), float(d2[0] - d2[1])))
             adv = 1 if (tok == model.blank and d == 0) else d
             trace.append((t, tok, d, adv))
             if tok != model.blank:

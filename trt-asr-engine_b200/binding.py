@@ -26,9 +26,12 @@ TRT_ASR_SYMBOLS = ["trt_asr_create_session", "trt_asr_destroy_session", "trt_asr
                    "trt_asr_push_features_f32", "trt_asr_poll_event"]
 B200_SYMBOLS = ["pkb_last_error", "pkb_version", "pkb_engine_create", "pkb_engine_destroy", "pkb_engine_num_layers",
                 "pkb_engine_kernel_launches", "pkb_stream_open", "pkb_stream_close", "pkb_stream_reset", "pkb_stream_push_features",
-                "pkb_stream_push_audio", "pkb_stream_set_feature_norm", "pkb_engine_step", "pkb_stream_has_pending",
+                "pkb_stream_push_audio", "pkb_stream_set_feature_norm", "pkb_engine_push_audio_batch",
+                "pkb_engine_push_audio_batch_device", "pkb_engine_event_record", "pkb_engine_event_elapsed_ms",
+                "pkb_engine_profile_enable", "pkb_engine_profile_read", "pkb_engine_step", "pkb_stream_has_pending",
                 "pkb_stream_num_tokens", "pkb_stream_tokens", "pkb_stream_last_steps", "pkb_stream_cache_len",
-                "pkb_stream_chunks_done", "pkb_stream_text", "pkb_detokenize", "pkb_encoder_streaming_step", "pkb_predictor_step",
+                "pkb_stream_chunks_done", "pkb_stream_text", "pkb_detokenize", "pkb_stream_import_state", "pkb_stream_export_state",
+                "pkb_stream_set_decoder_state", "pkb_stream_get_decoder_state", "pkb_encoder_streaming_step", "pkb_predictor_step",
                 "pkb_joint_step", "pkb_logmel", "pkb_gemm_test"]
 
 
@@ -108,10 +111,21 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.pkb_stream_push_features.argtypes = [vp, C.c_int32, fp, C.c_int32]
     lib.pkb_stream_push_audio.argtypes = [vp, C.c_int32, fp, C.c_size_t]
     lib.pkb_stream_set_feature_norm.argtypes = [vp, C.c_int32, fp, fp]
+    lib.pkb_engine_push_audio_batch.argtypes = [vp, C.c_int32, ip, C.c_void_p, C.c_int64, C.c_int32]
+    lib.pkb_engine_push_audio_batch_device.argtypes = [vp, C.c_int32, ip, C.c_void_p, C.c_int64, C.c_int32]
+    lib.pkb_engine_event_record.argtypes = [vp]
+    lib.pkb_engine_event_elapsed_ms.argtypes = [vp, C.c_int32, C.c_int32]
+    lib.pkb_engine_event_elapsed_ms.restype = C.c_double
+    lib.pkb_engine_profile_enable.argtypes = [vp, C.c_int32]
+    lib.pkb_engine_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), lp]
     lib.pkb_stream_tokens.argtypes = [vp, C.c_int32, ip, C.c_int32]
     lib.pkb_stream_last_steps.argtypes = [vp, C.c_int32, C.POINTER(PkbStep), C.c_int32]
     lib.pkb_stream_text.argtypes = [vp, C.c_int32, C.c_char_p, C.c_int32]
     lib.pkb_detokenize.argtypes = [vp, ip, C.c_int32, C.c_char_p, C.c_int32]
+    lib.pkb_stream_import_state.argtypes = [vp, C.c_int32, fp, fp, C.c_int32]
+    lib.pkb_stream_export_state.argtypes = [vp, C.c_int32, fp, fp, ip]
+    lib.pkb_stream_set_decoder_state.argtypes = [vp, C.c_int32, fp, fp, fp, C.c_int32, C.c_int32]
+    lib.pkb_stream_get_decoder_state.argtypes = [vp, C.c_int32, fp, fp, fp]
     lib.pkb_encoder_streaming_step.argtypes = [vp, C.c_int32, C.c_int32, fp, lp, fp, fp, lp, fp, lp, fp, fp, lp]
     lib.pkb_predictor_step.argtypes = [vp, C.c_int32, lp, fp, fp, fp, fp, fp]
     lib.pkb_joint_step.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, fp, fp, fp]
@@ -243,6 +257,29 @@ class Engine:
             m, d = np.ascontiguousarray(mean, np.float32), np.ascontiguousarray(std, np.float32)
             self._chk(self._lib.pkb_stream_set_feature_norm(self._e, s, _fptr(m), _fptr(d)))
 
+    def push_audio_batch(self, sids: np.ndarray, host_ptr: int, stride: int, count: int):
+        """sids int32 array; host_ptr = address of row 0 (e.g. tensor.data_ptr() of pinned memory)."""
+        self._chk(self._lib.pkb_engine_push_audio_batch(self._e, sids.size, sids.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                        C.c_void_p(host_ptr), stride, count))
+
+    def push_audio_batch_device(self, sids: np.ndarray, dev_ptr: int, stride: int, count: int):
+        self._chk(self._lib.pkb_engine_push_audio_batch_device(self._e, sids.size, sids.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                               C.c_void_p(dev_ptr), stride, count))
+
+    def event_record(self) -> int:
+        return self._chk(self._lib.pkb_engine_event_record(self._e))
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        return float(self._lib.pkb_engine_event_elapsed_ms(self._e, a, b))
+
+    def profile_enable(self, on: bool):
+        self._chk(self._lib.pkb_engine_profile_enable(self._e, int(on)))
+
+    def profile_read(self):
+        ms, fl, n = C.c_double(), C.c_double(), C.c_int64()
+        self._chk(self._lib.pkb_engine_profile_read(self._e, C.byref(ms), C.byref(fl), C.byref(n)))
+        return ms.value, fl.value, n.value
+
     def step(self) -> int:
         return self._chk(self._lib.pkb_engine_step(self._e))
 
@@ -279,6 +316,28 @@ class Engine:
 
     def kernel_launches(self) -> int:
         return int(self._lib.pkb_engine_kernel_launches(self._e))
+
+    # per-stream state across the ABI
+    def import_state(self, s: int, cache_ch: np.ndarray, cache_tm: np.ndarray, cache_len: int):
+        cc, ct = np.ascontiguousarray(cache_ch, np.float32), np.ascontiguousarray(cache_tm, np.float32)
+        assert cc.shape == (self.n_layers, 256, 1024) and ct.shape == (self.n_layers, 1024, 4)
+        self._chk(self._lib.pkb_stream_import_state(self._e, s, _fptr(cc), _fptr(ct), int(cache_len)))
+
+    def export_state(self, s: int):
+        cc, ct = np.zeros((self.n_layers, 256, 1024), np.float32), np.zeros((self.n_layers, 1024, 4), np.float32)
+        ln = C.c_int32()
+        self._chk(self._lib.pkb_stream_export_state(self._e, s, _fptr(cc), _fptr(ct), C.byref(ln)))
+        return cc, ct, ln.value
+
+    def set_decoder_state(self, s: int, h: np.ndarray, c: np.ndarray, g: np.ndarray, n_emitted: int, y_id: int):
+        h, c, g = (np.ascontiguousarray(a, np.float32) for a in (h, c, g))
+        assert h.size == 1280 and c.size == 1280 and g.size == 640
+        self._chk(self._lib.pkb_stream_set_decoder_state(self._e, s, _fptr(h), _fptr(c), _fptr(g), n_emitted, y_id))
+
+    def get_decoder_state(self, s: int):
+        h, c, g = np.zeros((2, 640), np.float32), np.zeros((2, 640), np.float32), np.zeros(640, np.float32)
+        self._chk(self._lib.pkb_stream_get_decoder_state(self._e, s, _fptr(h), _fptr(c), _fptr(g)))
+        return h, c, g
 
     # tensor-level calls (contract layouts)
     def encoder_streaming_step(self, audio_signal, length, cache_last_channel, cache_last_time, cache_last_channel_len):

@@ -329,6 +329,28 @@ int32_t pkb_stream_set_feature_norm(PkbEngine* e, int32_t s, const float* mean12
   PKB_ENTER(e);
   return guarded([&] { e->eng->set_feature_norm(s, mean128, std128); return 0; });
 }
+int32_t pkb_engine_push_audio_batch(PkbEngine* e, int32_t n, const int32_t* sids, const float* pcm, int64_t stride, int32_t count) {
+  PKB_ENTER(e);
+  if (!sids || (!pcm && n * count)) { g_last_error = "null argument"; return -1; }
+  return guarded([&] { e->eng->push_audio_batch(n, sids, pcm, stride, count, false); return 0; });
+}
+int32_t pkb_engine_push_audio_batch_device(PkbEngine* e, int32_t n, const int32_t* sids, const float* d_pcm, int64_t stride,
+                                           int32_t count) {
+  PKB_ENTER(e);
+  if (!sids || (!d_pcm && n * count)) { g_last_error = "null argument"; return -1; }
+  return guarded([&] { e->eng->push_audio_batch(n, sids, d_pcm, stride, count, true); return 0; });
+}
+int32_t pkb_engine_event_record(PkbEngine* e) { PKB_ENTER(e); return guarded([&] { return e->eng->event_record(); }); }
+double pkb_engine_event_elapsed_ms(PkbEngine* e, int32_t a, int32_t b) {
+  if (!e) return -1.0;
+  std::lock_guard<std::mutex> lock(e->mu);
+  try { return e->eng->event_elapsed_ms(a, b); } catch (const std::exception& ex) { g_last_error = ex.what(); return -1.0; }
+}
+int32_t pkb_engine_profile_enable(PkbEngine* e, int32_t on) { PKB_ENTER(e); return guarded([&] { e->eng->profile_enable(on != 0); return 0; }); }
+int32_t pkb_engine_profile_read(PkbEngine* e, double* ms, double* flops, int64_t* launches) {
+  PKB_ENTER(e);
+  return guarded([&] { long long l = 0; e->eng->profile_read(ms, flops, &l); *launches = l; return 0; });
+}
 int32_t pkb_engine_step(PkbEngine* e) { PKB_ENTER(e); return guarded([&] { return e->eng->step(); }); }
 int32_t pkb_stream_has_pending(PkbEngine* e, int32_t s) { PKB_ENTER(e); return guarded([&] { return e->eng->has_pending(s) ? 1 : 0; }); }
 int32_t pkb_stream_num_tokens(PkbEngine* e, int32_t s) { PKB_ENTER(e); return guarded([&] { return (int)e->eng->tokens(s).size(); }); }
@@ -369,6 +391,26 @@ int32_t pkb_stream_text(PkbEngine* e, int32_t s, char* out, int32_t cap) {
 int32_t pkb_detokenize(PkbEngine* e, const int32_t* ids, int32_t n, char* out, int32_t cap) {
   PKB_ENTER(e);
   return guarded([&] { return copy_text(e->eng->detokenize(std::vector<int>(ids, ids + n)), out, cap); });
+}
+int32_t pkb_stream_import_state(PkbEngine* e, int32_t s, const float* cc, const float* ct, int32_t len) {
+  PKB_ENTER(e);
+  if (!cc || !ct) { g_last_error = "null argument"; return -1; }
+  return guarded([&] { e->eng->import_stream_state(s, cc, ct, len); return 0; });
+}
+int32_t pkb_stream_export_state(PkbEngine* e, int32_t s, float* cc, float* ct, int32_t* len) {
+  PKB_ENTER(e);
+  if (!cc || !ct || !len) { g_last_error = "null argument"; return -1; }
+  return guarded([&] { int l = 0; e->eng->export_stream_state(s, cc, ct, &l); *len = l; return 0; });
+}
+int32_t pkb_stream_set_decoder_state(PkbEngine* e, int32_t s, const float* h, const float* c, const float* g, int32_t n_emitted, int32_t y_id) {
+  PKB_ENTER(e);
+  if (!h || !c || !g) { g_last_error = "null argument"; return -1; }
+  return guarded([&] { e->eng->set_decoder_state(s, h, c, g, n_emitted, y_id); return 0; });
+}
+int32_t pkb_stream_get_decoder_state(PkbEngine* e, int32_t s, float* h, float* c, float* g) {
+  PKB_ENTER(e);
+  if (!h || !c || !g) { g_last_error = "null argument"; return -1; }
+  return guarded([&] { e->eng->get_decoder_state(s, h, c, g); return 0; });
 }
 int32_t pkb_encoder_streaming_step(PkbEngine* e, int32_t B, int32_t T, const float* audio_signal, const int64_t* length,
                                    const float* cc, const float* ct, const int64_t* cl, float* enc_out, int64_t* enc_len, float* cc_out,

@@ -22,7 +22,12 @@ T* dev_alloc(size_t n) {
 template <typename T>
 T* dev_upload(const std::vector<T>& v) {
   T* p = dev_alloc<T>(v.size());
-  if (!v.empty()) PKB_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  if (!v.empty()) {
+    // cudaMemcpy from pageable memory returns once the data is STAGED; the DMA may still be in flight, and the engine's
+    // non-blocking stream is not ordered against it -- so wait for the device before anyone can consume the buffer.
+    PKB_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    PKB_CUDA(cudaDeviceSynchronize());
+  }
   return p;
 }
 
@@ -80,6 +85,26 @@ __global__ void fill_import_rows_kernel(int* row_entry, int* row_pos, int n_rows
   row_pos[i] = (i % kCacheS) - kCacheS;   // logical cache position j -> ring index head + 256 + (j - 256)
 }
 
+// dst[slot][off + k] = src[i*stride + k]
+__global__ void audio_append_kernel(const float* __restrict__ src, long long stride, float* __restrict__ audio_buf,
+                                    const int* __restrict__ slot, const int* __restrict__ off, const int* __restrict__ cnt) {
+  const int i = blockIdx.y;
+  const int n = cnt[i];
+  float* d = audio_buf + (size_t)slot[i] * 32768 + off[i];
+  const float* s = src + (size_t)i * stride;
+  for (int k = blockIdx.x * 1024 + threadIdx.x; k < min(n, (int)(blockIdx.x + 1) * 1024); k += 256) d[k] = s[k];
+}
+// phase 0: tmp[slot][k] = buf[slot][off + k];  phase 1: buf[slot][k] = tmp[slot][k]   (k < fill)
+__global__ void audio_move_kernel(float* __restrict__ buf, float* __restrict__ tmp, const int* __restrict__ slot,
+                                  const int* __restrict__ off, const int* __restrict__ fill, int phase) {
+  const int i = blockIdx.y;
+  const size_t base = (size_t)slot[i] * 32768;
+  const int n = fill[i], o = off[i];
+  for (int k = blockIdx.x * 1024 + threadIdx.x; k < min(n, (int)(blockIdx.x + 1) * 1024); k += 256) {
+    if (phase == 0) tmp[base + k] = buf[base + o + k]; else buf[base + k] = tmp[base + k];
+  }
+}
+
 bool is_special_piece(const std::string& s) {
   if (s == "<blank>" || s == "<pad>" || s == "<unk>") return true;
   return !s.empty() && s.front() == '<' && s.back() == '>';
@@ -110,7 +135,10 @@ struct Engine::Stream {
   long long frames_written = 0;          // frames ever written to the feature ring
   std::deque<Entry> pending;             // explicit chunks (legacy ABI granularity)
   bool audio_mode = false;
-  std::vector<float> audio;              // samples not yet turned into frames
+  std::vector<float> audio;              // host overflow FIFO: samples that did not fit the device audio buffer yet
+  bool needs_prime = false;              // predictor priming is deferred to the next batched pass (one launch set for all)
+  int dev_off = 0;                       // first valid sample inside this stream's device audio buffer (always even)
+  int dev_fill = 0;                      // valid samples from dev_off
   long long sched_chunk = 0;             // index of the next scheduled chunk (audio mode)
   bool has_norm = false;
   int cache_len = 0;
@@ -141,7 +169,7 @@ struct Engine::Impl {
   int *n_emitted = nullptr, *y_id = nullptr;
   // work buffers
   int Mcap = 0, Bcap = 0, T3cap = 0, T2cap = 0;
-  ActBuf a_sub1, a_sub2, a_sub3, a_ln, a_ff, a_hid, a_pred, a_g, a_imp, a_pos;
+  ActBuf a_sub1, a_sub2, a_sub3, a_ln, a_ff, a_xf, a_hid, a_pred, a_g, a_imp, a_pos;
   float *x = nullptr, *q = nullptr, *cglu = nullptr, *y1 = nullptr, *enc_proj = nullptr, *logits = nullptr, *gates = nullptr,
         *enc_out = nullptr, *ppos_tmp = nullptr, *scratch_f32 = nullptr;
   size_t scratch_f32_elems = 0;
@@ -155,9 +183,21 @@ struct Engine::Impl {
   int* res_host = nullptr;               // pinned: [Bcap] n_steps + [Bcap*32*3] steps
   int* counters_host = nullptr;          // pinned [2]
   // frontend staging
-  float* audio_dev = nullptr;
-  float* audio_host = nullptr;           // pinned
-  size_t audio_cap = 0;
+  float* audio_buf = nullptr;            // [slots][kAudioCap] per-stream device audio (carry + not yet framed samples)
+  float* audio_tmp = nullptr;            // [slots][kAudioCap] compaction scratch
+  float* audio_stage = nullptr;          // device staging for batched pushes from host memory
+  float* audio_stage_host = nullptr;     // pinned bounce buffer for pageable sources
+  size_t audio_stage_cap = 0;
+  int* push_meta = nullptr;              // device [3][Bcap]: slot, dst offset, count
+  int* push_meta_host = nullptr;         // pinned
+  std::vector<cudaEvent_t> user_events;
+  // optional per-launch timing of the tensor-core GEMM (bench roofline)
+  bool profile = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  std::vector<double> prof_flops;
+  size_t prof_used = 0;
+  double prof_ms = 0, prof_flops_sum = 0;
+  long long prof_launches = 0;
   FrontSegment* segs_dev = nullptr;
   FrontSegment* segs_host = nullptr;
   int* fprefix_dev = nullptr;
@@ -167,7 +207,7 @@ struct Engine::Impl {
 };
 
 constexpr int kFeatRing = 512;           // frames kept per stream (5.12 s)
-constexpr int kFramesPerPass = 64;       // frontend frames per stream per step (bounds the pinned audio staging)
+constexpr int kAudioCap = 32768;         // samples per stream resident on the device (2 s)
 constexpr int kNumBatchFields = 11;
 
 // ================================================================================================
@@ -206,6 +246,7 @@ Engine::Engine(const EngineOptions& opt) : opt_(opt) {
     streams_[i]->slot = i;
   }
   PKB_CUDA(cudaStreamSynchronize(st_));
+  PKB_CUDA(cudaDeviceSynchronize());   // init-time uploads went through the legacy stream (staged pageable copies)
 }
 
 Engine::~Engine() {
@@ -218,6 +259,43 @@ Engine::~Engine() {
 }
 
 void Engine::synchronize() { PKB_CUDA(cudaStreamSynchronize(st_)); }
+Engine::Impl* Engine::impl() { return im_.get(); }
+
+int Engine::event_record() {
+  cudaEvent_t e;
+  PKB_CUDA(cudaEventCreate(&e));
+  PKB_CUDA(cudaEventRecord(e, st_));
+  im_->user_events.push_back(e);
+  return (int)im_->user_events.size() - 1;
+}
+double Engine::event_elapsed_ms(int a, int b) {
+  PKB_CHECK(a >= 0 && b >= 0 && a < (int)im_->user_events.size() && b < (int)im_->user_events.size(), "bad event id");
+  PKB_CUDA(cudaEventSynchronize(im_->user_events[b]));
+  float ms = 0;
+  PKB_CUDA(cudaEventElapsedTime(&ms, im_->user_events[a], im_->user_events[b]));
+  return ms;
+}
+void Engine::profile_enable(bool on) {
+  PKB_CUDA(cudaStreamSynchronize(st_));
+  im_->profile = on;
+  im_->prof_used = 0;
+  im_->prof_ms = im_->prof_flops_sum = 0;
+  im_->prof_launches = 0;
+}
+void Engine::profile_collect() {      // call after a synchronised step
+  Impl& im = *im_;
+  for (size_t i = 0; i < im.prof_used; ++i) {
+    float ms = 0;
+    PKB_CUDA(cudaEventElapsedTime(&ms, im.prof_events[i].first, im.prof_events[i].second));
+    im.prof_ms += ms;
+    im.prof_flops_sum += im.prof_flops[i];
+    im.prof_launches += 1;
+  }
+  im.prof_used = 0;
+}
+void Engine::profile_read(double* ms, double* flops, long long* launches) {
+  *ms = im_->prof_ms; *flops = im_->prof_flops_sum; *launches = im_->prof_launches;
+}
 
 // ------------------------------------------------------------------------------------------------ weights
 static GemmW upload_gemm_w(const std::vector<uint16_t>& bits, int N, int K) {
@@ -405,9 +483,12 @@ void Engine::alloc_state() {
   im.a_sub3 = make_act(im.T3cap, 16 * kSubCh, split, st_);
   im.a_ln = make_act(std::max(im.Mcap, rows_dec), kDModel, split, st_);
   im.a_ff = make_act(im.Mcap, kFF, split, st_);
-  im.a_hid = make_act(rows_dec, kJointH, split, st_);
-  im.a_pred = make_act(rows_dec, 2 * kPredH, split, st_);
-  im.a_g = make_act(rows_dec, kPredH, split, st_);
+  // the decode side (joint / predictor) always runs on split hi+lo operands: it is a few percent of the step's FLOPs and
+  // keeps the logits fp32-grade, so bf16 mode differs from the oracle only through the encoder output
+  im.a_xf = make_act(std::max(im.Mcap, rows_dec), kDModel, true, st_);
+  im.a_hid = make_act(rows_dec, kJointH, true, st_);
+  im.a_pred = make_act(rows_dec, 2 * kPredH, true, st_);
+  im.a_g = make_act(rows_dec, kPredH, true, st_);
   im.a_imp = make_act(kCacheS, kDModel, split, st_);
   im.a_pos = make_act(kPosRows, kDModel, true, st_);
   im.x = dev_alloc<float>((size_t)im.Mcap * kDModel);
@@ -438,10 +519,14 @@ void Engine::alloc_state() {
   im.force_toks = dev_alloc<int>(im.Bcap);
   PKB_CUDA(cudaMallocHost(&im.res_host, (size_t)im.Bcap * (1 + kMaxStepsPerChunk * 3) * sizeof(int)));
   PKB_CUDA(cudaMallocHost(&im.counters_host, 2 * sizeof(int)));
-  // frontend staging: up to kFeatRing frames of audio per stream per pass
-  im.audio_cap = (size_t)im.Bcap * (kFramesPerPass * 160 + 400 + 2) + 1024;
-  im.audio_dev = dev_alloc<float>(im.audio_cap);
-  PKB_CUDA(cudaMallocHost(&im.audio_host, im.audio_cap * sizeof(float)));
+  // audio: per-stream device buffers + one staging area for batched host pushes (8192 samples per stream per push)
+  im.audio_buf = dev_alloc<float>((size_t)S * kAudioCap);
+  im.audio_tmp = dev_alloc<float>((size_t)S * kAudioCap);
+  im.audio_stage_cap = (size_t)im.Bcap * 8192;
+  im.audio_stage = dev_alloc<float>(im.audio_stage_cap);
+  PKB_CUDA(cudaMallocHost(&im.audio_stage_host, im.audio_stage_cap * sizeof(float)));
+  im.push_meta = dev_alloc<int>((size_t)3 * im.Bcap);
+  PKB_CUDA(cudaMallocHost(&im.push_meta_host, (size_t)3 * im.Bcap * sizeof(int)));
   im.segs_dev = dev_alloc<FrontSegment>(im.Bcap);
   PKB_CUDA(cudaMallocHost(&im.segs_host, (size_t)im.Bcap * sizeof(FrontSegment)));
   im.fprefix_dev = dev_alloc<int>(im.Bcap + 1);
@@ -502,6 +587,7 @@ void Engine::reset_stream(int sid) {
   Stream& s = *streams_[sid];
   Impl& im = *im_;
   s.frames_written = 0; s.pending.clear(); s.audio.clear(); s.audio_mode = false; s.sched_chunk = 0; s.has_norm = false;
+  s.dev_off = 0; s.dev_fill = 0;
   s.cache_len = 0; s.head = 0; s.chunks = 0; s.tokens.clear(); s.last = ChunkResult();
   const size_t slot = (size_t)s.slot;
   PKB_CUDA(cudaMemsetAsync(im.cache_tm + slot * L_ * kDModel * kTimeCtx, 0, (size_t)L_ * kDModel * kTimeCtx * 4, st_));
@@ -509,12 +595,12 @@ void Engine::reset_stream(int sid) {
   PKB_CUDA(cudaMemsetAsync(im.pred_c + slot * kPredL * kPredH, 0, kPredL * kPredH * 4, st_));
   PKB_CUDA(cudaMemsetAsync(im.pred_g + slot * kPredH, 0, kPredH * 4, st_));
   PKB_CUDA(cudaMemsetAsync(im.n_emitted + slot, 0, 4, st_));
-  prime_streams({sid});
+  s.needs_prime = true;     // primed (batched with every other freshly reset stream) right before its first decode
 }
 
 bool Engine::has_pending(int sid) const {
   const Stream& s = *streams_[sid];
-  return s.open && (!s.pending.empty() || !s.audio.empty());
+  return s.open && (!s.pending.empty() || !s.audio.empty() || s.dev_fill >= 400);
 }
 const std::vector<int>& Engine::tokens(int sid) const { return streams_[sid]->tokens; }
 const ChunkResult& Engine::last_chunk(int sid) const { return streams_[sid]->last; }
@@ -563,7 +649,83 @@ void Engine::queue_audio(int sid, const float* pcm, size_t n) {
   Stream& s = *streams_[sid];
   PKB_CHECK(s.audio_mode || s.frames_written == 0, "stream already received features; reset it before pushing audio");
   s.audio_mode = true;
-  s.audio.insert(s.audio.end(), pcm, pcm + n);
+  s.audio.insert(s.audio.end(), pcm, pcm + n);     // moved to the device buffer by step() as room allows
+}
+
+// Batched push: `count` samples for each of n streams, source row i at src + i*stride (host or device memory).
+// One H2D copy (host source) + one append kernel, no per-stream host work beyond bookkeeping.
+void Engine::push_audio_batch(int n, const int* sids, const float* src, long long stride, int count, bool src_on_device,
+                              bool internal) {
+  Impl& im = *im_;
+  PKB_CHECK(n >= 0 && n <= im.Bcap && count >= 0 && count <= 8192, "push_audio_batch: n <= max_streams, count <= 8192");
+  if (n == 0 || count == 0) return;
+  PKB_CUDA(cudaStreamSynchronize(st_));     // push_meta_host / staging reuse
+  bool need_compact = false;
+  for (int i = 0; i < n; ++i) {
+    PKB_CHECK(sids[i] >= 0 && sids[i] < (int)streams_.size() && streams_[sids[i]]->open, "bad stream id");
+    Stream& s = *streams_[sids[i]];
+    PKB_CHECK(s.audio_mode || s.frames_written == 0, "stream already received features; reset it before pushing audio");
+    PKB_CHECK(internal || s.audio.empty(), "push_audio_batch: stream has host-queued audio pending; call step() first");
+    PKB_CHECK(s.dev_fill + count <= kAudioCap, "device audio buffer full: call step() before pushing more");
+    if (s.dev_off + s.dev_fill + count > kAudioCap) need_compact = true;
+  }
+  if (need_compact) compact_audio();
+  const float* dsrc = src;
+  long long dstride = stride;
+  if (!src_on_device) {
+    PKB_CHECK((size_t)n * count <= im.audio_stage_cap, "push_audio_batch: staging too small");
+    cudaPointerAttributes at{};
+    const bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (stride == count) {
+      const float* h = src;
+      if (!pinned) { memcpy(im.audio_stage_host, src, (size_t)n * count * 4); h = im.audio_stage_host; }
+      PKB_CUDA(cudaMemcpyAsync(im.audio_stage, h, (size_t)n * count * 4, cudaMemcpyHostToDevice, st_));
+    } else {
+      for (int i = 0; i < n; ++i) memcpy(im.audio_stage_host + (size_t)i * count, src + (size_t)i * stride, (size_t)count * 4);
+      PKB_CUDA(cudaMemcpyAsync(im.audio_stage, im.audio_stage_host, (size_t)n * count * 4, cudaMemcpyHostToDevice, st_));
+    }
+    dsrc = im.audio_stage;
+    dstride = count;
+  }
+  int* h = im.push_meta_host;
+  for (int i = 0; i < n; ++i) {
+    Stream& s = *streams_[sids[i]];
+    h[i] = s.slot;
+    h[im.Bcap + i] = s.dev_off + s.dev_fill;
+    h[2 * im.Bcap + i] = count;
+    s.dev_fill += count;
+    s.audio_mode = true;
+  }
+  PKB_CUDA(cudaMemcpyAsync(im.push_meta, h, (size_t)3 * im.Bcap * sizeof(int), cudaMemcpyHostToDevice, st_));
+  audio_append_kernel<<<dim3((count + 1023) / 1024, n), 256, 0, st_>>>(dsrc, dstride, im.audio_buf, im.push_meta, im.push_meta + im.Bcap,
+                                                                       im.push_meta + 2 * im.Bcap);
+  PKB_CUDA(cudaGetLastError());
+  ++launches_;
+}
+
+// move every stream's valid samples to the front of its device buffer (through a scratch copy: ranges may overlap)
+void Engine::compact_audio() {
+  Impl& im = *im_;
+  PKB_CUDA(cudaStreamSynchronize(st_));
+  int* h = im.push_meta_host;
+  int n = 0;
+  for (auto& sp : streams_) {
+    Stream& s = *sp;
+    if (!s.open || s.dev_off == 0) continue;
+    h[n] = s.slot; h[im.Bcap + n] = s.dev_off; h[2 * im.Bcap + n] = s.dev_fill;
+    s.dev_off = 0;
+    ++n;
+  }
+  if (n == 0) return;
+  PKB_CUDA(cudaMemcpyAsync(im.push_meta, h, (size_t)3 * im.Bcap * sizeof(int), cudaMemcpyHostToDevice, st_));
+  audio_move_kernel<<<dim3(kAudioCap / 1024, n), 256, 0, st_>>>(im.audio_buf, im.audio_tmp, im.push_meta, im.push_meta + im.Bcap,
+                                                                im.push_meta + 2 * im.Bcap, 0);
+  audio_move_kernel<<<dim3(kAudioCap / 1024, n), 256, 0, st_>>>(im.audio_buf, im.audio_tmp, im.push_meta, im.push_meta + im.Bcap,
+                                                                im.push_meta + 2 * im.Bcap, 1);
+  PKB_CUDA(cudaGetLastError());
+  launches_ += 2;
+  PKB_CUDA(cudaStreamSynchronize(st_));
 }
 
 void Engine::set_feature_norm(int sid, const float* mean128, const float* std128) {
@@ -573,31 +735,41 @@ void Engine::set_feature_norm(int sid, const float* mean128, const float* std128
   float* dst = im_->norm_stats + (size_t)s.slot * 2 * kNMels;
   PKB_CUDA(cudaMemcpy(dst, mean128, kNMels * 4, cudaMemcpyHostToDevice));
   PKB_CUDA(cudaMemcpy(dst + kNMels, std128, kNMels * 4, cudaMemcpyHostToDevice));
+  PKB_CUDA(cudaDeviceSynchronize());   // pageable H2D: staged != landed (see dev_upload)
   s.has_norm = true;
 }
 
-// audio -> feature rings for every stream in audio mode (one launch), then cut chunks by the schedule
+// audio -> feature rings for every stream in audio mode (one launch); chunks are then cut by the schedule in step()
 void Engine::frontend_pass() {
   Impl& im = *im_;
+  // 1. top up device buffers from host overflow FIFOs (queue_audio path)
+  for (int sid = 0; sid < (int)streams_.size(); ++sid) {
+    Stream& s = *streams_[sid];
+    if (!s.open || s.audio.empty()) continue;
+    if (s.dev_off + s.dev_fill + 4096 > kAudioCap && s.dev_off > 0) compact_audio();
+    const int room = kAudioCap - (s.dev_off + s.dev_fill);
+    const int n = (int)std::min<size_t>(std::min<size_t>(s.audio.size(), (size_t)room), 8192);
+    if (n <= 0) continue;
+    std::vector<float> part(s.audio.begin(), s.audio.begin() + n);
+    s.audio.erase(s.audio.begin(), s.audio.begin() + n);
+    const int one = sid;
+    push_audio_batch(1, &one, part.data(), n, n, false, true);
+  }
+  // 2. one log-mel launch over every stream that holds at least one complete frame and has ring room
   int n_segs = 0, total_frames = 0;
-  size_t apos = 0;
   std::vector<std::pair<int, int>> done;   // (sid, frames)
   for (int sid = 0; sid < (int)streams_.size(); ++sid) {
     Stream& s = *streams_[sid];
-    if (!s.open || !s.audio_mode || s.audio.size() < 400) continue;
-    int frames = (int)((s.audio.size() - 400) / 160 + 1);
-    // do not overrun the ring: frames not yet consumed by the schedule must stay resident
+    if (!s.open || !s.audio_mode || s.dev_fill < 400) continue;
+    int frames = (s.dev_fill - 400) / 160 + 1;
+    // frames not yet consumed by the schedule must stay resident in the feature ring
     const long long next_start = s.sched_chunk == 0 ? 0 : 17 + 24 * (s.sched_chunk - 1);
     const long long keep_from = std::max(0LL, next_start - 9);
     const long long room = kFeatRing - (s.frames_written - keep_from);
     if (room <= 0) continue;
-    frames = (int)std::min<long long>(std::min(frames, kFramesPerPass), room);
-    const size_t nsamp = (size_t)(frames - 1) * 160 + 400;
-    if (apos & 1) ++apos;
-    PKB_CHECK(apos + nsamp <= im.audio_cap, "audio staging overflow");
-    memcpy(im.audio_host + apos, s.audio.data(), nsamp * sizeof(float));
+    frames = (int)std::min<long long>(frames, room);
     FrontSegment& sg = im.segs_host[n_segs];
-    sg.audio_off = (long long)apos;
+    sg.audio_off = (long long)s.slot * kAudioCap + s.dev_off;
     sg.out_off = (long long)s.slot * kFeatRing * kNMels;
     sg.out_stride = kNMels;
     sg.ring_cap = kFeatRing;
@@ -605,23 +777,24 @@ void Engine::frontend_pass() {
     sg.norm_off = s.has_norm ? s.slot * 2 * kNMels : -1;
     im.fprefix_host[n_segs] = total_frames;
     total_frames += frames;
-    apos += nsamp;
     ++n_segs;
     done.emplace_back(sid, frames);
   }
   if (n_segs == 0) return;
   im.fprefix_host[n_segs] = total_frames;
-  PKB_CUDA(cudaMemcpyAsync(im.audio_dev, im.audio_host, apos * sizeof(float), cudaMemcpyHostToDevice, st_));
   PKB_CUDA(cudaMemcpyAsync(im.segs_dev, im.segs_host, n_segs * sizeof(FrontSegment), cudaMemcpyHostToDevice, st_));
   PKB_CUDA(cudaMemcpyAsync(im.fprefix_dev, im.fprefix_host, (n_segs + 1) * sizeof(int), cudaMemcpyHostToDevice, st_));
-  im.frontend.logmel(im.audio_dev, im.segs_dev, im.fprefix_dev, n_segs, total_frames, im.feat_ring, im.norm_stats, sm_count_, st_);
+  im.frontend.logmel(im.audio_buf, im.segs_dev, im.fprefix_dev, n_segs, total_frames, im.feat_ring, im.norm_stats, sm_count_, st_);
   ++launches_;
-  PKB_CUDA(cudaStreamSynchronize(st_));    // staging is reused by the next pass
   for (auto& d : done) {
     Stream& s = *streams_[d.first];
-    s.audio.erase(s.audio.begin(), s.audio.begin() + (size_t)d.second * 160);
+    s.dev_off += d.second * 160;     // stays even
+    s.dev_fill -= d.second * 160;
     s.frames_written += d.second;
   }
+  // segs_host / fprefix_host are rewritten only by the next frontend_pass, which run_batch's final sync precedes;
+  // when no chunk follows, sync here
+  PKB_CUDA(cudaStreamSynchronize(st_));
 }
 
 // ------------------------------------------------------------------------------------------------ batching
@@ -691,8 +864,28 @@ static void run_gemm(Engine* eng, const EngineOptions& opt, cudaStream_t st, lon
   ++*launches;
   bool want_tc = opt.gemm_backend == 2 || (opt.gemm_backend == 0 && M > 16);
   if (tc_mask() >= 0 && !(tc_mask() & g_tc_site)) want_tc = false;
-  if (want_tc && lda_override <= 0 && gemm_tc_supported(g)) gemm_tc(g, a.map, w.map, st);
-  else gemm_simt(g, st);
+  if (want_tc && lda_override <= 0 && gemm_tc_supported(g)) {
+    Engine::Impl* im = eng->impl();
+    if (im->profile) {
+      if (im->prof_used == im->prof_events.size()) {
+        cudaEvent_t a0, a1;
+        PKB_CUDA(cudaEventCreate(&a0));
+        PKB_CUDA(cudaEventCreate(&a1));
+        im->prof_events.emplace_back(a0, a1);
+        im->prof_flops.push_back(0.0);
+      }
+      auto& ev = im->prof_events[im->prof_used];
+      im->prof_flops[im->prof_used] = 2.0 * (double)M * w.N * w.K;   // ALGORITHMIC flops (the split pass is not counted twice)
+      ++im->prof_used;
+      PKB_CUDA(cudaEventRecord(ev.first, st));
+      gemm_tc(g, a.map, w.map, st);
+      PKB_CUDA(cudaEventRecord(ev.second, st));
+    } else {
+      gemm_tc(g, a.map, w.map, st);
+    }
+  } else {
+    gemm_simt(g, st);
+  }
 }
 #define RUN_GEMM(a, w, M, Mdev, epi) run_gemm(this, opt_, st_, &launches_, a, 0, w, M, Mdev, epi)
 
@@ -768,7 +961,7 @@ void Engine::run_encoder(const BatchDev& b) {
     // norm_out (+ next layer's norm_feed_forward1; after the last layer: operand of the joint's encoder projection)
     const bool last = l + 1 == L_;
     launch_layernorm(im.x, M, w.n_out_g, w.n_out_b, last ? nullptr : im.layers[l + 1].n_ff1_g, last ? nullptr : im.layers[l + 1].n_ff1_b,
-                     1, im.a_ln.out(), nullptr, st_); ++launches_;
+                     1, last ? im.a_xf.out() : im.a_ln.out(), nullptr, st_); ++launches_;
   }
   launch_gather_output(b, im.x, im.enc_out, st_); ++launches_;
 }
@@ -794,7 +987,7 @@ void Engine::run_decode(const BatchDev& b, const std::vector<Entry>& entries) {
   // joint encoder projection for every packed row: E = joint.enc(x) + bias
   g_tc_site = 16;
   { EpiParams e; e.mode = EPI_BIAS_F32; e.out_f32 = im.enc_proj; e.ldo = kJointH; e.bias = im.joint_enc_b;
-    RUN_GEMM(im.a_ln, im.joint_enc, b.M, nullptr, e); }
+    RUN_GEMM(im.a_xf, im.joint_enc, b.M, nullptr, e); }
   DecodeDev d = make_decode_dev(im, opt_, b.B, b.slot, b.row_off, im.batch_ints + 10 * im.Bcap);
   launch_decode_begin(d, st_); ++launches_;
   const int max_iters = kValidOut * (kMaxSymbols + 1) + 2;
@@ -856,6 +1049,12 @@ void Engine::prime_streams(const std::vector<int>& sids) {
 void Engine::run_batch(const std::vector<Entry>& entries, float* enc_out_host) {
   Impl& im = *im_;
   if (entries.empty()) return;
+  if (enc_out_host == nullptr) {
+    std::vector<int> fresh;
+    for (const Entry& e : entries)
+      if (streams_[e.sid]->needs_prime) { fresh.push_back(e.sid); streams_[e.sid]->needs_prime = false; }
+    prime_streams(fresh);
+  }
   const BatchDev b = upload_batch(entries);
   run_encoder(b);
   const bool decode = enc_out_host == nullptr;
@@ -867,6 +1066,7 @@ void Engine::run_batch(const std::vector<Entry>& entries, float* enc_out_host) {
     PKB_CUDA(cudaMemcpyAsync(enc_out_host, im.enc_out, (size_t)b.B * kDModel * kValidOut * sizeof(float), cudaMemcpyDeviceToHost, st_));
   }
   PKB_CUDA(cudaStreamSynchronize(st_));
+  if (im.profile) profile_collect();
   const int* h = im.batch_ints_host;
   const int C = im.Bcap;
   for (int i = 0; i < b.B; ++i) {
@@ -989,6 +1189,47 @@ void Engine::export_state(int sid, float* cache_ch, float* cache_tm) {
   for (int l = 0; l < L_; ++l) memset(cache_ch + (size_t)l * kCacheS * kDModel, 0, (size_t)invalid * kDModel * 4);
 }
 
+void Engine::import_stream_state(int sid, const float* cache_ch, const float* cache_tm, int cache_len) {
+  PKB_CHECK(sid >= 0 && sid < (int)streams_.size() && streams_[sid]->open, "bad stream id");
+  import_state(sid, cache_ch, 0, cache_tm, cache_len);
+}
+void Engine::export_stream_state(int sid, float* cache_ch, float* cache_tm, int* cache_len) {
+  PKB_CHECK(sid >= 0 && sid < (int)streams_.size() && streams_[sid]->open, "bad stream id");
+  export_state(sid, cache_ch, cache_tm);
+  *cache_len = streams_[sid]->cache_len;
+}
+// predictor state in the contract layout of one stream: h,c [2,640], g [640]; also refreshes the cached joint.pred(g)
+void Engine::set_decoder_state(int sid, const float* h, const float* c, const float* g, int n_emitted, int y_id) {
+  PKB_CHECK(sid >= 0 && sid < (int)streams_.size() && streams_[sid]->open, "bad stream id");
+  Impl& im = *im_;
+  const size_t slot = streams_[sid]->slot;
+  streams_[sid]->needs_prime = false;
+  PKB_CUDA(cudaStreamSynchronize(st_));
+  PKB_CUDA(cudaMemcpy(im.pred_h + slot * kPredL * kPredH, h, kPredL * kPredH * 4, cudaMemcpyHostToDevice));
+  PKB_CUDA(cudaMemcpy(im.pred_c + slot * kPredL * kPredH, c, kPredL * kPredH * 4, cudaMemcpyHostToDevice));
+  PKB_CUDA(cudaMemcpy(im.pred_g + slot * kPredH, g, kPredH * 4, cudaMemcpyHostToDevice));
+  PKB_CUDA(cudaMemcpy(im.n_emitted + slot, &n_emitted, 4, cudaMemcpyHostToDevice));
+  PKB_CUDA(cudaMemcpy(im.y_id + slot, &y_id, 4, cudaMemcpyHostToDevice));
+  PKB_CUDA(cudaDeviceSynchronize());   // pageable H2D: staged != landed (see dev_upload)
+  f32_to_act_kernel<<<(kPredH + 255) / 256, 256, 0, st_>>>(im.pred_g + slot * kPredH, kPredH, 1, 1, kPredH, im.a_g.out());
+  int sl = (int)slot;
+  PKB_CUDA(cudaMemcpyAsync(im.pred_rowmap, &sl, 4, cudaMemcpyHostToDevice, st_));
+  g_tc_site = 16;
+  { EpiParams e; e.mode = EPI_BIAS_ROWMAP_F32; e.out_f32 = im.pred_proj; e.ldo = kJointH; e.bias = im.joint_pred_b; e.row_map = im.pred_rowmap;
+    RUN_GEMM(im.a_g, im.joint_pred, 1, nullptr, e); }
+  PKB_CUDA(cudaStreamSynchronize(st_));
+  launches_ += 1;
+}
+void Engine::get_decoder_state(int sid, float* h, float* c, float* g) {
+  PKB_CHECK(sid >= 0 && sid < (int)streams_.size() && streams_[sid]->open, "bad stream id");
+  Impl& im = *im_;
+  const size_t slot = streams_[sid]->slot;
+  PKB_CUDA(cudaStreamSynchronize(st_));
+  PKB_CUDA(cudaMemcpy(h, im.pred_h + slot * kPredL * kPredH, kPredL * kPredH * 4, cudaMemcpyDeviceToHost));
+  PKB_CUDA(cudaMemcpy(c, im.pred_c + slot * kPredL * kPredH, kPredL * kPredH * 4, cudaMemcpyDeviceToHost));
+  PKB_CUDA(cudaMemcpy(g, im.pred_g + slot * kPredH, kPredH * 4, cudaMemcpyDeviceToHost));
+}
+
 void Engine::encoder_streaming_step(int B, int T, const float* audio_signal, const int64_t* length, const float* cache_last_channel,
                                     const float* cache_last_time, const int64_t* cache_last_channel_len, float* encoder_output,
                                     int64_t* encoded_lengths, float* cache_last_channel_out, float* cache_last_time_out,
@@ -1020,7 +1261,7 @@ void Engine::predictor_step(int B, const int64_t* y, const float* h, const float
   Impl& im = *im_;
   PKB_CHECK(B >= 1 && B <= opt_.max_streams, "predictor_step: B exceeds max_streams");
   std::vector<int> sids;
-  for (int i = 0; i < B; ++i) sids.push_back(open_stream());
+  for (int i = 0; i < B; ++i) { sids.push_back(open_stream()); streams_[sids.back()]->needs_prime = false; }
   PKB_CUDA(cudaStreamSynchronize(st_));
   std::vector<float> hb(kPredL * kPredH), cb(kPredL * kPredH);
   for (int i = 0; i < B; ++i) {
@@ -1034,6 +1275,7 @@ void Engine::predictor_step(int B, const int64_t* y, const float* h, const float
     im.batch_ints_host[i] = (int)slot;
     im.res_host[i] = (int)y[i];
   }
+  PKB_CUDA(cudaDeviceSynchronize());     // pageable H2D: staged != landed (see dev_upload)
   PKB_CUDA(cudaMemcpyAsync(im.batch_ints, im.batch_ints_host, B * sizeof(int), cudaMemcpyHostToDevice, st_));
   PKB_CUDA(cudaMemcpyAsync(im.force_toks, im.res_host, B * sizeof(int), cudaMemcpyHostToDevice, st_));
   DecodeDev d = make_decode_dev(im, opt_, B, im.batch_ints, nullptr, nullptr);
@@ -1057,7 +1299,7 @@ void Engine::predictor_step(int B, const int64_t* y, const float* h, const float
 void Engine::joint_step(int B, int T, int U, const float* enc, const float* pred, float* out) {
   Impl& im = *im_;
   const int rows = B * T * U;
-  PKB_CHECK(B >= 1 && B * T <= im.a_ln.rows_cap && B * U <= im.a_g.rows_cap && rows <= im.a_hid.rows_cap,
+  PKB_CHECK(B >= 1 && B * T <= im.a_xf.rows_cap && B * U <= im.a_g.rows_cap && rows <= im.a_hid.rows_cap,
             "joint_step: B*T*U exceeds the decode row capacity (raise max_streams)");
   PKB_CUDA(cudaStreamSynchronize(st_));
   float* d_enc = dev_upload(std::vector<float>(enc, enc + (size_t)B * kDModel * T));
@@ -1065,14 +1307,14 @@ void Engine::joint_step(int B, int T, int U, const float* enc, const float* pred
   float* d_P = dev_alloc<float>((size_t)B * U * kJointH);
   // enc [B,1024,T] -> operand rows (b*T+t): row stride within b is 1 (t), col stride T
   for (int b = 0; b < B; ++b) {
-    ActOut a = im.a_ln.out(); a.ptr += (size_t)b * T * a.lda;
+    ActOut a = im.a_xf.out(); a.ptr += (size_t)b * T * a.lda;
     f32_to_act_kernel<<<(T * kDModel + 255) / 256, 256, 0, st_>>>(d_enc + (size_t)b * kDModel * T, 1, T, T, kDModel, a);
     ActOut p = im.a_g.out(); p.ptr += (size_t)b * U * p.lda;
     f32_to_act_kernel<<<(U * kPredH + 255) / 256, 256, 0, st_>>>(d_pred + (size_t)b * kPredH * U, 1, U, U, kPredH, p);
     launches_ += 2;
   }
   { EpiParams e; e.mode = EPI_BIAS_F32; e.out_f32 = im.enc_proj; e.ldo = kJointH; e.bias = im.joint_enc_b;
-    RUN_GEMM(im.a_ln, im.joint_enc, B * T, nullptr, e); }
+    RUN_GEMM(im.a_xf, im.joint_enc, B * T, nullptr, e); }
   { EpiParams e; e.mode = EPI_BIAS_F32; e.out_f32 = d_P; e.ldo = kJointH; e.bias = im.joint_pred_b;
     RUN_GEMM(im.a_g, im.joint_pred, B * U, nullptr, e); }
   joint_hidden_grid_kernel<<<rows, 128, 0, st_>>>(im.enc_proj, d_P, T, U, im.a_hid.out()); ++launches_;

@@ -54,6 +54,10 @@ class Engine {
   // (tools/verify_nemo/streaming_encoder_reference.py:522-550).
   void queue_audio(int sid, const float* pcm, size_t n);
   void set_feature_norm(int sid, const float* mean128, const float* std128);   // nullptrs: none
+  // batched push of `count` samples for n streams in one call; source rows `stride` floats apart, in host (pinned or
+  // pageable) or device memory; lands in per-stream device audio buffers with one copy + one kernel
+  void push_audio_batch(int n, const int* sids, const float* src, long long stride, int count, bool src_on_device,
+                        bool internal = false);
 
   // Advance every stream that has a pending chunk by one chunk.  Returns the number of chunks processed.
   int step();
@@ -63,6 +67,13 @@ class Engine {
   const ChunkResult& last_chunk(int sid) const;
   int cache_len(int sid) const;
   long long chunks_done(int sid) const;
+
+  // ---- per-stream state across the ABI (checkpoint / migration / functional-mode parity), contract layouts, host pointers
+  // cache_last_channel [L,256,1024], cache_last_time [L,1024,4] of ONE stream
+  void import_stream_state(int sid, const float* cache_ch, const float* cache_tm, int cache_len);
+  void export_stream_state(int sid, float* cache_ch, float* cache_tm, int* cache_len);
+  void set_decoder_state(int sid, const float* h, const float* c, const float* g, int n_emitted, int y_id);
+  void get_decoder_state(int sid, float* h, float* c, float* g);
 
   // ---- tensor-level entry points at the contract layouts (host pointers) ----
   void encoder_streaming_step(int B, int T, const float* audio_signal, const int64_t* length, const float* cache_last_channel,
@@ -84,12 +95,20 @@ class Engine {
   int sm_count() const { return sm_count_; }
   cudaStream_t stream() const { return st_; }
   void synchronize();
+  // CUDA events on the engine's own stream (bench timing) and per-launch timing of the tcgen05 GEMM (roofline)
+  int event_record();
+  double event_elapsed_ms(int a, int b);
+  void profile_enable(bool on);
+  void profile_collect();
+  void profile_read(double* ms, double* flops, long long* launches);
 
   struct Stream;
   struct Impl;
   struct Entry { int sid; int f0; int T; };
+  Impl* impl();
 
  private:
+  void compact_audio();
   void load_weights();
   void alloc_state();
   void run_batch(const std::vector<Entry>& entries, float* enc_out_host /*optional [B,1024,3]*/);

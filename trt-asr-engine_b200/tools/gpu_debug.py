@@ -30,6 +30,20 @@ def main():
     backend = int(os.environ.get("BACKEND", "1"))
     model = conftest.model_dir(layers)
     fr = conftest.FeaturesRef(conftest.build_oracle())
+    pre = os.environ.get("PRE", "")
+    if pre:
+        for pp in pre.split(","):
+            e0 = binding.Engine(model, max_streams=4 if pp[0] == "f" else 1, precision=int(pp[-1]))
+            if pp[0] == "g":
+                rng = np.random.default_rng(1)
+                for M, N, K in [(1, 256, 256), (300, 1024, 1024), (64, 8198, 640), (1000, 3072, 1024)]:
+                    A = rng.standard_normal((M, K)).astype(np.float32)
+                    Wb = f32_to_bf16_bits(rng.standard_normal((N, K)).astype(np.float32)).reshape(N, K)
+                    e0.gemm_test(0, A, Wb); e0.gemm_test(1, A, Wb)
+            else:
+                e0.logmel(synth_clip(10.0, 1)); e0.logmel(synth_clip(60.0, 2), True)
+            e0.close()
+            print("  pre-engine", pp, "done", flush=True)
     t0 = time.time()
     eng = binding.Engine(model, max_streams=int(os.environ.get("STREAMS", "4")), precision=prec, gemm_backend=backend, max_rows=int(os.environ.get("ROWS", "64")))
     print(f"[{sec}] engine up in {time.time()-t0:.1f}s layers={layers} prec={prec} backend={backend}", flush=True)
@@ -63,6 +77,19 @@ def main():
             d = np.abs(genc - enc.numpy())
             print(f"  chunk {k}: enc max|err|={d.max():.3e} p95={np.percentile(d,95):.3e} |enc|max={enc.abs().max():.2f} "
                   f"cache_ch err={np.abs(gcc-cc.numpy()).max():.3e} cache_tm err={np.abs(gct-ct.numpy()).max():.3e} len {gcl.tolist()} {cl.tolist()}", flush=True)
+    elif sec == "saturated":
+        m = ModelRef(model)
+        x = feats(fr, 1.0, 9)[None, :, :57]
+        for trial, (ln, scale) in enumerate([(256, 1.0), (256, 1.0), (256, 0.0), (100, 1.0), (16, 1.0), (256, 0.2)]):
+            rng = np.random.default_rng(5)
+            cc = (scale * rng.standard_normal((1, m.L, 256, 1024))).astype(np.float32)
+            ct = (scale * rng.standard_normal((1, m.L, 1024, 4))).astype(np.float32)
+            cc[:, :, :256 - ln] = 0
+            enc, el, cco, cto, clo = m.stream_step(torch.from_numpy(x), torch.tensor([57]), torch.from_numpy(cc), torch.from_numpy(ct), torch.tensor([ln]))
+            genc, gel, gcc, gct, gcl = eng.encoder_streaming_step(x, np.array([57]), cc, ct, np.array([ln]))
+            d = np.abs(genc - enc.numpy())
+            print(f"  trial {trial} len={ln} scale={scale}: enc max|err|={d.max():.3e} p95={np.percentile(d,95):.3e} cache_ch err={np.abs(gcc-cco.numpy()).max():.3e} "
+                  f"cache_tm err={np.abs(gct-cto.numpy()).max():.3e}", flush=True)
     elif sec == "decode":
         m = ModelRef(model)
         torch.manual_seed(0)

@@ -54,7 +54,7 @@ def synth_vocab(rng: np.random.Generator) -> list[str]:
     return pieces  # blank (8192) has no line, like the real vocab.txt (8192 lines)
 
 
-def build(out_dir: str, n_layers: int, seed: int, blank_bias: float, row_sigma: float, logit_gain: float):
+def build(out_dir: str, n_layers: int, seed: int, blank_rate: float, row_sigma: float, logit_gain: float):
     os.makedirs(out_dir, exist_ok=True)
     g = torch.Generator().manual_seed(seed)
     T = {}
@@ -117,9 +117,18 @@ def build(out_dir: str, n_layers: int, seed: int, blank_bias: float, row_sigma: 
     row_scale[BLANK:] = 1.0
     w_out *= row_scale[:, None]
     b_out = randn(VOCAB + N_DUR, std=0.1)
-    b_out[BLANK] += blank_bias
-    dur_bias = np.array([-0.5, 1.0, 0.8, 0.2, -0.2], dtype=np.float32) * logit_gain
-    b_out[VOCAB:] += dur_bias
+    # Calibrate the blank / duration biases on a proxy of the joint's hidden state, relu(enc_proj(x) + pred_proj(g)) with
+    # x ~ LayerNorm output and g ~ LSTM output, so that greedy decode behaves like speech: blank wins `blank_rate` of the
+    # steps and durations are mostly 1-2 (otherwise random logits emit a token on every step and hit the 8-symbol cap).
+    xs = randn(768, D_MODEL)
+    gs = np.tanh(randn(768, PRED_H)) * 0.5
+    hid = np.maximum(xs @ T["joint.enc.weight"][0].T + T["joint.enc.bias"][0] + gs @ T["joint.pred.weight"][0].T
+                     + T["joint.pred.bias"][0], 0.0).astype(np.float32)
+    tok_max = (hid @ w_out[:BLANK].T + b_out[:BLANK]).max(axis=1)
+    blank_raw = hid @ w_out[BLANK] + b_out[BLANK]
+    b_out[BLANK] += float(np.quantile(tok_max - blank_raw, blank_rate))
+    dur_sd = float((hid @ w_out[VOCAB:].T).std())
+    b_out[VOCAB:] += np.array([-1.0, 1.5, 1.2, 0.0, -1.0], dtype=np.float32) * dur_sd
     add("joint.joint_net.2.weight", w_out, DT_BF16)
     add("joint.joint_net.2.bias", b_out)
 
@@ -132,7 +141,7 @@ def build(out_dir: str, n_layers: int, seed: int, blank_bias: float, row_sigma: 
     vocab = synth_vocab(np.random.default_rng(seed + 17))
     with open(os.path.join(out_dir, "vocab.txt"), "w", encoding="utf-8") as f:
         f.write("\n".join(vocab) + "\n")
-    meta = dict(cfg, generator="make_synthetic_model.py", blank_bias=blank_bias, row_sigma=row_sigma,
+    meta = dict(cfg, generator="make_synthetic_model.py", gen_version=GEN_VERSION, blank_rate=blank_rate, row_sigma=row_sigma,
                 logit_gain=logit_gain, duration_values=[0, 1, 2, 3, 4],
                 note="seeded random weights; GEMM weights bf16-representable")
     with open(os.path.join(out_dir, "model_meta.json"), "w") as f:
@@ -147,25 +156,26 @@ def ensure_model(out_dir: str, n_layers: int = 24, seed: int = 0, **kw) -> str:
     if os.path.exists(meta) and os.path.exists(os.path.join(out_dir, "weights.bin")):
         with open(meta) as f:
             m = json.load(f)
-        if m.get("n_layers") == n_layers and m.get("seed") == seed:
+        if m.get("n_layers") == n_layers and m.get("seed") == seed and m.get("gen_version") == GEN_VERSION:
             return out_dir
-    kw.setdefault("blank_bias", DEFAULTS["blank_bias"])
+    kw.setdefault("blank_rate", DEFAULTS["blank_rate"])
     kw.setdefault("row_sigma", DEFAULTS["row_sigma"])
     kw.setdefault("logit_gain", DEFAULTS["logit_gain"])
     build(out_dir, n_layers, seed, **kw)
     return out_dir
 
 
-DEFAULTS = dict(blank_bias=9.0, row_sigma=0.6, logit_gain=3.0)
+DEFAULTS = dict(blank_rate=0.75, row_sigma=0.6, logit_gain=3.0)
+GEN_VERSION = 2
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", required=True)
     ap.add_argument("--layers", type=int, default=24)
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--blank-bias", type=float, default=DEFAULTS["blank_bias"])
+    ap.add_argument("--blank-rate", type=float, default=DEFAULTS["blank_rate"])
     ap.add_argument("--row-sigma", type=float, default=DEFAULTS["row_sigma"])
     ap.add_argument("--logit-gain", type=float, default=DEFAULTS["logit_gain"])
     a = ap.parse_args()
-    n = build(a.out, a.layers, a.seed, a.blank_bias, a.row_sigma, a.logit_gain)
+    n = build(a.out, a.layers, a.seed, a.blank_rate, a.row_sigma, a.logit_gain)
     print(f"wrote {a.out}: {n} parameters, {a.layers} layers")
