@@ -45,6 +45,16 @@ def shard(n_streams: int, rank: int, world: int):
     return [i for i in range(n_streams) if i % world == rank]
 
 
+def reduce_timings(vals, world: int, device="cuda"):
+    """max over ranks of each timing (the job finishes when the slowest rank does)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(vals), dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.tolist()]
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -291,10 +301,7 @@ def main():
     eng.profile_enable(False)
 
     n_tokens = sum(len(eng.tokens(int(s))) for s in sids[: min(n, 64)])
-    t = torch.tensor([dev_ms / 1e3, e2e_s, wall_resident], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_s, e2e_max, wall_max = (float(x) for x in t.tolist())
+    dev_s, e2e_max, wall_max = reduce_timings([dev_ms / 1e3, e2e_s, wall_resident], world)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -90,6 +90,21 @@ def main():
             d = np.abs(genc - enc.numpy())
             print(f"  trial {trial} len={ln} scale={scale}: enc max|err|={d.max():.3e} p95={np.percentile(d,95):.3e} cache_ch err={np.abs(gcc-cco.numpy()).max():.3e} "
                   f"cache_tm err={np.abs(gct-cto.numpy()).max():.3e}", flush=True)
+    elif sec == "lensweep":
+        m = ModelRef(model)
+        for T in (57, 41):
+            x = feats(fr, 1.0, 9)[None, :, :T]
+            for ln in (100, 120, 127, 128, 129, 134, 135, 140, 156, 200, 255, 256):
+                for scale in (0.0, 1.0):
+                    rng = np.random.default_rng(5)
+                    cc = (scale * rng.standard_normal((1, m.L, 256, 1024))).astype(np.float32)
+                    ct = (scale * rng.standard_normal((1, m.L, 1024, 4))).astype(np.float32)
+                    cc[:, :, :256 - ln] = 0
+                    enc, el, cco, cto, clo = m.stream_step(torch.from_numpy(x), torch.tensor([T]), torch.from_numpy(cc), torch.from_numpy(ct), torch.tensor([ln]))
+                    genc, gel, gcc, gct, gcl = eng.encoder_streaming_step(x, np.array([T]), cc, ct, np.array([ln]))
+                    d = np.abs(genc - enc.numpy())
+                    tm = np.abs(gct - cto.numpy())
+                    print(f"  T={T} len={ln} scale={scale}: enc max|err|={d.max():.3e} cache_tm err L0={tm[0,0].max():.3e} L1={tm[0,1].max():.3e}", flush=True)
     elif sec == "decode":
         m = ModelRef(model)
         torch.manual_seed(0)
