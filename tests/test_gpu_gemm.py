@@ -17,10 +17,12 @@ def eng(request, model_small):
 
 
 SHAPES = [(1, 256, 256), (6, 1024, 1024), (8, 4096, 1024), (17, 1024, 4096), (128, 256, 256), (130, 640, 640), (300, 1024, 1024),
-          (257, 2560, 1280), (64, 8198, 640), (1000, 3072, 1024)]
+          (257, 2560, 1280), (64, 8198, 640), (1000, 3072, 1024),
+          # more tiles than SMs: the persistent loop takes >= 3 tiles per CTA, both TMEM accumulator buffers change phase
+          (2048, 4096, 1024), (1536, 3072, 1024), (700, 8198, 640), (3072, 1024, 4096)]
 
 
-@pytest.mark.parametrize("backend", [0, 1], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("backend", [0, 1, 2, 3], ids=["simt", "tcgen05", "tcgen05-bn128", "tcgen05-bn256"])
 @pytest.mark.parametrize("M,N,K", SHAPES)
 def test_gemm(eng, backend, M, N, K):
     rng = np.random.default_rng(M * 7 + N + K)

@@ -1365,9 +1365,11 @@ void Engine::gemm_test(int backend, int M, int N, int K, const float* A, const u
   g.A = a.ptr; g.lda = K; g.a_lo_off = a.lo_off; g.W = w.w; g.M = M; g.N = N; g.K = K;
   g.epi.mode = EPI_F32; g.epi.out_f32 = d_C; g.epi.ldo = N;
   (void)epi_silu;
-  if (backend == 1) {
+  if (backend >= 1) {     // 1: heuristic tile width, 2: 128-wide tiles, 3: 256-wide tiles
     PKB_CHECK(gemm_tc_supported(g), "gemm_test: shape not supported by the tensor-core backend");
+    gemm_tc_set_bn(backend == 2 ? 128 : backend == 3 ? 256 : 0);
     gemm_tc(g, a.map, w.map, st_);
+    gemm_tc_set_bn(0);
   } else {
     gemm_simt(g, st_);
   }

@@ -137,5 +137,6 @@ void make_tensor_map_2d(TensorMap* out, const void* base, uint64_t rows, uint64_
                         uint32_t box_rows);
 void gemm_tc(const GemmArgs& g, const TensorMap& map_a, const TensorMap& map_w, cudaStream_t st);
 bool gemm_tc_supported(const GemmArgs& g);
+void gemm_tc_set_bn(int bn);   // validation hook: 0 = heuristic tile width, 128 / 256 = forced
 
 }  // namespace pkb

@@ -1,13 +1,17 @@
 // gemm_tc.cu -- tcgen05 / TMA / TMEM GEMM for sm_100a (see gemm.h):  C[m,n] = sum_k A[m,k] * W[n,k], fused epilogue.
 //
-// Structure (one 128x128 output tile per CTA, 192 threads):
-//   warp 0   : TMA producer  -- cp.async.bulk.tensor.2d of a 128x64 bf16 A tile and a 128x64 bf16 W tile per k-block
-//              into a kStages-deep shared-memory ring (128-byte swizzle), completion on "full" mbarriers
-//   warp 1   : MMA issuer    -- one elected lane issues 4 x tcgen05.mma (M128 N128 K16, bf16 -> f32) per k-block with the
-//              accumulator in TMEM (128 lanes x 128 columns); tcgen05.commit releases the smem slot ("empty" mbarrier)
-//              and finally signals the epilogue ("tmem_full" mbarrier).  Warp 1 also owns the TMEM allocation.
-//   warps 2-5: epilogue      -- tcgen05.ld 32 lanes x 16 columns at a time (warp w reads TMEM lane quarter w%4),
-//              apply the fused epilogue (bias / ReLU / SiLU / GLU / residual add / QKV ring scatter) and store.
+// Persistent, warp-specialised kernel: one CTA per SM loops over 128 x BN output tiles (BN = 128 or 256, m fastest so
+// that concurrently running CTAs share weight tiles through L2).  320 threads:
+//   warp 0    : TMA producer  -- per k-block one 128x64 bf16 A tile and BN/128 128x64 W tiles (cp.async.bulk.tensor.2d,
+//               128-byte swizzle) into a kStages-deep shared-memory ring; completion on "full" mbarriers
+//   warp 1    : MMA issuer    -- one lane issues 4 x tcgen05.mma (M128 N{128,256} K16, bf16 -> f32) per k-block; the
+//               accumulator lives in TMEM and is DOUBLE-BUFFERED (2 x BN columns): tile i+1 is accumulated while the
+//               epilogue drains tile i.  tcgen05.commit releases smem slots ("empty") and publishes tiles ("tmem_full").
+//   warps 2-9 : epilogue      -- warp w reads TMEM lane quarter w%4, column half (w-2)/4: tcgen05.ld 32 lanes x 16 columns,
+//               transposes the 32x16 block through a private padded smem tile so that every global store instruction
+//               writes whole 64-byte row segments (8 rows per instruction), applies the fused epilogue (bias / ReLU /
+//               SiLU / GLU / residual add / row map / QKV scatter into the per-stream rings) on float4 granules, and
+//               hands the TMEM buffer back ("tmem_empty") as soon as its last tcgen05.ld has landed.
 // Split ("precise") mode runs the k-loop twice over the same W tiles: first the bf16 high plane of A, then the low
 // plane, accumulating into the same TMEM tile -- fp32-grade products at 2x the tensor work, no extra weight traffic
 // from HBM (the W tile of the second pass hits L2).
@@ -19,12 +23,21 @@ namespace pkb {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64;
-constexpr int kStages = 6;
-constexpr int kTileBytes = BM * BK * 2;          // 16 KB (A and W tiles have the same size)
-constexpr int kThreads = 192;
-constexpr int kTmemCols = 128;
-constexpr size_t kSmemBytes = 1024 + (size_t)kStages * 2 * kTileBytes + 256;
+constexpr int BM = 128, BK = 64;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + kEpiWarps * 32;
+constexpr int kTileABytes = BM * BK * 2;          // 16 KB
+constexpr int kEpiPitch = 20;                     // floats per staged row (16 + 4 pad: conflict-free 128-bit access)
+constexpr int kEpiBytesPerWarp = 32 * kEpiPitch * 4;
+
+template <int BN>
+struct Cfg {
+  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kTileBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kTileABytes + kTileBBytes;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + (size_t)kEpiWarps * kEpiBytesPerWarp + 256;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -33,6 +46,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -67,16 +83,19 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                               // SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N=128, M=128
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N, M=128
+template <int BN>
+struct IDesc {
+  static constexpr uint32_t value = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
 
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc_v, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(kIdesc), "r"(accumulate)
+      "}" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc_v), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -92,21 +111,117 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
 }
 
+__device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) {
+  const __nv_bfloat162 p0 = __floats2bfloat162_rn(a, b), p1 = __floats2bfloat162_rn(c, d);
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+}
+// 4 adjacent activations -> bf16 hi plane (+ lo plane in split mode), 8-byte stores
+__device__ __forceinline__ void store_act4(__nv_bfloat16* A, size_t row, int lda, int col, float4 v, long long lo_off) {
+  __nv_bfloat16* dst = A + row * (size_t)lda + col;
+  const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+  *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+  if (lo_off) {
+    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+    *reinterpret_cast<uint2*>(dst + lo_off) = pack4_bf16(v.x - f0.x, v.y - f0.y, v.z - f1.x, v.w - f1.y);
+  }
+}
+
+// Fused epilogue on 4 adjacent columns n..n+3 (n % 4 == 0, n < N) of row m.
+__device__ __forceinline__ void epilogue_quad(const EpiParams& p, int m, int n, int N, float4 v) {
+  const bool f32_rows = p.mode == EPI_F32 || p.mode == EPI_BIAS_F32 || p.mode == EPI_BIAS_RELU_F32 || p.mode == EPI_BIAS_ROWMAP_F32 ||
+                        p.mode == EPI_RESADD_F32;
+  if (n + 3 >= N || (f32_rows && (p.ldo & 3))) {
+    // ragged right edge (N = 8198) or rows that are not 16-byte aligned: pairwise path
+    epilogue_pair(p, m, n, N, v.x, v.y);
+    if (n + 2 < N) epilogue_pair(p, m, n + 2, N, v.z, v.w);
+    return;
+  }
+  const int nn = n + p.n_off;
+  switch (p.mode) {
+    case EPI_F32:
+      *reinterpret_cast<float4*>(p.out_f32 + (size_t)m * p.ldo + nn) = v;
+      break;
+    case EPI_BIAS_F32:
+    case EPI_BIAS_RELU_F32:
+    case EPI_BIAS_ROWMAP_F32: {
+      const float4 b = *reinterpret_cast<const float4*>(p.bias + nn);
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+      if (p.mode == EPI_BIAS_RELU_F32) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      int r = m;
+      if (p.mode == EPI_BIAS_ROWMAP_F32) { r = p.row_map[m]; if (r < 0) break; }
+      *reinterpret_cast<float4*>(p.out_f32 + (size_t)r * p.ldo + nn) = v;
+      break;
+    }
+    case EPI_BIAS_RELU_ACT: {
+      const float4 b = *reinterpret_cast<const float4*>(p.bias + nn);
+      v.x = fmaxf(v.x + b.x, 0.f); v.y = fmaxf(v.y + b.y, 0.f); v.z = fmaxf(v.z + b.z, 0.f); v.w = fmaxf(v.w + b.w, 0.f);
+      store_act4(p.out_act, m, p.lda_out, nn, v, p.lo_off_out);
+      break;
+    }
+    case EPI_SILU_ACT:
+      v.x = silu(v.x); v.y = silu(v.y); v.z = silu(v.z); v.w = silu(v.w);
+      store_act4(p.out_act, m, p.lda_out, nn, v, p.lo_off_out);
+      break;
+    case EPI_RESADD_F32: {
+      float4* o = reinterpret_cast<float4*>(p.out_f32 + (size_t)m * p.ldo + nn);
+      float4 x = *o;
+      x.x += p.scale * v.x; x.y += p.scale * v.y; x.z += p.scale * v.z; x.w += p.scale * v.w;
+      *o = x;
+      break;
+    }
+    case EPI_GLU_F32:
+      *reinterpret_cast<float2*>(p.out_f32 + (size_t)m * p.ldo + (nn >> 1)) = make_float2(v.x * sigmoidf_(v.y), v.z * sigmoidf_(v.w));
+      break;
+    case EPI_QKV: {
+      if (nn < kDModel) {
+        *reinterpret_cast<float4*>(p.out_f32 + (size_t)m * p.ldo + nn) = v;
+        break;
+      }
+      const int e = p.row_entry[m];
+      const int slot = p.entry_slot[e];
+      const int phys = (p.entry_head[e] + kCacheS + p.row_pos[m]) % kRingCap;
+      if (nn < 2 * kDModel) {
+        const int c = nn - kDModel, h = c >> 7, d = c & 127;
+        const size_t i0 = (((size_t)slot * kHeads + h) * kDHead + d) * kRingCap + phys;   // K^T ring: 4 rows kRingCap apart
+        if (p.kv_f32) {
+          float* k = (float*)p.kring + i0;
+          k[0] = v.x; k[kRingCap] = v.y; k[2 * kRingCap] = v.z; k[3 * kRingCap] = v.w;
+        } else {
+          __nv_bfloat16* k = (__nv_bfloat16*)p.kring + i0;
+          k[0] = __float2bfloat16_rn(v.x); k[kRingCap] = __float2bfloat16_rn(v.y);
+          k[2 * kRingCap] = __float2bfloat16_rn(v.z); k[3 * kRingCap] = __float2bfloat16_rn(v.w);
+        }
+      } else {
+        const size_t i0 = ((size_t)slot * kRingCap + phys) * kDModel + (nn - 2 * kDModel);
+        if (p.kv_f32) *reinterpret_cast<float4*>((float*)p.vring + i0) = v;
+        else *reinterpret_cast<uint2*>((__nv_bfloat16*)p.vring + i0) = pack4_bf16(v.x, v.y, v.z, v.w);
+      }
+      break;
+    }
+    default: break;
+  }
+}
+
+template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const GemmArgs g,
                const int lo_row_off) {
+  using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const int M = g.M_dev ? min(*g.M_dev, g.M) : g.M;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  if (m0 >= M) return;                                   // uniform per CTA, before any barrier / allocation
+  const int tiles_m = (M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN;
+  const int total_tiles = tiles_m * tiles_n;
+  if ((int)blockIdx.x >= total_tiles) return;            // uniform per CTA, before any barrier / allocation
 
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = base;
-  uint8_t* sB = base + kStages * kTileBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + 2 * kStages * kTileBytes);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full_bar = empty_bar + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint8_t* sA = base;                                    // [kStages][16 KB]
+  uint8_t* sB = base + C::kStages * kTileABytes;         // [kStages][BN*128 B]
+  float* sEpi = reinterpret_cast<float*>(base + C::kStages * C::kStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sEpi) + kEpiWarps * kEpiBytesPerWarp);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tmem_full_bar = empty_bar + C::kStages;      // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb_per_pass = g.K / BK;
@@ -115,12 +230,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -130,47 +245,80 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], 2 * kTileBytes);
-        const int pass = kb / kb_per_pass, kk = (kb % kb_per_pass) * BK;
-        tma_load_2d(sA + s * kTileBytes, &map_a, &full_bar[s], kk, m0 + pass * lo_row_off);
-        tma_load_2d(sB + s * kTileBytes, &map_w, &full_bar[s], kk, n0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % C::kStages;
+          const uint32_t ph = (it / C::kStages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], C::kStageBytes);
+          const int pass = kb / kb_per_pass, kk = (kb % kb_per_pass) * BK;
+          tma_load_2d(sA + s * kTileABytes, &map_a, &full_bar[s], kk, m0 + pass * lo_row_off);
+#pragma unroll
+          for (int j = 0; j < BN / 128; ++j)
+            tma_load_2d(sB + s * C::kTileBBytes + j * kTileABytes, &map_w, &full_bar[s], kk, n0 + j * 128);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(&full_bar[s], ph);
+      int it = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+        const int acc = tl & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((tl >> 1) & 1) ^ 1);          // epilogue has drained this accumulator buffer
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t da = make_smem_desc(smem_u32(sA + s * kTileBytes));
-        const uint64_t db = make_smem_desc(smem_u32(sB + s * kTileBytes));
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % C::kStages;
+          const uint32_t ph = (it / C::kStages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = make_smem_desc(smem_u32(sA + s * kTileABytes));
+          const uint64_t db = make_smem_desc(smem_u32(sB + s * C::kTileBBytes));
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)                  // +32 bytes per K=16 step inside the 128-byte swizzle atom
-          umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), (kb | k) != 0 ? 1u : 0u);
-        umma_commit(&empty_bar[s]);                       // smem slot reusable once these MMAs have read it
+          for (int k = 0; k < BK / 16; ++k)                  // +32 bytes per K=16 step inside the 128-byte swizzle atom
+            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDesc<BN>::value, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[s]);                       // smem slot reusable once these MMAs have read it
+        }
+        umma_commit(&tmem_full_bar[acc]);                   // accumulator complete
       }
-      umma_commit(tmem_full_bar);                         // accumulator complete
     }
   } else {
-    // epilogue warps 2..5 -> TMEM lane quarters 2,3,0,1
-    const int q = warp & 3;
-    mbar_wait(tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int m = m0 + q * 32 + lane;
+    // epilogue warps 2..9: TMEM lane quarter = warp % 4 (hardware rule), column half = (warp - 2) / 4
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    float* stage = sEpi + (warp - 2) * (32 * kEpiPitch);
+    const int rsel = lane >> 2, c4 = lane & 3;
+    const int rd_row = (rsel & 1) * 4 + (rsel >> 1);        // rows r and r+4 in one quarter-warp: conflict-free reads
+    int tl = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+      const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+      const int acc = tl & 1;
+      mbar_wait(&tmem_full_bar[acc], (tl >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      if (m < M) {
+      for (int c0 = 0; c0 < BN / 2; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+        if (c0 + 16 == BN / 2) {                            // last TMEM read of this tile: give the buffer back to the MMA warp
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        __syncwarp();                                       // previous chunk's readers are done with the staging tile
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          const int n = n0 + c0 + j;
-          if (n < g.N) epilogue_pair(g.epi, m, n, g.N, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(stage + lane * kEpiPitch + 4 * j) =
+              make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        __syncwarp();
+        const int n = n0 + half * (BN / 2) + c0 + 4 * c4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = rd_row + 8 * i;
+          const float4 val = *reinterpret_cast<const float4*>(stage + r * kEpiPitch + 4 * c4);
+          const int m = m0 + q * 32 + r;
+          if (m < M && n < g.N) epilogue_quad(g.epi, m, n, g.N, val);
         }
       }
     }
@@ -179,7 +327,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::kTmemCols) : "memory");
   }
 }
 
@@ -199,6 +347,26 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+int g_force_bn = -1;      // 0: heuristic; 128 / 256: forced tile width (PARAKEET_B200_GEMM_BN or gemm_tc_set_bn)
+int g_sm_count = 0;
+int sm_count() {
+  if (!g_sm_count) {
+    int dev = 0;
+    PKB_CUDA(cudaGetDevice(&dev));
+    PKB_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return g_sm_count;
+}
+
+// Tile width: the wider tile halves the shared-memory operand traffic per MMA (96 vs 128 B/clk), the narrower one
+// quantises better into waves of `sms` CTAs.  Pick the one with the smaller (waves x tile cost).
+int pick_bn(int M, int N, int sms) {
+  const long long tm = (M + BM - 1) / BM;
+  const long long t128 = tm * ((N + 127) / 128), t256 = tm * ((N + 255) / 256);
+  const long long w128 = (t128 + sms - 1) / sms, w256 = (t256 + sms - 1) / sms;
+  return (w256 * 2 * 100 <= w128 * 105) ? 256 : 128;       // 256-wide costs 2x per tile; prefer it on ties (and within 5 %)
+}
+
 }  // namespace
 
 void make_tensor_map_2d(TensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows) {
@@ -213,6 +381,8 @@ void make_tensor_map_2d(TensorMap* out, const void* base, uint64_t rows, uint64_
   PKB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
 }
 
+void gemm_tc_set_bn(int bn) { g_force_bn = bn; }
+
 bool gemm_tc_supported(const GemmArgs& g) {
   return g.K % BK == 0 && g.lda == g.K && (g.a_lo_off % g.lda) == 0 && g.M > 0 && g.N > 0;
 }
@@ -221,13 +391,20 @@ void gemm_tc(const GemmArgs& g, const TensorMap& map_a, const TensorMap& map_w, 
   PKB_CHECK(gemm_tc_supported(g), "gemm_tc: unsupported shape");
   static bool attr = false;
   if (!attr) {
-    PKB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    PKB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<128>::kSmemBytes));
+    PKB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<256>::kSmemBytes));
     attr = true;
   }
-  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);
+  const int sms = sm_count();
+  if (g_force_bn < 0) { const char* v = getenv("PARAKEET_B200_GEMM_BN"); g_force_bn = v ? atoi(v) : 0; }
+  const int bn = g_force_bn == 128 || g_force_bn == 256 ? g_force_bn : pick_bn(g.M, g.N, sms);
+  const int tiles = ((g.M + BM - 1) / BM) * ((g.N + bn - 1) / bn);
+  const int grid = tiles < sms ? tiles : sms;
   const int lo_row_off = (int)(g.a_lo_off / g.lda);
-  gemm_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(*reinterpret_cast<const CUtensorMap*>(&map_a),
-                                                     *reinterpret_cast<const CUtensorMap*>(&map_w), g, lo_row_off);
+  const CUtensorMap& ma = *reinterpret_cast<const CUtensorMap*>(&map_a);
+  const CUtensorMap& mw = *reinterpret_cast<const CUtensorMap*>(&map_w);
+  if (bn == 256) gemm_tc_kernel<256><<<grid, kThreads, Cfg<256>::kSmemBytes, st>>>(ma, mw, g, lo_row_off);
+  else gemm_tc_kernel<128><<<grid, kThreads, Cfg<128>::kSmemBytes, st>>>(ma, mw, g, lo_row_off);
   PKB_CUDA(cudaGetLastError());
 }
 
