@@ -106,6 +106,57 @@ def test_encoder_saturated_cache(eng, oracle_small, features_ref):
     _check_enc(gct, cto.numpy(), eng.precision, "cache_last_time_out", sc)
 
 
+@pytest.mark.parametrize("T", [73, 129, 256], ids=["Tq8", "Tq15", "Tq30"])
+def test_encoder_large_chunk(eng, oracle_small, features_ref, T):
+    """Chunks longer than the steady-state 57 frames (the ABI accepts up to 256 per push): more query rows per stream
+    (8 / 15 / 30), a cache FIFO that drops Tq-3 rows, and a half-filled cache."""
+    m = oracle_small
+    rng = np.random.default_rng(11)
+    ln = 200
+    cc = (0.5 * rng.standard_normal((1, m.L, 256, 1024))).astype(np.float32)
+    cc[:, :, :256 - ln] = 0
+    ct = (0.5 * rng.standard_normal((1, m.L, 1024, 4))).astype(np.float32)
+    x = _feats(features_ref, 3.0, 21)[None, :, :T]
+    enc, el, cco, cto, clo = m.stream_step(torch.from_numpy(x), torch.tensor([T]), torch.from_numpy(cc), torch.from_numpy(ct),
+                                           torch.tensor([ln]))
+    genc, gel, gcc, gct, gcl = eng.encoder_streaming_step(x, np.array([T]), cc, ct, np.array([ln]))
+    assert gcl.tolist() == clo.tolist() and gel.tolist() == el.tolist()
+    sc = 1.0 if eng.precision == 1 else 2.0
+    _check_enc(genc, enc.numpy(), eng.precision, "encoder_output", sc)
+    _check_enc(gcc, cco.numpy(), eng.precision, "cache_last_channel_out", sc)
+    _check_enc(gct, cto.numpy(), eng.precision, "cache_last_time_out", sc)
+
+
+def test_long_stream_ring_wrap(eng, oracle_small, features_ref):
+    """120 chunks of one stream: the 288-slot K/V rings wrap several times and the cache saturates at 256 (chunk 86)."""
+    m = oracle_small
+    n_chunks = 120
+    f = _feats(features_ref, 0.41 + 0.24 * n_chunks + 0.5, 77)
+    sid = eng.open()
+    st = DecodeState(m)
+    prime(m, st)
+    cc, ct, cl = m.initial_cache(1)
+    same = 0
+    for b, e in streaming_schedule(n_chunks):
+        eng.push_features(sid, f[:, b:e])
+        assert eng.step() == 1
+        enc, el, cc, ct, cl = m.stream_step(torch.from_numpy(f[None, :, b:e]), torch.tensor([e - b]), cc, ct, cl)
+        want = [(t, tok, d) for t, tok, d, _ in tdt_greedy_chunk(m, st, enc, int(el))]
+        same += int(eng.last_steps(sid) == want)
+        assert eng.cache_len(sid) == int(cl)
+    assert int(cl) == 256
+    gcc, gct, gcl = eng.export_state(sid)
+    eng.close_stream(sid)
+    assert gcl == 256
+    if eng.precision == 1:
+        assert same == n_chunks
+        _check_enc(gcc, cc.numpy()[0], 1, "cache_last_channel after 120 chunks")
+        _check_enc(gct, ct.numpy()[0], 1, "cache_last_time after 120 chunks")
+    else:
+        assert same >= 0.85 * n_chunks, f"{same}/{n_chunks} chunks identical"
+        _check_enc(gcc, cc.numpy()[0], 0, "cache_last_channel after 120 chunks", 2.0)
+
+
 def test_predictor_and_joint(eng, oracle_small):
     """One step, like tools/onnxruntime/onnx_predictor_joint_parity.py:202-275 (token 0, zero state, randn enc seed 0) plus
     random states; reference budget: g 1.9e-7, h 1.5e-6, c 4.8e-6, logits 8.5e-4, both argmaxes equal."""

@@ -72,6 +72,21 @@ struct AttnArgs {
 };
 void launch_attention(const BatchDev& b, const AttnArgs& a, cudaStream_t st);
 
+// bf16 tensor-core version (attn_mma.cu): K and V rings both in the natural layout [layer][slot][kRingCap][1024] bf16, fetched by
+// TMA through `map_k` / `map_v` (2-D maps over [layers*slots*kRingCap, 1024], box 96 x 64, 128-byte swizzle).
+struct AttnMmaArgs {
+  const float* q;                // [M,1024] f32
+  const __nv_bfloat16* ppos_n;   // this layer's projected position table, natural layout [head][kPosRowsPad][128]
+  const float* bias_u;           // [8,128]
+  const float* bias_v;
+  ActOut ctx;                    // [M,1024] bf16
+  const void* map_k;             // host pointers to 128-byte CUtensorMap objects
+  const void* map_v;
+  int layer;
+  int n_slots;
+};
+void launch_attention_mma(const BatchDev& b, const AttnMmaArgs& a, cudaStream_t st);
+
 // Conv-module middle: depthwise k=9 over [time cache(4) | c(Tq) | 0000], folded BatchNorm, SiLU; updates the time cache.
 struct DwConvArgs {
   const float* c;          // post-GLU activations f32 [M,1024]

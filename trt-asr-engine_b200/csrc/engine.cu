@@ -51,7 +51,8 @@ struct LayerW {
   float *n_ff1_g, *n_ff1_b, *n_att_g, *n_att_b, *n_conv_g, *n_conv_b, *n_ff2_g, *n_ff2_b, *n_out_g, *n_out_b;
   GemmW ff1_1, ff1_2, qkv, kv, out, pw1, pw2, ff2_1, ff2_2;
   float *dw_w, *dw_b, *bias_u, *bias_v;
-  void* ppos_t;
+  void* ppos_t;                 // precise mode: transposed table [head][128][kPosRows] f32
+  __nv_bfloat16* ppos_n;        // bf16 mode: natural table [head][kPosRowsPad][128]
 };
 
 // ---- small utility kernels ----
@@ -68,6 +69,12 @@ __global__ void joint_hidden_grid_kernel(const float* __restrict__ E, const floa
   const int u = row % U, bt = row / U, b = bt / T;
   for (int c = threadIdx.x; c < kJointH; c += blockDim.x)
     store_act(a.ptr, row, a.lda, c, fmaxf(E[(size_t)bt * kJointH + c] + P[((size_t)b * U + u) * kJointH + c], 0.0f), a.lo_off);
+}
+// P_n[h][r][d] <- P[r][h*128+d]   (bf16, rows >= kPosRows stay zero)
+__global__ void ppos_natural_kernel(const float* __restrict__ P, __nv_bfloat16* __restrict__ out) {
+  const int r = blockIdx.x;
+  for (int c = threadIdx.x; c < kDModel; c += blockDim.x)
+    out[((size_t)(c >> 7) * kPosRowsPad + r) * kDHead + (c & 127)] = __float2bfloat16_rn(P[(size_t)r * kDModel + c]);
 }
 // P^T[h][d][r] <- P[r][h*128+d]
 __global__ void ppos_transpose_kernel(const float* __restrict__ P, void* __restrict__ out, int is_f32) {
@@ -161,6 +168,8 @@ struct Engine::Impl {
   unsigned* punct_bits = nullptr;
   // per-slot state
   void *kring = nullptr, *vring = nullptr, *acache = nullptr;
+  bool attn_mma = false;                 // bf16 mode: natural-layout K ring + tensor-core attention (attn_mma.cu)
+  TensorMap map_k, map_v;                // TMA maps over the K / V rings of all layers
   size_t ring_layer_elems = 0;           // elements per layer in each ring (slots * 288 * 1024)
   float* cache_tm = nullptr;             // [slots][L][1024][4]
   float* feat_ring = nullptr;            // [slots][kFeatRing][128]
@@ -410,6 +419,7 @@ void Engine::load_weights() {
     w.bias_u = dev_upload(wf.f32(p + "self_attn.pos_bias_u"));
     w.bias_v = dev_upload(wf.f32(p + "self_attn.pos_bias_v"));
     w.ppos_t = nullptr;   // filled in alloc_state (needs work buffers)
+    w.ppos_n = nullptr;
   }
   // predictor
   {
@@ -451,6 +461,11 @@ void Engine::alloc_state() {
   PKB_CUDA(cudaMalloc(&im.vring, im.ring_layer_elems * L_ * kv_elem));
   PKB_CUDA(cudaMemsetAsync(im.kring, 0, im.ring_layer_elems * L_ * kv_elem, st_));
   PKB_CUDA(cudaMemsetAsync(im.vring, 0, im.ring_layer_elems * L_ * kv_elem, st_));
+  im.attn_mma = !split;
+  if (im.attn_mma) {
+    make_tensor_map_2d(&im.map_k, im.kring, (uint64_t)L_ * S * kRingCap, kDModel, kDModel, 96);
+    make_tensor_map_2d(&im.map_v, im.vring, (uint64_t)L_ * S * kRingCap, kDModel, kDModel, 96);
+  }
   if (opt_.contract_cache) {
     PKB_CUDA(cudaMalloc(&im.acache, im.ring_layer_elems * L_ * kv_elem));
     PKB_CUDA(cudaMemsetAsync(im.acache, 0, im.ring_layer_elems * L_ * kv_elem, st_));
@@ -557,8 +572,14 @@ void Engine::alloc_state() {
       g.W = wp.w; g.M = kPosRows; g.N = kDModel; g.K = kDModel;
       g.epi.mode = EPI_F32; g.epi.out_f32 = im.ppos_tmp; g.epi.ldo = kDModel;
       gemm_simt(g, st_);
-      PKB_CUDA(cudaMalloc(&im.layers[l].ppos_t, (size_t)kPosRows * kDModel * kv_elem));
-      ppos_transpose_kernel<<<kPosRows, 256, 0, st_>>>(im.ppos_tmp, im.layers[l].ppos_t, split ? 1 : 0);
+      if (im.attn_mma) {
+        im.layers[l].ppos_n = dev_alloc<__nv_bfloat16>((size_t)kHeads * kPosRowsPad * kDHead);
+        PKB_CUDA(cudaMemsetAsync(im.layers[l].ppos_n, 0, (size_t)kHeads * kPosRowsPad * kDHead * 2, st_));
+        ppos_natural_kernel<<<kPosRows, 256, 0, st_>>>(im.ppos_tmp, im.layers[l].ppos_n);
+      } else {
+        PKB_CUDA(cudaMalloc(&im.layers[l].ppos_t, (size_t)kPosRows * kDModel * kv_elem));
+        ppos_transpose_kernel<<<kPosRows, 256, 0, st_>>>(im.ppos_tmp, im.layers[l].ppos_t, 1);
+      }
       PKB_CUDA(cudaStreamSynchronize(st_));
       cudaFree(wp.w);
     }
@@ -932,10 +953,17 @@ void Engine::run_encoder(const BatchDev& b) {
     g_tc_site = 256;
     { EpiParams e; e.mode = EPI_QKV; e.out_f32 = im.q; e.ldo = kDModel; e.row_entry = b.row_entry; e.row_pos = b.row_pos;
       e.entry_slot = b.slot; e.entry_head = b.head; e.kring = kr; e.vring = vr; e.kv_f32 = split ? 1 : 0;
+      e.k_natural = im.attn_mma ? 1 : 0;
       RUN_GEMM(im.a_ln, w.qkv, M, nullptr, e); }
-    { AttnArgs a; a.q = im.q; a.kring = kr; a.vring = vr; a.ppos_t = w.ppos_t; a.kv_f32 = split ? 1 : 0; a.bias_u = w.bias_u;
+    if (im.attn_mma) {
+      AttnMmaArgs a; a.q = im.q; a.ppos_n = w.ppos_n; a.bias_u = w.bias_u; a.bias_v = w.bias_v; a.ctx = im.a_ln.out();
+      a.map_k = &im.map_k; a.map_v = &im.map_v; a.layer = l; a.n_slots = opt_.max_streams;
+      launch_attention_mma(b, a, st_); ++launches_;
+    } else {
+      AttnArgs a; a.q = im.q; a.kring = kr; a.vring = vr; a.ppos_t = w.ppos_t; a.kv_f32 = 1; a.bias_u = w.bias_u;
       a.bias_v = w.bias_v; a.ctx = im.a_ln.out();
-      launch_attention(b, a, st_); ++launches_; }
+      launch_attention(b, a, st_); ++launches_;
+    }
     g_tc_site = 512;
     { EpiParams e; e.mode = EPI_RESADD_F32; e.out_f32 = im.x; e.ldo = kDModel; e.scale = 1.0f;
       RUN_GEMM(im.a_ln, w.out, M, nullptr, e); }
@@ -1160,6 +1188,7 @@ void Engine::import_state(int sid, const float* cache_ch, long long, const float
     e.kring = (char*)im.kring + (size_t)l * im.ring_layer_elems * kv_elem;
     e.vring = (char*)im.vring + (size_t)l * im.ring_layer_elems * kv_elem;
     e.kv_f32 = split;
+    e.k_natural = im.attn_mma ? 1 : 0;
     RUN_GEMM(im.a_imp, im.layers[l].kv, kCacheS, nullptr, e);
   }
   PKB_CUDA(cudaStreamSynchronize(st_));

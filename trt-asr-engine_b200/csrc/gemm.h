@@ -45,6 +45,7 @@ struct EpiParams {
   void* kring = nullptr;            // this layer's K^T ring  [slot][head][d][kRingCap]
   void* vring = nullptr;            // this layer's V ring    [slot][kRingCap][1024]
   int kv_f32 = 0;                   // ring element type: 1 = f32 (precise mode), 0 = bf16
+  int k_natural = 0;                // 1: the K ring has the V layout [slot][kRingCap][1024] (tensor-core attention); 0: K^T
 };
 
 struct GemmArgs {
@@ -108,7 +109,11 @@ __device__ __forceinline__ void epilogue_pair(const EpiParams& p, int m, int n, 
         const int e = p.row_entry[m];
         const int slot = p.entry_slot[e];
         const int phys = (p.entry_head[e] + kCacheS + p.row_pos[m]) % kRingCap;
-        if (n < 2 * kDModel) {
+        if (n < 2 * kDModel && p.k_natural) {
+          const size_t i0 = ((size_t)slot * kRingCap + phys) * kDModel + (n - kDModel);
+          if (p.kv_f32) { ((float*)p.kring)[i0] = v0; ((float*)p.kring)[i0 + 1] = v1; }
+          else { ((__nv_bfloat16*)p.kring)[i0] = __float2bfloat16_rn(v0); ((__nv_bfloat16*)p.kring)[i0 + 1] = __float2bfloat16_rn(v1); }
+        } else if (n < 2 * kDModel) {
           const int c = n - kDModel, h = c >> 7, d = c & 127;
           const size_t i0 = (((size_t)slot * kHeads + h) * kDHead + d) * kRingCap + phys;
           if (p.kv_f32) { ((float*)p.kring)[i0] = v0; ((float*)p.kring)[i0 + kRingCap] = v1; }

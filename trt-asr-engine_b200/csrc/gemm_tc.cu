@@ -180,7 +180,11 @@ __device__ __forceinline__ void epilogue_quad(const EpiParams& p, int m, int n, 
       const int e = p.row_entry[m];
       const int slot = p.entry_slot[e];
       const int phys = (p.entry_head[e] + kCacheS + p.row_pos[m]) % kRingCap;
-      if (nn < 2 * kDModel) {
+      if (nn < 2 * kDModel && p.k_natural) {
+        const size_t i0 = ((size_t)slot * kRingCap + phys) * kDModel + (nn - kDModel);
+        if (p.kv_f32) *reinterpret_cast<float4*>((float*)p.kring + i0) = v;
+        else *reinterpret_cast<uint2*>((__nv_bfloat16*)p.kring + i0) = pack4_bf16(v.x, v.y, v.z, v.w);
+      } else if (nn < 2 * kDModel) {
         const int c = nn - kDModel, h = c >> 7, d = c & 127;
         const size_t i0 = (((size_t)slot * kHeads + h) * kDHead + d) * kRingCap + phys;   // K^T ring: 4 rows kRingCap apart
         if (p.kv_f32) {
