@@ -3,11 +3,11 @@
 // Semantics: NeMo RelPositionMultiHeadAttention with a cache (see enc_kernels.cu); scores (q+u)K^T + rel_shift((q+v)P^T),
 // scaled by 1/sqrt(128), masked to the valid cache suffix and the new rows, softmax, times V.
 //
-// One CTA (4 warps) per (stream, head).  The kernel is HBM-bound by design: per (stream, head) it must read the 288 x 128
+// Persistent kernel, one CTA per SM, work item = (stream, head).  HBM-bound by design: per item it must read the 288 x 128
 // bf16 K and V ring slices (147 KB), everything else is on-chip.
 //   * K and V rings are [slot][288][1024] bf16; the slices are fetched with TMA (96-key x 64-dim boxes, 128-byte swizzle)
-//     into a 3-stage shared-memory ring: all three K blocks are in flight from the first instruction, each V block is
-//     requested as soon as the S phase has consumed the K block that occupied its stage.
+//     by a dedicated producer warp into a 6-stage shared-memory ring (full/empty mbarriers): the producer runs a whole
+//     item ahead of the 8 consumer warps, so the loads of item i+1 overlap the math of item i.
 //   * keys are walked in PHYSICAL ring order (the softmax sum does not care), so a wrapped FIFO needs no second copy and
 //     every box is one contiguous row range; validity and the relative position of slot p follow from the ring head.
 //   * all products run on mma.sync m16n8k16 (bf16 -> f32): G = (q+v) P^T first (P comes from L2, this hides the K
@@ -77,260 +77,315 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
+constexpr int kConsumerWarps = 8;
+constexpr int kAttnThreads = 32 * (1 + kConsumerWarps);       // warp 0: TMA producer
+constexpr int kConsumerThreads = 32 * kConsumerWarps;
+
 template <int R>
 struct Smem {
+  static constexpr int kStages = R == 8 ? 6 : R == 16 ? 5 : 4;
   static constexpr int kS = R * kSPitch * 4;
   static constexpr int kG = R * kGPitch * 4;             // later reused for the bf16 probabilities (R_pad x 592 B <= kG)
-  static constexpr size_t kBytes = 1024 + (size_t)kNumBlk * kStageBytes + kS + kG + 64;
+  static constexpr size_t kBytes = 1024 + (size_t)kStages * kStageBytes + kS + kG + 128;
 };
 
-// R = 8 (rows 8..15 of every m16 tile are identically zero and never loaded / stored), 16 or 32.
-template <int R>
-__global__ void __launch_bounds__(128)
-attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v, BatchDev b, AttnMmaArgs a) {
-  constexpr int MT = R <= 16 ? 1 : 2;
-  constexpr bool kHalf = R == 8;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* s_ring = base;
-  float* s_S = reinterpret_cast<float*>(base + kNumBlk * kStageBytes);
-  float* s_G = s_S + R * kSPitch;
-  uint8_t* s_P = reinterpret_cast<uint8_t*>(s_G);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_G) + Smem<R>::kG);
-
-  const int e = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int Tq = b.Tq[e], qlen = b.qlen[e], len = b.len[e], head = b.head[e], slot = b.slot[e];
-  const int row0 = b.row_off[e];
-
-  // which 96-key blocks hold at least one valid key (physical order; valid logical j in [256-len, 256+qlen))
-  const int v_start = (head + kCacheS - len) % kRingCap, v_cnt = len + qlen;
-  unsigned need = 0;
+struct Item {
+  int Tq, qlen, len, head, row0, ring_row0;
+  unsigned need;      // bit k: 96-key block k holds at least one valid key
+};
+__device__ __forceinline__ Item load_item(const BatchDev& b, const AttnMmaArgs& a, int e) {
+  Item it;
+  it.Tq = b.Tq[e]; it.qlen = b.qlen[e]; it.len = b.len[e]; it.head = b.head[e]; it.row0 = b.row_off[e];
+  it.ring_row0 = (a.layer * a.n_slots + b.slot[e]) * kRingCap;
+  // valid logical positions j in [256-len, 256+qlen) form one circular run of physical slots
+  const int v_start = (it.head + kCacheS - it.len) % kRingCap, v_cnt = it.len + it.qlen;
+  it.need = 0;
 #pragma unroll
   for (int k = 0; k < kNumBlk; ++k) {
     const int lo = k * kBlkKeys;
-    if (((lo - v_start + kRingCap) % kRingCap) < v_cnt || ((v_start - lo + kRingCap) % kRingCap) < kBlkKeys) need |= 1u << k;
+    if (((lo - v_start + kRingCap) % kRingCap) < v_cnt || ((v_start - lo + kRingCap) % kRingCap) < kBlkKeys) it.need |= 1u << k;
   }
-  const int ring_row0 = (a.layer * a.n_slots + slot) * kRingCap;
+  return it;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
 
+// Persistent: one CTA per SM walks (stream, head) items; the producer warp streams the K then V blocks of successive items
+// through the ring without waiting for the math, so HBM stays busy while the consumers are in their on-chip phases.
+// R = 8 (rows 8..15 of every m16 tile are identically zero and never loaded / stored), 16 or 32.
+template <int R>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v, BatchDev b, AttnMmaArgs a) {
+  constexpr int MT = R <= 16 ? 1 : 2;
+  constexpr bool kHalf = R == 8;
+  constexpr int kStages = Smem<R>::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_ring = base;
+  float* s_S = reinterpret_cast<float*>(base + kStages * kStageBytes);
+  float* s_G = s_S + R * kSPitch;
+  uint8_t* s_P = reinterpret_cast<uint8_t*>(s_G);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_G) + Smem<R>::kG);
+  uint64_t* empty_bar = full_bar + kStages;
+
+  const int n_items = b.B * kHeads;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
 #pragma unroll
-    for (int k = 0; k < kNumBlk; ++k) mbar_init(&full_bar[k], 1);
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kConsumerWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // ===== producer =====
+    if (lane == 0) {
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int e = item >> 3, h = item & 7;
+        const Item im = load_item(b, a, e);
 #pragma unroll
-    for (int k = 0; k < kNumBlk; ++k) {
-      if (!((need >> k) & 1u)) continue;
-      mbar_expect_tx(&full_bar[k], kStageBytes);
-      tma_load_2d(s_ring + k * kStageBytes, &map_k, &full_bar[k], h * kDHead, ring_row0 + k * kBlkKeys);
-      tma_load_2d(s_ring + k * kStageBytes + kBoxBytes, &map_k, &full_bar[k], h * kDHead + 64, ring_row0 + k * kBlkKeys);
+        for (int kv = 0; kv < 2; ++kv) {
+          const CUtensorMap* map = kv ? &map_v : &map_k;
+#pragma unroll
+          for (int k = 0; k < kNumBlk; ++k) {
+            if (!((im.need >> k) & 1u)) continue;
+            const int s = it % kStages;
+            mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
+            mbar_expect_tx(&full_bar[s], kStageBytes);
+            tma_load_2d(s_ring + s * kStageBytes, map, &full_bar[s], h * kDHead, im.ring_row0 + k * kBlkKeys);
+            tma_load_2d(s_ring + s * kStageBytes + kBoxBytes, map, &full_bar[s], h * kDHead + 64, im.ring_row0 + k * kBlkKeys);
+            ++it;
+          }
+        }
+      }
     }
+    return;
   }
 
-  // ---- query fragments.  qu: natural k order (matches ldmatrix on the K tiles); qv: permuted k order (matches the
-  //      16-byte-per-lane global loads of the position table): k-step (blk, s) lane t covers d = 32 blk + 8 t + 4 s + {0..3}
-  uint32_t qu[MT][8][4], qv[MT][8][4];
-  {
-    const float* bu = a.bias_u + h * kDHead;
-    const float* bv = a.bias_v + h * kDHead;
+  // ===== consumers =====
+  const int cw = warp - 1, g = lane >> 2, t = lane & 3;
+  const float scale = 0.08838834764831845f;       // 1/sqrt(128)
+  const uint32_t sp = smem_u32(s_P);
+  int it = 0;
+#pragma unroll 1
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int e = item >> 3, h = item & 7;
+    const Item im = load_item(b, a, e);
+    const int Tq = im.Tq;
+
+    // ---- query fragments from the bf16 planes written by the QKV epilogue (q+u: natural k order for ldmatrix on the
+    //      K tiles; q+v: permuted k order matching the 16-byte-per-lane loads of the position table, k-step (blk, s):
+    //      lane t covers d = 32 blk + 8 t + 4 s + {0..3})
+    uint32_t qu[MT][8][4], qv[MT][8][4];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
       for (int hr = 0; hr < 2; ++hr) {
         const int i = 16 * mt + g + 8 * hr;
         const bool ok = i < Tq && !(kHalf && hr == 1);
-        const float* qrow = a.q + (size_t)(row0 + (ok ? i : 0)) * kDModel + h * kDHead;
+        const __nv_bfloat16* qrow = a.q_bf16 + (size_t)(im.row0 + (ok ? i : 0)) * kDModel + h * kDHead;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-#pragma unroll
-          for (int part = 0; part < 2; ++part) {
-            const int du = 16 * ks + 8 * part + 2 * t;
-            const int dv = 32 * (ks >> 1) + 8 * t + 4 * (ks & 1) + 2 * part;
-            uint32_t pu = 0, pv = 0;
-            if (ok) {
-              const float2 x = *reinterpret_cast<const float2*>(qrow + du);
-              const float2 y = *reinterpret_cast<const float2*>(qrow + dv);
-              pu = pack_bf16x2(x.x + bu[du], x.y + bu[du + 1]);
-              pv = pack_bf16x2(y.x + bv[dv], y.y + bv[dv + 1]);
-            }
-            qu[mt][ks][hr + 2 * part] = pu;
-            qv[mt][ks][hr + 2 * part] = pv;
-          }
+          qu[mt][ks][hr] = ok ? *reinterpret_cast<const uint32_t*>(qrow + 16 * ks + 2 * t) : 0u;
+          qu[mt][ks][hr + 2] = ok ? *reinterpret_cast<const uint32_t*>(qrow + 16 * ks + 8 + 2 * t) : 0u;
         }
-      }
-    }
-  }
-
-  // ---- G[i][r] = (q_i + v) . P[r]  for the table rows this chunk can touch
-  {
-    const int r_lo = kPosNeg - (Tq - 1), r_hi = kPosNeg + kCacheS + Tq;      // rows [r_lo, r_hi)
-    const __nv_bfloat16* pn = a.ppos_n + (size_t)h * kPosRowsPad * kDHead;
-    for (int nt = (r_lo >> 3) + warp; nt * 8 < r_hi; nt += 4) {
-      const uint4* prow = reinterpret_cast<const uint4*>(pn + (size_t)(nt * 8 + g) * kDHead) + t;
-      uint4 w[4];
-#pragma unroll
-      for (int blk = 0; blk < 4; ++blk) w[blk] = __ldg(prow + 4 * blk);
-#pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int blk = 0; blk < 4; ++blk) {
-          mma_bf16(c, qv[mt][2 * blk], w[blk].x, w[blk].y);
-          mma_bf16(c, qv[mt][2 * blk + 1], w[blk].z, w[blk].w);
+          uint4 w = make_uint4(0u, 0u, 0u, 0u);
+          if (ok) w = *reinterpret_cast<const uint4*>(qrow + a.q_plane + 32 * blk + 8 * t);
+          qv[mt][2 * blk][hr] = w.x; qv[mt][2 * blk][hr + 2] = w.y;
+          qv[mt][2 * blk + 1][hr] = w.z; qv[mt][2 * blk + 1][hr + 2] = w.w;
         }
-        *reinterpret_cast<float2*>(s_G + (16 * mt + g) * kGPitch + nt * 8 + 2 * t) = make_float2(c[0], c[1]);
-        if (!kHalf) *reinterpret_cast<float2*>(s_G + (16 * mt + g + 8) * kGPitch + nt * 8 + 2 * t) = make_float2(c[2], c[3]);
       }
     }
-  }
-  __syncthreads();      // G complete; barrier inits visible to all waiters
 
-  // ---- S phase: scores for every needed key block, combined with the skewed position term, masked, scaled
-  const float scale = 0.08838834764831845f;       // 1/sqrt(128)
-#pragma unroll 1
-  for (int k = 0; k < kNumBlk; ++k) {
-    if (!((need >> k) & 1u)) continue;
-    mbar_wait(&full_bar[k], 0);
-    const uint32_t st = smem_u32(s_ring + k * kStageBytes);
-#pragma unroll 1
-    for (int nb = warp; nb < kBlkKeys / 8; nb += 4) {
-      float c[MT][4];
+    // ---- G[i][r] = (q_i + v) . P[r]  for the table rows this chunk can touch (P from L2; software-pipelined loads)
+    {
+      const int r_lo = kPosNeg - (Tq - 1), r_hi = kPosNeg + kCacheS + Tq;      // rows [r_lo, r_hi)
+      const __nv_bfloat16* pn = a.ppos_n + (size_t)h * kPosRowsPad * kDHead;
+      int nt = (r_lo >> 3) + cw;
+      uint4 w[4], wn[4];
+      if (nt * 8 < r_hi) {
+        const uint4* prow = reinterpret_cast<const uint4*>(pn + (size_t)(nt * 8 + g) * kDHead) + t;
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) { c[mt][0] = c[mt][1] = c[mt][2] = c[mt][3] = 0.f; }
-      const int key_l = 8 * nb + (lane & 7), mi = lane >> 3;
+        for (int blk = 0; blk < 4; ++blk) w[blk] = __ldg(prow + 4 * blk);
+      }
+      for (; nt * 8 < r_hi; nt += kConsumerWarps) {
+        const bool more = (nt + kConsumerWarps) * 8 < r_hi;
+        if (more) {
+          const uint4* prow = reinterpret_cast<const uint4*>(pn + (size_t)((nt + kConsumerWarps) * 8 + g) * kDHead) + t;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int chunk = 4 * (u & 1) + mi;
-        const uint32_t addr = st + (u >> 1) * kBoxBytes + key_l * 128 + ((chunk ^ (key_l & 7)) << 4);
-        uint32_t r0, r1, r2, r3;
-        ldsm_x4(addr, r0, r1, r2, r3);
-        const int ks = 4 * (u >> 1) + 2 * (u & 1);
+          for (int blk = 0; blk < 4; ++blk) wn[blk] = __ldg(prow + 4 * blk);
+        }
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-          mma_bf16(c[mt], qu[mt][ks], r0, r1);
-          mma_bf16(c[mt], qu[mt][ks + 1], r2, r3);
-        }
-      }
+          float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-#pragma unroll
-        for (int hr = 0; hr < (kHalf ? 1 : 2); ++hr) {
-          const int i = 16 * mt + g + 8 * hr;
-          if (i >= Tq) continue;
-          float out[2];
-#pragma unroll
-          for (int x = 0; x < 2; ++x) {
-            const int p = k * kBlkKeys + 8 * nb + 2 * t + x;
-            const int j = (p - head + kRingCap) % kRingCap;
-            const bool valid = j >= kCacheS - len && j < kCacheS + qlen;
-            out[x] = valid ? (c[mt][2 * hr + x] + s_G[i * kGPitch + (kCacheS + i - j) + kPosNeg]) * scale : -INFINITY;
+          for (int blk = 0; blk < 4; ++blk) {
+            mma_bf16(c, qv[mt][2 * blk], w[blk].x, w[blk].y);
+            mma_bf16(c, qv[mt][2 * blk + 1], w[blk].z, w[blk].w);
           }
-          *reinterpret_cast<float2*>(s_S + i * kSPitch + k * kBlkKeys + 8 * nb + 2 * t) = make_float2(out[0], out[1]);
+          *reinterpret_cast<float2*>(s_G + (16 * mt + g) * kGPitch + nt * 8 + 2 * t) = make_float2(c[0], c[1]);
+          if (!kHalf) *reinterpret_cast<float2*>(s_G + (16 * mt + g + 8) * kGPitch + nt * 8 + 2 * t) = make_float2(c[2], c[3]);
         }
+#pragma unroll
+        for (int blk = 0; blk < 4; ++blk) w[blk] = wn[blk];
       }
     }
-    __syncthreads();      // every warp is done with K block k (and, after the last block, with s_G)
-    if (tid == 0) {       // its stage now receives V block k
-      mbar_expect_tx(&full_bar[k], kStageBytes);
-      tma_load_2d(s_ring + k * kStageBytes, &map_v, &full_bar[k], h * kDHead, ring_row0 + k * kBlkKeys);
-      tma_load_2d(s_ring + k * kStageBytes + kBoxBytes, &map_v, &full_bar[k], h * kDHead + 64, ring_row0 + k * kBlkKeys);
-    }
-  }
+    consumer_sync();      // G complete
 
-  // ---- softmax (fp32) -> bf16 probabilities in the A-operand layout [rows][296] (rows >= Tq and skipped blocks are zero)
-  constexpr int RP = kHalf ? 8 : 16 * MT;
-  for (int i = warp; i < RP; i += 4) {
-    __nv_bfloat16* prow = reinterpret_cast<__nv_bfloat16*>(s_P + i * kPPitchB);
-    float v[kRingCap / 32];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int x = 0; x < kRingCap / 32; ++x) {
-      const int p = lane + 32 * x;
-      v[x] = (i < Tq && ((need >> (p / kBlkKeys)) & 1u)) ? s_S[i * kSPitch + p] : -INFINITY;
-      mx = fmaxf(mx, v[x]);
-    }
-    mx = warp_max(mx);
-    float sum = 0.f;
-#pragma unroll
-    for (int x = 0; x < kRingCap / 32; ++x) {
-      v[x] = mx > -INFINITY ? __expf(v[x] - mx) : 0.f;
-      sum += v[x];
-    }
-    sum = warp_sum(sum);
-    const float inv = (i < qlen && sum > 0.f) ? 1.f / sum : 0.f;      // padded query rows are fully masked -> zeros
-#pragma unroll
-    for (int x = 0; x < kRingCap / 32; ++x) prow[lane + 32 * x] = __float2bfloat16_rn(v[x] * inv);
-  }
-  __syncthreads();
-
-  // ---- O = P V : warp w owns head dims [32 w, 32 w + 32)
-  float o[MT][4][4];
-#pragma unroll
-  for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) { o[mt][nt][0] = o[mt][nt][1] = o[mt][nt][2] = o[mt][nt][3] = 0.f; }
-  const uint32_t sp = smem_u32(s_P);
+    // ---- S phase: scores for every needed key block, combined with the skewed position term, masked, scaled
 #pragma unroll 1
-  for (int k = 0; k < kNumBlk; ++k) {
-    if (!((need >> k) & 1u)) continue;
-    mbar_wait(&full_bar[k], 1);
-    const uint32_t st = smem_u32(s_ring + k * kStageBytes);
+    for (int k = 0; k < kNumBlk; ++k) {
+      if (!((im.need >> k) & 1u)) continue;
+      const int s = it % kStages;
+      mbar_wait(&full_bar[s], (it / kStages) & 1);
+      ++it;
+      const uint32_t st = smem_u32(s_ring + s * kStageBytes);
+#pragma unroll 1
+      for (int nb = cw; nb < kBlkKeys / 8; nb += kConsumerWarps) {
+        float c[MT][4];
 #pragma unroll
-    for (int kk = 0; kk < kBlkKeys / 16; ++kk) {
-      const int key0 = k * kBlkKeys + 16 * kk;
-      uint32_t af[MT][4];
+        for (int mt = 0; mt < MT; ++mt) { c[mt][0] = c[mt][1] = c[mt][2] = c[mt][3] = 0.f; }
+        const int key_l = 8 * nb + (lane & 7), mi = lane >> 3;
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        if (kHalf) {
-          const int l = lane & 15;      // .x2 takes its row addresses from lanes 0..15
-          ldsm_x2(sp + (l & 7) * kPPitchB + (key0 + (l >> 3) * 8) * 2, af[mt][0], af[mt][2]);
-          af[mt][1] = 0u; af[mt][3] = 0u;
-        } else {
-          const int mi = lane >> 3, ri = lane & 7;
-          ldsm_x4(sp + (16 * mt + (mi & 1) * 8 + ri) * kPPitchB + (key0 + (mi >> 1) * 8) * 2, af[mt][0], af[mt][1], af[mt][2], af[mt][3]);
+        for (int u = 0; u < 4; ++u) {
+          const int chunk = 4 * (u & 1) + mi;
+          const uint32_t addr = st + (u >> 1) * kBoxBytes + key_l * 128 + ((chunk ^ (key_l & 7)) << 4);
+          uint32_t r0, r1, r2, r3;
+          ldsm_x4(addr, r0, r1, r2, r3);
+          const int ks = 4 * (u >> 1) + 2 * (u & 1);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            mma_bf16(c[mt], qu[mt][ks], r0, r1);
+            mma_bf16(c[mt], qu[mt][ks + 1], r2, r3);
+          }
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+          for (int hr = 0; hr < (kHalf ? 1 : 2); ++hr) {
+            const int i = 16 * mt + g + 8 * hr;
+            if (i >= Tq) continue;
+            float out[2];
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+              const int p = k * kBlkKeys + 8 * nb + 2 * t + x;
+              int j = p - im.head;
+              j += j < 0 ? kRingCap : 0;
+              const bool valid = j >= kCacheS - im.len && j < kCacheS + im.qlen;
+              out[x] = valid ? (c[mt][2 * hr + x] + s_G[i * kGPitch + (kCacheS + i - j) + kPosNeg]) * scale : -INFINITY;
+            }
+            *reinterpret_cast<float2*>(s_S + i * kSPitch + k * kBlkKeys + 8 * nb + 2 * t) = make_float2(out[0], out[1]);
+          }
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);      // this warp is done with the K block
+    }
+    consumer_sync();      // scores complete; nobody reads s_G any more
+
+    // ---- softmax (fp32) -> bf16 probabilities in the A-operand layout [rows][296] (rows >= Tq and skipped blocks are zero)
+    constexpr int RP = kHalf ? 8 : 16 * MT;
+    for (int i = cw; i < RP; i += kConsumerWarps) {
+      __nv_bfloat16* prow = reinterpret_cast<__nv_bfloat16*>(s_P + i * kPPitchB);
+      float v[kRingCap / 32];
+      float mx = -INFINITY;
 #pragma unroll
-      for (int np = 0; np < 2; ++np) {
+      for (int x = 0; x < kRingCap / 32; ++x) {
+        const int p = lane + 32 * x;
+        v[x] = (i < Tq && ((im.need >> (p / kBlkKeys)) & 1u)) ? s_S[i * kSPitch + p] : -INFINITY;
+        mx = fmaxf(mx, v[x]);
+      }
+      mx = warp_max(mx);
+      float sum = 0.f;
+#pragma unroll
+      for (int x = 0; x < kRingCap / 32; ++x) {
+        v[x] = mx > -INFINITY ? __expf(v[x] - mx) : 0.f;
+        sum += v[x];
+      }
+      sum = warp_sum(sum);
+      const float inv = (i < im.qlen && sum > 0.f) ? 1.f / sum : 0.f;      // padded query rows are fully masked -> zeros
+#pragma unroll
+      for (int x = 0; x < kRingCap / 32; ++x) prow[lane + 32 * x] = __float2bfloat16_rn(v[x] * inv);
+    }
+    consumer_sync();
+
+    // ---- O = P V : consumer warp cw owns head dims [16 cw, 16 cw + 16)
+    float o[MT][2][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) { o[mt][nt][0] = o[mt][nt][1] = o[mt][nt][2] = o[mt][nt][3] = 0.f; }
+#pragma unroll 1
+    for (int k = 0; k < kNumBlk; ++k) {
+      if (!((im.need >> k) & 1u)) continue;
+      const int s = it % kStages;
+      mbar_wait(&full_bar[s], (it / kStages) & 1);
+      ++it;
+      const uint32_t st = smem_u32(s_ring + s * kStageBytes);
+#pragma unroll
+      for (int kk = 0; kk < kBlkKeys / 16; ++kk) {
+        const int key0 = k * kBlkKeys + 16 * kk;
+        uint32_t af[MT][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          if (kHalf) {
+            const int l = lane & 15;      // .x2 takes its row addresses from lanes 0..15
+            ldsm_x2(sp + (l & 7) * kPPitchB + (key0 + (l >> 3) * 8) * 2, af[mt][0], af[mt][2]);
+            af[mt][1] = 0u; af[mt][3] = 0u;
+          } else {
+            const int mi = lane >> 3, ri = lane & 7;
+            ldsm_x4(sp + (16 * mt + (mi & 1) * 8 + ri) * kPPitchB + (key0 + (mi >> 1) * 8) * 2, af[mt][0], af[mt][1], af[mt][2], af[mt][3]);
+          }
+        }
         const int mi = lane >> 3, ri = lane & 7;
         const int key_l = 16 * kk + (mi & 1) * 8 + ri;
-        const int chunk_g = 4 * warp + 2 * np + (mi >> 1);       // 16-byte chunk over the 128 head dims
+        const int chunk_g = 2 * cw + (mi >> 1);                  // 16-byte chunk over the 128 head dims
         const uint32_t addr = st + (chunk_g >> 3) * kBoxBytes + key_l * 128 + (((chunk_g & 7) ^ (key_l & 7)) << 4);
         uint32_t r0, r1, r2, r3;
         ldsm_x4_t(addr, r0, r1, r2, r3);
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-          mma_bf16(o[mt][2 * np], af[mt], r0, r1);
-          mma_bf16(o[mt][2 * np + 1], af[mt], r2, r3);
+          mma_bf16(o[mt][0], af[mt], r0, r1);
+          mma_bf16(o[mt][1], af[mt], r2, r3);
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
-  }
 
-  // ---- context rows -> bf16 operand of the output projection
+    // ---- context rows -> bf16 operand of the output projection
 #pragma unroll
-  for (int mt = 0; mt < MT; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-    for (int hr = 0; hr < (kHalf ? 1 : 2); ++hr) {
-      const int i = 16 * mt + g + 8 * hr;
-      if (i >= Tq) continue;
-      __nv_bfloat16* dst = a.ctx.ptr + (size_t)(row0 + i) * a.ctx.lda + h * kDHead + 32 * warp + 2 * t;
+      for (int hr = 0; hr < (kHalf ? 1 : 2); ++hr) {
+        const int i = 16 * mt + g + 8 * hr;
+        if (i >= Tq) continue;
+        __nv_bfloat16* dst = a.ctx.ptr + (size_t)(im.row0 + i) * a.ctx.lda + h * kDHead + 16 * cw + 2 * t;
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-        *reinterpret_cast<uint32_t*>(dst + 8 * nt) = pack_bf16x2(o[mt][nt][2 * hr], o[mt][nt][2 * hr + 1]);
-    }
+        for (int nt = 0; nt < 2; ++nt)
+          *reinterpret_cast<uint32_t*>(dst + 8 * nt) = pack_bf16x2(o[mt][nt][2 * hr], o[mt][nt][2 * hr + 1]);
+      }
+    consumer_sync();      // every warp is done with s_P before the next item's G phase overwrites it
+  }
 }
 
 template <int R>
-void launch_r(const BatchDev& b, const AttnMmaArgs& a, cudaStream_t st) {
+void launch_r(const BatchDev& b, const AttnMmaArgs& a, int sms, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
     PKB_CUDA(cudaFuncSetAttribute(attention_mma_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<R>::kBytes));
     attr = true;
   }
-  attention_mma_kernel<R><<<dim3(b.B, kHeads), 128, Smem<R>::kBytes, st>>>(*reinterpret_cast<const CUtensorMap*>(a.map_k),
-                                                                              *reinterpret_cast<const CUtensorMap*>(a.map_v), b, a);
+  const int items = b.B * kHeads;
+  attention_mma_kernel<R><<<items < sms ? items : sms, kAttnThreads, Smem<R>::kBytes, st>>>(
+      *reinterpret_cast<const CUtensorMap*>(a.map_k), *reinterpret_cast<const CUtensorMap*>(a.map_v), b, a);
   PKB_CUDA(cudaGetLastError());
 }
 
@@ -339,9 +394,15 @@ void launch_r(const BatchDev& b, const AttnMmaArgs& a, cudaStream_t st) {
 void launch_attention_mma(const BatchDev& b, const AttnMmaArgs& a, cudaStream_t st) {
   if (b.B <= 0) return;
   PKB_CHECK(a.ctx.lo_off == 0, "attention_mma: bf16 mode only");
-  if (b.max_Tq <= 8) launch_r<8>(b, a, st);
-  else if (b.max_Tq <= 16) launch_r<16>(b, a, st);
-  else launch_r<32>(b, a, st);
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    PKB_CUDA(cudaGetDevice(&dev));
+    PKB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  if (b.max_Tq <= 8) launch_r<8>(b, a, sms, st);
+  else if (b.max_Tq <= 16) launch_r<16>(b, a, sms, st);
+  else launch_r<32>(b, a, sms, st);
 }
 
 }  // namespace pkb

@@ -75,10 +75,9 @@ void launch_attention(const BatchDev& b, const AttnArgs& a, cudaStream_t st);
 // bf16 tensor-core version (attn_mma.cu): K and V rings both in the natural layout [layer][slot][kRingCap][1024] bf16, fetched by
 // TMA through `map_k` / `map_v` (2-D maps over [layers*slots*kRingCap, 1024], box 96 x 64, 128-byte swizzle).
 struct AttnMmaArgs {
-  const float* q;                // [M,1024] f32
+  const __nv_bfloat16* q_bf16;   // [2][Mcap,1024] bf16: plane 0 = q + pos_bias_u, plane 1 (q_plane elements further) = q + pos_bias_v
+  long long q_plane;
   const __nv_bfloat16* ppos_n;   // this layer's projected position table, natural layout [head][kPosRowsPad][128]
-  const float* bias_u;           // [8,128]
-  const float* bias_v;
   ActOut ctx;                    // [M,1024] bf16
   const void* map_k;             // host pointers to 128-byte CUtensorMap objects
   const void* map_v;

@@ -179,6 +179,7 @@ struct Engine::Impl {
   // work buffers
   int Mcap = 0, Bcap = 0, T3cap = 0, T2cap = 0;
   ActBuf a_sub1, a_sub2, a_sub3, a_ln, a_ff, a_xf, a_hid, a_pred, a_g, a_imp, a_pos;
+  __nv_bfloat16* q_bf16 = nullptr;       // bf16 mode: [2][Mcap,1024] (q + pos_bias_u | q + pos_bias_v)
   float *x = nullptr, *q = nullptr, *cglu = nullptr, *y1 = nullptr, *enc_proj = nullptr, *logits = nullptr, *gates = nullptr,
         *enc_out = nullptr, *ppos_tmp = nullptr, *scratch_f32 = nullptr;
   size_t scratch_f32_elems = 0;
@@ -508,6 +509,7 @@ void Engine::alloc_state() {
   im.a_pos = make_act(kPosRows, kDModel, true, st_);
   im.x = dev_alloc<float>((size_t)im.Mcap * kDModel);
   im.q = dev_alloc<float>((size_t)im.Mcap * kDModel);
+  if (im.attn_mma) im.q_bf16 = dev_alloc<__nv_bfloat16>((size_t)2 * im.Mcap * kDModel);
   im.cglu = dev_alloc<float>((size_t)im.Mcap * kDModel);
   im.y1 = dev_alloc<float>((size_t)im.T2cap * 32 * kSubCh);
   im.enc_proj = dev_alloc<float>((size_t)std::max(im.Mcap, rows_dec) * kJointH);
@@ -954,9 +956,10 @@ void Engine::run_encoder(const BatchDev& b) {
     { EpiParams e; e.mode = EPI_QKV; e.out_f32 = im.q; e.ldo = kDModel; e.row_entry = b.row_entry; e.row_pos = b.row_pos;
       e.entry_slot = b.slot; e.entry_head = b.head; e.kring = kr; e.vring = vr; e.kv_f32 = split ? 1 : 0;
       e.k_natural = im.attn_mma ? 1 : 0;
+      if (im.attn_mma) { e.q_bf16 = im.q_bf16; e.q_plane = (long long)im.Mcap * kDModel; e.bias_u = w.bias_u; e.bias_v = w.bias_v; }
       RUN_GEMM(im.a_ln, w.qkv, M, nullptr, e); }
     if (im.attn_mma) {
-      AttnMmaArgs a; a.q = im.q; a.ppos_n = w.ppos_n; a.bias_u = w.bias_u; a.bias_v = w.bias_v; a.ctx = im.a_ln.out();
+      AttnMmaArgs a; a.q_bf16 = im.q_bf16; a.q_plane = (long long)im.Mcap * kDModel; a.ppos_n = w.ppos_n; a.ctx = im.a_ln.out();
       a.map_k = &im.map_k; a.map_v = &im.map_v; a.layer = l; a.n_slots = opt_.max_streams;
       launch_attention_mma(b, a, st_); ++launches_;
     } else {

@@ -45,6 +45,10 @@ struct EpiParams {
   void* kring = nullptr;            // this layer's K^T ring  [slot][head][d][kRingCap]
   void* vring = nullptr;            // this layer's V ring    [slot][kRingCap][1024]
   int kv_f32 = 0;                   // ring element type: 1 = f32 (precise mode), 0 = bf16
+  __nv_bfloat16* q_bf16 = nullptr;  // non-null: q leaves as two bf16 planes (q + pos_bias_u, q + pos_bias_v) instead of f32
+  long long q_plane = 0;            // elements between the planes
+  const float* bias_u = nullptr;    // [1024] = pos_bias_u[head][128] flattened
+  const float* bias_v = nullptr;
   int k_natural = 0;                // 1: the K ring has the V layout [slot][kRingCap][1024] (tensor-core attention); 0: K^T
 };
 
@@ -102,7 +106,11 @@ __device__ __forceinline__ void epilogue_pair(const EpiParams& p, int m, int n, 
       p.out_f32[(size_t)m * p.ldo + (n >> 1)] = v0 * sigmoidf_(v1);
       break;
     case EPI_QKV: {
-      if (n < kDModel) {
+      if (n < kDModel && p.q_bf16) {
+        __nv_bfloat16* q = p.q_bf16 + (size_t)m * kDModel + n;
+        q[0] = __float2bfloat16_rn(v0 + p.bias_u[n]); q[1] = __float2bfloat16_rn(v1 + p.bias_u[n + 1]);
+        q[p.q_plane] = __float2bfloat16_rn(v0 + p.bias_v[n]); q[p.q_plane + 1] = __float2bfloat16_rn(v1 + p.bias_v[n + 1]);
+      } else if (n < kDModel) {
         p.out_f32[(size_t)m * p.ldo + n] = v0;
         p.out_f32[(size_t)m * p.ldo + n + 1] = v1;
       } else {

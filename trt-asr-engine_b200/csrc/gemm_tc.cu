@@ -126,87 +126,80 @@ __device__ __forceinline__ void store_act4(__nv_bfloat16* A, size_t row, int lda
   }
 }
 
-// Fused epilogue on 4 adjacent columns n..n+3 (n % 4 == 0, n < N) of row m.
-__device__ __forceinline__ void epilogue_quad(const EpiParams& p, int m, int n, int N, float4 v) {
-  const bool f32_rows = p.mode == EPI_F32 || p.mode == EPI_BIAS_F32 || p.mode == EPI_BIAS_RELU_F32 || p.mode == EPI_BIAS_ROWMAP_F32 ||
-                        p.mode == EPI_RESADD_F32;
-  if (n + 3 >= N || (f32_rows && (p.ldo & 3))) {
-    // ragged right edge (N = 8198) or rows that are not 16-byte aligned: pairwise path
-    epilogue_pair(p, m, n, N, v.x, v.y);
-    if (n + 2 < N) epilogue_pair(p, m, n + 2, N, v.z, v.w);
-    return;
-  }
+// Ragged right edge (N = 8198) or output rows that are not 16-byte aligned: generic pairwise path, kept out of line so
+// that the hot loop of every specialisation stays small enough for the instruction cache.
+__device__ __noinline__ void epilogue_edge(const EpiParams& p, int m, int n, int N, float4 v) {
+  epilogue_pair(p, m, n, N, v.x, v.y);
+  if (n + 2 < N) epilogue_pair(p, m, n + 2, N, v.z, v.w);
+}
+
+// Fused epilogue on 4 adjacent columns n..n+3 (n % 4 == 0, n + 3 < N) of row m; MODE is a compile-time EpiMode.
+template <int MODE>
+__device__ __forceinline__ void epilogue_quad(const EpiParams& p, int m, int n, float4 v) {
   const int nn = n + p.n_off;
-  switch (p.mode) {
-    case EPI_F32:
-      *reinterpret_cast<float4*>(p.out_f32 + (size_t)m * p.ldo + nn) = v;
-      break;
-    case EPI_BIAS_F32:
-    case EPI_BIAS_RELU_F32:
-    case EPI_BIAS_ROWMAP_F32: {
-      const float4 b = *reinterpret_cast<const float4*>(p.bias + nn);
-      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-      if (p.mode == EPI_BIAS_RELU_F32) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-      int r = m;
-      if (p.mode == EPI_BIAS_ROWMAP_F32) { r = p.row_map[m]; if (r < 0) break; }
-      *reinterpret_cast<float4*>(p.out_f32 + (size_t)r * p.ldo + nn) = v;
-      break;
-    }
-    case EPI_BIAS_RELU_ACT: {
-      const float4 b = *reinterpret_cast<const float4*>(p.bias + nn);
-      v.x = fmaxf(v.x + b.x, 0.f); v.y = fmaxf(v.y + b.y, 0.f); v.z = fmaxf(v.z + b.z, 0.f); v.w = fmaxf(v.w + b.w, 0.f);
-      store_act4(p.out_act, m, p.lda_out, nn, v, p.lo_off_out);
-      break;
-    }
-    case EPI_SILU_ACT:
-      v.x = silu(v.x); v.y = silu(v.y); v.z = silu(v.z); v.w = silu(v.w);
-      store_act4(p.out_act, m, p.lda_out, nn, v, p.lo_off_out);
-      break;
-    case EPI_RESADD_F32: {
-      float4* o = reinterpret_cast<float4*>(p.out_f32 + (size_t)m * p.ldo + nn);
-      float4 x = *o;
-      x.x += p.scale * v.x; x.y += p.scale * v.y; x.z += p.scale * v.z; x.w += p.scale * v.w;
-      *o = x;
-      break;
-    }
-    case EPI_GLU_F32:
-      *reinterpret_cast<float2*>(p.out_f32 + (size_t)m * p.ldo + (nn >> 1)) = make_float2(v.x * sigmoidf_(v.y), v.z * sigmoidf_(v.w));
-      break;
-    case EPI_QKV: {
-      if (nn < kDModel) {
-        *reinterpret_cast<float4*>(p.out_f32 + (size_t)m * p.ldo + nn) = v;
-        break;
-      }
-      const int e = p.row_entry[m];
-      const int slot = p.entry_slot[e];
-      const int phys = (p.entry_head[e] + kCacheS + p.row_pos[m]) % kRingCap;
-      if (nn < 2 * kDModel && p.k_natural) {
-        const size_t i0 = ((size_t)slot * kRingCap + phys) * kDModel + (nn - kDModel);
-        if (p.kv_f32) *reinterpret_cast<float4*>((float*)p.kring + i0) = v;
-        else *reinterpret_cast<uint2*>((__nv_bfloat16*)p.kring + i0) = pack4_bf16(v.x, v.y, v.z, v.w);
-      } else if (nn < 2 * kDModel) {
-        const int c = nn - kDModel, h = c >> 7, d = c & 127;
-        const size_t i0 = (((size_t)slot * kHeads + h) * kDHead + d) * kRingCap + phys;   // K^T ring: 4 rows kRingCap apart
-        if (p.kv_f32) {
-          float* k = (float*)p.kring + i0;
-          k[0] = v.x; k[kRingCap] = v.y; k[2 * kRingCap] = v.z; k[3 * kRingCap] = v.w;
-        } else {
-          __nv_bfloat16* k = (__nv_bfloat16*)p.kring + i0;
-          k[0] = __float2bfloat16_rn(v.x); k[kRingCap] = __float2bfloat16_rn(v.y);
-          k[2 * kRingCap] = __float2bfloat16_rn(v.z); k[3 * kRingCap] = __float2bfloat16_rn(v.w);
-        }
+  if constexpr (MODE == EPI_F32) {
+    *reinterpret_cast<float4*>(p.out_f32 + (size_t)m * p.ldo + nn) = v;
+  } else if constexpr (MODE == EPI_BIAS_F32 || MODE == EPI_BIAS_RELU_F32 || MODE == EPI_BIAS_ROWMAP_F32) {
+    const float4 b = *reinterpret_cast<const float4*>(p.bias + nn);
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    if constexpr (MODE == EPI_BIAS_RELU_F32) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    int r = m;
+    if constexpr (MODE == EPI_BIAS_ROWMAP_F32) { r = p.row_map[m]; if (r < 0) return; }
+    *reinterpret_cast<float4*>(p.out_f32 + (size_t)r * p.ldo + nn) = v;
+  } else if constexpr (MODE == EPI_BIAS_RELU_ACT) {
+    const float4 b = *reinterpret_cast<const float4*>(p.bias + nn);
+    v.x = fmaxf(v.x + b.x, 0.f); v.y = fmaxf(v.y + b.y, 0.f); v.z = fmaxf(v.z + b.z, 0.f); v.w = fmaxf(v.w + b.w, 0.f);
+    store_act4(p.out_act, m, p.lda_out, nn, v, p.lo_off_out);
+  } else if constexpr (MODE == EPI_SILU_ACT) {
+    v.x = silu(v.x); v.y = silu(v.y); v.z = silu(v.z); v.w = silu(v.w);
+    store_act4(p.out_act, m, p.lda_out, nn, v, p.lo_off_out);
+  } else if constexpr (MODE == EPI_RESADD_F32) {
+    float4* o = reinterpret_cast<float4*>(p.out_f32 + (size_t)m * p.ldo + nn);
+    float4 x = *o;
+    x.x += p.scale * v.x; x.y += p.scale * v.y; x.z += p.scale * v.z; x.w += p.scale * v.w;
+    *o = x;
+  } else if constexpr (MODE == EPI_GLU_F32) {
+    *reinterpret_cast<float2*>(p.out_f32 + (size_t)m * p.ldo + (nn >> 1)) = make_float2(v.x * sigmoidf_(v.y), v.z * sigmoidf_(v.w));
+  } else if constexpr (MODE == EPI_QKV) {
+    if (nn < kDModel) {
+      if (p.q_bf16) {
+        const float4 u = *reinterpret_cast<const float4*>(p.bias_u + nn), w = *reinterpret_cast<const float4*>(p.bias_v + nn);
+        __nv_bfloat16* q = p.q_bf16 + (size_t)m * kDModel + nn;
+        *reinterpret_cast<uint2*>(q) = pack4_bf16(v.x + u.x, v.y + u.y, v.z + u.z, v.w + u.w);
+        *reinterpret_cast<uint2*>(q + p.q_plane) = pack4_bf16(v.x + w.x, v.y + w.y, v.z + w.z, v.w + w.w);
       } else {
-        const size_t i0 = ((size_t)slot * kRingCap + phys) * kDModel + (nn - 2 * kDModel);
-        if (p.kv_f32) *reinterpret_cast<float4*>((float*)p.vring + i0) = v;
-        else *reinterpret_cast<uint2*>((__nv_bfloat16*)p.vring + i0) = pack4_bf16(v.x, v.y, v.z, v.w);
+        *reinterpret_cast<float4*>(p.out_f32 + (size_t)m * p.ldo + nn) = v;
       }
-      break;
+      return;
     }
-    default: break;
+    const int e = p.row_entry[m];
+    const int slot = p.entry_slot[e];
+    int phys = p.entry_head[e] + kCacheS + p.row_pos[m];      // head in [0, kRingCap), row_pos in [-kCacheS, kMaxTq)
+    phys -= phys >= kRingCap ? kRingCap : 0;
+    if (nn < 2 * kDModel && p.k_natural) {
+      const size_t i0 = ((size_t)slot * kRingCap + phys) * kDModel + (nn - kDModel);
+      if (p.kv_f32) *reinterpret_cast<float4*>((float*)p.kring + i0) = v;
+      else *reinterpret_cast<uint2*>((__nv_bfloat16*)p.kring + i0) = pack4_bf16(v.x, v.y, v.z, v.w);
+    } else if (nn < 2 * kDModel) {
+      const int c = nn - kDModel, h = c >> 7, d = c & 127;
+      const size_t i0 = (((size_t)slot * kHeads + h) * kDHead + d) * kRingCap + phys;   // K^T ring: 4 rows kRingCap apart
+      if (p.kv_f32) {
+        float* k = (float*)p.kring + i0;
+        k[0] = v.x; k[kRingCap] = v.y; k[2 * kRingCap] = v.z; k[3 * kRingCap] = v.w;
+      } else {
+        __nv_bfloat16* k = (__nv_bfloat16*)p.kring + i0;
+        k[0] = __float2bfloat16_rn(v.x); k[kRingCap] = __float2bfloat16_rn(v.y);
+        k[2 * kRingCap] = __float2bfloat16_rn(v.z); k[3 * kRingCap] = __float2bfloat16_rn(v.w);
+      }
+    } else {
+      const size_t i0 = ((size_t)slot * kRingCap + phys) * kDModel + (nn - 2 * kDModel);
+      if (p.kv_f32) *reinterpret_cast<float4*>((float*)p.vring + i0) = v;
+      else *reinterpret_cast<uint2*>((__nv_bfloat16*)p.vring + i0) = pack4_bf16(v.x, v.y, v.z, v.w);
+    }
   }
 }
 
-template <int BN>
+template <int BN, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const GemmArgs g,
                const int lo_row_off) {
@@ -228,6 +221,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // every full quad takes the vector path unless the output rows are not 16-byte aligned (f32 rows with ldo % 4 != 0)
+  const bool f32_rows = MODE == EPI_F32 || MODE == EPI_BIAS_F32 || MODE == EPI_BIAS_RELU_F32 || MODE == EPI_BIAS_ROWMAP_F32 ||
+                        MODE == EPI_RESADD_F32;
+  const bool ragged = f32_rows && (g.epi.ldo & 3);
   const int kb_per_pass = g.K / BK;
   const int num_kb = kb_per_pass * (g.a_lo_off != 0 ? 2 : 1);
 
@@ -322,7 +319,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int r = rd_row + 8 * i;
           const float4 val = *reinterpret_cast<const float4*>(stage + r * kEpiPitch + 4 * c4);
           const int m = m0 + q * 32 + r;
-          if (m < M && n < g.N) epilogue_quad(g.epi, m, n, g.N, val);
+          if (m < M && n < g.N) {
+            if (n + 3 < g.N && !ragged) epilogue_quad<MODE>(g.epi, m, n, val);
+            else epilogue_edge(g.epi, m, n, g.N, val);
+          }
         }
       }
     }
@@ -362,13 +362,14 @@ int sm_count() {
   return g_sm_count;
 }
 
-// Tile width: the wider tile halves the shared-memory operand traffic per MMA (96 vs 128 B/clk), the narrower one
-// quantises better into waves of `sms` CTAs.  Pick the one with the smaller (waves x tile cost).
+// Tile width.  The kernel is bound by L2->SM operand delivery (~6.2 KB/clk chip-wide, profiles/): per k-block a 128x128 tile
+// pulls 32 KB, a 128x256 tile 48 KB for twice the math, so a wide tile costs ~1.5 narrow ones; against that, narrow tiles
+// quantise better into waves of `sms` CTAs.  Pick the smaller (waves x tile cost); narrow on ties (shorter tail).
 int pick_bn(int M, int N, int sms) {
   const long long tm = (M + BM - 1) / BM;
   const long long t128 = tm * ((N + 127) / 128), t256 = tm * ((N + 255) / 256);
   const long long w128 = (t128 + sms - 1) / sms, w256 = (t256 + sms - 1) / sms;
-  return (w256 * 2 * 100 <= w128 * 105) ? 256 : 128;       // 256-wide costs 2x per tile; prefer it on ties (and within 5 %)
+  return (w256 * 3 < w128 * 2) ? 256 : 128;
 }
 
 }  // namespace
@@ -385,6 +386,16 @@ void make_tensor_map_2d(TensorMap* out, const void* base, uint64_t rows, uint64_
   PKB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
 }
 
+template <int BN, int MODE>
+void launch_cfg(int grid, const CUtensorMap& ma, const CUtensorMap& mw, const GemmArgs& g, int lo_row_off, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    PKB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN>::kSmemBytes));
+    attr = true;
+  }
+  gemm_tc_kernel<BN, MODE><<<grid, kThreads, Cfg<BN>::kSmemBytes, st>>>(ma, mw, g, lo_row_off);
+}
+
 void gemm_tc_set_bn(int bn) { g_force_bn = bn; }
 
 bool gemm_tc_supported(const GemmArgs& g) {
@@ -393,12 +404,6 @@ bool gemm_tc_supported(const GemmArgs& g) {
 
 void gemm_tc(const GemmArgs& g, const TensorMap& map_a, const TensorMap& map_w, cudaStream_t st) {
   PKB_CHECK(gemm_tc_supported(g), "gemm_tc: unsupported shape");
-  static bool attr = false;
-  if (!attr) {
-    PKB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<128>::kSmemBytes));
-    PKB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<256>::kSmemBytes));
-    attr = true;
-  }
   const int sms = sm_count();
   if (g_force_bn < 0) { const char* v = getenv("PARAKEET_B200_GEMM_BN"); g_force_bn = v ? atoi(v) : 0; }
   const int bn = g_force_bn == 128 || g_force_bn == 256 ? g_force_bn : pick_bn(g.M, g.N, sms);
@@ -407,8 +412,17 @@ void gemm_tc(const GemmArgs& g, const TensorMap& map_a, const TensorMap& map_w, 
   const int lo_row_off = (int)(g.a_lo_off / g.lda);
   const CUtensorMap& ma = *reinterpret_cast<const CUtensorMap*>(&map_a);
   const CUtensorMap& mw = *reinterpret_cast<const CUtensorMap*>(&map_w);
-  if (bn == 256) gemm_tc_kernel<256><<<grid, kThreads, Cfg<256>::kSmemBytes, st>>>(ma, mw, g, lo_row_off);
-  else gemm_tc_kernel<128><<<grid, kThreads, Cfg<128>::kSmemBytes, st>>>(ma, mw, g, lo_row_off);
+  switch (g.epi.mode) {
+#define PKB_GEMM_CASE(MODE)                                                                         \
+    case MODE:                                                                                      \
+      if (bn == 256) launch_cfg<256, MODE>(grid, ma, mw, g, lo_row_off, st);                        \
+      else launch_cfg<128, MODE>(grid, ma, mw, g, lo_row_off, st);                                  \
+      break;
+    PKB_GEMM_CASE(EPI_BIAS_F32) PKB_GEMM_CASE(EPI_BIAS_RELU_F32) PKB_GEMM_CASE(EPI_BIAS_RELU_ACT) PKB_GEMM_CASE(EPI_BIAS_ROWMAP_F32)
+    PKB_GEMM_CASE(EPI_SILU_ACT) PKB_GEMM_CASE(EPI_RESADD_F32) PKB_GEMM_CASE(EPI_QKV) PKB_GEMM_CASE(EPI_GLU_F32) PKB_GEMM_CASE(EPI_F32)
+#undef PKB_GEMM_CASE
+    default: PKB_CHECK(false, "gemm_tc: unknown epilogue mode");
+  }
   PKB_CUDA(cudaGetLastError());
 }
 
