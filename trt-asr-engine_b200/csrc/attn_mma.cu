@@ -83,7 +83,10 @@ constexpr int kConsumerThreads = 32 * kConsumerWarps;
 
 template <int R>
 struct Smem {
-  static constexpr int kStages = R == 8 ? 6 : R == 16 ? 5 : 4;
+  // R = 8 (the steady-state chunk): 3 stages, two CTAs per SM (16 consumer warps hide each other's latencies);
+  // the larger variants keep one CTA per SM
+  static constexpr int kStages = R == 8 ? 3 : R == 16 ? 5 : 4;
+  static constexpr int kCtasPerSm = R == 8 ? 2 : 1;
   static constexpr int kS = R * kSPitch * 4;
   static constexpr int kG = R * kGPitch * 4;             // later reused for the bf16 probabilities (R_pad x 592 B <= kG)
   static constexpr size_t kBytes = 1024 + (size_t)kStages * kStageBytes + kS + kG + 128;
@@ -116,7 +119,7 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;"
 // through the ring without waiting for the math, so HBM stays busy while the consumers are in their on-chip phases.
 // R = 8 (rows 8..15 of every m16 tile are identically zero and never loaded / stored), 16 or 32.
 template <int R>
-__global__ void __launch_bounds__(kAttnThreads, 1)
+__global__ void __launch_bounds__(kAttnThreads, Smem<R>::kCtasPerSm)
 attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v, BatchDev b, AttnMmaArgs a) {
   constexpr int MT = R <= 16 ? 1 : 2;
   constexpr bool kHalf = R == 8;
@@ -139,6 +142,7 @@ attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kConsumerWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  pdl_enter();          // set-up above overlaps the previous kernel's tail; no global data is touched before this point
   __syncthreads();
 
   if (warp == 0) {
@@ -384,9 +388,9 @@ void launch_r(const BatchDev& b, const AttnMmaArgs& a, int sms, cudaStream_t st)
     attr = true;
   }
   const int items = b.B * kHeads;
-  attention_mma_kernel<R><<<items < sms ? items : sms, kAttnThreads, Smem<R>::kBytes, st>>>(
-      *reinterpret_cast<const CUtensorMap*>(a.map_k), *reinterpret_cast<const CUtensorMap*>(a.map_v), b, a);
-  PKB_CUDA(cudaGetLastError());
+  const int ctas = sms * Smem<R>::kCtasPerSm;
+  launch_k(attention_mma_kernel<R>, dim3(items < ctas ? items : ctas), dim3(kAttnThreads), Smem<R>::kBytes, st,
+           *reinterpret_cast<const CUtensorMap*>(a.map_k), *reinterpret_cast<const CUtensorMap*>(a.map_v), b, a);
 }
 
 }  // namespace

@@ -4,8 +4,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
+#include <utility>
 
 namespace pkb {
 
@@ -53,7 +55,30 @@ struct CudaError : std::runtime_error {
     if (!(cond)) throw std::runtime_error(std::string("check failed: ") + (msg)); \
   } while (0)
 
+// Programmatic dependent launch: every hot-path kernel is launched with the stream-serialisation attribute, lets its
+// successor start scheduling immediately (pdl_trigger) and does its own set-up before pdl_wait(), which returns once the
+// predecessor grid has completed and flushed.  No kernel touches global data before pdl_wait().
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PARAKEET_B200_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
 #ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  PKB_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+}
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_trigger(); pdl_wait(); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -81,6 +106,17 @@ __device__ __forceinline__ void store_act(__nv_bfloat16* A, size_t row, int lda,
   split_bf16(v, hi, lo);
   A[row * (size_t)lda + col] = hi;
   if (lo_off) A[row * (size_t)lda + col + lo_off] = lo;
+}
+// 4 adjacent operand elements (col % 4 == 0): one 8-byte store per plane
+__device__ __forceinline__ void store_act4(__nv_bfloat16* A, size_t row, int lda, int col, float4 v, long long lo_off) {
+  __nv_bfloat16* dst = A + row * (size_t)lda + col;
+  const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+  *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+  if (lo_off) {
+    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+    const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+    *reinterpret_cast<uint2*>(dst + lo_off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+  }
 }
 #endif
 

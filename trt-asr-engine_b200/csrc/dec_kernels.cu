@@ -13,6 +13,7 @@ namespace pkb {
 // hidden[e] = relu(E[row(e, t_e)] + P[slot_e])  -> GEMM operand rows [B,640]  (E, P already include their biases)
 __global__ void __launch_bounds__(128)
 joint_hidden_kernel(DecodeDev d) {
+  pdl_enter();
   const int e = blockIdx.x;
   const bool act = d.active[e] != 0;
   const float* E = d.enc_proj + (size_t)(d.row_off[e] + (act ? d.t_cur[e] : 0)) * kJointH;
@@ -26,6 +27,7 @@ joint_hidden_kernel(DecodeDev d) {
 // One CTA per entry: fused argmax over both heads + the TDT advance rules + state update.
 __global__ void __launch_bounds__(256)
 tdt_select_kernel(DecodeDev d) {
+  pdl_enter();
   const int e = blockIdx.x, tid = threadIdx.x;
   if (!d.active[e]) {
     if (tid == 0) { d.emit_tok[e] = -1; d.pred_rowmap[e] = -1; }
@@ -101,6 +103,7 @@ tdt_select_kernel(DecodeDev d) {
 // act rows [emb(tok) ; h_layer0]  (K = 1280) for the layer-0 gate GEMM
 __global__ void __launch_bounds__(128)
 pred_input_kernel(DecodeDev d) {
+  pdl_enter();
   const int e = blockIdx.x;
   if (*d.m_pred == 0) return;
   const int tok = d.emit_tok[e];
@@ -116,6 +119,7 @@ pred_input_kernel(DecodeDev d) {
 //  layer 0: act rows <- [h0_new ; h1_old]       layer 1: act_g rows <- h1_new (K = 640), g state updated
 __global__ void __launch_bounds__(128)
 lstm_cell_kernel(DecodeDev d, int layer) {
+  pdl_enter();
   const int e = blockIdx.x;
   if (*d.m_pred == 0) return;
   const int tok = d.emit_tok[e];
@@ -147,6 +151,7 @@ lstm_cell_kernel(DecodeDev d, int layer) {
 }
 
 __global__ void decode_begin_kernel(DecodeDev d) {
+  pdl_enter();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e == 0) { *d.n_active = 0; *d.m_pred = 0; }
   if (e >= d.B) return;
@@ -159,11 +164,13 @@ __global__ void decode_begin_kernel(DecodeDev d) {
 }
 
 __global__ void decode_iter_reset_kernel(DecodeDev d) {
+  pdl_enter();
   if (threadIdx.x == 0) { *d.n_active = 0; *d.m_pred = 0; }
 }
 
 // priming / forced token (reset_utterance): mark entries to run the predictor on a given token
 __global__ void force_token_kernel(DecodeDev d, const int* toks) {
+  pdl_enter();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.B) return;
   d.emit_tok[e] = toks[e];
@@ -173,36 +180,36 @@ __global__ void force_token_kernel(DecodeDev d, const int* toks) {
 
 void launch_decode_begin(const DecodeDev& d, cudaStream_t st) {
   if (d.B <= 0) return;
-  decode_begin_kernel<<<(d.B + 127) / 128, 128, 0, st>>>(d);
+  launch_k(decode_begin_kernel, dim3((d.B + 127) / 128), dim3(128), 0, st, d);
   PKB_CUDA(cudaGetLastError());
 }
 void launch_decode_iter_reset(const DecodeDev& d, cudaStream_t st) {
-  decode_iter_reset_kernel<<<1, 32, 0, st>>>(d);
+  launch_k(decode_iter_reset_kernel, dim3(1), dim3(32), 0, st, d);
   PKB_CUDA(cudaGetLastError());
 }
 void launch_joint_hidden(const DecodeDev& d, cudaStream_t st) {
   if (d.B <= 0) return;
-  joint_hidden_kernel<<<d.B, 128, 0, st>>>(d);
+  launch_k(joint_hidden_kernel, dim3(d.B), dim3(128), 0, st, d);
   PKB_CUDA(cudaGetLastError());
 }
 void launch_tdt_select(const DecodeDev& d, cudaStream_t st) {
   if (d.B <= 0) return;
-  tdt_select_kernel<<<d.B, 256, 0, st>>>(d);
+  launch_k(tdt_select_kernel, dim3(d.B), dim3(256), 0, st, d);
   PKB_CUDA(cudaGetLastError());
 }
 void launch_pred_input(const DecodeDev& d, cudaStream_t st) {
   if (d.B <= 0) return;
-  pred_input_kernel<<<d.B, 128, 0, st>>>(d);
+  launch_k(pred_input_kernel, dim3(d.B), dim3(128), 0, st, d);
   PKB_CUDA(cudaGetLastError());
 }
 void launch_lstm_cell(const DecodeDev& d, int layer, cudaStream_t st) {
   if (d.B <= 0) return;
-  lstm_cell_kernel<<<d.B, 128, 0, st>>>(d, layer);
+  launch_k(lstm_cell_kernel, dim3(d.B), dim3(128), 0, st, d, layer);
   PKB_CUDA(cudaGetLastError());
 }
 void launch_force_token(const DecodeDev& d, const int* d_toks, cudaStream_t st) {
   if (d.B <= 0) return;
-  force_token_kernel<<<(d.B + 127) / 128, 128, 0, st>>>(d, d_toks);
+  launch_k(force_token_kernel, dim3((d.B + 127) / 128), dim3(128), 0, st, d, d_toks);
   PKB_CUDA(cudaGetLastError());
 }
 

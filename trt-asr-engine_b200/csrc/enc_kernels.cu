@@ -23,6 +23,7 @@ __device__ __forceinline__ int find_entry(const int* __restrict__ prefix, int B,
 
 // ------------------------------------------------------------------------------------------------ rows
 __global__ void build_rows_kernel(BatchDev b) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < b.M) {
     const int e = find_entry(b.row_off, b.B, i);
@@ -38,7 +39,7 @@ __global__ void build_rows_kernel(BatchDev b) {
 void launch_build_rows(const BatchDev& b, cudaStream_t st) {
   const int n = b.M > b.sumT3 ? b.M : b.sumT3;
   if (n <= 0) return;
-  build_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(b);
+  launch_k(build_rows_kernel, dim3((n + 255) / 256), dim3(256), 0, st, b);
   PKB_CUDA(cudaGetLastError());
 }
 
@@ -46,6 +47,7 @@ void launch_build_rows(const BatchDev& b, cudaStream_t st) {
 // One CTA per (entry, t2).  7 input rows -> conv0 (3 rows x 64 x 32ch at a time, in smem) -> depthwise -> 32 x 256 outputs.
 __global__ void __launch_bounds__(256)
 subsample_stage1_kernel(BatchDev b, const float* __restrict__ feat_ring, int ring_cap, SubsampleWeights w, ActOut a1) {
+  pdl_enter();
   __shared__ float s_in[7][kNMels + 2];        // [row][f+1], zero padded
   __shared__ float s_y0[3][66][33];            // [t1 row][f1+1][c] (+1 pad column against bank conflicts)
   const int g = blockIdx.x;
@@ -110,7 +112,7 @@ subsample_stage1_kernel(BatchDev b, const float* __restrict__ feat_ring, int rin
 void launch_subsample_stage1(const BatchDev& b, const float* feat_ring, int ring_cap, const SubsampleWeights& w, ActOut a1,
                              cudaStream_t st) {
   if (b.sumT2 <= 0) return;
-  subsample_stage1_kernel<<<b.sumT2, 256, 0, st>>>(b, feat_ring, ring_cap, w, a1);
+  launch_k(subsample_stage1_kernel, dim3(b.sumT2), dim3(256), 0, st, b, feat_ring, ring_cap, w, a1);
   PKB_CUDA(cudaGetLastError());
 }
 
@@ -118,6 +120,7 @@ void launch_subsample_stage1(const BatchDev& b, const float* feat_ring, int ring
 // One CTA per (entry, t3); thread == channel (256), loop over 16 output frequency bins.
 __global__ void __launch_bounds__(256)
 subsample_stage2_kernel(BatchDev b, const float* __restrict__ y1, SubsampleWeights w, ActOut a2) {
+  pdl_enter();
   const int g = blockIdx.x;
   const int e = find_entry(b.off3, b.B, g);
   const int t3 = g - b.off3[e];
@@ -146,7 +149,7 @@ subsample_stage2_kernel(BatchDev b, const float* __restrict__ y1, SubsampleWeigh
 }
 void launch_subsample_stage2(const BatchDev& b, const float* y1, const SubsampleWeights& w, ActOut a2, cudaStream_t st) {
   if (b.sumT3 <= 0) return;
-  subsample_stage2_kernel<<<b.sumT3, 256, 0, st>>>(b, y1, w, a2);
+  launch_k(subsample_stage2_kernel, dim3(b.sumT3), dim3(256), 0, st, b, y1, w, a2);
   PKB_CUDA(cudaGetLastError());
 }
 
@@ -176,6 +179,7 @@ __device__ __forceinline__ void ln_row(float (&v)[32], const float* __restrict__
 __global__ void __launch_bounds__(256)
 layernorm_kernel(float* __restrict__ x, int M, const float* __restrict__ g1, const float* __restrict__ b1,
                  const float* __restrict__ g2, const float* __restrict__ b2, int write_x, ActOut a, AcacheOut ac, int has_ac) {
+  pdl_enter();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -197,9 +201,7 @@ layernorm_kernel(float* __restrict__ x, int M, const float* __restrict__ g1, con
       if (ac.is_f32) {
         *reinterpret_cast<float4*>((float*)ac.ring + base + col) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
       } else {
-        __nv_bfloat16* r = (__nv_bfloat16*)ac.ring + base + col;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) r[j] = __float2bfloat16_rn(v[4 * i + j]);
+        store_act4((__nv_bfloat16*)ac.ring + base + col, 0, 0, 0, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), 0);
       }
     }
   }
@@ -212,14 +214,13 @@ layernorm_kernel(float* __restrict__ x, int M, const float* __restrict__ g1, con
   if (a.ptr == nullptr) return;
 #pragma unroll
   for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) store_act(a.ptr, row, a.lda, i * 128 + lane * 4 + j, v[4 * i + j], a.lo_off);
+    store_act4(a.ptr, row, a.lda, i * 128 + lane * 4, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), a.lo_off);
 }
 void launch_layernorm(float* x, int M, const float* g1, const float* b1, const float* g2, const float* b2, int write_x, ActOut a,
                       const AcacheOut* ac, cudaStream_t st) {
   if (M <= 0) return;
   AcacheOut z{};
-  layernorm_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, M, g1, b1, g2, b2, write_x, a, ac ? *ac : z, ac != nullptr);
+  launch_k(layernorm_kernel, dim3((M + 7) / 8), dim3(256), 0, st, x, M, g1, b1, g2, b2, write_x, a, ac ? *ac : z, (int)(ac != nullptr));
   PKB_CUDA(cudaGetLastError());
 }
 
@@ -238,6 +239,7 @@ template <> __device__ __forceinline__ float ld_kv<__nv_bfloat16>(const __nv_bfl
 template <typename KV>
 __global__ void __launch_bounds__(128)
 attention_kernel(BatchDev b, AttnArgs a) {
+  pdl_enter();
   extern __shared__ float smem[];
   const int e = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
   const int Tq = b.Tq[e], qlen = b.qlen[e], len = b.len[e], head = b.head[e], slot = b.slot[e];
@@ -347,8 +349,8 @@ void launch_attention(const BatchDev& b, const AttnArgs& a, cudaStream_t st) {
     else PKB_CUDA(cudaFuncSetAttribute(attention_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set[a.kv_f32] = smem;
   }
-  if (a.kv_f32) attention_kernel<float><<<dim3(b.B, kHeads), 128, smem, st>>>(b, a);
-  else attention_kernel<__nv_bfloat16><<<dim3(b.B, kHeads), 128, smem, st>>>(b, a);
+  if (a.kv_f32) launch_k(attention_kernel<float>, dim3(b.B, kHeads), dim3(128), smem, st, b, a);
+  else launch_k(attention_kernel<__nv_bfloat16>, dim3(b.B, kHeads), dim3(128), smem, st, b, a);
   PKB_CUDA(cudaGetLastError());
 }
 
@@ -356,6 +358,7 @@ void launch_attention(const BatchDev& b, const AttnArgs& a, cudaStream_t st) {
 // One CTA per (entry, 256-channel group); thread == channel.
 __global__ void __launch_bounds__(256)
 dwconv_kernel(BatchDev b, DwConvArgs a) {
+  pdl_enter();
   const int e = blockIdx.x, ch = blockIdx.y * 256 + threadIdx.x;
   const int Tq = b.Tq[e], qlen = b.qlen[e], row0 = b.row_off[e];
   float* cache = a.cache_tm + (size_t)b.slot[e] * a.slot_stride + (size_t)ch * kTimeCtx;
@@ -397,13 +400,14 @@ dwconv_kernel(BatchDev b, DwConvArgs a) {
 }
 void launch_dwconv(const BatchDev& b, const DwConvArgs& a, cudaStream_t st) {
   if (b.B <= 0) return;
-  dwconv_kernel<<<dim3(b.B, kDModel / 256), 256, 0, st>>>(b, a);
+  launch_k(dwconv_kernel, dim3(b.B, kDModel / 256), dim3(256), 0, st, b, a);
   PKB_CUDA(cudaGetLastError());
 }
 
 // ------------------------------------------------------------------------------------------------ output
 __global__ void __launch_bounds__(256)
 gather_output_kernel(BatchDev b, const float* __restrict__ x, float* __restrict__ enc_out) {
+  pdl_enter();
   const int e = blockIdx.x;
   const int row0 = b.row_off[e], Tq = b.Tq[e];
   for (int i = threadIdx.x; i < kDModel * kValidOut; i += 256) {
@@ -413,7 +417,7 @@ gather_output_kernel(BatchDev b, const float* __restrict__ x, float* __restrict_
 }
 void launch_gather_output(const BatchDev& b, const float* x, float* enc_out, cudaStream_t st) {
   if (b.B <= 0) return;
-  gather_output_kernel<<<b.B, 256, 0, st>>>(b, x, enc_out);
+  launch_k(gather_output_kernel, dim3(b.B), dim3(256), 0, st, b, x, enc_out);
   PKB_CUDA(cudaGetLastError());
 }
 

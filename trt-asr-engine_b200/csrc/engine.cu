@@ -95,6 +95,7 @@ __global__ void fill_import_rows_kernel(int* row_entry, int* row_pos, int n_rows
 // dst[slot][off + k] = src[i*stride + k]
 __global__ void audio_append_kernel(const float* __restrict__ src, long long stride, float* __restrict__ audio_buf,
                                     const int* __restrict__ slot, const int* __restrict__ off, const int* __restrict__ cnt) {
+  pdl_enter();
   const int i = blockIdx.y;
   const int n = cnt[i];
   float* d = audio_buf + (size_t)slot[i] * 32768 + off[i];
@@ -721,9 +722,8 @@ void Engine::push_audio_batch(int n, const int* sids, const float* src, long lon
     s.audio_mode = true;
   }
   PKB_CUDA(cudaMemcpyAsync(im.push_meta, h, (size_t)3 * im.Bcap * sizeof(int), cudaMemcpyHostToDevice, st_));
-  audio_append_kernel<<<dim3((count + 1023) / 1024, n), 256, 0, st_>>>(dsrc, dstride, im.audio_buf, im.push_meta, im.push_meta + im.Bcap,
-                                                                       im.push_meta + 2 * im.Bcap);
-  PKB_CUDA(cudaGetLastError());
+  launch_k(audio_append_kernel, dim3((count + 1023) / 1024, n), dim3(256), 0, st_, dsrc, dstride, im.audio_buf, (const int*)im.push_meta,
+           (const int*)(im.push_meta + im.Bcap), (const int*)(im.push_meta + 2 * im.Bcap));
   ++launches_;
 }
 

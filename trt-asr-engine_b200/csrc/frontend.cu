@@ -100,6 +100,7 @@ __device__ __forceinline__ float2 cmul(float2 x, float2 w) { return make_float2(
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 logmel_kernel(const float* __restrict__ audio, const FrontSegment* __restrict__ segs, const int* __restrict__ frame_prefix,
               int n_segs, int total_frames, FrontTablesDev tb, float* __restrict__ out, const float* __restrict__ stats) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_window = reinterpret_cast<float*>(smem_raw);            // 400
   float2* s_tw256 = reinterpret_cast<float2*>(s_window + kWin);    // 256: e^{-2 pi i k/256}
@@ -228,7 +229,7 @@ void Frontend::logmel(const float* d_audio, const FrontSegment* d_segs, const in
   int ctas = (total_frames + kWarpsPerCta - 1) / kWarpsPerCta;
   const int cap = sm_count * 4;   // persistent-style: <= 4 CTAs per SM, grid-stride over frames
   if (ctas > cap) ctas = cap;
-  logmel_kernel<<<ctas, kWarpsPerCta * 32, smem, st>>>(d_audio, d_segs, d_frame_prefix, n_segs, total_frames, *d, d_out, d_stats);
+  launch_k(logmel_kernel, dim3(ctas), dim3(kWarpsPerCta * 32), smem, st, d_audio, d_segs, d_frame_prefix, n_segs, total_frames, *d, d_out, d_stats);
   PKB_CUDA(cudaGetLastError());
 }
 

@@ -22,6 +22,7 @@ __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
 
 __global__ void __launch_bounds__(kWarps * 32)
 gemm_simt_kernel(const GemmArgs g) {
+  pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = (blockIdx.x * kWarps + warp) * 2;
   const int m0 = blockIdx.y * kRows;
@@ -77,7 +78,7 @@ void gemm_simt(const GemmArgs& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return;
   PKB_CHECK(g.K % 8 == 0 && g.lda % 8 == 0 && g.a_lo_off % 8 == 0, "gemm_simt: K, lda and a_lo_off must be multiples of 8");
   dim3 grid((g.N + 2 * kWarps - 1) / (2 * kWarps), (g.M + kRows - 1) / kRows);
-  gemm_simt_kernel<<<grid, kWarps * 32, 0, st>>>(g);
+  launch_k(gemm_simt_kernel, grid, dim3(kWarps * 32), 0, st, g);
   PKB_CUDA(cudaGetLastError());
 }
 

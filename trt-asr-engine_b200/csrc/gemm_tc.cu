@@ -115,17 +115,6 @@ __device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) 
   const __nv_bfloat162 p0 = __floats2bfloat162_rn(a, b), p1 = __floats2bfloat162_rn(c, d);
   return make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
 }
-// 4 adjacent activations -> bf16 hi plane (+ lo plane in split mode), 8-byte stores
-__device__ __forceinline__ void store_act4(__nv_bfloat16* A, size_t row, int lda, int col, float4 v, long long lo_off) {
-  __nv_bfloat16* dst = A + row * (size_t)lda + col;
-  const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
-  *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-  if (lo_off) {
-    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-    *reinterpret_cast<uint2*>(dst + lo_off) = pack4_bf16(v.x - f0.x, v.y - f0.y, v.z - f1.x, v.w - f1.y);
-  }
-}
-
 // Ragged right edge (N = 8198) or output rows that are not 16-byte aligned: generic pairwise path, kept out of line so
 // that the hot loop of every specialisation stays small enough for the instruction cache.
 __device__ __noinline__ void epilogue_edge(const EpiParams& p, int m, int n, int N, float4 v) {
@@ -205,11 +194,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                const int lo_row_off) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  const int M = g.M_dev ? min(*g.M_dev, g.M) : g.M;
-  const int tiles_m = (M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN;
-  const int total_tiles = tiles_m * tiles_n;
-  if ((int)blockIdx.x >= total_tiles) return;            // uniform per CTA, before any barrier / allocation
-
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = base;                                    // [kStages][16 KB]
   uint8_t* sB = base + C::kStages * kTileABytes;         // [kStages][BN*128 B]
@@ -243,6 +227,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+
+  pdl_enter();      // barrier init + TMEM allocation above overlap the previous kernel's tail; global data only from here on
+  const int M = g.M_dev ? min(*g.M_dev, g.M) : g.M;
+  const int tiles_m = (M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN;
+  const int total_tiles = tiles_m * tiles_n;            // CTAs beyond the (device-side) tile count fall through to the teardown
 
   if (warp == 0) {
     if (lane == 0) {
@@ -393,7 +382,7 @@ void launch_cfg(int grid, const CUtensorMap& ma, const CUtensorMap& mw, const Ge
     PKB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN>::kSmemBytes));
     attr = true;
   }
-  gemm_tc_kernel<BN, MODE><<<grid, kThreads, Cfg<BN>::kSmemBytes, st>>>(ma, mw, g, lo_row_off);
+  launch_k(gemm_tc_kernel<BN, MODE>, dim3(grid), dim3(kThreads), Cfg<BN>::kSmemBytes, st, ma, mw, g, lo_row_off);
 }
 
 void gemm_tc_set_bn(int bn) { g_force_bn = bn; }
