@@ -22,7 +22,7 @@ SHAPES = [(1, 256, 256), (6, 1024, 1024), (8, 4096, 1024), (17, 1024, 4096), (12
           (2048, 4096, 1024), (1536, 3072, 1024), (700, 8198, 640), (3072, 1024, 4096)]
 
 
-@pytest.mark.parametrize("backend", [0, 1, 2, 3], ids=["simt", "tcgen05", "tcgen05-bn128", "tcgen05-bn256"])
+@pytest.mark.parametrize("backend", [0, 1, 2, 3, 4], ids=["simt", "tcgen05", "tcgen05-bn128", "tcgen05-bn256", "tcgen05-2cta"])
 @pytest.mark.parametrize("M,N,K", SHAPES)
 def test_gemm(eng, backend, M, N, K):
     rng = np.random.default_rng(M * 7 + N + K)

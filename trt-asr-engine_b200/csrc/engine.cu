@@ -1397,9 +1397,9 @@ void Engine::gemm_test(int backend, int M, int N, int K, const float* A, const u
   g.A = a.ptr; g.lda = K; g.a_lo_off = a.lo_off; g.W = w.w; g.M = M; g.N = N; g.K = K;
   g.epi.mode = EPI_F32; g.epi.out_f32 = d_C; g.epi.ldo = N;
   (void)epi_silu;
-  if (backend >= 1) {     // 1: heuristic tile width, 2: 128-wide tiles, 3: 256-wide tiles
+  if (backend >= 1) {     // 1: heuristic, 2: 128-wide tiles, 3: 256-wide tiles, 4: CTA-pair 256 x 256 tiles (cta_group::2)
     PKB_CHECK(gemm_tc_supported(g), "gemm_test: shape not supported by the tensor-core backend");
-    gemm_tc_set_bn(backend == 2 ? 128 : backend == 3 ? 256 : 0);
+    gemm_tc_set_bn(backend == 2 ? 128 : backend == 3 ? 256 : backend == 4 ? 512 : 0);
     gemm_tc(g, a.map, w.map, st_);
     gemm_tc_set_bn(0);
   } else {

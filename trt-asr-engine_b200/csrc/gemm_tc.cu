@@ -123,8 +123,24 @@ __device__ __noinline__ void epilogue_edge(const EpiParams& p, int m, int n, int
 }
 
 // Fused epilogue on 4 adjacent columns n..n+3 (n % 4 == 0, n + 3 < N) of row m; MODE is a compile-time EpiMode.
+// Per-row context, computed once per (tile, row) instead of once per quad: the mapped output row (row-map mode, < 0 =
+// dropped) or the ring row slot * kRingCap + phys of the stream this packed row belongs to (QKV mode).
 template <int MODE>
-__device__ __forceinline__ void epilogue_quad(const EpiParams& p, int m, int n, float4 v) {
+__device__ __forceinline__ int epilogue_row_ctx(const EpiParams& p, int m) {
+  if constexpr (MODE == EPI_BIAS_ROWMAP_F32) {
+    return p.row_map[m];
+  } else if constexpr (MODE == EPI_QKV) {
+    const int e = p.row_entry[m];
+    int phys = p.entry_head[e] + kCacheS + p.row_pos[m];      // head in [0, kRingCap), row_pos in [-kCacheS, kMaxTq)
+    phys -= phys >= kRingCap ? kRingCap : 0;
+    return p.entry_slot[e] * kRingCap + phys;
+  } else {
+    return m;
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void epilogue_quad(const EpiParams& p, int m, int ctx, int n, float4 v) {
   const int nn = n + p.n_off;
   if constexpr (MODE == EPI_F32) {
     *reinterpret_cast<float4*>(p.out_f32 + (size_t)m * p.ldo + nn) = v;
@@ -132,9 +148,8 @@ __device__ __forceinline__ void epilogue_quad(const EpiParams& p, int m, int n, 
     const float4 b = *reinterpret_cast<const float4*>(p.bias + nn);
     v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
     if constexpr (MODE == EPI_BIAS_RELU_F32) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-    int r = m;
-    if constexpr (MODE == EPI_BIAS_ROWMAP_F32) { r = p.row_map[m]; if (r < 0) return; }
-    *reinterpret_cast<float4*>(p.out_f32 + (size_t)r * p.ldo + nn) = v;
+    if (ctx < 0) return;                                      // ctx == m except in row-map mode
+    *reinterpret_cast<float4*>(p.out_f32 + (size_t)ctx * p.ldo + nn) = v;
   } else if constexpr (MODE == EPI_BIAS_RELU_ACT) {
     const float4 b = *reinterpret_cast<const float4*>(p.bias + nn);
     v.x = fmaxf(v.x + b.x, 0.f); v.y = fmaxf(v.y + b.y, 0.f); v.z = fmaxf(v.z + b.z, 0.f); v.w = fmaxf(v.w + b.w, 0.f);
@@ -161,16 +176,13 @@ __device__ __forceinline__ void epilogue_quad(const EpiParams& p, int m, int n, 
       }
       return;
     }
-    const int e = p.row_entry[m];
-    const int slot = p.entry_slot[e];
-    int phys = p.entry_head[e] + kCacheS + p.row_pos[m];      // head in [0, kRingCap), row_pos in [-kCacheS, kMaxTq)
-    phys -= phys >= kRingCap ? kRingCap : 0;
     if (nn < 2 * kDModel && p.k_natural) {
-      const size_t i0 = ((size_t)slot * kRingCap + phys) * kDModel + (nn - kDModel);
+      const size_t i0 = (size_t)ctx * kDModel + (nn - kDModel);
       if (p.kv_f32) *reinterpret_cast<float4*>((float*)p.kring + i0) = v;
       else *reinterpret_cast<uint2*>((__nv_bfloat16*)p.kring + i0) = pack4_bf16(v.x, v.y, v.z, v.w);
     } else if (nn < 2 * kDModel) {
       const int c = nn - kDModel, h = c >> 7, d = c & 127;
+      const int slot = ctx / kRingCap, phys = ctx - slot * kRingCap;
       const size_t i0 = (((size_t)slot * kHeads + h) * kDHead + d) * kRingCap + phys;   // K^T ring: 4 rows kRingCap apart
       if (p.kv_f32) {
         float* k = (float*)p.kring + i0;
@@ -181,7 +193,7 @@ __device__ __forceinline__ void epilogue_quad(const EpiParams& p, int m, int n, 
         k[2 * kRingCap] = __float2bfloat16_rn(v.z); k[3 * kRingCap] = __float2bfloat16_rn(v.w);
       }
     } else {
-      const size_t i0 = ((size_t)slot * kRingCap + phys) * kDModel + (nn - 2 * kDModel);
+      const size_t i0 = (size_t)ctx * kDModel + (nn - 2 * kDModel);
       if (p.kv_f32) *reinterpret_cast<float4*>((float*)p.vring + i0) = v;
       else *reinterpret_cast<uint2*>((__nv_bfloat16*)p.vring + i0) = pack4_bf16(v.x, v.y, v.z, v.w);
     }
@@ -287,6 +299,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_wait(&tmem_full_bar[acc], (tl >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
+      int ctx[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = m0 + q * 32 + rd_row + 8 * i;
+        ctx[i] = m < M ? epilogue_row_ctx<MODE>(g.epi, m) : -1;
+      }
 #pragma unroll 1
       for (int c0 = 0; c0 < BN / 2; c0 += 16) {
         uint32_t v[16];
@@ -309,7 +327,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const float4 val = *reinterpret_cast<const float4*>(stage + r * kEpiPitch + 4 * c4);
           const int m = m0 + q * 32 + r;
           if (m < M && n < g.N) {
-            if (n + 3 < g.N && !ragged) epilogue_quad<MODE>(g.epi, m, n, val);
+            if (n + 3 < g.N && !ragged) epilogue_quad<MODE>(g.epi, m, ctx[i], n, val);
             else epilogue_edge(g.epi, m, n, g.N, val);
           }
         }
@@ -321,6 +339,202 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::kTmemCols) : "memory");
+  }
+}
+
+// ================================================================================================ 2-CTA variant
+// CTA pair (cluster of 2, tcgen05 cta_group::2) computing one 256 x 256 tile: CTA r of the pair stages the A rows
+// [m0 + 128 r, +128) and the W rows [n0 + 128 r, +128) of every k-block (32 KB per CTA per k-block for 128 x 256 x 64 MACs
+// per SM -- half the L2->SM operand traffic per MAC of the 128 x 128 single-CTA tile, which is what bounds that kernel).
+// The leader CTA (rank 0) issues tcgen05.mma.cta_group::2 (M = 256, N = 256); each SM accumulates its own 128 rows x 256
+// columns in its own TMEM (double-buffered: 512 columns) and runs its own epilogue.
+//   full[s]       : leader only; both CTAs' TMA loads complete_tx on it (64 KB per stage)
+//   empty[s]      : one per CTA; released by the leader's multicast tcgen05.commit
+//   tmem_full[a]  : one per CTA; multicast commit after the last k-block of a tile
+//   tmem_empty[a] : leader only; 16 arrivals (8 epilogue warps x 2 CTAs, the peer's arrive remotely)
+constexpr int kStages2 = 6;
+constexpr int kStageBytes2 = 2 * kTileABytes;
+constexpr size_t kSmemBytes2 = 1024 + (size_t)kStages2 * kStageBytes2 + (size_t)kEpiWarps * kEpiBytesPerWarp + 256;
+constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;      // shared::cluster address of the same offset in CTA rank 0 of the pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc_v, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc_v), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {      // arrives on `bar` at the same offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_rank0(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const GemmArgs g,
+                const int lo_row_off) {
+  constexpr int BN = 256, BM2 = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = base;                                    // [kStages2][16 KB]  this CTA's 128 A rows
+  uint8_t* sB = base + kStages2 * kTileABytes;           // [kStages2][16 KB]  this CTA's 128 W rows
+  float* sEpi = reinterpret_cast<float*>(base + kStages2 * kStageBytes2);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sEpi) + kEpiWarps * kEpiBytesPerWarp);
+  uint64_t* empty_bar = full_bar + kStages2;
+  uint64_t* tmem_full_bar = empty_bar + kStages2;        // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const bool f32_rows = MODE == EPI_F32 || MODE == EPI_BIAS_F32 || MODE == EPI_BIAS_RELU_F32 || MODE == EPI_BIAS_ROWMAP_F32 ||
+                        MODE == EPI_RESADD_F32;
+  const bool ragged = f32_rows && (g.epi.ldo & 3);
+  const int kb_per_pass = g.K / BK;
+  const int num_kb = kb_per_pass * (g.a_lo_off != 0 ? 2 : 1);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < kStages2; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 2 * kEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();                                    // barrier inits and the TMEM allocation are visible in both CTAs
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  pdl_enter();
+  const int M = g.M_dev ? min(*g.M_dev, g.M) : g.M;
+  const int tiles_m = (M + BM2 - 1) / BM2, tiles_n = (g.N + BN - 1) / BN;
+  const int total_tiles = tiles_m * tiles_n;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+        const int m0 = (tile % tiles_m) * BM2 + 128 * rank, n0 = (tile / tiles_m) * BN + 128 * rank;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStages2;
+          const uint32_t ph = (it / kStages2) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * kStageBytes2);
+          const uint32_t leader_full = smem_u32(&full_bar[s]) & kPeerBitMask;
+          const int pass = kb / kb_per_pass, kk = (kb % kb_per_pass) * BK;
+          tma_load_2d_2sm(sA + s * kTileABytes, &map_a, leader_full, kk, m0 + pass * lo_row_off);
+          tma_load_2d_2sm(sB + s * kTileABytes, &map_w, leader_full, kk, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      int it = 0, tl = 0;
+      for (int tile = pair; tile < total_tiles; tile += n_pairs, ++tl) {
+        const int acc = tl & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((tl >> 1) & 1) ^ 1);          // both CTAs' epilogues have drained this buffer
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStages2;
+          const uint32_t ph = (it / kStages2) & 1;
+          mbar_wait(&full_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = make_smem_desc(smem_u32(sA + s * kTileABytes));
+          const uint64_t db = make_smem_desc(smem_u32(sB + s * kTileABytes));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16_2sm(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc2, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[s]);
+        }
+        umma_commit_2sm(&tmem_full_bar[acc]);
+      }
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    float* stage = sEpi + (warp - 2) * (32 * kEpiPitch);
+    const int rsel = lane >> 2, c4 = lane & 3;
+    const int rd_row = (rsel & 1) * 4 + (rsel >> 1);
+    int tl = 0;
+    for (int tile = pair; tile < total_tiles; tile += n_pairs, ++tl) {
+      const int m0 = (tile % tiles_m) * BM2 + 128 * rank, n0 = (tile / tiles_m) * BN;
+      const int acc = tl & 1;
+      mbar_wait(&tmem_full_bar[acc], (tl >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
+      int ctx[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = m0 + q * 32 + rd_row + 8 * i;
+        ctx[i] = m < M ? epilogue_row_ctx<MODE>(g.epi, m) : -1;
+      }
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN / 2; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+        if (c0 + 16 == BN / 2) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive_rank0(&tmem_empty_bar[acc]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(stage + lane * kEpiPitch + 4 * j) =
+              make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        __syncwarp();
+        const int n = n0 + half * (BN / 2) + c0 + 4 * c4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = rd_row + 8 * i;
+          const float4 val = *reinterpret_cast<const float4*>(stage + r * kEpiPitch + 4 * c4);
+          const int m = m0 + q * 32 + r;
+          if (m < M && n < g.N) {
+            if (n + 3 < g.N && !ragged) epilogue_quad<MODE>(g.epi, m, ctx[i], n, val);
+            else epilogue_edge(g.epi, m, n, g.N, val);
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();                                    // neither CTA may exit (or free TMEM) while its peer can still reach it
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -340,6 +554,7 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+int g_two_cta = -1;       // PARAKEET_B200_GEMM_2CTA: 1 (default) = CTA-pair kernel where it applies, 0 = single-CTA kernel only
 int g_force_bn = -1;      // 0: heuristic; 128 / 256: forced tile width (PARAKEET_B200_GEMM_BN or gemm_tc_set_bn)
 int g_sm_count = 0;
 int sm_count() {
@@ -359,6 +574,20 @@ int pick_bn(int M, int N, int sms) {
   const long long t128 = tm * ((N + 127) / 128), t256 = tm * ((N + 255) / 256);
   const long long w128 = (t128 + sms - 1) / sms, w256 = (t256 + sms - 1) / sms;
   return (w256 * 3 < w128 * 2) ? 256 : 128;
+}
+
+// CTA-pair kernel or single-CTA kernel?  Measured on B200 (tools/kbench.cu, M = 6144): the pair kernel wins where its
+// 256 x 256 tiles fill whole waves of sms/2 pairs (N = 3072: +11 %) and on long-K problems, which are the most bound by
+// L2->SM operand delivery (N = 1024, K = 4096: +8 %); it loses where the coarser tiles quantise worse.
+bool pick_two_cta(int M, int N, int K, int sms) {
+  if (N % 256 != 0 || M < 2048) return false;
+  const int pairs = sms / 2;
+  const long long t2 = (long long)((M + 255) / 256) * (N / 256);
+  const double eff2 = (double)t2 / (double)(((t2 + pairs - 1) / pairs) * pairs);
+  const int bn = pick_bn(M, N, sms);
+  const long long t1 = (long long)((M + BM - 1) / BM) * ((N + bn - 1) / bn);
+  const double eff1 = (double)t1 / (double)(((t1 + sms - 1) / sms) * sms);
+  return eff2 > eff1 + 0.05 || (K >= 4096 && M >= 4096);
 }
 
 }  // namespace
@@ -385,6 +614,17 @@ void launch_cfg(int grid, const CUtensorMap& ma, const CUtensorMap& mw, const Ge
   launch_k(gemm_tc_kernel<BN, MODE>, dim3(grid), dim3(kThreads), Cfg<BN>::kSmemBytes, st, ma, mw, g, lo_row_off);
 }
 
+template <int MODE>
+void launch_cfg2(int pairs, const CUtensorMap& ma, const CUtensorMap& mw, const GemmArgs& g, int lo_row_off, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    PKB_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes2));
+    attr = true;
+  }
+  // cluster size comes from __cluster_dims__; the launch adds the programmatic-dependent-launch attribute
+  launch_k(gemm_tc2_kernel<MODE>, dim3(2 * pairs), dim3(kThreads), kSmemBytes2, st, ma, mw, g, lo_row_off);
+}
+
 void gemm_tc_set_bn(int bn) { g_force_bn = bn; }
 
 bool gemm_tc_supported(const GemmArgs& g) {
@@ -395,6 +635,23 @@ void gemm_tc(const GemmArgs& g, const TensorMap& map_a, const TensorMap& map_w, 
   PKB_CHECK(gemm_tc_supported(g), "gemm_tc: unsupported shape");
   const int sms = sm_count();
   if (g_force_bn < 0) { const char* v = getenv("PARAKEET_B200_GEMM_BN"); g_force_bn = v ? atoi(v) : 0; }
+  if (g_two_cta < 0) { const char* v = getenv("PARAKEET_B200_GEMM_2CTA"); g_two_cta = v ? atoi(v) : 1; }
+  const bool two_cta = g_force_bn == 512 || (g_force_bn == 0 && g_two_cta != 0 && pick_two_cta(g.M, g.N, g.K, sms));
+  if (two_cta) {
+    const int pair_tiles = ((g.M + 255) / 256) * ((g.N + 255) / 256);
+    const int pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;
+    const int lo_row_off2 = (int)(g.a_lo_off / g.lda);
+    const CUtensorMap& ma2 = *reinterpret_cast<const CUtensorMap*>(&map_a);
+    const CUtensorMap& mw2 = *reinterpret_cast<const CUtensorMap*>(&map_w);
+    switch (g.epi.mode) {
+#define PKB_GEMM_CASE2(MODE) case MODE: launch_cfg2<MODE>(pairs, ma2, mw2, g, lo_row_off2, st); break;
+      PKB_GEMM_CASE2(EPI_BIAS_F32) PKB_GEMM_CASE2(EPI_BIAS_RELU_F32) PKB_GEMM_CASE2(EPI_BIAS_RELU_ACT) PKB_GEMM_CASE2(EPI_BIAS_ROWMAP_F32)
+      PKB_GEMM_CASE2(EPI_SILU_ACT) PKB_GEMM_CASE2(EPI_RESADD_F32) PKB_GEMM_CASE2(EPI_QKV) PKB_GEMM_CASE2(EPI_GLU_F32) PKB_GEMM_CASE2(EPI_F32)
+#undef PKB_GEMM_CASE2
+      default: PKB_CHECK(false, "gemm_tc: unknown epilogue mode");
+    }
+    return;
+  }
   const int bn = g_force_bn == 128 || g_force_bn == 256 ? g_force_bn : pick_bn(g.M, g.N, sms);
   const int tiles = ((g.M + BM - 1) / BM) * ((g.N + bn - 1) / bn);
   const int grid = tiles < sms ? tiles : sms;
