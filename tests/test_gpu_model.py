@@ -224,6 +224,26 @@ def test_streaming_decode_token_parity(eng, oracle_small, features_ref):
         assert same >= 0.9 * total, f"{same}/{total} chunks identical"       # bf16 operands: see the 24-layer parity-set test
 
 
+@pytest.mark.parametrize("prec", [1, 0], ids=["precise", "bf16"])
+def test_decode_many_streams_fused_argmax(model_small, oracle_small, features_ref, prec):
+    """More than 16 streams in one batch: the joint output layer runs on the tensor-core kernel with the greedy selection
+    fused into its epilogue (slab maxima + first-argmax, logits never written).  Traces must match the oracle's full-logit
+    argmax (first maximum wins, blank/duration rules) stream by stream."""
+    m = oracle_small
+    n = 24
+    e = binding.Engine(model_small, max_streams=n, precision=prec, max_rows=8 * n)
+    e.precision = prec
+    feats = [_feats(features_ref, 2.5, 3000 + i) for i in range(n)]
+    total, same, toks = _run_streams(e, m, feats, n_chunks=5, starts=[i % 3 for i in range(n)])
+    e.close()
+    assert total == 5 * n
+    if prec == 1:
+        assert same == total, f"{same}/{total} chunks identical"
+        assert all(a == b for a, b in toks)
+    else:
+        assert same >= 0.9 * total, f"{same}/{total} chunks identical"
+
+
 def test_legacy_session_abi(model_small, oracle_small, features_ref):
     """The drop-in path: ParakeetSessionSafe (mirror of rust/parakeet_trt) -- push, poll, reset, error conventions."""
     m = oracle_small

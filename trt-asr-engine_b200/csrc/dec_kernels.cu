@@ -36,11 +36,16 @@ tdt_select_kernel(DecodeDev d) {
   const float* lg = d.logits + (size_t)e * kJointOut;
   float best = -INFINITY;
   int bidx = 0x7fffffff;
-  for (int i = tid; i < kVocab; i += 256) {
-    float v = lg[i];
-    if (v != v) v = -100.0f;                                  // NaN logits -> -100 (parakeet_trt.cpp:2971)
-    if (i == kBlank) v -= d.blank_penalty;                    // PARAKEET_BLANK_PENALTY (:3175-3178), default 0
-    if (v > best) { best = v; bidx = i; }                     // ascending i per thread: first max wins
+  if (d.fused_argmax) {
+    // the joint GEMM's epilogue already reduced every 128-column slab: finish over the kArgmaxParts slab winners
+    if (tid < kArgmaxParts) { best = d.part_val[(size_t)e * kArgmaxParts + tid]; bidx = d.part_idx[(size_t)e * kArgmaxParts + tid]; }
+  } else {
+    for (int i = tid; i < kVocab; i += 256) {
+      float v = lg[i];
+      if (v != v) v = -100.0f;                                  // NaN logits -> -100 (parakeet_trt.cpp:2971)
+      if (i == kBlank) v -= d.blank_penalty;                    // PARAKEET_BLANK_PENALTY (:3175-3178), default 0
+      if (v > best) { best = v; bidx = i; }                     // ascending i per thread: first max wins
+    }
   }
   // block reduce (value desc, index asc) == "first maximum wins" of the reference's strict '>' scan (:3200-3206)
 #pragma unroll
@@ -60,11 +65,12 @@ tdt_select_kernel(DecodeDev d) {
   const int slot = d.slot[e];
   // leading punctuation-only suppression while nothing has been emitted in this utterance (:3256-3262)
   if (d.punct_suppress && d.n_emitted[slot] == 0 && tok < kBlank && ((d.punct_bits[tok >> 5] >> (tok & 31)) & 1u)) tok = kBlank;
+  const float* dl = d.fused_argmax ? d.dur_logits + (size_t)e * kNDur : lg + kVocab;
   int dbest = 0;
-  float dv = lg[kVocab];
+  float dv = dl[0];
   if (dv != dv) dv = -100.0f;
   for (int i = 1; i < kNDur; ++i) {
-    float v = lg[kVocab + i];
+    float v = dl[i];
     if (v != v) v = -100.0f;
     if (v > dv) { dv = v; dbest = i; }
   }

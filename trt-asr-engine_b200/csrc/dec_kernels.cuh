@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "enc_kernels.cuh"
+#include "gemm.h"
 
 namespace pkb {
 
@@ -28,7 +29,11 @@ struct DecodeDev {
   // tensors
   const float* enc_proj = nullptr;   // [M,640]  joint.enc(enc) + bias
   float* pred_proj = nullptr;        // [slots,640] joint.pred(g) + bias (cached per stream, refreshed on emission)
-  const float* logits = nullptr;     // [B,8198]
+  const float* logits = nullptr;     // [B,8198]  (SIMT joint path: full logits)
+  const float* part_val = nullptr;   // tensor-core joint path: [B][kArgmaxParts] slab maxima / first argmaxes of the token head
+  const int* part_idx = nullptr;     //   (GEMM epilogue EPI_ARGMAX; NaN guard and blank penalty already applied)
+  const float* dur_logits = nullptr; // [B][kNDur]
+  int fused_argmax = 0;              // 1: select from the partials, 0: scan d.logits
   const float* gates = nullptr;      // [B,2560]
   const __nv_bfloat16* embed = nullptr;  // [8193,640]
   const unsigned* punct_bits = nullptr;  // [ceil(8193/32)]

@@ -182,7 +182,8 @@ struct Engine::Impl {
   ActBuf a_sub1, a_sub2, a_sub3, a_ln, a_ff, a_xf, a_hid, a_pred, a_g, a_imp, a_pos;
   __nv_bfloat16* q_bf16 = nullptr;       // bf16 mode: [2][Mcap,1024] (q + pos_bias_u | q + pos_bias_v)
   float *x = nullptr, *q = nullptr, *cglu = nullptr, *y1 = nullptr, *enc_proj = nullptr, *logits = nullptr, *gates = nullptr,
-        *enc_out = nullptr, *ppos_tmp = nullptr, *scratch_f32 = nullptr;
+        *enc_out = nullptr, *ppos_tmp = nullptr, *scratch_f32 = nullptr, *part_val = nullptr, *dur_logits = nullptr;
+  int* part_idx = nullptr;
   size_t scratch_f32_elems = 0;
   int* batch_ints = nullptr;             // device: entry arrays + prefixes
   int* batch_ints_host = nullptr;        // pinned
@@ -516,6 +517,9 @@ void Engine::alloc_state() {
   im.enc_proj = dev_alloc<float>((size_t)std::max(im.Mcap, rows_dec) * kJointH);
   im.logits = dev_alloc<float>((size_t)rows_dec * kJointOut);
   im.gates = dev_alloc<float>((size_t)rows_dec * 4 * kPredH);
+  im.part_val = dev_alloc<float>((size_t)rows_dec * kArgmaxParts);
+  im.part_idx = dev_alloc<int>((size_t)rows_dec * kArgmaxParts);
+  im.dur_logits = dev_alloc<float>((size_t)rows_dec * kNDur);
   im.enc_out = dev_alloc<float>((size_t)im.Bcap * kDModel * kValidOut);
   im.ppos_tmp = dev_alloc<float>((size_t)kPosRows * kDModel);
   im.scratch_f32_elems = (size_t)L_ * kCacheS * kDModel;     // one stream's contract cache (import / export staging)
@@ -1020,13 +1024,20 @@ void Engine::run_decode(const BatchDev& b, const std::vector<Entry>& entries) {
   { EpiParams e; e.mode = EPI_BIAS_F32; e.out_f32 = im.enc_proj; e.ldo = kJointH; e.bias = im.joint_enc_b;
     RUN_GEMM(im.a_xf, im.joint_enc, b.M, nullptr, e); }
   DecodeDev d = make_decode_dev(im, opt_, b.B, b.slot, b.row_off, im.batch_ints + 10 * im.Bcap);
+  d.fused_argmax = (opt_.gemm_backend == 2 || (opt_.gemm_backend == 0 && b.B > 16)) && tc_mask() < 0 ? 1 : 0;
   launch_decode_begin(d, st_); ++launches_;
   const int max_iters = kValidOut * (kMaxSymbols + 1) + 2;
   for (int it = 0; it < max_iters; ++it) {
     launch_decode_iter_reset(d, st_); ++launches_;
     launch_joint_hidden(d, st_); ++launches_;
-    { EpiParams e; e.mode = EPI_BIAS_F32; e.out_f32 = im.logits; e.ldo = kJointOut; e.bias = im.joint_out_b;
-      RUN_GEMM(im.a_hid, im.joint_out, b.B, nullptr, e); }
+    if (d.fused_argmax) {      // tensor-core joint: greedy selection fused into the epilogue, logits never leave the SM
+      EpiParams e; e.mode = EPI_ARGMAX; e.bias = im.joint_out_b; e.part_val = im.part_val; e.part_idx = im.part_idx;
+      e.dur_out = im.dur_logits; e.blank_penalty = opt_.blank_penalty;
+      RUN_GEMM(im.a_hid, im.joint_out, b.B, nullptr, e);
+    } else {
+      EpiParams e; e.mode = EPI_BIAS_F32; e.out_f32 = im.logits; e.ldo = kJointOut; e.bias = im.joint_out_b;
+      RUN_GEMM(im.a_hid, im.joint_out, b.B, nullptr, e);
+    }
     launch_tdt_select(d, st_); ++launches_;
     PKB_CUDA(cudaMemcpyAsync(im.counters_host, im.counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, st_));
     run_predictor_pass(d);
@@ -1042,6 +1053,7 @@ static DecodeDev make_decode_dev(Engine::Impl& im, const EngineOptions& opt, int
   d.t_cur = im.t_cur; d.n_sym = im.n_sym; d.active = im.active; d.emit_tok = im.emit_tok; d.pred_rowmap = im.pred_rowmap;
   d.n_steps = im.n_steps; d.steps = im.steps; d.n_active = im.counters; d.m_pred = im.counters + 1;
   d.enc_proj = im.enc_proj; d.pred_proj = im.pred_proj; d.logits = im.logits; d.gates = im.gates; d.embed = im.embed;
+  d.part_val = im.part_val; d.part_idx = im.part_idx; d.dur_logits = im.dur_logits;
   d.punct_bits = im.punct_bits; d.pred_h = im.pred_h; d.pred_c = im.pred_c; d.pred_g = im.pred_g; d.n_emitted = im.n_emitted;
   d.y_id = im.y_id; d.act_hidden = im.a_hid.out(); d.act_pred = im.a_pred.out(); d.act_g = im.a_g.out();
   return d;

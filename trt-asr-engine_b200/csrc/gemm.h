@@ -24,7 +24,12 @@ enum EpiMode : int {
   EPI_QKV = 6,             // n<1024: q f32; [1024,2048): K^T ring; [2048,3072): V ring
   EPI_GLU_F32 = 7,         // interleaved weights: out_f32[m,n/2] = acc[n] * sigmoid(acc[n+1]), n even
   EPI_F32 = 8,             // out_f32[m,n] = acc
+  EPI_ARGMAX = 9,          // joint output layer with the greedy selection fused (tensor-core backend only): per row and per
+                           // 128-column slab the running (max, first argmax) of acc + bias over the token head [0, kVocab)
+                           // goes to part_val / part_idx [m][2 * tiles_n]; the kNDur duration logits go to dur_out [m][kNDur].
+                           // NaN -> -100 and the blank penalty are applied here; the logits are never written.
 };
+constexpr int kArgmaxParts = 2 * ((kJointOut + 255) / 256);   // slabs per row (256-wide tiles, two 128-column halves each)
 
 struct EpiParams {
   int mode = EPI_F32;
@@ -49,6 +54,10 @@ struct EpiParams {
   long long q_plane = 0;            // elements between the planes
   const float* bias_u = nullptr;    // [1024] = pos_bias_u[head][128] flattened
   const float* bias_v = nullptr;
+  float* part_val = nullptr;        // EPI_ARGMAX: [M][kArgmaxParts]
+  int* part_idx = nullptr;
+  float* dur_out = nullptr;         // [M][kNDur]
+  float blank_penalty = 0.0f;
   int k_natural = 0;                // 1: the K ring has the V layout [slot][kRingCap][1024] (tensor-core attention); 0: K^T
 };
 

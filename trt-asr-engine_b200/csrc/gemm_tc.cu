@@ -305,6 +305,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int m = m0 + q * 32 + rd_row + 8 * i;
         ctx[i] = m < M ? epilogue_row_ctx<MODE>(g.epi, m) : -1;
       }
+      float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};      // EPI_ARGMAX: running first-maximum per row
+      int bidx[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
 #pragma unroll 1
       for (int c0 = 0; c0 < BN / 2; c0 += 16) {
         uint32_t v[16];
@@ -326,9 +328,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int r = rd_row + 8 * i;
           const float4 val = *reinterpret_cast<const float4*>(stage + r * kEpiPitch + 4 * c4);
           const int m = m0 + q * 32 + r;
-          if (m < M && n < g.N) {
-            if (n + 3 < g.N && !ragged) epilogue_quad<MODE>(g.epi, m, ctx[i], n, val);
-            else epilogue_edge(g.epi, m, n, g.N, val);
+          if constexpr (MODE == EPI_ARGMAX) {
+            if (m < M && n < g.N) {
+              const float vv[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+              for (int x = 0; x < 4; ++x) {
+                const int col = n + x;
+                if (col >= g.N) break;
+                float y = vv[x] + g.epi.bias[col];
+                if (y != y) y = -100.0f;                                  // NaN logits -> -100 (parakeet_trt.cpp:2971)
+                if (col == kBlank) y -= g.epi.blank_penalty;              // PARAKEET_BLANK_PENALTY (:3175-3178)
+                if (col < kVocab) { if (y > best[i]) { best[i] = y; bidx[i] = col; } }   // ascending columns: first maximum wins
+                else g.epi.dur_out[(size_t)m * kNDur + (col - kVocab)] = y;
+              }
+            }
+          } else {
+            if (m < M && n < g.N) {
+              if (n + 3 < g.N && !ragged) epilogue_quad<MODE>(g.epi, m, ctx[i], n, val);
+              else epilogue_edge(g.epi, m, n, g.N, val);
+            }
+          }
+        }
+      }
+      if constexpr (MODE == EPI_ARGMAX) {
+        // the 4 lanes c4 = 0..3 of a row hold disjoint column sets: warp-level (value desc, index asc) reduction, then one
+        // (max, argmax) per row and 128-column slab
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+          for (int off = 1; off <= 2; off <<= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best[i], off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bidx[i], off);
+            if (ov > best[i] || (ov == best[i] && oi < bidx[i])) { best[i] = ov; bidx[i] = oi; }
+          }
+          const int m = m0 + q * 32 + rd_row + 8 * i;
+          if (c4 == 0 && m < M) {
+            const size_t o = (size_t)m * kArgmaxParts + (size_t)(n0 / BN) * 2 + half;
+            g.epi.part_val[o] = best[i];
+            g.epi.part_idx[o] = bidx[i];
           }
         }
       }
@@ -636,7 +673,8 @@ void gemm_tc(const GemmArgs& g, const TensorMap& map_a, const TensorMap& map_w, 
   const int sms = sm_count();
   if (g_force_bn < 0) { const char* v = getenv("PARAKEET_B200_GEMM_BN"); g_force_bn = v ? atoi(v) : 0; }
   if (g_two_cta < 0) { const char* v = getenv("PARAKEET_B200_GEMM_2CTA"); g_two_cta = v ? atoi(v) : 1; }
-  const bool two_cta = g_force_bn == 512 || (g_force_bn == 0 && g_two_cta != 0 && pick_two_cta(g.M, g.N, g.K, sms));
+  const bool two_cta = g.epi.mode != EPI_ARGMAX &&
+                       (g_force_bn == 512 || (g_force_bn == 0 && g_two_cta != 0 && pick_two_cta(g.M, g.N, g.K, sms)));
   if (two_cta) {
     const int pair_tiles = ((g.M + 255) / 256) * ((g.N + 255) / 256);
     const int pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;
@@ -667,6 +705,11 @@ void gemm_tc(const GemmArgs& g, const TensorMap& map_a, const TensorMap& map_w, 
     PKB_GEMM_CASE(EPI_BIAS_F32) PKB_GEMM_CASE(EPI_BIAS_RELU_F32) PKB_GEMM_CASE(EPI_BIAS_RELU_ACT) PKB_GEMM_CASE(EPI_BIAS_ROWMAP_F32)
     PKB_GEMM_CASE(EPI_SILU_ACT) PKB_GEMM_CASE(EPI_RESADD_F32) PKB_GEMM_CASE(EPI_QKV) PKB_GEMM_CASE(EPI_GLU_F32) PKB_GEMM_CASE(EPI_F32)
 #undef PKB_GEMM_CASE
+    case EPI_ARGMAX: {      // slab geometry (kArgmaxParts) is defined for 256-wide tiles
+      const int tiles256 = ((g.M + BM - 1) / BM) * ((g.N + 255) / 256);
+      launch_cfg<256, EPI_ARGMAX>(tiles256 < sms ? tiles256 : sms, ma, mw, g, lo_row_off, st);
+      break;
+    }
     default: PKB_CHECK(false, "gemm_tc: unknown epilogue mode");
   }
   PKB_CUDA(cudaGetLastError());
