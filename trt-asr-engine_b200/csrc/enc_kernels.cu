@@ -178,7 +178,8 @@ __device__ __forceinline__ void ln_row(float (&v)[32], const float* __restrict__
 
 __global__ void __launch_bounds__(256)
 layernorm_kernel(float* __restrict__ x, int M, const float* __restrict__ g1, const float* __restrict__ b1,
-                 const float* __restrict__ g2, const float* __restrict__ b2, int write_x, ActOut a, AcacheOut ac, int has_ac) {
+                 const float* __restrict__ g2, const float* __restrict__ b2, int write_x, ActOut a, AcacheOut ac, int has_ac,
+                 LnResidual res) {
   pdl_enter();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -189,6 +190,23 @@ layernorm_kernel(float* __restrict__ x, int M, const float* __restrict__ g1, con
   for (int i = 0; i < 8; ++i) {
     const float4 t = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
     v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+  if (res.part != nullptr) {
+    // deferred residual of the preceding split-K GEMM: x += scale * (p_0 + p_1 + ...), splits added in index order
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int sp = 0; sp < res.splits; ++sp) {
+        const float4 t = *reinterpret_cast<const float4*>(res.part + (size_t)sp * res.split_stride + (size_t)row * kDModel + i * 128 + lane * 4);
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      }
+      v[4 * i] += res.scale * acc.x; v[4 * i + 1] += res.scale * acc.y; v[4 * i + 2] += res.scale * acc.z; v[4 * i + 3] += res.scale * acc.w;
+    }
+    if (!write_x) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(xr + i * 128 + lane * 4) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
   }
   ln_row(v, g1, b1, lane);
   if (has_ac) {
@@ -217,10 +235,12 @@ layernorm_kernel(float* __restrict__ x, int M, const float* __restrict__ g1, con
     store_act4(a.ptr, row, a.lda, i * 128 + lane * 4, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), a.lo_off);
 }
 void launch_layernorm(float* x, int M, const float* g1, const float* b1, const float* g2, const float* b2, int write_x, ActOut a,
-                      const AcacheOut* ac, cudaStream_t st) {
+                      const AcacheOut* ac, cudaStream_t st, const LnResidual* res) {
   if (M <= 0) return;
   AcacheOut z{};
-  launch_k(layernorm_kernel, dim3((M + 7) / 8), dim3(256), 0, st, x, M, g1, b1, g2, b2, write_x, a, ac ? *ac : z, (int)(ac != nullptr));
+  LnResidual r0{};
+  launch_k(layernorm_kernel, dim3((M + 7) / 8), dim3(256), 0, st, x, M, g1, b1, g2, b2, write_x, a, ac ? *ac : z, (int)(ac != nullptr),
+           res ? *res : r0);
   PKB_CUDA(cudaGetLastError());
 }
 

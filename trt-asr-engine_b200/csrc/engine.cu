@@ -184,6 +184,8 @@ struct Engine::Impl {
   float *x = nullptr, *q = nullptr, *cglu = nullptr, *y1 = nullptr, *enc_proj = nullptr, *logits = nullptr, *gates = nullptr,
         *enc_out = nullptr, *ppos_tmp = nullptr, *scratch_f32 = nullptr, *part_val = nullptr, *dur_logits = nullptr;
   int* part_idx = nullptr;
+  float* part_ws = nullptr;              // split-K partial sums [4][part_rows][1024] (deferred residual)
+  int part_rows = 0;
   size_t scratch_f32_elems = 0;
   int* batch_ints = nullptr;             // device: entry arrays + prefixes
   int* batch_ints_host = nullptr;        // pinned
@@ -517,6 +519,8 @@ void Engine::alloc_state() {
   im.enc_proj = dev_alloc<float>((size_t)std::max(im.Mcap, rows_dec) * kJointH);
   im.logits = dev_alloc<float>((size_t)rows_dec * kJointOut);
   im.gates = dev_alloc<float>((size_t)rows_dec * 4 * kPredH);
+  im.part_rows = std::min(im.Mcap, 2048);            // split-K is only used for small batched passes
+  im.part_ws = dev_alloc<float>((size_t)4 * im.part_rows * kDModel);
   im.part_val = dev_alloc<float>((size_t)rows_dec * kArgmaxParts);
   im.part_idx = dev_alloc<int>((size_t)rows_dec * kArgmaxParts);
   im.dur_logits = dev_alloc<float>((size_t)rows_dec * kNDur);
@@ -936,6 +940,25 @@ void Engine::run_encoder(const BatchDev& b) {
   // ---- conformer layers ----
   g_tc_site = 8;
   const int M = b.M;
+  // Residual GEMMs (N = 1024).  Large batches add into x in the epilogue.  Small batches leave too few 128 x 128 tiles for
+  // 148 SMs, so the k-range is split over more CTAs; the partial sums go to a workspace and the LayerNorm that follows adds
+  // them to x in a fixed order (deterministic, no atomics).
+  auto residual_gemm = [&](const ActBuf& act, const GemmW& wt, float scale) -> LnResidual {
+    const bool tc = (opt_.gemm_backend == 2 || (opt_.gemm_backend == 0 && M > 16)) && tc_mask() < 0 && !im.profile;
+    const int tiles = ((M + 127) / 128) * (wt.N / 128);
+    int splits = tiles > 0 ? std::min(4, sm_count_ / tiles) : 1;
+    splits = std::min(splits, wt.K / 64 / 2);
+    static const bool allow = [] { const char* v = getenv("PARAKEET_B200_SPLITK"); return !(v && v[0] == '0'); }();
+    if (tc && allow && splits >= 2 && M <= im.part_rows && wt.N == kDModel) {
+      EpiParams e; e.mode = EPI_PARTIAL_F32; e.out_f32 = im.part_ws; e.ldo = kDModel; e.splits = splits; e.part_rows = im.part_rows;
+      RUN_GEMM(act, wt, M, nullptr, e);
+      return LnResidual{im.part_ws, splits, (long long)im.part_rows * kDModel, scale};
+    }
+    EpiParams e; e.mode = EPI_RESADD_F32; e.out_f32 = im.x; e.ldo = kDModel; e.scale = scale;
+    RUN_GEMM(act, wt, M, nullptr, e);
+    return LnResidual{nullptr, 0, 0, 0.f};
+  };
+  LnResidual res{};
   launch_layernorm(im.x, M, im.layers[0].n_ff1_g, im.layers[0].n_ff1_b, nullptr, nullptr, 0, im.a_ln.out(), nullptr, st_); ++launches_;
   const size_t kv_elem = split ? 4 : 2;
   for (int l = 0; l < L_; ++l) {
@@ -947,15 +970,14 @@ void Engine::run_encoder(const BatchDev& b) {
     { EpiParams e; e.mode = EPI_SILU_ACT; e.out_act = im.a_ff.ptr; e.lda_out = kFF; e.lo_off_out = im.a_ff.lo_off;
       RUN_GEMM(im.a_ln, w.ff1_1, M, nullptr, e); }
     g_tc_site = 128;
-    { EpiParams e; e.mode = EPI_RESADD_F32; e.out_f32 = im.x; e.ldo = kDModel; e.scale = 0.5f;
-      RUN_GEMM(im.a_ff, w.ff1_2, M, nullptr, e); }
+    res = residual_gemm(im.a_ff, w.ff1_2, 0.5f);
     // self-attention
     AcacheOut ac{};
     if (im.acache) {
       ac.ring = (char*)im.acache + (size_t)l * im.ring_layer_elems * kv_elem; ac.is_f32 = split ? 1 : 0;
       ac.row_entry = b.row_entry; ac.row_pos = b.row_pos; ac.entry_slot = b.slot; ac.entry_head = b.head;
     }
-    launch_layernorm(im.x, M, w.n_att_g, w.n_att_b, nullptr, nullptr, 0, im.a_ln.out(), im.acache ? &ac : nullptr, st_); ++launches_;
+    launch_layernorm(im.x, M, w.n_att_g, w.n_att_b, nullptr, nullptr, 0, im.a_ln.out(), im.acache ? &ac : nullptr, st_, &res); ++launches_;
     g_tc_site = 256;
     { EpiParams e; e.mode = EPI_QKV; e.out_f32 = im.q; e.ldo = kDModel; e.row_entry = b.row_entry; e.row_pos = b.row_pos;
       e.entry_slot = b.slot; e.entry_head = b.head; e.kring = kr; e.vring = vr; e.kv_f32 = split ? 1 : 0;
@@ -972,10 +994,9 @@ void Engine::run_encoder(const BatchDev& b) {
       launch_attention(b, a, st_); ++launches_;
     }
     g_tc_site = 512;
-    { EpiParams e; e.mode = EPI_RESADD_F32; e.out_f32 = im.x; e.ldo = kDModel; e.scale = 1.0f;
-      RUN_GEMM(im.a_ln, w.out, M, nullptr, e); }
+    res = residual_gemm(im.a_ln, w.out, 1.0f);
     // convolution module
-    launch_layernorm(im.x, M, w.n_conv_g, w.n_conv_b, nullptr, nullptr, 0, im.a_ln.out(), nullptr, st_); ++launches_;
+    launch_layernorm(im.x, M, w.n_conv_g, w.n_conv_b, nullptr, nullptr, 0, im.a_ln.out(), nullptr, st_, &res); ++launches_;
     g_tc_site = 1024;
     { EpiParams e; e.mode = EPI_GLU_F32; e.out_f32 = im.cglu; e.ldo = kDModel;
       RUN_GEMM(im.a_ln, w.pw1, M, nullptr, e); }
@@ -983,20 +1004,18 @@ void Engine::run_encoder(const BatchDev& b) {
       a.w = w.dw_w; a.bias = w.dw_b; a.out = im.a_ln.out();
       launch_dwconv(b, a, st_); ++launches_; }
     g_tc_site = 2048;
-    { EpiParams e; e.mode = EPI_RESADD_F32; e.out_f32 = im.x; e.ldo = kDModel; e.scale = 1.0f;
-      RUN_GEMM(im.a_ln, w.pw2, M, nullptr, e); }
+    res = residual_gemm(im.a_ln, w.pw2, 1.0f);
     // FFN 2
-    launch_layernorm(im.x, M, w.n_ff2_g, w.n_ff2_b, nullptr, nullptr, 0, im.a_ln.out(), nullptr, st_); ++launches_;
+    launch_layernorm(im.x, M, w.n_ff2_g, w.n_ff2_b, nullptr, nullptr, 0, im.a_ln.out(), nullptr, st_, &res); ++launches_;
     g_tc_site = 64;
     { EpiParams e; e.mode = EPI_SILU_ACT; e.out_act = im.a_ff.ptr; e.lda_out = kFF; e.lo_off_out = im.a_ff.lo_off;
       RUN_GEMM(im.a_ln, w.ff2_1, M, nullptr, e); }
     g_tc_site = 128;
-    { EpiParams e; e.mode = EPI_RESADD_F32; e.out_f32 = im.x; e.ldo = kDModel; e.scale = 0.5f;
-      RUN_GEMM(im.a_ff, w.ff2_2, M, nullptr, e); }
+    res = residual_gemm(im.a_ff, w.ff2_2, 0.5f);
     // norm_out (+ next layer's norm_feed_forward1; after the last layer: operand of the joint's encoder projection)
     const bool last = l + 1 == L_;
     launch_layernorm(im.x, M, w.n_out_g, w.n_out_b, last ? nullptr : im.layers[l + 1].n_ff1_g, last ? nullptr : im.layers[l + 1].n_ff1_b,
-                     1, last ? im.a_xf.out() : im.a_ln.out(), nullptr, st_); ++launches_;
+                     1, last ? im.a_xf.out() : im.a_ln.out(), nullptr, st_, &res); ++launches_;
   }
   launch_gather_output(b, im.x, im.enc_out, st_); ++launches_;
 }

@@ -24,11 +24,15 @@ enum EpiMode : int {
   EPI_QKV = 6,             // n<1024: q f32; [1024,2048): K^T ring; [2048,3072): V ring
   EPI_GLU_F32 = 7,         // interleaved weights: out_f32[m,n/2] = acc[n] * sigmoid(acc[n+1]), n even
   EPI_F32 = 8,             // out_f32[m,n] = acc
+  EPI_PARTIAL_F32 = 10,
   EPI_ARGMAX = 9,          // joint output layer with the greedy selection fused (tensor-core backend only): per row and per
                            // 128-column slab the running (max, first argmax) of acc + bias over the token head [0, kVocab)
                            // goes to part_val / part_idx [m][2 * tiles_n]; the kNDur duration logits go to dur_out [m][kNDur].
                            // NaN -> -100 and the blank penalty are applied here; the logits are never written.
 };
+// EPI_PARTIAL_F32 (= 10, tensor-core backend only): split-K.  The k-range is cut into epi.splits parts, split s writes its raw
+// partial sums to out_f32[(s * part_rows + m) * ldo + n]; the consumer (the LayerNorm that follows every residual GEMM) adds
+// them to the residual stream in a fixed order, so the result does not depend on scheduling.
 constexpr int kArgmaxParts = 2 * ((kJointOut + 255) / 256);   // slabs per row (256-wide tiles, two 128-column halves each)
 
 struct EpiParams {
@@ -54,6 +58,8 @@ struct EpiParams {
   long long q_plane = 0;            // elements between the planes
   const float* bias_u = nullptr;    // [1024] = pos_bias_u[head][128] flattened
   const float* bias_v = nullptr;
+  int splits = 1;                   // EPI_PARTIAL_F32: number of k-splits
+  int part_rows = 0;                //                  rows per split in the workspace
   float* part_val = nullptr;        // EPI_ARGMAX: [M][kArgmaxParts]
   int* part_idx = nullptr;
   float* dur_out = nullptr;         // [M][kNDur]

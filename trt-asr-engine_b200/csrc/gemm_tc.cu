@@ -126,8 +126,10 @@ __device__ __noinline__ void epilogue_edge(const EpiParams& p, int m, int n, int
 // Per-row context, computed once per (tile, row) instead of once per quad: the mapped output row (row-map mode, < 0 =
 // dropped) or the ring row slot * kRingCap + phys of the stream this packed row belongs to (QKV mode).
 template <int MODE>
-__device__ __forceinline__ int epilogue_row_ctx(const EpiParams& p, int m) {
-  if constexpr (MODE == EPI_BIAS_ROWMAP_F32) {
+__device__ __forceinline__ int epilogue_row_ctx(const EpiParams& p, int m, int split) {
+  if constexpr (MODE == EPI_PARTIAL_F32) {
+    return split * p.part_rows + m;
+  } else if constexpr (MODE == EPI_BIAS_ROWMAP_F32) {
     return p.row_map[m];
   } else if constexpr (MODE == EPI_QKV) {
     const int e = p.row_entry[m];
@@ -144,6 +146,8 @@ __device__ __forceinline__ void epilogue_quad(const EpiParams& p, int m, int ctx
   const int nn = n + p.n_off;
   if constexpr (MODE == EPI_F32) {
     *reinterpret_cast<float4*>(p.out_f32 + (size_t)m * p.ldo + nn) = v;
+  } else if constexpr (MODE == EPI_PARTIAL_F32) {
+    *reinterpret_cast<float4*>(p.out_f32 + (size_t)ctx * p.ldo + nn) = v;
   } else if constexpr (MODE == EPI_BIAS_F32 || MODE == EPI_BIAS_RELU_F32 || MODE == EPI_BIAS_ROWMAP_F32) {
     const float4 b = *reinterpret_cast<const float4*>(p.bias + nn);
     v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
@@ -222,7 +226,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         MODE == EPI_RESADD_F32;
   const bool ragged = f32_rows && (g.epi.ldo & 3);
   const int kb_per_pass = g.K / BK;
-  const int num_kb = kb_per_pass * (g.a_lo_off != 0 ? 2 : 1);
+  const int n_pass = g.a_lo_off != 0 ? 2 : 1;
+  const int splits = MODE == EPI_PARTIAL_F32 ? g.epi.splits : 1;      // work unit = (tile, k-split), split fastest
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -243,19 +248,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   pdl_enter();      // barrier init + TMEM allocation above overlap the previous kernel's tail; global data only from here on
   const int M = g.M_dev ? min(*g.M_dev, g.M) : g.M;
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN;
-  const int total_tiles = tiles_m * tiles_n;            // CTAs beyond the (device-side) tile count fall through to the teardown
+  const int total_tiles = tiles_m * tiles_n * splits;   // CTAs beyond the (device-side) unit count fall through to the teardown
 
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < total_tiles; unit += gridDim.x) {
+        const int tile = unit / splits, sp = unit - tile * splits;
         const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+        const int kb_lo = sp * kb_per_pass / splits, kbs = (sp + 1) * kb_per_pass / splits - kb_lo;
+        const int num_kb = kbs * n_pass;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], C::kStageBytes);
-          const int pass = kb / kb_per_pass, kk = (kb % kb_per_pass) * BK;
+          const int pass = kb / kbs, kk = (kb_lo + kb % kbs) * BK;
           tma_load_2d(sA + s * kTileABytes, &map_a, &full_bar[s], kk, m0 + pass * lo_row_off);
 #pragma unroll
           for (int j = 0; j < BN / 128; ++j)
@@ -266,7 +274,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp == 1) {
     if (lane == 0) {
       int it = 0, tl = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+      for (int unit = blockIdx.x; unit < total_tiles; unit += gridDim.x, ++tl) {
+        const int sp = unit % splits;
+        const int num_kb = ((sp + 1) * kb_per_pass / splits - sp * kb_per_pass / splits) * n_pass;
         const int acc = tl & 1;
         mbar_wait(&tmem_empty_bar[acc], ((tl >> 1) & 1) ^ 1);          // epilogue has drained this accumulator buffer
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -293,7 +303,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int rsel = lane >> 2, c4 = lane & 3;
     const int rd_row = (rsel & 1) * 4 + (rsel >> 1);        // rows r and r+4 in one quarter-warp: conflict-free reads
     int tl = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+    for (int unit = blockIdx.x; unit < total_tiles; unit += gridDim.x, ++tl) {
+      const int tile = unit / splits, sp = unit - tile * splits;
       const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
       const int acc = tl & 1;
       mbar_wait(&tmem_full_bar[acc], (tl >> 1) & 1);
@@ -303,7 +314,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int m = m0 + q * 32 + rd_row + 8 * i;
-        ctx[i] = m < M ? epilogue_row_ctx<MODE>(g.epi, m) : -1;
+        ctx[i] = m < M ? epilogue_row_ctx<MODE>(g.epi, m, sp) : -1;
       }
       float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};      // EPI_ARGMAX: running first-maximum per row
       int bidx[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
@@ -536,7 +547,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int m = m0 + q * 32 + rd_row + 8 * i;
-        ctx[i] = m < M ? epilogue_row_ctx<MODE>(g.epi, m) : -1;
+        ctx[i] = m < M ? epilogue_row_ctx<MODE>(g.epi, m, 0) : -1;
       }
 #pragma unroll 1
       for (int c0 = 0; c0 < BN / 2; c0 += 16) {
@@ -673,7 +684,7 @@ void gemm_tc(const GemmArgs& g, const TensorMap& map_a, const TensorMap& map_w, 
   const int sms = sm_count();
   if (g_force_bn < 0) { const char* v = getenv("PARAKEET_B200_GEMM_BN"); g_force_bn = v ? atoi(v) : 0; }
   if (g_two_cta < 0) { const char* v = getenv("PARAKEET_B200_GEMM_2CTA"); g_two_cta = v ? atoi(v) : 1; }
-  const bool two_cta = g.epi.mode != EPI_ARGMAX &&
+  const bool two_cta = g.epi.mode != EPI_ARGMAX && g.epi.mode != EPI_PARTIAL_F32 &&
                        (g_force_bn == 512 || (g_force_bn == 0 && g_two_cta != 0 && pick_two_cta(g.M, g.N, g.K, sms)));
   if (two_cta) {
     const int pair_tiles = ((g.M + 255) / 256) * ((g.N + 255) / 256);
@@ -705,6 +716,11 @@ void gemm_tc(const GemmArgs& g, const TensorMap& map_a, const TensorMap& map_w, 
     PKB_GEMM_CASE(EPI_BIAS_F32) PKB_GEMM_CASE(EPI_BIAS_RELU_F32) PKB_GEMM_CASE(EPI_BIAS_RELU_ACT) PKB_GEMM_CASE(EPI_BIAS_ROWMAP_F32)
     PKB_GEMM_CASE(EPI_SILU_ACT) PKB_GEMM_CASE(EPI_RESADD_F32) PKB_GEMM_CASE(EPI_QKV) PKB_GEMM_CASE(EPI_GLU_F32) PKB_GEMM_CASE(EPI_F32)
 #undef PKB_GEMM_CASE
+    case EPI_PARTIAL_F32: {   // split-K: 128-wide tiles, one work unit per (tile, split)
+      const int units = ((g.M + BM - 1) / BM) * ((g.N + 127) / 128) * g.epi.splits;
+      launch_cfg<128, EPI_PARTIAL_F32>(units < sms ? units : sms, ma, mw, g, lo_row_off, st);
+      break;
+    }
     case EPI_ARGMAX: {      // slab geometry (kArgmaxParts) is defined for 256-wide tiles
       const int tiles256 = ((g.M + BM - 1) / BM) * ((g.N + 255) / 256);
       launch_cfg<256, EPI_ARGMAX>(tiles256 < sms ? tiles256 : sms, ma, mw, g, lo_row_off, st);
