@@ -55,6 +55,15 @@ def reduce_timings(vals, world: int, device="cuda"):
     return [float(x) for x in t.tolist()]
 
 
+def load_traffic():
+    """per-launch DRAM bytes of the dominant kernel from the committed `ncu --set full` capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -186,7 +195,8 @@ def main():
     ap.add_argument("--layers", type=int, default=24)
     ap.add_argument("--precision", type=int, default=int(os.environ.get("PKB_BENCH_PRECISION", "0")),
                     help="0 = bf16 operands, 1 = split bf16 hi+lo (fp32-grade)")
-    ap.add_argument("--ref-streams", type=int, default=4)
+    ap.add_argument("--ref-streams", type=int, default=8, help="streams of the bounded CPU sample (cpu_baseline / --impl reference)")
+    ap.add_argument("--ref-chunks", type=int, default=40, help="chunks per stream of the cpu_baseline sample (~15 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--prefill-chunks", type=int, default=88,
@@ -312,6 +322,7 @@ def main():
 
     audio_s = args.streams * args.steps * AUDIO_S_PER_STEP
     peak_tf, peak_hbm, peak_src = load_peaks()
+    traffic = load_traffic()
     achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     line = {
         "metric": METRIC, "value": audio_s / dev_s, "unit": "x real time", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -329,15 +340,18 @@ def main():
                 "d2h_bytes_per_step": n * 97 * 4 * world},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                     "traffic": None, "kernel": "gemm_tc_kernel (tcgen05/TMA/TMEM)", "launches_timed": int(gemm_launches),
+                     "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
+                     "algorithmic_flops_per_launch": gemm_flops / max(gemm_launches, 1),
+                     "kernel": "gemm_tc_kernel / gemm_tc2_kernel (tcgen05 + TMA + TMEM; single-CTA and CTA-pair variants)",
+                     "launches_timed": int(gemm_launches),
                      "peak_source": f"{peak_src} sustained bf16 (MEASURED_PEAKS.json)"},
     }
     if not args.no_latency and world == 1:
         line["latency_1stream"] = latency_one_stream(binding, model, args.precision, clips[0])
     if not args.no_cpu_baseline and world == 1:
-        rtfx, cores, wall, a_s = cpu_path_rtfx(model, args.ref_streams, 16, 1)
+        rtfx, cores, wall, a_s = cpu_path_rtfx(model, args.ref_streams, args.ref_chunks, 1)
         line["cpu_baseline"] = {"value": rtfx, "unit": "x real time", "cores": cores, "kind": "port",
-                                "sample": f"{args.ref_streams} streams x 16 chunks ({a_s:.2f} s audio), {wall:.1f} s of CPU work, "
+                                "sample": f"{args.ref_streams} streams x {args.ref_chunks} chunks ({a_s:.2f} s audio), {wall:.1f} s of CPU work, "
                                           "C restatement of rust/features + PyTorch-CPU restatement of the NeMo modules (not the Rust/ORT binaries)"}
     else:
         line["cpu_baseline"] = None

@@ -5,7 +5,9 @@
 //
 // Persistent kernel, one CTA per SM, work item = (stream, head).  HBM-bound by design: per item it must read the 288 x 128
 // bf16 K and V ring slices (147 KB), everything else is on-chip.
-//   * K and V rings are [slot][288][1024] bf16; the slices are fetched with TMA (96-key x 64-dim boxes, 128-byte swizzle)
+//   * K and V rings are head-major [slot][head][288][128] bf16, so one (stream, head) block of 96 keys is 24 KB of
+//     CONTIGUOUS HBM (a [288][1024] layout would read it as 128-byte pieces at a 2 KB stride, which caps HBM efficiency
+//     near 60 %); the slices are fetched with TMA (96-key x 64-dim boxes, 128-byte swizzle)
 //     by a dedicated producer warp into a 6-stage shared-memory ring (full/empty mbarriers): the producer runs a whole
 //     item ahead of the 8 consumer warps, so the loads of item i+1 overlap the math of item i.
 //   * keys are walked in PHYSICAL ring order (the softmax sum does not care), so a wrapped FIFO needs no second copy and
@@ -57,6 +59,9 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
@@ -99,7 +104,7 @@ struct Item {
 __device__ __forceinline__ Item load_item(const BatchDev& b, const AttnMmaArgs& a, int e) {
   Item it;
   it.Tq = b.Tq[e]; it.qlen = b.qlen[e]; it.len = b.len[e]; it.head = b.head[e]; it.row0 = b.row_off[e];
-  it.ring_row0 = (a.layer * a.n_slots + b.slot[e]) * kRingCap;
+  it.ring_row0 = (a.layer * a.n_slots + b.slot[e]) * (kHeads * kRingCap);      // + head * kRingCap: rings are head-major
   // valid logical positions j in [256-len, 256+qlen) form one circular run of physical slots
   const int v_start = (it.head + kCacheS - it.len) % kRingCap, v_cnt = it.len + it.qlen;
   it.need = 0;
@@ -161,8 +166,8 @@ attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
             const int s = it % kStages;
             mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
             mbar_expect_tx(&full_bar[s], kStageBytes);
-            tma_load_2d(s_ring + s * kStageBytes, map, &full_bar[s], h * kDHead, im.ring_row0 + k * kBlkKeys);
-            tma_load_2d(s_ring + s * kStageBytes + kBoxBytes, map, &full_bar[s], h * kDHead + 64, im.ring_row0 + k * kBlkKeys);
+            tma_load_2d(s_ring + s * kStageBytes, map, &full_bar[s], 0, im.ring_row0 + h * kRingCap + k * kBlkKeys);
+            tma_load_2d(s_ring + s * kStageBytes + kBoxBytes, map, &full_bar[s], 64, im.ring_row0 + h * kRingCap + k * kBlkKeys);
             ++it;
           }
         }
@@ -228,14 +233,15 @@ attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
         }
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-          float c[4] = {0.f, 0.f, 0.f, 0.f};
+          float c[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};      // two chains: half the dependent-HMMA latency
 #pragma unroll
           for (int blk = 0; blk < 4; ++blk) {
             mma_bf16(c, qv[mt][2 * blk], w[blk].x, w[blk].y);
-            mma_bf16(c, qv[mt][2 * blk + 1], w[blk].z, w[blk].w);
+            mma_bf16(c2, qv[mt][2 * blk + 1], w[blk].z, w[blk].w);
           }
-          *reinterpret_cast<float2*>(s_G + (16 * mt + g) * kGPitch + nt * 8 + 2 * t) = make_float2(c[0], c[1]);
-          if (!kHalf) *reinterpret_cast<float2*>(s_G + (16 * mt + g + 8) * kGPitch + nt * 8 + 2 * t) = make_float2(c[2], c[3]);
+          *reinterpret_cast<float2*>(s_G + (16 * mt + g) * kGPitch + nt * 8 + 2 * t) = make_float2(c[0] + c2[0], c[1] + c2[1]);
+          if (!kHalf)
+            *reinterpret_cast<float2*>(s_G + (16 * mt + g + 8) * kGPitch + nt * 8 + 2 * t) = make_float2(c[2] + c2[2], c[3] + c2[3]);
         }
 #pragma unroll
         for (int blk = 0; blk < 4; ++blk) w[blk] = wn[blk];
@@ -253,9 +259,12 @@ attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
       const uint32_t st = smem_u32(s_ring + s * kStageBytes);
 #pragma unroll 1
       for (int nb = cw; nb < kBlkKeys / 8; nb += kConsumerWarps) {
-        float c[MT][4];
+        float c[MT][4], cb[MT][4];
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) { c[mt][0] = c[mt][1] = c[mt][2] = c[mt][3] = 0.f; }
+        for (int mt = 0; mt < MT; ++mt) {
+          c[mt][0] = c[mt][1] = c[mt][2] = c[mt][3] = 0.f;
+          cb[mt][0] = cb[mt][1] = cb[mt][2] = cb[mt][3] = 0.f;
+        }
         const int key_l = 8 * nb + (lane & 7), mi = lane >> 3;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -267,11 +276,13 @@ attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
             mma_bf16(c[mt], qu[mt][ks], r0, r1);
-            mma_bf16(c[mt], qu[mt][ks + 1], r2, r3);
+            mma_bf16(cb[mt], qu[mt][ks + 1], r2, r3);
           }
         }
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+          for (int x = 0; x < 4; ++x) c[mt][x] += cb[mt][x];
 #pragma unroll
           for (int hr = 0; hr < (kHalf ? 1 : 2); ++hr) {
             const int i = 16 * mt + g + 8 * hr;
@@ -321,11 +332,14 @@ attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
     consumer_sync();
 
     // ---- O = P V : consumer warp cw owns head dims [16 cw, 16 cw + 16)
-    float o[MT][2][4];
+    float o[MT][2][4], ob[MT][2][4];      // even / odd k-steps accumulate separately (shorter dependent-HMMA chains)
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt) { o[mt][nt][0] = o[mt][nt][1] = o[mt][nt][2] = o[mt][nt][3] = 0.f; }
+      for (int nt = 0; nt < 2; ++nt) {
+        o[mt][nt][0] = o[mt][nt][1] = o[mt][nt][2] = o[mt][nt][3] = 0.f;
+        ob[mt][nt][0] = ob[mt][nt][1] = ob[mt][nt][2] = ob[mt][nt][3] = 0.f;
+      }
 #pragma unroll 1
     for (int k = 0; k < kNumBlk; ++k) {
       if (!((im.need >> k) & 1u)) continue;
@@ -356,8 +370,8 @@ attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
         ldsm_x4_t(addr, r0, r1, r2, r3);
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-          mma_bf16(o[mt][0], af[mt], r0, r1);
-          mma_bf16(o[mt][1], af[mt], r2, r3);
+          if (kk & 1) { mma_bf16(ob[mt][0], af[mt], r0, r1); mma_bf16(ob[mt][1], af[mt], r2, r3); }
+          else { mma_bf16(o[mt][0], af[mt], r0, r1); mma_bf16(o[mt][1], af[mt], r2, r3); }
         }
       }
       __syncwarp();
@@ -374,7 +388,8 @@ attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
         __nv_bfloat16* dst = a.ctx.ptr + (size_t)(im.row0 + i) * a.ctx.lda + h * kDHead + 16 * cw + 2 * t;
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt)
-          *reinterpret_cast<uint32_t*>(dst + 8 * nt) = pack_bf16x2(o[mt][nt][2 * hr], o[mt][nt][2 * hr + 1]);
+          *reinterpret_cast<uint32_t*>(dst + 8 * nt) =
+              pack_bf16x2(o[mt][nt][2 * hr] + ob[mt][nt][2 * hr], o[mt][nt][2 * hr + 1] + ob[mt][nt][2 * hr + 1]);
       }
     consumer_sync();      // every warp is done with s_P before the next item's G phase overwrites it
   }

@@ -468,8 +468,9 @@ void Engine::alloc_state() {
   PKB_CUDA(cudaMemsetAsync(im.vring, 0, im.ring_layer_elems * L_ * kv_elem, st_));
   im.attn_mma = !split;
   if (im.attn_mma) {
-    make_tensor_map_2d(&im.map_k, im.kring, (uint64_t)L_ * S * kRingCap, kDModel, kDModel, 96);
-    make_tensor_map_2d(&im.map_v, im.vring, (uint64_t)L_ * S * kRingCap, kDModel, kDModel, 96);
+    // head-major rings [layer][slot][head][kRingCap][128]: a 2-D map over rows of 128 elements
+    make_tensor_map_2d(&im.map_k, im.kring, (uint64_t)L_ * S * kHeads * kRingCap, kDHead, kDHead, 96);
+    make_tensor_map_2d(&im.map_v, im.vring, (uint64_t)L_ * S * kHeads * kRingCap, kDHead, kDHead, 96);
   }
   if (opt_.contract_cache) {
     PKB_CUDA(cudaMalloc(&im.acache, im.ring_layer_elems * L_ * kv_elem));

@@ -64,7 +64,8 @@ struct EpiParams {
   int* part_idx = nullptr;
   float* dur_out = nullptr;         // [M][kNDur]
   float blank_penalty = 0.0f;
-  int k_natural = 0;                // 1: the K ring has the V layout [slot][kRingCap][1024] (tensor-core attention); 0: K^T
+  int k_natural = 0;                // 1: K and V rings head-major [slot][head][kRingCap][128] (tensor-core attention);
+                                    // 0: K^T ring [slot][head][128][kRingCap] + V ring [slot][kRingCap][1024] (precise mode)
 };
 
 struct GemmArgs {
@@ -132,10 +133,12 @@ __device__ __forceinline__ void epilogue_pair(const EpiParams& p, int m, int n, 
         const int e = p.row_entry[m];
         const int slot = p.entry_slot[e];
         const int phys = (p.entry_head[e] + kCacheS + p.row_pos[m]) % kRingCap;
-        if (n < 2 * kDModel && p.k_natural) {
-          const size_t i0 = ((size_t)slot * kRingCap + phys) * kDModel + (n - kDModel);
-          if (p.kv_f32) { ((float*)p.kring)[i0] = v0; ((float*)p.kring)[i0 + 1] = v1; }
-          else { ((__nv_bfloat16*)p.kring)[i0] = __float2bfloat16_rn(v0); ((__nv_bfloat16*)p.kring)[i0 + 1] = __float2bfloat16_rn(v1); }
+        if (p.k_natural) {      // bf16 mode: both rings head-major [slot][head][kRingCap][128]
+          const int c = (n - kDModel) & (kDModel - 1), h = c >> 7, d = c & 127;
+          const size_t i0 = (((size_t)slot * kHeads + h) * kRingCap + phys) * kDHead + d;
+          void* ring = n < 2 * kDModel ? p.kring : p.vring;
+          if (p.kv_f32) { ((float*)ring)[i0] = v0; ((float*)ring)[i0 + 1] = v1; }
+          else { ((__nv_bfloat16*)ring)[i0] = __float2bfloat16_rn(v0); ((__nv_bfloat16*)ring)[i0 + 1] = __float2bfloat16_rn(v1); }
         } else if (n < 2 * kDModel) {
           const int c = n - kDModel, h = c >> 7, d = c & 127;
           const size_t i0 = (((size_t)slot * kHeads + h) * kDHead + d) * kRingCap + phys;

@@ -135,7 +135,8 @@ __device__ __forceinline__ int epilogue_row_ctx(const EpiParams& p, int m, int s
     const int e = p.row_entry[m];
     int phys = p.entry_head[e] + kCacheS + p.row_pos[m];      // head in [0, kRingCap), row_pos in [-kCacheS, kMaxTq)
     phys -= phys >= kRingCap ? kRingCap : 0;
-    return p.entry_slot[e] * kRingCap + phys;
+    // bf16 mode (k_natural): K and V rings are head-major [slot][head][kRingCap][128]; precise mode: K^T / V rings per slot
+    return p.entry_slot[e] * (p.k_natural ? kHeads * kRingCap : kRingCap) + phys;
   } else {
     return m;
   }
@@ -180,10 +181,12 @@ __device__ __forceinline__ void epilogue_quad(const EpiParams& p, int m, int ctx
       }
       return;
     }
-    if (nn < 2 * kDModel && p.k_natural) {
-      const size_t i0 = (size_t)ctx * kDModel + (nn - kDModel);
-      if (p.kv_f32) *reinterpret_cast<float4*>((float*)p.kring + i0) = v;
-      else *reinterpret_cast<uint2*>((__nv_bfloat16*)p.kring + i0) = pack4_bf16(v.x, v.y, v.z, v.w);
+    if (p.k_natural) {
+      const int c = (nn - kDModel) & (kDModel - 1), h = c >> 7, d = c & 127;
+      const size_t i0 = ((size_t)ctx + (size_t)h * kRingCap) * kDHead + d;
+      void* ring = nn < 2 * kDModel ? p.kring : p.vring;
+      if (p.kv_f32) *reinterpret_cast<float4*>((float*)ring + i0) = v;
+      else *reinterpret_cast<uint2*>((__nv_bfloat16*)ring + i0) = pack4_bf16(v.x, v.y, v.z, v.w);
     } else if (nn < 2 * kDModel) {
       const int c = nn - kDModel, h = c >> 7, d = c & 127;
       const int slot = ctx / kRingCap, phys = ctx - slot * kRingCap;
