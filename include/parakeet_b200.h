@@ -65,6 +65,11 @@ int32_t pkb_stream_push_features(PkbEngine* engine, int32_t stream, const float*
 int32_t pkb_stream_push_audio(PkbEngine* engine, int32_t stream, const float* pcm, size_t n);
 /* per-feature normalisation applied by the GPU frontend: (x - mean[m]) / std[m]; NULLs switch it off */
 int32_t pkb_stream_set_feature_norm(PkbEngine* engine, int32_t stream, const float* mean128, const float* std128);
+/* Offline mode = the reference's non-streaming `encoder` engine (contracts/parakeet-tdt-0.6b-v3.contract.json:67-96, selected in
+ * cpp/src/parakeet_trt.cpp:1720-1746 when the engine has no cache bindings): every push of 1..256 frames is encoded with full
+ * context, no caches are read or carried over, and all of its encoder frames are decoded (predictor state still carries over).
+ * Only on a freshly opened or reset stream.  The legacy session enters it with PARAKEET_B200_ENCODER=offline. */
+int32_t pkb_stream_set_offline(PkbEngine* engine, int32_t stream, int32_t offline);
 /* Batched push: `count` (<= 8192) samples for each of n streams; row i starts at pcm + i*stride floats.  Host memory
  * (pinned memory is copied without a bounce) or, for the _device variant, device memory (e.g. audio already decoded on the
  * GPU).  One H2D copy + one kernel for the whole batch -- the call a multi-stream server makes once per tick. */
@@ -114,6 +119,10 @@ int32_t pkb_encoder_streaming_step(PkbEngine* engine, int32_t B, int32_t T, cons
                                    const int64_t* cache_last_channel_len, float* encoder_output, int64_t* encoded_lengths,
                                    float* cache_last_channel_out, float* cache_last_time_out,
                                    int64_t* cache_last_channel_len_out);
+/* offline encoder: audio_signal [B,128,T] f32 (T <= 256), length [B] i64 (must equal T) -> encoder_output [B,1024,T_enc],
+ * encoded_lengths [B]; T_enc = three times floor((L-1)/2)+1. */
+int32_t pkb_encoder_offline_step(PkbEngine* engine, int32_t B, int32_t T, const float* audio_signal, const int64_t* length,
+                                 float* encoder_output, int64_t* encoded_lengths);
 /* predictor: y [B,1] i64, h,c [2,B,640] -> g [B,640,1], h_out,c_out [2,B,640] */
 int32_t pkb_predictor_step(PkbEngine* engine, int32_t B, const int64_t* y, const float* h, const float* c, float* g, float* h_out,
                            float* c_out);

@@ -157,6 +157,51 @@ def test_long_stream_ring_wrap(eng, oracle_small, features_ref):
         _check_enc(gcc, cc.numpy()[0], 0, "cache_last_channel after 120 chunks", 2.0)
 
 
+@pytest.mark.parametrize("T", [40, 129, 256], ids=["T40", "T129", "T256"])
+def test_offline_encoder(eng, oracle_small, features_ref, T):
+    """Offline encoder (the reference's non-streaming `encoder` engine, contract.json:67-96): full-context attention over the
+    push, symmetric conv padding, no caches, every token kept -- vs the oracle's offline() on the same frames."""
+    m = oracle_small
+    x = np.stack([_feats(features_ref, 3.0, 50 + i)[:, :T] for i in range(2)])
+    enc, el = m.offline(torch.from_numpy(x), torch.tensor([T, T]))
+    genc, gel = eng.encoder_offline_step(x, np.array([T, T]))
+    assert gel.tolist() == el.tolist() and genc.shape == tuple(enc.shape)
+    _check_enc(genc, enc.numpy(), eng.precision, "offline encoder_output", 1.0 if eng.precision == 1 else 2.0)
+
+
+def test_offline_session_decode(eng, oracle_small, features_ref):
+    """Offline streams next to a streaming stream in the same batched step: 10 s of features pushed as independent <= 256-frame
+    segments (BASELINE config 1 through this ABI), all encoder frames decoded, predictor state carried across pushes."""
+    m = oracle_small
+    f = _feats(features_ref, 10.0, 1234)
+    sid = eng.open()
+    eng.set_offline(sid, True)
+    s2 = eng.open()                       # a streaming neighbour in the same batch
+    st = DecodeState(m)
+    prime(m, st)
+    same = total = 0
+    sched = streaming_schedule(8)
+    for k, lo in enumerate(range(0, f.shape[1], 256)):
+        seg = f[:, lo:lo + 256]
+        eng.push_features(sid, seg)
+        if k < len(sched):
+            eng.push_features(s2, f[:, sched[k][0]:sched[k][1]])
+        eng.step()
+        enc, el = m.offline(torch.from_numpy(seg[None]), torch.tensor([seg.shape[1]]))
+        want = [(t, tok, d) for t, tok, d, _ in tdt_greedy_chunk(m, st, enc, int(el))]
+        total += 1
+        same += int(eng.last_steps(sid) == want)
+        assert eng.cache_len(sid) == 0
+    toks = eng.tokens(sid)
+    eng.close_stream(sid)
+    eng.close_stream(s2)
+    assert total == 4
+    if eng.precision == 1:
+        assert same == total and toks == st.tokens
+    else:
+        assert same >= total - 1
+
+
 def test_predictor_and_joint(eng, oracle_small):
     """One step, like tools/onnxruntime/onnx_predictor_joint_parity.py:202-275 (token 0, zero state, randn enc seed 0) plus
     random states; reference budget: g 1.9e-7, h 1.5e-6, c 4.8e-6, logits 8.5e-4, both argmaxes equal."""

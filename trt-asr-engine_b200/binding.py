@@ -26,7 +26,7 @@ TRT_ASR_SYMBOLS = ["trt_asr_create_session", "trt_asr_destroy_session", "trt_asr
                    "trt_asr_push_features_f32", "trt_asr_poll_event"]
 B200_SYMBOLS = ["pkb_last_error", "pkb_version", "pkb_engine_create", "pkb_engine_destroy", "pkb_engine_num_layers",
                 "pkb_engine_kernel_launches", "pkb_stream_open", "pkb_stream_close", "pkb_stream_reset", "pkb_stream_push_features",
-                "pkb_stream_push_audio", "pkb_stream_set_feature_norm", "pkb_engine_push_audio_batch",
+                "pkb_stream_push_audio", "pkb_stream_set_feature_norm", "pkb_stream_set_offline", "pkb_encoder_offline_step", "pkb_engine_push_audio_batch",
                 "pkb_engine_push_audio_batch_device", "pkb_engine_event_record", "pkb_engine_event_elapsed_ms",
                 "pkb_engine_profile_enable", "pkb_engine_profile_read", "pkb_engine_step", "pkb_stream_has_pending",
                 "pkb_stream_num_tokens", "pkb_stream_tokens", "pkb_stream_last_steps", "pkb_stream_cache_len",
@@ -127,6 +127,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.pkb_stream_set_decoder_state.argtypes = [vp, C.c_int32, fp, fp, fp, C.c_int32, C.c_int32]
     lib.pkb_stream_get_decoder_state.argtypes = [vp, C.c_int32, fp, fp, fp]
     lib.pkb_encoder_streaming_step.argtypes = [vp, C.c_int32, C.c_int32, fp, lp, fp, fp, lp, fp, lp, fp, fp, lp]
+    lib.pkb_stream_set_offline.argtypes = [vp, C.c_int32, C.c_int32]
+    lib.pkb_encoder_offline_step.argtypes = [vp, C.c_int32, C.c_int32, fp, lp, fp, lp]
     lib.pkb_predictor_step.argtypes = [vp, C.c_int32, lp, fp, fp, fp, fp, fp]
     lib.pkb_joint_step.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, fp, fp, fp]
     lib.pkb_logmel.argtypes = [vp, fp, C.c_size_t, fp, C.c_size_t, C.c_int32]
@@ -293,9 +295,9 @@ class Engine:
         return out[:n].tolist()
 
     def last_steps(self, s: int) -> List[Tuple[int, int, int]]:
-        buf = (PkbStep * 64)()
-        n = self._chk(self._lib.pkb_stream_last_steps(self._e, s, buf, 64))
-        return [(buf[i].time_idx, buf[i].token, buf[i].duration) for i in range(min(n, 64))]
+        buf = (PkbStep * 320)()
+        n = self._chk(self._lib.pkb_stream_last_steps(self._e, s, buf, 320))
+        return [(buf[i].time_idx, buf[i].token, buf[i].duration) for i in range(min(n, 320))]
 
     def cache_len(self, s: int) -> int:
         return self._chk(self._lib.pkb_stream_cache_len(self._e, s))
@@ -353,6 +355,22 @@ class Engine:
         self._chk(self._lib.pkb_encoder_streaming_step(self._e, B, T, _fptr(a), _lptr(ln), _fptr(cc), _fptr(ct), _lptr(cl), _fptr(enc),
                                                        _lptr(el), _fptr(cco), _fptr(cto), _lptr(clo)))
         return enc, el, cco, cto, clo
+
+    def set_offline(self, s: int, offline: bool = True):
+        self._chk(self._lib.pkb_stream_set_offline(self._e, s, int(offline)))
+
+    def encoder_offline_step(self, audio_signal, length):
+        """audio_signal [B,128,T] (T <= 256), length [B] -> (encoder_output [B,1024,T_enc], encoded_lengths [B])."""
+        a = np.ascontiguousarray(audio_signal, np.float32)
+        B, _, T = a.shape
+        ln = np.ascontiguousarray(length, np.int64)
+        t_enc = T
+        for _ in range(3):
+            t_enc = (t_enc - 1) // 2 + 1
+        out = np.zeros((B, 1024, t_enc), np.float32)
+        el = np.zeros(B, np.int64)
+        self._chk(self._lib.pkb_encoder_offline_step(self._e, B, T, _fptr(a), _lptr(ln), _fptr(out), _lptr(el)))
+        return out, el
 
     def predictor_step(self, y, h, c):
         y = np.ascontiguousarray(y, np.int64)

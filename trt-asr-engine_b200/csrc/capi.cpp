@@ -76,6 +76,7 @@ struct ParakeetSession {
   std::string last_text, last_err;
   size_t last_partial_tokens = 0;
   std::chrono::steady_clock::time_point last_partial_emit;
+  bool offline = false;      // PARAKEET_B200_ENCODER=offline: the reference's non-streaming encoder engine
   std::string dbg_id;
   uint64_t dbg_utt = 0, dbg_chunk = 0, dbg_feat = 0;
 };
@@ -98,6 +99,9 @@ ParakeetSession* parakeet_create_session(const ParakeetConfig* config) {
     o.blank_penalty = env_float("PARAKEET_BLANK_PENALTY", 0.0f);
     s->eng = new pkb::Engine(o);
     s->sid = s->eng->open_stream();
+    const char* mode = std::getenv("PARAKEET_B200_ENCODER");
+    s->offline = mode && std::string(mode) == "offline";
+    if (s->offline) s->eng->set_stream_offline(s->sid, true);
     s->last_partial_emit = std::chrono::steady_clock::now() - std::chrono::milliseconds(1000);
     return s;
   } catch (const std::exception& e) {
@@ -142,7 +146,7 @@ static void push_one_chunk(ParakeetSession* s, const float* feats, size_t T) {
     }
     s->last_partial_emit = now;
   }
-  if (env_bool("PARAKEET_EMIT_FINAL_EACH_CHUNK", false)) {
+  if (env_bool("PARAKEET_EMIT_FINAL_EACH_CHUNK", s->offline)) {      // default: !enc_streaming (parakeet_trt.cpp:3802)
     std::vector<int> chunk(toks.begin() + (std::ptrdiff_t)before, toks.end());
     EventInternal ev{PARAKEET_EVENT_FINAL_TEXT, s->eng->detokenize(chunk), ""};
     std::lock_guard<std::mutex> lock(s->event_mu);
@@ -329,6 +333,10 @@ int32_t pkb_stream_set_feature_norm(PkbEngine* e, int32_t s, const float* mean12
   PKB_ENTER(e);
   return guarded([&] { e->eng->set_feature_norm(s, mean128, std128); return 0; });
 }
+int32_t pkb_stream_set_offline(PkbEngine* e, int32_t s, int32_t offline) {
+  PKB_ENTER(e);
+  return guarded([&] { e->eng->set_stream_offline(s, offline != 0); return 0; });
+}
 int32_t pkb_engine_push_audio_batch(PkbEngine* e, int32_t n, const int32_t* sids, const float* pcm, int64_t stride, int32_t count) {
   PKB_ENTER(e);
   if (!sids || (!pcm && n * count)) { g_last_error = "null argument"; return -1; }
@@ -417,6 +425,12 @@ int32_t pkb_encoder_streaming_step(PkbEngine* e, int32_t B, int32_t T, const flo
                                    float* ct_out, int64_t* cl_out) {
   PKB_ENTER(e);
   return guarded([&] { e->eng->encoder_streaming_step(B, T, audio_signal, length, cc, ct, cl, enc_out, enc_len, cc_out, ct_out, cl_out); return 0; });
+}
+int32_t pkb_encoder_offline_step(PkbEngine* e, int32_t B, int32_t T, const float* audio_signal, const int64_t* length, float* enc_out,
+                                 int64_t* enc_len) {
+  PKB_ENTER(e);
+  if (!audio_signal || !length || !enc_out || !enc_len) { g_last_error = "null argument"; return -1; }
+  return guarded([&] { e->eng->encoder_offline_step(B, T, audio_signal, length, enc_out, enc_len); return 0; });
 }
 int32_t pkb_predictor_step(PkbEngine* e, int32_t B, const int64_t* y, const float* h, const float* c, float* g, float* h_out, float* c_out) {
   PKB_ENTER(e);

@@ -33,7 +33,7 @@ constexpr int kPredH = 640;
 constexpr int kPredL = 2;
 constexpr int kJointH = 640;
 constexpr int kMaxSymbols = 8;
-constexpr int kMaxTq = 30;       // T<=256 frames per push -> 32 tokens -> 30 after drop
+constexpr int kMaxTq = 32;       // T<=256 frames per push -> 32 tokens (streaming drops 2 of them, offline keeps all)
 constexpr int kPosRows = kCacheS + 2 * kMaxTq;  // relative positions -(kMaxTq-1) .. 256+kMaxTq-1 (padded)
 constexpr int kPosNeg = kMaxTq - 1;             // table row of relative position r is (r + kPosNeg)
 constexpr int kPosRowsPad = 320;                // rows of the natural-layout table (multiple of 8, zero padded)

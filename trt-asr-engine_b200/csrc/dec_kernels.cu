@@ -78,8 +78,8 @@ tdt_select_kernel(DecodeDev d) {
   const int adv = (tok == kBlank && dur == 0) ? 1 : dur;      // blank must advance (:3393-3403)
   int t = d.t_cur[e], ns = d.n_sym[e];
   const int k = d.n_steps[e];
-  if (k < kMaxStepsPerChunk) {
-    int* st = d.steps + ((size_t)e * kMaxStepsPerChunk + k) * 3;
+  if (k < d.max_steps) {
+    int* st = d.steps + ((size_t)e * d.max_steps + k) * 3;
     st[0] = t; st[1] = tok; st[2] = dur;
     d.n_steps[e] = k + 1;
   }

@@ -6,11 +6,13 @@
 
 namespace pkb {
 
-constexpr int kMaxStepsPerChunk = 32;   // >= valid_out_len * max_symbols (3*8 = 24 joint evaluations per chunk)
+constexpr int kMaxStepsPerChunk = 32;   // streaming: >= valid_out_len * max_symbols (3*8 = 24 joint evaluations per chunk)
+constexpr int kMaxStepsOffline = kMaxTq * (kMaxSymbols + 1);   // offline push: up to 32 encoder frames
 
 struct DecodeDev {
   int B = 0;
   int max_symbols = kMaxSymbols;
+  int max_steps = kMaxStepsPerChunk;   // capacity (records per entry) of `steps`
   int punct_suppress = 1;
   float blank_penalty = 0.0f;
   // per entry (this step)
@@ -23,7 +25,7 @@ struct DecodeDev {
   int* emit_tok = nullptr;        // [B] token emitted in this iteration or -1
   int* pred_rowmap = nullptr;     // [B] slot if emitted else -1 (row map of the pred-projection epilogue)
   int* n_steps = nullptr;         // [B]
-  int* steps = nullptr;           // [B][kMaxStepsPerChunk][3] = (time_idx, token, duration)
+  int* steps = nullptr;           // [B][max_steps][3] = (time_idx, token, duration)
   int* n_active = nullptr;        // scalar: entries still active after the last select
   int* m_pred = nullptr;          // scalar: B if any entry emitted in this iteration else 0 (device-side GEMM M)
   // tensors

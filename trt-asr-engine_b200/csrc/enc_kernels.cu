@@ -33,7 +33,8 @@ __global__ void build_rows_kernel(BatchDev b) {
   if (i < b.sumT3) {
     const int e = find_entry(b.off3, b.B, i);
     const int t3 = i - b.off3[e];
-    b.rowmap3[i] = (t3 >= kDropPre && t3 - kDropPre < b.Tq[e]) ? b.row_off[e] + t3 - kDropPre : -1;
+    const int dp = b.drop[e];
+    b.rowmap3[i] = (t3 >= dp && t3 - dp < b.Tq[e]) ? b.row_off[e] + t3 - dp : -1;
   }
 }
 void launch_build_rows(const BatchDev& b, cudaStream_t st) {
@@ -387,7 +388,8 @@ dwconv_kernel(BatchDev b, DwConvArgs a) {
   for (int i = 0; i < kConvK; ++i) w[i] = a.w[ch * kConvK + i];
   const float bias = a.bias[ch];
   // ext = [cache(4) | c(Tq, zero past qlen: pad_mask) | 0 0 0 0]; sliding window of 9
-  const float4 cv = *reinterpret_cast<const float4*>(cache);
+  const bool offline = b.offline[e] != 0;      // offline: zero left context (symmetric 4/4 padding), cache untouched
+  const float4 cv = offline ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(cache);
   float win[kConvK];
   win[0] = cv.x; win[1] = cv.y; win[2] = cv.z; win[3] = cv.w;
 #pragma unroll
@@ -416,7 +418,7 @@ dwconv_kernel(BatchDev b, DwConvArgs a) {
     const int tn = t + 5;                       // next ext index t+1+8 -> c index t+5
     win[kConvK - 1] = (tn < Tq && tn < qlen) ? a.c[(size_t)(row0 + tn) * kDModel + ch] : 0.0f;
   }
-  *reinterpret_cast<float4*>(cache) = make_float4(nc[0], nc[1], nc[2], nc[3]);
+  if (!offline) *reinterpret_cast<float4*>(cache) = make_float4(nc[0], nc[1], nc[2], nc[3]);
 }
 void launch_dwconv(const BatchDev& b, const DwConvArgs& a, cudaStream_t st) {
   if (b.B <= 0) return;
@@ -426,18 +428,18 @@ void launch_dwconv(const BatchDev& b, const DwConvArgs& a, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------------ output
 __global__ void __launch_bounds__(256)
-gather_output_kernel(BatchDev b, const float* __restrict__ x, float* __restrict__ enc_out) {
+gather_output_kernel(BatchDev b, const float* __restrict__ x, float* __restrict__ enc_out, int out_T) {
   pdl_enter();
   const int e = blockIdx.x;
   const int row0 = b.row_off[e], Tq = b.Tq[e];
-  for (int i = threadIdx.x; i < kDModel * kValidOut; i += 256) {
-    const int d = i / kValidOut, t = i % kValidOut;
-    enc_out[(size_t)e * kDModel * kValidOut + i] = t < Tq ? x[(size_t)(row0 + t) * kDModel + d] : 0.0f;
+  for (int i = threadIdx.x; i < kDModel * out_T; i += 256) {
+    const int d = i / out_T, t = i % out_T;
+    enc_out[(size_t)e * kDModel * out_T + i] = t < Tq ? x[(size_t)(row0 + t) * kDModel + d] : 0.0f;
   }
 }
-void launch_gather_output(const BatchDev& b, const float* x, float* enc_out, cudaStream_t st) {
+void launch_gather_output(const BatchDev& b, const float* x, float* enc_out, int out_T, cudaStream_t st) {
   if (b.B <= 0) return;
-  launch_k(gather_output_kernel, dim3(b.B), dim3(256), 0, st, b, x, enc_out);
+  launch_k(gather_output_kernel, dim3(b.B), dim3(256), 0, st, b, x, enc_out, out_T);
   PKB_CUDA(cudaGetLastError());
 }
 

@@ -12,6 +12,7 @@ struct BatchDev {
   int M = 0;          // packed encoder rows = sum Tq
   int sumT2 = 0, sumT3 = 0;
   int max_Tq = 0;
+  int max_tenc = 0;   // most encoder frames any entry emits (3 streaming, Tq offline)
   const int* slot = nullptr;    // [B] state slot of the stream
   const int* T = nullptr;       // [B] input feature frames of this chunk
   const int* f0 = nullptr;      // [B] absolute index of the chunk's first frame in the stream's feature ring
@@ -22,6 +23,8 @@ struct BatchDev {
   const int* qlen = nullptr;    // [B] valid new tokens (length after subsampling - 2, clamped to [0,Tq])
   const int* len = nullptr;     // [B] cache_last_channel_len on entry
   const int* head = nullptr;    // [B] physical ring index of logical cache position 0
+  const int* drop = nullptr;    // [B] pre-encode tokens dropped at the front (2 streaming = drop_extra_pre_encoded, 0 offline)
+  const int* offline = nullptr; // [B] 1: offline (full-context) encode of this push: no caches read or carried over
   const int* off2 = nullptr;    // [B+1] prefix sums of T2
   const int* off3 = nullptr;    // [B+1] prefix sums of T3
   const int* row_off = nullptr; // [B+1] prefix sums of Tq
@@ -100,7 +103,7 @@ struct DwConvArgs {
 void launch_dwconv(const BatchDev& b, const DwConvArgs& a, cudaStream_t st);
 
 // encoder_output [B,1024,valid] <- first `valid_out` rows of each entry (transposed), zero-filled past qlen
-void launch_gather_output(const BatchDev& b, const float* x, float* enc_out /*[B,1024,3]*/, cudaStream_t st);
+void launch_gather_output(const BatchDev& b, const float* x, float* enc_out /*[B,1024,out_T]*/, int out_T, cudaStream_t st);
 
 // ---- state import/export at the contract layouts (cache carry-over across the C ABI) ----
 // acache ring rows (logical 0..255) -> bf16 hi/lo operand rows, for re-projecting K/V after an import

@@ -143,6 +143,7 @@ struct Engine::Stream {
   long long frames_written = 0;          // frames ever written to the feature ring
   std::deque<Entry> pending;             // explicit chunks (legacy ABI granularity)
   bool audio_mode = false;
+  bool offline = false;                  // offline (full-context, cache-free) encoding of every push
   std::vector<float> audio;              // host overflow FIFO: samples that did not fit the device audio buffer yet
   bool needs_prime = false;              // predictor priming is deferred to the next batched pass (one launch set for all)
   int dev_off = 0;                       // first valid sample inside this stream's device audio buffer (always even)
@@ -222,7 +223,7 @@ struct Engine::Impl {
 
 constexpr int kFeatRing = 512;           // frames kept per stream (5.12 s)
 constexpr int kAudioCap = 32768;         // samples per stream resident on the device (2 s)
-constexpr int kNumBatchFields = 11;
+constexpr int kNumBatchFields = 13;
 
 // ================================================================================================
 Engine::Engine(const EngineOptions& opt) : opt_(opt) {
@@ -497,6 +498,7 @@ void Engine::alloc_state() {
   im.Mcap = opt_.max_rows > 0 ? opt_.max_rows : std::max(64, 8 * opt_.max_streams);
   im.Mcap = std::max(im.Mcap, kMaxTq + 2);
   im.T3cap = im.Mcap + kDropPre * im.Bcap;
+  im.Mcap = std::max(im.Mcap, kMaxTq);
   im.T2cap = 2 * im.T3cap + im.Bcap;
   const int rows_dec = std::max(im.Bcap, 64);
   im.a_sub1 = make_act(im.T2cap * 32, kSubCh, split, st_);
@@ -525,7 +527,7 @@ void Engine::alloc_state() {
   im.part_val = dev_alloc<float>((size_t)rows_dec * kArgmaxParts);
   im.part_idx = dev_alloc<int>((size_t)rows_dec * kArgmaxParts);
   im.dur_logits = dev_alloc<float>((size_t)rows_dec * kNDur);
-  im.enc_out = dev_alloc<float>((size_t)im.Bcap * kDModel * kValidOut);
+  im.enc_out = dev_alloc<float>((size_t)im.Bcap * kDModel * kMaxTq);
   im.ppos_tmp = dev_alloc<float>((size_t)kPosRows * kDModel);
   im.scratch_f32_elems = (size_t)L_ * kCacheS * kDModel;     // one stream's contract cache (import / export staging)
   im.scratch_f32 = dev_alloc<float>(im.scratch_f32_elems);
@@ -540,11 +542,11 @@ void Engine::alloc_state() {
   fill_import_rows_kernel<<<1, kCacheS, 0, st_>>>(im.imp_row_entry, im.imp_row_pos, kCacheS);
   im.t_cur = dev_alloc<int>(im.Bcap); im.n_sym = dev_alloc<int>(im.Bcap); im.active = dev_alloc<int>(im.Bcap);
   im.emit_tok = dev_alloc<int>(im.Bcap); im.pred_rowmap = dev_alloc<int>(im.Bcap);
-  im.n_steps = dev_alloc<int>((size_t)im.Bcap * (1 + kMaxStepsPerChunk * 3));
+  im.n_steps = dev_alloc<int>((size_t)im.Bcap * (1 + kMaxStepsOffline * 3));
   im.steps = im.n_steps + im.Bcap;
   im.counters = dev_alloc<int>(2);
   im.force_toks = dev_alloc<int>(im.Bcap);
-  PKB_CUDA(cudaMallocHost(&im.res_host, (size_t)im.Bcap * (1 + kMaxStepsPerChunk * 3) * sizeof(int)));
+  PKB_CUDA(cudaMallocHost(&im.res_host, (size_t)im.Bcap * (1 + kMaxStepsOffline * 3) * sizeof(int)));
   PKB_CUDA(cudaMallocHost(&im.counters_host, 2 * sizeof(int)));
   // audio: per-stream device buffers + one staging area for batched host pushes (8192 samples per stream per push)
   im.audio_buf = dev_alloc<float>((size_t)S * kAudioCap);
@@ -613,13 +615,14 @@ int Engine::open_stream() {
 void Engine::close_stream(int sid) {
   PKB_CHECK(sid >= 0 && sid < (int)streams_.size(), "bad stream id");
   streams_[sid]->open = false;
+  streams_[sid]->offline = false;
 }
 
 void Engine::reset_stream(int sid) {
   PKB_CHECK(sid >= 0 && sid < (int)streams_.size() && streams_[sid]->open, "bad stream id");
   Stream& s = *streams_[sid];
   Impl& im = *im_;
-  s.frames_written = 0; s.pending.clear(); s.audio.clear(); s.audio_mode = false; s.sched_chunk = 0; s.has_norm = false;
+  s.frames_written = 0; s.pending.clear(); s.audio.clear(); s.audio_mode = false;   // (s.offline is a property of the stream: kept) s.sched_chunk = 0; s.has_norm = false;
   s.dev_off = 0; s.dev_fill = 0;
   s.cache_len = 0; s.head = 0; s.chunks = 0; s.tokens.clear(); s.last = ChunkResult();
   const size_t slot = (size_t)s.slot;
@@ -629,6 +632,13 @@ void Engine::reset_stream(int sid) {
   PKB_CUDA(cudaMemsetAsync(im.pred_g + slot * kPredH, 0, kPredH * 4, st_));
   PKB_CUDA(cudaMemsetAsync(im.n_emitted + slot, 0, 4, st_));
   s.needs_prime = true;     // primed (batched with every other freshly reset stream) right before its first decode
+}
+
+void Engine::set_stream_offline(int sid, bool offline) {
+  PKB_CHECK(sid >= 0 && sid < (int)streams_.size() && streams_[sid]->open, "bad stream id");
+  Stream& s = *streams_[sid];
+  PKB_CHECK(s.frames_written == 0 && s.chunks == 0, "set_stream_offline: only on a freshly opened / reset stream");
+  s.offline = offline;
 }
 
 bool Engine::has_pending(int sid) const {
@@ -837,7 +847,7 @@ BatchDev Engine::upload_batch(const std::vector<Entry>& entries) {
   int* h = im.batch_ints_host;
   const int C = im.Bcap;
   int *slot = h, *T = h + C, *f0 = h + 2 * C, *T1 = h + 3 * C, *T2 = h + 4 * C, *T3 = h + 5 * C, *Tq = h + 6 * C, *qlen = h + 7 * C,
-      *len = h + 8 * C, *head = h + 9 * C, *tenc = h + 10 * C;
+      *len = h + 8 * C, *head = h + 9 * C, *tenc = h + 10 * C, *drop = h + 11 * C, *offl = h + 12 * C;
   int* off2 = h + kNumBatchFields * C;
   int* off3 = off2 + (C + 1);
   int* roff = off3 + (C + 1);
@@ -852,12 +862,21 @@ BatchDev Engine::upload_batch(const std::vector<Entry>& entries) {
     T1[i] = sub_len(T[i]);
     T2[i] = sub_len(T1[i]);
     T3[i] = sub_len(T2[i]);
-    Tq[i] = T3[i] - kDropPre;
-    PKB_CHECK(Tq[i] >= kCacheDrop && Tq[i] <= kMaxTq, "chunk must hold 33..256 feature frames (got " + std::to_string(T[i]) + ")");
+    // streaming (forward_for_export): drop_extra_pre_encoded tokens go, cache_drop_size more are recomputed next chunk,
+    // the first valid_out_len rows are emitted.  offline (the reference's `encoder` engine, contract.json:67-96): every
+    // token of the push is kept and emitted, no cache.
+    offl[i] = s.offline ? 1 : 0;
+    drop[i] = s.offline ? 0 : kDropPre;
+    Tq[i] = T3[i] - drop[i];
+    if (s.offline)
+      PKB_CHECK(Tq[i] >= 1 && Tq[i] <= kMaxTq, "offline push must hold 1..256 feature frames (got " + std::to_string(T[i]) + ")");
+    else
+      PKB_CHECK(Tq[i] >= kCacheDrop && Tq[i] <= kMaxTq, "chunk must hold 33..256 feature frames (got " + std::to_string(T[i]) + ")");
     qlen[i] = Tq[i];
-    len[i] = s.cache_len;
+    len[i] = s.offline ? 0 : s.cache_len;
     head[i] = s.head;
-    tenc[i] = std::min(qlen[i], kValidOut);
+    tenc[i] = s.offline ? Tq[i] : std::min(qlen[i], kValidOut);
+    b.max_tenc = std::max(b.max_tenc, tenc[i]);
     off2[i + 1] = off2[i] + T2[i];
     off3[i + 1] = off3[i] + T3[i];
     roff[i + 1] = roff[i] + Tq[i];
@@ -869,7 +888,7 @@ BatchDev Engine::upload_batch(const std::vector<Entry>& entries) {
   PKB_CUDA(cudaMemcpyAsync(im.batch_ints, h, nints * sizeof(int), cudaMemcpyHostToDevice, st_));
   int* d = im.batch_ints;
   b.slot = d; b.T = d + C; b.f0 = d + 2 * C; b.T1 = d + 3 * C; b.T2 = d + 4 * C; b.T3 = d + 5 * C; b.Tq = d + 6 * C;
-  b.qlen = d + 7 * C; b.len = d + 8 * C; b.head = d + 9 * C;
+  b.qlen = d + 7 * C; b.len = d + 8 * C; b.head = d + 9 * C; b.drop = d + 11 * C; b.offline = d + 12 * C;
   b.off2 = d + kNumBatchFields * C; b.off3 = b.off2 + (C + 1); b.row_off = b.off3 + (C + 1);
   b.row_entry = im.row_entry; b.row_pos = im.row_pos; b.rowmap3 = im.rowmap3;
   return b;
@@ -1018,7 +1037,7 @@ void Engine::run_encoder(const BatchDev& b) {
     launch_layernorm(im.x, M, w.n_out_g, w.n_out_b, last ? nullptr : im.layers[l + 1].n_ff1_g, last ? nullptr : im.layers[l + 1].n_ff1_b,
                      1, last ? im.a_xf.out() : im.a_ln.out(), nullptr, st_, &res); ++launches_;
   }
-  launch_gather_output(b, im.x, im.enc_out, st_); ++launches_;
+  launch_gather_output(b, im.x, im.enc_out, b.max_tenc, st_); ++launches_;
 }
 
 void Engine::run_predictor_pass(const DecodeDev& d) {
@@ -1044,9 +1063,10 @@ void Engine::run_decode(const BatchDev& b, const std::vector<Entry>& entries) {
   { EpiParams e; e.mode = EPI_BIAS_F32; e.out_f32 = im.enc_proj; e.ldo = kJointH; e.bias = im.joint_enc_b;
     RUN_GEMM(im.a_xf, im.joint_enc, b.M, nullptr, e); }
   DecodeDev d = make_decode_dev(im, opt_, b.B, b.slot, b.row_off, im.batch_ints + 10 * im.Bcap);
+  d.max_steps = b.max_tenc > kValidOut ? kMaxStepsOffline : kMaxStepsPerChunk;
   d.fused_argmax = (opt_.gemm_backend == 2 || (opt_.gemm_backend == 0 && b.B > 16)) && tc_mask() < 0 ? 1 : 0;
   launch_decode_begin(d, st_); ++launches_;
-  const int max_iters = kValidOut * (kMaxSymbols + 1) + 2;
+  const int max_iters = b.max_tenc * (kMaxSymbols + 1) + 2;
   for (int it = 0; it < max_iters; ++it) {
     launch_decode_iter_reset(d, st_); ++launches_;
     launch_joint_hidden(d, st_); ++launches_;
@@ -1119,14 +1139,16 @@ void Engine::run_batch(const std::vector<Entry>& entries, float* enc_out_host) {
     prime_streams(fresh);
   }
   const BatchDev b = upload_batch(entries);
+  const int max_steps = b.max_tenc > kValidOut ? kMaxStepsOffline : kMaxStepsPerChunk;
   run_encoder(b);
   const bool decode = enc_out_host == nullptr;
   if (decode) {
     run_decode(b, entries);
-    PKB_CUDA(cudaMemcpyAsync(im.res_host, im.n_steps, (size_t)im.Bcap * (1 + kMaxStepsPerChunk * 3) * sizeof(int),
+    // [Bcap] step counts, then [B][max_steps][3] records
+    PKB_CUDA(cudaMemcpyAsync(im.res_host, im.n_steps, ((size_t)im.Bcap + (size_t)b.B * max_steps * 3) * sizeof(int),
                              cudaMemcpyDeviceToHost, st_));
   } else {
-    PKB_CUDA(cudaMemcpyAsync(enc_out_host, im.enc_out, (size_t)b.B * kDModel * kValidOut * sizeof(float), cudaMemcpyDeviceToHost, st_));
+    PKB_CUDA(cudaMemcpyAsync(enc_out_host, im.enc_out, (size_t)b.B * kDModel * b.max_tenc * sizeof(float), cudaMemcpyDeviceToHost, st_));
   }
   PKB_CUDA(cudaStreamSynchronize(st_));
   if (im.profile) profile_collect();
@@ -1139,15 +1161,17 @@ void Engine::run_batch(const std::vector<Entry>& entries, float* enc_out_host) {
     s.last = ChunkResult();
     s.last.encoded_len = h[10 * C + i];
     if (decode) {
-      const int n = std::min(im.res_host[i], kMaxStepsPerChunk);
-      const int* st = im.res_host + C + (size_t)i * kMaxStepsPerChunk * 3;
+      const int n = std::min(im.res_host[i], max_steps);
+      const int* st = im.res_host + C + (size_t)i * max_steps * 3;
       for (int k = 0; k < n; ++k) {
         s.last.steps.push_back(StepRecord{st[3 * k], st[3 * k + 1], st[3 * k + 2]});
         if (st[3 * k + 1] != kBlank) s.tokens.push_back(st[3 * k + 1]);
       }
     }
-    s.cache_len = std::min(s.cache_len + keep, kCacheS);     // clamp(len + cache_keep_size, max=cache_len)
-    s.head = (s.head + keep) % kRingCap;
+    if (!s.offline) {
+      s.cache_len = std::min(s.cache_len + keep, kCacheS);     // clamp(len + cache_keep_size, max=cache_len)
+      s.head = (s.head + keep) % kRingCap;
+    }
     s.last.cache_len_out = s.cache_len;
     s.chunks += 1;
   }
@@ -1188,9 +1212,10 @@ int Engine::step() {
     if (!have) continue;
     const int T3 = sub_len(sub_len(sub_len(e.T)));
     const int T2 = sub_len(sub_len(e.T));
-    if (rows + T3 - kDropPre > im.Mcap || t3 + T3 > im.T3cap || t2 + T2 > im.T2cap) flush();
+    const int Tq = T3 - (s.offline ? 0 : kDropPre);
+    if (rows + Tq > im.Mcap || t3 + T3 > im.T3cap || t2 + T2 > im.T2cap) flush();
     batch.push_back(e);
-    rows += T3 - kDropPre; t3 += T3; t2 += T2;
+    rows += Tq; t3 += T3; t2 += T2;
     if (s.audio_mode) s.sched_chunk += 1; else s.pending.pop_front();
   }
   flush();
@@ -1317,6 +1342,29 @@ void Engine::encoder_streaming_step(int B, int T, const float* audio_signal, con
     encoded_lengths[i] = s.last.encoded_len;
     cache_last_channel_len_out[i] = s.cache_len;
     export_state(sids[i], cache_last_channel_out + i * ch_stride, cache_last_time_out + i * tm_stride);
+    close_stream(sids[i]);
+  }
+}
+
+// Offline encoder at the contract layout (contract.json:67-96): audio_signal [B,128,T], length [B] (== T) ->
+// encoder_output [B,1024,T_enc], encoded_lengths [B];  T <= 256 (the reference engine's profile, contract.json:284-287).
+void Engine::encoder_offline_step(int B, int T, const float* audio_signal, const int64_t* length, float* encoder_output,
+                                  int64_t* encoded_lengths) {
+  PKB_CHECK(B >= 1 && B <= opt_.max_streams, "encoder_offline_step: B exceeds max_streams");
+  std::vector<int> sids;
+  std::vector<Entry> entries;
+  for (int i = 0; i < B; ++i) {
+    PKB_CHECK(length[i] == T, "encoder_offline_step: length must equal T for every stream");
+    const int sid = open_stream();
+    sids.push_back(sid);
+    set_stream_offline(sid, true);
+    queue_features(sid, audio_signal + (size_t)i * kNMels * T, T);
+    entries.push_back(streams_[sid]->pending.front());
+    streams_[sid]->pending.pop_front();
+  }
+  run_batch(entries, encoder_output);
+  for (int i = 0; i < B; ++i) {
+    encoded_lengths[i] = streams_[sids[i]]->last.encoded_len;
     close_stream(sids[i]);
   }
 }

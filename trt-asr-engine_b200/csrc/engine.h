@@ -54,6 +54,9 @@ class Engine {
   // (tools/verify_nemo/streaming_encoder_reference.py:522-550).
   void queue_audio(int sid, const float* pcm, size_t n);
   void set_feature_norm(int sid, const float* mean128, const float* std128);   // nullptrs: none
+  // offline mode (the reference's non-streaming `encoder` engine): every push of <= 256 frames is encoded with full context and no
+  // caches, all of its encoder frames are decoded; only valid on a fresh stream
+  void set_stream_offline(int sid, bool offline);
   // batched push of `count` samples for n streams in one call; source rows `stride` floats apart, in host (pinned or
   // pageable) or device memory; lands in per-stream device audio buffers with one copy + one kernel
   void push_audio_batch(int n, const int* sids, const float* src, long long stride, int count, bool src_on_device,
@@ -80,6 +83,8 @@ class Engine {
                               const float* cache_last_time, const int64_t* cache_last_channel_len, float* encoder_output,
                               int64_t* encoded_lengths, float* cache_last_channel_out, float* cache_last_time_out,
                               int64_t* cache_last_channel_len_out);
+  void encoder_offline_step(int B, int T, const float* audio_signal, const int64_t* length, float* encoder_output /*[B,1024,T_enc]*/,
+                            int64_t* encoded_lengths);
   void predictor_step(int B, const int64_t* y, const float* h, const float* c, float* g, float* h_out, float* c_out);
   void joint_step(int B, int T, int U, const float* enc, const float* pred, float* out);
   // GPU frontend on host buffers: pcm[n] -> frames-major [T,128]; per_feature_norm applies utterance mean/std
