@@ -687,7 +687,7 @@ void gemm_tc(const GemmArgs& g, const TensorMap& map_a, const TensorMap& map_w, 
   const int sms = sm_count();
   if (g_force_bn < 0) { const char* v = getenv("PARAKEET_B200_GEMM_BN"); g_force_bn = v ? atoi(v) : 0; }
   if (g_two_cta < 0) { const char* v = getenv("PARAKEET_B200_GEMM_2CTA"); g_two_cta = v ? atoi(v) : 1; }
-  const bool two_cta = g.epi.mode != EPI_ARGMAX && g.epi.mode != EPI_PARTIAL_F32 &&
+  const bool two_cta = g.epi.mode != EPI_ARGMAX && !(g.epi.mode == EPI_PARTIAL_F32 && g.epi.splits > 1) &&
                        (g_force_bn == 512 || (g_force_bn == 0 && g_two_cta != 0 && pick_two_cta(g.M, g.N, g.K, sms)));
   if (two_cta) {
     const int pair_tiles = ((g.M + 255) / 256) * ((g.N + 255) / 256);
@@ -699,6 +699,7 @@ void gemm_tc(const GemmArgs& g, const TensorMap& map_a, const TensorMap& map_w, 
 #define PKB_GEMM_CASE2(MODE) case MODE: launch_cfg2<MODE>(pairs, ma2, mw2, g, lo_row_off2, st); break;
       PKB_GEMM_CASE2(EPI_BIAS_F32) PKB_GEMM_CASE2(EPI_BIAS_RELU_F32) PKB_GEMM_CASE2(EPI_BIAS_RELU_ACT) PKB_GEMM_CASE2(EPI_BIAS_ROWMAP_F32)
       PKB_GEMM_CASE2(EPI_SILU_ACT) PKB_GEMM_CASE2(EPI_RESADD_F32) PKB_GEMM_CASE2(EPI_QKV) PKB_GEMM_CASE2(EPI_GLU_F32) PKB_GEMM_CASE2(EPI_F32)
+      PKB_GEMM_CASE2(EPI_PARTIAL_F32)
 #undef PKB_GEMM_CASE2
       default: PKB_CHECK(false, "gemm_tc: unknown epilogue mode");
     }

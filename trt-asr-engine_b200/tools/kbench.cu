@@ -18,27 +18,29 @@ int main(int argc, char** argv) {
   const int iters = argc > 5 ? atoi(argv[5]) : 50;
   const char* epi = argc > 6 ? argv[6] : "f32";
   const int with_ln = argc > 7 ? atoi(argv[7]) : 0;
+  const int rot = argc > 8 ? atoi(argv[8]) : 1;      // number of distinct weight copies rotated through (rot * N * K * 2 B > L2: cold weights)
   cudaStream_t st;
   PKB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   const size_t rows_a = ((size_t)M + 127) / 128 * 128, rows_w = ((size_t)N + 127) / 128 * 128;
   __nv_bfloat16 *A, *W, *act;
   PKB_CUDA(cudaMalloc(&A, rows_a * K * 2));
-  PKB_CUDA(cudaMalloc(&W, rows_w * K * 2));
+  PKB_CUDA(cudaMalloc(&W, (size_t)rot * rows_w * K * 2));
   PKB_CUDA(cudaMalloc(&act, rows_a * (size_t)N * 2));
   std::vector<uint16_t> h(rows_a * K);
   for (size_t i = 0; i < h.size(); ++i) h[i] = 0x3c00 + (uint16_t)(i * 2654435761u >> 24);   // small positive bf16 values
   PKB_CUDA(cudaMemcpy(A, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
   h.assign(rows_w * K, 0);
   for (size_t i = 0; i < h.size(); ++i) h[i] = 0x3800 + (uint16_t)(i * 40503u >> 8 & 0xff);
-  PKB_CUDA(cudaMemcpy(W, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+  for (int r = 0; r < rot; ++r) PKB_CUDA(cudaMemcpy(W + (size_t)r * rows_w * K, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
   float* out = dalloc_f((size_t)M * N);
   float* x = dalloc_f((size_t)M * 1024);
   float* g1 = dalloc_f(1024);
   __nv_bfloat16* lnA;
   PKB_CUDA(cudaMalloc(&lnA, rows_a * 1024 * 2));
-  TensorMap ma, mw;
+  TensorMap ma;
+  std::vector<TensorMap> mws(rot);
   make_tensor_map_2d(&ma, A, rows_a, K, K, 128);
-  make_tensor_map_2d(&mw, W, rows_w, K, K, 128);
+  for (int r = 0; r < rot; ++r) make_tensor_map_2d(&mws[r], W + (size_t)r * rows_w * K, rows_w, K, K, 128);
   GemmArgs g;
   g.A = A; g.lda = K; g.W = W; g.M = M; g.N = N; g.K = K;
   if (!strcmp(epi, "resadd")) { g.epi.mode = EPI_RESADD_F32; g.epi.out_f32 = out; g.epi.ldo = N; g.epi.scale = 0.5f; }
@@ -50,11 +52,12 @@ int main(int argc, char** argv) {
   PKB_CUDA(cudaEventCreate(&e0));
   PKB_CUDA(cudaEventCreate(&e1));
   for (int rep = 0; rep < 3; ++rep) {
-    for (int i = 0; i < 5; ++i) gemm_tc(g, ma, mw, st);
+    for (int i = 0; i < 5; ++i) gemm_tc(g, ma, mws[0], st);
     PKB_CUDA(cudaStreamSynchronize(st));
     PKB_CUDA(cudaEventRecord(e0, st));
     for (int i = 0; i < iters; ++i) {
-      gemm_tc(g, ma, mw, st);
+      g.W = W + (size_t)(i % rot) * rows_w * K;
+      gemm_tc(g, ma, mws[i % rot], st);
       if (with_ln) launch_layernorm(x, M, g1, g1, nullptr, nullptr, 0, ActOut{lnA, 1024, 0}, nullptr, st);
     }
     PKB_CUDA(cudaEventRecord(e1, st));
@@ -62,7 +65,7 @@ int main(int argc, char** argv) {
     float ms = 0;
     PKB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     const double us = 1e3 * ms / iters;
-    printf("gemm M=%d N=%d K=%d epi=%s ln=%d: %.2f us/iter  %.1f TFLOP/s\n", M, N, K, epi, with_ln, us, 2.0 * M * N * K / us * 1e-6);
+    printf("gemm M=%d N=%d K=%d epi=%s ln=%d rot=%d: %.2f us/iter  %.1f TFLOP/s\n", M, N, K, epi, with_ln, rot, us, 2.0 * M * N * K / us * 1e-6);
   }
   return 0;
 }
