@@ -289,6 +289,23 @@ def test_decode_many_streams_fused_argmax(model_small, oracle_small, features_re
         assert same >= 0.9 * total, f"{same}/{total} chunks identical"
 
 
+def test_engine_destroy_releases_memory(model_small):
+    """create / destroy cycles (what parakeet_create_session / parakeet_destroy_session do per session) must not leak device memory."""
+    def cycle():
+        e = binding.Engine(model_small, max_streams=8, precision=0)
+        s = e.open()
+        e.close_stream(s)
+        e.close()
+    cycle()
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    for _ in range(3):
+        cycle()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 64 << 20, f"leaked {(free0 - free1) >> 20} MiB over 3 engine lifetimes"
+
+
 def test_legacy_session_abi(model_small, oracle_small, features_ref):
     """The drop-in path: ParakeetSessionSafe (mirror of rust/parakeet_trt) -- push, poll, reset, error conventions."""
     m = oracle_small

@@ -82,16 +82,18 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-constexpr int kConsumerWarps = 8;
-constexpr int kAttnThreads = 32 * (1 + kConsumerWarps);       // warp 0: TMA producer
-constexpr int kConsumerThreads = 32 * kConsumerWarps;
+// Launch shape: CW consumer warps (+1 producer warp) per CTA, kStages ring stages, kCtasPerSm co-resident CTAs.
+// PARAKEET_B200_ATTN_CFG selects among the compiled shapes for R = 8 (A/B measurements; default 0).
 
-template <int R>
+template <int R, int CFG>
 struct Smem {
-  // R = 8 (the steady-state chunk): 3 stages, two CTAs per SM (16 consumer warps hide each other's latencies);
-  // the larger variants keep one CTA per SM
-  static constexpr int kStages = R == 8 ? 3 : R == 16 ? 5 : 4;
-  static constexpr int kCtasPerSm = R == 8 ? 2 : 1;
+  // R = 8 (the steady-state chunk), CFG 0 (default): 4 consumer warps, 2 stages, THREE CTAs per SM -- the consumers of one item
+  // run a chain of short dependent phases, so throughput comes from independent items in flight (measured 245 vs 316 us per
+  // layer at 1024 streams against CFG 1: 8 consumer warps, 3 stages, two CTAs per SM).  Larger variants: one CTA per SM.
+  static constexpr int kCW = (R == 8 && CFG == 0) ? 4 : 8;
+  static constexpr int kStages = R == 8 ? (CFG == 0 ? 2 : 3) : R == 16 ? 5 : 4;
+  static constexpr int kCtasPerSm = R == 8 ? (CFG == 0 ? 3 : 2) : 1;
+  static constexpr int kThreads = 32 * (1 + kCW);
   static constexpr int kS = R * kSPitch * 4;
   static constexpr int kG = R * kGPitch * 4;             // later reused for the bf16 probabilities (R_pad x 592 B <= kG)
   static constexpr size_t kBytes = 1024 + (size_t)kStages * kStageBytes + kS + kG + 128;
@@ -118,24 +120,28 @@ __device__ __forceinline__ Item load_item(const BatchDev& b, const AttnMmaArgs& 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
+template <int THREADS>
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
 
 // Persistent: one CTA per SM walks (stream, head) items; the producer warp streams the K then V blocks of successive items
 // through the ring without waiting for the math, so HBM stays busy while the consumers are in their on-chip phases.
 // R = 8 (rows 8..15 of every m16 tile are identically zero and never loaded / stored), 16 or 32.
-template <int R>
-__global__ void __launch_bounds__(kAttnThreads, Smem<R>::kCtasPerSm)
+template <int R, int CFG>
+__global__ void __launch_bounds__(Smem<R, CFG>::kThreads, Smem<R, CFG>::kCtasPerSm)
 attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v, BatchDev b, AttnMmaArgs a) {
   constexpr int MT = R <= 16 ? 1 : 2;
   constexpr bool kHalf = R == 8;
-  constexpr int kStages = Smem<R>::kStages;
+  constexpr int kStages = Smem<R, CFG>::kStages;
+  constexpr int kConsumerWarps = Smem<R, CFG>::kCW;
+  constexpr int kConsumerThreads = 32 * kConsumerWarps;
+  constexpr int NTW = 16 / kConsumerWarps;        // 8-wide head-dim tiles per consumer warp in the PV phase (2 or 4)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* s_ring = base;
   float* s_S = reinterpret_cast<float*>(base + kStages * kStageBytes);
   float* s_G = s_S + R * kSPitch;
   uint8_t* s_P = reinterpret_cast<uint8_t*>(s_G);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_G) + Smem<R>::kG);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_G) + Smem<R, CFG>::kG);
   uint64_t* empty_bar = full_bar + kStages;
 
   const int n_items = b.B * kHeads;
@@ -247,7 +253,7 @@ attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
         for (int blk = 0; blk < 4; ++blk) w[blk] = wn[blk];
       }
     }
-    consumer_sync();      // G complete
+    consumer_sync<kConsumerThreads>();      // G complete
 
     // ---- S phase: scores for every needed key block, combined with the skewed position term, masked, scaled
 #pragma unroll 1
@@ -303,7 +309,7 @@ attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);      // this warp is done with the K block
     }
-    consumer_sync();      // scores complete; nobody reads s_G any more
+    consumer_sync<kConsumerThreads>();      // scores complete; nobody reads s_G any more
 
     // ---- softmax (fp32) -> bf16 probabilities in the A-operand layout [rows][296] (rows >= Tq and skipped blocks are zero)
     constexpr int RP = kHalf ? 8 : 16 * MT;
@@ -329,14 +335,14 @@ attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
 #pragma unroll
       for (int x = 0; x < kRingCap / 32; ++x) prow[lane + 32 * x] = __float2bfloat16_rn(v[x] * inv);
     }
-    consumer_sync();
+    consumer_sync<kConsumerThreads>();
 
     // ---- O = P V : consumer warp cw owns head dims [16 cw, 16 cw + 16)
-    float o[MT][2][4], ob[MT][2][4];      // even / odd k-steps accumulate separately (shorter dependent-HMMA chains)
+    float o[MT][NTW][4], ob[MT][NTW][4];      // even / odd k-steps accumulate separately (shorter dependent-HMMA chains)
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
+      for (int nt = 0; nt < NTW; ++nt) {
         o[mt][nt][0] = o[mt][nt][1] = o[mt][nt][2] = o[mt][nt][3] = 0.f;
         ob[mt][nt][0] = ob[mt][nt][1] = ob[mt][nt][2] = ob[mt][nt][3] = 0.f;
       }
@@ -364,14 +370,17 @@ attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
         }
         const int mi = lane >> 3, ri = lane & 7;
         const int key_l = 16 * kk + (mi & 1) * 8 + ri;
-        const int chunk_g = 2 * cw + (mi >> 1);                  // 16-byte chunk over the 128 head dims
-        const uint32_t addr = st + (chunk_g >> 3) * kBoxBytes + key_l * 128 + (((chunk_g & 7) ^ (key_l & 7)) << 4);
-        uint32_t r0, r1, r2, r3;
-        ldsm_x4_t(addr, r0, r1, r2, r3);
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          if (kk & 1) { mma_bf16(ob[mt][0], af[mt], r0, r1); mma_bf16(ob[mt][1], af[mt], r2, r3); }
-          else { mma_bf16(o[mt][0], af[mt], r0, r1); mma_bf16(o[mt][1], af[mt], r2, r3); }
+        for (int np = 0; np < NTW / 2; ++np) {
+          const int chunk_g = NTW * cw + 2 * np + (mi >> 1);     // 16-byte chunk over the 128 head dims
+          const uint32_t addr = st + (chunk_g >> 3) * kBoxBytes + key_l * 128 + (((chunk_g & 7) ^ (key_l & 7)) << 4);
+          uint32_t r0, r1, r2, r3;
+          ldsm_x4_t(addr, r0, r1, r2, r3);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            if (kk & 1) { mma_bf16(ob[mt][2 * np], af[mt], r0, r1); mma_bf16(ob[mt][2 * np + 1], af[mt], r2, r3); }
+            else { mma_bf16(o[mt][2 * np], af[mt], r0, r1); mma_bf16(o[mt][2 * np + 1], af[mt], r2, r3); }
+          }
         }
       }
       __syncwarp();
@@ -385,26 +394,26 @@ attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
       for (int hr = 0; hr < (kHalf ? 1 : 2); ++hr) {
         const int i = 16 * mt + g + 8 * hr;
         if (i >= Tq) continue;
-        __nv_bfloat16* dst = a.ctx.ptr + (size_t)(im.row0 + i) * a.ctx.lda + h * kDHead + 16 * cw + 2 * t;
+        __nv_bfloat16* dst = a.ctx.ptr + (size_t)(im.row0 + i) * a.ctx.lda + h * kDHead + 8 * NTW * cw + 2 * t;
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
+        for (int nt = 0; nt < NTW; ++nt)
           *reinterpret_cast<uint32_t*>(dst + 8 * nt) =
               pack_bf16x2(o[mt][nt][2 * hr] + ob[mt][nt][2 * hr], o[mt][nt][2 * hr + 1] + ob[mt][nt][2 * hr + 1]);
       }
-    consumer_sync();      // every warp is done with s_P before the next item's G phase overwrites it
+    consumer_sync<kConsumerThreads>();      // every warp is done with s_P before the next item's G phase overwrites it
   }
 }
 
-template <int R>
+template <int R, int CFG>
 void launch_r(const BatchDev& b, const AttnMmaArgs& a, int sms, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    PKB_CUDA(cudaFuncSetAttribute(attention_mma_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<R>::kBytes));
+    PKB_CUDA(cudaFuncSetAttribute(attention_mma_kernel<R, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<R, CFG>::kBytes));
     attr = true;
   }
   const int items = b.B * kHeads;
-  const int ctas = sms * Smem<R>::kCtasPerSm;
-  launch_k(attention_mma_kernel<R>, dim3(items < ctas ? items : ctas), dim3(kAttnThreads), Smem<R>::kBytes, st,
+  const int ctas = sms * Smem<R, CFG>::kCtasPerSm;
+  launch_k(attention_mma_kernel<R, CFG>, dim3(items < ctas ? items : ctas), dim3(Smem<R, CFG>::kThreads), Smem<R, CFG>::kBytes, st,
            *reinterpret_cast<const CUtensorMap*>(a.map_k), *reinterpret_cast<const CUtensorMap*>(a.map_v), b, a);
 }
 
@@ -419,9 +428,11 @@ void launch_attention_mma(const BatchDev& b, const AttnMmaArgs& a, cudaStream_t 
     PKB_CUDA(cudaGetDevice(&dev));
     PKB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  if (b.max_Tq <= 8) launch_r<8>(b, a, sms, st);
-  else if (b.max_Tq <= 16) launch_r<16>(b, a, sms, st);
-  else launch_r<32>(b, a, sms, st);
+  static int cfg = -1;
+  if (cfg < 0) { const char* v = getenv("PARAKEET_B200_ATTN_CFG"); cfg = v ? atoi(v) : 0; }
+  if (b.max_Tq <= 8) { if (cfg == 1) launch_r<8, 1>(b, a, sms, st); else launch_r<8, 0>(b, a, sms, st); }
+  else if (b.max_Tq <= 16) launch_r<16, 0>(b, a, sms, st);
+  else launch_r<32, 0>(b, a, sms, st);
 }
 
 }  // namespace pkb

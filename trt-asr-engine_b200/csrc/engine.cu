@@ -12,12 +12,30 @@ namespace pkb {
 
 namespace {
 
-template <typename T>
-T* dev_alloc(size_t n) {
-  T* p = nullptr;
-  if (n == 0) n = 1;
-  PKB_CUDA(cudaMalloc(&p, n * sizeof(T)));
+// Allocation registry: everything allocated while an Engine is being constructed belongs to that Engine and is released by
+// its destructor (a process may create and destroy many sessions: parakeet_create_session / parakeet_destroy_session).
+// Transient buffers of individual calls are allocated outside a scope and freed by their owners.
+thread_local std::vector<void*>* g_dev_scope = nullptr;
+thread_local std::vector<void*>* g_host_scope = nullptr;
+void* dev_alloc_bytes(size_t bytes) {
+  void* p = nullptr;
+  PKB_CUDA(cudaMalloc(&p, bytes ? bytes : 1));
+  if (g_dev_scope) g_dev_scope->push_back(p);
   return p;
+}
+template <typename T>
+T* dev_alloc(size_t n) { return static_cast<T*>(dev_alloc_bytes(n * sizeof(T))); }
+void dev_free(void* p) {      // free a buffer that may have been registered in the current scope
+  if (g_dev_scope) {
+    auto it = std::find(g_dev_scope->begin(), g_dev_scope->end(), p);
+    if (it != g_dev_scope->end()) g_dev_scope->erase(it);
+  }
+  cudaFree(p);
+}
+template <typename T>
+void host_alloc(T** p, size_t bytes) {
+  PKB_CUDA(cudaMallocHost(p, bytes));
+  if (g_host_scope) g_host_scope->push_back(*p);
 }
 template <typename T>
 T* dev_upload(const std::vector<T>& v) {
@@ -158,6 +176,7 @@ struct Engine::Stream {
 };
 
 struct Engine::Impl {
+  std::vector<void*> dev_allocs, host_allocs;      // owned device / pinned-host buffers (see g_dev_scope)
   Frontend frontend;
   // weights
   SubsampleWeights sub{};
@@ -236,6 +255,10 @@ Engine::Engine(const EngineOptions& opt) : opt_(opt) {
                                   std::to_string(prop.major) + "." + std::to_string(prop.minor));
   PKB_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
   im_.reset(new Impl());
+  struct ScopeGuard {
+    ScopeGuard(std::vector<void*>* d, std::vector<void*>* h) { g_dev_scope = d; g_host_scope = h; }
+    ~ScopeGuard() { g_dev_scope = nullptr; g_host_scope = nullptr; }
+  } scope(&im_->dev_allocs, &im_->host_allocs);
   // vocab
   {
     std::ifstream f(opt_.model_dir + "/vocab.txt");
@@ -265,12 +288,14 @@ Engine::Engine(const EngineOptions& opt) : opt_(opt) {
 }
 
 Engine::~Engine() {
-  // process teardown frees device memory; explicit frees are skipped on purpose (one engine per process lifetime
-  // in every caller), but the stream is destroyed so that a leaked engine does not keep work queued.
-  if (st_) {
-    cudaStreamSynchronize(st_);
-    cudaStreamDestroy(st_);
+  if (st_) cudaStreamSynchronize(st_);
+  if (im_) {
+    for (auto& e : im_->user_events) cudaEventDestroy(e);
+    for (auto& pr : im_->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (void* p : im_->dev_allocs) cudaFree(p);
+    for (void* p : im_->host_allocs) cudaFreeHost(p);
   }
+  if (st_) cudaStreamDestroy(st_);
 }
 
 void Engine::synchronize() { PKB_CUDA(cudaStreamSynchronize(st_)); }
@@ -463,8 +488,8 @@ void Engine::alloc_state() {
   const size_t S = (size_t)opt_.max_streams;
   const size_t kv_elem = split ? 4 : 2;
   im.ring_layer_elems = S * kRingCap * kDModel;
-  PKB_CUDA(cudaMalloc(&im.kring, im.ring_layer_elems * L_ * kv_elem));
-  PKB_CUDA(cudaMalloc(&im.vring, im.ring_layer_elems * L_ * kv_elem));
+  im.kring = dev_alloc_bytes(im.ring_layer_elems * L_ * kv_elem);
+  im.vring = dev_alloc_bytes(im.ring_layer_elems * L_ * kv_elem);
   PKB_CUDA(cudaMemsetAsync(im.kring, 0, im.ring_layer_elems * L_ * kv_elem, st_));
   PKB_CUDA(cudaMemsetAsync(im.vring, 0, im.ring_layer_elems * L_ * kv_elem, st_));
   im.attn_mma = !split;
@@ -474,7 +499,7 @@ void Engine::alloc_state() {
     make_tensor_map_2d(&im.map_v, im.vring, (uint64_t)L_ * S * kHeads * kRingCap, kDHead, kDHead, 96);
   }
   if (opt_.contract_cache) {
-    PKB_CUDA(cudaMalloc(&im.acache, im.ring_layer_elems * L_ * kv_elem));
+    im.acache = dev_alloc_bytes(im.ring_layer_elems * L_ * kv_elem);
     PKB_CUDA(cudaMemsetAsync(im.acache, 0, im.ring_layer_elems * L_ * kv_elem, st_));
   }
   im.cache_tm = dev_alloc<float>(S * L_ * kDModel * kTimeCtx);
@@ -534,7 +559,7 @@ void Engine::alloc_state() {
   im.scratch_f32 = dev_alloc<float>(im.scratch_f32_elems);
   const size_t nints = (size_t)kNumBatchFields * im.Bcap + 3 * (im.Bcap + 1);
   im.batch_ints = dev_alloc<int>(nints);
-  PKB_CUDA(cudaMallocHost(&im.batch_ints_host, nints * sizeof(int)));
+  host_alloc(&im.batch_ints_host, nints * sizeof(int));
   im.row_entry = dev_alloc<int>(im.Mcap);
   im.row_pos = dev_alloc<int>(im.Mcap);
   im.rowmap3 = dev_alloc<int>(im.T3cap);
@@ -547,22 +572,22 @@ void Engine::alloc_state() {
   im.steps = im.n_steps + im.Bcap;
   im.counters = dev_alloc<int>(2);
   im.force_toks = dev_alloc<int>(im.Bcap);
-  PKB_CUDA(cudaMallocHost(&im.res_host, (size_t)im.Bcap * (1 + kMaxStepsOffline * 3) * sizeof(int)));
-  PKB_CUDA(cudaMallocHost(&im.counters_host, 2 * sizeof(int)));
+  host_alloc(&im.res_host, (size_t)im.Bcap * (1 + kMaxStepsOffline * 3) * sizeof(int));
+  host_alloc(&im.counters_host, 2 * sizeof(int));
   // audio: per-stream device buffers + one staging area for batched host pushes (8192 samples per stream per push)
   im.audio_buf = dev_alloc<float>((size_t)S * kAudioCap);
   im.audio_tmp = dev_alloc<float>((size_t)S * kAudioCap);
   im.audio_stage_cap = (size_t)im.Bcap * 8192;
   im.audio_stage = dev_alloc<float>(im.audio_stage_cap);
-  PKB_CUDA(cudaMallocHost(&im.audio_stage_host, im.audio_stage_cap * sizeof(float)));
+  host_alloc(&im.audio_stage_host, im.audio_stage_cap * sizeof(float));
   im.push_meta = dev_alloc<int>((size_t)3 * im.Bcap);
-  PKB_CUDA(cudaMallocHost(&im.push_meta_host, (size_t)3 * im.Bcap * sizeof(int)));
+  host_alloc(&im.push_meta_host, (size_t)3 * im.Bcap * sizeof(int));
   im.segs_dev = dev_alloc<FrontSegment>(im.Bcap);
-  PKB_CUDA(cudaMallocHost(&im.segs_host, (size_t)im.Bcap * sizeof(FrontSegment)));
+  host_alloc(&im.segs_host, (size_t)im.Bcap * sizeof(FrontSegment));
   im.fprefix_dev = dev_alloc<int>(im.Bcap + 1);
-  PKB_CUDA(cudaMallocHost(&im.fprefix_host, (size_t)(im.Bcap + 1) * sizeof(int)));
+  host_alloc(&im.fprefix_host, (size_t)(im.Bcap + 1) * sizeof(int));
   im.feat_stage_dev = dev_alloc<float>((size_t)kNMels * 256);
-  PKB_CUDA(cudaMallocHost(&im.feat_stage_host, (size_t)kNMels * 256 * sizeof(float)));
+  host_alloc(&im.feat_stage_host, (size_t)kNMels * 256 * sizeof(float));
 
   // ---- projected relative-position table per layer:  P_l[r] = linear_pos_l(pe[r]),  r in [-kPosNeg, kPosRows-kPosNeg)
   // pe[r][2i] = sin(r * div_i), pe[r][2i+1] = cos(r * div_i), div_i = exp(-(ln 1e4) * 2i / d_model)   (NeMo RelPositionalEncoding)
@@ -592,13 +617,13 @@ void Engine::alloc_state() {
         PKB_CUDA(cudaMemsetAsync(im.layers[l].ppos_n, 0, (size_t)kHeads * kPosRowsPad * kDHead * 2, st_));
         ppos_natural_kernel<<<kPosRows, 256, 0, st_>>>(im.ppos_tmp, im.layers[l].ppos_n);
       } else {
-        PKB_CUDA(cudaMalloc(&im.layers[l].ppos_t, (size_t)kPosRows * kDModel * kv_elem));
+        im.layers[l].ppos_t = dev_alloc_bytes((size_t)kPosRows * kDModel * kv_elem);
         ppos_transpose_kernel<<<kPosRows, 256, 0, st_>>>(im.ppos_tmp, im.layers[l].ppos_t, 1);
       }
       PKB_CUDA(cudaStreamSynchronize(st_));
-      cudaFree(wp.w);
+      dev_free(wp.w);
     }
-    cudaFree(pe_dev);
+    dev_free(pe_dev);
   }
 }
 
