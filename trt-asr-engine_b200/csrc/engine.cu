@@ -548,7 +548,7 @@ void Engine::alloc_state() {
   im.logits = dev_alloc<float>((size_t)rows_dec * kJointOut);
   im.gates = dev_alloc<float>((size_t)rows_dec * 4 * kPredH);
   im.part_rows_split = std::min(im.Mcap, 2048);      // split-K (up to 4 ways) is only used for small batched passes
-  im.part_rows = std::max(im.Mcap, 4 * im.part_rows_split) / 4;     // row stride between splits; 1 split may use all 4 slabs
+  im.part_rows = std::max(2 * im.Mcap, 4 * im.part_rows_split) / 4;   // row stride between 4 splits; 1-2 splits may use Mcap-row slabs
   im.part_ws = dev_alloc<float>((size_t)4 * im.part_rows * kDModel);
   im.part_val = dev_alloc<float>((size_t)rows_dec * kArgmaxParts);
   im.part_idx = dev_alloc<int>((size_t)rows_dec * kArgmaxParts);
@@ -1000,10 +1000,16 @@ void Engine::run_encoder(const BatchDev& b) {
     static const bool defer_all = [] { const char* v = getenv("PARAKEET_B200_DEFER"); return !(v && v[0] == '0'); }();
     splits = std::max(splits, 1);
     if (splits > 1 && M > im.part_rows_split) splits = 1;
+    int stride_rows = im.part_rows, pair_split = 0;
+    if (tc && allow && splits == 1) {      // large batch on the CTA-pair kernel: a 2-way k-split can fill its last wave
+      const int ps = gemm_tc_pair_splits(M, wt.N, wt.K);
+      if (ps == 2 && 2 * (size_t)im.Mcap <= (size_t)4 * im.part_rows) { splits = 2; stride_rows = im.Mcap; pair_split = 1; }
+    }
     if (tc && allow && (splits >= 2 || defer_all) && wt.N == kDModel) {
-      EpiParams e; e.mode = EPI_PARTIAL_F32; e.out_f32 = im.part_ws; e.ldo = kDModel; e.splits = splits; e.part_rows = im.part_rows;
+      EpiParams e; e.mode = EPI_PARTIAL_F32; e.out_f32 = im.part_ws; e.ldo = kDModel; e.splits = splits; e.part_rows = stride_rows;
+      e.pair_split = pair_split;
       RUN_GEMM(act, wt, M, nullptr, e);
-      return LnResidual{im.part_ws, splits, (long long)im.part_rows * kDModel, scale};
+      return LnResidual{im.part_ws, splits, (long long)stride_rows * kDModel, scale};
     }
     EpiParams e; e.mode = EPI_RESADD_F32; e.out_f32 = im.x; e.ldo = kDModel; e.scale = scale;
     RUN_GEMM(act, wt, M, nullptr, e);

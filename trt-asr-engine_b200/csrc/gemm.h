@@ -60,6 +60,7 @@ struct EpiParams {
   const float* bias_v = nullptr;
   int splits = 1;                   // EPI_PARTIAL_F32: number of k-splits
   int part_rows = 0;                //                  rows per split in the workspace
+  int pair_split = 0;               //                  1: the split count was chosen for the CTA-pair kernel (256 x 256 tiles)
   float* part_val = nullptr;        // EPI_ARGMAX: [M][kArgmaxParts]
   int* part_idx = nullptr;
   float* dur_out = nullptr;         // [M][kNDur]
@@ -168,6 +169,7 @@ void make_tensor_map_2d(TensorMap* out, const void* base, uint64_t rows, uint64_
                         uint32_t box_rows);
 void gemm_tc(const GemmArgs& g, const TensorMap& map_a, const TensorMap& map_w, cudaStream_t st);
 bool gemm_tc_supported(const GemmArgs& g);
+int gemm_tc_pair_splits(int M, int N, int K);   // 0: pair kernel not used for this shape; else recommended k-splits (1 or 2)
 void gemm_tc_set_bn(int bn);   // validation hook: 0 = heuristic tile width, 128 / 256 = forced
 
 }  // namespace pkb

@@ -471,7 +471,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         MODE == EPI_RESADD_F32;
   const bool ragged = f32_rows && (g.epi.ldo & 3);
   const int kb_per_pass = g.K / BK;
-  const int num_kb = kb_per_pass * (g.a_lo_off != 0 ? 2 : 1);
+  const int n_pass = g.a_lo_off != 0 ? 2 : 1;
+  const int splits = MODE == EPI_PARTIAL_F32 ? g.epi.splits : 1;      // work unit = (pair tile, k-split), split fastest
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -492,20 +493,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   pdl_enter();
   const int M = g.M_dev ? min(*g.M_dev, g.M) : g.M;
   const int tiles_m = (M + BM2 - 1) / BM2, tiles_n = (g.N + BN - 1) / BN;
-  const int total_tiles = tiles_m * tiles_n;
+  const int total_tiles = tiles_m * tiles_n * splits;
 
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
-      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+      for (int unit = pair; unit < total_tiles; unit += n_pairs) {
+        const int tile = unit / splits, sp = unit - tile * splits;
         const int m0 = (tile % tiles_m) * BM2 + 128 * rank, n0 = (tile / tiles_m) * BN + 128 * rank;
+        const int kb_lo = sp * kb_per_pass / splits, kbs = (sp + 1) * kb_per_pass / splits - kb_lo;
+        const int num_kb = kbs * n_pass;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % kStages2;
           const uint32_t ph = (it / kStages2) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * kStageBytes2);
           const uint32_t leader_full = smem_u32(&full_bar[s]) & kPeerBitMask;
-          const int pass = kb / kb_per_pass, kk = (kb % kb_per_pass) * BK;
+          const int pass = kb / kbs, kk = (kb_lo + kb % kbs) * BK;
           tma_load_2d_2sm(sA + s * kTileABytes, &map_a, leader_full, kk, m0 + pass * lo_row_off);
           tma_load_2d_2sm(sB + s * kTileABytes, &map_w, leader_full, kk, n0);
         }
@@ -514,7 +518,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
       int it = 0, tl = 0;
-      for (int tile = pair; tile < total_tiles; tile += n_pairs, ++tl) {
+      for (int unit = pair; unit < total_tiles; unit += n_pairs, ++tl) {
+        const int sp = unit % splits;
+        const int num_kb = ((sp + 1) * kb_per_pass / splits - sp * kb_per_pass / splits) * n_pass;
         const int acc = tl & 1;
         mbar_wait(&tmem_empty_bar[acc], ((tl >> 1) & 1) ^ 1);          // both CTAs' epilogues have drained this buffer
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -540,7 +546,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int rsel = lane >> 2, c4 = lane & 3;
     const int rd_row = (rsel & 1) * 4 + (rsel >> 1);
     int tl = 0;
-    for (int tile = pair; tile < total_tiles; tile += n_pairs, ++tl) {
+    for (int unit = pair; unit < total_tiles; unit += n_pairs, ++tl) {
+      const int tile = unit / splits, sp = unit - tile * splits;
       const int m0 = (tile % tiles_m) * BM2 + 128 * rank, n0 = (tile / tiles_m) * BN;
       const int acc = tl & 1;
       mbar_wait(&tmem_full_bar[acc], (tl >> 1) & 1);
@@ -550,7 +557,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int m = m0 + q * 32 + rd_row + 8 * i;
-        ctx[i] = m < M ? epilogue_row_ctx<MODE>(g.epi, m, 0) : -1;
+        ctx[i] = m < M ? epilogue_row_ctx<MODE>(g.epi, m, sp) : -1;
       }
 #pragma unroll 1
       for (int c0 = 0; c0 < BN / 2; c0 += 16) {
@@ -678,6 +685,19 @@ void launch_cfg2(int pairs, const CUtensorMap& ma, const CUtensorMap& mw, const 
 
 void gemm_tc_set_bn(int bn) { g_force_bn = bn; }
 
+// Residual GEMMs on the CTA-pair kernel: 256 x 256 tiles can leave the last wave of sms/2 pairs mostly empty (M = 6144,
+// N = 1024: 96 tiles on 74 pairs).  Returns the k-split count (1 or 2) that fills the waves better, 0 if the pair kernel would
+// not be chosen for this shape at all.
+int gemm_tc_pair_splits(int M, int N, int K) {
+  const int sms = sm_count();
+  if (g_two_cta < 0) { const char* v = getenv("PARAKEET_B200_GEMM_2CTA"); g_two_cta = v ? atoi(v) : 1; }
+  if (g_force_bn > 0 || g_two_cta == 0 || !pick_two_cta(M, N, K, sms)) return 0;
+  const int pairs = sms / 2;
+  const long long t = (long long)((M + 255) / 256) * (N / 256);
+  auto waves_cost = [&](int s) { return (double)((t * s + pairs - 1) / pairs) / s; };      // rounds x (1/s of the k-loop)
+  return (K / BK >= 32 && waves_cost(2) < 0.85 * waves_cost(1)) ? 2 : 1;
+}
+
 bool gemm_tc_supported(const GemmArgs& g) {
   return g.K % BK == 0 && g.lda == g.K && (g.a_lo_off % g.lda) == 0 && g.M > 0 && g.N > 0;
 }
@@ -687,10 +707,10 @@ void gemm_tc(const GemmArgs& g, const TensorMap& map_a, const TensorMap& map_w, 
   const int sms = sm_count();
   if (g_force_bn < 0) { const char* v = getenv("PARAKEET_B200_GEMM_BN"); g_force_bn = v ? atoi(v) : 0; }
   if (g_two_cta < 0) { const char* v = getenv("PARAKEET_B200_GEMM_2CTA"); g_two_cta = v ? atoi(v) : 1; }
-  const bool two_cta = g.epi.mode != EPI_ARGMAX && !(g.epi.mode == EPI_PARTIAL_F32 && g.epi.splits > 1) &&
+  const bool two_cta = g.epi.mode != EPI_ARGMAX && !(g.epi.mode == EPI_PARTIAL_F32 && g.epi.splits > 1 && !g.epi.pair_split) &&
                        (g_force_bn == 512 || (g_force_bn == 0 && g_two_cta != 0 && pick_two_cta(g.M, g.N, g.K, sms)));
   if (two_cta) {
-    const int pair_tiles = ((g.M + 255) / 256) * ((g.N + 255) / 256);
+    const int pair_tiles = ((g.M + 255) / 256) * ((g.N + 255) / 256) * (g.epi.mode == EPI_PARTIAL_F32 ? g.epi.splits : 1);
     const int pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;
     const int lo_row_off2 = (int)(g.a_lo_off / g.lda);
     const CUtensorMap& ma2 = *reinterpret_cast<const CUtensorMap*>(&map_a);
