@@ -132,6 +132,13 @@ int32_t pkb_joint_step(PkbEngine* engine, int32_t B, int32_t T, int32_t U, const
 /* GPU log-mel frontend on host buffers: pcm[n] -> frames-major [n_frames,128]; returns n_frames (or < 0).
  * per_feature_norm != 0 applies the whole-utterance mean/std normalisation of rust/features (lib.rs:127-172). */
 int64_t pkb_logmel(PkbEngine* engine, const float* pcm, size_t n, float* out, size_t out_cap_floats, int32_t per_feature_norm);
+/* Stand-alone GPU frontend (no model weights): what a caller of the legacy parakeet_push_features() uses in place of
+ * rust/features (LogMelExtractor::compute, lib.rs:66-120).  pcm[n] (host, 16 kHz f32) -> frames-major [n_frames,128] log-mel,
+ * no normalisation; returns n_frames or < 0. */
+typedef struct PkbFrontend PkbFrontend;
+PkbFrontend* pkb_frontend_create(int32_t device_id);                 /* NULL on failure */
+void pkb_frontend_destroy(PkbFrontend* frontend);
+int64_t pkb_frontend_logmel(PkbFrontend* frontend, const float* pcm, size_t n, float* out, size_t out_cap_floats);
 /* C[M,N] = A[M,K] (f32) x W[N,K]^T (bf16 bits) through one GEMM backend (0 = CUDA cores, 1 = tcgen05): kernel validation */
 int32_t pkb_gemm_test(PkbEngine* engine, int32_t backend, int32_t M, int32_t N, int32_t K, const float* A, const uint16_t* W,
                       float* C);

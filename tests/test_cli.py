@@ -1,0 +1,98 @@
+"""parakeet_cli (the C++ counterpart of the reference's rust/cli) over the public C ABI."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import binding
+from conftest import PKG
+
+CLI = os.path.join(PKG, "bin", "parakeet_cli")
+
+
+def _build():
+    if not os.path.exists(CLI):
+        subprocess.check_call(["make", "-C", PKG, "bin/parakeet_cli"], stdout=subprocess.DEVNULL)
+
+
+def _write_wav16(path, pcm_f32):
+    q = np.clip(np.round(pcm_f32 * 32768.0), -32768, 32767).astype("<i2")
+    with open(path, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", 36 + q.nbytes) + b"WAVE" + b"fmt " + struct.pack("<IHHIIHH", 16, 1, 1, 16000, 32000, 2, 16))
+        f.write(b"data" + struct.pack("<I", q.nbytes) + q.tobytes())
+    return q.astype(np.float32) / 32768.0
+
+
+def test_cli_usage_and_errors(tmp_path):
+    _build()
+    out = subprocess.run([CLI, "--help"], capture_output=True, text=True)
+    assert out.returncode == 0 and "--stream-sim" in out.stdout and "--features-input" in out.stdout
+    bad = subprocess.run([CLI, "x.wav"], capture_output=True, text=True)
+    assert bad.returncode == 1 and "model-dir" in bad.stderr
+    bad = subprocess.run([CLI, str(tmp_path / "missing.wav"), "--model-dir", str(tmp_path)], capture_output=True, text=True)
+    assert bad.returncode == 1 and "cannot open" in bad.stderr
+    # feature tap whose JSON sidecar names an unsupported sample format (rust/cli/src/main.rs:240-244)
+    (tmp_path / "tap.raw").write_bytes(np.zeros(128 * 40, np.float32).tobytes())
+    (tmp_path / "tap.json").write_text('{"kind": "mel_features", "format": "f16le", "layout": "bins_major", "mel_bins": 128, "num_frames": 40}')
+    bad = subprocess.run([CLI, str(tmp_path / "tap.json"), "--features-input", "--model-dir", str(tmp_path)], capture_output=True, text=True)
+    assert bad.returncode == 1 and "not supported" in bad.stderr
+
+
+@pytest.mark.gpu
+def test_cli_stream_sim_matches_the_abi_path(tmp_path, model_small, features_ref):
+    """WAV -> GPU log-mel -> per-feature norm (whole-file stats) -> 0.5 s pushes: the CLI's dumped features match the oracle and
+    its per-chunk transcripts match the same pushes made through the Python mirror of the safe wrapper."""
+    from synth_audio import synth_clip
+    _build()
+    pcm = _write_wav16(str(tmp_path / "a.wav"), synth_clip(4.0, 77))
+    env = dict(os.environ, PARAKEET_EMIT_FINAL_EACH_CHUNK="1")
+    run = subprocess.run([CLI, str(tmp_path / "a.wav"), "--model-dir", model_small, "--stream-sim", "0.5", "--no-sleep", "--feature-norm",
+                          "per_feature", "--dump-features", str(tmp_path / "f.raw")], capture_output=True, text=True, env=env, timeout=300)
+    assert run.returncode == 0, run.stderr
+    finals = [ln[len("Final: "):] for ln in run.stdout.splitlines() if ln.startswith("Final: ")]
+    # the same pipeline on the checker + the ABI
+    whole = features_ref.logmel(pcm)
+    mean, std = features_ref.stats(whole)
+    chunks = []
+    for pos in range(0, pcm.size, 8000):
+        f = features_ref.logmel(pcm[pos:pos + 8000])
+        if f.shape[0]:
+            chunks.append(np.ascontiguousarray(((f - mean) / std).T))
+    dumped = np.fromfile(str(tmp_path / "f.raw"), np.float32)
+    want = np.concatenate([c.ravel() for c in chunks])
+    assert dumped.size == want.size and np.max(np.abs(dumped - want)) < 2e-3      # 1e-3 feature budget / std floor effects on bin 0 aside
+    os.environ["PARAKEET_EMIT_FINAL_EACH_CHUNK"] = "1"
+    try:
+        s = binding.ParakeetSessionSafe(model_small, 0, use_fp16=True)
+        got = []
+        for c in chunks:
+            s.push_features(c, c.shape[1])
+            while True:
+                ev = s.poll_event()
+                if ev is None:
+                    break
+                if ev.kind == "final":
+                    got.append(ev.text)
+        s.close()
+    finally:
+        del os.environ["PARAKEET_EMIT_FINAL_EACH_CHUNK"]
+    assert len(finals) == len(got) == len(chunks)
+    assert sum(a == b for a, b in zip(finals, got)) >= len(got) - 1      # bf16 session on 1e-5-different features: allow one flip
+
+
+@pytest.mark.gpu
+def test_cli_feature_replay(tmp_path, model_small, features_ref):
+    """Feature-tap replay (frames-major raw + JSON sidecar) reproduces the transcript of the same features pushed directly."""
+    from conftest import normalized_features
+    _build()
+    f = normalized_features(features_ref, 6.0, 5)            # [128, T] bins-major
+    np.ascontiguousarray(f.T).tofile(str(tmp_path / "tap_FEATURES.raw"))
+    (tmp_path / "tap_FEATURES.json").write_text('{"kind":"mel_features","format":"f32le","layout":"frames_major","shape":[%d,128]}' % f.shape[1])
+    env = dict(os.environ, PARAKEET_EMIT_FINAL_EACH_CHUNK="1")
+    run = subprocess.run([CLI, str(tmp_path / "tap_FEATURES.json"), "--features-input", "--model-dir", model_small, "-v"], capture_output=True,
+                         text=True, env=env, timeout=300)
+    assert run.returncode == 0, run.stderr
+    assert "Loaded %d frames of 128 mel features" % f.shape[1] in run.stderr
+    assert len([ln for ln in run.stdout.splitlines() if ln.startswith("Transcript: ")]) == (f.shape[1] + 255) // 256

@@ -32,7 +32,7 @@ B200_SYMBOLS = ["pkb_last_error", "pkb_version", "pkb_engine_create", "pkb_engin
                 "pkb_stream_num_tokens", "pkb_stream_tokens", "pkb_stream_last_steps", "pkb_stream_cache_len",
                 "pkb_stream_chunks_done", "pkb_stream_text", "pkb_detokenize", "pkb_stream_import_state", "pkb_stream_export_state",
                 "pkb_stream_set_decoder_state", "pkb_stream_get_decoder_state", "pkb_encoder_streaming_step", "pkb_predictor_step",
-                "pkb_joint_step", "pkb_logmel", "pkb_gemm_test"]
+                "pkb_joint_step", "pkb_logmel", "pkb_gemm_test", "pkb_frontend_create", "pkb_frontend_destroy", "pkb_frontend_logmel"]
 
 
 class ParakeetConfig(C.Structure):

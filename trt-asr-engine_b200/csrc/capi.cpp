@@ -68,6 +68,13 @@ struct PkbEngine {
   std::mutex mu;   // one caller at a time per engine
 };
 
+struct PkbFrontend {
+  pkb::Frontend* fe = nullptr;
+  cudaStream_t st = nullptr;
+  int device = 0, sms = 148;
+  std::mutex mu;
+};
+
 struct ParakeetSession {
   pkb::Engine* eng = nullptr;
   int sid = -1;
@@ -339,13 +346,13 @@ int32_t pkb_stream_set_offline(PkbEngine* e, int32_t s, int32_t offline) {
 }
 int32_t pkb_engine_push_audio_batch(PkbEngine* e, int32_t n, const int32_t* sids, const float* pcm, int64_t stride, int32_t count) {
   PKB_ENTER(e);
-  if (!sids || (!pcm && n * count)) { g_last_error = "null argument"; return -1; }
+  if (!sids || (!pcm && n > 0 && count > 0)) { g_last_error = "null argument"; return -1; }
   return guarded([&] { e->eng->push_audio_batch(n, sids, pcm, stride, count, false); return 0; });
 }
 int32_t pkb_engine_push_audio_batch_device(PkbEngine* e, int32_t n, const int32_t* sids, const float* d_pcm, int64_t stride,
                                            int32_t count) {
   PKB_ENTER(e);
-  if (!sids || (!d_pcm && n * count)) { g_last_error = "null argument"; return -1; }
+  if (!sids || (!d_pcm && n > 0 && count > 0)) { g_last_error = "null argument"; return -1; }
   return guarded([&] { e->eng->push_audio_batch(n, sids, d_pcm, stride, count, true); return 0; });
 }
 int32_t pkb_engine_event_record(PkbEngine* e) { PKB_ENTER(e); return guarded([&] { return e->eng->event_record(); }); }
@@ -449,6 +456,62 @@ int64_t pkb_logmel(PkbEngine* e, const float* pcm, size_t n, float* out, size_t 
     return (int64_t)e->eng->logmel(pcm, n, out, per_feature_norm);
   } catch (const std::exception& ex) {
     g_last_error = ex.what();
+    return -2;
+  }
+}
+PkbFrontend* pkb_frontend_create(int32_t device_id) {
+  try {
+    PKB_CUDA(cudaSetDevice(device_id));
+    cudaDeviceProp prop;
+    PKB_CUDA(cudaGetDeviceProperties(&prop, device_id));
+    PKB_CHECK(prop.major == 10, "this library is built for sm_100a (B200) only");
+    PkbFrontend* f = new PkbFrontend();
+    f->device = device_id;
+    f->sms = prop.multiProcessorCount;
+    f->fe = new pkb::Frontend();
+    PKB_CUDA(cudaStreamCreateWithFlags(&f->st, cudaStreamNonBlocking));
+    PKB_CUDA(cudaDeviceSynchronize());
+    return f;
+  } catch (const std::exception& ex) {
+    g_last_error = ex.what();
+    return nullptr;
+  }
+}
+void pkb_frontend_destroy(PkbFrontend* f) {
+  if (!f) return;
+  cudaStreamSynchronize(f->st);
+  cudaStreamDestroy(f->st);
+  delete f->fe;
+  delete f;
+}
+int64_t pkb_frontend_logmel(PkbFrontend* f, const float* pcm, size_t n, float* out, size_t cap) {
+  if (!f || !pcm || !out) { g_last_error = "null argument"; return -1; }
+  std::lock_guard<std::mutex> lock(f->mu);
+  float *d_audio = nullptr, *d_out = nullptr;
+  pkb::FrontSegment* d_seg = nullptr;
+  int* d_prefix = nullptr;
+  try {
+    const size_t T = n < 400 ? 0 : (n - 400) / 160 + 1;
+    if (T == 0) return 0;
+    if (T * pkb::kNMels > cap) { g_last_error = "output buffer too small"; return -1; }
+    PKB_CUDA(cudaSetDevice(f->device));
+    PKB_CUDA(cudaMalloc(&d_audio, (n + 2) * 4));
+    PKB_CUDA(cudaMalloc(&d_out, T * pkb::kNMels * 4));
+    PKB_CUDA(cudaMalloc(&d_seg, sizeof(pkb::FrontSegment)));
+    PKB_CUDA(cudaMalloc(&d_prefix, 2 * sizeof(int)));
+    const pkb::FrontSegment sg{0, 0, pkb::kNMels, 0, 0, -1};
+    const int prefix[2] = {0, (int)T};
+    PKB_CUDA(cudaMemcpyAsync(d_audio, pcm, n * 4, cudaMemcpyHostToDevice, f->st));
+    PKB_CUDA(cudaMemcpyAsync(d_seg, &sg, sizeof(sg), cudaMemcpyHostToDevice, f->st));
+    PKB_CUDA(cudaMemcpyAsync(d_prefix, prefix, sizeof(prefix), cudaMemcpyHostToDevice, f->st));
+    f->fe->logmel(d_audio, d_seg, d_prefix, 1, (int)T, d_out, nullptr, f->sms, f->st);
+    PKB_CUDA(cudaMemcpyAsync(out, d_out, T * pkb::kNMels * 4, cudaMemcpyDeviceToHost, f->st));
+    PKB_CUDA(cudaStreamSynchronize(f->st));
+    cudaFree(d_audio); cudaFree(d_out); cudaFree(d_seg); cudaFree(d_prefix);
+    return (int64_t)T;
+  } catch (const std::exception& ex) {
+    g_last_error = ex.what();
+    cudaFree(d_audio); cudaFree(d_out); cudaFree(d_seg); cudaFree(d_prefix);
     return -2;
   }
 }

@@ -19,6 +19,7 @@ namespace pkb {
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kNfft = 512, kWin = 400, kHop = 160, kBins = 257, kHalf = 256;
+constexpr int kMaxSegsSmem = 2048;       // segments whose frame prefix is staged in shared memory
 
 struct FrontTablesHost {
   std::vector<float> window;       // [400]
@@ -110,6 +111,7 @@ logmel_kernel(const float* __restrict__ audio, const FrontSegment* __restrict__ 
   int* s_off = s_cnt + kNMels;
   float* s_w = reinterpret_cast<float*>(s_off + kNMels);            // n_w (<= 768)
   WarpBuf* s_warp = reinterpret_cast<WarpBuf*>(s_w + 768);
+  int* s_prefix = reinterpret_cast<int*>(s_warp + kWarpsPerCta);   // [kMaxSegsSmem + 1] frame prefix (binary-searched per frame)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < kWin; i += blockDim.x) s_window[i] = tb.window[i];
@@ -125,6 +127,10 @@ logmel_kernel(const float* __restrict__ audio, const FrontSegment* __restrict__ 
   }
   for (int i = tid; i < kNMels; i += blockDim.x) { s_lo[i] = tb.mel_lo[i]; s_cnt[i] = tb.mel_cnt[i]; s_off[i] = tb.mel_off[i]; }
   for (int i = tid; i < tb.n_w; i += blockDim.x) s_w[i] = tb.mel_w[i];
+  const bool prefix_in_smem = n_segs <= kMaxSegsSmem;
+  if (prefix_in_smem)
+    for (int i = tid; i <= n_segs; i += blockDim.x) s_prefix[i] = frame_prefix[i];
+  const int* prefix = prefix_in_smem ? s_prefix : frame_prefix;      // 10 dependent global loads per frame otherwise
   __syncthreads();
 
   WarpBuf& wb = s_warp[warp];
@@ -134,10 +140,10 @@ logmel_kernel(const float* __restrict__ audio, const FrontSegment* __restrict__ 
     int lo = 0, hi = n_segs - 1;
     while (lo < hi) {
       int mid = (lo + hi + 1) >> 1;
-      if (frame_prefix[mid] <= gf) lo = mid; else hi = mid - 1;
+      if (prefix[mid] <= gf) lo = mid; else hi = mid - 1;
     }
     const FrontSegment sg = segs[lo];
-    const int t = gf - frame_prefix[lo];
+    const int t = gf - prefix[lo];
     const float* x = audio + sg.audio_off + (size_t)t * kHop;
 
     // windowed frame -> packed complex z[n] = x[2n] + i x[2n+1]; samples >= 400 are zero
@@ -213,7 +219,7 @@ logmel_kernel(const float* __restrict__ audio, const FrontSegment* __restrict__ 
 }
 
 static size_t logmel_smem_bytes() {
-  return (kWin + 2 * kHalf + 2 * (kBins + 1) + 3 * kNMels + 768) * 4 + sizeof(WarpBuf) * kWarpsPerCta;
+  return (kWin + 2 * kHalf + 2 * (kBins + 1) + 3 * kNMels + 768) * 4 + sizeof(WarpBuf) * kWarpsPerCta + (kMaxSegsSmem + 1) * 4;
 }
 
 void Frontend::logmel(const float* d_audio, const FrontSegment* d_segs, const int* d_frame_prefix, int n_segs,
