@@ -12,9 +12,11 @@
 //     item ahead of the 8 consumer warps, so the loads of item i+1 overlap the math of item i.
 //   * keys are walked in PHYSICAL ring order (the softmax sum does not care), so a wrapped FIFO needs no second copy and
 //     every box is one contiguous row range; validity and the relative position of slot p follow from the ring head.
-//   * all products run on mma.sync m16n8k16 (bf16 -> f32): G = (q+v) P^T first (P comes from L2, this hides the K
-//     latency), then S = (q+u) K^T with B fragments via ldmatrix from the swizzled tiles, softmax in fp32 in smem,
-//     O = P V with ldmatrix.trans on the V tiles.  R = query rows handled (8: the steady-state 6-row chunk, 16, 32).
+//   * the position term G = (q+v) P^T is NOT computed here: it is the same P for every stream, so one batched tcgen05 GEMM
+//     per layer produces it for all streams and heads (engine.cu) and this kernel only stages its rows;
+//     S = (q+u) K^T (B fragments via ldmatrix from the swizzled tiles) and O = P V (ldmatrix.trans on the V tiles) run
+//     on mma.sync m16n8k16 (bf16 -> f32), softmax in fp32 in smem.  R = query rows handled (8: the steady-state 6-row
+//     chunk, 16, 32).
 #include <cuda.h>
 
 #include "enc_kernels.cuh"
@@ -28,7 +30,7 @@ constexpr int kNumBlk = kRingCap / kBlkKeys;
 constexpr int kBoxBytes = kBlkKeys * 128;          // one 96 x 64 bf16 box
 constexpr int kStageBytes = 2 * kBoxBytes;         // d 0..63 and d 64..127
 constexpr int kSPitch = 296;                       // floats; 296 % 32 == 8 -> conflict-free float2 fragment stores
-constexpr int kGPitch = 328;                       // floats; covers the 320 table rows
+constexpr int kGPitch = 328;                       // bf16 elements per staged row of position scores (covers the 320 table rows; 16-byte multiple)
 constexpr int kPPitchB = 592;                      // bytes per probability row (296 bf16); 37 x 16 B -> conflict-free ldmatrix
 static_assert(kRingCap % kBlkKeys == 0 && kPosRowsPad >= kPosRows, "ring / table geometry");
 
@@ -95,7 +97,7 @@ struct Smem {
   static constexpr int kCtasPerSm = R == 8 ? (CFG == 0 ? 3 : 2) : 1;
   static constexpr int kThreads = 32 * (1 + kCW);
   static constexpr int kS = R * kSPitch * 4;
-  static constexpr int kG = R * kGPitch * 4;             // later reused for the bf16 probabilities (R_pad x 592 B <= kG)
+  static constexpr int kG = (R < 16 ? 8 : R) * (kGPitch * 2 > kPPitchB ? kGPitch * 2 : kPPitchB);   // bf16 G rows, later the bf16 probabilities
   static constexpr size_t kBytes = 1024 + (size_t)kStages * kStageBytes + kS + kG + 128;
 };
 
@@ -139,7 +141,7 @@ attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* s_ring = base;
   float* s_S = reinterpret_cast<float*>(base + kStages * kStageBytes);
-  float* s_G = s_S + R * kSPitch;
+  __nv_bfloat16* s_G = reinterpret_cast<__nv_bfloat16*>(s_S + R * kSPitch);      // [R][kGPitch] bf16, later the probabilities
   uint8_t* s_P = reinterpret_cast<uint8_t*>(s_G);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_G) + Smem<R, CFG>::kG);
   uint64_t* empty_bar = full_bar + kStages;
@@ -193,10 +195,8 @@ attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
     const Item im = load_item(b, a, e);
     const int Tq = im.Tq;
 
-    // ---- query fragments from the bf16 planes written by the QKV epilogue (q+u: natural k order for ldmatrix on the
-    //      K tiles; q+v: permuted k order matching the 16-byte-per-lane loads of the position table, k-step (blk, s):
-    //      lane t covers d = 32 blk + 8 t + 4 s + {0..3})
-    uint32_t qu[MT][8][4], qv[MT][8][4];
+    // ---- query fragments (q + pos_bias_u, bf16 plane written by the QKV epilogue; natural k order = ldmatrix order of the K tiles)
+    uint32_t qu[MT][8][4];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
@@ -209,48 +209,17 @@ attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
           qu[mt][ks][hr] = ok ? *reinterpret_cast<const uint32_t*>(qrow + 16 * ks + 2 * t) : 0u;
           qu[mt][ks][hr + 2] = ok ? *reinterpret_cast<const uint32_t*>(qrow + 16 * ks + 8 + 2 * t) : 0u;
         }
-#pragma unroll
-        for (int blk = 0; blk < 4; ++blk) {
-          uint4 w = make_uint4(0u, 0u, 0u, 0u);
-          if (ok) w = *reinterpret_cast<const uint4*>(qrow + a.q_plane + 32 * blk + 8 * t);
-          qv[mt][2 * blk][hr] = w.x; qv[mt][2 * blk][hr + 2] = w.y;
-          qv[mt][2 * blk + 1][hr] = w.z; qv[mt][2 * blk + 1][hr + 2] = w.w;
-        }
       }
     }
 
-    // ---- G[i][r] = (q_i + v) . P[r]  for the table rows this chunk can touch (P from L2; software-pipelined loads)
+    // ---- position scores G[i][r] = (q_i + pos_bias_v) . P[r]: one batched tcgen05 GEMM per layer computes them for every
+    //      stream and head (engine.cu); here the item's rows are staged in shared memory (bf16 [rows][kGPitch])
     {
-      const int r_lo = kPosNeg - (Tq - 1), r_hi = kPosNeg + kCacheS + Tq;      // rows [r_lo, r_hi)
-      const __nv_bfloat16* pn = a.ppos_n + (size_t)h * kPosRowsPad * kDHead;
-      int nt = (r_lo >> 3) + cw;
-      uint4 w[4], wn[4];
-      if (nt * 8 < r_hi) {
-        const uint4* prow = reinterpret_cast<const uint4*>(pn + (size_t)(nt * 8 + g) * kDHead) + t;
-#pragma unroll
-        for (int blk = 0; blk < 4; ++blk) w[blk] = __ldg(prow + 4 * blk);
-      }
-      for (; nt * 8 < r_hi; nt += kConsumerWarps) {
-        const bool more = (nt + kConsumerWarps) * 8 < r_hi;
-        if (more) {
-          const uint4* prow = reinterpret_cast<const uint4*>(pn + (size_t)((nt + kConsumerWarps) * 8 + g) * kDHead) + t;
-#pragma unroll
-          for (int blk = 0; blk < 4; ++blk) wn[blk] = __ldg(prow + 4 * blk);
-        }
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          float c[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};      // two chains: half the dependent-HMMA latency
-#pragma unroll
-          for (int blk = 0; blk < 4; ++blk) {
-            mma_bf16(c, qv[mt][2 * blk], w[blk].x, w[blk].y);
-            mma_bf16(c2, qv[mt][2 * blk + 1], w[blk].z, w[blk].w);
-          }
-          *reinterpret_cast<float2*>(s_G + (16 * mt + g) * kGPitch + nt * 8 + 2 * t) = make_float2(c[0] + c2[0], c[1] + c2[1]);
-          if (!kHalf)
-            *reinterpret_cast<float2*>(s_G + (16 * mt + g + 8) * kGPitch + nt * 8 + 2 * t) = make_float2(c[2] + c2[2], c[3] + c2[3]);
-        }
-#pragma unroll
-        for (int blk = 0; blk < 4; ++blk) w[blk] = wn[blk];
+      const int cthread = tid - 32;
+      for (int x = cthread; x < Tq * (kPosRowsPad / 8); x += kConsumerThreads) {
+        const int i = x / (kPosRowsPad / 8), c = x % (kPosRowsPad / 8);
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.g_pos + (size_t)(im.row0 + i) * (kHeads * kPosRowsPad) + h * kPosRowsPad) + c);
+        *reinterpret_cast<uint4*>(s_G + i * kGPitch + 8 * c) = v;
       }
     }
     consumer_sync<kConsumerThreads>();      // G complete
@@ -300,7 +269,7 @@ attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
               int j = p - im.head;
               j += j < 0 ? kRingCap : 0;
               const bool valid = j >= kCacheS - im.len && j < kCacheS + im.qlen;
-              out[x] = valid ? (c[mt][2 * hr + x] + s_G[i * kGPitch + (kCacheS + i - j) + kPosNeg]) * scale : -INFINITY;
+              out[x] = valid ? (c[mt][2 * hr + x] + __bfloat162float(s_G[i * kGPitch + (kCacheS + i - j) + kPosNeg])) * scale : -INFINITY;
             }
             *reinterpret_cast<float2*>(s_S + i * kSPitch + k * kBlkKeys + 8 * nb + 2 * t) = make_float2(out[0], out[1]);
           }

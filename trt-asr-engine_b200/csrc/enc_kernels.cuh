@@ -82,7 +82,7 @@ void launch_attention(const BatchDev& b, const AttnArgs& a, cudaStream_t st);
 struct AttnMmaArgs {
   const __nv_bfloat16* q_bf16;   // [2][Mcap,1024] bf16: plane 0 = q + pos_bias_u, plane 1 (q_plane elements further) = q + pos_bias_v
   long long q_plane;
-  const __nv_bfloat16* ppos_n;   // this layer's projected position table, natural layout [head][kPosRowsPad][128]
+  const __nv_bfloat16* g_pos;    // position scores (q + pos_bias_v) . P[r], bf16 [M][8 heads][kPosRowsPad] (batched GEMM, engine.cu)
   ActOut ctx;                    // [M,1024] bf16
   const void* map_k;             // host pointers to 128-byte CUtensorMap objects
   const void* map_v;

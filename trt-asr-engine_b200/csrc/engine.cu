@@ -71,6 +71,7 @@ struct LayerW {
   float *dw_w, *dw_b, *bias_u, *bias_v;
   void* ppos_t;                 // precise mode: transposed table [head][128][kPosRows] f32
   __nv_bfloat16* ppos_n;        // bf16 mode: natural table [head][kPosRowsPad][128]
+  TensorMap ppos_map;           //           TMA map over it as the W operand [8 * kPosRowsPad, 128] of the position-score GEMM
 };
 
 // ---- small utility kernels ----
@@ -200,7 +201,10 @@ struct Engine::Impl {
   // work buffers
   int Mcap = 0, Bcap = 0, T3cap = 0, T2cap = 0;
   ActBuf a_sub1, a_sub2, a_sub3, a_ln, a_ff, a_xf, a_hid, a_pred, a_g, a_imp, a_pos;
-  __nv_bfloat16* q_bf16 = nullptr;       // bf16 mode: [2][Mcap,1024] (q + pos_bias_u | q + pos_bias_v)
+  __nv_bfloat16* q_bf16 = nullptr;       // bf16 mode: [2][q_rows,1024] (q + pos_bias_u | q + pos_bias_v), q_rows = Mcap padded to 128
+  long long q_plane = 0;                 //           elements between the planes
+  TensorMap map_qv;                      //           TMA map over the q + pos_bias_v plane (A operand of the position-score GEMM)
+  __nv_bfloat16* g_pos = nullptr;        //           position scores [q_rows][8][kPosRowsPad] bf16
   float *x = nullptr, *q = nullptr, *cglu = nullptr, *y1 = nullptr, *enc_proj = nullptr, *logits = nullptr, *gates = nullptr,
         *enc_out = nullptr, *ppos_tmp = nullptr, *scratch_f32 = nullptr, *part_val = nullptr, *dur_logits = nullptr;
   int* part_idx = nullptr;
@@ -541,7 +545,14 @@ void Engine::alloc_state() {
   im.a_pos = make_act(kPosRows, kDModel, true, st_);
   im.x = dev_alloc<float>((size_t)im.Mcap * kDModel);
   im.q = dev_alloc<float>((size_t)im.Mcap * kDModel);
-  if (im.attn_mma) im.q_bf16 = dev_alloc<__nv_bfloat16>((size_t)2 * im.Mcap * kDModel);
+  if (im.attn_mma) {
+    const size_t q_rows = ((size_t)im.Mcap + 127) / 128 * 128;
+    im.q_plane = (long long)q_rows * kDModel;
+    im.q_bf16 = dev_alloc<__nv_bfloat16>((size_t)2 * im.q_plane);
+    PKB_CUDA(cudaMemsetAsync(im.q_bf16, 0, (size_t)2 * im.q_plane * 2, st_));
+    make_tensor_map_2d(&im.map_qv, im.q_bf16 + im.q_plane, q_rows, kDModel, kDModel, 128);
+    im.g_pos = dev_alloc<__nv_bfloat16>(q_rows * kHeads * kPosRowsPad);
+  }
   im.cglu = dev_alloc<float>((size_t)im.Mcap * kDModel);
   im.y1 = dev_alloc<float>((size_t)im.T2cap * 32 * kSubCh);
   im.enc_proj = dev_alloc<float>((size_t)std::max(im.Mcap, rows_dec) * kJointH);
@@ -616,6 +627,7 @@ void Engine::alloc_state() {
         im.layers[l].ppos_n = dev_alloc<__nv_bfloat16>((size_t)kHeads * kPosRowsPad * kDHead);
         PKB_CUDA(cudaMemsetAsync(im.layers[l].ppos_n, 0, (size_t)kHeads * kPosRowsPad * kDHead * 2, st_));
         ppos_natural_kernel<<<kPosRows, 256, 0, st_>>>(im.ppos_tmp, im.layers[l].ppos_n);
+        make_tensor_map_2d(&im.layers[l].ppos_map, im.layers[l].ppos_n, (uint64_t)kHeads * kPosRowsPad, kDHead, kDHead, 128);
       } else {
         im.layers[l].ppos_t = dev_alloc_bytes((size_t)kPosRows * kDModel * kv_elem);
         ppos_transpose_kernel<<<kPosRows, 256, 0, st_>>>(im.ppos_tmp, im.layers[l].ppos_t, 1);
@@ -1039,10 +1051,17 @@ void Engine::run_encoder(const BatchDev& b) {
     { EpiParams e; e.mode = EPI_QKV; e.out_f32 = im.q; e.ldo = kDModel; e.row_entry = b.row_entry; e.row_pos = b.row_pos;
       e.entry_slot = b.slot; e.entry_head = b.head; e.kring = kr; e.vring = vr; e.kv_f32 = split ? 1 : 0;
       e.k_natural = im.attn_mma ? 1 : 0;
-      if (im.attn_mma) { e.q_bf16 = im.q_bf16; e.q_plane = (long long)im.Mcap * kDModel; e.bias_u = w.bias_u; e.bias_v = w.bias_v; }
+      if (im.attn_mma) { e.q_bf16 = im.q_bf16; e.q_plane = im.q_plane; e.bias_u = w.bias_u; e.bias_v = w.bias_v; }
       RUN_GEMM(im.a_ln, w.qkv, M, nullptr, e); }
     if (im.attn_mma) {
-      AttnMmaArgs a; a.q_bf16 = im.q_bf16; a.q_plane = (long long)im.Mcap * kDModel; a.ppos_n = w.ppos_n; a.ctx = im.a_ln.out();
+      // position scores for every (row, head): G[m][h][r] = (q_m + pos_bias_v)[h] . P_h[r] -- 8 batched [M,128] x [320,128]^T
+      // problems in one tcgen05 launch (the table is the same for every stream, so this does not belong in the per-stream kernel)
+      { GemmArgs g;
+        g.A = im.q_bf16 + im.q_plane; g.lda = kDModel; g.W = w.ppos_n; g.M = M; g.N = kPosRowsPad; g.K = kDHead;
+        g.batch = kHeads; g.a_col_stride = kDHead; g.w_row_stride = kPosRowsPad; g.out_col_stride = kPosRowsPad;
+        g.epi.mode = EPI_ACT; g.epi.out_act = im.g_pos; g.epi.lda_out = kHeads * kPosRowsPad;
+        gemm_tc(g, im.map_qv, w.ppos_map, st_); ++launches_; }
+      AttnMmaArgs a; a.q_bf16 = im.q_bf16; a.q_plane = im.q_plane; a.g_pos = im.g_pos; a.ctx = im.a_ln.out();
       a.map_k = &im.map_k; a.map_v = &im.map_v; a.layer = l; a.n_slots = opt_.max_streams;
       launch_attention_mma(b, a, st_); ++launches_;
     } else {

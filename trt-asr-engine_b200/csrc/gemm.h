@@ -25,6 +25,7 @@ enum EpiMode : int {
   EPI_GLU_F32 = 7,         // interleaved weights: out_f32[m,n/2] = acc[n] * sigmoid(acc[n+1]), n even
   EPI_F32 = 8,             // out_f32[m,n] = acc
   EPI_PARTIAL_F32 = 10,
+  EPI_ACT = 11,            // out_act[m,n] = acc   (bf16 hi[/lo], no bias / activation)
   EPI_ARGMAX = 9,          // joint output layer with the greedy selection fused (tensor-core backend only): per row and per
                            // 128-column slab the running (max, first argmax) of acc + bias over the token head [0, kVocab)
                            // goes to part_val / part_idx [m][2 * tiles_n]; the kNDur duration logits go to dur_out [m][kNDur].
@@ -75,6 +76,10 @@ struct GemmArgs {
   long long a_lo_off = 0;
   const __nv_bfloat16* W = nullptr;
   int M = 0, N = 0, K = 0;
+  // batched problems sharing one launch (tensor-core backend): batch b multiplies A[:, b*a_col_stride : +K] by
+  // W[b*w_row_stride : +N, :] and writes at column offset b*out_col_stride of the output (e.g. one batch per attention head)
+  int batch = 1;
+  int a_col_stride = 0, w_row_stride = 0, out_col_stride = 0;
   const int* M_dev = nullptr;   // optional device-side row count: effective M = min(*M_dev, M) (decode: rows known only on device)
   EpiParams epi;
 };
@@ -109,6 +114,10 @@ __device__ __forceinline__ void epilogue_pair(const EpiParams& p, int m, int n, 
       }
       break;
     }
+    case EPI_ACT:
+      store_act(p.out_act, m, p.lda_out, n, v0, p.lo_off_out);
+      if (has1) store_act(p.out_act, m, p.lda_out, n + 1, v1, p.lo_off_out);
+      break;
     case EPI_SILU_ACT:
       store_act(p.out_act, m, p.lda_out, n, silu(v0), p.lo_off_out);
       if (has1) store_act(p.out_act, m, p.lda_out, n + 1, silu(v1), p.lo_off_out);

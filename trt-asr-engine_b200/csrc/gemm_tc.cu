@@ -159,6 +159,8 @@ __device__ __forceinline__ void epilogue_quad(const EpiParams& p, int m, int ctx
     const float4 b = *reinterpret_cast<const float4*>(p.bias + nn);
     v.x = fmaxf(v.x + b.x, 0.f); v.y = fmaxf(v.y + b.y, 0.f); v.z = fmaxf(v.z + b.z, 0.f); v.w = fmaxf(v.w + b.w, 0.f);
     store_act4(p.out_act, m, p.lda_out, nn, v, p.lo_off_out);
+  } else if constexpr (MODE == EPI_ACT) {
+    store_act4(p.out_act, m, p.lda_out, nn, v, p.lo_off_out);
   } else if constexpr (MODE == EPI_SILU_ACT) {
     v.x = silu(v.x); v.y = silu(v.y); v.z = silu(v.z); v.w = silu(v.w);
     store_act4(p.out_act, m, p.lda_out, nn, v, p.lo_off_out);
@@ -251,26 +253,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   pdl_enter();      // barrier init + TMEM allocation above overlap the previous kernel's tail; global data only from here on
   const int M = g.M_dev ? min(*g.M_dev, g.M) : g.M;
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN;
-  const int total_tiles = tiles_m * tiles_n * splits;   // CTAs beyond the (device-side) unit count fall through to the teardown
+  const int tiles_mn = tiles_m * tiles_n;
+  const int total_tiles = tiles_mn * splits * g.batch;  // CTAs beyond the (device-side) unit count fall through to the teardown
 
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
       for (int unit = blockIdx.x; unit < total_tiles; unit += gridDim.x) {
-        const int tile = unit / splits, sp = unit - tile * splits;
+        const int tile_b = unit / splits, sp = unit - tile_b * splits;
+        const int bt = tile_b / tiles_mn, tile = tile_b - bt * tiles_mn;
         const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
         const int kb_lo = sp * kb_per_pass / splits, kbs = (sp + 1) * kb_per_pass / splits - kb_lo;
         const int num_kb = kbs * n_pass;
+        const int a_col0 = bt * g.a_col_stride, w_row0 = bt * g.w_row_stride;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], C::kStageBytes);
           const int pass = kb / kbs, kk = (kb_lo + kb % kbs) * BK;
-          tma_load_2d(sA + s * kTileABytes, &map_a, &full_bar[s], kk, m0 + pass * lo_row_off);
+          tma_load_2d(sA + s * kTileABytes, &map_a, &full_bar[s], a_col0 + kk, m0 + pass * lo_row_off);
 #pragma unroll
           for (int j = 0; j < BN / 128; ++j)
-            tma_load_2d(sB + s * C::kTileBBytes + j * kTileABytes, &map_w, &full_bar[s], kk, n0 + j * 128);
+            tma_load_2d(sB + s * C::kTileBBytes + j * kTileABytes, &map_w, &full_bar[s], kk, w_row0 + n0 + j * 128);
         }
       }
     }
@@ -307,8 +312,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int rd_row = (rsel & 1) * 4 + (rsel >> 1);        // rows r and r+4 in one quarter-warp: conflict-free reads
     int tl = 0;
     for (int unit = blockIdx.x; unit < total_tiles; unit += gridDim.x, ++tl) {
-      const int tile = unit / splits, sp = unit - tile * splits;
+      const int tile_b = unit / splits, sp = unit - tile_b * splits;
+      const int bt = tile_b / tiles_mn, tile = tile_b - bt * tiles_mn;
       const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+      const int n_out0 = bt * g.out_col_stride;      // batched problems: column offset of this batch in the output
       const int acc = tl & 1;
       mbar_wait(&tmem_full_bar[acc], (tl >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -358,8 +365,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           } else {
             if (m < M && n < g.N) {
-              if (n + 3 < g.N && !ragged) epilogue_quad<MODE>(g.epi, m, ctx[i], n, val);
-              else epilogue_edge(g.epi, m, n, g.N, val);
+              if (n + 3 < g.N && !ragged) epilogue_quad<MODE>(g.epi, m, ctx[i], n + n_out0, val);
+              else epilogue_edge(g.epi, m, n + n_out0, g.N + n_out0, val);
             }
           }
         }
@@ -699,7 +706,8 @@ int gemm_tc_pair_splits(int M, int N, int K) {
 }
 
 bool gemm_tc_supported(const GemmArgs& g) {
-  return g.K % BK == 0 && g.lda == g.K && (g.a_lo_off % g.lda) == 0 && g.M > 0 && g.N > 0;
+  // (batched problems address a column window of A through the tensor map: lda may exceed K)
+  return g.K % BK == 0 && (g.lda == g.K || (g.batch > 1 && g.a_lo_off == 0)) && (g.a_lo_off % g.lda) == 0 && g.M > 0 && g.N > 0;
 }
 
 void gemm_tc(const GemmArgs& g, const TensorMap& map_a, const TensorMap& map_w, cudaStream_t st) {
@@ -707,7 +715,7 @@ void gemm_tc(const GemmArgs& g, const TensorMap& map_a, const TensorMap& map_w, 
   const int sms = sm_count();
   if (g_force_bn < 0) { const char* v = getenv("PARAKEET_B200_GEMM_BN"); g_force_bn = v ? atoi(v) : 0; }
   if (g_two_cta < 0) { const char* v = getenv("PARAKEET_B200_GEMM_2CTA"); g_two_cta = v ? atoi(v) : 1; }
-  const bool two_cta = g.epi.mode != EPI_ARGMAX && !(g.epi.mode == EPI_PARTIAL_F32 && g.epi.splits > 1 && !g.epi.pair_split) &&
+  const bool two_cta = g.epi.mode != EPI_ARGMAX && g.epi.mode != EPI_ACT && g.batch == 1 && !(g.epi.mode == EPI_PARTIAL_F32 && g.epi.splits > 1 && !g.epi.pair_split) &&
                        (g_force_bn == 512 || (g_force_bn == 0 && g_two_cta != 0 && pick_two_cta(g.M, g.N, g.K, sms)));
   if (two_cta) {
     const int pair_tiles = ((g.M + 255) / 256) * ((g.N + 255) / 256) * (g.epi.mode == EPI_PARTIAL_F32 ? g.epi.splits : 1);
@@ -725,8 +733,8 @@ void gemm_tc(const GemmArgs& g, const TensorMap& map_a, const TensorMap& map_w, 
     }
     return;
   }
-  const int bn = g_force_bn == 128 || g_force_bn == 256 ? g_force_bn : pick_bn(g.M, g.N, sms);
-  const int tiles = ((g.M + BM - 1) / BM) * ((g.N + bn - 1) / bn);
+  const int bn = g.batch > 1 ? 128 : g_force_bn == 128 || g_force_bn == 256 ? g_force_bn : pick_bn(g.M, g.N, sms);
+  const int tiles = ((g.M + BM - 1) / BM) * ((g.N + bn - 1) / bn) * g.batch;
   const int grid = tiles < sms ? tiles : sms;
   const int lo_row_off = (int)(g.a_lo_off / g.lda);
   const CUtensorMap& ma = *reinterpret_cast<const CUtensorMap*>(&map_a);
@@ -739,6 +747,7 @@ void gemm_tc(const GemmArgs& g, const TensorMap& map_a, const TensorMap& map_w, 
       break;
     PKB_GEMM_CASE(EPI_BIAS_F32) PKB_GEMM_CASE(EPI_BIAS_RELU_F32) PKB_GEMM_CASE(EPI_BIAS_RELU_ACT) PKB_GEMM_CASE(EPI_BIAS_ROWMAP_F32)
     PKB_GEMM_CASE(EPI_SILU_ACT) PKB_GEMM_CASE(EPI_RESADD_F32) PKB_GEMM_CASE(EPI_QKV) PKB_GEMM_CASE(EPI_GLU_F32) PKB_GEMM_CASE(EPI_F32)
+    PKB_GEMM_CASE(EPI_ACT)
 #undef PKB_GEMM_CASE
     case EPI_PARTIAL_F32: {   // split-K: 128-wide tiles, one work unit per (tile, split)
       const int units = ((g.M + BM - 1) / BM) * ((g.N + 127) / 128) * g.epi.splits;
