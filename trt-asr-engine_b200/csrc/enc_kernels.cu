@@ -45,12 +45,14 @@ void launch_build_rows(const BatchDev& b, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------ subsampling stage 1
-// One CTA per (entry, t2).  7 input rows -> conv0 (3 rows x 64 x 32ch at a time, in smem) -> depthwise -> 32 x 256 outputs.
+// One CTA per (entry, t2).  7 input rows -> conv0 (3 rows x 64 x 32 channels at a time, in smem) -> depthwise -> 32 x 256 outputs.
+// Register tiling: a thread owns 2 adjacent channels and 4 adjacent conv0 columns, so the 9 inputs it loads per (row, tap row)
+// feed 24 FMAs (the shared-memory loads, not the FMAs, bound the first version of this kernel).
 __global__ void __launch_bounds__(256)
 subsample_stage1_kernel(BatchDev b, const float* __restrict__ feat_ring, int ring_cap, SubsampleWeights w, ActOut a1) {
   pdl_enter();
-  __shared__ float s_in[7][kNMels + 2];        // [row][f+1], zero padded
-  __shared__ float s_y0[3][66][33];            // [t1 row][f1+1][c] (+1 pad column against bank conflicts)
+  __shared__ float s_in[7][kNMels + 2];                 // [row][f+1], zero padded
+  __shared__ __align__(8) float s_y0[3][66][34];        // [t1 row][f1+1][c]  (pitch 34: 8-byte aligned channel pairs)
   const int g = blockIdx.x;
   const int e = find_entry(b.off2, b.B, g);
   const int t2 = g - b.off2[e];
@@ -66,47 +68,64 @@ subsample_stage1_kernel(BatchDev b, const float* __restrict__ feat_ring, int rin
     if (t >= 0 && t < T && f >= 0 && f < kNMels) v = ring[(size_t)((f0 + t) % ring_cap) * kNMels + f];
     s_in[r][fp] = v;
   }
-  const int c_l = tid & 31, fgrp = tid >> 5;   // channel within group, 8 f-groups
+  const int cp = tid & 15, fgrp = tid >> 4;      // channel pair within the 32-channel group, 16 groups of 4 conv0 columns
   for (int cg = 0; cg < kSubCh / 32; ++cg) {
-    const int c = cg * 32 + c_l;
-    float k0[9], k2[9];
+    const int c = cg * 32 + 2 * cp;
+    float k0[2][9], k2[2][9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { k0[i] = w.w0[c * 9 + i]; k2[i] = w.w2[c * 9 + i]; }
-    const float bias0 = w.b0[c], bias2 = w.b2[c];
+    for (int i = 0; i < 9; ++i) {
+      k0[0][i] = w.w0[c * 9 + i]; k0[1][i] = w.w0[(c + 1) * 9 + i];
+      k2[0][i] = w.w2[c * 9 + i]; k2[1][i] = w.w2[(c + 1) * 9 + i];
+    }
+    const float bias0[2] = {w.b0[c], w.b0[c + 1]}, bias2[2] = {w.b2[c], w.b2[c + 1]};
     __syncthreads();   // s_in ready (first iteration) / previous s_y0 consumers done
-    // conv0 + ReLU for t1 = 2*t2-1 .. 2*t2+1
+    // conv0 + ReLU for t1 = 2*t2-1 .. 2*t2+1, columns f1 = 4*fgrp .. 4*fgrp+3
 #pragma unroll
     for (int r1 = 0; r1 < 3; ++r1) {
       const int t1 = 2 * t2 - 1 + r1;
       const bool row_ok = t1 >= 0 && t1 < T1;
-      for (int i = 0; i < 8; ++i) {
-        const int f1 = fgrp + 8 * i;
-        float acc = 0.0f;
-        if (row_ok) {
-          acc = bias0;
+      float acc[4][2];
 #pragma unroll
-          for (int dt = 0; dt < 3; ++dt)
+      for (int i = 0; i < 4; ++i) { acc[i][0] = bias0[0]; acc[i][1] = bias0[1]; }
 #pragma unroll
-            for (int df = 0; df < 3; ++df)
-              acc = fmaf(k0[dt * 3 + df], s_in[2 * r1 + dt][2 * f1 + df], acc);   // input row 2*t1-1+dt == local 2*r1+dt
-          acc = fmaxf(acc, 0.0f);
-        }
-        s_y0[r1][f1 + 1][c_l] = acc;
+      for (int dt = 0; dt < 3; ++dt) {
+        float in[9];                                   // padded inputs 8*fgrp .. 8*fgrp+8 of row 2*r1+dt
+#pragma unroll
+        for (int x = 0; x < 9; ++x) in[x] = s_in[2 * r1 + dt][8 * fgrp + x];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int df = 0; df < 3; ++df) {
+            acc[i][0] = fmaf(k0[0][dt * 3 + df], in[2 * i + df], acc[i][0]);
+            acc[i][1] = fmaf(k0[1][dt * 3 + df], in[2 * i + df], acc[i][1]);
+          }
       }
-      if (tid < 64) { s_y0[r1][(tid >> 5) * 65][c_l] = 0.0f; }   // f1 = -1 and f1 = 64 padding columns
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 v = row_ok ? make_float2(fmaxf(acc[i][0], 0.0f), fmaxf(acc[i][1], 0.0f)) : make_float2(0.f, 0.f);
+        *reinterpret_cast<float2*>(&s_y0[r1][4 * fgrp + i + 1][2 * cp]) = v;
+      }
+      if (tid < 32) {                                   // f1 = -1 and f1 = 64 padding columns
+        s_y0[r1][0][tid] = 0.0f;
+        s_y0[r1][65][tid] = 0.0f;
+      }
     }
     __syncthreads();
-    // depthwise conv.2 (3x3, s2, p1): f2 = fgrp + 8*i
+    // depthwise conv.2 (3x3, s2, p1): f2 = 2*fgrp, 2*fgrp+1
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int f2 = fgrp + 8 * i;
-      float acc = bias2;
+    for (int i = 0; i < 2; ++i) {
+      const int f2 = 2 * fgrp + i;
+      float a0 = bias2[0], a1v = bias2[1];
 #pragma unroll
       for (int dt = 0; dt < 3; ++dt)
 #pragma unroll
-        for (int df = 0; df < 3; ++df)
-          acc = fmaf(k2[dt * 3 + df], s_y0[dt][2 * f2 + df][c_l], acc);            // y0 col 2*f2-1+df == padded 2*f2+df
-      store_act(a1.ptr, (size_t)g * 32 + f2, a1.lda, c, acc, a1.lo_off);
+        for (int df = 0; df < 3; ++df) {
+          const float2 y = *reinterpret_cast<const float2*>(&s_y0[dt][2 * f2 + df][2 * cp]);      // y0 col 2*f2-1+df == padded 2*f2+df
+          a0 = fmaf(k2[0][dt * 3 + df], y.x, a0);
+          a1v = fmaf(k2[1][dt * 3 + df], y.y, a1v);
+        }
+      store_act(a1.ptr, (size_t)g * 32 + f2, a1.lda, c, a0, a1.lo_off);
+      store_act(a1.ptr, (size_t)g * 32 + f2, a1.lda, c + 1, a1v, a1.lo_off);
     }
   }
 }
@@ -120,7 +139,7 @@ void launch_subsample_stage1(const BatchDev& b, const float* feat_ring, int ring
 // ------------------------------------------------------------------------------------------------ subsampling stage 2
 // One CTA per (entry, t3); thread == channel (256), loop over 16 output frequency bins.
 __global__ void __launch_bounds__(256)
-subsample_stage2_kernel(BatchDev b, const float* __restrict__ y1, SubsampleWeights w, ActOut a2) {
+subsample_stage2_kernel(BatchDev b, ActOut y1, SubsampleWeights w, ActOut a2) {
   pdl_enter();
   const int g = blockIdx.x;
   const int e = find_entry(b.off3, b.B, g);
@@ -131,7 +150,7 @@ subsample_stage2_kernel(BatchDev b, const float* __restrict__ y1, SubsampleWeigh
 #pragma unroll
   for (int i = 0; i < 9; ++i) k[i] = w.w5[c * 9 + i];
   const float bias = w.b5[c];
-  const float* base = y1 + (size_t)b.off2[e] * 32 * kSubCh;   // [T2][32][256]
+  const __nv_bfloat16* base = y1.ptr + (size_t)b.off2[e] * 32 * kSubCh;   // [T2][32][256]
   for (int f3 = 0; f3 < 16; ++f3) {
     float acc = bias;
 #pragma unroll
@@ -142,13 +161,16 @@ subsample_stage2_kernel(BatchDev b, const float* __restrict__ y1, SubsampleWeigh
       for (int df = 0; df < 3; ++df) {
         const int f2 = 2 * f3 - 1 + df;
         if (f2 < 0 || f2 >= 32) continue;
-        acc = fmaf(k[dt * 3 + df], base[((size_t)t2 * 32 + f2) * kSubCh + c], acc);
+        const size_t idx = ((size_t)t2 * 32 + f2) * kSubCh + c;
+        float yv = __bfloat162float(base[idx]);
+        if (y1.lo_off) yv += __bfloat162float(base[idx + y1.lo_off]);
+        acc = fmaf(k[dt * 3 + df], yv, acc);
       }
     }
     store_act(a2.ptr, (size_t)g * 16 + f3, a2.lda, c, acc, a2.lo_off);
   }
 }
-void launch_subsample_stage2(const BatchDev& b, const float* y1, const SubsampleWeights& w, ActOut a2, cudaStream_t st) {
+void launch_subsample_stage2(const BatchDev& b, ActOut y1, const SubsampleWeights& w, ActOut a2, cudaStream_t st) {
   if (b.sumT3 <= 0) return;
   launch_k(subsample_stage2_kernel, dim3(b.sumT3), dim3(256), 0, st, b, y1, w, a2);
   PKB_CUDA(cudaGetLastError());

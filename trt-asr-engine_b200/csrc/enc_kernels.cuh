@@ -50,8 +50,9 @@ void launch_build_rows(const BatchDev& b, cudaStream_t st);
 // conv0(1->256,3x3,s2,p1)+ReLU fused with depthwise conv.2 (3x3,s2,p1): feature ring -> A1 [sumT2*32, 256]
 void launch_subsample_stage1(const BatchDev& b, const float* feat_ring, int ring_cap, const SubsampleWeights& w, ActOut a1,
                              cudaStream_t st);
-// depthwise conv.5 over y1 f32 [sumT2*32, 256] (channels-last) -> A2 [sumT3*16, 256]
-void launch_subsample_stage2(const BatchDev& b, const float* y1, const SubsampleWeights& w, ActOut a2, cudaStream_t st);
+// depthwise conv.5 over y1 [sumT2*32, 256] (channels-last; bf16 hi plane [+ lo plane in precise mode], as written by the pointwise
+// GEMM's EPI_BIAS_RELU_ACT epilogue) -> A2 [sumT3*16, 256]
+void launch_subsample_stage2(const BatchDev& b, ActOut y1, const SubsampleWeights& w, ActOut a2, cudaStream_t st);
 
 // LayerNorm over rows of x f32 [M,1024] (one warp per row, eps 1e-5).
 //  write_x == 0:  A <- LN1(x)

@@ -200,12 +200,12 @@ struct Engine::Impl {
   int *n_emitted = nullptr, *y_id = nullptr;
   // work buffers
   int Mcap = 0, Bcap = 0, T3cap = 0, T2cap = 0;
-  ActBuf a_sub1, a_sub2, a_sub3, a_ln, a_ff, a_xf, a_hid, a_pred, a_g, a_imp, a_pos;
+  ActBuf a_y1, a_sub1, a_sub2, a_sub3, a_ln, a_ff, a_xf, a_hid, a_pred, a_g, a_imp, a_pos;
   __nv_bfloat16* q_bf16 = nullptr;       // bf16 mode: [2][q_rows,1024] (q + pos_bias_u | q + pos_bias_v), q_rows = Mcap padded to 128
   long long q_plane = 0;                 //           elements between the planes
   TensorMap map_qv;                      //           TMA map over the q + pos_bias_v plane (A operand of the position-score GEMM)
   __nv_bfloat16* g_pos = nullptr;        //           position scores [q_rows][8][kPosRowsPad] bf16
-  float *x = nullptr, *q = nullptr, *cglu = nullptr, *y1 = nullptr, *enc_proj = nullptr, *logits = nullptr, *gates = nullptr,
+  float *x = nullptr, *q = nullptr, *cglu = nullptr, *enc_proj = nullptr, *logits = nullptr, *gates = nullptr,
         *enc_out = nullptr, *ppos_tmp = nullptr, *scratch_f32 = nullptr, *part_val = nullptr, *dur_logits = nullptr;
   int* part_idx = nullptr;
   float* part_ws = nullptr;              // split-K partial sums [4][part_rows][1024] (deferred residual)
@@ -554,7 +554,7 @@ void Engine::alloc_state() {
     im.g_pos = dev_alloc<__nv_bfloat16>(q_rows * kHeads * kPosRowsPad);
   }
   im.cglu = dev_alloc<float>((size_t)im.Mcap * kDModel);
-  im.y1 = dev_alloc<float>((size_t)im.T2cap * 32 * kSubCh);
+  im.a_y1 = make_act(im.T2cap * 32, kSubCh, split, st_);
   im.enc_proj = dev_alloc<float>((size_t)std::max(im.Mcap, rows_dec) * kJointH);
   im.logits = dev_alloc<float>((size_t)rows_dec * kJointOut);
   im.gates = dev_alloc<float>((size_t)rows_dec * 4 * kPredH);
@@ -985,9 +985,9 @@ void Engine::run_encoder(const BatchDev& b) {
   // ---- pre-encode ----
   launch_subsample_stage1(b, im.feat_ring, kFeatRing, im.sub, im.a_sub1.out(), st_); ++launches_;
   g_tc_site = 1;
-  { EpiParams e; e.mode = EPI_BIAS_RELU_F32; e.out_f32 = im.y1; e.ldo = kSubCh; e.bias = im.sub_pw1_b;
+  { EpiParams e; e.mode = EPI_BIAS_RELU_ACT; e.out_act = im.a_y1.ptr; e.lda_out = kSubCh; e.lo_off_out = im.a_y1.lo_off; e.bias = im.sub_pw1_b;
     RUN_GEMM(im.a_sub1, im.sub_pw1, b.sumT2 * 32, nullptr, e); }
-  launch_subsample_stage2(b, im.y1, im.sub, im.a_sub2.out(), st_); ++launches_;
+  launch_subsample_stage2(b, im.a_y1.out(), im.sub, im.a_sub2.out(), st_); ++launches_;
   g_tc_site = 2;
   { EpiParams e; e.mode = EPI_BIAS_RELU_ACT; e.out_act = im.a_sub3.ptr; e.lda_out = kSubCh; e.lo_off_out = im.a_sub3.lo_off;
     e.bias = im.sub_pw2_b;
