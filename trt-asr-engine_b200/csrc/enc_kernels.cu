@@ -137,7 +137,7 @@ void launch_subsample_stage1(const BatchDev& b, const float* feat_ring, int ring
 }
 
 // ------------------------------------------------------------------------------------------------ subsampling stage 2
-// One CTA per (entry, t3); thread == channel (256), loop over 16 output frequency bins.
+// One CTA (256 threads) per (entry, t3): thread = (channel quad, output-bin quarter); 8-byte loads of 4 adjacent bf16 channels.
 __global__ void __launch_bounds__(256)
 subsample_stage2_kernel(BatchDev b, ActOut y1, SubsampleWeights w, ActOut a2) {
   pdl_enter();
@@ -145,14 +145,19 @@ subsample_stage2_kernel(BatchDev b, ActOut y1, SubsampleWeights w, ActOut a2) {
   const int e = find_entry(b.off3, b.B, g);
   const int t3 = g - b.off3[e];
   const int T2 = b.T2[e];
-  const int c = threadIdx.x;
-  float k[9];
+  const int c = 4 * (threadIdx.x & 63), fq = threadIdx.x >> 6;      // channels c..c+3, output bins f3 = 4*fq .. 4*fq+3
+  float k[4][9], bias[4];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) k[i] = w.w5[c * 9 + i];
-  const float bias = w.b5[c];
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) k[j][i] = w.w5[(c + j) * 9 + i];
+    bias[j] = w.b5[c + j];
+  }
   const __nv_bfloat16* base = y1.ptr + (size_t)b.off2[e] * 32 * kSubCh;   // [T2][32][256]
-  for (int f3 = 0; f3 < 16; ++f3) {
-    float acc = bias;
+#pragma unroll
+  for (int i3 = 0; i3 < 4; ++i3) {
+    const int f3 = 4 * fq + i3;
+    float acc[4] = {bias[0], bias[1], bias[2], bias[3]};
 #pragma unroll
     for (int dt = 0; dt < 3; ++dt) {
       const int t2 = 2 * t3 - 1 + dt;
@@ -162,12 +167,22 @@ subsample_stage2_kernel(BatchDev b, ActOut y1, SubsampleWeights w, ActOut a2) {
         const int f2 = 2 * f3 - 1 + df;
         if (f2 < 0 || f2 >= 32) continue;
         const size_t idx = ((size_t)t2 * 32 + f2) * kSubCh + c;
-        float yv = __bfloat162float(base[idx]);
-        if (y1.lo_off) yv += __bfloat162float(base[idx + y1.lo_off]);
-        acc = fmaf(k[dt * 3 + df], yv, acc);
+        const uint2 raw = *reinterpret_cast<const uint2*>(base + idx);
+        float2 p0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+        float2 p1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+        if (y1.lo_off) {
+          const uint2 lo = *reinterpret_cast<const uint2*>(base + idx + y1.lo_off);
+          const float2 l0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lo.x));
+          const float2 l1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lo.y));
+          p0.x += l0.x; p0.y += l0.y; p1.x += l1.x; p1.y += l1.y;
+        }
+        acc[0] = fmaf(k[0][dt * 3 + df], p0.x, acc[0]);
+        acc[1] = fmaf(k[1][dt * 3 + df], p0.y, acc[1]);
+        acc[2] = fmaf(k[2][dt * 3 + df], p1.x, acc[2]);
+        acc[3] = fmaf(k[3][dt * 3 + df], p1.y, acc[3]);
       }
     }
-    store_act(a2.ptr, (size_t)g * 16 + f3, a2.lda, c, acc, a2.lo_off);
+    store_act4(a2.ptr, (size_t)g * 16 + f3, a2.lda, c, make_float4(acc[0], acc[1], acc[2], acc[3]), a2.lo_off);
   }
 }
 void launch_subsample_stage2(const BatchDev& b, ActOut y1, const SubsampleWeights& w, ActOut a2, cudaStream_t st) {
