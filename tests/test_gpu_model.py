@@ -289,6 +289,24 @@ def test_decode_many_streams_fused_argmax(model_small, oracle_small, features_re
         assert same >= 0.9 * total, f"{same}/{total} chunks identical"
 
 
+def test_debug_tdt_steps_trace(model_small, features_ref, capfd, monkeypatch):
+    """PARAKEET_DEBUG_TDT_STEPS=N prints the first N decode steps in the reference's stderr format, the one
+    tools/verify_nemo/compare_tdt_trace.py:43-66 parses."""
+    import re
+    monkeypatch.setenv("PARAKEET_DEBUG_TDT_STEPS", "5")
+    f = _feats(features_ref, 2.0, 8)
+    s = binding.ParakeetSessionSafe(model_small, 0, use_fp16=False)
+    for b, e in streaming_schedule(4):
+        s.push_features(f[:, b:e], e - b)
+    s.close()
+    err = capfd.readouterr().err
+    rx = re.compile(r"tdt_step time_idx=(\d+) u=(\d+) best_tok=(\d+) best_dur_idx=(\d+) duration=(\d+) advance=(\d+) blank=(\d) blank_dur0_clamped=(\d)")
+    rows = [tuple(int(x) for x in m.groups()) for m in rx.finditer(err)]
+    assert len(rows) == 5
+    for t, u, tok, di, dur, adv, blank, clamped in rows:
+        assert 0 <= t < 3 and blank == int(tok == 8192) and di == dur and adv == (1 if clamped else dur) and clamped == int(blank and dur == 0)
+
+
 def test_engine_destroy_releases_memory(model_small):
     """create / destroy cycles (what parakeet_create_session / parakeet_destroy_session do per session) must not leak device memory."""
     def cycle():

@@ -5,6 +5,7 @@
 //   poll -> strings owned by the session until the next poll (:3860-3876); PARTIAL_TEXT at most every 100 ms of wall
 //   clock when the token count changed (:3680-3712); FINAL_TEXT per push only when PARAKEET_EMIT_FINAL_EACH_CHUNK is set
 //   (default off for a streaming encoder, :3802-3815); exceptions never cross the ABI.
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -83,6 +84,7 @@ struct ParakeetSession {
   std::string last_text, last_err;
   size_t last_partial_tokens = 0;
   std::chrono::steady_clock::time_point last_partial_emit;
+  uint64_t dbg_steps_left = 0;   // PARAKEET_DEBUG_TDT_STEPS: decode steps still to be traced on stderr
   bool offline = false;      // PARAKEET_B200_ENCODER=offline: the reference's non-streaming encoder engine
   std::string dbg_id;
   uint64_t dbg_utt = 0, dbg_chunk = 0, dbg_feat = 0;
@@ -109,6 +111,7 @@ ParakeetSession* parakeet_create_session(const ParakeetConfig* config) {
     const char* mode = std::getenv("PARAKEET_B200_ENCODER");
     s->offline = mode && std::string(mode) == "offline";
     if (s->offline) s->eng->set_stream_offline(s->sid, true);
+    s->dbg_steps_left = (uint64_t)std::max(0L, env_long("PARAKEET_DEBUG_TDT_STEPS", 0));
     s->last_partial_emit = std::chrono::steady_clock::now() - std::chrono::milliseconds(1000);
     return s;
   } catch (const std::exception& e) {
@@ -143,6 +146,21 @@ static void push_one_chunk(ParakeetSession* s, const float* feats, size_t T) {
   s->eng->queue_features(s->sid, feats, (int)T);
   s->eng->step();
   const std::vector<int>& toks = s->eng->tokens(s->sid);
+  if (s->dbg_steps_left > 0) {
+    // decode trace in the line format the reference prints and tools/verify_nemo/compare_tdt_trace.py:43-66 parses
+    // (--cpp-stderr): the first PARAKEET_DEBUG_TDT_STEPS steps of the session (parakeet_trt.cpp:2874)
+    int prev_t = -1, u = 0;
+    for (const pkb::StepRecord& r : s->eng->last_chunk(s->sid).steps) {
+      if (s->dbg_steps_left == 0) break;
+      u = r.time_idx == prev_t ? u + 1 : 0;
+      prev_t = r.time_idx;
+      const bool blank = r.token == pkb::kBlank, clamped = blank && r.duration == 0;
+      std::cerr << "[parakeet_trt] tdt_step time_idx=" << r.time_idx << " u=" << u << " best_tok=" << r.token << " best_dur_idx=" << r.duration
+                << " duration=" << r.duration << " advance=" << (clamped ? 1 : r.duration) << " blank=" << (blank ? 1 : 0)
+                << " blank_dur0_clamped=" << (clamped ? 1 : 0) << "\n";
+      --s->dbg_steps_left;
+    }
+  }
   const auto now = std::chrono::steady_clock::now();
   if (now - s->last_partial_emit >= std::chrono::milliseconds(100)) {
     if (toks.size() != s->last_partial_tokens) {
