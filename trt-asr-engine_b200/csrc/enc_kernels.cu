@@ -236,7 +236,16 @@ layernorm_kernel(float* __restrict__ x, int M, const float* __restrict__ g1, con
     for (int i = 0; i < 8; ++i) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int sp = 0; sp < res.splits; ++sp) {
-        const float4 t = *reinterpret_cast<const float4*>(res.part + (size_t)sp * res.split_stride + (size_t)row * kDModel + i * 128 + lane * 4);
+        const size_t off = (size_t)sp * res.split_stride + (size_t)row * kDModel + i * 128 + lane * 4;
+        float4 t;
+        if (res.bf16) {
+          const uint2 raw = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(res.part) + off);
+          const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+          const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+          t = make_float4(lo.x, lo.y, hi.x, hi.y);
+        } else {
+          t = *reinterpret_cast<const float4*>(res.part + off);
+        }
         acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
       }
       v[4 * i] += res.scale * acc.x; v[4 * i + 1] += res.scale * acc.y; v[4 * i + 2] += res.scale * acc.z; v[4 * i + 3] += res.scale * acc.w;

@@ -60,7 +60,7 @@ void launch_subsample_stage2(const BatchDev& b, ActOut y1, const SubsampleWeight
 //                 norm_feed_forward1; after the last layer A is the joint's encoder-projection operand)
 //  acache != null: LN1(x) rows are also stored in the contract cache ring (cache_last_channel, pre-projection)
 // deferred residual (split-K GEMM partial sums, see gemm.h EPI_PARTIAL_F32): x += scale * sum_s part[s]
-struct LnResidual { const float* part; int splits; long long split_stride; float scale; };
+struct LnResidual { const float* part; int splits; long long split_stride; float scale; int bf16; };   // bf16: partials are bf16 elements
 struct AcacheOut { void* ring; int is_f32; const int* row_entry; const int* row_pos; const int* entry_slot; const int* entry_head; };
 void launch_layernorm(float* x, int M, const float* g1, const float* b1, const float* g2, const float* b2, int write_x, ActOut a,
                       const AcacheOut* ac, cudaStream_t st, const LnResidual* res = nullptr);

@@ -61,6 +61,7 @@ struct EpiParams {
   const float* bias_v = nullptr;
   int splits = 1;                   // EPI_PARTIAL_F32: number of k-splits
   int part_rows = 0;                //                  rows per split in the workspace
+  int part_bf16 = 0;                //                  1: partial sums stored as bf16 (bf16 mode; halves the workspace traffic)
   int pair_split = 0;               //                  1: the split count was chosen for the CTA-pair kernel (256 x 256 tiles)
   float* part_val = nullptr;        // EPI_ARGMAX: [M][kArgmaxParts]
   int* part_idx = nullptr;

@@ -148,7 +148,8 @@ __device__ __forceinline__ void epilogue_quad(const EpiParams& p, int m, int ctx
   if constexpr (MODE == EPI_F32) {
     *reinterpret_cast<float4*>(p.out_f32 + (size_t)m * p.ldo + nn) = v;
   } else if constexpr (MODE == EPI_PARTIAL_F32) {
-    *reinterpret_cast<float4*>(p.out_f32 + (size_t)ctx * p.ldo + nn) = v;
+    if (p.part_bf16) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out_f32) + (size_t)ctx * p.ldo + nn) = pack4_bf16(v.x, v.y, v.z, v.w);
+    else *reinterpret_cast<float4*>(p.out_f32 + (size_t)ctx * p.ldo + nn) = v;
   } else if constexpr (MODE == EPI_BIAS_F32 || MODE == EPI_BIAS_RELU_F32 || MODE == EPI_BIAS_ROWMAP_F32) {
     const float4 b = *reinterpret_cast<const float4*>(p.bias + nn);
     v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
