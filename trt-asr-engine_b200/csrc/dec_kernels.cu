@@ -159,7 +159,7 @@ lstm_cell_kernel(DecodeDev d, int layer) {
 __global__ void decode_begin_kernel(DecodeDev d) {
   pdl_enter();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e == 0) { *d.n_active = 0; *d.m_pred = 0; }
+  if (e == 0) { *d.n_active = 1; *d.m_pred = 0; *d.m_joint = 0; }      // n_active > 0: the first iteration runs
   if (e >= d.B) return;
   d.t_cur[e] = 0;
   d.n_sym[e] = 0;
@@ -171,7 +171,7 @@ __global__ void decode_begin_kernel(DecodeDev d) {
 
 __global__ void decode_iter_reset_kernel(DecodeDev d) {
   pdl_enter();
-  if (threadIdx.x == 0) { *d.n_active = 0; *d.m_pred = 0; }
+  if (threadIdx.x == 0) { *d.m_joint = *d.n_active > 0 ? d.B : 0; *d.n_active = 0; *d.m_pred = 0; }
 }
 
 // priming / forced token (reset_utterance): mark entries to run the predictor on a given token

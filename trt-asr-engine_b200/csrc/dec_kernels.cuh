@@ -28,6 +28,8 @@ struct DecodeDev {
   int* steps = nullptr;           // [B][max_steps][3] = (time_idx, token, duration)
   int* n_active = nullptr;        // scalar: entries still active after the last select
   int* m_pred = nullptr;          // scalar: B if any entry emitted in this iteration else 0 (device-side GEMM M)
+  int* m_joint = nullptr;         // scalar: B while any entry is still active at the start of the iteration else 0 (joint GEMM M):
+                                  // iterations enqueued speculatively after the batch has finished cost nothing
   // tensors
   const float* enc_proj = nullptr;   // [M,640]  joint.enc(enc) + bias
   float* pred_proj = nullptr;        // [slots,640] joint.pred(g) + bias (cached per stream, refreshed on emission)

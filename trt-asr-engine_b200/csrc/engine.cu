@@ -219,7 +219,8 @@ struct Engine::Impl {
   int *t_cur = nullptr, *n_sym = nullptr, *active = nullptr, *emit_tok = nullptr, *pred_rowmap = nullptr, *n_steps = nullptr,
       *steps = nullptr, *counters = nullptr, *force_toks = nullptr;
   int* res_host = nullptr;               // pinned: [Bcap] n_steps + [Bcap*32*3] steps
-  int* counters_host = nullptr;          // pinned [2]
+  int* counters_host = nullptr;          // pinned [4]: n_active of the last two decode iterations at [0] and [2]
+  cudaEvent_t dec_events[2] = {nullptr, nullptr};
   // frontend staging
   float* audio_buf = nullptr;            // [slots][kAudioCap] per-stream device audio (carry + not yet framed samples)
   float* audio_tmp = nullptr;            // [slots][kAudioCap] compaction scratch
@@ -295,6 +296,7 @@ Engine::~Engine() {
   if (st_) cudaStreamSynchronize(st_);
   if (im_) {
     for (auto& e : im_->user_events) cudaEventDestroy(e);
+    for (auto& e : im_->dec_events) if (e) cudaEventDestroy(e);
     for (auto& pr : im_->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (void* p : im_->dev_allocs) cudaFree(p);
     for (void* p : im_->host_allocs) cudaFreeHost(p);
@@ -581,10 +583,11 @@ void Engine::alloc_state() {
   im.emit_tok = dev_alloc<int>(im.Bcap); im.pred_rowmap = dev_alloc<int>(im.Bcap);
   im.n_steps = dev_alloc<int>((size_t)im.Bcap * (1 + kMaxStepsOffline * 3));
   im.steps = im.n_steps + im.Bcap;
-  im.counters = dev_alloc<int>(2);
+  im.counters = dev_alloc<int>(4);
   im.force_toks = dev_alloc<int>(im.Bcap);
   host_alloc(&im.res_host, (size_t)im.Bcap * (1 + kMaxStepsOffline * 3) * sizeof(int));
-  host_alloc(&im.counters_host, 2 * sizeof(int));
+  host_alloc(&im.counters_host, 4 * sizeof(int));
+  for (auto& e : im.dec_events) PKB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   // audio: per-stream device buffers + one staging area for batched host pushes (8192 samples per stream per push)
   im.audio_buf = dev_alloc<float>((size_t)S * kAudioCap);
   im.audio_tmp = dev_alloc<float>((size_t)S * kAudioCap);
@@ -1133,16 +1136,22 @@ void Engine::run_decode(const BatchDev& b, const std::vector<Entry>& entries) {
     if (d.fused_argmax) {      // tensor-core joint: greedy selection fused into the epilogue, logits never leave the SM
       EpiParams e; e.mode = EPI_ARGMAX; e.bias = im.joint_out_b; e.part_val = im.part_val; e.part_idx = im.part_idx;
       e.dur_out = im.dur_logits; e.blank_penalty = opt_.blank_penalty;
-      RUN_GEMM(im.a_hid, im.joint_out, b.B, nullptr, e);
+      RUN_GEMM(im.a_hid, im.joint_out, b.B, d.m_joint, e);
     } else {
       EpiParams e; e.mode = EPI_BIAS_F32; e.out_f32 = im.logits; e.ldo = kJointOut; e.bias = im.joint_out_b;
-      RUN_GEMM(im.a_hid, im.joint_out, b.B, nullptr, e);
+      RUN_GEMM(im.a_hid, im.joint_out, b.B, d.m_joint, e);
     }
     launch_tdt_select(d, st_); ++launches_;
-    PKB_CUDA(cudaMemcpyAsync(im.counters_host, im.counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, st_));
+    // The host only needs "is anybody still active?".  Iteration it+1 is enqueued BEFORE the answer of iteration it is awaited,
+    // so the GPU never idles on the round trip; the one iteration enqueued after the batch has finished sees m_joint == 0 and
+    // m_pred == 0 and does nothing.
+    PKB_CUDA(cudaMemcpyAsync(im.counters_host + 2 * (it & 1), im.counters, sizeof(int), cudaMemcpyDeviceToHost, st_));
+    PKB_CUDA(cudaEventRecord(im.dec_events[it & 1], st_));
     run_predictor_pass(d);
-    PKB_CUDA(cudaStreamSynchronize(st_));
-    if (im.counters_host[0] == 0) break;
+    if (it >= 1) {
+      PKB_CUDA(cudaEventSynchronize(im.dec_events[(it - 1) & 1]));
+      if (im.counters_host[2 * ((it - 1) & 1)] == 0) break;
+    }
   }
 }
 
@@ -1151,7 +1160,7 @@ static DecodeDev make_decode_dev(Engine::Impl& im, const EngineOptions& opt, int
   d.B = B; d.max_symbols = kMaxSymbols; d.punct_suppress = opt.punct_suppress; d.blank_penalty = opt.blank_penalty;
   d.slot = slot; d.row_off = row_off; d.t_enc = t_enc;
   d.t_cur = im.t_cur; d.n_sym = im.n_sym; d.active = im.active; d.emit_tok = im.emit_tok; d.pred_rowmap = im.pred_rowmap;
-  d.n_steps = im.n_steps; d.steps = im.steps; d.n_active = im.counters; d.m_pred = im.counters + 1;
+  d.n_steps = im.n_steps; d.steps = im.steps; d.n_active = im.counters; d.m_pred = im.counters + 1; d.m_joint = im.counters + 2;
   d.enc_proj = im.enc_proj; d.pred_proj = im.pred_proj; d.logits = im.logits; d.gates = im.gates; d.embed = im.embed;
   d.part_val = im.part_val; d.part_idx = im.part_idx; d.dur_logits = im.dur_logits;
   d.punct_bits = im.punct_bits; d.pred_h = im.pred_h; d.pred_c = im.pred_c; d.pred_g = im.pred_g; d.n_emitted = im.n_emitted;
