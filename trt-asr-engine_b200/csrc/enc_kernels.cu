@@ -434,6 +434,10 @@ dwconv_kernel(BatchDev b, DwConvArgs a) {
 #pragma unroll
   for (int i = 0; i < kConvK; ++i) w[i] = a.w[ch * kConvK + i];
   const float bias = a.bias[ch];
+  auto ld_c = [&](int t) -> float {
+    const size_t i = (size_t)(row0 + t) * kDModel + ch;
+    return a.c_bf16 ? __bfloat162float(a.c_bf16[i]) : a.c[i];
+  };
   // ext = [cache(4) | c(Tq, zero past qlen: pad_mask) | 0 0 0 0]; sliding window of 9
   const bool offline = b.offline[e] != 0;      // offline: zero left context (symmetric 4/4 padding), cache untouched
   const float4 cv = offline ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(cache);
@@ -442,7 +446,7 @@ dwconv_kernel(BatchDev b, DwConvArgs a) {
 #pragma unroll
   for (int i = 4; i < kConvK; ++i) {
     const int t = i - 4;
-    win[i] = (t < Tq && t < qlen) ? a.c[(size_t)(row0 + t) * kDModel + ch] : 0.0f;
+    win[i] = (t < Tq && t < qlen) ? ld_c(t) : 0.0f;
   }
   // new cache = ext[Tq+1 .. Tq+5)   (new_x[:-3][-4:], cache_drop_size 3)
   float nc[4];
@@ -451,7 +455,7 @@ dwconv_kernel(BatchDev b, DwConvArgs a) {
     const int idx = Tq + 1 + i;                 // index into ext
     float v = 0.0f;
     if (idx < 4) v = idx == 0 ? cv.x : idx == 1 ? cv.y : idx == 2 ? cv.z : cv.w;
-    else if (idx - 4 < Tq) v = (idx - 4 < qlen) ? a.c[(size_t)(row0 + idx - 4) * kDModel + ch] : 0.0f;
+    else if (idx - 4 < Tq) v = (idx - 4 < qlen) ? ld_c(idx - 4) : 0.0f;
     nc[i] = v;
   }
   for (int t = 0; t < Tq; ++t) {
@@ -463,7 +467,7 @@ dwconv_kernel(BatchDev b, DwConvArgs a) {
 #pragma unroll
     for (int i = 0; i < kConvK - 1; ++i) win[i] = win[i + 1];
     const int tn = t + 5;                       // next ext index t+1+8 -> c index t+5
-    win[kConvK - 1] = (tn < Tq && tn < qlen) ? a.c[(size_t)(row0 + tn) * kDModel + ch] : 0.0f;
+    win[kConvK - 1] = (tn < Tq && tn < qlen) ? ld_c(tn) : 0.0f;
   }
   if (!offline) *reinterpret_cast<float4*>(cache) = make_float4(nc[0], nc[1], nc[2], nc[3]);
 }

@@ -94,7 +94,8 @@ void launch_attention_mma(const BatchDev& b, const AttnMmaArgs& a, cudaStream_t 
 
 // Conv-module middle: depthwise k=9 over [time cache(4) | c(Tq) | 0000], folded BatchNorm, SiLU; updates the time cache.
 struct DwConvArgs {
-  const float* c;          // post-GLU activations f32 [M,1024]
+  const float* c;          // post-GLU activations f32 [M,1024] (precise mode), or
+  const __nv_bfloat16* c_bf16;   // ... bf16 [M,1024] (bf16 mode); exactly one of the two is non-null
   float* cache_tm;         // this layer's time cache [slot][1024][4]  (stride between slots passed separately)
   long long slot_stride;   // floats between consecutive slots of cache_tm
   const float* w;          // [1024,9] depthwise weights with BN scale folded in

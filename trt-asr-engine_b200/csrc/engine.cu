@@ -1082,8 +1082,9 @@ void Engine::run_encoder(const BatchDev& b) {
     launch_layernorm(im.x, M, w.n_conv_g, w.n_conv_b, nullptr, nullptr, 0, im.a_ln.out(), nullptr, st_, &res); ++launches_;
     g_tc_site = 1024;
     { EpiParams e; e.mode = EPI_GLU_F32; e.out_f32 = im.cglu; e.ldo = kDModel;
+      if (!split) { e.out_act = reinterpret_cast<__nv_bfloat16*>(im.cglu); e.lda_out = kDModel; }      // bf16 mode: bf16 elements in the same buffer
       RUN_GEMM(im.a_ln, w.pw1, M, nullptr, e); }
-    { DwConvArgs a; a.c = im.cglu; a.cache_tm = im.cache_tm + (size_t)l * kDModel * kTimeCtx; a.slot_stride = (long long)L_ * kDModel * kTimeCtx;
+    { DwConvArgs a; a.c = split ? im.cglu : nullptr; a.c_bf16 = split ? nullptr : reinterpret_cast<const __nv_bfloat16*>(im.cglu); a.cache_tm = im.cache_tm + (size_t)l * kDModel * kTimeCtx; a.slot_stride = (long long)L_ * kDModel * kTimeCtx;
       a.w = w.dw_w; a.bias = w.dw_b; a.out = im.a_ln.out();
       launch_dwconv(b, a, st_); ++launches_; }
     g_tc_site = 2048;

@@ -130,7 +130,8 @@ __device__ __forceinline__ void epilogue_pair(const EpiParams& p, int m, int n, 
       break;
     }
     case EPI_GLU_F32:
-      p.out_f32[(size_t)m * p.ldo + (n >> 1)] = v0 * sigmoidf_(v1);
+      if (p.out_act) p.out_act[(size_t)m * p.lda_out + (n >> 1)] = __float2bfloat16_rn(v0 * sigmoidf_(v1));
+      else p.out_f32[(size_t)m * p.ldo + (n >> 1)] = v0 * sigmoidf_(v1);
       break;
     case EPI_QKV: {
       if (n < kDModel && p.q_bf16) {

@@ -171,7 +171,13 @@ __device__ __forceinline__ void epilogue_quad(const EpiParams& p, int m, int ctx
     x.x += p.scale * v.x; x.y += p.scale * v.y; x.z += p.scale * v.z; x.w += p.scale * v.w;
     *o = x;
   } else if constexpr (MODE == EPI_GLU_F32) {
-    *reinterpret_cast<float2*>(p.out_f32 + (size_t)m * p.ldo + (nn >> 1)) = make_float2(v.x * sigmoidf_(v.y), v.z * sigmoidf_(v.w));
+    const float g0 = v.x * sigmoidf_(v.y), g1 = v.z * sigmoidf_(v.w);
+    if (p.out_act) {      // bf16 mode: the depthwise kernel reads bf16
+      const __nv_bfloat162 h = __floats2bfloat162_rn(g0, g1);
+      *reinterpret_cast<uint32_t*>(p.out_act + (size_t)m * p.lda_out + (nn >> 1)) = *reinterpret_cast<const uint32_t*>(&h);
+    } else {
+      *reinterpret_cast<float2*>(p.out_f32 + (size_t)m * p.ldo + (nn >> 1)) = make_float2(g0, g1);
+    }
   } else if constexpr (MODE == EPI_QKV) {
     if (nn < kDModel) {
       if (p.q_bf16) {
