@@ -129,9 +129,142 @@ subsample_stage1_kernel(BatchDev b, const float* __restrict__ feat_ring, int rin
     }
   }
 }
+// ------------------------------------------------------------------------------------------------ stage 1 on tensor cores (bf16 mode)
+// Same mapping (one CTA per (entry, t2)), but conv0 -- 192 positions x 256 channels x 9 taps -- runs as mma.sync m16n8k16
+// (K = 9 taps padded to 16): A fragments are im2col patches built from the staged input rows, B fragments the bf16 filter
+// taps, f32 accumulation, bias + ReLU on the accumulator fragments.  The CUDA-core version spends ~0.85 ms per 1024-stream
+// step on this conv; here it is a few dozen MMAs per warp.  Channels are processed in two halves of 128 to keep the
+// conv0 output tile (bf16 [3][66][128+8]) at 54 KB.
+namespace {
+constexpr int kS1Half = 128;                  // channels per pass
+constexpr int kS1Pitch = kS1Half + 8;         // bf16 elements per (row, column) cell: 272 B -> conflict-free fragment stores
+__device__ __forceinline__ uint32_t pack_bf16x2_f(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+}  // namespace
+
+__global__ void __launch_bounds__(256, 3)
+subsample_stage1_mma_kernel(BatchDev b, const float* __restrict__ feat_ring, int ring_cap, SubsampleWeights w, ActOut a1) {
+  pdl_enter();
+  extern __shared__ __align__(16) unsigned char s1_raw[];
+  float (*s_in)[kNMels + 2] = reinterpret_cast<float (*)[kNMels + 2]>(s1_raw);                        // [7][130]
+  __nv_bfloat16* s_y0 = reinterpret_cast<__nv_bfloat16*>(s1_raw + 7 * (kNMels + 2) * 4 + 8);          // [3][66][kS1Pitch]
+  const int g = blockIdx.x;
+  const int e = find_entry(b.off2, b.B, g);
+  const int t2 = g - b.off2[e];
+  const int T = b.T[e], T1 = b.T1[e];
+  const float* ring = feat_ring + (size_t)b.slot[e] * ring_cap * kNMels;
+  const int f0 = b.f0[e];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, t = lane & 3;
+
+  for (int i = tid; i < 7 * (kNMels + 2); i += 256) {
+    const int r = i / (kNMels + 2), fp = i % (kNMels + 2);
+    const int tt = 4 * t2 - 3 + r, f = fp - 1;
+    float v = 0.0f;
+    if (tt >= 0 && tt < T && f >= 0 && f < kNMels) v = ring[(size_t)((f0 + tt) % ring_cap) * kNMels + f];
+    s_in[r][fp] = v;
+  }
+  // zero the f1 = -1 / 64 padding columns of the conv0 tile once (both passes reuse them)
+  for (int i = tid; i < 3 * 2 * kS1Pitch; i += 256) {
+    const int r1 = i / (2 * kS1Pitch), rest = i % (2 * kS1Pitch);
+    s_y0[(r1 * 66 + (rest / kS1Pitch) * 65) * kS1Pitch + rest % kS1Pitch] = __float2bfloat16_rn(0.0f);
+  }
+  __syncthreads();
+
+  // A fragments: m-tile mt covers row r1 = mt / 4, columns f1 = 16 (mt % 4) + {gq, gq + 8}; k index = tap 3 dt + df
+  // lane t holds taps (2t, 2t+1) [a0: row gq, a1: row gq+8] and, for t == 0, tap 8 [a2, a3]
+  uint32_t af[12][4];
+  {
+    const int k0 = 2 * t, k1 = 2 * t + 1;
+    const int dt0 = k0 / 3, df0 = k0 % 3, dt1 = k1 / 3, df1 = k1 % 3;
+#pragma unroll
+    for (int mt = 0; mt < 12; ++mt) {
+      const int r1 = mt >> 2, fb = 16 * (mt & 3);
+#pragma unroll
+      for (int hr = 0; hr < 2; ++hr) {
+        const int f1 = fb + gq + 8 * hr;
+        af[mt][hr] = pack_bf16x2_f(s_in[2 * r1 + dt0][2 * f1 + df0], s_in[2 * r1 + dt1][2 * f1 + df1]);
+        af[mt][2 + hr] = t == 0 ? pack_bf16x2_f(s_in[2 * r1 + 2][2 * f1 + 2], 0.0f) : 0u;
+      }
+    }
+  }
+
+#pragma unroll 1
+  for (int half = 0; half < kSubCh / kS1Half; ++half) {
+    if (half) __syncthreads();      // the depthwise stage of the previous pass is done with s_y0
+    // conv0 + bias + ReLU: warp w owns channels [half*128 + 16 w, +16) = 2 n-tiles
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const int cl = 16 * warp + 8 * nt;                      // channel offset inside the half
+      const int cB = half * kS1Half + cl + gq;                 // B fragment: channel = n index = gq
+      const uint32_t b0 = pack_bf16x2_f(w.w0[cB * 9 + 2 * t], w.w0[cB * 9 + 2 * t + 1]);
+      const uint32_t b1 = t == 0 ? pack_bf16x2_f(w.w0[cB * 9 + 8], 0.0f) : 0u;
+      const int cC = half * kS1Half + cl + 2 * t;              // C fragment: channels 2t, 2t+1
+      const float bias0 = w.b0[cC], bias1 = w.b0[cC + 1];
+#pragma unroll
+      for (int mt = 0; mt < 12; ++mt) {
+        float c[4] = {bias0, bias1, bias0, bias1};
+        mma_bf16_16816(c, af[mt], b0, b1);
+        const int r1 = mt >> 2, fb = 16 * (mt & 3);
+        const bool row_ok = (2 * t2 - 1 + r1) >= 0 && (2 * t2 - 1 + r1) < T1;
+#pragma unroll
+        for (int hr = 0; hr < 2; ++hr) {
+          const int f1 = fb + gq + 8 * hr;
+          const uint32_t v = row_ok ? pack_bf16x2_f(fmaxf(c[2 * hr], 0.0f), fmaxf(c[2 * hr + 1], 0.0f)) : 0u;
+          *reinterpret_cast<uint32_t*>(s_y0 + ((r1 * 66) + f1 + 1) * kS1Pitch + cl + 2 * t) = v;
+        }
+      }
+    }
+    __syncthreads();
+    // depthwise conv.2 (3x3, s2, p1) on CUDA cores: thread = (channel pair cp of 64, quarter fq of the 32 output bins)
+    {
+      const int cp = tid & 63, fq = tid >> 6;
+      const int c = half * kS1Half + 2 * cp;
+      float k2[2][9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) { k2[0][i] = w.w2[c * 9 + i]; k2[1][i] = w.w2[(c + 1) * 9 + i]; }
+      const float bias2[2] = {w.b2[c], w.b2[c + 1]};
+#pragma unroll 2
+      for (int i = 0; i < 8; ++i) {
+        const int f2 = 8 * fq + i;
+        float a0 = bias2[0], a1v = bias2[1];
+#pragma unroll
+        for (int dt = 0; dt < 3; ++dt)
+#pragma unroll
+          for (int df = 0; df < 3; ++df) {
+            const __nv_bfloat162 y = *reinterpret_cast<const __nv_bfloat162*>(s_y0 + ((dt * 66) + 2 * f2 + df) * kS1Pitch + 2 * cp);
+            const float2 yf = __bfloat1622float2(y);
+            a0 = fmaf(k2[0][dt * 3 + df], yf.x, a0);
+            a1v = fmaf(k2[1][dt * 3 + df], yf.y, a1v);
+          }
+        const __nv_bfloat162 o = __floats2bfloat162_rn(a0, a1v);
+        *reinterpret_cast<__nv_bfloat162*>(a1.ptr + ((size_t)g * 32 + f2) * a1.lda + c) = o;      // bf16 mode: hi plane only
+      }
+    }
+  }
+}
+
 void launch_subsample_stage1(const BatchDev& b, const float* feat_ring, int ring_cap, const SubsampleWeights& w, ActOut a1,
                              cudaStream_t st) {
   if (b.sumT2 <= 0) return;
+  static const bool use_mma = [] { const char* v = getenv("PARAKEET_B200_SUB_MMA"); return !(v && v[0] == '0'); }();
+  if (a1.lo_off == 0 && use_mma) {      // bf16 mode: conv0 on tensor cores
+    constexpr size_t smem = 7 * (kNMels + 2) * 4 + 8 + (size_t)3 * 66 * kS1Pitch * 2;
+    static bool attr = false;
+    if (!attr) {
+      PKB_CUDA(cudaFuncSetAttribute(subsample_stage1_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+    }
+    launch_k(subsample_stage1_mma_kernel, dim3(b.sumT2), dim3(256), smem, st, b, feat_ring, ring_cap, w, a1);
+    return;
+  }
   launch_k(subsample_stage1_kernel, dim3(b.sumT2), dim3(256), 0, st, b, feat_ring, ring_cap, w, a1);
   PKB_CUDA(cudaGetLastError());
 }
