@@ -28,7 +28,7 @@ B200_SYMBOLS = ["pkb_last_error", "pkb_version", "pkb_engine_create", "pkb_engin
                 "pkb_engine_kernel_launches", "pkb_stream_open", "pkb_stream_close", "pkb_stream_reset", "pkb_stream_push_features",
                 "pkb_stream_push_audio", "pkb_stream_set_feature_norm", "pkb_stream_set_offline", "pkb_encoder_offline_step", "pkb_engine_push_audio_batch",
                 "pkb_engine_push_audio_batch_device", "pkb_engine_event_record", "pkb_engine_event_elapsed_ms",
-                "pkb_engine_profile_enable", "pkb_engine_profile_read", "pkb_engine_step", "pkb_stream_has_pending",
+                "pkb_engine_profile_enable", "pkb_engine_profile_read", "pkb_engine_profile_read_class", "pkb_engine_step", "pkb_stream_has_pending",
                 "pkb_stream_num_tokens", "pkb_stream_tokens", "pkb_stream_last_steps", "pkb_stream_cache_len",
                 "pkb_stream_chunks_done", "pkb_stream_text", "pkb_detokenize", "pkb_stream_import_state", "pkb_stream_export_state",
                 "pkb_stream_set_decoder_state", "pkb_stream_get_decoder_state", "pkb_encoder_streaming_step", "pkb_predictor_step",
@@ -118,6 +118,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.pkb_engine_event_elapsed_ms.restype = C.c_double
     lib.pkb_engine_profile_enable.argtypes = [vp, C.c_int32]
     lib.pkb_engine_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), lp]
+    lib.pkb_engine_profile_read_class.argtypes = [vp, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), lp]
     lib.pkb_stream_tokens.argtypes = [vp, C.c_int32, ip, C.c_int32]
     lib.pkb_stream_last_steps.argtypes = [vp, C.c_int32, C.POINTER(PkbStep), C.c_int32]
     lib.pkb_stream_text.argtypes = [vp, C.c_int32, C.c_char_p, C.c_int32]
@@ -281,6 +282,12 @@ class Engine:
         ms, fl, n = C.c_double(), C.c_double(), C.c_int64()
         self._chk(self._lib.pkb_engine_profile_read(self._e, C.byref(ms), C.byref(fl), C.byref(n)))
         return ms.value, fl.value, n.value
+
+    def profile_read_class(self, cls: int):
+        """cls 0: tcgen05 GEMM (work = FLOPs); 1: attention; 2: log-mel frontend (work = algorithmic bytes)."""
+        ms, wk, n = C.c_double(), C.c_double(), C.c_int64()
+        self._chk(self._lib.pkb_engine_profile_read_class(self._e, cls, C.byref(ms), C.byref(wk), C.byref(n)))
+        return ms.value, wk.value, n.value
 
     def step(self) -> int:
         return self._chk(self._lib.pkb_engine_step(self._e))

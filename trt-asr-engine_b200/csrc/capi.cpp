@@ -382,7 +382,11 @@ double pkb_engine_event_elapsed_ms(PkbEngine* e, int32_t a, int32_t b) {
 int32_t pkb_engine_profile_enable(PkbEngine* e, int32_t on) { PKB_ENTER(e); return guarded([&] { e->eng->profile_enable(on != 0); return 0; }); }
 int32_t pkb_engine_profile_read(PkbEngine* e, double* ms, double* flops, int64_t* launches) {
   PKB_ENTER(e);
-  return guarded([&] { long long l = 0; e->eng->profile_read(ms, flops, &l); *launches = l; return 0; });
+  return guarded([&] { long long l = 0; e->eng->profile_read(0, ms, flops, &l); *launches = l; return 0; });
+}
+int32_t pkb_engine_profile_read_class(PkbEngine* e, int32_t cls, double* ms, double* work, int64_t* launches) {
+  PKB_ENTER(e);
+  return guarded([&] { long long l = 0; e->eng->profile_read(cls, ms, work, &l); *launches = l; return 0; });
 }
 int32_t pkb_engine_step(PkbEngine* e) { PKB_ENTER(e); return guarded([&] { return e->eng->step(); }); }
 int32_t pkb_stream_has_pending(PkbEngine* e, int32_t s) { PKB_ENTER(e); return guarded([&] { return e->eng->has_pending(s) ? 1 : 0; }); }

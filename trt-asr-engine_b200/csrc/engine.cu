@@ -233,10 +233,11 @@ struct Engine::Impl {
   // optional per-launch timing of the tensor-core GEMM (bench roofline)
   bool profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
-  std::vector<double> prof_flops;
+  std::vector<double> prof_flops;        // algorithmic work of the bracketed launch: FLOPs (class 0) or bytes (classes 1, 2)
+  std::vector<int> prof_class;           // 0 = tcgen05 GEMM, 1 = attention, 2 = log-mel frontend
   size_t prof_used = 0;
-  double prof_ms = 0, prof_flops_sum = 0;
-  long long prof_launches = 0;
+  double prof_ms[3] = {0, 0, 0}, prof_work[3] = {0, 0, 0};
+  long long prof_launches[3] = {0, 0, 0};
   FrontSegment* segs_dev = nullptr;
   FrontSegment* segs_host = nullptr;
   int* fprefix_dev = nullptr;
@@ -325,22 +326,44 @@ void Engine::profile_enable(bool on) {
   PKB_CUDA(cudaStreamSynchronize(st_));
   im_->profile = on;
   im_->prof_used = 0;
-  im_->prof_ms = im_->prof_flops_sum = 0;
-  im_->prof_launches = 0;
+  for (int c = 0; c < 3; ++c) { im_->prof_ms[c] = im_->prof_work[c] = 0; im_->prof_launches[c] = 0; }
+}
+// profile mode: bracket the next launch with two CUDA events on the engine stream
+int Engine::prof_begin(int cls, double work) {
+  Impl& im = *im_;
+  if (!im.profile) return -1;
+  if (im.prof_used == im.prof_events.size()) {
+    cudaEvent_t a0, a1;
+    PKB_CUDA(cudaEventCreate(&a0));
+    PKB_CUDA(cudaEventCreate(&a1));
+    im.prof_events.emplace_back(a0, a1);
+    im.prof_flops.push_back(0.0);
+    im.prof_class.push_back(0);
+  }
+  const int i = (int)im.prof_used++;
+  im.prof_flops[i] = work;
+  im.prof_class[i] = cls;
+  PKB_CUDA(cudaEventRecord(im.prof_events[i].first, st_));
+  return i;
+}
+void Engine::prof_end(int i) {
+  if (i >= 0) PKB_CUDA(cudaEventRecord(im_->prof_events[i].second, st_));
 }
 void Engine::profile_collect() {      // call after a synchronised step
   Impl& im = *im_;
   for (size_t i = 0; i < im.prof_used; ++i) {
     float ms = 0;
     PKB_CUDA(cudaEventElapsedTime(&ms, im.prof_events[i].first, im.prof_events[i].second));
-    im.prof_ms += ms;
-    im.prof_flops_sum += im.prof_flops[i];
-    im.prof_launches += 1;
+    const int c = im.prof_class[i];
+    im.prof_ms[c] += ms;
+    im.prof_work[c] += im.prof_flops[i];
+    im.prof_launches[c] += 1;
   }
   im.prof_used = 0;
 }
-void Engine::profile_read(double* ms, double* flops, long long* launches) {
-  *ms = im_->prof_ms; *flops = im_->prof_flops_sum; *launches = im_->prof_launches;
+void Engine::profile_read(int cls, double* ms, double* work, long long* launches) {
+  PKB_CHECK(cls >= 0 && cls < 3, "profile class");
+  *ms = im_->prof_ms[cls]; *work = im_->prof_work[cls]; *launches = im_->prof_launches[cls];
 }
 
 // ------------------------------------------------------------------------------------------------ weights
@@ -867,8 +890,10 @@ void Engine::frontend_pass() {
   im.fprefix_host[n_segs] = total_frames;
   PKB_CUDA(cudaMemcpyAsync(im.segs_dev, im.segs_host, n_segs * sizeof(FrontSegment), cudaMemcpyHostToDevice, st_));
   PKB_CUDA(cudaMemcpyAsync(im.fprefix_dev, im.fprefix_host, (n_segs + 1) * sizeof(int), cudaMemcpyHostToDevice, st_));
+  const int pi = prof_begin(2, (double)total_frames * (kNMels * 4.0 + 160 * 4.0));      // 640 B of new samples read + 512 B written per frame
   im.frontend.logmel(im.audio_buf, im.segs_dev, im.fprefix_dev, n_segs, total_frames, im.feat_ring, im.norm_stats, sm_count_, st_);
   ++launches_;
+  prof_end(pi);
   for (auto& d : done) {
     Stream& s = *streams_[d.first];
     s.dev_off += d.second * 160;     // stays even
@@ -957,24 +982,9 @@ static void run_gemm(Engine* eng, const EngineOptions& opt, cudaStream_t st, lon
   bool want_tc = opt.gemm_backend == 2 || (opt.gemm_backend == 0 && M > 16);
   if (tc_mask() >= 0 && !(tc_mask() & g_tc_site)) want_tc = false;
   if (want_tc && lda_override <= 0 && gemm_tc_supported(g)) {
-    Engine::Impl* im = eng->impl();
-    if (im->profile) {
-      if (im->prof_used == im->prof_events.size()) {
-        cudaEvent_t a0, a1;
-        PKB_CUDA(cudaEventCreate(&a0));
-        PKB_CUDA(cudaEventCreate(&a1));
-        im->prof_events.emplace_back(a0, a1);
-        im->prof_flops.push_back(0.0);
-      }
-      auto& ev = im->prof_events[im->prof_used];
-      im->prof_flops[im->prof_used] = 2.0 * (double)M * w.N * w.K;   // ALGORITHMIC flops (the split pass is not counted twice)
-      ++im->prof_used;
-      PKB_CUDA(cudaEventRecord(ev.first, st));
-      gemm_tc(g, a.map, w.map, st);
-      PKB_CUDA(cudaEventRecord(ev.second, st));
-    } else {
-      gemm_tc(g, a.map, w.map, st);
-    }
+    const int pi = eng->prof_begin(0, 2.0 * (double)M * w.N * w.K);   // ALGORITHMIC flops (the split pass is not counted twice)
+    gemm_tc(g, a.map, w.map, st);
+    eng->prof_end(pi);
   } else {
     gemm_simt(g, st);
   }
@@ -1070,7 +1080,10 @@ void Engine::run_encoder(const BatchDev& b) {
         gemm_tc(g, im.map_qv, w.ppos_map, st_); ++launches_; }
       AttnMmaArgs a; a.q_bf16 = im.q_bf16; a.q_plane = im.q_plane; a.g_pos = im.g_pos; a.ctx = im.a_ln.out();
       a.map_k = &im.map_k; a.map_v = &im.map_v; a.layer = l; a.n_slots = opt_.max_streams;
+      // algorithmic bytes: the valid K and V rows of every (stream, head): 2 x (256 + Tq) x 128 x 2 B (steady state; early chunks less)
+      const int pi = prof_begin(1, (double)b.B * kHeads * 2.0 * (kCacheS + b.max_Tq) * kDHead * 2.0);
       launch_attention_mma(b, a, st_); ++launches_;
+      prof_end(pi);
     } else {
       AttnArgs a; a.q = im.q; a.kring = kr; a.vring = vr; a.ppos_t = w.ppos_t; a.kv_f32 = 1; a.bias_u = w.bias_u;
       a.bias_v = w.bias_v; a.ctx = im.a_ln.out();

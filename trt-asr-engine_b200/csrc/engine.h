@@ -105,7 +105,9 @@ class Engine {
   double event_elapsed_ms(int a, int b);
   void profile_enable(bool on);
   void profile_collect();
-  void profile_read(double* ms, double* flops, long long* launches);
+  void profile_read(int cls, double* ms, double* work, long long* launches);   // cls 0: tcgen05 GEMM (work = FLOPs), 1: attention, 2: frontend (bytes)
+  int prof_begin(int cls, double work);
+  void prof_end(int idx);
 
   struct Stream;
   struct Impl;
