@@ -125,6 +125,21 @@ int32_t pkb_encoder_streaming_step(PkbEngine* engine, int32_t B, int32_t T, cons
  * encoded_lengths [B]; T_enc = three times floor((L-1)/2)+1. */
 int32_t pkb_encoder_offline_step(PkbEngine* engine, int32_t B, int32_t T, const float* audio_signal, const int64_t* length,
                                  float* encoder_output, int64_t* encoded_lengths);
+/* Whole-utterance offline path: what the reference's non-streaming `encoder` graph computes when its time axis is dynamic
+ * (contracts/parakeet-tdt-0.6b-v3.contract.json:67-96 -- the ONNX export run by tools/onnxruntime, BASELINE configs 1 and 5;
+ * the TensorRT build of the same graph is capped at T <= 256 by its profile, contract.json:284-287), followed by the greedy TDT
+ * loop of cpp/src/parakeet_trt.cpp:2914-3676 over every encoder frame.  n utterances, utterance i bound to the freshly opened /
+ * reset stream streams[i].  Input: either audio (audio[i]: n_samples[i] samples of 16 kHz f32 PCM; log-mel and, if
+ * per_feature_norm != 0, the whole-utterance normalisation of rust/features run on the GPU) or features (features[i]: n_frames[i]
+ * frames, [128,T] bins-major if bins_major != 0 else [T,128]); the other pair is NULL.  Self-attention spans ALL frames of an
+ * utterance; the sum of encoder frames (T/8 each) must fit the engine's max_rows.  encoder_output (NULL, or per-utterance
+ * pointers, each NULL or [1024, T_enc_i] f32) receives the encoder output in the contract layout; decode != 0 fills
+ * pkb_stream_tokens / pkb_stream_last_steps of each stream.  Host pointers. */
+int32_t pkb_offline_utterances(PkbEngine* engine, int32_t n, const int32_t* streams, const float* const* audio,
+                               const size_t* n_samples, int32_t per_feature_norm, const float* const* features,
+                               const int32_t* n_frames, int32_t bins_major, float* const* encoder_output, int32_t decode);
+/* encoder frames produced for T feature frames: three times floor((L-1)/2)+1 */
+int32_t pkb_encoded_length(int32_t n_frames);
 /* predictor: y [B,1] i64, h,c [2,B,640] -> g [B,640,1], h_out,c_out [2,B,640] */
 int32_t pkb_predictor_step(PkbEngine* engine, int32_t B, const int64_t* y, const float* h, const float* c, float* g, float* h_out,
                            float* c_out);

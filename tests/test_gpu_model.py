@@ -289,6 +289,40 @@ def test_decode_many_streams_fused_argmax(model_small, oracle_small, features_re
         assert same >= 0.9 * total, f"{same}/{total} chunks identical"
 
 
+def test_audio_mode_schedule_and_reset(eng, features_ref):
+    """Audio pushed in arbitrary pieces is framed on the GPU and cut by the 41/57-frame schedule
+    (streaming_encoder_reference.py:522-550): the traces equal those of a stream fed the same GPU log-mel frames through
+    push_features by that schedule -- and again after pkb_stream_reset (== parakeet_reset_utterance: the schedule restarts at
+    chunk 0)."""
+    from synth_audio import synth_clip
+    pcm = synth_clip(3.0, 321)
+    feats = np.ascontiguousarray(eng.logmel(pcm).T)            # [128,T], same kernel as the streaming frontend
+    n_chunks = 1 + (feats.shape[1] - 41) // 24
+    ref = eng.open()
+    want = []
+    for b, e in streaming_schedule(n_chunks):
+        if e > feats.shape[1]:
+            break
+        eng.push_features(ref, feats[:, b:e])
+        assert eng.step() == 1
+        want.append(eng.last_steps(ref))
+    want_tokens = eng.tokens(ref)
+    eng.close_stream(ref)
+    assert len(want) >= 8
+    s = eng.open()
+    for rep in range(2):
+        got = []
+        for lo in range(0, pcm.size, 5000):
+            eng.push_audio(s, pcm[lo:lo + 5000])
+            while eng.step():
+                got.append(eng.last_steps(s))
+        assert got == want[:len(got)] and len(got) >= len(want) - 1, (rep, len(got), len(want))
+        if len(got) == len(want):
+            assert eng.tokens(s) == want_tokens
+        eng.reset(s)
+    eng.close_stream(s)
+
+
 def test_debug_tdt_steps_trace(model_small, features_ref, capfd, monkeypatch):
     """PARAKEET_DEBUG_TDT_STEPS=N prints the first N decode steps in the reference's stderr format, the one
     tools/verify_nemo/compare_tdt_trace.py:43-66 parses."""

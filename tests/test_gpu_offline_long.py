@@ -1,0 +1,146 @@
+"""Whole-utterance offline path (pkb_offline_utterances; BASELINE configs 1 and 5) on the GPU vs the oracle's offline():
+full self-attention over ALL frames of an utterance, symmetric conv padding, greedy TDT over every encoder frame.
+
+Tolerances: those of test_gpu_model.py (precise: 2e-3; bf16: p95 3e-2 / max 1.5e-1, x2 as for the <=256-frame offline engine).
+Decode traces: precise mode identical; bf16 mode identical up to the first decision whose top-2 logit gap is below TAU (a
+decision that close is ambiguous for any bf16 implementation, see test_gpu_parity_set.py), and that prefix must be non-trivial.
+"""
+import numpy as np
+import pytest
+import torch
+
+import binding
+from conftest import normalized_features
+from model_ref import DecodeState, ModelRef, prime, tdt_greedy_chunk
+from synth_audio import synth_clip
+
+pytestmark = pytest.mark.gpu
+TAU = 0.25
+
+
+def _feats(features_ref, seconds, seed):
+    f = normalized_features(features_ref, seconds, seed)
+    f[0] = 0.0    # empty mel filter 0 (summation-noise column, see test_oracle_features)
+    return f
+
+
+def _tol(prec, scale):
+    p95, mx = (2e-3, 2e-3) if prec == 1 else (3e-2, 1.5e-1)
+    return p95 * scale, mx * scale
+
+
+def _check(got, want, prec, what, scale=2.0):
+    d = np.abs(got - want)
+    p95, mx = _tol(prec, scale)
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    assert np.percentile(d, 95) <= p95 and d.max() <= mx, (what, float(np.percentile(d, 95)), float(d.max()))
+
+
+def _oracle_trace(m, enc, t_enc):
+    st = DecodeState(m)
+    prime(m, st)
+    mg = []
+    tr = [(t, tok, d) for t, tok, d, _ in tdt_greedy_chunk(m, st, enc, t_enc, margins=mg)]
+    amb = next((i for i, (a, b) in enumerate(mg) if a <= TAU or b <= TAU), len(tr))
+    return tr, st.tokens, amb
+
+
+def _check_trace(got, want, amb, prec, what):
+    if prec == 1:
+        assert got == want, (what, "first difference at", next((i for i, (a, b) in enumerate(zip(got, want)) if a != b), min(len(got), len(want))))
+    else:
+        assert got[:amb] == want[:amb], (what, amb, next((i for i, (a, b) in enumerate(zip(got, want)) if a != b), -1))
+
+
+@pytest.mark.parametrize("prec", [1, 0], ids=["precise", "bf16"])
+def test_two_utterances_ragged(model_small, oracle_small, features_ref, prec):
+    """Two utterances of different length in one call (10 s -> 125 encoder frames, 31 s -> 388: several 64-row tiles and ragged
+    tails), features in the contract's bins-major layout; every utterance equals the oracle run on it alone."""
+    m = oracle_small
+    eng = binding.Engine(model_small, max_streams=2, precision=prec, max_rows=640)
+    fs = [_feats(features_ref, 10.0, 1234), _feats(features_ref, 31.0, 77)]
+    sids = [eng.open(), eng.open()]
+    outs = eng.offline_utterances(sids, features=fs, bins_major=True, want_encoder_output=True, decode=True)
+    min_amb = []
+    for i, f in enumerate(fs):
+        enc, el = m.offline(torch.from_numpy(f[None]), torch.tensor([f.shape[1]]))
+        assert outs[i].shape[1] == int(el) == binding.load_library().pkb_encoded_length(f.shape[1])
+        _check(outs[i], enc[0].numpy(), prec, f"utterance {i} encoder_output")
+        want, toks, amb = _oracle_trace(m, enc, int(el))
+        got = eng.last_steps(sids[i])
+        _check_trace(got, want, amb, prec, f"utterance {i} trace")
+        min_amb.append(amb)
+        if prec == 1:
+            assert eng.tokens(sids[i]) == toks
+    assert max(min_amb) >= 20, "margin filter left nothing to compare"
+    eng.close()
+
+
+@pytest.mark.parametrize("prec", [1, 0], ids=["precise", "bf16"])
+def test_config1_full_model_from_audio(model_full, features_ref, prec):
+    """BASELINE config 1: one synthetic 10 s 16 kHz clip, batch 1, 24 layers, audio in -> tokens out (GPU log-mel + per-feature
+    normalisation + encoder over all 998 frames + TDT).  The oracle is fed the GPU's own features (the frontend has its own
+    parity test) so this isolates encoder + decode."""
+    m = ModelRef(model_full)
+    eng = binding.Engine(model_full, max_streams=1, precision=prec, max_rows=256)
+    pcm = synth_clip(10.0, 1234)
+    f = eng.logmel(pcm, per_feature_norm=True)          # [T,128]
+    assert f.shape == (998, 128)
+    sid = eng.open()
+    outs = eng.offline_utterances([sid], audio=[pcm], per_feature_norm=True, want_encoder_output=True, decode=True)
+    enc, el = m.offline(torch.from_numpy(np.ascontiguousarray(f.T)[None]), torch.tensor([f.shape[0]]))
+    assert int(el) == 125 and outs[0].shape == (1024, 125)
+    _check(outs[0], enc[0].numpy(), prec, "config 1 encoder_output")
+    want, toks, amb = _oracle_trace(m, enc, 125)
+    _check_trace(eng.last_steps(sid), want, amb, prec, "config 1 trace")
+    if prec == 1:
+        assert eng.tokens(sid) == toks
+    # a second utterance on the same (reset) stream reproduces the first one exactly
+    first = eng.last_steps(sid)
+    eng.reset(sid)
+    eng.offline_utterances([sid], audio=[pcm], per_feature_norm=True, decode=True)
+    assert eng.last_steps(sid) == first
+    eng.close()
+
+
+@pytest.mark.parametrize("prec", [1, 0], ids=["precise", "bf16"])
+def test_four_minutes(model_small, oracle_small, features_ref, prec):
+    """240 s -> 3000 encoder frames (47 key tiles per query tile, relative positions up to +-2999)."""
+    m = oracle_small
+    eng = binding.Engine(model_small, max_streams=1, precision=prec, max_rows=3072)
+    f = _feats(features_ref, 240.0, 5)
+    sid = eng.open()
+    outs = eng.offline_utterances([sid], features=[np.ascontiguousarray(f.T)], bins_major=False, want_encoder_output=True, decode=True)
+    enc, el = m.offline(torch.from_numpy(f[None]), torch.tensor([f.shape[1]]))
+    _check(outs[0], enc[0].numpy(), prec, "4 min encoder_output")
+    want, toks, amb = _oracle_trace(m, enc, int(el))
+    _check_trace(eng.last_steps(sid), want, amb, prec, "4 min trace")
+    eng.close()
+
+
+def test_long_form_properties(model_small, features_ref):
+    """Size-independent properties at a size the oracle cannot reach in seconds (20 min, 15 000 encoder frames, bf16 mode):
+    the same clip twice in one batch gives bit-identical outputs (no cross-utterance leakage, deterministic), and a clip
+    shorter than one key tile appended to the batch matches its stand-alone result to bf16 tolerance."""
+    eng = binding.Engine(model_small, max_streams=3, precision=0, max_rows=2 * 15008 + 64)
+    f = _feats(features_ref, 1200.0, 9)
+    short = _feats(features_ref, 4.0, 10)
+    sids = [eng.open() for _ in range(3)]
+    outs = eng.offline_utterances(sids, features=[f, f, short], want_encoder_output=True, decode=True)
+    assert outs[0].shape[1] == 15000
+    assert np.array_equal(outs[0], outs[1]) and np.isfinite(outs[0]).all()
+    assert eng.last_steps(sids[0]) == eng.last_steps(sids[1]) and len(eng.last_steps(sids[0])) >= 15000 // 4
+    for s in sids:
+        eng.reset(s)
+    # (stand-alone, the small GEMMs pick another k-split, so this comparison is to bf16 tolerance, not bit-exact)
+    o2 = eng.offline_utterances([sids[0]], features=[short], want_encoder_output=True, decode=False)
+    _check(o2[0], outs[2], 0, "short utterance: batched vs alone")
+    eng.close()
+
+
+def test_capacity_error(model_small, features_ref):
+    eng = binding.Engine(model_small, max_streams=1, precision=0, max_rows=64)
+    sid = eng.open()
+    with pytest.raises(RuntimeError, match="row capacity"):
+        eng.offline_utterances([sid], features=[_feats(features_ref, 10.0, 1)], decode=False)
+    eng.close()

@@ -26,7 +26,7 @@ TRT_ASR_SYMBOLS = ["trt_asr_create_session", "trt_asr_destroy_session", "trt_asr
                    "trt_asr_push_features_f32", "trt_asr_poll_event"]
 B200_SYMBOLS = ["pkb_last_error", "pkb_version", "pkb_engine_create", "pkb_engine_destroy", "pkb_engine_num_layers",
                 "pkb_engine_kernel_launches", "pkb_stream_open", "pkb_stream_close", "pkb_stream_reset", "pkb_stream_push_features",
-                "pkb_stream_push_audio", "pkb_stream_set_feature_norm", "pkb_stream_set_offline", "pkb_encoder_offline_step", "pkb_engine_push_audio_batch",
+                "pkb_stream_push_audio", "pkb_stream_set_feature_norm", "pkb_stream_set_offline", "pkb_encoder_offline_step", "pkb_offline_utterances", "pkb_encoded_length", "pkb_engine_push_audio_batch",
                 "pkb_engine_push_audio_batch_device", "pkb_engine_event_record", "pkb_engine_event_elapsed_ms",
                 "pkb_engine_profile_enable", "pkb_engine_profile_read", "pkb_engine_profile_read_class", "pkb_engine_step", "pkb_stream_has_pending",
                 "pkb_stream_num_tokens", "pkb_stream_tokens", "pkb_stream_last_steps", "pkb_stream_cache_len",
@@ -130,6 +130,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.pkb_encoder_streaming_step.argtypes = [vp, C.c_int32, C.c_int32, fp, lp, fp, fp, lp, fp, lp, fp, fp, lp]
     lib.pkb_stream_set_offline.argtypes = [vp, C.c_int32, C.c_int32]
     lib.pkb_encoder_offline_step.argtypes = [vp, C.c_int32, C.c_int32, fp, lp, fp, lp]
+    lib.pkb_offline_utterances.argtypes = [vp, C.c_int32, ip, C.POINTER(fp), C.POINTER(C.c_size_t), C.c_int32, C.POINTER(fp), ip, C.c_int32,
+                                           C.POINTER(fp), C.c_int32]
+    lib.pkb_encoded_length.argtypes = [C.c_int32]
     lib.pkb_predictor_step.argtypes = [vp, C.c_int32, lp, fp, fp, fp, fp, fp]
     lib.pkb_joint_step.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, fp, fp, fp]
     lib.pkb_logmel.argtypes = [vp, fp, C.c_size_t, fp, C.c_size_t, C.c_int32]
@@ -302,9 +305,14 @@ class Engine:
         return out[:n].tolist()
 
     def last_steps(self, s: int) -> List[Tuple[int, int, int]]:
-        buf = (PkbStep * 320)()
-        n = self._chk(self._lib.pkb_stream_last_steps(self._e, s, buf, 320))
-        return [(buf[i].time_idx, buf[i].token, buf[i].duration) for i in range(min(n, 320))]
+        cap = 320
+        buf = (PkbStep * cap)()
+        n = self._chk(self._lib.pkb_stream_last_steps(self._e, s, buf, cap))
+        if n > cap:      # a whole-utterance decode trace
+            cap = n
+            buf = (PkbStep * cap)()
+            n = self._chk(self._lib.pkb_stream_last_steps(self._e, s, buf, cap))
+        return [(buf[i].time_idx, buf[i].token, buf[i].duration) for i in range(min(n, cap))]
 
     def cache_len(self, s: int) -> int:
         return self._chk(self._lib.pkb_stream_cache_len(self._e, s))
@@ -378,6 +386,35 @@ class Engine:
         el = np.zeros(B, np.int64)
         self._chk(self._lib.pkb_encoder_offline_step(self._e, B, T, _fptr(a), _lptr(ln), _fptr(out), _lptr(el)))
         return out, el
+
+    def offline_utterances(self, sids, audio=None, features=None, per_feature_norm: bool = True, bins_major: bool = True,
+                           want_encoder_output: bool = False, decode: bool = True):
+        """Whole-utterance offline path (pkb_offline_utterances): `audio` = list of 1-D f32 PCM arrays, or `features` = list of
+        [128,T] (bins_major) / [T,128] arrays; one freshly opened stream id per utterance.  Returns the list of
+        encoder_output [1024,T_enc] arrays (or None); tokens / decode trace through tokens(s) / last_steps(s)."""
+        n = len(sids)
+        ids = np.ascontiguousarray(sids, np.int32)
+        fpp = C.POINTER(C.c_float) * n
+        keep = []
+        a_ptrs = ns = f_ptrs = nf = None
+        t_frames = []
+        if audio is not None:
+            keep = [np.ascontiguousarray(a, np.float32) for a in audio]
+            a_ptrs = fpp(*[_fptr(a) for a in keep])
+            ns = (C.c_size_t * n)(*[a.size for a in keep])
+            t_frames = [(a.size - 400) // 160 + 1 for a in keep]
+        else:
+            keep = [np.ascontiguousarray(f, np.float32) for f in features]
+            f_ptrs = fpp(*[_fptr(f) for f in keep])
+            t_frames = [f.shape[1] if bins_major else f.shape[0] for f in keep]
+            nf = (C.c_int32 * n)(*t_frames)
+        outs = o_ptrs = None
+        if want_encoder_output:
+            outs = [np.zeros((1024, self._lib.pkb_encoded_length(t)), np.float32) for t in t_frames]
+            o_ptrs = fpp(*[_fptr(o) for o in outs])
+        self._chk(self._lib.pkb_offline_utterances(self._e, n, ids.ctypes.data_as(C.POINTER(C.c_int32)), a_ptrs, ns, int(per_feature_norm),
+                                                   f_ptrs, nf, int(bins_major), o_ptrs, int(decode)))
+        return outs
 
     def predictor_step(self, y, h, c):
         y = np.ascontiguousarray(y, np.int64)

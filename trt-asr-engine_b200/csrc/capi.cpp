@@ -461,6 +461,20 @@ int32_t pkb_encoder_offline_step(PkbEngine* e, int32_t B, int32_t T, const float
   if (!audio_signal || !length || !enc_out || !enc_len) { g_last_error = "null argument"; return -1; }
   return guarded([&] { e->eng->encoder_offline_step(B, T, audio_signal, length, enc_out, enc_len); return 0; });
 }
+int32_t pkb_offline_utterances(PkbEngine* e, int32_t n, const int32_t* streams, const float* const* audio, const size_t* n_samples,
+                               int32_t per_feature_norm, const float* const* features, const int32_t* n_frames, int32_t bins_major,
+                               float* const* encoder_output, int32_t decode) {
+  PKB_ENTER(e);
+  if (!streams || (!audio && !features)) { g_last_error = "null argument"; return -1; }
+  return guarded([&] {
+    e->eng->offline_utterances(n, streams, audio, n_samples, per_feature_norm, features, n_frames, bins_major, encoder_output, decode);
+    return 0;
+  });
+}
+int32_t pkb_encoded_length(int32_t L) {
+  for (int i = 0; i < 3; ++i) L = L <= 0 ? 0 : (L - 1) / 2 + 1;
+  return L;
+}
 int32_t pkb_predictor_step(PkbEngine* e, int32_t B, const int64_t* y, const float* h, const float* c, float* g, float* h_out, float* c_out) {
   PKB_ENTER(e);
   return guarded([&] { e->eng->predictor_step(B, y, h, c, g, h_out, c_out); return 0; });

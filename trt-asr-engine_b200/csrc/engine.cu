@@ -1,5 +1,6 @@
 // engine.cu -- see engine.h.  Host orchestration of the batched streaming step.
 #include "engine.h"
+#include "offline_long.cuh"
 
 #include <math.h>
 #include <string.h>
@@ -238,6 +239,15 @@ struct Engine::Impl {
   size_t prof_used = 0;
   double prof_ms[3] = {0, 0, 0}, prof_work[3] = {0, 0, 0};
   long long prof_launches[3] = {0, 0, 0};
+  // whole-utterance offline path (allocated on first use; see Engine::offline_utterances)
+  std::vector<GemmW> lf_wpos;            // linear_pos weights per layer (the streaming path only keeps its 320-row projected table)
+  float* lf_feat = nullptr;              // [lf_feat_frames][128] normalised log-mel frames of the utterances of one call
+  size_t lf_feat_frames = 0;
+  ActBuf lf_pos_act;                     // sinusoid table operand [2*Mcap][1024] (hi + lo planes)
+  void* lf_qkv = nullptr;                // [Mcap][3072] q | k | v  (bf16, f32 in precise mode)
+  void* lf_ppos = nullptr;               // [2*Mcap][1024] this layer's projected table (bf16 / f32)
+  int* lf_steps = nullptr;               // decode trace [B][lf_steps_per][3]
+  size_t lf_steps_ints = 0;
   FrontSegment* segs_dev = nullptr;
   FrontSegment* segs_host = nullptr;
   int* fprefix_dev = nullptr;
@@ -686,7 +696,8 @@ void Engine::reset_stream(int sid) {
   PKB_CHECK(sid >= 0 && sid < (int)streams_.size() && streams_[sid]->open, "bad stream id");
   Stream& s = *streams_[sid];
   Impl& im = *im_;
-  s.frames_written = 0; s.pending.clear(); s.audio.clear(); s.audio_mode = false;   // (s.offline is a property of the stream: kept) s.sched_chunk = 0; s.has_norm = false;
+  s.frames_written = 0; s.pending.clear(); s.audio.clear(); s.audio_mode = false;   // (s.offline is a property of the stream: kept)
+  s.sched_chunk = 0; s.has_norm = false;
   s.dev_off = 0; s.dev_fill = 0;
   s.cache_len = 0; s.head = 0; s.chunks = 0; s.tokens.clear(); s.last = ChunkResult();
   const size_t slot = (size_t)s.slot;
@@ -991,12 +1002,12 @@ static void run_gemm(Engine* eng, const EngineOptions& opt, cudaStream_t st, lon
 }
 #define RUN_GEMM(a, w, M, Mdev, epi) run_gemm(this, opt_, st_, &launches_, a, 0, w, M, Mdev, epi)
 
-void Engine::run_encoder(const BatchDev& b) {
+void Engine::run_encoder(const BatchDev& b, const LongForm* lf) {
   Impl& im = *im_;
   const bool split = opt_.precision == 1;
   launch_build_rows(b, st_); ++launches_;
   // ---- pre-encode ----
-  launch_subsample_stage1(b, im.feat_ring, kFeatRing, im.sub, im.a_sub1.out(), st_); ++launches_;
+  launch_subsample_stage1(b, lf ? im.lf_feat : im.feat_ring, lf ? (int)im.lf_feat_frames : kFeatRing, im.sub, im.a_sub1.out(), st_); ++launches_;
   g_tc_site = 1;
   { EpiParams e; e.mode = EPI_BIAS_RELU_ACT; e.out_act = im.a_y1.ptr; e.lda_out = kSubCh; e.lo_off_out = im.a_y1.lo_off; e.bias = im.sub_pw1_b;
     RUN_GEMM(im.a_sub1, im.sub_pw1, b.sumT2 * 32, nullptr, e); }
@@ -1063,8 +1074,25 @@ void Engine::run_encoder(const BatchDev& b) {
       ac.ring = (char*)im.acache + (size_t)l * im.ring_layer_elems * kv_elem; ac.is_f32 = split ? 1 : 0;
       ac.row_entry = b.row_entry; ac.row_pos = b.row_pos; ac.entry_slot = b.slot; ac.entry_head = b.head;
     }
-    launch_layernorm(im.x, M, w.n_att_g, w.n_att_b, nullptr, nullptr, 0, im.a_ln.out(), im.acache ? &ac : nullptr, st_, &res); ++launches_;
+    launch_layernorm(im.x, M, w.n_att_g, w.n_att_b, nullptr, nullptr, 0, im.a_ln.out(), (im.acache && !lf) ? &ac : nullptr, st_, &res); ++launches_;
     g_tc_site = 256;
+    if (lf) {
+      // whole-utterance attention: q | k | v rows stay in one [M,3072] buffer (no rings), the layer's projected position
+      // table linear_pos(pe) over 2Tm-1 relative positions is one more GEMM, the score tiles are formed in lf_attention
+      { EpiParams e;
+        if (split) { e.mode = EPI_F32; e.out_f32 = (float*)im.lf_qkv; e.ldo = 3 * kDModel; }
+        else { e.mode = EPI_ACT; e.out_act = (__nv_bfloat16*)im.lf_qkv; e.lda_out = 3 * kDModel; }
+        RUN_GEMM(im.a_ln, w.qkv, M, nullptr, e); }
+      { EpiParams e;
+        if (split) { e.mode = EPI_F32; e.out_f32 = (float*)im.lf_ppos; e.ldo = kDModel; }
+        else { e.mode = EPI_ACT; e.out_act = (__nv_bfloat16*)im.lf_ppos; e.lda_out = kDModel; }
+        RUN_GEMM(im.lf_pos_act, im.lf_wpos[l], 2 * lf->Tm - 1, nullptr, e); }
+      LfAttnArgs a;
+      if (split) { a.qkv_f32 = (const float*)im.lf_qkv; a.ppos_f32 = (const float*)im.lf_ppos; }
+      else { a.qkv_bf16 = (const __nv_bfloat16*)im.lf_qkv; a.ppos_bf16 = (const __nv_bfloat16*)im.lf_ppos; }
+      a.Tm = lf->Tm; a.max_T = b.max_Tq; a.bias_u = w.bias_u; a.bias_v = w.bias_v; a.ctx = im.a_ln.out();
+      launch_lf_attention(b, a, st_); ++launches_;
+    } else {
     { EpiParams e; e.mode = EPI_QKV; e.out_f32 = im.q; e.ldo = kDModel; e.row_entry = b.row_entry; e.row_pos = b.row_pos;
       e.entry_slot = b.slot; e.entry_head = b.head; e.kring = kr; e.vring = vr; e.kv_f32 = split ? 1 : 0;
       e.k_natural = im.attn_mma ? 1 : 0;
@@ -1089,6 +1117,7 @@ void Engine::run_encoder(const BatchDev& b) {
       a.bias_v = w.bias_v; a.ctx = im.a_ln.out();
       launch_attention(b, a, st_); ++launches_;
     }
+    }
     g_tc_site = 512;
     res = residual_gemm(im.a_ln, w.out, 1.0f);
     // convolution module
@@ -1097,6 +1126,11 @@ void Engine::run_encoder(const BatchDev& b) {
     { EpiParams e; e.mode = EPI_GLU_F32; e.out_f32 = im.cglu; e.ldo = kDModel;
       if (!split) { e.out_act = reinterpret_cast<__nv_bfloat16*>(im.cglu); e.lda_out = kDModel; }      // bf16 mode: bf16 elements in the same buffer
       RUN_GEMM(im.a_ln, w.pw1, M, nullptr, e); }
+    if (lf) {
+      LfDwConvArgs a; a.c = split ? im.cglu : nullptr; a.c_bf16 = split ? nullptr : reinterpret_cast<const __nv_bfloat16*>(im.cglu);
+      a.w = w.dw_w; a.bias = w.dw_b; a.out = im.a_ln.out(); a.M = M;
+      launch_lf_dwconv(b, a, st_); ++launches_;
+    } else
     { DwConvArgs a; a.c = split ? im.cglu : nullptr; a.c_bf16 = split ? nullptr : reinterpret_cast<const __nv_bfloat16*>(im.cglu); a.cache_tm = im.cache_tm + (size_t)l * kDModel * kTimeCtx; a.slot_stride = (long long)L_ * kDModel * kTimeCtx;
       a.w = w.dw_w; a.bias = w.dw_b; a.out = im.a_ln.out();
       launch_dwconv(b, a, st_); ++launches_; }
@@ -1114,7 +1148,7 @@ void Engine::run_encoder(const BatchDev& b) {
     launch_layernorm(im.x, M, w.n_out_g, w.n_out_b, last ? nullptr : im.layers[l + 1].n_ff1_g, last ? nullptr : im.layers[l + 1].n_ff1_b,
                      1, last ? im.a_xf.out() : im.a_ln.out(), nullptr, st_, &res); ++launches_;
   }
-  launch_gather_output(b, im.x, im.enc_out, b.max_tenc, st_); ++launches_;
+  if (!lf) { launch_gather_output(b, im.x, im.enc_out, b.max_tenc, st_); ++launches_; }
 }
 
 void Engine::run_predictor_pass(const DecodeDev& d) {
@@ -1132,15 +1166,15 @@ void Engine::run_predictor_pass(const DecodeDev& d) {
 
 static DecodeDev make_decode_dev(Engine::Impl& im, const EngineOptions& opt, int B, const int* slot, const int* row_off, const int* t_enc);
 
-void Engine::run_decode(const BatchDev& b, const std::vector<Entry>& entries) {
+void Engine::run_decode(const BatchDev& b, const int* slots, int* steps, int max_steps) {
   Impl& im = *im_;
-  (void)entries;
   // joint encoder projection for every packed row: E = joint.enc(x) + bias
   g_tc_site = 16;
   { EpiParams e; e.mode = EPI_BIAS_F32; e.out_f32 = im.enc_proj; e.ldo = kJointH; e.bias = im.joint_enc_b;
     RUN_GEMM(im.a_xf, im.joint_enc, b.M, nullptr, e); }
-  DecodeDev d = make_decode_dev(im, opt_, b.B, b.slot, b.row_off, im.batch_ints + 10 * im.Bcap);
+  DecodeDev d = make_decode_dev(im, opt_, b.B, slots ? slots : b.slot, b.row_off, im.batch_ints + 10 * im.Bcap);
   d.max_steps = b.max_tenc > kValidOut ? kMaxStepsOffline : kMaxStepsPerChunk;
+  if (steps) { d.steps = steps; d.max_steps = max_steps; }
   d.fused_argmax = (opt_.gemm_backend == 2 || (opt_.gemm_backend == 0 && b.B > 16)) && tc_mask() < 0 ? 1 : 0;
   launch_decode_begin(d, st_); ++launches_;
   const int max_iters = b.max_tenc * (kMaxSymbols + 1) + 2;
@@ -1226,7 +1260,7 @@ void Engine::run_batch(const std::vector<Entry>& entries, float* enc_out_host) {
   run_encoder(b);
   const bool decode = enc_out_host == nullptr;
   if (decode) {
-    run_decode(b, entries);
+    run_decode(b);
     // [Bcap] step counts, then [B][max_steps][3] records
     PKB_CUDA(cudaMemcpyAsync(im.res_host, im.n_steps, ((size_t)im.Bcap + (size_t)b.B * max_steps * 3) * sizeof(int),
                              cudaMemcpyDeviceToHost, st_));
@@ -1449,6 +1483,195 @@ void Engine::encoder_offline_step(int B, int T, const float* audio_signal, const
   for (int i = 0; i < B; ++i) {
     encoded_lengths[i] = streams_[sids[i]]->last.encoded_len;
     close_stream(sids[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ whole-utterance offline path
+// Buffers of the long-form path are created on first use (a streaming-only server never pays for them) and owned by the Engine.
+void Engine::lf_prepare(size_t total_frames, size_t steps_ints) {
+  Impl& im = *im_;
+  const bool split = opt_.precision == 1;
+  auto own = [&](void* p) { im.dev_allocs.push_back(p); return p; };
+  auto disown_free = [&](void* p) {
+    if (!p) return;
+    auto it = std::find(im.dev_allocs.begin(), im.dev_allocs.end(), p);
+    if (it != im.dev_allocs.end()) im.dev_allocs.erase(it);
+    cudaFree(p);
+  };
+  if (im.lf_wpos.empty()) {
+    WeightsFile wf(opt_.model_dir + "/weights.bin");
+    for (int l = 0; l < L_; ++l) {
+      GemmW w = upload_gemm_w(wf.bf16("encoder.layers." + std::to_string(l) + ".self_attn.linear_pos.weight"), kDModel, kDModel);
+      own(w.w);
+      im.lf_wpos.push_back(w);
+    }
+    im.lf_pos_act = make_act(2 * im.Mcap, kDModel, true, st_);
+    own(im.lf_pos_act.ptr);
+    const size_t rows = ((size_t)im.Mcap + 127) / 128 * 128;
+    im.lf_qkv = own(dev_alloc_bytes(rows * 3 * kDModel * (split ? 4 : 2)));
+    im.lf_ppos = own(dev_alloc_bytes((size_t)2 * im.Mcap * kDModel * (split ? 4 : 2)));
+  }
+  if (total_frames > im.lf_feat_frames) {
+    disown_free(im.lf_feat);
+    im.lf_feat = (float*)own(dev_alloc_bytes(total_frames * kNMels * sizeof(float)));
+    im.lf_feat_frames = total_frames;
+  }
+  if (steps_ints > im.lf_steps_ints) {
+    disown_free(im.lf_steps);
+    im.lf_steps = (int*)own(dev_alloc_bytes(steps_ints * sizeof(int)));
+    im.lf_steps_ints = steps_ints;
+  }
+}
+
+void Engine::offline_utterances(int n, const int* sids, const float* const* pcm, const size_t* n_samples, int per_feature_norm,
+                                const float* const* feats, const int* T_in, int bins_major, float* const* enc_out, int decode) {
+  Impl& im = *im_;
+  PKB_CHECK(n >= 1 && n <= im.Bcap, "offline_utterances: 1..max_streams utterances per call");
+  PKB_CHECK((pcm != nullptr) != (feats != nullptr), "offline_utterances: give either audio or features");
+  PKB_CHECK(pcm ? n_samples != nullptr : T_in != nullptr, "offline_utterances: missing lengths");
+  std::vector<int> T(n), f0(n);
+  size_t total_frames = 0;
+  for (int i = 0; i < n; ++i) {
+    PKB_CHECK(sids[i] >= 0 && sids[i] < (int)streams_.size() && streams_[sids[i]]->open, "offline_utterances: bad stream id");
+    const Stream& s = *streams_[sids[i]];
+    PKB_CHECK(s.frames_written == 0 && s.chunks == 0 && s.pending.empty(), "offline_utterances: only on a freshly opened / reset stream");
+    long long t = pcm ? (n_samples[i] >= 400 ? (long long)((n_samples[i] - 400) / 160 + 1) : 0) : T_in[i];
+    PKB_CHECK(t >= 1 && t < (1 << 28), "offline_utterances: utterance needs at least one feature frame");
+    T[i] = (int)t;
+    f0[i] = (int)total_frames;
+    total_frames += (size_t)t;
+  }
+  PKB_CHECK(total_frames < (1u << 30), "offline_utterances: too many frames in one call");
+  // ---- batch descriptor (same fields as a streaming step; every entry is one utterance, nothing dropped, no cache)
+  int* h = im.batch_ints_host;
+  const int C = im.Bcap;
+  PKB_CUDA(cudaStreamSynchronize(st_));
+  int *slot = h, *Tf = h + C, *f0h = h + 2 * C, *T1 = h + 3 * C, *T2 = h + 4 * C, *T3 = h + 5 * C, *Tq = h + 6 * C, *qlen = h + 7 * C,
+      *len = h + 8 * C, *head = h + 9 * C, *tenc = h + 10 * C, *drop = h + 11 * C, *offl = h + 12 * C;
+  int* off2 = h + kNumBatchFields * C;
+  int* off3 = off2 + (C + 1);
+  int* roff = off3 + (C + 1);
+  BatchDev b;
+  b.B = n;
+  off2[0] = off3[0] = roff[0] = 0;
+  for (int i = 0; i < n; ++i) {
+    slot[i] = 0;                              // feature base: all utterances live in the one lf_feat buffer, at frame f0
+    head[i] = streams_[sids[i]]->slot;        // (the ring head is unused here: this field carries the decoder-state slot)
+    Tf[i] = T[i]; f0h[i] = f0[i];
+    T1[i] = sub_len(T[i]); T2[i] = sub_len(T1[i]); T3[i] = sub_len(T2[i]);
+    Tq[i] = T3[i]; qlen[i] = T3[i]; len[i] = 0; tenc[i] = T3[i]; drop[i] = 0; offl[i] = 1;
+    off2[i + 1] = off2[i] + T2[i]; off3[i + 1] = off3[i] + T3[i]; roff[i + 1] = roff[i] + Tq[i];
+    b.max_Tq = std::max(b.max_Tq, Tq[i]);
+  }
+  b.max_tenc = b.max_Tq;
+  b.M = roff[n]; b.sumT2 = off2[n]; b.sumT3 = off3[n];
+  PKB_CHECK(b.M <= im.Mcap && b.sumT3 <= im.T3cap && b.sumT2 <= im.T2cap,
+            "offline_utterances: " + std::to_string(b.M) + " encoder frames exceed the engine's row capacity (max_rows = " +
+                std::to_string(im.Mcap) + ")");
+  const int steps_per = b.max_tenc * (kMaxSymbols + 1);
+  lf_prepare(total_frames, decode ? (size_t)n * steps_per * 3 : 0);
+
+  // ---- features
+  if (pcm) {
+    size_t total_samples = 0;
+    std::vector<size_t> aoff(n);
+    for (int i = 0; i < n; ++i) { aoff[i] = total_samples; total_samples += (n_samples[i] + 1) & ~(size_t)1; }   // even offsets (float2 loads)
+    float* d_audio = dev_alloc<float>(total_samples + 2);
+    FrontSegment* d_seg = dev_alloc<FrontSegment>(n);
+    int* d_ints = dev_alloc<int>(2 * n + 1);
+    float* d_stats = dev_alloc<float>((size_t)n * 2 * kNMels);
+    std::vector<FrontSegment> segs(n);
+    std::vector<int> ints(2 * n + 1);
+    for (int i = 0; i < n; ++i) {
+      PKB_CUDA(cudaMemcpyAsync(d_audio + aoff[i], pcm[i], n_samples[i] * sizeof(float), cudaMemcpyHostToDevice, st_));
+      segs[i] = FrontSegment{(long long)aoff[i], (long long)f0[i] * kNMels, kNMels, 0, 0, -1};
+      ints[i] = f0[i];
+      ints[n + 1 + i] = T[i];
+    }
+    ints[n] = (int)total_frames;
+    PKB_CUDA(cudaMemcpyAsync(d_seg, segs.data(), n * sizeof(FrontSegment), cudaMemcpyHostToDevice, st_));
+    PKB_CUDA(cudaMemcpyAsync(d_ints, ints.data(), ints.size() * sizeof(int), cudaMemcpyHostToDevice, st_));
+    im.frontend.logmel(d_audio, d_seg, d_ints, n, (int)total_frames, im.lf_feat, nullptr, sm_count_, st_); ++launches_;
+    if (per_feature_norm) {
+      int maxT = 0;
+      for (int i = 0; i < n; ++i) maxT = std::max(maxT, T[i]);
+      im.frontend.per_feature_stats(im.lf_feat, d_seg, d_ints + n + 1, n, d_stats, st_); ++launches_;
+      im.frontend.apply_norm(im.lf_feat, d_seg, d_ints + n + 1, n, maxT, d_stats, st_); ++launches_;
+    }
+    PKB_CUDA(cudaStreamSynchronize(st_));      // the pageable sources and the host vectors above are done with
+    cudaFree(d_audio); cudaFree(d_seg); cudaFree(d_ints); cudaFree(d_stats);
+  } else {
+    for (int i = 0; i < n; ++i) {
+      if (bins_major) {
+        float* d_tmp = dev_alloc<float>((size_t)T[i] * kNMels);
+        PKB_CUDA(cudaMemcpyAsync(d_tmp, feats[i], (size_t)T[i] * kNMels * sizeof(float), cudaMemcpyHostToDevice, st_));
+        im.frontend.bins_to_frames(d_tmp, T[i], im.lf_feat, (int)im.lf_feat_frames, f0[i], st_); ++launches_;
+        PKB_CUDA(cudaStreamSynchronize(st_));
+        cudaFree(d_tmp);
+      } else {
+        PKB_CUDA(cudaMemcpyAsync(im.lf_feat + (size_t)f0[i] * kNMels, feats[i], (size_t)T[i] * kNMels * sizeof(float), cudaMemcpyHostToDevice, st_));
+      }
+    }
+    PKB_CUDA(cudaStreamSynchronize(st_));
+  }
+
+  // ---- predictor priming for the utterances that will be decoded (prime_streams reuses batch_ints: do it before the upload)
+  if (decode) {
+    std::vector<int> fresh;
+    for (int i = 0; i < n; ++i)
+      if (streams_[sids[i]]->needs_prime) { fresh.push_back(sids[i]); streams_[sids[i]]->needs_prime = false; }
+    prime_streams(fresh);
+    // prime_streams wrote slots into batch_ints_host[0..]: restore the feature-base field
+    for (int i = 0; i < n; ++i) slot[i] = 0;
+  }
+  const size_t nints = (size_t)kNumBatchFields * C + 3 * (C + 1);
+  PKB_CUDA(cudaMemcpyAsync(im.batch_ints, h, nints * sizeof(int), cudaMemcpyHostToDevice, st_));
+  int* d = im.batch_ints;
+  b.slot = d; b.T = d + C; b.f0 = d + 2 * C; b.T1 = d + 3 * C; b.T2 = d + 4 * C; b.T3 = d + 5 * C; b.Tq = d + 6 * C;
+  b.qlen = d + 7 * C; b.len = d + 8 * C; b.head = d + 9 * C; b.drop = d + 11 * C; b.offline = d + 12 * C;
+  b.off2 = d + kNumBatchFields * C; b.off3 = b.off2 + (C + 1); b.row_off = b.off3 + (C + 1);
+  b.row_entry = im.row_entry; b.row_pos = im.row_pos; b.rowmap3 = im.rowmap3;
+
+  // ---- encoder over all frames
+  LongForm lf{b.max_Tq};
+  launch_lf_posemb(im.lf_pos_act.out(), lf.Tm, st_); ++launches_;
+  run_encoder(b, &lf);
+  std::vector<float> rows;
+  if (enc_out) {
+    rows.resize((size_t)b.M * kDModel);
+    PKB_CUDA(cudaMemcpyAsync(rows.data(), im.x, rows.size() * sizeof(float), cudaMemcpyDeviceToHost, st_));
+  }
+  // ---- greedy TDT over every frame of every utterance
+  std::vector<int> counts, recs;
+  if (decode) {
+    run_decode(b, b.head, im.lf_steps, steps_per);
+    counts.resize(n);
+    recs.resize((size_t)n * steps_per * 3);
+    PKB_CUDA(cudaMemcpyAsync(counts.data(), im.n_steps, n * sizeof(int), cudaMemcpyDeviceToHost, st_));
+    PKB_CUDA(cudaMemcpyAsync(recs.data(), im.lf_steps, recs.size() * sizeof(int), cudaMemcpyDeviceToHost, st_));
+  }
+  PKB_CUDA(cudaStreamSynchronize(st_));
+  if (im.profile) profile_collect();
+  for (int i = 0; i < n; ++i) {
+    Stream& s = *streams_[sids[i]];
+    const int Te = h[6 * C + i], r0 = roff[i];
+    if (enc_out && enc_out[i]) {      // contract layout [1024, T_enc]
+      float* o = enc_out[i];
+      for (int t = 0; t < Te; ++t)
+        for (int c = 0; c < kDModel; ++c) o[(size_t)c * Te + t] = rows[(size_t)(r0 + t) * kDModel + c];
+    }
+    s.last = ChunkResult();
+    s.last.encoded_len = Te;
+    s.frames_written += T[i];
+    s.chunks += 1;
+    if (decode) {
+      const int cnt = std::min(counts[i], steps_per);
+      const int* st = recs.data() + (size_t)i * steps_per * 3;
+      for (int k = 0; k < cnt; ++k) {
+        s.last.steps.push_back(StepRecord{st[3 * k], st[3 * k + 1], st[3 * k + 2]});
+        if (st[3 * k + 1] != kBlank) s.tokens.push_back(st[3 * k + 1]);
+      }
+    }
   }
 }
 

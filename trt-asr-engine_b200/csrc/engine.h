@@ -85,6 +85,15 @@ class Engine {
                               int64_t* cache_last_channel_len_out);
   void encoder_offline_step(int B, int T, const float* audio_signal, const int64_t* length, float* encoder_output /*[B,1024,T_enc]*/,
                             int64_t* encoded_lengths);
+  // ---- whole-utterance offline path (BASELINE configs 1 and 5; the reference's `encoder` graph run with a dynamic time axis,
+  // contract.json:67-96, + the TDT loop over all of its frames) ----
+  // n utterances, utterance i bound to the freshly opened / reset stream sids[i].  Input per utterance: either 16 kHz PCM
+  // (pcm[i], n_samples[i]; log-mel and optional whole-utterance per-feature normalisation run on the GPU) or features
+  // (feats[i]: T[i] frames, bins-major [128,T] when bins_major else frames-major [T,128]).  The encoder attends over ALL frames
+  // of an utterance (no caches, no 256-frame limit); sum of encoder frames <= max_rows.  enc_out[i] (optional, host) receives
+  // encoder_output [1024, T_enc_i]; decode != 0 runs greedy TDT over every frame: tokens(sid) / last_chunk(sid).
+  void offline_utterances(int n, const int* sids, const float* const* pcm, const size_t* n_samples, int per_feature_norm,
+                          const float* const* feats, const int* T, int bins_major, float* const* enc_out, int decode);
   void predictor_step(int B, const int64_t* y, const float* h, const float* c, float* g, float* h_out, float* c_out);
   void joint_step(int B, int T, int U, const float* enc, const float* pred, float* out);
   // GPU frontend on host buffers: pcm[n] -> frames-major [T,128]; per_feature_norm applies utterance mean/std
@@ -119,8 +128,11 @@ class Engine {
   void load_weights();
   void alloc_state();
   void run_batch(const std::vector<Entry>& entries, float* enc_out_host /*optional [B,1024,3]*/);
-  void run_encoder(const BatchDev& b);
-  void run_decode(const BatchDev& b, const std::vector<Entry>& entries);
+  struct LongForm { int Tm; };       // whole-utterance pass: Tm = longest utterance (centre of the relative-position table)
+  void run_encoder(const BatchDev& b, const LongForm* lf = nullptr);
+  // slots / steps / max_steps override the per-chunk defaults for the whole-utterance path
+  void run_decode(const BatchDev& b, const int* slots = nullptr, int* steps = nullptr, int max_steps = 0);
+  void lf_prepare(size_t total_frames, size_t steps_ints);
   void run_predictor_pass(const DecodeDev& d);
   void frontend_pass();
   void prime_streams(const std::vector<int>& sids);
