@@ -199,6 +199,8 @@ def main():
     ap.add_argument("--ref-chunks", type=int, default=40, help="chunks per stream of the cpu_baseline sample (~15 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--longform", type=int, default=0, help="also run BASELINE config 5's shape: this many clips through the whole-utterance offline path")
+    ap.add_argument("--longform-seconds", type=float, default=3600.0)
     ap.add_argument("--prefill-chunks", type=int, default=88,
                     help="untimed chunks per stream before the timed region; 86 saturate the 256-step attention cache (1 + 3 per chunk)")
     args = ap.parse_args()
@@ -313,7 +315,16 @@ def main():
     gemm_ms, gemm_flops, gemm_launches = eng.profile_read()
     attn_ms, attn_bytes, attn_launches = eng.profile_read_class(1)
     fe_ms, fe_bytes, fe_launches = eng.profile_read_class(2)
+    dec_ms, dec_bytes, dec_loops = eng.profile_read_class(3)
     eng.profile_enable(False)
+    # the frontend kernel at a size where it is not launch-bound: log-mel of one 1 h clip (BASELINE config 5's frontend)
+    fe1h = None
+    if world == 1 and not args.no_latency:
+        eng.profile_enable(True)
+        hour = np.tile(clips[0][:160000], 360)
+        eng.logmel(hour)
+        fe1h = eng.profile_read_class(2)
+        eng.profile_enable(False)
 
     n_tokens = sum(len(eng.tokens(int(s))) for s in sids[: min(n, 64)])
     dev_s, e2e_max, wall_max = reduce_timings([dev_ms / 1e3, e2e_s, wall_resident], world)
@@ -358,6 +369,21 @@ def main():
          "algorithmic_bytes_per_launch": fe_bytes / max(fe_launches, 1),
          "note": "latency-bound at this size (24 new frames per stream per step); 0.3 % of the step"},
     ]
+    line["roofline_hbm"].append(
+        {"kernel": "TDT decode loop (joint_hidden -> joint output GEMM with fused argmax -> tdt_select -> predictor pass), whole loop",
+         "bound": "hbm", "achieved": dec_bytes / max(dec_ms, 1e-9) / 1e6, "peak": peak_hbm, "unit": "GB/s",
+         "frac": dec_bytes / max(dec_ms, 1e-9) / 1e6 / peak_hbm, "launches_timed": int(dec_loops),
+         "algorithmic_bytes_per_launch": dec_bytes / max(dec_loops, 1),
+         "note": "bytes = iterations x (10.5 MB joint output weights + per-stream rows); the 24 MB of decoder weights stay in the 126 MB "
+                 "L2, so the loop is bound by its ~7 dependent launches per iteration, not by HBM"})
+    if fe1h is not None and fe1h[0] > 0:
+        line["roofline_hbm"].append(
+            {"kernel": "logmel_kernel, one 1 h clip (359 998 frames in one launch)", "bound": "hbm", "achieved": fe1h[1] / fe1h[0] / 1e6,
+             "peak": peak_hbm, "unit": "GB/s", "frac": fe1h[1] / fe1h[0] / 1e6 / peak_hbm, "launches_timed": int(fe1h[2]),
+             "algorithmic_bytes_per_launch": fe1h[1] / max(fe1h[2], 1)})
+    if args.longform > 0 and world == 1:
+        eng.close()
+        line["longform"] = longform(binding, model, args.precision, args.longform, args.longform_seconds, clips[0])
     if not args.no_latency and world == 1:
         line["latency_1stream"] = latency_one_stream(binding, model, args.precision, clips[0])
     if not args.no_cpu_baseline and world == 1:
@@ -370,6 +396,34 @@ def main():
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def longform(binding, model, precision, batch, seconds, clip):
+    """BASELINE config 5 (long-form offline): `batch` clips of `seconds` s through pkb_offline_utterances -- full-utterance log-mel +
+    per-feature normalisation + encoder over ALL frames (full self-attention) + TDT decode; host audio in, tokens out."""
+    n_samp = int(seconds * 16000)
+    audio = [np.roll(np.tile(clip[:160000], n_samp // 160000 + 1)[:n_samp], 977 * i) for i in range(batch)]
+    t_enc = binding.load_library().pkb_encoded_length((n_samp - 400) // 160 + 1)
+    eng = binding.Engine(model, max_streams=batch, precision=precision, max_rows=batch * t_enc + 64, contract_cache=0)
+    sids = [eng.open() for _ in range(batch)]
+    eng.offline_utterances(sids[:1], audio=[audio[0][:160000]], decode=True)       # warm-up (lazy buffers, first launches)
+    for s in sids:
+        eng.reset(s)
+    eng.profile_enable(True)
+    t0 = time.perf_counter()
+    eng.offline_utterances(sids, audio=audio, per_feature_norm=True, decode=True)
+    wall = time.perf_counter() - t0
+    gemm_ms, gemm_flops, _ = eng.profile_read()
+    att_ms, att_flops, att_l = eng.profile_read_class(4)
+    dec_ms, _, _ = eng.profile_read_class(3)
+    eng.profile_enable(False)
+    n_tok = sum(len(eng.tokens(s)) for s in sids)
+    eng.close()
+    return {"workload": f"{batch} clips x {seconds:.0f} s, whole-utterance offline (config 5 shape), encoder frames per clip {t_enc}",
+            "rtfx_e2e": batch * seconds / wall, "wall_s": wall, "tokens": n_tok,
+            "gemm_ms": gemm_ms, "gemm_tflops": gemm_flops / max(gemm_ms, 1e-9) / 1e9,
+            "attention_ms": att_ms, "attention_tflops_algorithmic": att_flops / max(att_ms, 1e-9) / 1e9, "attention_launches": int(att_l),
+            "decode_ms": dec_ms}
 
 
 def latency_one_stream(binding, model, precision, clip):

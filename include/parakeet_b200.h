@@ -88,7 +88,8 @@ double pkb_engine_event_elapsed_ms(PkbEngine* engine, int32_t ev_a, int32_t ev_b
 /* per-launch CUDA-event timing of the tcgen05 GEMM kernel: enable, run steps, read sum(ms), sum(flops), launches */
 int32_t pkb_engine_profile_enable(PkbEngine* engine, int32_t on);
 int32_t pkb_engine_profile_read(PkbEngine* engine, double* ms, double* flops, int64_t* launches);
-/* same for a kernel class: 0 = tcgen05 GEMM (work = algorithmic FLOPs), 1 = attention, 2 = log-mel frontend (work = algorithmic bytes) */
+/* same for a kernel class: 0 = tcgen05 GEMM (work = algorithmic FLOPs), 1 = streaming attention, 2 = log-mel frontend, 3 = TDT decode
+ * loop (work = algorithmic bytes), 4 = whole-utterance attention (work = algorithmic FLOPs) */
 int32_t pkb_engine_profile_read_class(PkbEngine* engine, int32_t cls, double* ms, double* work, int64_t* launches);
 
 /* ---- results ---- */

@@ -177,6 +177,8 @@ struct Engine::Stream {
   ChunkResult last;
 };
 
+constexpr int kProfClasses = 5;   // 0 tcgen05 GEMM, 1 streaming attention, 2 log-mel, 3 decode loop, 4 whole-utterance attention
+
 struct Engine::Impl {
   std::vector<void*> dev_allocs, host_allocs;      // owned device / pinned-host buffers (see g_dev_scope)
   Frontend frontend;
@@ -237,8 +239,8 @@ struct Engine::Impl {
   std::vector<double> prof_flops;        // algorithmic work of the bracketed launch: FLOPs (class 0) or bytes (classes 1, 2)
   std::vector<int> prof_class;           // 0 = tcgen05 GEMM, 1 = attention, 2 = log-mel frontend
   size_t prof_used = 0;
-  double prof_ms[3] = {0, 0, 0}, prof_work[3] = {0, 0, 0};
-  long long prof_launches[3] = {0, 0, 0};
+  double prof_ms[kProfClasses] = {}, prof_work[kProfClasses] = {};
+  long long prof_launches[kProfClasses] = {};
   // whole-utterance offline path (allocated on first use; see Engine::offline_utterances)
   std::vector<GemmW> lf_wpos;            // linear_pos weights per layer (the streaming path only keeps its 320-row projected table)
   float* lf_feat = nullptr;              // [lf_feat_frames][128] normalised log-mel frames of the utterances of one call
@@ -336,7 +338,7 @@ void Engine::profile_enable(bool on) {
   PKB_CUDA(cudaStreamSynchronize(st_));
   im_->profile = on;
   im_->prof_used = 0;
-  for (int c = 0; c < 3; ++c) { im_->prof_ms[c] = im_->prof_work[c] = 0; im_->prof_launches[c] = 0; }
+  for (int c = 0; c < kProfClasses; ++c) { im_->prof_ms[c] = im_->prof_work[c] = 0; im_->prof_launches[c] = 0; }
 }
 // profile mode: bracket the next launch with two CUDA events on the engine stream
 int Engine::prof_begin(int cls, double work) {
@@ -372,7 +374,7 @@ void Engine::profile_collect() {      // call after a synchronised step
   im.prof_used = 0;
 }
 void Engine::profile_read(int cls, double* ms, double* work, long long* launches) {
-  PKB_CHECK(cls >= 0 && cls < 3, "profile class");
+  PKB_CHECK(cls >= 0 && cls < kProfClasses, "profile class");
   *ms = im_->prof_ms[cls]; *work = im_->prof_work[cls]; *launches = im_->prof_launches[cls];
 }
 
@@ -1091,7 +1093,12 @@ void Engine::run_encoder(const BatchDev& b, const LongForm* lf) {
       if (split) { a.qkv_f32 = (const float*)im.lf_qkv; a.ppos_f32 = (const float*)im.lf_ppos; }
       else { a.qkv_bf16 = (const __nv_bfloat16*)im.lf_qkv; a.ppos_bf16 = (const __nv_bfloat16*)im.lf_ppos; }
       a.Tm = lf->Tm; a.max_T = b.max_Tq; a.bias_u = w.bias_u; a.bias_v = w.bias_v; a.ctx = im.a_ln.out();
+      double pairs = 0.0;      // sum over utterances of T^2 (host copy of the batch fields)
+      for (int i = 0; i < b.B; ++i) { const double t = im.batch_ints_host[6 * im.Bcap + i]; pairs += t * t; }
+      // algorithmic FLOPs: content score, position score and value product, 128 MACs each per (query, key, head)
+      const int pi = prof_begin(4, 2.0 * 3.0 * kDHead * kHeads * pairs);
       launch_lf_attention(b, a, st_); ++launches_;
+      prof_end(pi);
     } else {
     { EpiParams e; e.mode = EPI_QKV; e.out_f32 = im.q; e.ldo = kDModel; e.row_entry = b.row_entry; e.row_pos = b.row_pos;
       e.entry_slot = b.slot; e.entry_head = b.head; e.kring = kr; e.vring = vr; e.kv_f32 = split ? 1 : 0;
@@ -1178,7 +1185,10 @@ void Engine::run_decode(const BatchDev& b, const int* slots, int* steps, int max
   d.fused_argmax = (opt_.gemm_backend == 2 || (opt_.gemm_backend == 0 && b.B > 16)) && tc_mask() < 0 ? 1 : 0;
   launch_decode_begin(d, st_); ++launches_;
   const int max_iters = b.max_tenc * (kMaxSymbols + 1) + 2;
+  const int prof_i = prof_begin(3, 0.0);      // the whole loop; its algorithmic bytes are known when it ends
+  int iters_done = 0;
   for (int it = 0; it < max_iters; ++it) {
+    ++iters_done;
     launch_decode_iter_reset(d, st_); ++launches_;
     launch_joint_hidden(d, st_); ++launches_;
     if (d.fused_argmax) {      // tensor-core joint: greedy selection fused into the epilogue, logits never leave the SM
@@ -1200,6 +1210,15 @@ void Engine::run_decode(const BatchDev& b, const int* slots, int* steps, int max
       PKB_CUDA(cudaEventSynchronize(im.dec_events[(it - 1) & 1]));
       if (im.counters_host[2 * ((it - 1) & 1)] == 0) break;
     }
+  }
+  if (prof_i >= 0) {
+    // per working iteration (the last one enqueued is the speculative no-op): the output layer of the joint, [8198,640] bf16 +
+    // bias (its two input projections are evaluated once per chunk / per emitted token, not per iteration), plus per stream the
+    // encoder-projection row, the predictor-projection row and the (token, duration) record; emitting iterations also stream
+    // the LSTM weights (13.1 MB) -- the host does not see which ones emit, so those bytes are left out (lower bound)
+    const double per_iter = (double)kJointOut * kJointH * 2.0 + kJointOut * 4.0 + (double)b.B * (2.0 * kJointH * 4.0 + 12.0);
+    im.prof_flops[prof_i] = per_iter * std::max(iters_done - 1, 1);
+    prof_end(prof_i);
   }
 }
 
@@ -1591,7 +1610,9 @@ void Engine::offline_utterances(int n, const int* sids, const float* const* pcm,
     ints[n] = (int)total_frames;
     PKB_CUDA(cudaMemcpyAsync(d_seg, segs.data(), n * sizeof(FrontSegment), cudaMemcpyHostToDevice, st_));
     PKB_CUDA(cudaMemcpyAsync(d_ints, ints.data(), ints.size() * sizeof(int), cudaMemcpyHostToDevice, st_));
+    const int pi = prof_begin(2, (double)total_frames * (kNMels * 4.0 + 160 * 4.0));
     im.frontend.logmel(d_audio, d_seg, d_ints, n, (int)total_frames, im.lf_feat, nullptr, sm_count_, st_); ++launches_;
+    prof_end(pi);
     if (per_feature_norm) {
       int maxT = 0;
       for (int i = 0; i < n; ++i) maxT = std::max(maxT, T[i]);
@@ -1759,13 +1780,16 @@ size_t Engine::logmel(const float* pcm, size_t n, float* out, int per_feature_no
   PKB_CUDA(cudaMemcpyAsync(d_seg, &sg, sizeof(sg), cudaMemcpyHostToDevice, st_));
   PKB_CUDA(cudaMemcpyAsync(d_prefix, prefix, sizeof(prefix), cudaMemcpyHostToDevice, st_));
   PKB_CUDA(cudaMemcpyAsync(d_prefix + 2, &frames, sizeof(int), cudaMemcpyHostToDevice, st_));
+  const int pi = prof_begin(2, (double)T * (kNMels * 4.0 + 160 * 4.0));      // 640 B of new samples read + 512 B written per frame
   im.frontend.logmel(d_audio, d_seg, d_prefix, 1, (int)T, d_out, nullptr, sm_count_, st_); ++launches_;
+  prof_end(pi);
   if (per_feature_norm) {
     im.frontend.per_feature_stats(d_out, d_seg, d_prefix + 2, 1, d_stats, st_); ++launches_;
     im.frontend.apply_norm(d_out, d_seg, d_prefix + 2, 1, (int)T, d_stats, st_); ++launches_;
   }
   PKB_CUDA(cudaMemcpyAsync(out, d_out, T * kNMels * 4, cudaMemcpyDeviceToHost, st_));
   PKB_CUDA(cudaStreamSynchronize(st_));
+  if (im.profile) profile_collect();
   cudaFree(d_audio); cudaFree(d_out); cudaFree(d_stats); cudaFree(d_seg); cudaFree(d_prefix);
   return T;
 }

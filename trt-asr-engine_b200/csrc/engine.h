@@ -114,7 +114,7 @@ class Engine {
   double event_elapsed_ms(int a, int b);
   void profile_enable(bool on);
   void profile_collect();
-  void profile_read(int cls, double* ms, double* work, long long* launches);   // cls 0: tcgen05 GEMM (work = FLOPs), 1: attention, 2: frontend (bytes)
+  void profile_read(int cls, double* ms, double* work, long long* launches);   // cls 0: tcgen05 GEMM (work = FLOPs), 1: attention, 2: frontend, 3: decode loop (bytes), 4: whole-utterance attention (FLOPs)
   int prof_begin(int cls, double work);
   void prof_end(int idx);
 
