@@ -249,6 +249,7 @@ struct Engine::Impl {
   void* lf_qkv = nullptr;                // [Mcap][3072] q | k | v  (bf16, f32 in precise mode)
   void* lf_ppos = nullptr;               // [2*Mcap][1024] this layer's projected table (bf16 / f32)
   int* lf_steps = nullptr;               // decode trace [B][lf_steps_per][3]
+  TensorMap lf_map_qkv, lf_map_pos;      // TMA maps of this call's q|k|v rows and projected table (bf16 mode)
   size_t lf_steps_ints = 0;
   FrontSegment* segs_dev = nullptr;
   FrontSegment* segs_host = nullptr;
@@ -1093,6 +1094,13 @@ void Engine::run_encoder(const BatchDev& b, const LongForm* lf) {
       if (split) { a.qkv_f32 = (const float*)im.lf_qkv; a.ppos_f32 = (const float*)im.lf_ppos; }
       else { a.qkv_bf16 = (const __nv_bfloat16*)im.lf_qkv; a.ppos_bf16 = (const __nv_bfloat16*)im.lf_ppos; }
       a.Tm = lf->Tm; a.max_T = b.max_Tq; a.bias_u = w.bias_u; a.bias_v = w.bias_v; a.ctx = im.a_ln.out();
+      if (!split) {
+        if (l == 0) {      // same buffers for every layer: the maps only depend on this call's row counts
+          make_tensor_map_2d(&im.lf_map_qkv, im.lf_qkv, (uint64_t)M, 3 * kDModel, 3 * kDModel, 64);
+          make_tensor_map_2d(&im.lf_map_pos, im.lf_ppos, (uint64_t)(2 * lf->Tm - 1), kDModel, kDModel, 128);
+        }
+        a.map_qkv = &im.lf_map_qkv; a.map_pos = &im.lf_map_pos;
+      }
       double pairs = 0.0;      // sum over utterances of T^2 (host copy of the batch fields)
       for (int i = 0; i < b.B; ++i) { const double t = im.batch_ints_host[6 * im.Bcap + i]; pairs += t * t; }
       // algorithmic FLOPs: content score, position score and value product, 128 MACs each per (query, key, head)

@@ -8,6 +8,8 @@
 // B200-first layout: the position term is not materialised as a [T, 2T-1] matrix (64 GB per layer for a 1 h clip); each
 // 64 x 64 score tile multiplies the 64 queries with the 127-row window of the projected table that the tile can touch and
 // applies the rel_shift skew by index inside the CTA.
+#include <cuda.h>
+
 #include "offline_long.cuh"
 
 namespace pkb {
@@ -30,6 +32,33 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
 }
 
 constexpr int kBM = 64;            // query rows per CTA (16 per warp)
@@ -254,6 +283,218 @@ lf_attention_mma_kernel(BatchDev b, LfAttnArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ attention, TMA-staged version
+// Same tiling and arithmetic as lf_attention_mma_kernel, but the K, V and table-window tiles arrive by TMA (64-dim x 64/128-row
+// boxes, 128-byte swizzle -> conflict-free ldmatrix without padding) instead of LDG + STS through the LSU: the first version
+// was bound by the shared-memory data pipe (l1tex lsu wavefronts 67 % of peak, tensor pipe 37 %; profiles/r01_lfattn_r1k), and a
+// third of those wavefronts were the staging copies.  Single buffers, split in two phases so the copies still overlap the math:
+// K and the window are free again after the score phase (their next tile loads during softmax + PV), V after the PV phase (its
+// next tile loads during the next score phase).
+namespace {
+constexpr int kBoxK = kBN * 128;                 // one 64-row x 64-dim bf16 box = 8 KB
+constexpr int kBoxP = kWinRows * 128;            // one 128-row x 64-dim box = 16 KB
+constexpr int kOffV = 2 * kBoxK, kOffP = 4 * kBoxK, kOffG = kOffP + 2 * kBoxP, kOffBar = kOffG + 4 * 16 * kGPitchF * 4;
+constexpr size_t kLfSmemTma = 1024 + kOffBar + 64;
+__device__ __forceinline__ uint32_t swz(uint32_t tile, int box_bytes, int row, int chunk16) {      // (row, 16-byte chunk 0..15) inside a two-box tile
+  return tile + (chunk16 >> 3) * box_bytes + row * 128 + (((chunk16 & 7) ^ (row & 7)) << 4);
+}
+}  // namespace
+
+__global__ void __launch_bounds__(128, 2)
+lf_attention_tma_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_pos, BatchDev b, LfAttnArgs a) {
+  extern __shared__ __align__(16) unsigned char lf_smem[];
+  unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)lf_smem + 1023) & ~(uintptr_t)1023);
+  float* sG = reinterpret_cast<float*>(base + kOffG);
+  uint64_t* bar_kp = reinterpret_cast<uint64_t*>(base + kOffBar);
+  uint64_t* bar_v = bar_kp + 1;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  if (tid == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_pos) : "memory");
+    mbar_init(bar_kp, 1);
+    mbar_init(bar_v, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pdl_enter();
+  const int e = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * kBM;
+  const int T = b.Tq[e];
+  if (i0 >= T) return;
+  const int row0 = b.row_off[e];
+  const __nv_bfloat16* qkv = a.qkv_bf16 + (size_t)row0 * (3 * kDModel) + h * kDHead;
+
+  // ---- stage Qu / Qv (bf16, 256-byte rows) in the window buffer, pull them into A fragments
+  {
+    __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(base + kOffP);
+    for (int x = tid; x < kBM * 16; x += 128) {
+      const int r = x >> 4, c8 = (x & 15) * 8;
+      uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+      const bool ok = i0 + r < T;
+      if (ok) raw = *reinterpret_cast<const uint4*>(qkv + (size_t)(i0 + r) * (3 * kDModel) + c8);
+      const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+      uint32_t ou[4], ov[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 q = __bfloat1622float2(q2[k]);
+        const int d = h * kDHead + c8 + 2 * k;
+        ou[k] = ok ? pack_bf16x2(q.x + a.bias_u[d], q.y + a.bias_u[d + 1]) : 0u;
+        ov[k] = ok ? pack_bf16x2(q.x + a.bias_v[d], q.y + a.bias_v[d + 1]) : 0u;
+      }
+      *reinterpret_cast<uint4*>(sQ + r * kDHead + c8) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+      *reinterpret_cast<uint4*>(sQ + (kBM + r) * kDHead + c8) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+    }
+  }
+  __syncthreads();
+  uint32_t qu[8][4], qv[8][4];
+  {
+    const __nv_bfloat16* sQ = reinterpret_cast<const __nv_bfloat16*>(base + kOffP);
+    const int r = 16 * warp + (lane & 15), c = (lane >> 4) * 8;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      ldsm_x4(smem_u32(sQ + r * kDHead + 16 * ks + c), qu[ks][0], qu[ks][1], qu[ks][2], qu[ks][3]);
+      ldsm_x4(smem_u32(sQ + (kBM + r) * kDHead + 16 * ks + c), qv[ks][0], qv[ks][1], qv[ks][2], qv[ks][3]);
+    }
+  }
+  __syncthreads();
+
+  const int n_tiles = (T + kBN - 1) / kBN;
+  const int col_k = kDModel + h * kDHead, col_v = 2 * kDModel + h * kDHead, col_p = h * kDHead;
+  auto issue_kp = [&](int tile) {
+    const int j0 = tile * kBN;
+    mbar_expect_tx(bar_kp, 2 * kBoxK + 2 * kBoxP);
+    tma_load_2d(base, &map_qkv, bar_kp, col_k, row0 + j0);
+    tma_load_2d(base + kBoxK, &map_qkv, bar_kp, col_k + 64, row0 + j0);
+    const int prow = i0 - j0 - (kBN - 1) + (a.Tm - 1);        // table row of window row 0 (rows outside the table read as zero)
+    tma_load_2d(base + kOffP, &map_pos, bar_kp, col_p, prow);
+    tma_load_2d(base + kOffP + kBoxP, &map_pos, bar_kp, col_p + 64, prow);
+  };
+  auto issue_v = [&](int tile) {
+    mbar_expect_tx(bar_v, 2 * kBoxK);
+    tma_load_2d(base + kOffV, &map_qkv, bar_v, col_v, row0 + tile * kBN);
+    tma_load_2d(base + kOffV + kBoxK, &map_qkv, bar_v, col_v + 64, row0 + tile * kBN);
+  };
+  if (tid == 0) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the Q staging (generic proxy) precedes TMA writes to the same bytes
+    issue_kp(0);
+    issue_v(0);
+  }
+
+  float o[16][4];
+#pragma unroll
+  for (int nt = 0; nt < 16; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  float* sGw = sG + warp * 16 * kGPitchF;
+  const int bl_row = lane & 7, bl_chunk = lane >> 3;
+  const uint32_t uK = smem_u32(base), uV = smem_u32(base + kOffV), uP = smem_u32(base + kOffP);
+
+#pragma unroll 1
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    const int j0 = tile * kBN;
+    const uint32_t ph = tile & 1;
+    mbar_wait(bar_kp, ph);
+    // ---- position scores of this warp's rows over its 80 window columns -> skew buffer
+#pragma unroll 1
+    for (int nt = 0; nt < kGCols / 8; ++nt) {
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+      const int prow = 16 * warp + 8 * nt + bl_row;
+#pragma unroll
+      for (int kp = 0; kp < 4; ++kp) {
+        uint32_t r0, r1, r2, r3;
+        ldsm_x4(swz(uP, kBoxP, prow, 4 * kp + bl_chunk), r0, r1, r2, r3);
+        mma_bf16(c, qv[2 * kp], r0, r1);
+        mma_bf16(c, qv[2 * kp + 1], r2, r3);
+      }
+      *reinterpret_cast<float2*>(sGw + g * kGPitchF + 8 * nt + 2 * t) = make_float2(c[0], c[1]);
+      *reinterpret_cast<float2*>(sGw + (g + 8) * kGPitchF + 8 * nt + 2 * t) = make_float2(c[2], c[3]);
+    }
+    __syncwarp();
+    // ---- content scores
+    float s[8][4];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
+      const int krow = 8 * nb + bl_row;
+#pragma unroll
+      for (int kp = 0; kp < 4; ++kp) {
+        uint32_t r0, r1, r2, r3;
+        ldsm_x4(swz(uK, kBoxK, krow, 4 * kp + bl_chunk), r0, r1, r2, r3);
+        mma_bf16(s[nb], qu[2 * kp], r0, r1);
+        mma_bf16(s[nb], qu[2 * kp + 1], r2, r3);
+      }
+    }
+    __syncthreads();                 // every warp is done with K and the window
+    if (tid == 0 && tile + 1 < n_tiles) issue_kp(tile + 1);
+    // ---- skewed position term, scale, mask
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const int rl = g + 8 * (x >> 1), c = 8 * nb + 2 * t + (x & 1);
+        const float gpos = sGw[rl * kGPitchF + (rl - c + (kBN - 1))];
+        const float v = (j0 + c < T) ? (s[nb][x] + gpos) * kScale : -INFINITY;
+        s[nb][x] = v;
+        mx[x >> 1] = fmaxf(mx[x >> 1], v);
+      }
+    float alpha[2];
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      mx[hr] = fmaxf(mx[hr], __shfl_xor_sync(0xffffffffu, mx[hr], 1));
+      mx[hr] = fmaxf(mx[hr], __shfl_xor_sync(0xffffffffu, mx[hr], 2));
+      const float m_new = fmaxf(m_run[hr], mx[hr]);
+      alpha[hr] = __expf(m_run[hr] - m_new);
+      m_run[hr] = m_new;
+    }
+    float rs[2] = {0.f, 0.f};
+    uint32_t pa[4][4];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      const float p0 = __expf(s[nb][0] - m_run[0]), p1 = __expf(s[nb][1] - m_run[0]);
+      const float p2 = __expf(s[nb][2] - m_run[1]), p3 = __expf(s[nb][3] - m_run[1]);
+      rs[0] += p0 + p1;
+      rs[1] += p2 + p3;
+      pa[nb >> 1][(nb & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+      pa[nb >> 1][(nb & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+    }
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      rs[hr] += __shfl_xor_sync(0xffffffffu, rs[hr], 1);
+      rs[hr] += __shfl_xor_sync(0xffffffffu, rs[hr], 2);
+      l_run[hr] = l_run[hr] * alpha[hr] + rs[hr];
+    }
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+      o[nt][0] *= alpha[0]; o[nt][1] *= alpha[0];
+      o[nt][2] *= alpha[1]; o[nt][3] *= alpha[1];
+    }
+    // ---- O += P V
+    mbar_wait(bar_v, ph);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int vrow = 16 * kk + (lane & 15);
+#pragma unroll
+      for (int np = 0; np < 8; ++np) {
+        uint32_t r0, r1, r2, r3;
+        ldsm_x4_t(swz(uV, kBoxK, vrow, 2 * np + (lane >> 4)), r0, r1, r2, r3);
+        mma_bf16(o[2 * np], pa[kk], r0, r1);
+        mma_bf16(o[2 * np + 1], pa[kk], r2, r3);
+      }
+    }
+    __syncthreads();                 // every warp is done with V
+    if (tid == 0 && tile + 1 < n_tiles) issue_v(tile + 1);
+  }
+
+#pragma unroll
+  for (int hr = 0; hr < 2; ++hr) {
+    const int i = i0 + 16 * warp + g + 8 * hr;
+    if (i >= T) continue;
+    const float inv = l_run[hr] > 0.f ? 1.f / l_run[hr] : 0.f;
+    __nv_bfloat16* dst = a.ctx.ptr + (size_t)(row0 + i) * a.ctx.lda + h * kDHead + 2 * t;
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt)
+      *reinterpret_cast<uint32_t*>(dst + 8 * nt) = pack_bf16x2(o[nt][2 * hr] * inv, o[nt][2 * hr + 1] * inv);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ attention, f32 CUDA cores
 // One CTA (128 threads) per (query row, head, entry); the row's T scores live in shared memory.
 __global__ void __launch_bounds__(128)
@@ -325,9 +566,16 @@ void launch_lf_attention(const BatchDev& b, const LfAttnArgs& a, cudaStream_t st
     static bool attr = false;
     if (!attr) {
       PKB_CUDA(cudaFuncSetAttribute(lf_attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLfSmem));
+      PKB_CUDA(cudaFuncSetAttribute(lf_attention_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLfSmemTma));
       attr = true;
     }
-    launch_k(lf_attention_mma_kernel, dim3((a.max_T + kBM - 1) / kBM, kHeads, b.B), dim3(128), kLfSmem, st, b, a);
+    static const bool use_tma = [] { const char* v = getenv("PARAKEET_B200_LF_ATTN_TMA"); return !(v && v[0] == '0'); }();
+    const dim3 grid((a.max_T + kBM - 1) / kBM, kHeads, b.B);
+    if (use_tma && a.map_qkv && a.map_pos)
+      launch_k(lf_attention_tma_kernel, grid, dim3(128), kLfSmemTma, st, *reinterpret_cast<const CUtensorMap*>(a.map_qkv),
+               *reinterpret_cast<const CUtensorMap*>(a.map_pos), b, a);
+    else
+      launch_k(lf_attention_mma_kernel, grid, dim3(128), kLfSmem, st, b, a);
   } else {
     PKB_CHECK(a.qkv_f32 && a.ppos_f32, "lf_attention: precise mode needs f32 q/k/v and table");
     const size_t smem = (size_t)a.max_T * sizeof(float);

@@ -23,6 +23,11 @@ struct LfAttnArgs {
   const float* bias_u = nullptr;             // [1024]
   const float* bias_v = nullptr;
   ActOut ctx{};                              // [M][1024] operand of linear_out
+  // bf16 mode, TMA-staged kernel: host pointers to 128-byte CUtensorMap objects (gemm.h make_tensor_map_2d: 64-column boxes,
+  // 128-byte swizzle) over qkv [M rows][3072] with 64-row boxes and over the table [2Tm-1 rows][1024] with 128-row boxes;
+  // rows outside a map read as zero.  NULL: the LDG/STS-staged kernel runs instead.
+  const void* map_qkv = nullptr;
+  const void* map_pos = nullptr;
 };
 // Every entry e of the batch is an utterance of b.Tq[e] encoder rows starting at packed row b.row_off[e]; each query row
 // attends to all rows of its utterance:  softmax_j(((q_i+u).k_j + (q_i+v).p_{i-j}) / sqrt(128)) v_j.
