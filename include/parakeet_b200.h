@@ -96,6 +96,14 @@ int32_t pkb_engine_profile_read_class(PkbEngine* engine, int32_t cls, double* ms
 int32_t pkb_stream_num_tokens(PkbEngine* engine, int32_t stream);
 int32_t pkb_stream_tokens(PkbEngine* engine, int32_t stream, int32_t* out, int32_t cap);      /* copies min(n,cap), returns n */
 int32_t pkb_stream_last_steps(PkbEngine* engine, int32_t stream, PkbStep* out, int32_t cap);  /* decode trace of the last chunk */
+/* Timestamps in the encoder timebase (one encoder frame = 80 ms: 10 ms feature shift x 8 subsampling, docs/ARCHITECTURE_RUNTIME.md:46-47;
+ * TDT durations advance encoder frames, docs/DECISION_LOG.md:55-58): the utterance-relative encoder frame of every emitted token
+ * (copies min(n,cap), returns n) and the number of encoder frames decoded so far (the live edge). */
+int32_t pkb_stream_token_frames(PkbEngine* engine, int32_t stream, int32_t* out, int32_t cap);
+int64_t pkb_stream_encoder_frames(PkbEngine* engine, int32_t stream);
+/* "Stable prefix + revision window" (MAGNOLIA_INTEGRATION_HANDOFF.md:105-135): how many leading tokens lie at least
+ * revision_window_ms behind the live edge, i.e. may be committed as final text; the rest is the revisable suffix. */
+int32_t pkb_stream_stable_prefix(PkbEngine* engine, int32_t stream, int32_t revision_window_ms);
 int32_t pkb_stream_cache_len(PkbEngine* engine, int32_t stream);                               /* cache_last_channel_len */
 int64_t pkb_stream_chunks_done(PkbEngine* engine, int32_t stream);
 int32_t pkb_stream_text(PkbEngine* engine, int32_t stream, char* out, int32_t cap);           /* detokenised transcript so far */

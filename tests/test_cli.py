@@ -96,3 +96,21 @@ def test_cli_feature_replay(tmp_path, model_small, features_ref):
     assert run.returncode == 0, run.stderr
     assert "Loaded %d frames of 128 mel features" % f.shape[1] in run.stderr
     assert len([ln for ln in run.stdout.splitlines() if ln.startswith("Transcript: ")]) == (f.shape[1] + 255) // 256
+
+
+@pytest.mark.gpu
+def test_cli_whole_utterance(tmp_path, model_small):
+    """--whole-utterance: one full-context pass over the file; same transcript as pkb_offline_utterances through the binding."""
+    from synth_audio import synth_clip
+    _build()
+    pcm = _write_wav16(str(tmp_path / "a.wav"), synth_clip(12.0, 31))
+    run = subprocess.run([CLI, str(tmp_path / "a.wav"), "--model-dir", model_small, "--whole-utterance", "--feature-norm", "per_feature", "-v"],
+                         capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stderr
+    lines = [ln[len("Transcript: "):] for ln in run.stdout.splitlines() if ln.startswith("Transcript: ")]
+    assert len(lines) == 1 and "1198 feature frames -> 150 encoder frames" in run.stderr
+    eng = binding.Engine(model_small, max_streams=1, precision=0, max_rows=256)
+    s = eng.open()
+    eng.offline_utterances([s], audio=[pcm], per_feature_norm=True)
+    assert lines[0] == eng.text(s)
+    eng.close()

@@ -236,6 +236,8 @@ def _run_streams(eng, m, feats_list, n_chunks, starts):
         ora.append([st, *m.initial_cache(1)])
     sched = streaming_schedule(n_chunks)
     total = same = 0
+    frames = [[] for _ in feats_list]      # expected token timestamps (encoder frames) from the GPU's own traces
+    edge = [0] * len(feats_list)
     for step in range(n_chunks + max(starts)):
         live = [i for i in range(len(feats_list)) if 0 <= step - starts[i] < n_chunks]
         for i in live:
@@ -251,6 +253,14 @@ def _run_streams(eng, m, feats_list, n_chunks, starts):
             total += 1
             same += int(eng.last_steps(sids[i]) == want)
             assert eng.cache_len(sids[i]) == int(cl)
+            frames[i] += [edge[i] + t for t, tok, _ in eng.last_steps(sids[i]) if tok != m.blank]
+            edge[i] += int(el)
+    # timestamps in the 80 ms encoder timebase and the stable-prefix count (pkb_stream_token_frames / _stable_prefix)
+    for i, s in enumerate(sids):
+        assert eng.token_frames(s) == frames[i] and len(frames[i]) == len(eng.tokens(s))
+        assert eng.encoder_frames(s) == edge[i] == 3 * n_chunks
+        for window_ms in (0, 400, 2000, 10 ** 6):
+            assert eng.stable_prefix(s, window_ms) == sum(1 for f in frames[i] if f * 80 <= edge[i] * 80 - window_ms)
     toks = [(eng.tokens(s), o[0].tokens) for s, o in zip(sids, ora)]
     for s in sids:
         eng.close_stream(s)

@@ -29,7 +29,7 @@ B200_SYMBOLS = ["pkb_last_error", "pkb_version", "pkb_engine_create", "pkb_engin
                 "pkb_stream_push_audio", "pkb_stream_set_feature_norm", "pkb_stream_set_offline", "pkb_encoder_offline_step", "pkb_offline_utterances", "pkb_encoded_length", "pkb_engine_push_audio_batch",
                 "pkb_engine_push_audio_batch_device", "pkb_engine_event_record", "pkb_engine_event_elapsed_ms",
                 "pkb_engine_profile_enable", "pkb_engine_profile_read", "pkb_engine_profile_read_class", "pkb_engine_step", "pkb_stream_has_pending",
-                "pkb_stream_num_tokens", "pkb_stream_tokens", "pkb_stream_last_steps", "pkb_stream_cache_len",
+                "pkb_stream_num_tokens", "pkb_stream_tokens", "pkb_stream_token_frames", "pkb_stream_encoder_frames", "pkb_stream_stable_prefix", "pkb_stream_last_steps", "pkb_stream_cache_len",
                 "pkb_stream_chunks_done", "pkb_stream_text", "pkb_detokenize", "pkb_stream_import_state", "pkb_stream_export_state",
                 "pkb_stream_set_decoder_state", "pkb_stream_get_decoder_state", "pkb_encoder_streaming_step", "pkb_predictor_step",
                 "pkb_joint_step", "pkb_logmel", "pkb_gemm_test", "pkb_frontend_create", "pkb_frontend_destroy", "pkb_frontend_logmel"]
@@ -121,6 +121,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.pkb_engine_profile_read_class.argtypes = [vp, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), lp]
     lib.pkb_stream_tokens.argtypes = [vp, C.c_int32, ip, C.c_int32]
     lib.pkb_stream_last_steps.argtypes = [vp, C.c_int32, C.POINTER(PkbStep), C.c_int32]
+    lib.pkb_stream_token_frames.argtypes = [vp, C.c_int32, ip, C.c_int32]
+    lib.pkb_stream_encoder_frames.argtypes = [vp, C.c_int32]
+    lib.pkb_stream_encoder_frames.restype = C.c_int64
+    lib.pkb_stream_stable_prefix.argtypes = [vp, C.c_int32, C.c_int32]
     lib.pkb_stream_text.argtypes = [vp, C.c_int32, C.c_char_p, C.c_int32]
     lib.pkb_detokenize.argtypes = [vp, ip, C.c_int32, C.c_char_p, C.c_int32]
     lib.pkb_stream_import_state.argtypes = [vp, C.c_int32, fp, fp, C.c_int32]
@@ -313,6 +317,18 @@ class Engine:
             buf = (PkbStep * cap)()
             n = self._chk(self._lib.pkb_stream_last_steps(self._e, s, buf, cap))
         return [(buf[i].time_idx, buf[i].token, buf[i].duration) for i in range(min(n, cap))]
+
+    def token_frames(self, s: int) -> List[int]:
+        n = self._chk(self._lib.pkb_stream_token_frames(self._e, s, None, 0))
+        out = np.zeros(max(n, 1), np.int32)
+        self._chk(self._lib.pkb_stream_token_frames(self._e, s, out.ctypes.data_as(C.POINTER(C.c_int32)), n))
+        return out[:n].tolist()
+
+    def encoder_frames(self, s: int) -> int:
+        return self._chk(int(self._lib.pkb_stream_encoder_frames(self._e, s)))
+
+    def stable_prefix(self, s: int, revision_window_ms: int) -> int:
+        return self._chk(self._lib.pkb_stream_stable_prefix(self._e, s, revision_window_ms))
 
     def cache_len(self, s: int) -> int:
         return self._chk(self._lib.pkb_stream_cache_len(self._e, s))

@@ -407,6 +407,23 @@ int32_t pkb_stream_last_steps(PkbEngine* e, int32_t s, PkbStep* out, int32_t cap
     return (int)r.steps.size();
   });
 }
+int32_t pkb_stream_token_frames(PkbEngine* e, int32_t s, int32_t* out, int32_t cap) {
+  PKB_ENTER(e);
+  return guarded([&] {
+    const std::vector<int>& t = e->eng->token_frames(s);
+    for (int i = 0; i < cap && i < (int)t.size(); ++i) out[i] = t[i];
+    return (int)t.size();
+  });
+}
+int64_t pkb_stream_encoder_frames(PkbEngine* e, int32_t s) {
+  if (!e) return -1;
+  std::lock_guard<std::mutex> lock(e->mu);
+  try { return e->eng->encoder_frames_done(s); } catch (const std::exception& ex) { g_last_error = ex.what(); return -2; }
+}
+int32_t pkb_stream_stable_prefix(PkbEngine* e, int32_t s, int32_t revision_window_ms) {
+  PKB_ENTER(e);
+  return guarded([&] { return e->eng->stable_prefix(s, revision_window_ms); });
+}
 int32_t pkb_stream_cache_len(PkbEngine* e, int32_t s) { PKB_ENTER(e); return guarded([&] { return e->eng->cache_len(s); }); }
 int64_t pkb_stream_chunks_done(PkbEngine* e, int32_t s) {
   if (!e) return -1;

@@ -174,6 +174,8 @@ struct Engine::Stream {
   int head = 0;
   long long chunks = 0;
   std::vector<int> tokens;
+  std::vector<int> token_frames;         // encoder frame (80 ms timebase) each token was emitted on, counted from the utterance start
+  long long enc_frames = 0;              // encoder frames decoded so far (the live edge of the transcript)
   ChunkResult last;
 };
 
@@ -702,7 +704,7 @@ void Engine::reset_stream(int sid) {
   s.frames_written = 0; s.pending.clear(); s.audio.clear(); s.audio_mode = false;   // (s.offline is a property of the stream: kept)
   s.sched_chunk = 0; s.has_norm = false;
   s.dev_off = 0; s.dev_fill = 0;
-  s.cache_len = 0; s.head = 0; s.chunks = 0; s.tokens.clear(); s.last = ChunkResult();
+  s.cache_len = 0; s.head = 0; s.chunks = 0; s.tokens.clear(); s.token_frames.clear(); s.enc_frames = 0; s.last = ChunkResult();
   const size_t slot = (size_t)s.slot;
   PKB_CUDA(cudaMemsetAsync(im.cache_tm + slot * L_ * kDModel * kTimeCtx, 0, (size_t)L_ * kDModel * kTimeCtx * 4, st_));
   PKB_CUDA(cudaMemsetAsync(im.pred_h + slot * kPredL * kPredH, 0, kPredL * kPredH * 4, st_));
@@ -725,6 +727,15 @@ bool Engine::has_pending(int sid) const {
 }
 const std::vector<int>& Engine::tokens(int sid) const { return streams_[sid]->tokens; }
 const ChunkResult& Engine::last_chunk(int sid) const { return streams_[sid]->last; }
+const std::vector<int>& Engine::token_frames(int sid) const { return streams_[sid]->token_frames; }
+long long Engine::encoder_frames_done(int sid) const { return streams_[sid]->enc_frames; }
+int Engine::stable_prefix(int sid, int revision_window_ms) const {
+  const Stream& s = *streams_[sid];
+  const long long edge_ms = s.enc_frames * 80 - std::max(revision_window_ms, 0);
+  // token_frames is non-decreasing: count the tokens emitted at or before the window's left edge
+  return (int)(std::upper_bound(s.token_frames.begin(), s.token_frames.end(), edge_ms,
+                                [](long long ms, int frame) { return ms < (long long)frame * 80; }) - s.token_frames.begin());
+}
 int Engine::cache_len(int sid) const { return streams_[sid]->cache_len; }
 long long Engine::chunks_done(int sid) const { return streams_[sid]->chunks; }
 
@@ -1309,8 +1320,9 @@ void Engine::run_batch(const std::vector<Entry>& entries, float* enc_out_host) {
       const int* st = im.res_host + C + (size_t)i * max_steps * 3;
       for (int k = 0; k < n; ++k) {
         s.last.steps.push_back(StepRecord{st[3 * k], st[3 * k + 1], st[3 * k + 2]});
-        if (st[3 * k + 1] != kBlank) s.tokens.push_back(st[3 * k + 1]);
+        if (st[3 * k + 1] != kBlank) { s.tokens.push_back(st[3 * k + 1]); s.token_frames.push_back((int)(s.enc_frames + st[3 * k])); }
       }
+      s.enc_frames += s.last.encoded_len;
     }
     if (!s.offline) {
       s.cache_len = std::min(s.cache_len + keep, kCacheS);     // clamp(len + cache_keep_size, max=cache_len)
@@ -1698,8 +1710,9 @@ void Engine::offline_utterances(int n, const int* sids, const float* const* pcm,
       const int* st = recs.data() + (size_t)i * steps_per * 3;
       for (int k = 0; k < cnt; ++k) {
         s.last.steps.push_back(StepRecord{st[3 * k], st[3 * k + 1], st[3 * k + 2]});
-        if (st[3 * k + 1] != kBlank) s.tokens.push_back(st[3 * k + 1]);
+        if (st[3 * k + 1] != kBlank) { s.tokens.push_back(st[3 * k + 1]); s.token_frames.push_back((int)(s.enc_frames + st[3 * k])); }
       }
+      s.enc_frames += Te;
     }
   }
 }

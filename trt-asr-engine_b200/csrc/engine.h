@@ -68,6 +68,14 @@ class Engine {
 
   const std::vector<int>& tokens(int sid) const;
   const ChunkResult& last_chunk(int sid) const;
+  // Timestamps in the encoder timebase (80 ms per frame: 10 ms feature shift x 8 subsampling, docs/ARCHITECTURE_RUNTIME.md:46-47):
+  // the absolute encoder frame each token was emitted on, and the number of encoder frames decoded so far.
+  const std::vector<int>& token_frames(int sid) const;
+  long long encoder_frames_done(int sid) const;
+  // "Stable prefix + revision window" (MAGNOLIA_INTEGRATION_HANDOFF.md:105-135): number of leading tokens older than
+  // revision_window_ms behind the live edge -- the part of the transcript a UI may commit.  Greedy TDT never rewrites an emitted
+  // token, so the policy reduces to its time threshold.
+  int stable_prefix(int sid, int revision_window_ms) const;
   int cache_len(int sid) const;
   long long chunks_done(int sid) const;
 

@@ -5,7 +5,7 @@
 // frontend that replaces rust/features).  Inputs: WAV (PCM16 or float32, mono, 16 kHz), raw PCM (f32le), or a feature tap
 // (f32le raw + optional JSON sidecar: kind / format / layout / mel_bins / num_frames / shape, main.rs:132-165).
 //   parakeet_cli <input> --model-dir DIR [--stream-sim SEC] [--device-id N] [--raw-pcm] [--sample-rate HZ] [--features-input]
-//                [--n-mels N] [--verbose|-v] [--dump-features PATH] [--feature-norm none|per_feature] [--no-sleep]
+//                [--n-mels N] [--verbose|-v] [--dump-features PATH] [--feature-norm none|per_feature] [--no-sleep] [--whole-utterance]
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -29,7 +29,7 @@ struct Args {
   double stream_sim = -1.0;
   int device_id = 0, n_mels = -1;
   long sample_rate = -1;
-  bool raw_pcm = false, features_input = false, verbose = false, no_sleep = false;
+  bool raw_pcm = false, features_input = false, verbose = false, no_sleep = false, whole_utterance = false;
 };
 
 [[noreturn]] void die(const std::string& msg) {
@@ -189,9 +189,11 @@ int main(int argc, char** argv) {
     else if (s == "--dump-features") a.dump_features = need("--dump-features");
     else if (s == "--feature-norm") a.feature_norm = need("--feature-norm");
     else if (s == "--no-sleep") a.no_sleep = true;      // additive: stream simulation without the real-time sleeps
+    else if (s == "--whole-utterance") a.whole_utterance = true;   // additive: one full-context pass over the whole file (pkb_offline_utterances)
     else if (s == "--help" || s == "-h") {
       std::printf("usage: parakeet_cli <input> --model-dir DIR [--stream-sim SEC] [--device-id N] [--raw-pcm] [--sample-rate HZ]\n"
-                  "       [--features-input] [--n-mels N] [-v|--verbose] [--dump-features PATH] [--feature-norm none|per_feature] [--no-sleep]\n");
+                  "       [--features-input] [--n-mels N] [-v|--verbose] [--dump-features PATH] [--feature-norm none|per_feature] [--no-sleep]\n"
+                  "       [--whole-utterance]\n");
       return 0;
     } else if (!s.empty() && s[0] == '-') die("unknown option " + s);
     else a.input = s;
@@ -250,6 +252,33 @@ int main(int argc, char** argv) {
     std::vector<float> audio = a.raw_pcm ? load_f32le(a.input, "Raw PCM") : load_wav(a.input, &rate);
     if (rate != 16000) die("expected 16 kHz audio (got " + std::to_string(rate) + " Hz); resample first");
     if (a.verbose) std::fprintf(stderr, "[replay] Loaded %zu samples (%.2f s)\n", audio.size(), audio.size() / 16000.0);
+    if (a.whole_utterance) {
+      // The offline file mode of the reference CLI pushes the whole file at once (main.rs:484-535) and the runtime cuts it into
+      // independent <= 256-frame segments; this mode keeps the utterance whole: log-mel, normalisation, self-attention over ALL
+      // frames and the TDT loop in one pkb_offline_utterances call.
+      if (audio.size() < 400) die("audio shorter than one 25 ms frame");
+      const int frames = (int)((audio.size() - 400) / 160 + 1);
+      PkbEngineConfig ec{};
+      ec.model_dir = a.model_dir.c_str(); ec.device_id = a.device_id; ec.max_streams = 1; ec.precision = 0; ec.gemm_backend = 0;
+      ec.contract_cache = 0; ec.punct_suppression = 1; ec.max_rows = pkb_encoded_length(frames) + 64;
+      PkbEngine* eng = pkb_engine_create(&ec);
+      if (!eng) die(std::string("engine creation failed: ") + pkb_last_error());
+      const int32_t sid = pkb_stream_open(eng);
+      const float* ap = audio.data();
+      const size_t ns = audio.size();
+      std::printf("Starting transcription (whole utterance)...\n");
+      if (sid < 0 || pkb_offline_utterances(eng, 1, &sid, &ap, &ns, per_feature ? 1 : 0, nullptr, nullptr, 0, nullptr, 1) != 0)
+        die(std::string("pkb_offline_utterances failed: ") + pkb_last_error());
+      std::vector<char> text((size_t)pkb_stream_text(eng, sid, nullptr, 0) + 1);
+      pkb_stream_text(eng, sid, text.data(), (int32_t)text.size());
+      if (a.verbose) std::fprintf(stderr, "[replay] %d feature frames -> %d encoder frames, %d tokens\n", frames, pkb_encoded_length(frames),
+                                  pkb_stream_num_tokens(eng, sid));
+      std::printf("Transcript: %s\n", text.data());
+      pkb_engine_destroy(eng);
+      if (a.verbose)
+        std::fprintf(stderr, "[replay] Completed in %.2fs\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
+      return 0;
+    }
     Frontend fe(a.device_id);
     std::vector<float> mean, stdv;
     std::vector<float> whole_tc;
