@@ -67,6 +67,7 @@ struct EpiParams {
   int* part_idx = nullptr;
   float* dur_out = nullptr;         // [M][kNDur]
   float blank_penalty = 0.0f;
+  int direct_bf16 = 0;              // set by gemm_tc(): bf16 output rows are written straight from the TMEM-load registers (see gemm_tc.cu)
   int k_natural = 0;                // 1: K and V rings head-major [slot][head][kRingCap][128] (tensor-core attention);
                                     // 0: K^T ring [slot][head][128][kRingCap] + V ring [slot][kRingCap][1024] (precise mode)
 };

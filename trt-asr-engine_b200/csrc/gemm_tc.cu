@@ -240,6 +240,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int kb_per_pass = g.K / BK;
   const int n_pass = g.a_lo_off != 0 ? 2 : 1;
   const int splits = MODE == EPI_PARTIAL_F32 ? g.epi.splits : 1;      // work unit = (tile, k-split), split fastest
+  // bf16 rows (plain operand plane / bf16 partial sums) with 16-byte aligned 16-column groups: registers -> global directly
+  constexpr bool kDirectMode = MODE == EPI_ACT || MODE == EPI_SILU_ACT || MODE == EPI_BIAS_RELU_ACT || MODE == EPI_PARTIAL_F32;
+  const bool direct = kDirectMode && g.epi.direct_bf16 != 0;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -335,6 +338,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};      // EPI_ARGMAX: running first-maximum per row
       int bidx[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+      // direct path (bf16 outputs): the lane keeps its own TMEM row, so no staging tile is involved
+      const int m_d = m0 + q * 32 + lane;
+      __nv_bfloat16* drow = nullptr;
+      if (direct && m_d < M) {
+        if constexpr (MODE == EPI_PARTIAL_F32)
+          drow = reinterpret_cast<__nv_bfloat16*>(g.epi.out_f32) + (size_t)epilogue_row_ctx<MODE>(g.epi, m_d, sp) * g.epi.ldo;
+        else
+          drow = g.epi.out_act + (size_t)m_d * g.epi.lda_out;
+      }
 #pragma unroll 1
       for (int c0 = 0; c0 < BN / 2; c0 += 16) {
         uint32_t v[16];
@@ -343,6 +355,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        if (direct) {
+          // 16 adjacent columns of one row per lane -> 32 contiguous bytes of bf16 = one full sector, written straight from the
+          // registers the TMEM load filled (no shared-memory transpose: its ~50 extra instructions per chunk made short-K
+          // GEMMs epilogue-bound)
+          const int nn = n0 + half * (BN / 2) + c0 + n_out0 + g.epi.n_off;
+          if (drow != nullptr && n0 + half * (BN / 2) + c0 < g.N) {
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+            if constexpr (MODE == EPI_SILU_ACT) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = silu(f[j]);
+            } else if constexpr (MODE == EPI_BIAS_RELU_ACT) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 bq = *reinterpret_cast<const float4*>(g.epi.bias + nn + 4 * j);
+                f[4 * j] = fmaxf(f[4 * j] + bq.x, 0.f); f[4 * j + 1] = fmaxf(f[4 * j + 1] + bq.y, 0.f);
+                f[4 * j + 2] = fmaxf(f[4 * j + 2] + bq.z, 0.f); f[4 * j + 3] = fmaxf(f[4 * j + 3] + bq.w, 0.f);
+              }
+            }
+            const uint2 p0 = pack4_bf16(f[0], f[1], f[2], f[3]), p1 = pack4_bf16(f[4], f[5], f[6], f[7]);
+            const uint2 p2 = pack4_bf16(f[8], f[9], f[10], f[11]), p3 = pack4_bf16(f[12], f[13], f[14], f[15]);
+            uint4* dst = reinterpret_cast<uint4*>(drow + nn);
+            dst[0] = make_uint4(p0.x, p0.y, p1.x, p1.y);
+            dst[1] = make_uint4(p2.x, p2.y, p3.x, p3.y);
+          }
+          continue;
         }
         __syncwarp();                                       // previous chunk's readers are done with the staging tile
 #pragma unroll
@@ -659,7 +699,9 @@ bool pick_two_cta(int M, int N, int K, int sms) {
   const int bn = pick_bn(M, N, sms);
   const long long t1 = (long long)((M + BM - 1) / BM) * ((N + bn - 1) / bn);
   const double eff1 = (double)t1 / (double)(((t1 + sms - 1) / sms) * sms);
-  return eff2 > eff1 + 0.05 || (K >= 4096 && M >= 4096);
+  // (N = 1024, K = 1024, the attention-output and conv pointwise_conv2 projections: 16.9 vs 19.0 us although its 96 pair tiles
+  // fill only 65 % of two rounds -- the 128 x 128 tiles of the single-CTA kernel are bound by operand delivery there)
+  return eff2 > eff1 + 0.05 || (K >= 4096 && M >= 4096) || (N == 1024 && K == 1024 && M >= 4096);
 }
 
 }  // namespace
@@ -717,8 +759,20 @@ bool gemm_tc_supported(const GemmArgs& g) {
   return g.K % BK == 0 && (g.lda == g.K || (g.batch > 1 && g.a_lo_off == 0)) && (g.a_lo_off % g.lda) == 0 && g.M > 0 && g.N > 0;
 }
 
-void gemm_tc(const GemmArgs& g, const TensorMap& map_a, const TensorMap& map_w, cudaStream_t st) {
-  PKB_CHECK(gemm_tc_supported(g), "gemm_tc: unsupported shape");
+void gemm_tc(const GemmArgs& g_in, const TensorMap& map_a, const TensorMap& map_w, cudaStream_t st) {
+  PKB_CHECK(gemm_tc_supported(g_in), "gemm_tc: unsupported shape");
+  GemmArgs g = g_in;
+  {
+    // direct bf16 epilogue (single-CTA kernel): every 16-column group of an output row must be one aligned 32-byte run
+    static const bool allow = [] { const char* v = getenv("PARAKEET_B200_EPI_DIRECT"); return !(v && v[0] == '0'); }();
+    const EpiParams& e = g.epi;
+    bool ok = allow && g.N % 16 == 0 && e.n_off % 8 == 0 && g.out_col_stride % 8 == 0;
+    if (e.mode == EPI_PARTIAL_F32) ok = ok && e.part_bf16 && e.ldo % 8 == 0 && ((uintptr_t)e.out_f32 & 15) == 0;
+    else if (e.mode == EPI_ACT || e.mode == EPI_SILU_ACT || e.mode == EPI_BIAS_RELU_ACT)
+      ok = ok && e.lo_off_out == 0 && e.lda_out % 8 == 0 && ((uintptr_t)e.out_act & 15) == 0 && (e.mode != EPI_BIAS_RELU_ACT || ((uintptr_t)e.bias & 15) == 0);
+    else ok = false;
+    g.epi.direct_bf16 = ok ? 1 : 0;
+  }
   const int sms = sm_count();
   if (g_force_bn < 0) { const char* v = getenv("PARAKEET_B200_GEMM_BN"); g_force_bn = v ? atoi(v) : 0; }
   if (g_two_cta < 0) { const char* v = getenv("PARAKEET_B200_GEMM_2CTA"); g_two_cta = v ? atoi(v) : 1; }

@@ -46,6 +46,13 @@ int main(int argc, char** argv) {
   if (!strcmp(epi, "resadd")) { g.epi.mode = EPI_RESADD_F32; g.epi.out_f32 = out; g.epi.ldo = N; g.epi.scale = 0.5f; }
   else if (!strcmp(epi, "silu")) { g.epi.mode = EPI_SILU_ACT; g.epi.out_act = act; g.epi.lda_out = N; }
   else if (!strcmp(epi, "glu")) { g.epi.mode = EPI_GLU_F32; g.epi.out_f32 = out; g.epi.ldo = N / 2; }
+  else if (!strncmp(epi, "partial", 7)) {      // partial<splits>[p][b]: split-K partial sums; p = split chosen for the CTA-pair kernel; b = bf16 partials
+    const int sp = epi[7] ? epi[7] - '0' : 1;
+    float* ws = dalloc_f((size_t)sp * M * N);
+    g.epi.mode = EPI_PARTIAL_F32; g.epi.out_f32 = ws; g.epi.ldo = N; g.epi.splits = sp; g.epi.part_rows = M;
+    g.epi.pair_split = strchr(epi + 7, 'p') ? 1 : 0;
+    g.epi.part_bf16 = strchr(epi + 7, 'b') ? 1 : 0;
+  }
   else { g.epi.mode = EPI_F32; g.epi.out_f32 = out; g.epi.ldo = N; }
   PKB_CUDA(cudaDeviceSynchronize());
   cudaEvent_t e0, e1;
