@@ -61,6 +61,15 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// K / V ring blocks are read exactly once per step: loading them with an L2 evict-first policy keeps the 1.2 GB-per-layer stream
+// from flushing the residual stream, the GEMM operands and the partial sums (all re-read within the layer) out of the 126 MB L2
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
@@ -161,6 +170,9 @@ attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
   if (warp == 0) {
     // ===== producer =====
     if (lane == 0) {
+      uint64_t pol_stream = 0;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+      const bool hint = a.evict_first != 0;
       int it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int e = item >> 3, h = item & 7;
@@ -174,8 +186,14 @@ attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
             const int s = it % kStages;
             mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
             mbar_expect_tx(&full_bar[s], kStageBytes);
-            tma_load_2d(s_ring + s * kStageBytes, map, &full_bar[s], 0, im.ring_row0 + h * kRingCap + k * kBlkKeys);
-            tma_load_2d(s_ring + s * kStageBytes + kBoxBytes, map, &full_bar[s], 64, im.ring_row0 + h * kRingCap + k * kBlkKeys);
+            const int row = im.ring_row0 + h * kRingCap + k * kBlkKeys;
+            if (hint) {
+              tma_load_2d_hint(s_ring + s * kStageBytes, map, &full_bar[s], 0, row, pol_stream);
+              tma_load_2d_hint(s_ring + s * kStageBytes + kBoxBytes, map, &full_bar[s], 64, row, pol_stream);
+            } else {
+              tma_load_2d(s_ring + s * kStageBytes, map, &full_bar[s], 0, row);
+              tma_load_2d(s_ring + s * kStageBytes + kBoxBytes, map, &full_bar[s], 64, row);
+            }
             ++it;
           }
         }
@@ -391,6 +409,9 @@ void launch_r(const BatchDev& b, const AttnMmaArgs& a, int sms, cudaStream_t st)
 void launch_attention_mma(const BatchDev& b, const AttnMmaArgs& a, cudaStream_t st) {
   if (b.B <= 0) return;
   PKB_CHECK(a.ctx.lo_off == 0, "attention_mma: bf16 mode only");
+  static const int evict = [] { const char* v = getenv("PARAKEET_B200_ATTN_EVICT"); return (v && v[0] == '0') ? 0 : 1; }();
+  AttnMmaArgs a2 = a;
+  a2.evict_first = evict;
   static int sms = 0;
   if (!sms) {
     int dev = 0;
@@ -399,9 +420,9 @@ void launch_attention_mma(const BatchDev& b, const AttnMmaArgs& a, cudaStream_t 
   }
   static int cfg = -1;
   if (cfg < 0) { const char* v = getenv("PARAKEET_B200_ATTN_CFG"); cfg = v ? atoi(v) : 0; }
-  if (b.max_Tq <= 8) { if (cfg == 1) launch_r<8, 1>(b, a, sms, st); else launch_r<8, 0>(b, a, sms, st); }
-  else if (b.max_Tq <= 16) launch_r<16, 0>(b, a, sms, st);
-  else launch_r<32, 0>(b, a, sms, st);
+  if (b.max_Tq <= 8) { if (cfg == 1) launch_r<8, 1>(b, a2, sms, st); else launch_r<8, 0>(b, a2, sms, st); }
+  else if (b.max_Tq <= 16) launch_r<16, 0>(b, a2, sms, st);
+  else launch_r<32, 0>(b, a2, sms, st);
 }
 
 }  // namespace pkb

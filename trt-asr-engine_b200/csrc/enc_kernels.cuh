@@ -89,6 +89,7 @@ struct AttnMmaArgs {
   const void* map_v;
   int layer;
   int n_slots;
+  int evict_first = 0;           // set by launch_attention_mma: K / V blocks are loaded with an L2 evict-first policy
 };
 void launch_attention_mma(const BatchDev& b, const AttnMmaArgs& a, cudaStream_t st);
 
