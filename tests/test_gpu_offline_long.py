@@ -145,3 +145,37 @@ def test_capacity_error(model_small, features_ref):
     with pytest.raises(RuntimeError, match="row capacity"):
         eng.offline_utterances([sid], features=[_feats(features_ref, 10.0, 1)], decode=False)
     eng.close()
+
+
+@pytest.mark.parametrize("prec", [1, 0], ids=["precise", "bf16"])
+def test_tiny_and_odd_lengths(model_small, oracle_small, features_ref, prec):
+    """Edge sizes in one batch: a single feature frame (1 encoder frame), 9 frames (2), 63 / 64 / 65 encoder frames (tile edge)."""
+    m = oracle_small
+    full = _feats(features_ref, 6.0, 42)
+    lens = [1, 9, 8 * 63 - 3, 8 * 64 - 7, 8 * 64 + 1]
+    fs = [np.ascontiguousarray(full[:, :n]) for n in lens]
+    eng = binding.Engine(model_small, max_streams=len(fs), precision=prec, max_rows=256)
+    sids = [eng.open() for _ in fs]
+    outs = eng.offline_utterances(sids, features=fs, want_encoder_output=True, decode=True)
+    for i, f in enumerate(fs):
+        enc, el = m.offline(torch.from_numpy(f[None]), torch.tensor([f.shape[1]]))
+        assert outs[i].shape == (1024, int(el)), (lens[i], outs[i].shape, int(el))
+        _check(outs[i], enc[0].numpy(), prec, f"{lens[i]} frames")
+        want, toks, amb = _oracle_trace(m, enc, int(el))
+        _check_trace(eng.last_steps(sids[i]), want, amb, prec, f"{lens[i]} frames trace")
+    assert [outs[i].shape[1] for i in range(5)] == [1, 2, 63, 64, 65]
+    eng.close()
+
+
+def test_offline_argument_errors(model_small):
+    eng = binding.Engine(model_small, max_streams=2, precision=0, max_rows=64)
+    s = eng.open()
+    with pytest.raises(RuntimeError, match="at least one feature frame"):
+        eng.offline_utterances([s], audio=[np.zeros(399, np.float32)])
+    eng.push_features(s, np.zeros((128, 41), np.float32))          # a stream that already streams cannot switch
+    eng.step()
+    with pytest.raises(RuntimeError, match="freshly opened"):
+        eng.offline_utterances([s], features=[np.zeros((128, 40), np.float32)])
+    with pytest.raises(RuntimeError, match="bad stream id"):
+        eng.offline_utterances([7], features=[np.zeros((128, 40), np.float32)])
+    eng.close()

@@ -604,9 +604,65 @@ dwconv_kernel(BatchDev b, DwConvArgs a) {
   }
   if (!offline) *reinterpret_cast<float4*>(cache) = make_float4(nc[0], nc[1], nc[2], nc[3]);
 }
+// bf16 mode: two adjacent channels per thread (4-byte loads / stores of bf16 pairs: 128 B per warp and row instead of 64 B, half
+// the threads); per channel the arithmetic and its order are exactly those of dwconv_kernel.
+__global__ void __launch_bounds__(256)
+dwconv2_kernel(BatchDev b, DwConvArgs a) {
+  pdl_enter();
+  const int e = blockIdx.x, ch = 2 * (blockIdx.y * 256 + threadIdx.x);
+  const int Tq = b.Tq[e], qlen = b.qlen[e], row0 = b.row_off[e];
+  float* cache = a.cache_tm + (size_t)b.slot[e] * a.slot_stride + (size_t)ch * kTimeCtx;
+  float w[2][kConvK];
+#pragma unroll
+  for (int i = 0; i < kConvK; ++i) { w[0][i] = a.w[ch * kConvK + i]; w[1][i] = a.w[(ch + 1) * kConvK + i]; }
+  const float2 bias = *reinterpret_cast<const float2*>(a.bias + ch);
+  auto ld_c = [&](int t) -> float2 {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a.c_bf16 + (size_t)(row0 + t) * kDModel + ch));
+  };
+  const bool offline = b.offline[e] != 0;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 c0 = offline ? z4 : *reinterpret_cast<const float4*>(cache);
+  const float4 c1 = offline ? z4 : *reinterpret_cast<const float4*>(cache + kTimeCtx);
+  float win[2][kConvK];
+  win[0][0] = c0.x; win[0][1] = c0.y; win[0][2] = c0.z; win[0][3] = c0.w;
+  win[1][0] = c1.x; win[1][1] = c1.y; win[1][2] = c1.z; win[1][3] = c1.w;
+#pragma unroll
+  for (int i = 4; i < kConvK; ++i) {
+    const int t = i - 4;
+    const float2 v = (t < Tq && t < qlen) ? ld_c(t) : make_float2(0.f, 0.f);
+    win[0][i] = v.x; win[1][i] = v.y;
+  }
+  float nc[2][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = Tq + 1 + i;
+    float2 v = make_float2(0.f, 0.f);
+    if (idx < 4) v = idx == 0 ? make_float2(c0.x, c1.x) : idx == 1 ? make_float2(c0.y, c1.y) : idx == 2 ? make_float2(c0.z, c1.z) : make_float2(c0.w, c1.w);
+    else if (idx - 4 < Tq) v = (idx - 4 < qlen) ? ld_c(idx - 4) : make_float2(0.f, 0.f);
+    nc[0][i] = v.x; nc[1][i] = v.y;
+  }
+  for (int t = 0; t < Tq; ++t) {
+    float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kConvK; ++i) { acc0 = fmaf(w[0][i], win[0][i], acc0); acc1 = fmaf(w[1][i], win[1][i], acc1); }
+    acc0 += bias.x; acc1 += bias.y;
+    *reinterpret_cast<__nv_bfloat162*>(a.out.ptr + (size_t)(row0 + t) * a.out.lda + ch) = __floats2bfloat162_rn(silu(acc0), silu(acc1));
+#pragma unroll
+    for (int i = 0; i < kConvK - 1; ++i) { win[0][i] = win[0][i + 1]; win[1][i] = win[1][i + 1]; }
+    const int tn = t + 5;
+    const float2 v = (tn < Tq && tn < qlen) ? ld_c(tn) : make_float2(0.f, 0.f);
+    win[0][kConvK - 1] = v.x; win[1][kConvK - 1] = v.y;
+  }
+  if (!offline) {
+    *reinterpret_cast<float4*>(cache) = make_float4(nc[0][0], nc[0][1], nc[0][2], nc[0][3]);
+    *reinterpret_cast<float4*>(cache + kTimeCtx) = make_float4(nc[1][0], nc[1][1], nc[1][2], nc[1][3]);
+  }
+}
 void launch_dwconv(const BatchDev& b, const DwConvArgs& a, cudaStream_t st) {
   if (b.B <= 0) return;
-  launch_k(dwconv_kernel, dim3(b.B, kDModel / 256), dim3(256), 0, st, b, a);
+  static const bool pair = [] { const char* v = getenv("PARAKEET_B200_DWCONV2"); return !(v && v[0] == '0'); }();
+  if (pair && a.c_bf16 != nullptr && a.out.lo_off == 0) launch_k(dwconv2_kernel, dim3(b.B, kDModel / 512), dim3(256), 0, st, b, a);
+  else launch_k(dwconv_kernel, dim3(b.B, kDModel / 256), dim3(256), 0, st, b, a);
   PKB_CUDA(cudaGetLastError());
 }
 
