@@ -199,6 +199,8 @@ def main():
     ap.add_argument("--ref-chunks", type=int, default=40, help="chunks per stream of the cpu_baseline sample (~15 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--engines-per-gpu", type=int, default=0, help="0 = auto (2 when this rank holds <= --two-engine-max-streams streams)")
+    ap.add_argument("--two-engine-max-streams", type=int, default=0)
     ap.add_argument("--longform", type=int, default=0, help="also run BASELINE config 5's shape: this many clips through the whole-utterance offline path")
     ap.add_argument("--longform-seconds", type=float, default=3600.0)
     ap.add_argument("--prefill-chunks", type=int, default=88,
@@ -235,8 +237,24 @@ def main():
 
     mine = shard(args.streams, rank, world)
     n = len(mine)
-    eng = binding.Engine(model, device_id=local_rank, max_streams=n, precision=args.precision, max_rows=8 * n)
-    sids = np.array([eng.open() for _ in mine], np.int32)
+    # Small per-GPU batches are bound by the latency of ~410 dependent launches per step, not by throughput: two engines per GPU
+    # (each with half of this rank's streams, its own CUDA stream and buffers, driven by its own host thread) interleave two such
+    # chains on the same GPU.  Large batches are throughput-bound and use one engine.
+    n_eng = args.engines_per_gpu if args.engines_per_gpu > 0 else (2 if 2 <= n <= args.two_engine_max_streams else 1)
+    bounds = [(j * n // n_eng, (j + 1) * n // n_eng) for j in range(n_eng)]
+    engs = [binding.Engine(model, device_id=local_rank, max_streams=hi - lo, precision=args.precision, max_rows=8 * (hi - lo))
+            for lo, hi in bounds]
+    sid_lists = [np.array([e.open() for _ in range(hi - lo)], np.int32) for e, (lo, hi) in zip(engs, bounds)]
+    eng = engs[0]
+    sids = sid_lists[0]
+    pool = None
+    if n_eng > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(n_eng)
+
+    def each(fn):
+        """fn(engine index) on every engine: concurrently (ctypes calls release the GIL) when there is more than one"""
+        return [fn(0)] if pool is None else list(pool.map(fn, range(n_eng)))
 
     prof_steps = 2
     total_pushes = 16            # audio ring: the pushes cycle through 16 x 0.24 s of synthetic audio per stream
@@ -267,14 +285,19 @@ def main():
     def do_step(resident: bool):
         k = cursor[0] % total_pushes
         cursor[0] += 1
-        if resident:
-            eng.push_audio_batch_device(sids, dev[k].data_ptr(), SAMPLES_PER_STEP, SAMPLES_PER_STEP)
-        else:
-            eng.push_audio_batch(sids, host[k].data_ptr(), SAMPLES_PER_STEP, SAMPLES_PER_STEP)
-        return eng.step()
+
+        def work(j):
+            off = bounds[j][0] * SAMPLES_PER_STEP * 4
+            if resident:
+                engs[j].push_audio_batch_device(sid_lists[j], dev[k].data_ptr() + off, SAMPLES_PER_STEP, SAMPLES_PER_STEP)
+            else:
+                engs[j].push_audio_batch(sid_lists[j], host[k].data_ptr() + off, SAMPLES_PER_STEP, SAMPLES_PER_STEP)
+            return engs[j].step()
+        return sum(each(work))
 
     # prefill: 2 pushes = 46 frames >= the 41 frames of chunk 0; afterwards every push yields exactly one chunk per stream
-    eng.push_audio_batch_device(sids, dev[0].data_ptr(), SAMPLES_PER_STEP, SAMPLES_PER_STEP)
+    for j in range(n_eng):
+        engs[j].push_audio_batch_device(sid_lists[j], dev[0].data_ptr() + bounds[j][0] * SAMPLES_PER_STEP * 4, SAMPLES_PER_STEP, SAMPLES_PER_STEP)
     cursor[0] = 1
     assert do_step(True) == n, "prefill did not produce chunk 0 for every stream"
     for _ in range(max(args.prefill_chunks - 1, 0) + args.warmup):
@@ -285,16 +308,17 @@ def main():
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    launches0 = eng.kernel_launches()
-    e0 = eng.event_record()
+    launches0 = sum(e.kernel_launches() for e in engs)
+    ev0 = [e.event_record() for e in engs]
     t0 = time.perf_counter()
     for _ in range(args.steps):
         do_step(True)
-    e1 = eng.event_record()
-    dev_ms = eng.event_elapsed_ms(e0, e1)
+    ev1 = [e.event_record() for e in engs]
+    # device time of the region: every engine's own stream, first event to last event; the job ends with the slowest engine
+    dev_ms = max(e.event_elapsed_ms(a, b) for e, a, b in zip(engs, ev0, ev1))
     barrier()
     wall_resident = time.perf_counter() - t0
-    launches = eng.kernel_launches() - launches0
+    launches = sum(e.kernel_launches() for e in engs) - launches0
     clocks = sampler.stop()
 
     # ---- timed region 2: end to end from pinned host memory through the C ABI (H2D + step + D2H of the decode traces)
@@ -309,14 +333,20 @@ def main():
     barrier()
 
     # ---- per-launch timing of the dominant kernel (tcgen05 GEMM) for the roofline
-    eng.profile_enable(True)
+    for e in engs:
+        e.profile_enable(True)
     for _ in range(prof_steps):
         do_step(True)
-    gemm_ms, gemm_flops, gemm_launches = eng.profile_read()
-    attn_ms, attn_bytes, attn_launches = eng.profile_read_class(1)
-    fe_ms, fe_bytes, fe_launches = eng.profile_read_class(2)
-    dec_ms, dec_bytes, dec_loops = eng.profile_read_class(3)
-    eng.profile_enable(False)
+
+    def prof(cls):
+        r = [e.profile_read_class(cls) for e in engs]
+        return sum(x[0] for x in r), sum(x[1] for x in r), sum(x[2] for x in r)
+    gemm_ms, gemm_flops, gemm_launches = prof(0)
+    attn_ms, attn_bytes, attn_launches = prof(1)
+    fe_ms, fe_bytes, fe_launches = prof(2)
+    dec_ms, dec_bytes, dec_loops = prof(3)
+    for e in engs:
+        e.profile_enable(False)
     # the frontend kernel at a size where it is not launch-bound: log-mel of one 1 h clip (BASELINE config 5's frontend)
     fe1h = None
     if world == 1 and not args.no_latency:
@@ -326,7 +356,7 @@ def main():
         fe1h = eng.profile_read_class(2)
         eng.profile_enable(False)
 
-    n_tokens = sum(len(eng.tokens(int(s))) for s in sids[: min(n, 64)])
+    n_tokens = sum(len(eng.tokens(int(s))) for s in sids[: min(len(sids), 64)])
     dev_s, e2e_max, wall_max = reduce_timings([dev_ms / 1e3, e2e_s, wall_resident], world)
     if rank != 0:
         if world > 1:
@@ -344,7 +374,7 @@ def main():
         "config": {"workload": f"{args.streams} concurrent streams sharded over {world} GPU(s) (stream i -> rank i mod N), cache-aware "
                                "streaming chunk step (57-frame slice, cache 256, 24-frame shift) + TDT greedy decode, GPU log-mel frontend",
                    "model": f"parakeet-tdt-0.6b-v3 architecture, seeded random weights, {args.layers} layers",
-                   "streams_per_gpu": n, "audio_s_per_step": args.streams * AUDIO_S_PER_STEP, "precision": args.precision,
+                   "streams_per_gpu": n, "engines_per_gpu": n_eng, "audio_s_per_step": args.streams * AUDIO_S_PER_STEP, "precision": args.precision,
                    "l2_policy": "working set per step (1.2 GB weights + 29 MB K/V per stream) exceeds the 126 MB L2; no flush needed",
                    "wall_ms_per_step_resident": 1e3 * wall_max / args.steps, "tokens_emitted_first_64_streams": n_tokens,
                    "cache_last_channel_len_at_timing": cache_len0, "prefill_chunks": args.prefill_chunks},
@@ -382,7 +412,8 @@ def main():
              "peak": peak_hbm, "unit": "GB/s", "frac": fe1h[1] / fe1h[0] / 1e6 / peak_hbm, "launches_timed": int(fe1h[2]),
              "algorithmic_bytes_per_launch": fe1h[1] / max(fe1h[2], 1)})
     if args.longform > 0 and world == 1:
-        eng.close()
+        for e in engs:
+            e.close()
         line["longform"] = longform(binding, model, args.precision, args.longform, args.longform_seconds, synth_clip(10.0, 1234))
     if not args.no_latency and world == 1:
         line["latency_1stream"] = latency_one_stream(binding, model, args.precision, clips[0])
