@@ -1,0 +1,67 @@
+"""BASELINE.json's full size on one GPU: 1024 concurrent streams, 24 layers, batched chunk steps.
+
+The oracle cannot run 1024 streams in seconds, so the full batch is checked through size-independent properties:
+  * the 1024 streams carry 16 distinct clips, 64 copies each, spread over the whole batch: every copy must produce the
+    bit-identical (time_idx, token, duration) trace as the first one -- no cross-stream leakage, no dependence on the row a
+    stream occupies in the packed batch, deterministic kernels;
+  * the 16 distinct streams are also run by the CPU oracle (closed loop, 10 chunks each).  precise mode: >= 99 % of the chunk
+    traces identical; bf16 mode: the first chunk (before any closed-loop divergence can compound) identical wherever every
+    decision of the oracle has a top-2 logit gap above TAU (the parity-set test covers bf16 chunk by chunk in functional mode).
+"""
+import numpy as np
+import pytest
+import torch
+
+import binding
+from conftest import normalized_features
+from model_ref import DecodeState, ModelRef, prime, streaming_schedule, tdt_greedy_chunk
+
+pytestmark = pytest.mark.gpu
+N_STREAMS, N_DISTINCT, N_CHUNKS, TAU = 1024, 16, 10, 0.25
+
+
+@pytest.mark.parametrize("precision", [0, 1], ids=["bf16", "precise"])
+def test_1024_streams_duplicates_and_oracle(model_full, features_ref, precision):
+    secs = 0.41 + 0.24 * N_CHUNKS + 0.5
+    feats = []
+    for i in range(N_DISTINCT):
+        f = normalized_features(features_ref, secs, 3000 + i)
+        f[0] = 0.0
+        feats.append(f)
+    eng = binding.Engine(model_full, max_streams=N_STREAMS, precision=precision)
+    sids = [eng.open() for _ in range(N_STREAMS)]
+    traces = [[] for _ in range(N_STREAMS)]
+    for b, e in streaming_schedule(N_CHUNKS):
+        for i, s in enumerate(sids):
+            eng.push_features(s, feats[i % N_DISTINCT][:, b:e])
+        assert eng.step() == N_STREAMS
+        for i, s in enumerate(sids):
+            traces[i].append(eng.last_steps(s))
+    tokens = [eng.tokens(s) for s in sids]
+    assert all(eng.cache_len(s) == 1 + 3 * (N_CHUNKS - 1) for s in sids)
+    eng.close()
+    # every copy equals the first copy of its clip
+    bad = [i for i in range(N_STREAMS) if traces[i] != traces[i % N_DISTINCT] or tokens[i] != tokens[i % N_DISTINCT]]
+    assert not bad, f"{len(bad)} of {N_STREAMS} streams differ from their duplicate, first: {bad[:4]}"
+    assert sum(len(t) for t in tokens[:N_DISTINCT]) > 0, "no stream emitted a token"
+    # the distinct streams against the oracle
+    m = ModelRef(model_full)
+    same = total = first_conf = first_same = 0
+    for d in range(N_DISTINCT):
+        st = DecodeState(m)
+        prime(m, st)
+        cc, ct, cl = m.initial_cache(1)
+        for k, (b, e) in enumerate(streaming_schedule(N_CHUNKS)):
+            enc, el, cc, ct, cl = m.stream_step(torch.from_numpy(feats[d][None, :, b:e]), torch.tensor([e - b]), cc, ct, cl)
+            mg = []
+            want = [(t, tok, dur) for t, tok, dur, _ in tdt_greedy_chunk(m, st, enc, int(el), margins=mg)]
+            total += 1
+            same += int(traces[d][k] == want)
+            if k == 0 and all(a > TAU and b_ > TAU for a, b_ in mg):
+                first_conf += 1
+                first_same += int(traces[d][k] == want)
+    print(f"\n[1024 streams precision={precision}] chunks identical to the oracle: {same}/{total}; confident first chunks {first_same}/{first_conf}")
+    if precision == 1:
+        assert same >= 0.99 * total, f"{same}/{total}"
+    else:
+        assert first_conf >= N_DISTINCT // 2 and first_same == first_conf
