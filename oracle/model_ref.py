@@ -14,11 +14,16 @@ reference only through these call sites, which this file follows:
   * greedy TDT loop  tools/verify_nemo/tdt_trace.py:277-353 == cpp/src/parakeet_trt.cpp:2914-3676 -> tdt_greedy_chunk
   * 41/57-frame schedule  tools/verify_nemo/streaming_encoder_reference.py:522-550 -> streaming_schedule
 
-PARITY UNPINNED for encoder/predictor/joint numerics: NeMo, the .nemo weights and the golden JSONL tensors
+PARITY UNPINNED AGAINST THE REFERENCE'S OWN OUTPUTS: NeMo, the .nemo weights and the golden JSONL tensors
 (artifacts/reference/, git-ignored) are all absent, so this restates NeMo 2.6.0's published module semantics
-(SURVEY.md section 8a [UPSTREAM]).  What IS pinned by checked-in reference evidence and tested in
-tests/test_oracle_kats.py: layouts, the schedule, encoded_lengths=3, cache_len sequences 1,4,7,... and
-1,2,3,4 (docs/VALIDATION_REPORT_TRACE.md:173-177, 209-213), conv-cache last column zero (:212).
+(SURVEY.md section 8a [UPSTREAM]).  What pins it instead:
+  * numerically, against independent public implementations that ARE in this image (tests/test_oracle_vs_hf.py): the
+    full-context encoder equals transformers 5.5 `ParakeetEncoder` (Hugging Face's port of the NeMo FastConformer encoder)
+    on the same seeded weights to 2e-6; the predictor equals torch.nn.LSTM (what NeMo's RNNTDecoder wraps) to 1e-6.
+    The cache-aware streaming step runs the same `_layer()` as the full-context encoder;
+  * structurally, by checked-in reference evidence (tests/test_oracle_kats.py): layouts, the schedule, encoded_lengths=3,
+    cache_len sequences 1,4,7,... and 1,2,3,4 (docs/VALIDATION_REPORT_TRACE.md:173-177, 209-213), conv-cache last column
+    zero (:212).
 """
 from __future__ import annotations
 

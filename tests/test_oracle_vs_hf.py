@@ -1,0 +1,97 @@
+"""Pins the oracle's encoder restatement against an INDEPENDENT public implementation of the same architecture:
+`transformers.models.parakeet.ParakeetEncoder` (Hugging Face's port of NeMo's FastConformer encoder, validated by its authors
+against NeMo; transformers 5.5 ships in this image).  NeMo itself, the .nemo weights and the reference's golden JSONL are not
+available offline, so this is the strongest numeric pin the sandbox allows for `oracle/model_ref.py`:
+the seeded synthetic weights are loaded into both, name by name, and the full-context (`offline`) encoder outputs compared.
+What it covers: dw_striding subsampling (conv indices, channel-major flatten), the RelPositionalEncoding table and rel_shift
+indexing, pos_bias_u / pos_bias_v, the (ac + bd)/sqrt(d_k) scaling, the macaron FFN halves, GLU -> depthwise -> BatchNorm(eval)
+-> SiLU ordering, LayerNorm placement.  The cache-aware streaming step shares `_layer()` with `offline()` and is pinned
+structurally in test_oracle_kats.py.  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import model_dir, normalized_features
+from model_ref import ModelRef
+
+parakeet = pytest.importorskip("transformers.models.parakeet.modeling_parakeet")
+from transformers.models.parakeet.configuration_parakeet import ParakeetEncoderConfig      # noqa: E402
+
+
+def _hf_encoder(m: ModelRef):
+    cfg = ParakeetEncoderConfig(hidden_size=m.D, num_hidden_layers=m.L, num_attention_heads=m.H, intermediate_size=m.cfg["ff_dim"],
+                                hidden_act="silu", attention_bias=False, convolution_bias=False, conv_kernel_size=m.cfg["conv_kernel"],
+                                subsampling_factor=8, subsampling_conv_channels=m.cfg["sub_channels"], num_mel_bins=m.cfg["feat_in"],
+                                dropout=0.0, dropout_positions=0.0, layerdrop=0.0, activation_dropout=0.0, attention_dropout=0.0,
+                                max_position_embeddings=5000, scale_input=False)      # xscaling false: audit_model_arch.json:34
+    cfg._attn_implementation = "eager"
+    enc = parakeet.ParakeetEncoder(cfg).eval()
+    sd = {}
+    w = m.w
+    for i in (0, 2, 3, 5, 6):
+        sd[f"subsampling.layers.{i}.weight"] = w[f"encoder.pre_encode.conv.{i}.weight"]
+        sd[f"subsampling.layers.{i}.bias"] = w[f"encoder.pre_encode.conv.{i}.bias"]
+    sd["subsampling.linear.weight"] = w["encoder.pre_encode.out.weight"]
+    sd["subsampling.linear.bias"] = w["encoder.pre_encode.out.bias"]
+    for l in range(m.L):
+        p, q = f"encoder.layers.{l}.", f"layers.{l}."
+        for n in ("norm_feed_forward1", "norm_self_att", "norm_conv", "norm_feed_forward2", "norm_out"):
+            sd[q + n + ".weight"] = w[p + n + ".weight"]
+            sd[q + n + ".bias"] = w[p + n + ".bias"]
+        for ff in ("feed_forward1", "feed_forward2"):
+            sd[q + ff + ".linear1.weight"] = w[p + ff + ".linear1.weight"]
+            sd[q + ff + ".linear2.weight"] = w[p + ff + ".linear2.weight"]
+        for a, b in (("linear_q", "q_proj"), ("linear_k", "k_proj"), ("linear_v", "v_proj"), ("linear_out", "o_proj"),
+                     ("linear_pos", "relative_k_proj")):
+            sd[q + f"self_attn.{b}.weight"] = w[p + f"self_attn.{a}.weight"]
+        sd[q + "self_attn.bias_u"] = w[p + "self_attn.pos_bias_u"].reshape(m.H, m.dk)
+        sd[q + "self_attn.bias_v"] = w[p + "self_attn.pos_bias_v"].reshape(m.H, m.dk)
+        for n in ("pointwise_conv1", "pointwise_conv2"):
+            t = w[p + f"conv.{n}.weight"]
+            sd[q + f"conv.{n}.weight"] = t if t.dim() == 3 else t.unsqueeze(-1)
+        sd[q + "conv.depthwise_conv.weight"] = w[p + "conv.depthwise_conv.weight"]
+        for a, b in (("weight", "weight"), ("bias", "bias"), ("running_mean", "running_mean"), ("running_var", "running_var")):
+            sd[q + f"conv.norm.{b}"] = w[p + f"conv.batch_norm.{a}"]
+    missing, unexpected = enc.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all(k.endswith("num_batches_tracked") or k.endswith("inv_freq") for k in missing), missing
+    return enc
+
+
+@pytest.mark.parametrize("seconds", [2.0, 10.0], ids=["2s", "10s"])
+def test_offline_encoder_matches_hf_parakeet(features_ref, seconds):
+    m = ModelRef(model_dir(2))
+    enc = _hf_encoder(m)
+    f = normalized_features(features_ref, seconds, 1234)              # [128, T]
+    f[0] = 0.0
+    x = torch.from_numpy(f[None])
+    want, el = m.offline(x, torch.tensor([f.shape[1]]))               # [1, 1024, T_enc]
+    with torch.no_grad():
+        got = enc(input_features=x.transpose(1, 2)).last_hidden_state  # [1, T_enc, 1024]
+    assert got.shape[1] == int(el) == want.shape[2]
+    d = (got.transpose(1, 2) - want).abs()
+    # two fp32 implementations with different operation order (fused vs separate scaling, conv via Conv1d); measured 1.7e-6 on O(1) outputs
+    assert float(d.max()) < 2e-5, float(d.max())
+    assert float(want.abs().mean()) > 0.1
+
+
+def test_predictor_matches_torch_lstm():
+    """RNNTDecoder.predict is an embedding + torch.nn.LSTM (NeMo rnnt_modules / rnn.py LSTMDropout): the oracle's hand-written
+    cell must equal nn.LSTM loaded with the same weights, step by step with carried state."""
+    m = ModelRef(model_dir(2))
+    H, L = m.cfg["pred_hidden"], m.cfg["pred_layers"]
+    lstm = torch.nn.LSTM(H, H, num_layers=L).eval()
+    pre = "decoder.prediction.dec_rnn.lstm."
+    lstm.load_state_dict({k: m.w[pre + k] for k in lstm.state_dict()})
+    emb = m.w["decoder.prediction.embed.weight"]
+    torch.manual_seed(3)
+    h = 0.3 * torch.randn(L, 2, H)
+    c = 0.3 * torch.randn(L, 2, H)
+    h2, c2 = h.clone(), c.clone()
+    for y in ([5, 8192], [700, 17], [8192, 3]):
+        yt = torch.tensor(y).unsqueeze(1)
+        g, h, c = m.predictor_step(yt, h, c)
+        with torch.no_grad():
+            out, (h2, c2) = lstm(emb[yt[:, 0]].unsqueeze(0), (h2, c2))
+        assert float((g[:, :, 0] - out[0]).abs().max()) < 1e-6
+        assert float((h - h2).abs().max()) < 1e-6 and float((c - c2).abs().max()) < 1e-6
