@@ -351,6 +351,49 @@ def test_debug_tdt_steps_trace(model_small, features_ref, capfd, monkeypatch):
         assert 0 <= t < 3 and blank == int(tok == 8192) and di == dur and adv == (1 if clamped else dur) and clamped == int(blank and dur == 0)
 
 
+def test_tdt_snapshot_dir(model_small, oracle_small, features_ref, tmp_path, monkeypatch):
+    """PARAKEET_TDT_SNAPSHOT_DIR (parakeet_trt.cpp:2315-2400, 2612-2650, 3519-3590): the step-0 tensors of the session's first
+    streaming chunk land in the reference's files; their contents equal the oracle's tensors for that chunk."""
+    import json
+    m = oracle_small
+    f = _feats(features_ref, 1.5, 11)
+    d = tmp_path / "snap"
+    monkeypatch.setenv("PARAKEET_TDT_SNAPSHOT_DIR", str(d))
+    monkeypatch.setenv("PARAKEET_B200_PRECISION", "1")
+    s = binding.ParakeetSessionSafe(model_small, 0, use_fp16=False)
+    s.push_features(np.ascontiguousarray(f[:, :41]), 41)
+    s.push_features(np.ascontiguousarray(f[:, 8:65]), 57)        # only the first chunk is dumped
+    s.close()
+    names = {"features_in_trt.f32", "cache_last_channel_in_trt.f32", "cache_last_time_in_trt.f32", "meta_enc_trt.json",
+             "cache_last_channel_len_out_trt.bin", "cache_last_channel_len_out_trt.json", "enc_slice_trt.f32", "enc_out_t0_trt.f32",
+             "pred_g_trt.f32", "dur_logits_trt.f32", "meta_trt.json"}
+    assert {p.name for p in d.iterdir()} == names
+    rd = lambda n: np.fromfile(str(d / n), np.float32)
+    assert np.array_equal(rd("features_in_trt.f32").reshape(128, 41), f[:, :41])
+    assert rd("cache_last_channel_in_trt.f32").size == m.L * 256 * 1024 and not rd("cache_last_channel_in_trt.f32").any()
+    assert rd("cache_last_time_in_trt.f32").size == m.L * 1024 * 4
+    meta_enc = json.loads((d / "meta_enc_trt.json").read_text())
+    assert meta_enc["features_shape"] == [1, 128, 41] and meta_enc["features_valid"] == 41 and meta_enc["cache_last_channel_len"] == 0
+    assert int(np.fromfile(str(d / "cache_last_channel_len_out_trt.bin"), np.int64)[0]) == 1
+    assert json.loads((d / "cache_last_channel_len_out_trt.json").read_text())["effective"] == 1
+    # the oracle on the same chunk
+    cc, ct, cl = m.initial_cache(1)
+    enc, el, *_ = m.stream_step(torch.from_numpy(f[None, :, :41]), torch.tensor([41]), cc, ct, cl)
+    st = DecodeState(m)
+    prime(m, st)
+    g0 = st.g[0, :, 0].numpy().copy()
+    logits = m.joint_logits(enc[:, :, :1], st.g)[0, 0, 0].numpy()
+    want = tdt_greedy_chunk(m, st, enc, int(el))
+    assert np.abs(rd("enc_slice_trt.f32").reshape(1024, 3) - enc[0].numpy()).max() < 2e-3
+    assert np.abs(rd("enc_out_t0_trt.f32") - enc[0, :, 0].numpy()).max() < 2e-3
+    assert np.abs(rd("pred_g_trt.f32") - g0).max() < 1e-4
+    assert np.abs(rd("dur_logits_trt.f32") - logits[m.vocab:m.vocab + 5]).max() < 2e-3
+    meta = json.loads((d / "meta_trt.json").read_text())
+    assert meta["enc_shape"] == [1, 1024, 3] and meta["dur_offset"] == 8193 and meta["dur_bins_used"] == 5
+    assert (meta["best_tok"], meta["best_dur_idx"]) == (want[0][1], want[0][2])
+    assert meta["best_dur_idx"] == int(np.argmax(rd("dur_logits_trt.f32")))
+
+
 def test_engine_destroy_releases_memory(model_small):
     """create / destroy cycles (what parakeet_create_session / parakeet_destroy_session do per session) must not leak device memory."""
     def cycle():

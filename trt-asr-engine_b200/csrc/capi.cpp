@@ -9,11 +9,15 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <iostream>
 #include <mutex>
 #include <queue>
+#include <sstream>
 #include <string>
 #include <vector>
+
+#include <sys/stat.h>
 
 #include "../../include/parakeet_b200.h"
 #include "../../include/parakeet_trt.h"
@@ -86,6 +90,7 @@ struct ParakeetSession {
   std::chrono::steady_clock::time_point last_partial_emit;
   uint64_t dbg_steps_left = 0;   // PARAKEET_DEBUG_TDT_STEPS: decode steps still to be traced on stderr
   bool offline = false;      // PARAKEET_B200_ENCODER=offline: the reference's non-streaming encoder engine
+  bool snapshot_done = false; // PARAKEET_TDT_SNAPSHOT_DIR: step-0 tensors are dumped once per session
   std::string dbg_id;
   uint64_t dbg_utt = 0, dbg_chunk = 0, dbg_feat = 0;
 };
@@ -141,10 +146,83 @@ void parakeet_reset_utterance(ParakeetSession* session) {
   while (!session->events.empty()) session->events.pop();
 }
 
+// PARAKEET_TDT_SNAPSHOT_DIR (parakeet_trt.cpp:2315-2400, 2612-2650, 3519-3590): once per session, on its first streaming chunk,
+// the tensors around encoder step 0 and joint step (t=0, u=0) are written as raw little-endian f32 files + JSON sidecars under
+// that directory, with the reference's file names, so that its triage scripts (tools/onnxruntime/compare_encoder_step0.py,
+// compare_joint_step0.py) can read this library's tensors in place of the TensorRT ones.
+static void write_f32_file(const std::string& path, const float* p, size_t n) {
+  std::ofstream f(path, std::ios::binary);
+  f.write(reinterpret_cast<const char*>(p), (std::streamsize)(n * sizeof(float)));
+}
+static void write_text_file(const std::string& path, const std::string& t) { std::ofstream f(path); f << t; }
+
+struct SnapshotPre { std::vector<float> cache_ch, cache_tm, g; int cache_len = 0; int y_id = -1; };
+
+static void snapshot_before(ParakeetSession* s, const std::string& dir, const float* feats, size_t T, SnapshotPre* pre) {
+  const int L = s->eng->n_layers();
+  mkdir(dir.c_str(), 0777);
+  pre->cache_ch.assign((size_t)L * pkb::kCacheS * pkb::kDModel, 0.f);
+  pre->cache_tm.assign((size_t)L * pkb::kDModel * pkb::kTimeCtx, 0.f);
+  s->eng->export_stream_state(s->sid, pre->cache_ch.data(), pre->cache_tm.data(), &pre->cache_len);
+  std::vector<float> h(pkb::kPredL * pkb::kPredH), c(pkb::kPredL * pkb::kPredH);
+  pre->g.assign(pkb::kPredH, 0.f);
+  pre->y_id = s->eng->prime_now(s->sid);           // the predictor is primed lazily; the snapshot wants g as the joint will see it
+  s->eng->get_decoder_state(s->sid, h.data(), c.data(), pre->g.data());
+  write_f32_file(dir + "/features_in_trt.f32", feats, (size_t)pkb::kNMels * T);
+  write_f32_file(dir + "/cache_last_channel_in_trt.f32", pre->cache_ch.data(), pre->cache_ch.size());
+  write_f32_file(dir + "/cache_last_time_in_trt.f32", pre->cache_tm.data(), pre->cache_tm.size());
+  std::ostringstream meta;
+  meta << "{\"features_shape\":[1," << pkb::kNMels << "," << T << "],\"features_valid\":" << T << ",\"features_dtype\":\"f32\","
+       << "\"cache_last_channel_shape\":[1," << L << "," << pkb::kCacheS << "," << pkb::kDModel << "],\"cache_last_time_shape\":[1," << L << ","
+       << pkb::kDModel << "," << pkb::kTimeCtx << "],\"cache_last_channel_len\":" << pre->cache_len << "}";
+  write_text_file(dir + "/meta_enc_trt.json", meta.str());
+}
+
+static void snapshot_after(ParakeetSession* s, const std::string& dir, const SnapshotPre& pre) {
+  const pkb::ChunkResult& r = s->eng->last_chunk(s->sid);
+  // cache_last_channel_len_out: raw int64 + the JSON the reference writes next to it
+  const int64_t len_out = r.cache_len_out;
+  { std::ofstream f(dir + "/cache_last_channel_len_out_trt.bin", std::ios::binary); f.write(reinterpret_cast<const char*>(&len_out), 8); }
+  std::ostringstream lj;
+  lj << "{\"dtype\":\"i64\",\"shape\":\"[1]\",\"bytes\":8,\"raw_i32\":" << (int32_t)len_out << ",\"raw_i64\":" << len_out << ",\"raw_f32\":\"nan\",\"raw\":"
+     << len_out << ",\"effective\":" << len_out << "}";
+  write_text_file(dir + "/cache_last_channel_len_out_trt.json", lj.str());
+  // encoder slice fed to the joint [1,1024,3], its frame 0, the predictor output of step (0,0), the duration logits of that step
+  std::vector<float> enc((size_t)pkb::kDModel * pkb::kValidOut, 0.f), enc_t0(pkb::kDModel), logits(pkb::kJointOut);
+  const int T_enc = s->eng->last_encoder_output(s->sid, enc.data(), pkb::kValidOut);
+  const int Tc = std::min(T_enc, (int)pkb::kValidOut);
+  for (int c = 0; c < pkb::kDModel; ++c) enc_t0[c] = Tc > 0 ? enc[(size_t)c * Tc] : 0.f;
+  s->eng->joint_step(1, 1, 1, enc_t0.data(), pre.g.data(), logits.data());
+  write_f32_file(dir + "/enc_slice_trt.f32", enc.data(), (size_t)pkb::kDModel * Tc);
+  write_f32_file(dir + "/enc_out_t0_trt.f32", enc_t0.data(), enc_t0.size());
+  write_f32_file(dir + "/pred_g_trt.f32", pre.g.data(), pre.g.size());
+  write_f32_file(dir + "/dur_logits_trt.f32", logits.data() + pkb::kVocab, pkb::kNDur);
+  const int best_tok = r.steps.empty() ? -1 : r.steps[0].token, best_dur = r.steps.empty() ? -1 : r.steps[0].duration;
+  std::ostringstream meta;
+  meta << "{\"enc_shape\":[1," << pkb::kDModel << "," << Tc << "],\"enc_out_t0_shape\":[1," << pkb::kDModel << ",1],\"pred_shape\":[1," << pkb::kPredH
+       << ",1],\"dur_shape\":[" << pkb::kNDur << "],\"tok_offset\":0,\"dur_offset\":" << pkb::kVocab << ",\"token_span\":" << pkb::kVocab
+       << ",\"dur_bins_used\":" << pkb::kNDur << ",\"best_tok\":" << best_tok << ",\"best_dur_idx\":" << best_dur << ",\"y_id\":" << pre.y_id << "}";
+  write_text_file(dir + "/meta_trt.json", meta.str());
+  std::cerr << "[parakeet_trt] tdt_snapshot dir=" << dir << " enc=" << dir << "/enc_slice_trt.f32 pred=" << dir << "/pred_g_trt.f32 dur=" << dir
+            << "/dur_logits_trt.f32 enc_out_t0=" << dir << "/enc_out_t0_trt.f32\n";
+}
+
 static void push_one_chunk(ParakeetSession* s, const float* feats, size_t T) {
   const size_t before = s->eng->tokens(s->sid).size();
+  const char* snap = std::getenv("PARAKEET_TDT_SNAPSHOT_DIR");
+  const bool want_snap = snap && *snap && !s->offline && !s->snapshot_done;
+  SnapshotPre pre;
+  if (want_snap) {
+    try { snapshot_before(s, snap, feats, T, &pre); }
+    catch (const std::exception& e) { std::cerr << "[parakeet_trt] WARN: failed to write encoder snapshot: " << e.what() << "\n"; }
+  }
   s->eng->queue_features(s->sid, feats, (int)T);
   s->eng->step();
+  if (want_snap) {
+    try { snapshot_after(s, snap, pre); }
+    catch (const std::exception& e) { std::cerr << "[parakeet_trt] WARN: failed to write TDT snapshot: " << e.what() << "\n"; }
+    s->snapshot_done = true;
+  }
   const std::vector<int>& toks = s->eng->tokens(s->sid);
   if (s->dbg_steps_left > 0) {
     // decode trace in the line format the reference prints and tools/verify_nemo/compare_tdt_trace.py:43-66 parses

@@ -176,6 +176,7 @@ struct Engine::Stream {
   std::vector<int> tokens;
   std::vector<int> token_frames;         // encoder frame (80 ms timebase) each token was emitted on, counted from the utterance start
   long long enc_frames = 0;              // encoder frames decoded so far (the live edge of the transcript)
+  int last_entry = -1, last_out_T = 0;   // where the stream's encoder_output of the last batched pass sits in enc_out [B,1024,out_T]
   ChunkResult last;
 };
 
@@ -727,6 +728,26 @@ bool Engine::has_pending(int sid) const {
 }
 const std::vector<int>& Engine::tokens(int sid) const { return streams_[sid]->tokens; }
 const ChunkResult& Engine::last_chunk(int sid) const { return streams_[sid]->last; }
+int Engine::prime_now(int sid) {
+  PKB_CHECK(sid >= 0 && sid < (int)streams_.size() && streams_[sid]->open, "bad stream id");
+  Stream& s = *streams_[sid];
+  if (s.needs_prime) { s.needs_prime = false; prime_streams({sid}); }
+  if (!s.tokens.empty()) return s.tokens.back();
+  return tok_lang_ >= 0 ? tok_lang_ : tok_start_ >= 0 ? tok_start_ : kBlank;
+}
+int Engine::last_encoder_output(int sid, float* out, int cap_T) {
+  PKB_CHECK(sid >= 0 && sid < (int)streams_.size(), "bad stream id");
+  const Stream& s = *streams_[sid];
+  PKB_CHECK(s.last_entry >= 0 && s.last_out_T > 0, "last_encoder_output: the stream has not been through a batched pass (or only a whole-utterance one)");
+  const int T = std::min(s.last.encoded_len, cap_T);
+  std::vector<float> tmp((size_t)kDModel * s.last_out_T);
+  PKB_CUDA(cudaMemcpyAsync(tmp.data(), im_->enc_out + (size_t)s.last_entry * kDModel * s.last_out_T, tmp.size() * sizeof(float),
+                           cudaMemcpyDeviceToHost, st_));
+  PKB_CUDA(cudaStreamSynchronize(st_));
+  for (int c = 0; c < kDModel; ++c)
+    for (int t = 0; t < T; ++t) out[(size_t)c * T + t] = tmp[(size_t)c * s.last_out_T + t];
+  return s.last.encoded_len;
+}
 const std::vector<int>& Engine::token_frames(int sid) const { return streams_[sid]->token_frames; }
 long long Engine::encoder_frames_done(int sid) const { return streams_[sid]->enc_frames; }
 int Engine::stable_prefix(int sid, int revision_window_ms) const {
@@ -1293,6 +1314,7 @@ void Engine::run_batch(const std::vector<Entry>& entries, float* enc_out_host) {
       if (streams_[e.sid]->needs_prime) { fresh.push_back(e.sid); streams_[e.sid]->needs_prime = false; }
     prime_streams(fresh);
   }
+  for (auto& sp : streams_) sp->last_entry = -1;      // enc_out is about to be overwritten
   const BatchDev b = upload_batch(entries);
   const int max_steps = b.max_tenc > kValidOut ? kMaxStepsOffline : kMaxStepsPerChunk;
   run_encoder(b);
@@ -1315,6 +1337,7 @@ void Engine::run_batch(const std::vector<Entry>& entries, float* enc_out_host) {
     const int keep = Tq - kCacheDrop;
     s.last = ChunkResult();
     s.last.encoded_len = h[10 * C + i];
+    s.last_entry = i; s.last_out_T = b.max_tenc;
     if (decode) {
       const int n = std::min(im.res_host[i], max_steps);
       const int* st = im.res_host + C + (size_t)i * max_steps * 3;

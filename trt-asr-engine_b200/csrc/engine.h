@@ -70,6 +70,10 @@ class Engine {
   const ChunkResult& last_chunk(int sid) const;
   // Timestamps in the encoder timebase (80 ms per frame: 10 ms feature shift x 8 subsampling, docs/ARCHITECTURE_RUNTIME.md:46-47):
   // the absolute encoder frame each token was emitted on, and the number of encoder frames decoded so far.
+  // encoder_output [1024, T] (contract layout, T = min(encoded_len, cap_T)) of the stream's chunk in the LAST batched pass; returns encoded_len
+  int last_encoder_output(int sid, float* out, int cap_T);
+  // run the deferred predictor priming of a freshly reset stream now; returns the token the predictor was last stepped on
+  int prime_now(int sid);
   const std::vector<int>& token_frames(int sid) const;
   long long encoder_frames_done(int sid) const;
   // "Stable prefix + revision window" (MAGNOLIA_INTEGRATION_HANDOFF.md:105-135): number of leading tokens older than
