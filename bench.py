@@ -78,29 +78,37 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.windows = index, None, [], []
 
     def start(self):
+        """Start the sampling process (it takes a few hundred ms to deliver its first line, so it is started during the warm-up
+        steps); only samples received inside a window opened by begin() / end() -- the timed regions -- are reported."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._pump, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
 
+    def begin(self):
+        self.windows.append([time.perf_counter(), None])
+
+    def end(self):
+        self.windows[-1][1] = time.perf_counter()
+
     def _pump(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
         self.proc.terminate()
         sm, mx, reasons = [], 0.0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        inside = [ln for ts, ln in self.lines if any(a <= ts <= (b if b is not None else ts) for a, b in self.windows)]
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             try:
                 sm.append(float(f[0]))
@@ -300,14 +308,16 @@ def main():
         engs[j].push_audio_batch_device(sid_lists[j], dev[0].data_ptr() + bounds[j][0] * SAMPLES_PER_STEP * 4, SAMPLES_PER_STEP, SAMPLES_PER_STEP)
     cursor[0] = 1
     assert do_step(True) == n, "prefill did not produce chunk 0 for every stream"
-    for _ in range(max(args.prefill_chunks - 1, 0) + args.warmup):
+    sampler = ClockSampler(local_rank)
+    for i in range(max(args.prefill_chunks - 1, 0) + args.warmup):
+        if i == max(args.prefill_chunks - 1, 0):
+            sampler.start()          # running (and past its start-up latency) before the timed regions begin
         assert do_step(True) == n
     cache_len0 = eng.cache_len(int(sids[0]))
 
     # ---- timed region 1: audio resident in HBM, CUDA events on the engine stream
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.begin()
     launches0 = sum(e.kernel_launches() for e in engs)
     ev0 = [e.event_record() for e in engs]
     t0 = time.perf_counter()
@@ -319,18 +329,21 @@ def main():
     barrier()
     wall_resident = time.perf_counter() - t0
     launches = sum(e.kernel_launches() for e in engs) - launches0
-    clocks = sampler.stop()
+    sampler.end()
 
     # ---- timed region 2: end to end from pinned host memory through the C ABI (H2D + step + D2H of the decode traces)
     for _ in range(2):
         do_step(False)
     barrier()
+    sampler.begin()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         do_step(False)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    sampler.end()
     barrier()
+    clocks = sampler.stop()      # samples taken during the two timed regions (device-resident and end-to-end)
 
     # ---- per-launch timing of the dominant kernel (tcgen05 GEMM) for the roofline
     for e in engs:
