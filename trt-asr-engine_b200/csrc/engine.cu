@@ -1090,56 +1090,8 @@ void Engine::run_encoder(const BatchDev& b, const LongForm* lf) {
     RUN_GEMM(act, wt, M, nullptr, e);
     return LnResidual{nullptr, 0, 0, 0.f, 0};
   };
-  LnResidual res{};
-  launch_layernorm(im.x, M, im.layers[0].n_ff1_g, im.layers[0].n_ff1_b, nullptr, nullptr, 0, im.a_ln.out(), nullptr, st_); ++launches_;
-  const size_t kv_elem = split ? 4 : 2;
-  for (int l = 0; l < L_; ++l) {
-    const LayerW& w = im.layers[l];
-    char* kr = (char*)im.kring + (size_t)l * im.ring_layer_elems * kv_elem;
-    char* vr = (char*)im.vring + (size_t)l * im.ring_layer_elems * kv_elem;
-    // FFN 1 (half-step residual)
-    g_tc_site = 64;
-    { EpiParams e; e.mode = EPI_SILU_ACT; e.out_act = im.a_ff.ptr; e.lda_out = kFF; e.lo_off_out = im.a_ff.lo_off;
-      RUN_GEMM(im.a_ln, w.ff1_1, M, nullptr, e); }
-    g_tc_site = 128;
-    res = residual_gemm(im.a_ff, w.ff1_2, 0.5f);
-    // self-attention
-    AcacheOut ac{};
-    if (im.acache) {
-      ac.ring = (char*)im.acache + (size_t)l * im.ring_layer_elems * kv_elem; ac.is_f32 = split ? 1 : 0;
-      ac.row_entry = b.row_entry; ac.row_pos = b.row_pos; ac.entry_slot = b.slot; ac.entry_head = b.head;
-    }
-    launch_layernorm(im.x, M, w.n_att_g, w.n_att_b, nullptr, nullptr, 0, im.a_ln.out(), (im.acache && !lf) ? &ac : nullptr, st_, &res); ++launches_;
-    g_tc_site = 256;
-    if (lf) {
-      // whole-utterance attention: q | k | v rows stay in one [M,3072] buffer (no rings), the layer's projected position
-      // table linear_pos(pe) over 2Tm-1 relative positions is one more GEMM, the score tiles are formed in lf_attention
-      { EpiParams e;
-        if (split) { e.mode = EPI_F32; e.out_f32 = (float*)im.lf_qkv; e.ldo = 3 * kDModel; }
-        else { e.mode = EPI_ACT; e.out_act = (__nv_bfloat16*)im.lf_qkv; e.lda_out = 3 * kDModel; }
-        RUN_GEMM(im.a_ln, w.qkv, M, nullptr, e); }
-      { EpiParams e;
-        if (split) { e.mode = EPI_F32; e.out_f32 = (float*)im.lf_ppos; e.ldo = kDModel; }
-        else { e.mode = EPI_ACT; e.out_act = (__nv_bfloat16*)im.lf_ppos; e.lda_out = kDModel; }
-        RUN_GEMM(im.lf_pos_act, im.lf_wpos[l], 2 * lf->Tm - 1, nullptr, e); }
-      LfAttnArgs a;
-      if (split) { a.qkv_f32 = (const float*)im.lf_qkv; a.ppos_f32 = (const float*)im.lf_ppos; }
-      else { a.qkv_bf16 = (const __nv_bfloat16*)im.lf_qkv; a.ppos_bf16 = (const __nv_bfloat16*)im.lf_ppos; }
-      a.Tm = lf->Tm; a.max_T = b.max_Tq; a.bias_u = w.bias_u; a.bias_v = w.bias_v; a.ctx = im.a_ln.out();
-      if (!split) {
-        if (l == 0) {      // same buffers for every layer: the maps only depend on this call's row counts
-          make_tensor_map_2d(&im.lf_map_qkv, im.lf_qkv, (uint64_t)M, 3 * kDModel, 3 * kDModel, 64);
-          make_tensor_map_2d(&im.lf_map_pos, im.lf_ppos, (uint64_t)(2 * lf->Tm - 1), kDModel, kDModel, 128);
-        }
-        a.map_qkv = &im.lf_map_qkv; a.map_pos = &im.lf_map_pos;
-      }
-      double pairs = 0.0;      // sum over utterances of T^2 (host copy of the batch fields)
-      for (int i = 0; i < b.B; ++i) { const double t = im.batch_ints_host[6 * im.Bcap + i]; pairs += t * t; }
-      // algorithmic FLOPs: content score, position score and value product, 128 MACs each per (query, key, head)
-      const int pi = prof_begin(4, 2.0 * 3.0 * kDHead * kHeads * pairs);
-      launch_lf_attention(b, a, st_); ++launches_;
-      prof_end(pi);
-    } else {
+  // q | k | v projection + attention of one layer over [per-stream K/V ring (256 cached rows) || the chunk's rows]
+  auto attention_streaming = [&](int l, const LayerW& w, char* kr, char* vr) {
     { EpiParams e; e.mode = EPI_QKV; e.out_f32 = im.q; e.ldo = kDModel; e.row_entry = b.row_entry; e.row_pos = b.row_pos;
       e.entry_slot = b.slot; e.entry_head = b.head; e.kring = kr; e.vring = vr; e.kv_f32 = split ? 1 : 0;
       e.k_natural = im.attn_mma ? 1 : 0;
@@ -1164,7 +1116,59 @@ void Engine::run_encoder(const BatchDev& b, const LongForm* lf) {
       a.bias_v = w.bias_v; a.ctx = im.a_ln.out();
       launch_attention(b, a, st_); ++launches_;
     }
+  };
+  // whole-utterance attention of one layer: q | k | v rows stay in one [M,3072] buffer (no rings), the layer's projected position
+  // table linear_pos(pe) over 2Tm-1 relative positions is one more GEMM, the score tiles are formed in lf_attention
+  auto attention_whole_utterance = [&](int l, const LayerW& w, const LongForm& lf) {
+    { EpiParams e;
+      if (split) { e.mode = EPI_F32; e.out_f32 = (float*)im.lf_qkv; e.ldo = 3 * kDModel; }
+      else { e.mode = EPI_ACT; e.out_act = (__nv_bfloat16*)im.lf_qkv; e.lda_out = 3 * kDModel; }
+      RUN_GEMM(im.a_ln, w.qkv, M, nullptr, e); }
+    { EpiParams e;
+      if (split) { e.mode = EPI_F32; e.out_f32 = (float*)im.lf_ppos; e.ldo = kDModel; }
+      else { e.mode = EPI_ACT; e.out_act = (__nv_bfloat16*)im.lf_ppos; e.lda_out = kDModel; }
+      RUN_GEMM(im.lf_pos_act, im.lf_wpos[l], 2 * lf.Tm - 1, nullptr, e); }
+    LfAttnArgs a;
+    if (split) { a.qkv_f32 = (const float*)im.lf_qkv; a.ppos_f32 = (const float*)im.lf_ppos; }
+    else { a.qkv_bf16 = (const __nv_bfloat16*)im.lf_qkv; a.ppos_bf16 = (const __nv_bfloat16*)im.lf_ppos; }
+    a.Tm = lf.Tm; a.max_T = b.max_Tq; a.bias_u = w.bias_u; a.bias_v = w.bias_v; a.ctx = im.a_ln.out();
+    if (!split) {
+      if (l == 0) {      // same buffers for every layer: the maps only depend on this call's row counts
+        make_tensor_map_2d(&im.lf_map_qkv, im.lf_qkv, (uint64_t)M, 3 * kDModel, 3 * kDModel, 64);
+        make_tensor_map_2d(&im.lf_map_pos, im.lf_ppos, (uint64_t)(2 * lf.Tm - 1), kDModel, kDModel, 128);
+      }
+      a.map_qkv = &im.lf_map_qkv; a.map_pos = &im.lf_map_pos;
     }
+    double pairs = 0.0;      // sum over utterances of T^2 (host copy of the batch fields)
+    for (int i = 0; i < b.B; ++i) { const double t = im.batch_ints_host[6 * im.Bcap + i]; pairs += t * t; }
+    // algorithmic FLOPs: content score, position score and value product, 128 MACs each per (query, key, head)
+    const int pi = prof_begin(4, 2.0 * 3.0 * kDHead * kHeads * pairs);
+    launch_lf_attention(b, a, st_); ++launches_;
+    prof_end(pi);
+  };
+  LnResidual res{};
+  launch_layernorm(im.x, M, im.layers[0].n_ff1_g, im.layers[0].n_ff1_b, nullptr, nullptr, 0, im.a_ln.out(), nullptr, st_); ++launches_;
+  const size_t kv_elem = split ? 4 : 2;
+  for (int l = 0; l < L_; ++l) {
+    const LayerW& w = im.layers[l];
+    char* kr = (char*)im.kring + (size_t)l * im.ring_layer_elems * kv_elem;
+    char* vr = (char*)im.vring + (size_t)l * im.ring_layer_elems * kv_elem;
+    // FFN 1 (half-step residual)
+    g_tc_site = 64;
+    { EpiParams e; e.mode = EPI_SILU_ACT; e.out_act = im.a_ff.ptr; e.lda_out = kFF; e.lo_off_out = im.a_ff.lo_off;
+      RUN_GEMM(im.a_ln, w.ff1_1, M, nullptr, e); }
+    g_tc_site = 128;
+    res = residual_gemm(im.a_ff, w.ff1_2, 0.5f);
+    // self-attention
+    AcacheOut ac{};
+    if (im.acache) {
+      ac.ring = (char*)im.acache + (size_t)l * im.ring_layer_elems * kv_elem; ac.is_f32 = split ? 1 : 0;
+      ac.row_entry = b.row_entry; ac.row_pos = b.row_pos; ac.entry_slot = b.slot; ac.entry_head = b.head;
+    }
+    launch_layernorm(im.x, M, w.n_att_g, w.n_att_b, nullptr, nullptr, 0, im.a_ln.out(), (im.acache && !lf) ? &ac : nullptr, st_, &res); ++launches_;
+    g_tc_site = 256;
+    if (lf) attention_whole_utterance(l, w, *lf);
+    else attention_streaming(l, w, kr, vr);
     g_tc_site = 512;
     res = residual_gemm(im.a_ln, w.out, 1.0f);
     // convolution module
@@ -1173,14 +1177,16 @@ void Engine::run_encoder(const BatchDev& b, const LongForm* lf) {
     { EpiParams e; e.mode = EPI_GLU_F32; e.out_f32 = im.cglu; e.ldo = kDModel;
       if (!split) { e.out_act = reinterpret_cast<__nv_bfloat16*>(im.cglu); e.lda_out = kDModel; }      // bf16 mode: bf16 elements in the same buffer
       RUN_GEMM(im.a_ln, w.pw1, M, nullptr, e); }
-    if (lf) {
+    if (lf) {      // whole utterance: symmetric (4,4) zero padding, no time cache
       LfDwConvArgs a; a.c = split ? im.cglu : nullptr; a.c_bf16 = split ? nullptr : reinterpret_cast<const __nv_bfloat16*>(im.cglu);
       a.w = w.dw_w; a.bias = w.dw_b; a.out = im.a_ln.out(); a.M = M;
       launch_lf_dwconv(b, a, st_); ++launches_;
-    } else
-    { DwConvArgs a; a.c = split ? im.cglu : nullptr; a.c_bf16 = split ? nullptr : reinterpret_cast<const __nv_bfloat16*>(im.cglu); a.cache_tm = im.cache_tm + (size_t)l * kDModel * kTimeCtx; a.slot_stride = (long long)L_ * kDModel * kTimeCtx;
+    } else {
+      DwConvArgs a; a.c = split ? im.cglu : nullptr; a.c_bf16 = split ? nullptr : reinterpret_cast<const __nv_bfloat16*>(im.cglu);
+      a.cache_tm = im.cache_tm + (size_t)l * kDModel * kTimeCtx; a.slot_stride = (long long)L_ * kDModel * kTimeCtx;
       a.w = w.dw_w; a.bias = w.dw_b; a.out = im.a_ln.out();
-      launch_dwconv(b, a, st_); ++launches_; }
+      launch_dwconv(b, a, st_); ++launches_;
+    }
     g_tc_site = 2048;
     res = residual_gemm(im.a_ln, w.pw2, 1.0f);
     // FFN 2
