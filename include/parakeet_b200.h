@@ -142,11 +142,15 @@ int32_t pkb_encoder_offline_step(PkbEngine* engine, int32_t B, int32_t T, const 
  * per_feature_norm != 0, the whole-utterance normalisation of rust/features run on the GPU) or features (features[i]: n_frames[i]
  * frames, [128,T] bins-major if bins_major != 0 else [T,128]); the other pair is NULL.  Self-attention spans ALL frames of an
  * utterance; the sum of encoder frames (T/8 each) must fit the engine's max_rows.  encoder_output (NULL, or per-utterance
- * pointers, each NULL or [1024, T_enc_i] f32) receives the encoder output in the contract layout; decode != 0 fills
- * pkb_stream_tokens / pkb_stream_last_steps of each stream.  Host pointers. */
+ * pointers, each NULL or [1024, T_enc_i] f32) receives the encoder output in the contract layout; decode == 1 fills
+ * pkb_stream_tokens / pkb_stream_last_steps of each stream before returning; decode == 2 only parks the utterances' encoder
+ * rows on the device: pkb_offline_decode_pending() then decodes ALL parked utterances of the engine in one batched TDT loop
+ * (clips encoded in several memory-sized groups share one decode pass); it returns the number of utterances decoded.
+ * Host pointers. */
 int32_t pkb_offline_utterances(PkbEngine* engine, int32_t n, const int32_t* streams, const float* const* audio,
                                const size_t* n_samples, int32_t per_feature_norm, const float* const* features,
                                const int32_t* n_frames, int32_t bins_major, float* const* encoder_output, int32_t decode);
+int32_t pkb_offline_decode_pending(PkbEngine* engine);
 /* encoder frames produced for T feature frames: three times floor((L-1)/2)+1 */
 int32_t pkb_encoded_length(int32_t n_frames);
 /* predictor: y [B,1] i64, h,c [2,B,640] -> g [B,640,1], h_out,c_out [2,B,640] */

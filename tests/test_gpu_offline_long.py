@@ -179,3 +179,29 @@ def test_offline_argument_errors(model_small):
     with pytest.raises(RuntimeError, match="bad stream id"):
         eng.offline_utterances([7], features=[np.zeros((128, 40), np.float32)])
     eng.close()
+
+
+@pytest.mark.parametrize("prec", [1, 0], ids=["precise", "bf16"])
+def test_deferred_batched_decode(model_small, features_ref, prec):
+    """decode=2 parks the encoder rows of utterances encoded in separate calls; pkb_offline_decode_pending decodes them in one
+    batched loop.  With the same encoder groups the encoder rows are the same bits, and the per-utterance decode arithmetic does
+    not depend on how many utterances share the loop (same joint backend for <= 16), so the traces equal immediate decoding."""
+    fs = [_feats(features_ref, sec, 60 + i) for i, sec in enumerate((3.0, 12.0, 7.5, 20.0, 5.0))]
+    eng = binding.Engine(model_small, max_streams=5, precision=prec, max_rows=512)
+    sids = [eng.open() for _ in fs]
+    want = []
+    groups = [(0, 2), (2, 3), (3, 5)]
+    for lo, hi in groups:                           # immediate decode, same encoder groups (same GEMM shapes -> same encoder bits)
+        eng.offline_utterances(sids[lo:hi], features=fs[lo:hi], decode=True)
+        for s in sids[lo:hi]:
+            want.append((eng.last_steps(s), eng.tokens(s), eng.token_frames(s)))
+            eng.reset(s)
+    eng.offline_utterances(sids[:2], features=fs[:2], decode=2)      # encoded in three groups ...
+    eng.offline_utterances(sids[2:3], features=fs[2:3], decode=2)
+    assert eng.tokens(sids[0]) == [] and eng.last_steps(sids[0]) == []
+    eng.offline_utterances(sids[3:], features=fs[3:], decode=2)
+    assert eng.offline_decode_pending() == 5                         # ... decoded together
+    assert eng.offline_decode_pending() == 0
+    for s, (steps, toks, frames) in zip(sids, want):
+        assert eng.last_steps(s) == steps and eng.tokens(s) == toks and eng.token_frames(s) == frames
+    eng.close()

@@ -26,7 +26,7 @@ TRT_ASR_SYMBOLS = ["trt_asr_create_session", "trt_asr_destroy_session", "trt_asr
                    "trt_asr_push_features_f32", "trt_asr_poll_event"]
 B200_SYMBOLS = ["pkb_last_error", "pkb_version", "pkb_engine_create", "pkb_engine_destroy", "pkb_engine_num_layers",
                 "pkb_engine_kernel_launches", "pkb_stream_open", "pkb_stream_close", "pkb_stream_reset", "pkb_stream_push_features",
-                "pkb_stream_push_audio", "pkb_stream_set_feature_norm", "pkb_stream_set_offline", "pkb_encoder_offline_step", "pkb_offline_utterances", "pkb_encoded_length", "pkb_engine_push_audio_batch",
+                "pkb_stream_push_audio", "pkb_stream_set_feature_norm", "pkb_stream_set_offline", "pkb_encoder_offline_step", "pkb_offline_utterances", "pkb_offline_decode_pending", "pkb_encoded_length", "pkb_engine_push_audio_batch",
                 "pkb_engine_push_audio_batch_device", "pkb_engine_event_record", "pkb_engine_event_elapsed_ms",
                 "pkb_engine_profile_enable", "pkb_engine_profile_read", "pkb_engine_profile_read_class", "pkb_engine_step", "pkb_stream_has_pending",
                 "pkb_stream_num_tokens", "pkb_stream_tokens", "pkb_stream_token_frames", "pkb_stream_encoder_frames", "pkb_stream_stable_prefix", "pkb_stream_last_steps", "pkb_stream_cache_len",
@@ -137,6 +137,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.pkb_offline_utterances.argtypes = [vp, C.c_int32, ip, C.POINTER(fp), C.POINTER(C.c_size_t), C.c_int32, C.POINTER(fp), ip, C.c_int32,
                                            C.POINTER(fp), C.c_int32]
     lib.pkb_encoded_length.argtypes = [C.c_int32]
+    lib.pkb_offline_decode_pending.argtypes = [vp]
     lib.pkb_predictor_step.argtypes = [vp, C.c_int32, lp, fp, fp, fp, fp, fp]
     lib.pkb_joint_step.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, fp, fp, fp]
     lib.pkb_logmel.argtypes = [vp, fp, C.c_size_t, fp, C.c_size_t, C.c_int32]
@@ -404,7 +405,7 @@ class Engine:
         return out, el
 
     def offline_utterances(self, sids, audio=None, features=None, per_feature_norm: bool = True, bins_major: bool = True,
-                           want_encoder_output: bool = False, decode: bool = True):
+                           want_encoder_output: bool = False, decode=True):
         """Whole-utterance offline path (pkb_offline_utterances): `audio` = list of 1-D f32 PCM arrays, or `features` = list of
         [128,T] (bins_major) / [T,128] arrays; one freshly opened stream id per utterance.  Returns the list of
         encoder_output [1024,T_enc] arrays (or None); tokens / decode trace through tokens(s) / last_steps(s)."""
@@ -431,6 +432,10 @@ class Engine:
         self._chk(self._lib.pkb_offline_utterances(self._e, n, ids.ctypes.data_as(C.POINTER(C.c_int32)), a_ptrs, ns, int(per_feature_norm),
                                                    f_ptrs, nf, int(bins_major), o_ptrs, int(decode)))
         return outs
+
+    def offline_decode_pending(self) -> int:
+        """Decode every utterance parked by offline_utterances(decode=2) in one batched TDT loop."""
+        return self._chk(self._lib.pkb_offline_decode_pending(self._e))
 
     def predictor_step(self, y, h, c):
         y = np.ascontiguousarray(y, np.int64)

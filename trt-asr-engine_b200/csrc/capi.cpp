@@ -566,6 +566,10 @@ int32_t pkb_offline_utterances(PkbEngine* e, int32_t n, const int32_t* streams, 
     return 0;
   });
 }
+int32_t pkb_offline_decode_pending(PkbEngine* e) {
+  PKB_ENTER(e);
+  return guarded([&] { return e->eng->offline_decode_pending(); });
+}
 int32_t pkb_encoded_length(int32_t L) {
   for (int i = 0; i < 3; ++i) L = L <= 0 ? 0 : (L - 1) / 2 + 1;
   return L;

@@ -176,6 +176,8 @@ struct Engine::Stream {
   std::vector<int> tokens;
   std::vector<int> token_frames;         // encoder frame (80 ms timebase) each token was emitted on, counted from the utterance start
   long long enc_frames = 0;              // encoder frames decoded so far (the live edge of the transcript)
+  long long lf_store_off = -1;           // >= 0: the utterance's joint encoder projections wait in the deferred-decode store at this row
+  int lf_store_T = 0;
   int last_entry = -1, last_out_T = 0;   // where the stream's encoder_output of the last batched pass sits in enc_out [B,1024,out_T]
   ChunkResult last;
 };
@@ -252,6 +254,8 @@ struct Engine::Impl {
   void* lf_qkv = nullptr;                // [Mcap][3072] q | k | v  (bf16, f32 in precise mode)
   void* lf_ppos = nullptr;               // [2*Mcap][1024] this layer's projected table (bf16 / f32)
   int* lf_steps = nullptr;               // decode trace [B][lf_steps_per][3]
+  float* lf_store = nullptr;             // deferred decode: joint.enc(encoder rows) of encoded, not yet decoded utterances [rows][640]
+  size_t lf_store_cap = 0, lf_store_used = 0;
   TensorMap lf_map_qkv, lf_map_pos;      // TMA maps of this call's q|k|v rows and projected table (bf16 mode)
   size_t lf_steps_ints = 0;
   FrontSegment* segs_dev = nullptr;
@@ -706,6 +710,7 @@ void Engine::reset_stream(int sid) {
   s.sched_chunk = 0; s.has_norm = false;
   s.dev_off = 0; s.dev_fill = 0;
   s.cache_len = 0; s.head = 0; s.chunks = 0; s.tokens.clear(); s.token_frames.clear(); s.enc_frames = 0; s.last = ChunkResult();
+  s.lf_store_off = -1; s.lf_store_T = 0;
   const size_t slot = (size_t)s.slot;
   PKB_CUDA(cudaMemsetAsync(im.cache_tm + slot * L_ * kDModel * kTimeCtx, 0, (size_t)L_ * kDModel * kTimeCtx * 4, st_));
   PKB_CUDA(cudaMemsetAsync(im.pred_h + slot * kPredL * kPredH, 0, kPredL * kPredH * 4, st_));
@@ -1219,13 +1224,16 @@ void Engine::run_predictor_pass(const DecodeDev& d) {
 
 static DecodeDev make_decode_dev(Engine::Impl& im, const EngineOptions& opt, int B, const int* slot, const int* row_off, const int* t_enc);
 
-void Engine::run_decode(const BatchDev& b, const int* slots, int* steps, int max_steps) {
+void Engine::run_decode(const BatchDev& b, const int* slots, int* steps, int max_steps, const float* enc_proj_rows) {
   Impl& im = *im_;
-  // joint encoder projection for every packed row: E = joint.enc(x) + bias
+  // joint encoder projection for every packed row: E = joint.enc(x) + bias  (or rows projected earlier: deferred decode)
   g_tc_site = 16;
-  { EpiParams e; e.mode = EPI_BIAS_F32; e.out_f32 = im.enc_proj; e.ldo = kJointH; e.bias = im.joint_enc_b;
-    RUN_GEMM(im.a_xf, im.joint_enc, b.M, nullptr, e); }
+  if (enc_proj_rows == nullptr) {
+    EpiParams e; e.mode = EPI_BIAS_F32; e.out_f32 = im.enc_proj; e.ldo = kJointH; e.bias = im.joint_enc_b;
+    RUN_GEMM(im.a_xf, im.joint_enc, b.M, nullptr, e);
+  }
   DecodeDev d = make_decode_dev(im, opt_, b.B, slots ? slots : b.slot, b.row_off, im.batch_ints + 10 * im.Bcap);
+  if (enc_proj_rows) d.enc_proj = enc_proj_rows;
   d.max_steps = b.max_tenc > kValidOut ? kMaxStepsOffline : kMaxStepsPerChunk;
   if (steps) { d.steps = steps; d.max_steps = max_steps; }
   d.fused_argmax = (opt_.gemm_backend == 2 || (opt_.gemm_backend == 0 && b.B > 16)) && tc_mask() < 0 ? 1 : 0;
@@ -1711,9 +1719,35 @@ void Engine::offline_utterances(int n, const int* sids, const float* const* pcm,
     rows.resize((size_t)b.M * kDModel);
     PKB_CUDA(cudaMemcpyAsync(rows.data(), im.x, rows.size() * sizeof(float), cudaMemcpyDeviceToHost, st_));
   }
+  if (decode == 2) {
+    // deferred decode: only project the rows for the joint now and park them; offline_decode_pending() decodes every parked
+    // utterance of the engine in ONE batched loop (a decode iteration costs the same launch chain for 4 or for 32 utterances)
+    if (im.lf_store_used + (size_t)b.M > im.lf_store_cap) {
+      const size_t cap = std::max(im.lf_store_cap * 2, im.lf_store_used + (size_t)b.M);
+      float* p = (float*)dev_alloc_bytes(cap * kJointH * sizeof(float));
+      im.dev_allocs.push_back(p);
+      if (im.lf_store_used) PKB_CUDA(cudaMemcpyAsync(p, im.lf_store, im.lf_store_used * kJointH * sizeof(float), cudaMemcpyDeviceToDevice, st_));
+      PKB_CUDA(cudaStreamSynchronize(st_));
+      if (im.lf_store) {
+        im.dev_allocs.erase(std::find(im.dev_allocs.begin(), im.dev_allocs.end(), (void*)im.lf_store));
+        cudaFree(im.lf_store);
+      }
+      im.lf_store = p;
+      im.lf_store_cap = cap;
+    }
+    g_tc_site = 16;
+    { EpiParams e; e.mode = EPI_BIAS_F32; e.out_f32 = im.lf_store + im.lf_store_used * kJointH; e.ldo = kJointH; e.bias = im.joint_enc_b;
+      RUN_GEMM(im.a_xf, im.joint_enc, b.M, nullptr, e); }
+    for (int i = 0; i < n; ++i) {
+      Stream& s = *streams_[sids[i]];
+      s.lf_store_off = (long long)im.lf_store_used + roff[i];
+      s.lf_store_T = h[6 * C + i];
+    }
+    im.lf_store_used += (size_t)b.M;
+  }
   // ---- greedy TDT over every frame of every utterance
   std::vector<int> counts, recs;
-  if (decode) {
+  if (decode == 1) {
     run_decode(b, b.head, im.lf_steps, steps_per);
     counts.resize(n);
     recs.resize((size_t)n * steps_per * 3);
@@ -1734,7 +1768,7 @@ void Engine::offline_utterances(int n, const int* sids, const float* const* pcm,
     s.last.encoded_len = Te;
     s.frames_written += T[i];
     s.chunks += 1;
-    if (decode) {
+    if (decode == 1) {
       const int cnt = std::min(counts[i], steps_per);
       const int* st = recs.data() + (size_t)i * steps_per * 3;
       for (int k = 0; k < cnt; ++k) {
@@ -1744,6 +1778,62 @@ void Engine::offline_utterances(int n, const int* sids, const float* const* pcm,
       s.enc_frames += Te;
     }
   }
+}
+
+// Decode every utterance whose encoder rows were parked by offline_utterances(decode = 2), all in one batched TDT loop.
+int Engine::offline_decode_pending() {
+  Impl& im = *im_;
+  std::vector<int> sids;
+  for (int i = 0; i < (int)streams_.size(); ++i)
+    if (streams_[i]->open && streams_[i]->lf_store_off >= 0) sids.push_back(i);
+  const int n = (int)sids.size();
+  if (n == 0) return 0;
+  PKB_CUDA(cudaStreamSynchronize(st_));
+  std::vector<int> fresh;
+  for (int sid : sids)
+    if (streams_[sid]->needs_prime) { fresh.push_back(sid); streams_[sid]->needs_prime = false; }
+  prime_streams(fresh);
+  int* h = im.batch_ints_host;
+  const int C = im.Bcap;
+  int* head = h + 9 * C;      // decoder-state slots (see offline_utterances)
+  int* tenc = h + 10 * C;
+  int* roff = h + kNumBatchFields * C + 2 * (C + 1);
+  BatchDev b;
+  b.B = n;
+  for (int i = 0; i < n; ++i) {
+    const Stream& s = *streams_[sids[i]];
+    PKB_CHECK(s.lf_store_off < (1ll << 31), "deferred-decode store too large");
+    head[i] = s.slot; tenc[i] = s.lf_store_T; roff[i] = (int)s.lf_store_off;      // each entry's own first row (not a prefix sum here)
+    b.max_tenc = std::max(b.max_tenc, s.lf_store_T);
+  }
+  roff[n] = 0;
+  b.max_Tq = b.max_tenc;
+  const size_t nints = (size_t)kNumBatchFields * C + 3 * (C + 1);
+  PKB_CUDA(cudaMemcpyAsync(im.batch_ints, h, nints * sizeof(int), cudaMemcpyHostToDevice, st_));
+  b.head = im.batch_ints + 9 * C;
+  b.row_off = im.batch_ints + kNumBatchFields * C + 2 * (C + 1);
+  const int steps_per = b.max_tenc * (kMaxSymbols + 1);
+  lf_prepare(0, (size_t)n * steps_per * 3);
+  run_decode(b, b.head, im.lf_steps, steps_per, im.lf_store);
+  std::vector<int> counts(n), recs((size_t)n * steps_per * 3);
+  PKB_CUDA(cudaMemcpyAsync(counts.data(), im.n_steps, n * sizeof(int), cudaMemcpyDeviceToHost, st_));
+  PKB_CUDA(cudaMemcpyAsync(recs.data(), im.lf_steps, recs.size() * sizeof(int), cudaMemcpyDeviceToHost, st_));
+  PKB_CUDA(cudaStreamSynchronize(st_));
+  if (im.profile) profile_collect();
+  for (int i = 0; i < n; ++i) {
+    Stream& s = *streams_[sids[i]];
+    const int cnt = std::min(counts[i], steps_per);
+    const int* st = recs.data() + (size_t)i * steps_per * 3;
+    s.last.steps.clear();
+    for (int k = 0; k < cnt; ++k) {
+      s.last.steps.push_back(StepRecord{st[3 * k], st[3 * k + 1], st[3 * k + 2]});
+      if (st[3 * k + 1] != kBlank) { s.tokens.push_back(st[3 * k + 1]); s.token_frames.push_back((int)(s.enc_frames + st[3 * k])); }
+    }
+    s.enc_frames += s.lf_store_T;
+    s.lf_store_off = -1; s.lf_store_T = 0;
+  }
+  im.lf_store_used = 0;
+  return n;
 }
 
 void Engine::predictor_step(int B, const int64_t* y, const float* h, const float* c, float* g, float* h_out, float* c_out) {

@@ -103,9 +103,12 @@ class Engine {
   // (pcm[i], n_samples[i]; log-mel and optional whole-utterance per-feature normalisation run on the GPU) or features
   // (feats[i]: T[i] frames, bins-major [128,T] when bins_major else frames-major [T,128]).  The encoder attends over ALL frames
   // of an utterance (no caches, no 256-frame limit); sum of encoder frames <= max_rows.  enc_out[i] (optional, host) receives
-  // encoder_output [1024, T_enc_i]; decode != 0 runs greedy TDT over every frame: tokens(sid) / last_chunk(sid).
+  // encoder_output [1024, T_enc_i]; decode == 1 runs greedy TDT over every frame now: tokens(sid) / last_chunk(sid); decode == 2
+  // defers it to offline_decode_pending().
   void offline_utterances(int n, const int* sids, const float* const* pcm, const size_t* n_samples, int per_feature_norm,
                           const float* const* feats, const int* T, int bins_major, float* const* enc_out, int decode);
+  // decode == 2 in offline_utterances parks the utterances' rows; this decodes all parked utterances in one batched loop; returns how many
+  int offline_decode_pending();
   void predictor_step(int B, const int64_t* y, const float* h, const float* c, float* g, float* h_out, float* c_out);
   void joint_step(int B, int T, int U, const float* enc, const float* pred, float* out);
   // GPU frontend on host buffers: pcm[n] -> frames-major [T,128]; per_feature_norm applies utterance mean/std
@@ -143,7 +146,7 @@ class Engine {
   struct LongForm { int Tm; };       // whole-utterance pass: Tm = longest utterance (centre of the relative-position table)
   void run_encoder(const BatchDev& b, const LongForm* lf = nullptr);
   // slots / steps / max_steps override the per-chunk defaults for the whole-utterance path
-  void run_decode(const BatchDev& b, const int* slots = nullptr, int* steps = nullptr, int max_steps = 0);
+  void run_decode(const BatchDev& b, const int* slots = nullptr, int* steps = nullptr, int max_steps = 0, const float* enc_proj_rows = nullptr);
   void lf_prepare(size_t total_frames, size_t steps_ints);
   void run_predictor_pass(const DecodeDev& d);
   void frontend_pass();
