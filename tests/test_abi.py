@@ -100,3 +100,10 @@ def test_weights_container_roundtrip(tmp_path):
     # round-to-nearest-even at the bf16 boundary
     x = np.array([1.0 + 2 ** -8, 1.0 + 3 * 2 ** -8], np.float32)
     assert f32_to_bf16_bits(x).tolist() == [0x3F80, 0x3F82]
+
+
+def test_encoded_length_formula():
+    """pkb_encoded_length == NeMo calc_length applied three times (floor((L - 1) / 2) + 1); pure host function, no GPU."""
+    lib = binding.load_library()
+    for n, want in [(0, 0), (1, 1), (2, 1), (9, 2), (41, 6), (57, 8), (256, 32), (998, 125), (359998, 45000)]:
+        assert lib.pkb_encoded_length(n) == want, n
