@@ -114,3 +114,38 @@ def test_cli_whole_utterance(tmp_path, model_small):
     eng.offline_utterances([s], audio=[pcm], per_feature_norm=True)
     assert lines[0] == eng.text(s)
     eng.close()
+
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("layout", ["bins_major", "frames_major"])
+def test_cli_parses_reference_written_tap(tmp_path, layout):
+    """tests/golden/tap_features_*.{raw,json} were written by the reference's own FeatureTapWriter (cpp/include/audio_tap.h:600-780,
+    tests/golden/make_tap_golden.py): the CLI reads the sidecar (layout, mel_bins, format) and the raw file before it needs a GPU."""
+    _build()
+    run = subprocess.run([CLI, os.path.join(GOLDEN, f"tap_features_{layout}.json"), "--features-input", "--model-dir", str(tmp_path), "-v"],
+                         capture_output=True, text=True)
+    assert "Loaded 48 frames of 128 mel features" in run.stderr, run.stderr
+    assert run.returncode == 1 and "session creation failed" in run.stderr      # no model / no GPU here: fails loudly after parsing
+
+
+@pytest.mark.gpu
+def test_cli_replays_reference_written_taps(model_small):
+    """Both layouts of the reference-written tap hold the same 48 frames: same transcript, equal to pushing the frames directly."""
+    _build()
+    outs = []
+    for layout in ("bins_major", "frames_major"):
+        run = subprocess.run([CLI, os.path.join(GOLDEN, f"tap_features_{layout}.raw"), "--features-input", "--model-dir", model_small],
+                             capture_output=True, text=True, env=dict(os.environ, PARAKEET_EMIT_FINAL_EACH_CHUNK="1"), timeout=300)
+        assert run.returncode == 0, run.stderr
+        outs.append([ln for ln in run.stdout.splitlines() if ln.startswith("Transcript: ")])
+    assert outs[0] == outs[1] and len(outs[0]) == 1
+    f = np.fromfile(os.path.join(GOLDEN, "tap_features_bins_major.raw"), np.float32).reshape(128, 48)
+    assert np.array_equal(f, np.fromfile(os.path.join(GOLDEN, "tap_features_frames_major.raw"), np.float32).reshape(48, 128).T)
+    eng = binding.Engine(model_small, max_streams=1, precision=0)
+    s = eng.open()
+    eng.push_features(s, f)
+    eng.step()
+    assert outs[0][0] == "Transcript: " + eng.text(s)
+    eng.close()
