@@ -178,6 +178,9 @@ def test_offline_argument_errors(model_small):
         eng.offline_utterances([s], features=[np.zeros((128, 40), np.float32)])
     with pytest.raises(RuntimeError, match="bad stream id"):
         eng.offline_utterances([7], features=[np.zeros((128, 40), np.float32)])
+    s2 = eng.open()
+    with pytest.raises(RuntimeError, match="one utterance per call"):
+        eng.offline_utterances([s2, s2], features=[np.zeros((128, 40), np.float32)] * 2)
     eng.close()
 
 

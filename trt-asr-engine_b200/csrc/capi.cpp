@@ -9,6 +9,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <filesystem>
 #include <fstream>
 #include <iostream>
 #include <mutex>
@@ -16,8 +17,6 @@
 #include <sstream>
 #include <string>
 #include <vector>
-
-#include <sys/stat.h>
 
 #include "../../include/parakeet_b200.h"
 #include "../../include/parakeet_trt.h"
@@ -160,7 +159,7 @@ struct SnapshotPre { std::vector<float> cache_ch, cache_tm, g; int cache_len = 0
 
 static void snapshot_before(ParakeetSession* s, const std::string& dir, const float* feats, size_t T, SnapshotPre* pre) {
   const int L = s->eng->n_layers();
-  mkdir(dir.c_str(), 0777);
+  std::filesystem::create_directories(dir);
   pre->cache_ch.assign((size_t)L * pkb::kCacheS * pkb::kDModel, 0.f);
   pre->cache_tm.assign((size_t)L * pkb::kDModel * pkb::kTimeCtx, 0.f);
   s->eng->export_stream_state(s->sid, pre->cache_ch.data(), pre->cache_tm.data(), &pre->cache_len);

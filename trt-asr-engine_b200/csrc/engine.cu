@@ -1611,6 +1611,7 @@ void Engine::offline_utterances(int n, const int* sids, const float* const* pcm,
     PKB_CHECK(sids[i] >= 0 && sids[i] < (int)streams_.size() && streams_[sids[i]]->open, "offline_utterances: bad stream id");
     const Stream& s = *streams_[sids[i]];
     PKB_CHECK(s.frames_written == 0 && s.chunks == 0 && s.pending.empty(), "offline_utterances: only on a freshly opened / reset stream");
+    for (int j = 0; j < i; ++j) PKB_CHECK(sids[j] != sids[i], "offline_utterances: a stream may carry only one utterance per call");
     long long t = pcm ? (n_samples[i] >= 400 ? (long long)((n_samples[i] - 400) / 160 + 1) : 0) : T_in[i];
     PKB_CHECK(t >= 1 && t < (1 << 28), "offline_utterances: utterance needs at least one feature frame");
     T[i] = (int)t;
