@@ -20,7 +20,8 @@ PARITY UNPINNED AGAINST THE REFERENCE'S OWN OUTPUTS: NeMo, the .nemo weights and
   * numerically, against independent public implementations that ARE in this image (tests/test_oracle_vs_hf.py): the
     full-context encoder equals transformers 5.5 `ParakeetEncoder` (Hugging Face's port of the NeMo FastConformer encoder)
     on the same seeded weights to 2e-6; the predictor equals torch.nn.LSTM (what NeMo's RNNTDecoder wraps) to 1e-6.
-    The cache-aware streaming step runs the same `_layer()` as the full-context encoder;
+    The cache-aware streaming step runs the same `_layer()` as the full-context encoder, and with an empty cache and no
+    dropped tokens its emitted frames equal offline() on the same frames (same test file);
   * structurally, by checked-in reference evidence (tests/test_oracle_kats.py): layouts, the schedule, encoded_lengths=3,
     cache_len sequences 1,4,7,... and 1,2,3,4 (docs/VALIDATION_REPORT_TRACE.md:173-177, 209-213), conv-cache last column
     zero (:212).

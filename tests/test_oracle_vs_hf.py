@@ -95,3 +95,22 @@ def test_predictor_matches_torch_lstm():
             out, (h2, c2) = lstm(emb[yt[:, 0]].unsqueeze(0), (h2, c2))
         assert float((g[:, :, 0] - out[0]).abs().max()) < 1e-6
         assert float((h - h2).abs().max()) < 1e-6 and float((c - c2).abs().max()) < 1e-6
+
+
+def test_first_streaming_chunk_equals_full_context(features_ref):
+    """Chains the streaming step to the pinned full-context encoder: with an EMPTY cache and drop_extra_pre_encoded = 0 the
+    cache-aware step attends over exactly the chunk's own tokens (the 256 cache positions are masked out, relative positions
+    come from the longer 256 + Tq table through the same rel_shift), and its conv sees [zero cache(4) | chunk | 0000] -- the
+    symmetric (4,4) padding of the full-context module.  So its emitted frames must equal offline() on the same frames."""
+    m = ModelRef(model_dir(2))
+    m.drop_pre = 0
+    f = normalized_features(features_ref, 1.0, 77)[:, :57]
+    f[0] = 0.0
+    x = torch.from_numpy(f[None])
+    cc, ct, cl = m.initial_cache(1)
+    enc_s, el_s, cc1, ct1, cl1 = m.stream_step(x, torch.tensor([57]), cc, ct, cl)
+    enc_o, el_o = m.offline(x, torch.tensor([57]))
+    assert int(el_o) == 8 and enc_s.shape[2] == m.valid_out
+    assert float((enc_s - enc_o[:, :, : m.valid_out]).abs().max()) < 1e-5
+    # and the caches it hands on are what the next chunk needs: cache_len = tokens kept, time cache = last 4 kept GLU columns
+    assert int(cl1) == 8 - m.drop
