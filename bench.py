@@ -173,6 +173,41 @@ def cpu_path_rtfx(model_dir: str, n_streams: int, n_chunks: int, warm_chunks: in
     return audio_s / wall, cores, wall, audio_s
 
 
+def cpu_config1_offline(model_dir: str, seconds: float = 10.0):
+    """BASELINE config 1 on the CPU checker: one synthetic clip, batch 1, log-mel + per-feature normalisation + full-context encoder +
+    greedy TDT (the reference's ORT-CPU offline path restated).  Returns (rtfx, wall_s)."""
+    import ctypes
+
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from model_ref import DecodeState, ModelRef, prime, tdt_greedy_chunk
+    from synth_audio import synth_clip
+    so = os.path.join(ROOT, "oracle", "_build", "libfeatures_ref.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "_build/libfeatures_ref.so"], stdout=subprocess.DEVNULL)
+    fr = ctypes.CDLL(so)
+    fr.fr_num_frames.restype = ctypes.c_size_t
+    fr.fr_num_frames.argtypes = [ctypes.c_size_t]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m = ModelRef(model_dir)
+    pcm = synth_clip(seconds, 1234)
+    best = None
+    for _ in range(2):                       # second pass warm
+        t0 = time.perf_counter()
+        T = fr.fr_num_frames(pcm.size)
+        feat = np.zeros((T, 128), np.float32)
+        fr.fr_logmel(pcm.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(pcm.size), feat.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(cores))
+        feat = (feat - feat.mean(0)) / (feat.std(0, ddof=1) + 1e-5)
+        enc, el = m.offline(torch.from_numpy(np.ascontiguousarray(feat.T)[None]), torch.tensor([T]))
+        st = DecodeState(m)
+        prime(m, st)
+        tdt_greedy_chunk(m, st, enc, int(el))
+        wall = time.perf_counter() - t0
+        best = wall if best is None else min(best, wall)
+    return seconds / best, best
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -189,6 +224,9 @@ def run_reference(args, rank):
                        "streams": n_streams},
             "cpu_baseline": {"value": rtfx, "unit": "x real time", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rtfx, "unit": "x real time", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    c1_rtfx, c1_wall = cpu_config1_offline(model)
+    line["config1_offline_10s"] = {"rtfx": c1_rtfx, "wall_s": c1_wall, "cores": cores,
+                                   "what": "BASELINE config 1: one 10 s clip, batch 1, log-mel + per-feature norm + full-context encoder + greedy TDT on the CPU port"}
     print(json.dumps(line), flush=True)
 
 
@@ -429,6 +467,8 @@ def main():
             e.close()
         line["longform"] = longform(binding, model, args.precision, args.longform, args.longform_seconds, synth_clip(10.0, 1234))
     if not args.no_latency and world == 1:
+        line["config1_offline_10s"] = config1_offline(binding, model, args.precision)
+    if not args.no_latency and world == 1:
         line["latency_1stream"] = latency_one_stream(binding, model, args.precision, clips[0])
     if not args.no_cpu_baseline and world == 1:
         rtfx, cores, wall, a_s = cpu_path_rtfx(model, args.ref_streams, args.ref_chunks, 1)
@@ -473,6 +513,23 @@ def longform(binding, model, precision, batch, seconds, clip):
             "gemm_ms": gemm_ms, "gemm_tflops": gemm_flops / max(gemm_ms, 1e-9) / 1e9,
             "attention_ms": att_ms, "attention_tflops_algorithmic": att_flops / max(att_ms, 1e-9) / 1e9, "attention_launches": int(att_l),
             "decode_ms": dec_ms}
+
+
+def config1_offline(binding, model, precision):
+    """BASELINE config 1 on the GPU: one synthetic 10 s clip, batch 1, host PCM in -> tokens out through pkb_offline_utterances."""
+    from synth_audio import synth_clip
+    pcm = synth_clip(10.0, 1234)
+    eng = binding.Engine(model, max_streams=1, precision=precision, max_rows=256, contract_cache=0)
+    s = eng.open()
+    walls = []
+    for _ in range(6):
+        t0 = time.perf_counter()
+        eng.offline_utterances([s], audio=[pcm], per_feature_norm=True, decode=True)
+        walls.append(time.perf_counter() - t0)
+        eng.reset(s)
+    eng.close()
+    w = float(np.median(walls[1:]))
+    return {"wall_ms": 1e3 * w, "rtfx": 10.0 / w, "what": "BASELINE config 1: one 10 s clip, batch 1, host PCM in -> tokens out (whole-utterance path)"}
 
 
 def latency_one_stream(binding, model, precision, clip):
