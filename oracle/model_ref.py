@@ -22,6 +22,8 @@ PARITY UNPINNED AGAINST THE REFERENCE'S OWN OUTPUTS: NeMo, the .nemo weights and
     on the same seeded weights to 2e-6; the predictor equals torch.nn.LSTM (what NeMo's RNNTDecoder wraps) to 1e-6.
     The cache-aware streaming step runs the same `_layer()` as the full-context encoder, and with an empty cache and no
     dropped tokens its emitted frames equal offline() on the same frames (same test file);
+  * the greedy TDT loop: the reference's own tools/verify_nemo/tdt_trace.py, executed unmodified on these modules, produced
+    tests/golden/tdt_trace_ref.json; tdt_greedy_chunk + prime reproduce it step for step (tests/test_oracle_kats.py);
   * structurally, by checked-in reference evidence (tests/test_oracle_kats.py): layouts, the schedule, encoded_lengths=3,
     cache_len sequences 1,4,7,... and 1,2,3,4 (docs/VALIDATION_REPORT_TRACE.md:173-177, 209-213), conv-cache last column
     zero (:212).

@@ -205,3 +205,39 @@ def test_prime_and_decode_runs(oracle_small, features_ref):
         n_steps += len(tr)
         assert all(0 <= t < 3 and 0 <= tok <= 8192 and 0 <= d <= 4 for t, tok, d, _ in tr)
     assert n_steps >= 5
+
+
+def test_tdt_loop_matches_the_references_own_python_loop(features_ref):
+    """tests/golden/tdt_trace_ref.json is the trace of the REFERENCE's tools/verify_nemo/tdt_trace.py, executed unmodified on the
+    oracle's encoder / predictor / joint for the seeded 2-layer model (tests/golden/make_tdt_trace_golden.py).  The oracle's own
+    loop (tdt_greedy_chunk + prime: the restatement the GPU decode is checked against) must make the same decisions: priming token,
+    per-chunk time indices, u counters, blank + duration-0 clamp, duration advance, leftover advance dropped at the chunk end.
+    (The Python reference has no leading-punctuation suppression -- that is the C++ runtime's, parakeet_trt.cpp:3256-3262 -- so it is
+    switched off here.)  Steps are compared up to the first decision whose top-2 gap is below 1e-4 (CPU BLAS differences)."""
+    import json
+    import os
+    from conftest import model_dir, normalized_features
+    from model_ref import DecodeState, ModelRef, prime, tdt_greedy_chunk
+    doc = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tdt_trace_ref.json")))
+    m = ModelRef(model_dir(2))
+    f = normalized_features(features_ref, doc["clip"]["seconds"], doc["clip"]["seed"])
+    f[0] = 0.0
+    st = DecodeState(m)
+    prime(m, st)
+    assert st.y_id == doc["meta"]["y0"] and doc["meta"]["blank_id"] == m.blank
+    got = []
+    C = doc["chunk_frames"]
+    for ci, lo in enumerate(range(0, f.shape[1], C)):
+        seg = f[:, lo:lo + C]
+        enc, el = m.offline(torch.from_numpy(np.ascontiguousarray(seg)[None]), torch.tensor([seg.shape[1]]))
+        prev_t, u = -1, 0
+        for t, tok, d, adv in tdt_greedy_chunk(m, st, enc, int(el), punct_suppression=False):
+            u = u + 1 if t == prev_t else 0
+            prev_t = t
+            got.append((ci, t, u, tok, d, adv))
+    want = [(s_["chunk_idx"], s_["time_idx"], s_["u"], s_["best_tok"], s_["duration"], s_["advance"]) for s_ in doc["steps"]]
+    amb = next((i for i, s_ in enumerate(doc["steps"]) if min(s_["tok_gap"], s_["dur_gap"]) < 1e-4), len(want))
+    assert amb >= 60, amb
+    assert got[:amb] == want[:amb]
+    if amb == len(want):
+        assert len(got) == len(want)
