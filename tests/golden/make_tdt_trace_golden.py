@@ -89,6 +89,9 @@ def main():
         except SystemExit as e:
             assert not e.code, e.code
         lines = [json.loads(ln) for ln in open(out)]
+        if os.environ.get("KEEP_JSONL"):      # the raw reference-format trace, e.g. for tools/verify_nemo/compare_tdt_trace.py
+            import shutil
+            shutil.copy(out, os.environ["KEEP_JSONL"])
     meta = lines[0]
     steps = [{"chunk_idx": r["chunk_idx"], "time_idx": r["time_idx"], "u": r["u"], "y_id": r["y_id"], "best_tok": r["best_tok"],
               "best_dur_idx": r["best_dur_idx"], "duration": r["duration"], "advance": r["advance"],
