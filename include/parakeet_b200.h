@@ -65,6 +65,12 @@ int32_t pkb_stream_push_features(PkbEngine* engine, int32_t stream, const float*
 int32_t pkb_stream_push_audio(PkbEngine* engine, int32_t stream, const float* pcm, size_t n);
 /* per-feature normalisation applied by the GPU frontend: (x - mean[m]) / std[m]; NULLs switch it off */
 int32_t pkb_stream_set_feature_norm(PkbEngine* engine, int32_t stream, const float* mean128, const float* std128);
+/* Streaming-safe alternative (the reference records its model-matching whole-utterance statistics as "not streaming-safe" and
+ * leaves the choice open: /root/reference/docs/DECISION_LOG.md:44-47, 55-58; docs/ARCHITECTURE_RUNTIME.md:48-50): every frame the GPU
+ * frontend produces is normalised with the CAUSAL running mean / unbiased std (+1e-5, as rust/features/src/lib.rs:150-158) of the
+ * stream's own frames up to and including that frame.  Audio input only; on a freshly opened or reset stream; the mode survives
+ * pkb_stream_reset (the statistics restart), pkb_stream_close clears it.  Takes precedence over fixed statistics. */
+int32_t pkb_stream_set_feature_norm_running(PkbEngine* engine, int32_t stream, int32_t on);
 /* Offline mode = the reference's non-streaming `encoder` engine (contracts/parakeet-tdt-0.6b-v3.contract.json:67-96, selected in
  * cpp/src/parakeet_trt.cpp:1720-1746 when the engine has no cache bindings): every push of 1..256 frames is encoded with full
  * context, no caches are read or carried over, and all of its encoder frames are decoded (predictor state still carries over).

@@ -26,7 +26,7 @@ TRT_ASR_SYMBOLS = ["trt_asr_create_session", "trt_asr_destroy_session", "trt_asr
                    "trt_asr_push_features_f32", "trt_asr_poll_event"]
 B200_SYMBOLS = ["pkb_last_error", "pkb_version", "pkb_engine_create", "pkb_engine_destroy", "pkb_engine_num_layers",
                 "pkb_engine_kernel_launches", "pkb_stream_open", "pkb_stream_close", "pkb_stream_reset", "pkb_stream_push_features",
-                "pkb_stream_push_audio", "pkb_stream_set_feature_norm", "pkb_stream_set_offline", "pkb_encoder_offline_step", "pkb_offline_utterances", "pkb_offline_decode_pending", "pkb_encoded_length", "pkb_engine_push_audio_batch",
+                "pkb_stream_push_audio", "pkb_stream_set_feature_norm", "pkb_stream_set_feature_norm_running", "pkb_stream_set_offline", "pkb_encoder_offline_step", "pkb_offline_utterances", "pkb_offline_decode_pending", "pkb_encoded_length", "pkb_engine_push_audio_batch",
                 "pkb_engine_push_audio_batch_device", "pkb_engine_event_record", "pkb_engine_event_elapsed_ms",
                 "pkb_engine_profile_enable", "pkb_engine_profile_read", "pkb_engine_profile_read_class", "pkb_engine_step", "pkb_stream_has_pending",
                 "pkb_stream_num_tokens", "pkb_stream_tokens", "pkb_stream_token_frames", "pkb_stream_encoder_frames", "pkb_stream_stable_prefix", "pkb_stream_last_steps", "pkb_stream_cache_len",
@@ -133,6 +133,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.pkb_stream_get_decoder_state.argtypes = [vp, C.c_int32, fp, fp, fp]
     lib.pkb_encoder_streaming_step.argtypes = [vp, C.c_int32, C.c_int32, fp, lp, fp, fp, lp, fp, lp, fp, fp, lp]
     lib.pkb_stream_set_offline.argtypes = [vp, C.c_int32, C.c_int32]
+    lib.pkb_stream_set_feature_norm_running.argtypes = [vp, C.c_int32, C.c_int32]
     lib.pkb_encoder_offline_step.argtypes = [vp, C.c_int32, C.c_int32, fp, lp, fp, lp]
     lib.pkb_offline_utterances.argtypes = [vp, C.c_int32, ip, C.POINTER(fp), C.POINTER(C.c_size_t), C.c_int32, C.POINTER(fp), ip, C.c_int32,
                                            C.POINTER(fp), C.c_int32]
@@ -267,6 +268,10 @@ class Engine:
         else:
             m, d = np.ascontiguousarray(mean, np.float32), np.ascontiguousarray(std, np.float32)
             self._chk(self._lib.pkb_stream_set_feature_norm(self._e, s, _fptr(m), _fptr(d)))
+
+    def set_feature_norm_running(self, s: int, on: bool = True):
+        """streaming-safe normalisation: causal running mean / std per feature (GPU frontend, audio input)."""
+        self._chk(self._lib.pkb_stream_set_feature_norm_running(self._e, s, int(on)))
 
     def push_audio_batch(self, sids: np.ndarray, host_ptr: int, stride: int, count: int):
         """sids int32 array; host_ptr = address of row 0 (e.g. tensor.data_ptr() of pinned memory)."""

@@ -6,7 +6,9 @@
 //   clock when the token count changed (:3680-3712); FINAL_TEXT per push only when PARAKEET_EMIT_FINAL_EACH_CHUNK is set
 //   (default off for a streaming encoder, :3802-3815); exceptions never cross the ABI.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
 #include <filesystem>
@@ -67,9 +69,36 @@ int guarded(F&& f) {
 
 }  // namespace
 
+// Every ABI entry runs on the engine's device, whatever device the calling thread had current (a Rust worker thread, a process
+// that holds one engine per GPU), and restores the caller's device on exit.
+struct DeviceGuard {
+  int prev = -1, dev;
+  explicit DeviceGuard(int d) : dev(d) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
+};
+
 struct PkbEngine {
   pkb::Engine* eng = nullptr;
   std::mutex mu;   // one caller at a time per engine
+};
+
+// One engine per (model_dir, device, options) shared by every legacy session of the process: the reference's multi-session use
+// (MAGNOLIA_INTEGRATION_HANDOFF.md:10-12; SURVEY.md 8b "existing 6 symbols become a B=1 view") must not load the weights once per
+// session, and pushes that arrive together are served by ONE batched pass.  Sessions are stream slots of the shared engine.
+struct SharedEngine {
+  pkb::Engine* eng = nullptr;
+  std::string key;
+  int device = 0;
+  int refs = 0;
+  std::mutex mu;                       // engine state + the fields below
+  std::condition_variable cv_done;     // followers: "your chunk has been processed"
+  std::condition_variable cv_leader;   // leader: "another session has staged a chunk"
+  bool leader_active = false;
+  int queued = 0;
+  std::vector<ParakeetSession*> sessions;
 };
 
 struct PkbFrontend {
@@ -80,8 +109,11 @@ struct PkbFrontend {
 };
 
 struct ParakeetSession {
-  pkb::Engine* eng = nullptr;
+  SharedEngine* sh = nullptr;
+  pkb::Engine* eng = nullptr;    // == sh->eng
   int sid = -1;
+  bool waiting = false;          // a staged chunk awaits the next batched pass
+  std::string pass_error;        // set by the leader when that pass failed
   std::mutex event_mu;
   std::queue<EventInternal> events;
   std::string last_text, last_err;
@@ -94,6 +126,67 @@ struct ParakeetSession {
   uint64_t dbg_utt = 0, dbg_chunk = 0, dbg_feat = 0;
 };
 
+namespace {
+
+std::mutex g_registry_mu;
+std::vector<SharedEngine*> g_registry;
+
+// Find (or create) the shared engine of this configuration with a free stream slot and make `s` one of its streams.
+void attach_shared(ParakeetSession* s, const pkb::EngineOptions& o) {
+  std::ostringstream k;
+  k << o.model_dir << '|' << o.device_id << '|' << o.precision << '|' << o.gemm_backend << '|' << o.punct_suppress << '|' << o.blank_penalty << '|'
+    << o.max_streams;
+  const std::string key = k.str();
+  std::lock_guard<std::mutex> reg(g_registry_mu);
+  for (SharedEngine* sh : g_registry) {
+    if (sh->key != key) continue;
+    std::lock_guard<std::mutex> lk(sh->mu);
+    if (sh->refs >= o.max_streams) continue;      // full: look for (or create) the next engine of this configuration
+    s->sid = sh->eng->open_stream();
+    s->sh = sh; s->eng = sh->eng;
+    sh->refs += 1;
+    sh->sessions.push_back(s);
+    return;
+  }
+  std::unique_ptr<SharedEngine> sh(new SharedEngine());
+  sh->key = key;
+  sh->device = o.device_id;
+  sh->eng = new pkb::Engine(o);
+  try {
+    s->sid = sh->eng->open_stream();
+  } catch (...) {
+    delete sh->eng;
+    throw;
+  }
+  s->sh = sh.get(); s->eng = sh->eng;
+  sh->refs = 1;
+  sh->sessions.push_back(s);
+  g_registry.push_back(sh.release());
+}
+
+void detach_shared(ParakeetSession* s) {
+  SharedEngine* sh = s->sh;
+  if (!sh) return;
+  std::lock_guard<std::mutex> reg(g_registry_mu);
+  bool last = false;
+  {
+    DeviceGuard dg(sh->device);
+    std::lock_guard<std::mutex> lk(sh->mu);
+    try { if (s->sid >= 0) sh->eng->close_stream(s->sid); } catch (...) {}
+    sh->sessions.erase(std::remove(sh->sessions.begin(), sh->sessions.end(), s), sh->sessions.end());
+    sh->refs -= 1;
+    last = sh->refs <= 0;
+    if (last) { delete sh->eng; sh->eng = nullptr; }
+  }
+  if (last) {
+    g_registry.erase(std::remove(g_registry.begin(), g_registry.end(), sh), g_registry.end());
+    delete sh;
+  }
+  s->sh = nullptr; s->eng = nullptr; s->sid = -1;
+}
+
+}  // namespace
+
 extern "C" {
 
 // ================================================================================================ parakeet_trt.h
@@ -105,36 +198,38 @@ ParakeetSession* parakeet_create_session(const ParakeetConfig* config) {
     pkb::EngineOptions o;
     o.model_dir = config->model_dir;
     o.device_id = config->device_id;
-    o.max_streams = 1;
+    o.max_streams = (int)std::min(1024L, std::max(1L, env_long("PARAKEET_B200_MAX_SESSIONS", 8)));
     o.precision = (int)env_long("PARAKEET_B200_PRECISION", config->use_fp16 ? 0 : 1);
     o.gemm_backend = (int)env_long("PARAKEET_B200_GEMM", 0);
     o.punct_suppress = env_bool("PARAKEET_DISABLE_PUNCT_SUPPRESSION", false) ? 0 : 1;
     o.blank_penalty = env_float("PARAKEET_BLANK_PENALTY", 0.0f);
-    s->eng = new pkb::Engine(o);
-    s->sid = s->eng->open_stream();
+    DeviceGuard dg(o.device_id);
+    attach_shared(s, o);
     const char* mode = std::getenv("PARAKEET_B200_ENCODER");
     s->offline = mode && std::string(mode) == "offline";
-    if (s->offline) s->eng->set_stream_offline(s->sid, true);
+    if (s->offline) { std::lock_guard<std::mutex> lk(s->sh->mu); s->eng->set_stream_offline(s->sid, true); }
     s->dbg_steps_left = (uint64_t)std::max(0L, env_long("PARAKEET_DEBUG_TDT_STEPS", 0));
     s->last_partial_emit = std::chrono::steady_clock::now() - std::chrono::milliseconds(1000);
     return s;
   } catch (const std::exception& e) {
     std::cerr << "[parakeet_trt] create_session failed: " << e.what() << "\n";
     g_last_error = e.what();
-    if (s) { delete s->eng; delete s; }
+    if (s) { detach_shared(s); delete s; }
     return nullptr;
   }
 }
 
 void parakeet_destroy_session(ParakeetSession* session) {
   if (!session) return;
-  delete session->eng;
+  detach_shared(session);
   delete session;
 }
 
 void parakeet_reset_utterance(ParakeetSession* session) {
   if (!session) return;
   try {
+    DeviceGuard dg(session->sh->device);
+    std::lock_guard<std::mutex> lk(session->sh->mu);
     session->eng->reset_stream(session->sid);
   } catch (const std::exception& e) {
     std::cerr << "[parakeet_trt] reset_utterance failed: " << e.what() << "\n";
@@ -206,22 +301,36 @@ static void snapshot_after(ParakeetSession* s, const std::string& dir, const Sna
             << "/dur_logits_trt.f32 enc_out_t0=" << dir << "/enc_out_t0_trt.f32\n";
 }
 
-static void push_one_chunk(ParakeetSession* s, const float* feats, size_t T) {
-  const size_t before = s->eng->tokens(s->sid).size();
-  const char* snap = std::getenv("PARAKEET_TDT_SNAPSHOT_DIR");
-  const bool want_snap = snap && *snap && !s->offline && !s->snapshot_done;
-  SnapshotPre pre;
-  if (want_snap) {
-    try { snapshot_before(s, snap, feats, T, &pre); }
-    catch (const std::exception& e) { std::cerr << "[parakeet_trt] WARN: failed to write encoder snapshot: " << e.what() << "\n"; }
+// NaN / Inf guard after the encoder step (parakeet_trt.cpp:913-1013, 2449-2481): the first 10 guarded tensors of the process, then one in
+// 100, or every one with PARAKEET_NAN_GUARD_ALWAYS=1; findings go to stderr in the reference's line format; PARAKEET_NAN_GUARD_HALT=1
+// aborts the process on the first finding.
+static void nan_guard_after_chunk(ParakeetSession* s, int cache_len_in, size_t T) {
+  static std::atomic<int> s_guard_count{0};
+  static const char* kStage[3] = {"enc_output", "enc_cache_ch_out", "enc_cache_tm_out"};
+  const bool force = env_bool("PARAKEET_NAN_GUARD_ALWAYS", false);
+  for (int stage = 0; stage < (s->offline ? 1 : 3); ++stage) {
+    const int n = s_guard_count.fetch_add(1, std::memory_order_relaxed);
+    if (!force && n >= 10 && (n % 100) != 0) continue;
+    const pkb::Engine::GuardResult r = s->eng->nan_guard(s->sid, stage);
+    if (r.nan_count == 0 && r.inf_count == 0) continue;
+    std::cerr << "[parakeet_trt] NAN_GUARD ALERT stage=" << kStage[stage] << " nan_count=" << r.nan_count << " inf_count=" << r.inf_count
+              << " finite_count=" << (r.sample_n - (size_t)r.nan_count - (size_t)r.inf_count) << " sample_n=" << r.sample_n << "/" << r.count
+              << " dtype=" << (stage == 1 && s->eng->options().precision == 0 ? "bf16" : "fp32") << " cache_len_in=" << cache_len_in
+              << " length_in=" << T;
+    if (stage == 0) std::cerr << " chunk_idx=" << s->dbg_chunk << " feature_idx=" << s->dbg_feat;
+    if (r.nan_count > 0) std::cerr << " first_nan_idx=" << r.first_nan;
+    if (r.inf_count > 0) std::cerr << " first_inf_idx=" << r.first_inf;
+    std::cerr << "\n";
+    if (env_bool("PARAKEET_NAN_GUARD_HALT", false)) {
+      std::cerr << "[parakeet_trt] NAN_GUARD_HALT enabled, aborting\n";
+      std::abort();
+    }
   }
-  s->eng->queue_features(s->sid, feats, (int)T);
-  s->eng->step();
-  if (want_snap) {
-    try { snapshot_after(s, snap, pre); }
-    catch (const std::exception& e) { std::cerr << "[parakeet_trt] WARN: failed to write TDT snapshot: " << e.what() << "\n"; }
-    s->snapshot_done = true;
-  }
+}
+
+// Everything the reference does after the decode loop of one push (trace lines, partial / final events), for one session whose chunk
+// has just been processed.  Called with the shared engine locked.
+static void after_chunk(ParakeetSession* s, size_t tokens_before) {
   const std::vector<int>& toks = s->eng->tokens(s->sid);
   if (s->dbg_steps_left > 0) {
     // decode trace in the line format the reference prints and tools/verify_nemo/compare_tdt_trace.py:43-66 parses
@@ -249,11 +358,66 @@ static void push_one_chunk(ParakeetSession* s, const float* feats, size_t T) {
     s->last_partial_emit = now;
   }
   if (env_bool("PARAKEET_EMIT_FINAL_EACH_CHUNK", s->offline)) {      // default: !enc_streaming (parakeet_trt.cpp:3802)
-    std::vector<int> chunk(toks.begin() + (std::ptrdiff_t)before, toks.end());
+    std::vector<int> chunk(toks.begin() + (std::ptrdiff_t)tokens_before, toks.end());
     EventInternal ev{PARAKEET_EVENT_FINAL_TEXT, s->eng->detokenize(chunk), ""};
     std::lock_guard<std::mutex> lock(s->event_mu);
     s->events.push(std::move(ev));
   }
+}
+
+// One push = one encoder chunk of this session.  The chunk is staged in the shared engine; the first session to arrive becomes the
+// leader of the next batched pass, waits a moment for the other sessions that are pushing right now (PARAKEET_B200_COALESCE_US, default
+// 200 us, only when the engine has more than one session), runs ONE pass for every staged chunk and wakes the followers.
+static void push_one_chunk(ParakeetSession* s, const float* feats, size_t T) {
+  SharedEngine* sh = s->sh;
+  DeviceGuard dg(sh->device);
+  std::unique_lock<std::mutex> lk(sh->mu);
+  const size_t before = s->eng->tokens(s->sid).size();
+  const int cache_len_in = s->eng->cache_len(s->sid);
+  const char* snap = std::getenv("PARAKEET_TDT_SNAPSHOT_DIR");
+  const bool want_snap = snap && *snap && !s->offline && !s->snapshot_done;
+  SnapshotPre pre;
+  if (want_snap) {
+    try { snapshot_before(s, snap, feats, T, &pre); }
+    catch (const std::exception& e) { std::cerr << "[parakeet_trt] WARN: failed to write encoder snapshot: " << e.what() << "\n"; }
+  }
+  s->eng->queue_features(s->sid, feats, (int)T);      // staging only; throws on a chunk the encoder cannot take (nothing is queued then)
+  s->waiting = true;
+  s->pass_error.clear();
+  sh->queued += 1;
+  if (!sh->leader_active) {
+    sh->leader_active = true;
+    if (sh->refs > 1) {
+      static const long window_us = std::max(0L, env_long("PARAKEET_B200_COALESCE_US", 200));
+      if (window_us > 0) sh->cv_leader.wait_for(lk, std::chrono::microseconds(window_us), [&] { return sh->queued >= sh->refs; });
+    }
+    std::string err;
+    try {
+      s->eng->step();
+    } catch (const std::exception& e) {
+      err = e.what();
+    }
+    for (ParakeetSession* o : sh->sessions) {
+      if (!o->waiting) continue;
+      o->waiting = false;
+      o->pass_error = err;
+      if (!err.empty()) { try { sh->eng->drop_pending(o->sid); } catch (...) {} }
+    }
+    sh->queued = 0;
+    sh->leader_active = false;
+    sh->cv_done.notify_all();
+  } else {
+    sh->cv_leader.notify_one();
+    sh->cv_done.wait(lk, [&] { return !s->waiting; });
+  }
+  if (!s->pass_error.empty()) throw std::runtime_error(s->pass_error);
+  nan_guard_after_chunk(s, cache_len_in, T);
+  if (want_snap) {
+    try { snapshot_after(s, snap, pre); }
+    catch (const std::exception& e) { std::cerr << "[parakeet_trt] WARN: failed to write TDT snapshot: " << e.what() << "\n"; }
+    s->snapshot_done = true;
+  }
+  after_chunk(s, before);
 }
 
 int parakeet_push_features(ParakeetSession* session, const float* features, size_t num_frames) {
@@ -398,6 +562,7 @@ PkbEngine* pkb_engine_create(const PkbEngineConfig* c) {
     o.punct_suppress = c->punct_suppression;
     o.max_rows = c->max_rows;
     o.blank_penalty = env_float("PARAKEET_BLANK_PENALTY", 0.0f);
+    DeviceGuard dg(o.device_id);
     PkbEngine* e = new PkbEngine();
     e->eng = new pkb::Engine(o);
     return e;
@@ -408,6 +573,7 @@ PkbEngine* pkb_engine_create(const PkbEngineConfig* c) {
 }
 void pkb_engine_destroy(PkbEngine* e) {
   if (!e) return;
+  DeviceGuard dg(e->eng->options().device_id);
   delete e->eng;
   delete e;
 }
@@ -416,6 +582,7 @@ int64_t pkb_engine_kernel_launches(PkbEngine* e) { return e ? e->eng->kernel_lau
 
 #define PKB_ENTER(e)                                        \
   if (!(e)) { g_last_error = "null engine"; return -1; }    \
+  DeviceGuard _dg((e)->eng->options().device_id);           \
   std::lock_guard<std::mutex> _lock((e)->mu)
 
 int32_t pkb_stream_open(PkbEngine* e) { PKB_ENTER(e); return guarded([&] { return e->eng->open_stream(); }); }
@@ -435,6 +602,10 @@ int32_t pkb_stream_set_feature_norm(PkbEngine* e, int32_t s, const float* mean12
   PKB_ENTER(e);
   return guarded([&] { e->eng->set_feature_norm(s, mean128, std128); return 0; });
 }
+int32_t pkb_stream_set_feature_norm_running(PkbEngine* e, int32_t s, int32_t on) {
+  PKB_ENTER(e);
+  return guarded([&] { e->eng->set_feature_norm_running(s, on != 0); return 0; });
+}
 int32_t pkb_stream_set_offline(PkbEngine* e, int32_t s, int32_t offline) {
   PKB_ENTER(e);
   return guarded([&] { e->eng->set_stream_offline(s, offline != 0); return 0; });
@@ -453,6 +624,7 @@ int32_t pkb_engine_push_audio_batch_device(PkbEngine* e, int32_t n, const int32_
 int32_t pkb_engine_event_record(PkbEngine* e) { PKB_ENTER(e); return guarded([&] { return e->eng->event_record(); }); }
 double pkb_engine_event_elapsed_ms(PkbEngine* e, int32_t a, int32_t b) {
   if (!e) return -1.0;
+  DeviceGuard dg(e->eng->options().device_id);
   std::lock_guard<std::mutex> lock(e->mu);
   try { return e->eng->event_elapsed_ms(a, b); } catch (const std::exception& ex) { g_last_error = ex.what(); return -1.0; }
 }
@@ -583,6 +755,7 @@ int32_t pkb_joint_step(PkbEngine* e, int32_t B, int32_t T, int32_t U, const floa
 }
 int64_t pkb_logmel(PkbEngine* e, const float* pcm, size_t n, float* out, size_t out_cap_floats, int32_t per_feature_norm) {
   if (!e) { g_last_error = "null engine"; return -1; }
+  DeviceGuard dg(e->eng->options().device_id);
   std::lock_guard<std::mutex> lock(e->mu);
   try {
     const size_t T = n < 400 ? 0 : (n - 400) / 160 + 1;
@@ -595,7 +768,7 @@ int64_t pkb_logmel(PkbEngine* e, const float* pcm, size_t n, float* out, size_t 
 }
 PkbFrontend* pkb_frontend_create(int32_t device_id) {
   try {
-    PKB_CUDA(cudaSetDevice(device_id));
+    DeviceGuard dg(device_id);
     cudaDeviceProp prop;
     PKB_CUDA(cudaGetDeviceProperties(&prop, device_id));
     PKB_CHECK(prop.major == 10, "this library is built for sm_100a (B200) only");
@@ -613,6 +786,7 @@ PkbFrontend* pkb_frontend_create(int32_t device_id) {
 }
 void pkb_frontend_destroy(PkbFrontend* f) {
   if (!f) return;
+  DeviceGuard dg(f->device);
   cudaStreamSynchronize(f->st);
   cudaStreamDestroy(f->st);
   delete f->fe;
@@ -628,7 +802,7 @@ int64_t pkb_frontend_logmel(PkbFrontend* f, const float* pcm, size_t n, float* o
     const size_t T = n < 400 ? 0 : (n - 400) / 160 + 1;
     if (T == 0) return 0;
     if (T * pkb::kNMels > cap) { g_last_error = "output buffer too small"; return -1; }
-    PKB_CUDA(cudaSetDevice(f->device));
+    DeviceGuard dg(f->device);
     PKB_CUDA(cudaMalloc(&d_audio, (n + 2) * 4));
     PKB_CUDA(cudaMalloc(&d_out, T * pkb::kNMels * 4));
     PKB_CUDA(cudaMalloc(&d_seg, sizeof(pkb::FrontSegment)));

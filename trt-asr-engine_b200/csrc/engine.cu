@@ -50,6 +50,25 @@ T* dev_upload(const std::vector<T>& v) {
   return p;
 }
 
+// transient device buffers of one call: released on every exit path (exceptions included)
+struct DevTmp {
+  std::vector<void*> ptrs;
+  template <typename T>
+  T* alloc(size_t n) {
+    void* p = nullptr;
+    PKB_CUDA(cudaMalloc(&p, std::max<size_t>(n * sizeof(T), 1)));
+    ptrs.push_back(p);
+    return static_cast<T*>(p);
+  }
+  template <typename T>
+  T* upload(const T* host, size_t n) {
+    T* p = alloc<T>(n);
+    if (n) { PKB_CUDA(cudaMemcpy(p, host, n * sizeof(T), cudaMemcpyHostToDevice)); PKB_CUDA(cudaDeviceSynchronize()); }
+    return p;
+  }
+  ~DevTmp() { for (void* p : ptrs) cudaFree(p); }
+};
+
 inline int sub_len(int L) { return L <= 0 ? 0 : (L - 1) / 2 + 1; }   // floor((L + 2 - 3)/2) + 1, calc_length of dw_striding
 
 struct GemmW {
@@ -133,6 +152,18 @@ __global__ void audio_move_kernel(float* __restrict__ buf, float* __restrict__ t
   }
 }
 
+// NaN / Inf census of up to 4 row segments (f32 or bf16): out = {nan count, inf count, first nan index, first inf index}
+struct GuardRows { long long off[4]; int n_rows; int row_len; };
+__global__ void guard_scan_kernel(const void* __restrict__ base, int is_bf16, GuardRows rows, int* __restrict__ out) {
+  const int total = rows.n_rows * rows.row_len;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / rows.row_len, c = i - r * rows.row_len;
+    const float v = is_bf16 ? __bfloat162float(((const __nv_bfloat16*)base)[rows.off[r] + c]) : ((const float*)base)[rows.off[r] + c];
+    if (v != v) { atomicAdd(out, 1); atomicMin(out + 2, i); }
+    else if (isinf(v)) { atomicAdd(out + 1, 1); atomicMin(out + 3, i); }
+  }
+}
+
 bool is_special_piece(const std::string& s) {
   if (s == "<blank>" || s == "<pad>" || s == "<unk>") return true;
   return !s.empty() && s.front() == '<' && s.back() == '>';
@@ -170,6 +201,7 @@ struct Engine::Stream {
   int dev_fill = 0;                      // valid samples from dev_off
   long long sched_chunk = 0;             // index of the next scheduled chunk (audio mode)
   bool has_norm = false;
+  bool run_norm = false;                 // streaming-safe running mean / std normalisation of the GPU frontend's frames
   int cache_len = 0;
   int head = 0;
   long long chunks = 0;
@@ -182,6 +214,7 @@ struct Engine::Stream {
   ChunkResult last;
 };
 
+constexpr int kRunStats = 1 + 2 * kNMels + 3;      // padded to a multiple of 4 floats
 constexpr int kProfClasses = 5;   // 0 tcgen05 GEMM, 1 streaming attention, 2 log-mel, 3 decode loop, 4 whole-utterance attention
 
 struct Engine::Impl {
@@ -204,6 +237,7 @@ struct Engine::Impl {
   float* cache_tm = nullptr;             // [slots][L][1024][4]
   float* feat_ring = nullptr;            // [slots][kFeatRing][128]
   float* norm_stats = nullptr;           // [slots][2][128]
+  float* run_stats = nullptr;            // [slots][kRunStats]: frame count, running mean[128], M2[128] (running normalisation)
   float *pred_h = nullptr, *pred_c = nullptr, *pred_g = nullptr, *pred_proj = nullptr;
   int *n_emitted = nullptr, *y_id = nullptr;
   // work buffers
@@ -262,8 +296,18 @@ struct Engine::Impl {
   FrontSegment* segs_host = nullptr;
   int* fprefix_dev = nullptr;
   int* fprefix_host = nullptr;
-  float* feat_stage_dev = nullptr;       // [128*256] legacy push staging
-  float* feat_stage_host = nullptr;
+  // feature pushes (the legacy ABI's input): chunks queued since the last batched pass wait bins-major in one pinned staging
+  // area; ONE H2D copy + ONE transpose kernel per pass move all of them into the per-stream feature rings
+  float* fstage_dev = nullptr;
+  float* fstage_host = nullptr;
+  size_t fstage_cap = 0, fstage_used = 0;      // floats
+  FeatPush* fpush_dev = nullptr;
+  FeatPush* fpush_host = nullptr;
+  int fpush_cap = 0, fpush_n = 0, fpush_max_T = 0;
+  bool fstage_inflight = false;                // flushed to the device, host area not yet known to be consumed
+  int* meta2 = nullptr;                        // device [2]: (slot, head) of a single-stream import / export
+  int* guard_dev = nullptr;                    // device [4]: nan count, inf count, first nan index, first inf index (NaN guard)
+  int* guard_host = nullptr;                   // pinned
 };
 
 constexpr int kFeatRing = 512;           // frames kept per stream (5.12 s)
@@ -554,6 +598,8 @@ void Engine::alloc_state() {
   im.cache_tm = dev_alloc<float>(S * L_ * kDModel * kTimeCtx);
   im.feat_ring = dev_alloc<float>(S * kFeatRing * kNMels);
   im.norm_stats = dev_alloc<float>(S * 2 * kNMels);
+  im.run_stats = dev_alloc<float>(S * kRunStats);
+  PKB_CUDA(cudaMemsetAsync(im.run_stats, 0, S * kRunStats * 4, st_));
   im.pred_h = dev_alloc<float>(S * kPredL * kPredH);
   im.pred_c = dev_alloc<float>(S * kPredL * kPredH);
   im.pred_g = dev_alloc<float>(S * kPredH);
@@ -643,8 +689,15 @@ void Engine::alloc_state() {
   host_alloc(&im.segs_host, (size_t)im.Bcap * sizeof(FrontSegment));
   im.fprefix_dev = dev_alloc<int>(im.Bcap + 1);
   host_alloc(&im.fprefix_host, (size_t)(im.Bcap + 1) * sizeof(int));
-  im.feat_stage_dev = dev_alloc<float>((size_t)kNMels * 256);
-  host_alloc(&im.feat_stage_host, (size_t)kNMels * 256 * sizeof(float));
+  im.fstage_cap = (size_t)kNMels * std::max(512, 64 * im.Bcap);      // one steady-state chunk (57 frames) per stream, >= 2 maximal pushes
+  im.fstage_dev = dev_alloc<float>(im.fstage_cap);
+  host_alloc(&im.fstage_host, im.fstage_cap * sizeof(float));
+  im.fpush_cap = 2 * im.Bcap + 16;
+  im.fpush_dev = dev_alloc<FeatPush>(im.fpush_cap);
+  host_alloc(&im.fpush_host, (size_t)im.fpush_cap * sizeof(FeatPush));
+  im.meta2 = dev_alloc<int>(2);
+  im.guard_dev = dev_alloc<int>(4);
+  host_alloc(&im.guard_host, 4 * sizeof(int));
 
   // ---- projected relative-position table per layer:  P_l[r] = linear_pos_l(pe[r]),  r in [-kPosNeg, kPosRows-kPosNeg)
   // pe[r][2i] = sin(r * div_i), pe[r][2i+1] = cos(r * div_i), div_i = exp(-(ln 1e4) * 2i / d_model)   (NeMo RelPositionalEncoding)
@@ -700,6 +753,16 @@ void Engine::close_stream(int sid) {
   PKB_CHECK(sid >= 0 && sid < (int)streams_.size(), "bad stream id");
   streams_[sid]->open = false;
   streams_[sid]->offline = false;
+  streams_[sid]->run_norm = false;
+  streams_[sid]->pending.clear();
+  streams_[sid]->audio.clear();
+}
+
+// forget the chunks a stream has queued but not processed (error recovery of the one-chunk-per-push legacy session)
+void Engine::drop_pending(int sid) {
+  PKB_CHECK(sid >= 0 && sid < (int)streams_.size(), "bad stream id");
+  Stream& s = *streams_[sid];
+  while (!s.pending.empty()) { s.frames_written = std::min(s.frames_written, s.pending.back().f0); s.pending.pop_back(); }
 }
 
 void Engine::reset_stream(int sid) {
@@ -717,6 +780,7 @@ void Engine::reset_stream(int sid) {
   PKB_CUDA(cudaMemsetAsync(im.pred_c + slot * kPredL * kPredH, 0, kPredL * kPredH * 4, st_));
   PKB_CUDA(cudaMemsetAsync(im.pred_g + slot * kPredH, 0, kPredH * 4, st_));
   PKB_CUDA(cudaMemsetAsync(im.n_emitted + slot, 0, 4, st_));
+  PKB_CUDA(cudaMemsetAsync(im.run_stats + slot * kRunStats, 0, kRunStats * 4, st_));      // (s.run_norm, the mode, is kept)
   s.needs_prime = true;     // primed (batched with every other freshly reset stream) right before its first decode
 }
 
@@ -727,9 +791,28 @@ void Engine::set_stream_offline(int sid, bool offline) {
   s.offline = offline;
 }
 
+// Next chunk of the cache-aware schedule (tools/verify_nemo/streaming_encoder_reference.py:522-550): chunk 0 = frames [0,41);
+// chunk k = [start-9, start+48), start = 17 + 24 (k-1).
+static inline void sched_chunk_range(long long k, long long* lo, long long* hi) {
+  const long long start = k == 0 ? 0 : 17 + 24 * (k - 1);
+  *lo = k == 0 ? 0 : start - 9;
+  *hi = start + (k == 0 ? 41 : 48);
+}
+
+// True while step() still has work for the stream: an explicit chunk, audio that yields at least one more frame, or frames
+// already in the feature ring that complete the next scheduled chunk (one frontend pass can produce several chunks' worth of
+// frames, step() cuts one chunk per stream: callers drain with `while (has_pending) step()`).
 bool Engine::has_pending(int sid) const {
+  PKB_CHECK(sid >= 0 && sid < (int)streams_.size(), "bad stream id");
   const Stream& s = *streams_[sid];
-  return s.open && (!s.pending.empty() || !s.audio.empty() || s.dev_fill >= 400);
+  if (!s.open) return false;
+  if (!s.pending.empty() || !s.audio.empty() || s.dev_fill >= 400) return true;
+  if (s.audio_mode) {
+    long long lo, hi;
+    sched_chunk_range(s.sched_chunk, &lo, &hi);
+    return s.frames_written >= hi;
+  }
+  return false;
 }
 const std::vector<int>& Engine::tokens(int sid) const { return streams_[sid]->tokens; }
 const ChunkResult& Engine::last_chunk(int sid) const { return streams_[sid]->last; }
@@ -784,6 +867,51 @@ std::string Engine::detokenize(const std::vector<int>& ids) const {
   return out.substr(i);
 }
 
+// ------------------------------------------------------------------------------------------------ NaN / Inf guard
+// The reference samples the first 4096 elements of encoder_output and of the two cache outputs after every guarded encoder step
+// (parakeet_trt.cpp:913-1013, call sites :2449-2481).  Same census here, on the device: stage 0 = the stream's encoder_output of the
+// last pass, 1 = its cache_last_channel (the 4 newest rows of layer 0 in the contract ring), 2 = its cache_last_time (layer 0).
+Engine::GuardResult Engine::nan_guard(int sid, int stage) {
+  PKB_CHECK(sid >= 0 && sid < (int)streams_.size() && streams_[sid]->open, "bad stream id");
+  Impl& im = *im_;
+  const Stream& s = *streams_[sid];
+  GuardResult r;
+  GuardRows rows{};
+  const void* base = nullptr;
+  int is_bf16 = 0;
+  if (stage == 0) {
+    if (s.last_entry < 0 || s.last_out_T <= 0) return r;
+    base = im.enc_out + (size_t)s.last_entry * kDModel * s.last_out_T;
+    r.count = (size_t)kDModel * s.last_out_T;
+    rows.n_rows = 1; rows.row_len = (int)std::min<size_t>(r.count, 4096); rows.off[0] = 0;
+  } else if (stage == 1) {
+    if (!im.acache) return r;
+    base = im.acache;      // layer 0
+    is_bf16 = opt_.precision == 1 ? 0 : 1;
+    r.count = (size_t)L_ * kCacheS * kDModel;
+    rows.n_rows = 4; rows.row_len = kDModel;
+    for (int j = 0; j < 4; ++j) rows.off[j] = ((long long)s.slot * kRingCap + (s.head + kCacheS - 4 + j) % kRingCap) * kDModel;
+  } else {
+    base = im.cache_tm + (size_t)s.slot * L_ * kDModel * kTimeCtx;
+    r.count = (size_t)L_ * kDModel * kTimeCtx;
+    rows.n_rows = 1; rows.row_len = (int)std::min<size_t>(r.count, 4096); rows.off[0] = 0;
+  }
+  r.sample_n = (size_t)rows.n_rows * rows.row_len;
+  const int init[4] = {0, 0, 0x7fffffff, 0x7fffffff};
+  PKB_CUDA(cudaStreamSynchronize(st_));
+  memcpy(im.guard_host, init, sizeof(init));
+  PKB_CUDA(cudaMemcpyAsync(im.guard_dev, im.guard_host, sizeof(init), cudaMemcpyHostToDevice, st_));
+  guard_scan_kernel<<<4, 256, 0, st_>>>(base, is_bf16, rows, im.guard_dev);
+  PKB_CUDA(cudaGetLastError());
+  ++launches_;
+  PKB_CUDA(cudaMemcpyAsync(im.guard_host, im.guard_dev, sizeof(init), cudaMemcpyDeviceToHost, st_));
+  PKB_CUDA(cudaStreamSynchronize(st_));
+  r.nan_count = im.guard_host[0]; r.inf_count = im.guard_host[1];
+  r.first_nan = r.nan_count ? im.guard_host[2] : -1;
+  r.first_inf = r.inf_count ? im.guard_host[3] : -1;
+  return r;
+}
+
 // ------------------------------------------------------------------------------------------------ input queues
 void Engine::queue_features(int sid, const float* feats, int T) {
   PKB_CHECK(sid >= 0 && sid < (int)streams_.size() && streams_[sid]->open, "bad stream id");
@@ -791,15 +919,42 @@ void Engine::queue_features(int sid, const float* feats, int T) {
   Stream& s = *streams_[sid];
   Impl& im = *im_;
   PKB_CHECK(!s.audio_mode, "stream is in audio mode");
-  PKB_CHECK(s.pending.empty() || s.frames_written - s.pending.front().f0 + T <= kFeatRing, "feature ring full: call step() first");
-  PKB_CUDA(cudaStreamSynchronize(st_));   // staging buffer reuse
-  memcpy(im.feat_stage_host, feats, (size_t)kNMels * T * sizeof(float));
-  PKB_CUDA(cudaMemcpyAsync(im.feat_stage_dev, im.feat_stage_host, (size_t)kNMels * T * sizeof(float), cudaMemcpyHostToDevice, st_));
-  im.frontend.bins_to_frames(im.feat_stage_dev, T, im.feat_ring + (size_t)s.slot * kFeatRing * kNMels, kFeatRing,
-                             (int)(s.frames_written % kFeatRing), st_);
-  ++launches_;
-  s.pending.push_back(Entry{sid, (int)(s.frames_written % kFeatRing), T});
+  {      // reject a chunk the encoder cannot take HERE, so that a queued chunk can always be processed (see step())
+    const int Tq = sub_len(sub_len(sub_len(T))) - (s.offline ? 0 : kDropPre);
+    if (s.offline) PKB_CHECK(Tq >= 1 && Tq <= kMaxTq, "offline push must hold 1..256 feature frames (got " + std::to_string(T) + ")");
+    else PKB_CHECK(Tq >= kCacheDrop && Tq <= kMaxTq, "chunk must hold 33..256 feature frames (got " + std::to_string(T) + ")");
+  }
+  // all frame indices are absolute here; the ring index is taken (mod kFeatRing) only when the batch is uploaded
+  PKB_CHECK(s.pending.empty() || s.frames_written + T - s.pending.front().f0 <= kFeatRing, "feature ring full: call step() first");
+  const size_t need = (size_t)kNMels * T;
+  if (im.fstage_inflight) { PKB_CUDA(cudaStreamSynchronize(st_)); im.fstage_inflight = false; im.fstage_used = 0; im.fpush_n = 0; im.fpush_max_T = 0; }
+  if (im.fstage_used + need > im.fstage_cap || im.fpush_n == im.fpush_cap) flush_feature_stage(true);
+  memcpy(im.fstage_host + im.fstage_used, feats, need * sizeof(float));
+  FeatPush& d = im.fpush_host[im.fpush_n++];
+  d.src_off = (long long)im.fstage_used;
+  d.ring_off = (long long)s.slot * kFeatRing * kNMels;
+  d.T = T;
+  d.frame0 = (int)(s.frames_written % kFeatRing);
+  im.fstage_used += need;
+  im.fpush_max_T = std::max(im.fpush_max_T, T);
+  s.pending.push_back(Entry{sid, s.frames_written, T});
   s.frames_written += T;
+}
+
+// Staged feature pushes -> feature rings: one H2D copy of the staging area, one copy of the descriptors, one transpose kernel.
+void Engine::flush_feature_stage(bool sync) {
+  Impl& im = *im_;
+  if (im.fpush_n > 0 && !im.fstage_inflight) {
+    PKB_CUDA(cudaMemcpyAsync(im.fstage_dev, im.fstage_host, im.fstage_used * sizeof(float), cudaMemcpyHostToDevice, st_));
+    PKB_CUDA(cudaMemcpyAsync(im.fpush_dev, im.fpush_host, (size_t)im.fpush_n * sizeof(FeatPush), cudaMemcpyHostToDevice, st_));
+    im.frontend.bins_to_frames_batch(im.fstage_dev, im.fpush_dev, im.fpush_n, im.fpush_max_T, im.feat_ring, kFeatRing, st_);
+    ++launches_;
+    im.fstage_inflight = true;
+  }
+  if (sync && im.fstage_inflight) {
+    PKB_CUDA(cudaStreamSynchronize(st_));
+    im.fstage_inflight = false; im.fstage_used = 0; im.fpush_n = 0; im.fpush_max_T = 0;
+  }
 }
 
 void Engine::queue_audio(int sid, const float* pcm, size_t n) {
@@ -896,6 +1051,14 @@ void Engine::set_feature_norm(int sid, const float* mean128, const float* std128
   s.has_norm = true;
 }
 
+void Engine::set_feature_norm_running(int sid, bool on) {
+  PKB_CHECK(sid >= 0 && sid < (int)streams_.size() && streams_[sid]->open, "bad stream id");
+  Stream& s = *streams_[sid];
+  PKB_CHECK(s.frames_written == 0, "set_feature_norm_running: only on a freshly opened / reset stream");
+  s.run_norm = on;
+  PKB_CUDA(cudaMemsetAsync(im_->run_stats + (size_t)s.slot * kRunStats, 0, kRunStats * 4, st_));
+}
+
 // audio -> feature rings for every stream in audio mode (one launch); chunks are then cut by the schedule in step()
 void Engine::frontend_pass() {
   Impl& im = *im_;
@@ -914,6 +1077,7 @@ void Engine::frontend_pass() {
   }
   // 2. one log-mel launch over every stream that holds at least one complete frame and has ring room
   int n_segs = 0, total_frames = 0;
+  bool any_running = false;
   std::vector<std::pair<int, int>> done;   // (sid, frames)
   for (int sid = 0; sid < (int)streams_.size(); ++sid) {
     Stream& s = *streams_[sid];
@@ -931,7 +1095,9 @@ void Engine::frontend_pass() {
     sg.out_stride = kNMels;
     sg.ring_cap = kFeatRing;
     sg.frame0 = (int)(s.frames_written % kFeatRing);
-    sg.norm_off = s.has_norm ? s.slot * 2 * kNMels : -1;
+    sg.norm_off = (s.has_norm && !s.run_norm) ? s.slot * 2 * kNMels : -1;
+    sg.run_state = s.run_norm ? 1 + s.slot * kRunStats : 0;
+    any_running = any_running || s.run_norm;
     im.fprefix_host[n_segs] = total_frames;
     total_frames += frames;
     ++n_segs;
@@ -945,6 +1111,7 @@ void Engine::frontend_pass() {
   im.frontend.logmel(im.audio_buf, im.segs_dev, im.fprefix_dev, n_segs, total_frames, im.feat_ring, im.norm_stats, sm_count_, st_);
   ++launches_;
   prof_end(pi);
+  if (any_running) { im.frontend.running_norm(im.feat_ring, im.segs_dev, im.fprefix_dev, n_segs, im.run_stats, st_); ++launches_; }
   for (auto& d : done) {
     Stream& s = *streams_[d.first];
     s.dev_off += d.second * 160;     // stays even
@@ -975,7 +1142,7 @@ BatchDev Engine::upload_batch(const std::vector<Entry>& entries) {
     const Stream& s = *streams_[entries[i].sid];
     slot[i] = s.slot;
     T[i] = entries[i].T;
-    f0[i] = entries[i].f0;
+    f0[i] = (int)(entries[i].f0 % kFeatRing);
     T1[i] = sub_len(T[i]);
     T2[i] = sub_len(T1[i]);
     T3[i] = sub_len(T2[i]);
@@ -1329,6 +1496,7 @@ void Engine::run_batch(const std::vector<Entry>& entries, float* enc_out_host) {
     prime_streams(fresh);
   }
   for (auto& sp : streams_) sp->last_entry = -1;      // enc_out is about to be overwritten
+  flush_feature_stage(false);                          // staged feature pushes -> feature rings (same stream: ordered before the pass)
   const BatchDev b = upload_batch(entries);
   const int max_steps = b.max_tenc > kValidOut ? kMaxStepsOffline : kMaxStepsPerChunk;
   run_encoder(b);
@@ -1342,6 +1510,7 @@ void Engine::run_batch(const std::vector<Entry>& entries, float* enc_out_host) {
     PKB_CUDA(cudaMemcpyAsync(enc_out_host, im.enc_out, (size_t)b.B * kDModel * b.max_tenc * sizeof(float), cudaMemcpyDeviceToHost, st_));
   }
   PKB_CUDA(cudaStreamSynchronize(st_));
+  if (im.fstage_inflight) { im.fstage_inflight = false; im.fstage_used = 0; im.fpush_n = 0; im.fpush_max_T = 0; }
   if (im.profile) profile_collect();
   const int* h = im.batch_ints_host;
   const int C = im.Bcap;
@@ -1376,9 +1545,15 @@ int Engine::step() {
   int total = 0;
   std::vector<Entry> batch;
   int rows = 0, t3 = 0, t2 = 0;
+  // A chunk leaves its stream's queue (explicit chunks) or advances its schedule (audio mode) only AFTER its batched pass has
+  // succeeded: a pass that throws (bad chunk length, row capacity) leaves every chunk of the batch where it was.
   auto flush = [&]() {
     if (batch.empty()) return;
     run_batch(batch, nullptr);
+    for (const Entry& e : batch) {
+      Stream& s = *streams_[e.sid];
+      if (s.audio_mode) s.sched_chunk += 1; else s.pending.pop_front();
+    }
     total += (int)batch.size();
     batch.clear();
     rows = t3 = t2 = 0;
@@ -1389,12 +1564,10 @@ int Engine::step() {
     Entry e{sid, 0, 0};
     bool have = false;
     if (s.audio_mode) {
-      // streaming_encoder_reference.py:522-550: chunk 0 = [0,41); chunk k = [start-9, start+48), start = 17 + 24(k-1)
-      const long long start = s.sched_chunk == 0 ? 0 : 17 + 24 * (s.sched_chunk - 1);
-      const long long lo = s.sched_chunk == 0 ? 0 : start - 9;
-      const long long hi = start + (s.sched_chunk == 0 ? 41 : 48);
+      long long lo, hi;
+      sched_chunk_range(s.sched_chunk, &lo, &hi);
       if (s.frames_written >= hi) {
-        e.f0 = (int)(lo % kFeatRing);
+        e.f0 = lo;
         e.T = (int)(hi - lo);
         have = true;
       }
@@ -1409,7 +1582,6 @@ int Engine::step() {
     if (rows + Tq > im.Mcap || t3 + T3 > im.T3cap || t2 + T2 > im.T2cap) flush();
     batch.push_back(e);
     rows += Tq; t3 += T3; t2 += T2;
-    if (s.audio_mode) s.sched_chunk += 1; else s.pending.pop_front();
   }
   flush();
   return total;
@@ -1426,7 +1598,8 @@ void Engine::import_state(int sid, const float* cache_ch, long long, const float
   s.cache_len = cache_len;
   s.head = 0;
   int hv[2] = {s.slot, 0};
-  int* meta = dev_alloc<int>(2);
+  int* meta = im.meta2;
+  PKB_CUDA(cudaStreamSynchronize(st_));      // meta2 / scratch reuse
   PKB_CUDA(cudaMemcpyAsync(meta, hv, sizeof(hv), cudaMemcpyHostToDevice, st_));
   PKB_CUDA(cudaMemcpyAsync(im.scratch_f32, cache_ch, im.scratch_f32_elems * 4, cudaMemcpyHostToDevice, st_));
   PKB_CUDA(cudaMemcpyAsync(im.cache_tm + (size_t)s.slot * L_ * kDModel * kTimeCtx, cache_tm, (size_t)L_ * kDModel * kTimeCtx * 4,
@@ -1445,7 +1618,6 @@ void Engine::import_state(int sid, const float* cache_ch, long long, const float
     RUN_GEMM(im.a_imp, im.layers[l].kv, kCacheS, nullptr, e);
   }
   PKB_CUDA(cudaStreamSynchronize(st_));
-  cudaFree(meta);
 }
 
 void Engine::export_state(int sid, float* cache_ch, float* cache_tm) {
@@ -1455,7 +1627,8 @@ void Engine::export_state(int sid, float* cache_ch, float* cache_tm) {
   const bool split = opt_.precision == 1;
   const size_t kv_elem = split ? 4 : 2;
   int hv[2] = {s.slot, s.head};
-  int* meta = dev_alloc<int>(2);
+  int* meta = im.meta2;
+  PKB_CUDA(cudaStreamSynchronize(st_));
   PKB_CUDA(cudaMemcpyAsync(meta, hv, sizeof(hv), cudaMemcpyHostToDevice, st_));
   for (int l = 0; l < L_; ++l) {
     const char* ac = (const char*)im.acache + (size_t)l * im.ring_layer_elems * kv_elem;
@@ -1465,7 +1638,6 @@ void Engine::export_state(int sid, float* cache_ch, float* cache_tm) {
   PKB_CUDA(cudaMemcpyAsync(cache_tm, im.cache_tm + (size_t)s.slot * L_ * kDModel * kTimeCtx, (size_t)L_ * kDModel * kTimeCtx * 4,
                            cudaMemcpyDeviceToHost, st_));
   PKB_CUDA(cudaStreamSynchronize(st_));
-  cudaFree(meta);
   // rows that were never filled are zeros in the contract cache (zero-initialised FIFO)
   const int invalid = kCacheS - s.cache_len;
   for (int l = 0; l < L_; ++l) memset(cache_ch + (size_t)l * kCacheS * kDModel, 0, (size_t)invalid * kDModel * 4);
@@ -1512,18 +1684,33 @@ void Engine::get_decoder_state(int sid, float* h, float* c, float* g) {
   PKB_CUDA(cudaMemcpy(g, im.pred_g + slot * kPredH, kPredH * 4, cudaMemcpyDeviceToHost));
 }
 
+// Streams borrowed by a tensor-level call: closed again on every exit path (an exception must not leak slots).
+struct Engine::TempStreams {
+  Engine* e;
+  std::vector<int> sids;
+  explicit TempStreams(Engine* eng) : e(eng) {}
+  int open() { sids.push_back(e->open_stream()); return sids.back(); }
+  ~TempStreams() { for (int s : sids) e->close_stream(s); }
+};
+
 void Engine::encoder_streaming_step(int B, int T, const float* audio_signal, const int64_t* length, const float* cache_last_channel,
                                     const float* cache_last_time, const int64_t* cache_last_channel_len, float* encoder_output,
                                     int64_t* encoded_lengths, float* cache_last_channel_out, float* cache_last_time_out,
                                     int64_t* cache_last_channel_len_out) {
   PKB_CHECK(B >= 1 && B <= opt_.max_streams, "encoder_streaming_step: B exceeds max_streams");
-  const size_t ch_stride = (size_t)L_ * kCacheS * kDModel, tm_stride = (size_t)L_ * kDModel * kTimeCtx;
-  std::vector<int> sids;
-  std::vector<Entry> entries;
+  // everything that can be rejected is rejected before a stream slot is borrowed
+  const int Tq = sub_len(sub_len(sub_len(T))) - kDropPre;
+  PKB_CHECK(T >= 1 && T <= 256 && Tq >= kCacheDrop && Tq <= kMaxTq, "chunk must hold 33..256 feature frames (got " + std::to_string(T) + ")");
+  PKB_CHECK(im_->acache != nullptr, "encoder_streaming_step needs contract_cache=1");
   for (int i = 0; i < B; ++i) {
     PKB_CHECK(length[i] == T, "encoder_streaming_step: length must equal T for every stream");
-    const int sid = open_stream();
-    sids.push_back(sid);
+    PKB_CHECK(cache_last_channel_len[i] >= 0 && cache_last_channel_len[i] <= kCacheS, "cache_last_channel_len out of range");
+  }
+  const size_t ch_stride = (size_t)L_ * kCacheS * kDModel, tm_stride = (size_t)L_ * kDModel * kTimeCtx;
+  TempStreams tmp(this);
+  std::vector<Entry> entries;
+  for (int i = 0; i < B; ++i) {
+    const int sid = tmp.open();
     import_state(sid, cache_last_channel + i * ch_stride, 0, cache_last_time + i * tm_stride, (int)cache_last_channel_len[i]);
     queue_features(sid, audio_signal + (size_t)i * kNMels * T, T);
     entries.push_back(streams_[sid]->pending.front());
@@ -1531,11 +1718,10 @@ void Engine::encoder_streaming_step(int B, int T, const float* audio_signal, con
   }
   run_batch(entries, encoder_output);
   for (int i = 0; i < B; ++i) {
-    Stream& s = *streams_[sids[i]];
+    Stream& s = *streams_[tmp.sids[i]];
     encoded_lengths[i] = s.last.encoded_len;
     cache_last_channel_len_out[i] = s.cache_len;
-    export_state(sids[i], cache_last_channel_out + i * ch_stride, cache_last_time_out + i * tm_stride);
-    close_stream(sids[i]);
+    export_state(tmp.sids[i], cache_last_channel_out + i * ch_stride, cache_last_time_out + i * tm_stride);
   }
 }
 
@@ -1544,22 +1730,19 @@ void Engine::encoder_streaming_step(int B, int T, const float* audio_signal, con
 void Engine::encoder_offline_step(int B, int T, const float* audio_signal, const int64_t* length, float* encoder_output,
                                   int64_t* encoded_lengths) {
   PKB_CHECK(B >= 1 && B <= opt_.max_streams, "encoder_offline_step: B exceeds max_streams");
-  std::vector<int> sids;
+  PKB_CHECK(T >= 1 && T <= 256, "offline push must hold 1..256 feature frames (got " + std::to_string(T) + ")");
+  for (int i = 0; i < B; ++i) PKB_CHECK(length[i] == T, "encoder_offline_step: length must equal T for every stream");
+  TempStreams tmp(this);
   std::vector<Entry> entries;
   for (int i = 0; i < B; ++i) {
-    PKB_CHECK(length[i] == T, "encoder_offline_step: length must equal T for every stream");
-    const int sid = open_stream();
-    sids.push_back(sid);
+    const int sid = tmp.open();
     set_stream_offline(sid, true);
     queue_features(sid, audio_signal + (size_t)i * kNMels * T, T);
     entries.push_back(streams_[sid]->pending.front());
     streams_[sid]->pending.pop_front();
   }
   run_batch(entries, encoder_output);
-  for (int i = 0; i < B; ++i) {
-    encoded_lengths[i] = streams_[sids[i]]->last.encoded_len;
-    close_stream(sids[i]);
-  }
+  for (int i = 0; i < B; ++i) encoded_lengths[i] = streams_[tmp.sids[i]]->last.encoded_len;
 }
 
 // ------------------------------------------------------------------------------------------------ whole-utterance offline path
@@ -1653,15 +1836,16 @@ void Engine::offline_utterances(int n, const int* sids, const float* const* pcm,
     size_t total_samples = 0;
     std::vector<size_t> aoff(n);
     for (int i = 0; i < n; ++i) { aoff[i] = total_samples; total_samples += (n_samples[i] + 1) & ~(size_t)1; }   // even offsets (float2 loads)
-    float* d_audio = dev_alloc<float>(total_samples + 2);
-    FrontSegment* d_seg = dev_alloc<FrontSegment>(n);
-    int* d_ints = dev_alloc<int>(2 * n + 1);
-    float* d_stats = dev_alloc<float>((size_t)n * 2 * kNMels);
+    DevTmp tmp;
+    float* d_audio = tmp.alloc<float>(total_samples + 2);
+    FrontSegment* d_seg = tmp.alloc<FrontSegment>(n);
+    int* d_ints = tmp.alloc<int>(2 * n + 1);
+    float* d_stats = tmp.alloc<float>((size_t)n * 2 * kNMels);
     std::vector<FrontSegment> segs(n);
     std::vector<int> ints(2 * n + 1);
     for (int i = 0; i < n; ++i) {
       PKB_CUDA(cudaMemcpyAsync(d_audio + aoff[i], pcm[i], n_samples[i] * sizeof(float), cudaMemcpyHostToDevice, st_));
-      segs[i] = FrontSegment{(long long)aoff[i], (long long)f0[i] * kNMels, kNMels, 0, 0, -1};
+      segs[i] = FrontSegment{(long long)aoff[i], (long long)f0[i] * kNMels, kNMels, 0, 0, -1, 0};
       ints[i] = f0[i];
       ints[n + 1 + i] = T[i];
     }
@@ -1678,15 +1862,14 @@ void Engine::offline_utterances(int n, const int* sids, const float* const* pcm,
       im.frontend.apply_norm(im.lf_feat, d_seg, d_ints + n + 1, n, maxT, d_stats, st_); ++launches_;
     }
     PKB_CUDA(cudaStreamSynchronize(st_));      // the pageable sources and the host vectors above are done with
-    cudaFree(d_audio); cudaFree(d_seg); cudaFree(d_ints); cudaFree(d_stats);
   } else {
     for (int i = 0; i < n; ++i) {
       if (bins_major) {
-        float* d_tmp = dev_alloc<float>((size_t)T[i] * kNMels);
+        DevTmp tmp;
+        float* d_tmp = tmp.alloc<float>((size_t)T[i] * kNMels);
         PKB_CUDA(cudaMemcpyAsync(d_tmp, feats[i], (size_t)T[i] * kNMels * sizeof(float), cudaMemcpyHostToDevice, st_));
         im.frontend.bins_to_frames(d_tmp, T[i], im.lf_feat, (int)im.lf_feat_frames, f0[i], st_); ++launches_;
         PKB_CUDA(cudaStreamSynchronize(st_));
-        cudaFree(d_tmp);
       } else {
         PKB_CUDA(cudaMemcpyAsync(im.lf_feat + (size_t)f0[i] * kNMels, feats[i], (size_t)T[i] * kNMels * sizeof(float), cudaMemcpyHostToDevice, st_));
       }
@@ -1840,8 +2023,9 @@ int Engine::offline_decode_pending() {
 void Engine::predictor_step(int B, const int64_t* y, const float* h, const float* c, float* g, float* h_out, float* c_out) {
   Impl& im = *im_;
   PKB_CHECK(B >= 1 && B <= opt_.max_streams, "predictor_step: B exceeds max_streams");
-  std::vector<int> sids;
-  for (int i = 0; i < B; ++i) { sids.push_back(open_stream()); streams_[sids.back()]->needs_prime = false; }
+  TempStreams tmp(this);
+  for (int i = 0; i < B; ++i) streams_[tmp.open()]->needs_prime = false;
+  const std::vector<int>& sids = tmp.sids;
   PKB_CUDA(cudaStreamSynchronize(st_));
   std::vector<float> hb(kPredL * kPredH), cb(kPredL * kPredH);
   for (int i = 0; i < B; ++i) {
@@ -1872,7 +2056,6 @@ void Engine::predictor_step(int B, const int64_t* y, const float* h, const float
       memcpy(c_out + ((size_t)l * B + i) * kPredH, &cb[l * kPredH], kPredH * 4);
     }
     PKB_CUDA(cudaMemcpy(g + (size_t)i * kPredH, im.pred_g + slot * kPredH, kPredH * 4, cudaMemcpyDeviceToHost));  // [B,640,1]
-    close_stream(sids[i]);
   }
 }
 
@@ -1882,9 +2065,10 @@ void Engine::joint_step(int B, int T, int U, const float* enc, const float* pred
   PKB_CHECK(B >= 1 && B * T <= im.a_xf.rows_cap && B * U <= im.a_g.rows_cap && rows <= im.a_hid.rows_cap,
             "joint_step: B*T*U exceeds the decode row capacity (raise max_streams)");
   PKB_CUDA(cudaStreamSynchronize(st_));
-  float* d_enc = dev_upload(std::vector<float>(enc, enc + (size_t)B * kDModel * T));
-  float* d_pred = dev_upload(std::vector<float>(pred, pred + (size_t)B * kPredH * U));
-  float* d_P = dev_alloc<float>((size_t)B * U * kJointH);
+  DevTmp tmp;
+  float* d_enc = tmp.upload(enc, (size_t)B * kDModel * T);
+  float* d_pred = tmp.upload(pred, (size_t)B * kPredH * U);
+  float* d_P = tmp.alloc<float>((size_t)B * U * kJointH);
   // enc [B,1024,T] -> operand rows (b*T+t): row stride within b is 1 (t), col stride T
   for (int b = 0; b < B; ++b) {
     ActOut a = im.a_xf.out(); a.ptr += (size_t)b * T * a.lda;
@@ -1902,7 +2086,6 @@ void Engine::joint_step(int B, int T, int U, const float* enc, const float* pred
     RUN_GEMM(im.a_hid, im.joint_out, rows, nullptr, e); }
   PKB_CUDA(cudaMemcpyAsync(out, im.logits, (size_t)rows * kJointOut * 4, cudaMemcpyDeviceToHost, st_));
   PKB_CUDA(cudaStreamSynchronize(st_));
-  cudaFree(d_enc); cudaFree(d_pred); cudaFree(d_P);
 }
 
 size_t Engine::logmel(const float* pcm, size_t n, float* out, int per_feature_norm) {
@@ -1910,14 +2093,15 @@ size_t Engine::logmel(const float* pcm, size_t n, float* out, int per_feature_no
   if (n < 400) return 0;
   const size_t T = (n - 400) / 160 + 1;
   PKB_CHECK(T < (1u << 30), "clip too long");
-  float* d_audio = dev_alloc<float>(n);
-  float* d_out = dev_alloc<float>(T * kNMels);
-  float* d_stats = dev_alloc<float>(2 * kNMels);
+  DevTmp tmp;
+  float* d_audio = tmp.alloc<float>(n);
+  float* d_out = tmp.alloc<float>(T * kNMels);
+  float* d_stats = tmp.alloc<float>(2 * kNMels);
   PKB_CUDA(cudaMemcpyAsync(d_audio, pcm, n * 4, cudaMemcpyHostToDevice, st_));
-  FrontSegment sg{0, 0, kNMels, 0, 0, -1};
+  FrontSegment sg{0, 0, kNMels, 0, 0, -1, 0};
   int prefix[2] = {0, (int)T}, frames = (int)T;
-  FrontSegment* d_seg = dev_alloc<FrontSegment>(1);
-  int* d_prefix = dev_alloc<int>(3);
+  FrontSegment* d_seg = tmp.alloc<FrontSegment>(1);
+  int* d_prefix = tmp.alloc<int>(3);
   PKB_CUDA(cudaMemcpyAsync(d_seg, &sg, sizeof(sg), cudaMemcpyHostToDevice, st_));
   PKB_CUDA(cudaMemcpyAsync(d_prefix, prefix, sizeof(prefix), cudaMemcpyHostToDevice, st_));
   PKB_CUDA(cudaMemcpyAsync(d_prefix + 2, &frames, sizeof(int), cudaMemcpyHostToDevice, st_));
@@ -1931,7 +2115,6 @@ size_t Engine::logmel(const float* pcm, size_t n, float* out, int per_feature_no
   PKB_CUDA(cudaMemcpyAsync(out, d_out, T * kNMels * 4, cudaMemcpyDeviceToHost, st_));
   PKB_CUDA(cudaStreamSynchronize(st_));
   if (im.profile) profile_collect();
-  cudaFree(d_audio); cudaFree(d_out); cudaFree(d_stats); cudaFree(d_seg); cudaFree(d_prefix);
   return T;
 }
 

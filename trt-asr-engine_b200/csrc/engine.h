@@ -54,6 +54,8 @@ class Engine {
   // (tools/verify_nemo/streaming_encoder_reference.py:522-550).
   void queue_audio(int sid, const float* pcm, size_t n);
   void set_feature_norm(int sid, const float* mean128, const float* std128);   // nullptrs: none
+  // streaming-safe alternative: causal running mean / std per feature over the stream's own frames (GPU frontend, audio input)
+  void set_feature_norm_running(int sid, bool on);
   // offline mode (the reference's non-streaming `encoder` engine): every push of <= 256 frames is encoded with full context and no
   // caches, all of its encoder frames are decoded; only valid on a fresh stream
   void set_stream_offline(int sid, bool offline);
@@ -64,7 +66,10 @@ class Engine {
 
   // Advance every stream that has a pending chunk by one chunk.  Returns the number of chunks processed.
   int step();
+  // work left for step(): an explicit chunk, audio that still yields frames, or ring frames completing the next scheduled chunk
+  // (drain with `while (has_pending(sid)) step();`)
   bool has_pending(int sid) const;
+  void drop_pending(int sid);              // forget queued, unprocessed chunks of a stream (error recovery)
 
   const std::vector<int>& tokens(int sid) const;
   const ChunkResult& last_chunk(int sid) const;
@@ -116,6 +121,11 @@ class Engine {
   // standalone GEMM for validation of the tensor-core backend: C = A(f32, split or rounded per precision) * W^T
   void gemm_test(int backend, int M, int N, int K, const float* A, const uint16_t* W_bf16, float* C, int epi_silu);
 
+  // NaN / Inf census of a stream's tensors after its last pass (the reference's nan_guard_device, parakeet_trt.cpp:913-1013):
+  // stage 0 encoder_output, 1 cache_last_channel (newest rows, layer 0), 2 cache_last_time (layer 0)
+  struct GuardResult { int nan_count = 0, inf_count = 0, first_nan = -1, first_inf = -1; size_t sample_n = 0, count = 0; };
+  GuardResult nan_guard(int sid, int stage);
+
   const EngineOptions& options() const { return opt_; }
   int n_layers() const { return L_; }
   const std::vector<std::string>& vocab() const { return vocab_; }
@@ -135,7 +145,8 @@ class Engine {
 
   struct Stream;
   struct Impl;
-  struct Entry { int sid; int f0; int T; };
+  struct TempStreams;
+  struct Entry { int sid; long long f0; int T; };      // f0: ABSOLUTE index of the chunk's first frame (ring index = f0 % ring capacity)
   Impl* impl();
 
  private:
@@ -150,6 +161,7 @@ class Engine {
   void lf_prepare(size_t total_frames, size_t steps_ints);
   void run_predictor_pass(const DecodeDev& d);
   void frontend_pass();
+  void flush_feature_stage(bool sync);
   void prime_streams(const std::vector<int>& sids);
   void import_state(int sid, const float* cache_ch, long long ch_stride_unused, const float* cache_tm, int cache_len);
   void export_state(int sid, float* cache_ch, float* cache_tm);

@@ -297,6 +297,39 @@ feature_norm_kernel(float* __restrict__ feat, const FrontSegment* __restrict__ s
   (void)max_frames;
 }
 
+// One CTA per segment, thread == mel bin: sequential over the segment's new frames (24 per streaming step).
+__global__ void __launch_bounds__(128)
+running_norm_kernel(float* __restrict__ out, const FrontSegment* __restrict__ segs, const int* __restrict__ frame_prefix,
+                    float* __restrict__ state) {
+  const FrontSegment sg = segs[blockIdx.x];
+  if (sg.run_state == 0) return;
+  const int m = threadIdx.x;
+  float* st = state + (sg.run_state - 1);
+  const int T = frame_prefix[blockIdx.x + 1] - frame_prefix[blockIdx.x];
+  float n = st[0], mean = st[1 + m], m2 = st[1 + kNMels + m];
+  __syncthreads();      // every thread has read the shared count before thread 0 updates it
+  for (int t = 0; t < T; ++t) {
+    const int orow = sg.ring_cap > 0 ? (sg.frame0 + t) % sg.ring_cap : t;
+    float* o = out + sg.out_off + (size_t)orow * sg.out_stride + m;
+    const float x = *o;
+    n += 1.0f;
+    const float delta = x - mean;
+    mean += delta / n;
+    m2 = fmaf(delta, x - mean, m2);
+    *o = n > 1.5f ? (x - mean) / (sqrtf(m2 / (n - 1.0f)) + 1e-5f) : 0.0f;
+  }
+  st[1 + m] = mean;
+  st[1 + kNMels + m] = m2;
+  if (m == 0) st[0] = n;
+}
+
+void Frontend::running_norm(float* d_out, const FrontSegment* d_segs, const int* d_frame_prefix, int n_segs, float* d_state,
+                            cudaStream_t st) {
+  if (n_segs <= 0) return;
+  running_norm_kernel<<<n_segs, kNMels, 0, st>>>(d_out, d_segs, d_frame_prefix, d_state);
+  PKB_CUDA(cudaGetLastError());
+}
+
 void Frontend::per_feature_stats(const float* d_feat, const FrontSegment* d_segs, const int* d_frames, int n_segs,
                                  float* d_stats, cudaStream_t st) {
   if (n_segs <= 0) return;
@@ -327,6 +360,36 @@ bins_to_frames_kernel(const float* __restrict__ src, int T, float* __restrict__ 
     const int t = t0 + r;
     if (t < T) ring[(size_t)((frame0 + t) % ring_cap) * kNMels + m0 + tx] = tile[tx][r];
   }
+}
+
+__global__ void __launch_bounds__(256)
+bins_to_frames_batch_kernel(const float* __restrict__ stage, const FeatPush* __restrict__ push, float* __restrict__ rings, int ring_cap) {
+  __shared__ float tile[32][33];
+  const FeatPush p = push[blockIdx.z];
+  const int t0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  if (t0 >= p.T) return;
+  const float* src = stage + p.src_off;
+  float* ring = rings + p.ring_off;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int t = t0 + tx;
+    tile[r][tx] = t < p.T ? src[(size_t)(m0 + r) * p.T + t] : 0.0f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int t = t0 + r;
+    if (t < p.T) ring[(size_t)((p.frame0 + t) % ring_cap) * kNMels + m0 + tx] = tile[tx][r];
+  }
+}
+
+void Frontend::bins_to_frames_batch(const float* d_stage, const FeatPush* d_push, int n, int max_T, float* d_rings, int ring_cap,
+                                    cudaStream_t st) {
+  if (n <= 0 || max_T <= 0) return;
+  for (int i0 = 0; i0 < n; i0 += 65535) {      // grid.z limit
+    const int cnt = n - i0 < 65535 ? n - i0 : 65535;
+    bins_to_frames_batch_kernel<<<dim3((max_T + 31) / 32, kNMels / 32, cnt), 256, 0, st>>>(d_stage, d_push + i0, d_rings, ring_cap);
+  }
+  PKB_CUDA(cudaGetLastError());
 }
 
 void Frontend::bins_to_frames(const float* d_src, int T, float* d_ring, int ring_cap, int frame0, cudaStream_t st) {
