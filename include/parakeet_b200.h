@@ -114,6 +114,15 @@ int32_t pkb_stream_cache_len(PkbEngine* engine, int32_t stream);                
 int64_t pkb_stream_chunks_done(PkbEngine* engine, int32_t stream);
 int32_t pkb_stream_text(PkbEngine* engine, int32_t stream, char* out, int32_t cap);           /* detokenised transcript so far */
 int32_t pkb_detokenize(PkbEngine* engine, const int32_t* ids, int32_t n, char* out, int32_t cap);
+int32_t pkb_token_is_punct_only(PkbEngine* engine, int32_t id);   /* the predicate of the leading-punctuation suppression */
+/* The token table without an engine or a GPU (replaces the reference's Tokenizer, cpp/src/tokenizer.cpp:9-84: constructor = open,
+ * decode, is_punct_only, vocab_size).  pkb_vocab_decode copies min(len, cap-1) bytes + NUL and returns the full length. */
+typedef struct PkbVocab PkbVocab;
+PkbVocab* pkb_vocab_open(const char* vocab_txt_path);              /* NULL on failure (pkb_last_error) */
+void pkb_vocab_close(PkbVocab* vocab);
+int32_t pkb_vocab_size(const PkbVocab* vocab);
+int32_t pkb_vocab_decode(const PkbVocab* vocab, const int32_t* ids, int32_t n, char* out, int32_t cap);
+int32_t pkb_vocab_is_punct_only(const PkbVocab* vocab, int32_t id);
 
 /* ---- per-stream state across the ABI (cache carry-over made explicit: checkpoint, migration, functional-mode parity) ----
  * One stream's encoder caches in the contract layout: cache_last_channel [L,256,1024] (valid region = the last

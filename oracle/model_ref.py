@@ -322,12 +322,13 @@ def prime(model: ModelRef, st: DecodeState) -> None:
 
 def tdt_greedy_chunk(model: ModelRef, st: DecodeState, enc_out: torch.Tensor, t_enc: int,
                      max_symbols: int = 8, punct_suppression: bool = True,
-                     margins: Optional[list] = None) -> List[Tuple[int, int, int, int]]:
+                     margins: Optional[list] = None, blank_penalty: float = 0.0) -> List[Tuple[int, int, int, int]]:
     """Greedy TDT over one chunk's encoder frames; mutates st.  Returns the per-step trace
     [(time_idx, best_tok, duration, advance)].  Follows parakeet_trt.cpp:2914-3676 / tdt_trace.py:277-353:
     first-max-wins argmax (strict '>'), blank+dur0 -> advance 1, non-blank -> predictor step,
     advance 0 -> stay, forced +1 after max_symbols, leftover advance dropped at chunk end,
-    leading punctuation-only suppression while nothing has been emitted (:3256-3262)."""
+    leading punctuation-only suppression while nothing has been emitted (:3256-3262); NaN logits read as -100 (:2971, both heads);
+    PARAKEET_BLANK_PENALTY is subtracted from the blank logit before the token argmax (:3175-3178)."""
     dur_values = [0, 1, 2, 3, 4]
     V = model.vocab
     trace = []
@@ -336,6 +337,10 @@ def tdt_greedy_chunk(model: ModelRef, st: DecodeState, enc_out: torch.Tensor, t_
         advanced = False
         for _u in range(max_symbols):
             logits = model.joint_logits(enc_out[:, :, t:t + 1], st.g)[0, 0, 0]
+            logits = torch.where(torch.isnan(logits), torch.full_like(logits, -100.0), logits)
+            if blank_penalty != 0.0:
+                logits = logits.clone()
+                logits[model.blank] -= blank_penalty
             tok = int(torch.argmax(logits[:V]))       # torch.argmax returns the first maximal index
             if punct_suppression and not st.tokens and model.is_punct_only(tok):
                 tok = model.blank

@@ -4,7 +4,8 @@ FUNCTIONAL mode, like the reference's own harness (tools/onnxruntime/onnx_stream
 chunk the GPU stream receives the ORACLE's state (encoder caches in the contract layout + predictor state) through the
 state-import entry points, runs the chunk, and its (time_idx, token, duration) trace is compared with the oracle's.
   precise mode: every chunk must be identical.
-  bf16 mode   : >= 99 % of the CONFIDENT chunks must be identical, where a chunk is confident when every decision the oracle
+  bf16 mode   : >= 99 % of ALL chunks identical (the north_star criterion, unfiltered), and as the diagnostic that separates
+                arithmetic noise from a broken path: >= 99 % of the CONFIDENT chunks must be identical, where a chunk is confident when every decision the oracle
                 takes in it has a top-2 logit gap above TAU on both heads -- decisions closer than the stated bf16 logit
                 tolerance are ambiguous for any bf16 implementation (the reference's own fp16 TensorRT engine flips there:
                 docs/VALIDATION_REPORT_TRACE.md:57-72).  The share of confident chunks is asserted too, so the filter
@@ -66,6 +67,7 @@ def test_parity_set_functional(model_full, features_ref, precision):
     if precision == 1:
         assert same_all == total
     else:
+        assert same_all >= 0.99 * total, f"{same_all}/{total} of ALL chunks identical (north_star: >= 99 %)"
         assert confident >= 0.6 * total, "margin filter removed too many chunks"
         assert same_conf >= 0.99 * confident, f"{same_conf}/{confident} confident chunks identical"
     eng.close()

@@ -1,5 +1,6 @@
 """Oracle pin for the frontend: the reference's only test (shape) + analytic known answers."""
 import numpy as np
+import pytest
 
 from synth_audio import synth_clip
 
@@ -77,3 +78,25 @@ def test_per_feature_norm(features_ref):
     assert np.allclose(n.mean(0)[live], 0, atol=1e-3) and np.allclose(n.std(0, ddof=1)[live], 1, atol=1e-3)
     m1, s1 = features_ref.stats(f[:1])                                             # T <= 1 -> denominator 1
     assert np.allclose(m1, f[0]) and np.allclose(s1, 1e-5)
+
+
+def test_feature_values_against_torchaudio(features_ref):
+    """Independent second opinion on the feature VALUES (the reference holds no golden feature vectors: its only test checks the
+    frame count, rust/features/src/lib.rs:229-241): torchaudio's MelSpectrogram configured like the reference extractor -- n_fft 512,
+    symmetric Hann-400, hop 160, no centring, power spectrum, 128 un-normalised HTK triangles over 0..8 kHz -- then ln(E + 1e-5)
+    (lib.rs:66-120, 174-223).  torch.stft centres a short window inside its 512-sample frame (56 zeros either side) where the
+    reference zero-pads the tail; the power spectrum does not see that shift, so the signal is offset by 56 samples to frame alike.
+    Agreement 1e-4 measured; asserted at the north_star tolerance of 1e-3."""
+    torchaudio = pytest.importorskip("torchaudio")
+    import torch
+    from synth_audio import synth_clip
+    ms = torchaudio.transforms.MelSpectrogram(sample_rate=16000, n_fft=512, win_length=400, hop_length=160, f_min=0.0, f_max=8000.0,
+                                              n_mels=128, window_fn=lambda n: torch.hann_window(n, periodic=False), power=2.0,
+                                              center=False, norm=None, mel_scale="htk")
+    for seed, secs, gain in ((5, 3.0, 1.0), (6, 1.0, 0.05), (7, 2.0, 4.0)):
+        x = (gain * synth_clip(secs, seed)).astype(np.float32)
+        ref = features_ref.logmel(x)
+        xp = torch.cat([torch.zeros(56), torch.from_numpy(x), torch.zeros(56)])
+        got = torch.log(ms(xp[None])[0].T + 1e-5).numpy()
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() < 1e-3, float(np.abs(got - ref).max())

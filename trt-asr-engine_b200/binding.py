@@ -30,7 +30,8 @@ B200_SYMBOLS = ["pkb_last_error", "pkb_version", "pkb_engine_create", "pkb_engin
                 "pkb_engine_push_audio_batch_device", "pkb_engine_event_record", "pkb_engine_event_elapsed_ms",
                 "pkb_engine_profile_enable", "pkb_engine_profile_read", "pkb_engine_profile_read_class", "pkb_engine_step", "pkb_stream_has_pending",
                 "pkb_stream_num_tokens", "pkb_stream_tokens", "pkb_stream_token_frames", "pkb_stream_encoder_frames", "pkb_stream_stable_prefix", "pkb_stream_last_steps", "pkb_stream_cache_len",
-                "pkb_stream_chunks_done", "pkb_stream_text", "pkb_detokenize", "pkb_stream_import_state", "pkb_stream_export_state",
+                "pkb_stream_chunks_done", "pkb_stream_text", "pkb_detokenize", "pkb_token_is_punct_only", "pkb_vocab_open", "pkb_vocab_close",
+                "pkb_vocab_size", "pkb_vocab_decode", "pkb_vocab_is_punct_only", "pkb_stream_import_state", "pkb_stream_export_state",
                 "pkb_stream_set_decoder_state", "pkb_stream_get_decoder_state", "pkb_encoder_streaming_step", "pkb_predictor_step",
                 "pkb_joint_step", "pkb_logmel", "pkb_gemm_test", "pkb_frontend_create", "pkb_frontend_destroy", "pkb_frontend_logmel"]
 
@@ -127,6 +128,14 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.pkb_stream_stable_prefix.argtypes = [vp, C.c_int32, C.c_int32]
     lib.pkb_stream_text.argtypes = [vp, C.c_int32, C.c_char_p, C.c_int32]
     lib.pkb_detokenize.argtypes = [vp, ip, C.c_int32, C.c_char_p, C.c_int32]
+    lib.pkb_token_is_punct_only.argtypes = [vp, C.c_int32]
+    lib.pkb_vocab_open.restype = vp
+    lib.pkb_vocab_open.argtypes = [C.c_char_p]
+    lib.pkb_vocab_close.argtypes = [vp]
+    lib.pkb_vocab_close.restype = None
+    lib.pkb_vocab_size.argtypes = [vp]
+    lib.pkb_vocab_decode.argtypes = [vp, ip, C.c_int32, C.c_char_p, C.c_int32]
+    lib.pkb_vocab_is_punct_only.argtypes = [vp, C.c_int32]
     lib.pkb_stream_import_state.argtypes = [vp, C.c_int32, fp, fp, C.c_int32]
     lib.pkb_stream_export_state.argtypes = [vp, C.c_int32, fp, fp, ip]
     lib.pkb_stream_set_decoder_state.argtypes = [vp, C.c_int32, fp, fp, fp, C.c_int32, C.c_int32]
@@ -208,6 +217,40 @@ class ParakeetSessionSafe:
             self._s = None
 
     def __del__(self):  # lib.rs:108-112 (Drop)
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Vocab:
+    """The product's token table on its own (pkb_vocab_*; no GPU): mirror of the reference's `Tokenizer` (cpp/include/tokenizer.h)."""
+
+    def __init__(self, vocab_path: str):
+        self._lib = load_library()
+        self._v = self._lib.pkb_vocab_open(vocab_path.encode())
+        if not self._v:
+            raise RuntimeError("pkb_vocab_open failed: " + self._lib.pkb_last_error().decode())
+
+    def vocab_size(self) -> int:
+        return int(self._lib.pkb_vocab_size(self._v))
+
+    def decode(self, ids) -> str:
+        a = np.ascontiguousarray(ids, np.int32)
+        n = self._lib.pkb_vocab_decode(self._v, a.ctypes.data_as(C.POINTER(C.c_int32)), a.size, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        self._lib.pkb_vocab_decode(self._v, a.ctypes.data_as(C.POINTER(C.c_int32)), a.size, buf, n + 1)
+        return buf.value.decode("utf-8", "replace")
+
+    def is_punct_only(self, i: int) -> bool:
+        return bool(self._lib.pkb_vocab_is_punct_only(self._v, int(i)))
+
+    def close(self):
+        if self._v:
+            self._lib.pkb_vocab_close(self._v)
+            self._v = None
+
+    def __del__(self):
         try:
             self.close()
         except Exception:
@@ -352,6 +395,9 @@ class Engine:
         buf = C.create_string_buffer(1 << 16)
         self._chk(self._lib.pkb_detokenize(self._e, a.ctypes.data_as(C.POINTER(C.c_int32)), a.size, buf, len(buf)))
         return buf.value.decode("utf-8", "replace")
+
+    def token_is_punct_only(self, i: int) -> bool:
+        return bool(self._chk(self._lib.pkb_token_is_punct_only(self._e, int(i))))
 
     def kernel_launches(self) -> int:
         return int(self._lib.pkb_engine_kernel_launches(self._e))

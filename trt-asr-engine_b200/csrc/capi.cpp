@@ -101,6 +101,10 @@ struct SharedEngine {
   std::vector<ParakeetSession*> sessions;
 };
 
+struct PkbVocab {
+  pkb::Vocab v;
+};
+
 struct PkbFrontend {
   pkb::Frontend* fe = nullptr;
   cudaStream_t st = nullptr;
@@ -695,6 +699,29 @@ int32_t pkb_detokenize(PkbEngine* e, const int32_t* ids, int32_t n, char* out, i
   PKB_ENTER(e);
   return guarded([&] { return copy_text(e->eng->detokenize(std::vector<int>(ids, ids + n)), out, cap); });
 }
+int32_t pkb_token_is_punct_only(PkbEngine* e, int32_t id) {
+  PKB_ENTER(e);
+  return e->eng->vocab().is_punct_only(id) ? 1 : 0;
+}
+// ---- the token table on its own (no GPU): what cpp/src/tokenizer.cpp gives the reference's callers
+PkbVocab* pkb_vocab_open(const char* vocab_path) {
+  if (!vocab_path) { g_last_error = "null path"; return nullptr; }
+  try {
+    PkbVocab* v = new PkbVocab();
+    v->v = pkb::Vocab(vocab_path);
+    return v;
+  } catch (const std::exception& ex) {
+    g_last_error = ex.what();
+    return nullptr;
+  }
+}
+void pkb_vocab_close(PkbVocab* v) { delete v; }
+int32_t pkb_vocab_size(const PkbVocab* v) { return v ? v->v.size() : -1; }
+int32_t pkb_vocab_decode(const PkbVocab* v, const int32_t* ids, int32_t n, char* out, int32_t cap) {
+  if (!v || (!ids && n > 0) || n < 0) { g_last_error = "null argument"; return -1; }
+  return copy_text(v->v.decode(ids, (size_t)n), out, cap);
+}
+int32_t pkb_vocab_is_punct_only(const PkbVocab* v, int32_t id) { return v && v->v.is_punct_only(id) ? 1 : 0; }
 int32_t pkb_stream_import_state(PkbEngine* e, int32_t s, const float* cc, const float* ct, int32_t len) {
   PKB_ENTER(e);
   if (!cc || !ct) { g_last_error = "null argument"; return -1; }

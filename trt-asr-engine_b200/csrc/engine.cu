@@ -164,27 +164,6 @@ __global__ void guard_scan_kernel(const void* __restrict__ base, int is_bf16, Gu
   }
 }
 
-bool is_special_piece(const std::string& s) {
-  if (s == "<blank>" || s == "<pad>" || s == "<unk>") return true;
-  return !s.empty() && s.front() == '<' && s.back() == '>';
-}
-bool starts_with_sp_marker(const std::string& s) {
-  return s.size() >= 3 && (unsigned char)s[0] == 0xE2 && (unsigned char)s[1] == 0x96 && (unsigned char)s[2] == 0x81;
-}
-// punctuation-only piece (semantics of /root/reference/cpp/src/tokenizer.cpp:59-84)
-bool piece_is_punct_only(const std::string& s) {
-  if (is_special_piece(s)) return false;
-  size_t i = starts_with_sp_marker(s) ? 3 : 0;
-  if (i >= s.size()) return false;
-  bool non_space = false;
-  for (; i < s.size(); ++i) {
-    const unsigned char c = (unsigned char)s[i];
-    if (isalnum(c)) return false;
-    if (!isspace(c)) non_space = true;
-  }
-  return non_space;
-}
-
 }  // namespace
 
 // ================================================================================================
@@ -329,23 +308,11 @@ Engine::Engine(const EngineOptions& opt) : opt_(opt) {
     ScopeGuard(std::vector<void*>* d, std::vector<void*>* h) { g_dev_scope = d; g_host_scope = h; }
     ~ScopeGuard() { g_dev_scope = nullptr; g_host_scope = nullptr; }
   } scope(&im_->dev_allocs, &im_->host_allocs);
-  // vocab
-  {
-    std::ifstream f(opt_.model_dir + "/vocab.txt");
-    PKB_CHECK((bool)f, "cannot open " + opt_.model_dir + "/vocab.txt");
-    std::string line;
-    while (std::getline(f, line)) {
-      if (!line.empty() && line.back() == '\r') line.pop_back();
-      vocab_.push_back(line);
-    }
-    PKB_CHECK(!vocab_.empty() && (int)vocab_.size() <= kVocab, "vocab.txt must have 1..8193 lines");
-    punct_bits_.assign((kVocab + 31) / 32, 0u);
-    for (size_t i = 0; i < vocab_.size(); ++i) {
-      if (vocab_[i] == "<|startoftranscript|>") tok_start_ = (int)i;
-      if (vocab_[i] == "<|en|>") tok_lang_ = (int)i;
-      if (piece_is_punct_only(vocab_[i])) punct_bits_[i >> 5] |= 1u << (i & 31);
-    }
-  }
+  vocab_ = Vocab(opt_.model_dir + "/vocab.txt");
+  PKB_CHECK(vocab_.size() <= kVocab, "vocab.txt must have 1..8193 lines");
+  tok_start_ = vocab_.find("<|startoftranscript|>");
+  tok_lang_ = vocab_.find("<|en|>");
+  punct_bits_ = vocab_.punct_bitmap(kVocab);
   load_weights();
   alloc_state();
   streams_.resize(opt_.max_streams);
@@ -848,24 +815,7 @@ int Engine::stable_prefix(int sid, int revision_window_ms) const {
 int Engine::cache_len(int sid) const { return streams_[sid]->cache_len; }
 long long Engine::chunks_done(int sid) const { return streams_[sid]->chunks; }
 
-std::string Engine::detokenize(const std::vector<int>& ids) const {
-  // SentencePiece-style join (semantics of /root/reference/cpp/src/tokenizer.cpp:32-57)
-  std::string out;
-  for (int id : ids) {
-    if (id < 0 || id >= (int)vocab_.size()) continue;
-    const std::string& t = vocab_[id];
-    if (is_special_piece(t)) continue;
-    if (starts_with_sp_marker(t)) {
-      if (!out.empty() && out.back() != ' ') out.push_back(' ');
-      out.append(t, 3, std::string::npos);
-    } else {
-      out.append(t);
-    }
-  }
-  size_t i = 0;
-  while (i < out.size() && out[i] == ' ') ++i;
-  return out.substr(i);
-}
+std::string Engine::detokenize(const std::vector<int>& ids) const { return vocab_.decode(ids); }
 
 // ------------------------------------------------------------------------------------------------ NaN / Inf guard
 // The reference samples the first 4096 elements of encoder_output and of the two cache outputs after every guarded encoder step

@@ -14,6 +14,7 @@
 #include "enc_kernels.cuh"
 #include "frontend.h"
 #include "gemm.h"
+#include "vocab.h"
 #include "weights_file.h"
 
 namespace pkb {
@@ -128,7 +129,7 @@ class Engine {
 
   const EngineOptions& options() const { return opt_; }
   int n_layers() const { return L_; }
-  const std::vector<std::string>& vocab() const { return vocab_; }
+  const Vocab& vocab() const { return vocab_; }
   std::string detokenize(const std::vector<int>& ids) const;
   long long kernel_launches() const { return launches_; }
   int sm_count() const { return sm_count_; }
@@ -173,8 +174,8 @@ class Engine {
   cudaStream_t st_ = nullptr;
   std::unique_ptr<Impl> im_;
   std::vector<std::unique_ptr<Stream>> streams_;
-  std::vector<std::string> vocab_;
-  std::vector<unsigned> punct_bits_;
+  Vocab vocab_;
+  std::vector<uint32_t> punct_bits_;
   int tok_start_ = -1, tok_lang_ = -1;
   long long launches_ = 0;
 };
