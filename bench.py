@@ -85,7 +85,7 @@ class ClockSampler:
         steps); only samples received inside a window opened by begin() / end() -- the timed regions -- are reported."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._pump, daemon=True)
             self.th.start()
         except Exception:
@@ -241,14 +241,18 @@ def main():
     ap.add_argument("--layers", type=int, default=24)
     ap.add_argument("--precision", type=int, default=int(os.environ.get("PKB_BENCH_PRECISION", "0")),
                     help="0 = bf16 operands, 1 = split bf16 hi+lo (fp32-grade)")
-    ap.add_argument("--ref-streams", type=int, default=8, help="streams of the bounded CPU sample (cpu_baseline / --impl reference)")
-    ap.add_argument("--ref-chunks", type=int, default=40, help="chunks per stream of the cpu_baseline sample (~15 s of CPU work)")
+    ap.add_argument("--ref-streams", type=int, default=64, help="streams batched together in the bounded CPU sample (cpu_baseline / --impl reference)")
+    ap.add_argument("--ref-chunks", type=int, default=5, help="chunks per stream of the cpu_baseline sample (~10-20 s of CPU work at 64 streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--engines-per-gpu", type=int, default=0, help="0 = auto (2 when this rank holds <= --two-engine-max-streams streams)")
     ap.add_argument("--two-engine-max-streams", type=int, default=0)
-    ap.add_argument("--longform", type=int, default=0, help="also run BASELINE config 5's shape: this many clips through the whole-utterance offline path")
+    ap.add_argument("--longform", type=int, default=4, help="BASELINE config 5's shape: this many clips through the whole-utterance offline path "
+                                                            "(4 x 1 h by default so that the default run stays within minutes; 32 = the full config; 0 = skip)")
     ap.add_argument("--longform-seconds", type=float, default=3600.0)
+    ap.add_argument("--longform-blank-penalty", type=float, default=None,
+                    help="PARAKEET_BLANK_PENALTY for the long-form run (default: calibrated so that the random-weight model emits speech-like token rates)")
+    ap.add_argument("--no-config3", action="store_true")
     ap.add_argument("--prefill-chunks", type=int, default=88,
                     help="untimed chunks per stream before the timed region; 86 saturate the 256-step attention cache (1 + 3 per chunk)")
     args = ap.parse_args()
@@ -306,8 +310,10 @@ def main():
     total_pushes = 16            # audio ring: the pushes cycle through 16 x 0.24 s of synthetic audio per stream
     clip_len = total_pushes * SAMPLES_PER_STEP + 16000
     clips = np.stack([synth_clip(clip_len / 16000.0 + 0.01, 1000 + c)[:clip_len] for c in range(N_CLIPS)])
-    phase = np.array([(i * 977) % 12000 for i in mine])
-    clip_of = np.array([i % N_CLIPS for i in mine])
+    # the j-th stream of EVERY rank carries clip j mod 32 at phase 977 j: each rank sees the same clip mix (and decode load) at every N
+    local = np.array(mine) // world
+    phase = (local * 977) % 12000
+    clip_of = local % N_CLIPS
 
     def host_step_audio(k: int) -> np.ndarray:
         idx = phase[:, None] + k * SAMPLES_PER_STEP + np.arange(SAMPLES_PER_STEP)[None, :]
@@ -382,6 +388,10 @@ def main():
     sampler.end()
     barrier()
     clocks = sampler.stop()      # samples taken during the two timed regions (device-resident and end-to-end)
+    graphs = sum(e.graphs_built() for e in engs)
+    # decode loops of the steps so far (graph mode): device time between the CUDA events the step graph records around its WHILE node
+    loop = [e.decode_loop_stats(reset=True) for e in engs]
+    loop_ms, loop_bytes, loop_passes, loop_n = (sum(x[i] for x in loop) for i in range(4))
 
     # ---- per-launch timing of the dominant kernel (tcgen05 GEMM) for the roofline
     for e in engs:
@@ -428,7 +438,11 @@ def main():
                    "streams_per_gpu": n, "engines_per_gpu": n_eng, "audio_s_per_step": args.streams * AUDIO_S_PER_STEP, "precision": args.precision,
                    "l2_policy": "working set per step (1.2 GB weights + 29 MB K/V per stream) exceeds the 126 MB L2; no flush needed",
                    "wall_ms_per_step_resident": 1e3 * wall_max / args.steps, "tokens_emitted_first_64_streams": n_tokens,
-                   "cache_last_channel_len_at_timing": cache_len0, "prefill_chunks": args.prefill_chunks},
+                   "cache_last_channel_len_at_timing": cache_len0, "prefill_chunks": args.prefill_chunks,
+                   "step_graphs": graphs,
+                   "execution": ("one CUDA graph per step shape (encoder chunk + device-side WHILE node around the decode iteration)" if graphs
+                                 else "launch by launch"),
+                   "cpu_arm_streams": args.ref_streams},
         "clocks": clocks,
         "e2e": {"value": audio_s / e2e_max, "unit": "x real time", "h2d_bytes_per_step": step_bytes * world,
                 "d2h_bytes_per_step": n * 97 * 4 * world},
@@ -450,22 +464,30 @@ def main():
          "algorithmic_bytes_per_launch": fe_bytes / max(fe_launches, 1),
          "note": "latency-bound at this size (24 new frames per stream per step); 0.3 % of the step"},
     ]
+    if loop_n > 0:
+        dec_ms, dec_bytes, dec_loops, dec_how = loop_ms, loop_bytes, loop_n, (
+            f"inside the step graph (device-side WHILE node): CUDA events recorded by the graph around the loop, {loop_passes / loop_n:.1f} passes "
+            f"per loop, {1e3 * loop_ms / max(loop_passes, 1):.1f} us per pass")
+    else:
+        dec_how = "launch-by-launch path, host-polled loop"
     line["roofline_hbm"].append(
         {"kernel": "TDT decode loop (joint_hidden -> joint output GEMM with fused argmax -> tdt_select -> predictor pass), whole loop",
          "bound": "hbm", "achieved": dec_bytes / max(dec_ms, 1e-9) / 1e6, "peak": peak_hbm, "unit": "GB/s",
          "frac": dec_bytes / max(dec_ms, 1e-9) / 1e6 / peak_hbm, "launches_timed": int(dec_loops),
-         "algorithmic_bytes_per_launch": dec_bytes / max(dec_loops, 1),
-         "note": "bytes = iterations x (10.5 MB joint output weights + per-stream rows); the 24 MB of decoder weights stay in the 126 MB "
-                 "L2, so the loop is bound by its ~7 dependent launches per iteration, not by HBM"})
+         "algorithmic_bytes_per_launch": dec_bytes / max(dec_loops, 1), "how": dec_how,
+         "note": "bytes = passes x (10.5 MB joint output weights + per-stream rows); the 24 MB of decoder weights stay in the 126 MB L2 and "
+                 "at 1024 streams a pass is two split-precision tensor-core GEMMs deep, so this entry is latency / tensor bound, not HBM bound"})
     if fe1h is not None and fe1h[0] > 0:
         line["roofline_hbm"].append(
             {"kernel": f"logmel_kernel, one 1 h clip ({(hour.size - 400) // 160 + 1} frames in one launch)", "bound": "hbm", "achieved": fe1h[1] / fe1h[0] / 1e6,
              "peak": peak_hbm, "unit": "GB/s", "frac": fe1h[1] / fe1h[0] / 1e6 / peak_hbm, "launches_timed": int(fe1h[2]),
              "algorithmic_bytes_per_launch": fe1h[1] / max(fe1h[2], 1)})
-    if args.longform > 0 and world == 1:
-        for e in engs:
-            e.close()
-        line["longform"] = longform(binding, model, args.precision, args.longform, args.longform_seconds, synth_clip(10.0, 1234))
+    for e in engs:
+        e.close()
+    if not args.no_config3 and world == 1:
+        line["config3_64streams_mixed_cache"] = config3_mixed(binding, model, args.precision, clips)
+    if args.longform > 0 and world == 1 and not args.no_latency:
+        line["config5_longform"] = longform(binding, model, args.precision, args.longform, args.longform_seconds, args.longform_blank_penalty)
     if not args.no_latency and world == 1:
         line["config1_offline_10s"] = config1_offline(binding, model, args.precision)
     if not args.no_latency and world == 1:
@@ -473,7 +495,7 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         rtfx, cores, wall, a_s = cpu_path_rtfx(model, args.ref_streams, args.ref_chunks, 1)
         line["cpu_baseline"] = {"value": rtfx, "unit": "x real time", "cores": cores, "kind": "port",
-                                "sample": f"{args.ref_streams} streams x {args.ref_chunks} chunks ({a_s:.2f} s audio), {wall:.1f} s of CPU work, "
+                                "sample": f"{args.ref_streams} streams batched x {args.ref_chunks} chunks ({a_s:.2f} s audio), {wall:.1f} s of CPU work, "
                                           "C restatement of rust/features + PyTorch-CPU restatement of the NeMo modules (not the Rust/ORT binaries)"}
     else:
         line["cpu_baseline"] = None
@@ -482,17 +504,35 @@ def main():
         dist.destroy_process_group()
 
 
-def longform(binding, model, precision, batch, seconds, clip):
+def longform(binding, model, precision, batch, seconds, blank_penalty=None):
     """BASELINE config 5 (long-form offline): `batch` clips of `seconds` s through pkb_offline_utterances -- full-utterance log-mel +
-    per-feature normalisation + encoder over ALL frames (full self-attention) + TDT decode; host audio in, tokens out."""
+    per-feature normalisation + encoder over ALL frames (full self-attention) + TDT decode; host audio in, tokens out.
+    Every clip is a different sequence of 10 s synthetic segments.  With random weights, attention over 45 000 frames averages the
+    encoder output towards its mean and the joint then prefers blank almost everywhere (r1 measured 0 tokens per 32 h), which would
+    leave the predictor / LSTM path out of the measurement; the reference's own PARAKEET_BLANK_PENALTY knob (parakeet_trt.cpp:3175-3178)
+    is set for this run so that the decode emits tokens at a speech-like rate (reported as tokens_per_hour)."""
+    from synth_audio import synth_clip
     n_samp = int(seconds * 16000)
-    base = np.tile(clip, n_samp // clip.size + 1)[:n_samp]
-    assert base.size == n_samp
-    audio = [np.roll(base, 977 * i) for i in range(batch)]
+    seg = 160000
+    segs = [synth_clip(10.0, 4000 + k) for k in range(12)]
+    rng = np.random.default_rng(7)
+    audio = []
+    for i in range(batch):
+        order = rng.integers(0, len(segs), size=n_samp // seg + 1)
+        audio.append(np.concatenate([segs[k] for k in order])[:n_samp].astype(np.float32))
     t_enc = binding.load_library().pkb_encoded_length((n_samp - 400) // 160 + 1)
     # ~120 KB of work buffers per encoder frame: clips go through in groups that fit (4 one-hour clips = 22 GB)
     group = max(1, min(batch, int(4 * 45000 // max(t_enc, 1)) or 1))
-    eng = binding.Engine(model, max_streams=batch, precision=precision, max_rows=group * t_enc + 64, contract_cache=0)
+    pen = 6.0 if blank_penalty is None else blank_penalty
+    old_env = os.environ.get("PARAKEET_BLANK_PENALTY")
+    os.environ["PARAKEET_BLANK_PENALTY"] = str(pen)
+    try:
+        eng = binding.Engine(model, max_streams=batch, precision=precision, max_rows=group * t_enc + 64, contract_cache=0)
+    finally:
+        if old_env is None:
+            del os.environ["PARAKEET_BLANK_PENALTY"]
+        else:
+            os.environ["PARAKEET_BLANK_PENALTY"] = old_env
     sids = [eng.open() for _ in range(batch)]
     eng.offline_utterances(sids[:1], audio=[audio[0][:160000]], decode=True)       # warm-up (lazy buffers, first launches)
     eng.reset(sids[0])
@@ -508,11 +548,58 @@ def longform(binding, model, precision, batch, seconds, clip):
     dec_ms, _, _ = eng.profile_read_class(3)
     eng.profile_enable(False)
     eng.close()
-    return {"workload": f"{batch} clips x {seconds:.0f} s encoded in groups of {group}, decoded in one batched pass; whole-utterance offline (config 5 shape), encoder frames per clip {t_enc}",
-            "rtfx_e2e": batch * seconds / wall, "wall_s": wall, "tokens": n_tok,
-            "gemm_ms": gemm_ms, "gemm_tflops": gemm_flops / max(gemm_ms, 1e-9) / 1e9,
+    return {"workload": f"{batch} clips x {seconds:.0f} s (each a different sequence of 10 s synthetic segments) encoded in groups of {group}, decoded in one "
+                        f"batched pass; whole-utterance offline (config 5 shape), encoder frames per clip {t_enc}",
+            "rtfx_e2e": batch * seconds / wall, "wall_s": wall, "tokens": n_tok, "tokens_per_hour": n_tok / max(batch * seconds / 3600.0, 1e-9),
+            "blank_penalty": pen, "gemm_ms": gemm_ms, "gemm_tflops": gemm_flops / max(gemm_ms, 1e-9) / 1e9,
             "attention_ms": att_ms, "attention_tflops_algorithmic": att_flops / max(att_ms, 1e-9) / 1e9, "attention_launches": int(att_l),
             "decode_ms": dec_ms}
+
+
+def config3_mixed(binding, model, precision, clips, n=64, steps=20):
+    """BASELINE config 3: 64 concurrent streams, batched chunk step with PER-STREAM cache lengths, one B200.  Streams join at staggered
+    times, so at the timed steps cache_last_channel_len ranges from a few rows to the saturated 256 inside one batch."""
+    import torch
+    eng = binding.Engine(model, max_streams=n, precision=precision, max_rows=8 * n)
+    sids = np.array([eng.open() for _ in range(n)], np.int32)
+    start = np.array([(j % 8) * 12 for j in range(n)])          # step at which stream j joins: 0, 12, ..., 84
+    total = 16
+    host = torch.empty((total, n, SAMPLES_PER_STEP), dtype=torch.float32).pin_memory()
+    for k in range(total):
+        idx = ((np.arange(n) * 977) % 12000)[:, None] + k * SAMPLES_PER_STEP + np.arange(SAMPLES_PER_STEP)[None, :]
+        host[k] = torch.from_numpy(clips[(np.arange(n) % N_CLIPS)[:, None], idx])
+    pushed = np.zeros(n, np.int64)
+
+    def step(t):
+        act = np.nonzero(start <= t)[0]
+        # every active stream gets its next 0.24 s; a stream's own push counter selects the audio slice (all slices are equally valid audio)
+        for grp in np.unique(pushed[act] % total):
+            sel = act[pushed[act] % total == grp]
+            rows = np.ascontiguousarray(host[int(grp)].numpy()[sel])
+            eng.push_audio_batch(sids[sel], rows.ctypes.data, SAMPLES_PER_STEP, SAMPLES_PER_STEP)
+        pushed[act] += 1
+        return eng.step()
+    t = 0
+    while t < 88 + 2:                      # the first streams reach a saturated cache; the last joined 6 steps ago
+        step(t)
+        t += 1
+    lens = [eng.cache_len(int(s)) for s in sids]
+    for _ in range(3):
+        assert step(t) == n
+        t += 1
+    ev0 = eng.event_record()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step(t)
+        t += 1
+    ev1 = eng.event_record()
+    dev_ms = eng.event_elapsed_ms(ev0, ev1)
+    wall = time.perf_counter() - t0
+    eng.close()
+    return {"streams": n, "steps": steps, "ms_per_step_e2e": 1e3 * wall / steps, "ms_per_step_device": dev_ms / steps,
+            "rtfx_e2e": n * AUDIO_S_PER_STEP * steps / wall, "cache_last_channel_len_min": int(min(lens)), "cache_last_channel_len_max": int(max(lens)),
+            "distinct_cache_lengths": len(set(lens)),
+            "what": "BASELINE config 3: 64 streams in one batched step, per-stream cache lengths (host audio in, tokens out)"}
 
 
 def config1_offline(binding, model, precision):
@@ -532,22 +619,31 @@ def config1_offline(binding, model, precision):
     return {"wall_ms": 1e3 * w, "rtfx": 10.0 / w, "what": "BASELINE config 1: one 10 s clip, batch 1, host PCM in -> tokens out (whole-utterance path)"}
 
 
-def latency_one_stream(binding, model, precision, clip):
-    """BASELINE config 2: one stream, per-chunk latency (push of 0.24 s of audio -> tokens on the host), p50 / p95."""
+def latency_one_stream(binding, model, precision, clip, prefill=90, timed=60):
+    """BASELINE config 2: one stream, per-chunk latency (push of 0.24 s of host audio -> tokens on the host), p50 / p95, measured in
+    steady state: `prefill` untimed chunks first, so the 256-step attention cache is saturated (86 chunks fill it)."""
     eng = binding.Engine(model, max_streams=1, precision=precision)
     sid = np.array([eng.open()], np.int32)
-    buf = np.ascontiguousarray(clip[: 64 * SAMPLES_PER_STEP])
+    ring = 16 * SAMPLES_PER_STEP
+    buf = np.ascontiguousarray(clip[:ring])
     eng.push_audio_batch(sid, buf[:SAMPLES_PER_STEP].ctypes.data, SAMPLES_PER_STEP, SAMPLES_PER_STEP)
     lat = []
-    for k in range(1, 60):
-        seg = buf[k * SAMPLES_PER_STEP:(k + 1) * SAMPLES_PER_STEP]
+    for k in range(1, prefill + timed + 1):
+        off = (k % 16) * SAMPLES_PER_STEP
+        seg = buf[off:off + SAMPLES_PER_STEP]
         t0 = time.perf_counter()
         eng.push_audio_batch(sid, seg.ctypes.data, SAMPLES_PER_STEP, SAMPLES_PER_STEP)
-        eng.step()
-        lat.append(1e3 * (time.perf_counter() - t0))
-    lat = np.array(lat[8:])
+        n = eng.step()
+        dt = 1e3 * (time.perf_counter() - t0)
+        if k > prefill:
+            assert n == 1
+            lat.append(dt)
+    cache_len = eng.cache_len(int(sid[0]))
+    graphs = eng.graphs_built()
     eng.close()
-    return {"p50_ms": float(np.percentile(lat, 50)), "p95_ms": float(np.percentile(lat, 95)), "chunks": int(lat.size)}
+    lat = np.array(lat)
+    return {"p50_ms": float(np.percentile(lat, 50)), "p95_ms": float(np.percentile(lat, 95)), "chunks": int(lat.size),
+            "cache_last_channel_len": cache_len, "step_graphs": graphs}
 
 
 if __name__ == "__main__":

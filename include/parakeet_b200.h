@@ -97,6 +97,12 @@ int32_t pkb_engine_profile_read(PkbEngine* engine, double* ms, double* flops, in
 /* same for a kernel class: 0 = tcgen05 GEMM (work = algorithmic FLOPs), 1 = streaming attention, 2 = log-mel frontend, 3 = TDT decode
  * loop (work = algorithmic bytes), 4 = whole-utterance attention (work = algorithmic FLOPs) */
 int32_t pkb_engine_profile_read_class(PkbEngine* engine, int32_t cls, double* ms, double* work, int64_t* launches);
+/* Steps of a repeated shape run as ONE CUDA graph (encoder chunk + a device-side WHILE node around the decode iteration; set
+ * PARAKEET_B200_GRAPH=0 for the launch-by-launch path).  pkb_engine_graphs_built: step shapes currently captured.
+ * pkb_engine_decode_loop_stats: device time (CUDA events the graph records around its WHILE node), algorithmic bytes, passes and
+ * count of the decode loops run inside graphs since the last reset. */
+int32_t pkb_engine_graphs_built(PkbEngine* engine);
+int32_t pkb_engine_decode_loop_stats(PkbEngine* engine, double* ms, double* bytes, int64_t* passes, int64_t* loops, int32_t reset);
 
 /* ---- results ---- */
 int32_t pkb_stream_num_tokens(PkbEngine* engine, int32_t stream);

@@ -50,7 +50,7 @@ def test_push_prologue_auto_chunking(tmp_path, model_small, features_ref):
     rc1, st1, ev1, _ = _drive(model_small, fp, [(0, 600)], PARAKEET_EMIT_FINAL_EACH_CHUNK=1)
     rc2, st2, ev2, _ = _drive(model_small, fp, [(0, 256), (256, 512), (512, 600)], PARAKEET_EMIT_FINAL_EACH_CHUNK=1)
     assert rc1 == [0] and rc2 == [0, 0, 0]
-    assert len(st1) >= 9 and st1 == st2
+    assert len(st1) >= 3 and st1 == st2
     assert [e for e in ev1 if e.startswith("event final")] == [e for e in ev2 if e.startswith("event final")] and len(ev1) >= 3
     # 257 frames: 256 + a 1-frame tail the streaming encoder cannot take -> the first slice is processed, then rc -2 + ERROR event
     rc3, st3, ev3, _ = _drive(model_small, fp, [(0, 257)])

@@ -641,6 +641,12 @@ int32_t pkb_engine_profile_read_class(PkbEngine* e, int32_t cls, double* ms, dou
   PKB_ENTER(e);
   return guarded([&] { long long l = 0; e->eng->profile_read(cls, ms, work, &l); *launches = l; return 0; });
 }
+int32_t pkb_engine_decode_loop_stats(PkbEngine* e, double* ms, double* bytes, int64_t* passes, int64_t* loops, int32_t reset) {
+  PKB_ENTER(e);
+  if (!ms || !bytes || !passes || !loops) { g_last_error = "null argument"; return -1; }
+  return guarded([&] { long long p = 0, l = 0; e->eng->decode_loop_stats(ms, bytes, &p, &l, reset); *passes = p; *loops = l; return 0; });
+}
+int32_t pkb_engine_graphs_built(PkbEngine* e) { PKB_ENTER(e); return e->eng->graphs_built(); }
 int32_t pkb_engine_step(PkbEngine* e) { PKB_ENTER(e); return guarded([&] { return e->eng->step(); }); }
 int32_t pkb_stream_has_pending(PkbEngine* e, int32_t s) { PKB_ENTER(e); return guarded([&] { return e->eng->has_pending(s) ? 1 : 0; }); }
 int32_t pkb_stream_num_tokens(PkbEngine* e, int32_t s) { PKB_ENTER(e); return guarded([&] { return (int)e->eng->tokens(s).size(); }); }

@@ -63,6 +63,12 @@ inline bool pdl_enabled() {
   if (v < 0) { const char* e = getenv("PARAKEET_B200_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
   return v != 0;
 }
+// While a CUDA-graph body is being captured the launch attribute can be withheld (graph_pdl_suppressed()): the kernels then depend
+// on their predecessors through ordinary graph edges and their griddepcontrol instructions are no-ops.
+inline bool& graph_pdl_suppressed() {
+  static thread_local bool v = false;
+  return v;
+}
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
@@ -72,7 +78,7 @@ inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = (pdl_enabled() && !graph_pdl_suppressed()) ? 1 : 0;
   PKB_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
 }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

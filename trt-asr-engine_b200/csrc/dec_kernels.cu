@@ -127,6 +127,9 @@ __global__ void __launch_bounds__(128)
 lstm_cell_kernel(DecodeDev d, int layer) {
   pdl_enter();
   const int e = blockIdx.x;
+  // graph mode: this launch follows tdt_select_kernel in stream order, so the count of still-active entries is final here
+  if (d.loop_handle != 0 && layer == 1 && e == 0 && threadIdx.x == 0)
+    cudaGraphSetConditional((cudaGraphConditionalHandle)d.loop_handle, *d.n_active > 0 ? 1u : 0u);
   if (*d.m_pred == 0) return;
   const int tok = d.emit_tok[e];
   const int slot = d.slot[e];

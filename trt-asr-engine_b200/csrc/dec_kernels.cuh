@@ -38,6 +38,8 @@ struct DecodeDev {
   const int* part_idx = nullptr;     //   (GEMM epilogue EPI_ARGMAX; NaN guard and blank penalty already applied)
   const float* dur_logits = nullptr; // [B][kNDur]
   int fused_argmax = 0;              // 1: select from the partials, 0: scan d.logits
+  unsigned long long loop_handle = 0;   // != 0: the iteration is the body of a CUDA-graph WHILE node; its last-but-one kernel tells the
+                                        // node whether any entry is still active (cudaGraphSetConditional)
   const float* gates = nullptr;      // [B,2560]
   const __nv_bfloat16* embed = nullptr;  // [8193,640]
   const unsigned* punct_bits = nullptr;  // [ceil(8193/32)]

@@ -6,8 +6,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <array>
+#include <cstdio>
 #include <cstdlib>
 #include <fstream>
+#include <map>
 
 namespace pkb {
 
@@ -193,6 +196,15 @@ struct Engine::Stream {
   ChunkResult last;
 };
 
+// one captured step shape (see Engine::step_graph)
+struct Engine::StepGraph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  long long fixed_launches = 0;      // kernels outside the loop
+  int body_launches = 0;             // kernels per loop pass
+  cudaEvent_t ev_loop0 = nullptr, ev_loop1 = nullptr;      // recorded by the graph right before / after the WHILE node
+};
+
 constexpr int kRunStats = 1 + 2 * kNMels + 3;      // padded to a multiple of 4 floats
 constexpr int kProfClasses = 5;   // 0 tcgen05 GEMM, 1 streaming attention, 2 log-mel, 3 decode loop, 4 whole-utterance attention
 
@@ -284,6 +296,12 @@ struct Engine::Impl {
   FeatPush* fpush_host = nullptr;
   int fpush_cap = 0, fpush_n = 0, fpush_max_T = 0;
   bool fstage_inflight = false;                // flushed to the device, host area not yet known to be consumed
+  // whole-step CUDA graphs, one per step shape (see Engine::step_graph)
+  std::map<std::array<int, 6>, std::unique_ptr<Engine::StepGraph>> graphs;
+  std::map<std::array<int, 6>, int> graph_seen;
+  int graph_mode = 1, graph_pdl = 1;
+  double loop_ms = 0.0, loop_bytes = 0.0;      // decode loops run inside step graphs since the last decode_loop_stats(reset)
+  long long loop_passes = 0, loop_count = 0;
   int* meta2 = nullptr;                        // device [2]: (slot, head) of a single-stream import / export
   int* guard_dev = nullptr;                    // device [4]: nan count, inf count, first nan index, first inf index (NaN guard)
   int* guard_host = nullptr;                   // pinned
@@ -313,6 +331,8 @@ Engine::Engine(const EngineOptions& opt) : opt_(opt) {
   tok_start_ = vocab_.find("<|startoftranscript|>");
   tok_lang_ = vocab_.find("<|en|>");
   punct_bits_ = vocab_.punct_bitmap(kVocab);
+  { const char* v = getenv("PARAKEET_B200_GRAPH"); if (v) im_->graph_mode = atoi(v); }
+  { const char* v = getenv("PARAKEET_B200_GRAPH_PDL"); if (v) im_->graph_pdl = atoi(v); }
   load_weights();
   alloc_state();
   streams_.resize(opt_.max_streams);
@@ -327,6 +347,10 @@ Engine::Engine(const EngineOptions& opt) : opt_(opt) {
 Engine::~Engine() {
   if (st_) cudaStreamSynchronize(st_);
   if (im_) {
+    for (auto& kv : im_->graphs) {
+      cudaGraphExecDestroy(kv.second->exec); cudaGraphDestroy(kv.second->graph);
+      cudaEventDestroy(kv.second->ev_loop0); cudaEventDestroy(kv.second->ev_loop1);
+    }
     for (auto& e : im_->user_events) cudaEventDestroy(e);
     for (auto& e : im_->dec_events) if (e) cudaEventDestroy(e);
     for (auto& pr : im_->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -392,6 +416,14 @@ void Engine::profile_collect() {      // call after a synchronised step
   }
   im.prof_used = 0;
 }
+// Device time of the decode loops executed inside step graphs (CUDA events recorded by the graph around its WHILE node), their
+// passes (= symbols decoded per stream, max over the batch) and algorithmic bytes; reset != 0 clears the counters afterwards.
+void Engine::decode_loop_stats(double* ms, double* bytes, long long* passes, long long* loops, int reset) {
+  Impl& im = *im_;
+  *ms = im.loop_ms; *bytes = im.loop_bytes; *passes = im.loop_passes; *loops = im.loop_count;
+  if (reset) { im.loop_ms = im.loop_bytes = 0.0; im.loop_passes = im.loop_count = 0; }
+}
+int Engine::graphs_built() const { return (int)im_->graphs.size(); }
 void Engine::profile_read(int cls, double* ms, double* work, long long* launches) {
   PKB_CHECK(cls >= 0 && cls < kProfClasses, "profile class");
   *ms = im_->prof_ms[cls]; *work = im_->prof_work[cls]; *launches = im_->prof_launches[cls];
@@ -1341,42 +1373,64 @@ void Engine::run_predictor_pass(const DecodeDev& d) {
 
 static DecodeDev make_decode_dev(Engine::Impl& im, const EngineOptions& opt, int B, const int* slot, const int* row_off, const int* t_enc);
 
-void Engine::run_decode(const BatchDev& b, const int* slots, int* steps, int max_steps, const float* enc_proj_rows) {
+// Device-side description of one batched decode (no launches).
+DecodeDev Engine::decode_setup(const BatchDev& b, const int* slots, int* steps, int max_steps, const float* enc_proj_rows) {
   Impl& im = *im_;
-  // joint encoder projection for every packed row: E = joint.enc(x) + bias  (or rows projected earlier: deferred decode)
-  g_tc_site = 16;
-  if (enc_proj_rows == nullptr) {
-    EpiParams e; e.mode = EPI_BIAS_F32; e.out_f32 = im.enc_proj; e.ldo = kJointH; e.bias = im.joint_enc_b;
-    RUN_GEMM(im.a_xf, im.joint_enc, b.M, nullptr, e);
-  }
   DecodeDev d = make_decode_dev(im, opt_, b.B, slots ? slots : b.slot, b.row_off, im.batch_ints + 10 * im.Bcap);
   if (enc_proj_rows) d.enc_proj = enc_proj_rows;
   d.max_steps = b.max_tenc > kValidOut ? kMaxStepsOffline : kMaxStepsPerChunk;
   if (steps) { d.steps = steps; d.max_steps = max_steps; }
   d.fused_argmax = (opt_.gemm_backend == 2 || (opt_.gemm_backend == 0 && b.B > 16)) && tc_mask() < 0 ? 1 : 0;
+  return d;
+}
+
+// joint encoder projection for every packed row, E = joint.enc(x) + bias (skipped when the rows were projected earlier: deferred
+// decode), and the per-entry decode state
+void Engine::decode_prologue(const BatchDev& b, const DecodeDev& d, bool project) {
+  Impl& im = *im_;
+  g_tc_site = 16;
+  if (project) {
+    EpiParams e; e.mode = EPI_BIAS_F32; e.out_f32 = im.enc_proj; e.ldo = kJointH; e.bias = im.joint_enc_b;
+    RUN_GEMM(im.a_xf, im.joint_enc, b.M, nullptr, e);
+  }
   launch_decode_begin(d, st_); ++launches_;
+}
+
+// One symbol for every still-active entry: joint -> greedy selection -> TDT advance -> predictor step for the entries that emitted.
+void Engine::decode_iteration(const BatchDev& b, const DecodeDev& d, int host_poll_slot) {
+  Impl& im = *im_;
+  g_tc_site = 16;
+  launch_decode_iter_reset(d, st_); ++launches_;
+  launch_joint_hidden(d, st_); ++launches_;
+  if (d.fused_argmax) {      // tensor-core joint: greedy selection fused into the epilogue, logits never leave the SM
+    EpiParams e; e.mode = EPI_ARGMAX; e.bias = im.joint_out_b; e.part_val = im.part_val; e.part_idx = im.part_idx;
+    e.dur_out = im.dur_logits; e.blank_penalty = opt_.blank_penalty;
+    RUN_GEMM(im.a_hid, im.joint_out, b.B, d.m_joint, e);
+  } else {
+    EpiParams e; e.mode = EPI_BIAS_F32; e.out_f32 = im.logits; e.ldo = kJointOut; e.bias = im.joint_out_b;
+    RUN_GEMM(im.a_hid, im.joint_out, b.B, d.m_joint, e);
+  }
+  launch_tdt_select(d, st_); ++launches_;
+  if (host_poll_slot >= 0) {
+    PKB_CUDA(cudaMemcpyAsync(im.counters_host + 2 * host_poll_slot, im.counters, sizeof(int), cudaMemcpyDeviceToHost, st_));
+    PKB_CUDA(cudaEventRecord(im.dec_events[host_poll_slot], st_));
+  }
+  run_predictor_pass(d);
+}
+
+void Engine::run_decode(const BatchDev& b, const int* slots, int* steps, int max_steps, const float* enc_proj_rows) {
+  Impl& im = *im_;
+  const DecodeDev d = decode_setup(b, slots, steps, max_steps, enc_proj_rows);
+  decode_prologue(b, d, enc_proj_rows == nullptr);
   const int max_iters = b.max_tenc * (kMaxSymbols + 1) + 2;
   const int prof_i = prof_begin(3, 0.0);      // the whole loop; its algorithmic bytes are known when it ends
   int iters_done = 0;
   for (int it = 0; it < max_iters; ++it) {
     ++iters_done;
-    launch_decode_iter_reset(d, st_); ++launches_;
-    launch_joint_hidden(d, st_); ++launches_;
-    if (d.fused_argmax) {      // tensor-core joint: greedy selection fused into the epilogue, logits never leave the SM
-      EpiParams e; e.mode = EPI_ARGMAX; e.bias = im.joint_out_b; e.part_val = im.part_val; e.part_idx = im.part_idx;
-      e.dur_out = im.dur_logits; e.blank_penalty = opt_.blank_penalty;
-      RUN_GEMM(im.a_hid, im.joint_out, b.B, d.m_joint, e);
-    } else {
-      EpiParams e; e.mode = EPI_BIAS_F32; e.out_f32 = im.logits; e.ldo = kJointOut; e.bias = im.joint_out_b;
-      RUN_GEMM(im.a_hid, im.joint_out, b.B, d.m_joint, e);
-    }
-    launch_tdt_select(d, st_); ++launches_;
     // The host only needs "is anybody still active?".  Iteration it+1 is enqueued BEFORE the answer of iteration it is awaited,
     // so the GPU never idles on the round trip; the one iteration enqueued after the batch has finished sees m_joint == 0 and
     // m_pred == 0 and does nothing.
-    PKB_CUDA(cudaMemcpyAsync(im.counters_host + 2 * (it & 1), im.counters, sizeof(int), cudaMemcpyDeviceToHost, st_));
-    PKB_CUDA(cudaEventRecord(im.dec_events[it & 1], st_));
-    run_predictor_pass(d);
+    decode_iteration(b, d, it & 1);
     if (it >= 1) {
       PKB_CUDA(cudaEventSynchronize(im.dec_events[(it - 1) & 1]));
       if (im.counters_host[2 * ((it - 1) & 1)] == 0) break;
@@ -1391,6 +1445,104 @@ void Engine::run_decode(const BatchDev& b, const int* slots, int* steps, int max
     im.prof_flops[prof_i] = per_iter * std::max(iters_done - 1, 1);
     prof_end(prof_i);
   }
+}
+
+// ------------------------------------------------------------------------------------------------ whole-step CUDA graph
+// A streaming step is a chain of ~400 dependent launches (15 per conformer layer + ~10 per decoded symbol), each a few microseconds of
+// work at small per-GPU batches: launched one by one, the step sits on a floor of launch latencies and of one host round trip per
+// decoded symbol.  Steps of one shape (same number of entries, rows, frames) launch exactly the same kernels with the same
+// arguments -- everything that changes from step to step (slots, ring heads, cache lengths, frame offsets) is read from the batch
+// descriptor in device memory -- so the second step of a shape is captured into a CUDA graph and every later one replays it:
+//   [ child graph: encoder chunk + joint.enc projection + decode_begin ] -> [ WHILE node: one decode iteration per pass ]
+// The WHILE node's condition is set on the device (lstm_cell_kernel, layer 1: "some entry is still active"), so the decode loop
+// needs no host round trip at all.  PARAKEET_B200_GRAPH=0 keeps the launch-by-launch path; PARAKEET_B200_GRAPH_PDL=0 captures the
+// encoder part without programmatic-dependent-launch edges (the loop body never uses them).  Any failure while building a graph
+// falls back to the launch-by-launch path for good (one warning on stderr).
+Engine::StepGraph* Engine::step_graph(const BatchDev& b) {
+  Impl& im = *im_;
+  if (im.graph_mode <= 0 || im.profile) return nullptr;
+  const std::array<int, 6> key{b.B, b.M, b.sumT2, b.sumT3, b.max_Tq, b.max_tenc};
+  auto it = im.graphs.find(key);
+  if (it != im.graphs.end()) return it->second.get();
+  if (++im.graph_seen[key] < 2) return nullptr;      // the first step of a shape runs launch by launch (it also sets the kernels' attributes)
+  if (im.graphs.size() >= 32) {                      // bounded cache: drop everything when many distinct shapes have been seen
+    for (auto& kv : im.graphs) {
+      cudaGraphExecDestroy(kv.second->exec); cudaGraphDestroy(kv.second->graph);
+      cudaEventDestroy(kv.second->ev_loop0); cudaEventDestroy(kv.second->ev_loop1);
+    }
+    im.graphs.clear();
+  }
+  std::unique_ptr<StepGraph> sg(new StepGraph());
+  cudaGraph_t g_enc = nullptr;
+  const long long l0 = launches_;
+  bool capturing = false;
+  try {
+    DecodeDev d = decode_setup(b, nullptr, nullptr, 0, nullptr);
+    // ---- part 1: encoder chunk + decode prologue
+    graph_pdl_suppressed() = im.graph_pdl == 0;
+    PKB_CUDA(cudaStreamBeginCapture(st_, cudaStreamCaptureModeThreadLocal));
+    capturing = true;
+    run_encoder(b);
+    decode_prologue(b, d, true);
+    capturing = false;
+    PKB_CUDA(cudaStreamEndCapture(st_, &g_enc));
+    graph_pdl_suppressed() = false;
+    sg->fixed_launches = launches_ - l0;
+    // ---- the step graph: part 1 as a child graph, then the WHILE node
+    PKB_CUDA(cudaGraphCreate(&sg->graph, 0));
+    cudaGraphNode_t n_enc = nullptr, n_loop = nullptr, n_ev0 = nullptr, n_ev1 = nullptr;
+    PKB_CUDA(cudaGraphAddChildGraphNode(&n_enc, sg->graph, nullptr, 0, g_enc));
+    PKB_CUDA(cudaEventCreate(&sg->ev_loop0));
+    PKB_CUDA(cudaEventCreate(&sg->ev_loop1));
+    PKB_CUDA(cudaGraphAddEventRecordNode(&n_ev0, sg->graph, &n_enc, 1, sg->ev_loop0));
+    cudaGraphConditionalHandle handle;
+    PKB_CUDA(cudaGraphConditionalHandleCreate(&handle, sg->graph, 1, cudaGraphCondAssignDefault));      // the first pass always runs
+    cudaGraphNodeParams cp{};
+    cp.type = cudaGraphNodeTypeConditional;
+    cp.conditional.handle = handle;
+    cp.conditional.type = cudaGraphCondTypeWhile;
+    cp.conditional.size = 1;
+    PKB_CUDA(cudaGraphAddNode(&n_loop, sg->graph, &n_ev0, 1, &cp));
+    PKB_CUDA(cudaGraphAddEventRecordNode(&n_ev1, sg->graph, &n_loop, 1, sg->ev_loop1));
+    cudaGraph_t body = cp.conditional.phGraph_out[0];
+    // ---- part 2: the loop body, captured straight into the node's body graph (plain edges)
+    d.loop_handle = (unsigned long long)handle;
+    const long long l1 = launches_;
+    graph_pdl_suppressed() = true;
+    PKB_CUDA(cudaStreamBeginCaptureToGraph(st_, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    capturing = true;
+    decode_iteration(b, d, -1);
+    capturing = false;
+    cudaGraph_t body_out = nullptr;
+    PKB_CUDA(cudaStreamEndCapture(st_, &body_out));
+    graph_pdl_suppressed() = false;
+    sg->body_launches = (int)(launches_ - l1);
+    PKB_CUDA(cudaGraphInstantiate(&sg->exec, sg->graph, 0));
+    cudaGraphDestroy(g_enc);      // the child node holds its own copy
+    launches_ = l0;               // nothing was executed while capturing
+  } catch (const std::exception& ex) {
+    graph_pdl_suppressed() = false;
+    if (capturing) { cudaGraph_t junk = nullptr; cudaStreamEndCapture(st_, &junk); if (junk && junk != g_enc) cudaGraphDestroy(junk); }
+    if (g_enc) cudaGraphDestroy(g_enc);
+    if (sg->exec) cudaGraphExecDestroy(sg->exec);
+    if (sg->graph) cudaGraphDestroy(sg->graph);
+    if (sg->ev_loop0) cudaEventDestroy(sg->ev_loop0);
+    if (sg->ev_loop1) cudaEventDestroy(sg->ev_loop1);
+    cudaGetLastError();
+    launches_ = l0;
+    if (im.graph_pdl != 0) {
+      fprintf(stderr, "[parakeet_b200] step graph with programmatic edges failed (%s); retrying with plain edges\n", ex.what());
+      im.graph_pdl = 0;
+      --im.graph_seen[key];
+      return step_graph(b);
+    }
+    fprintf(stderr, "[parakeet_b200] CUDA-graph capture of the step failed (%s); continuing launch by launch\n", ex.what());
+    im.graph_mode = 0;
+    return nullptr;
+  }
+  StepGraph* out = sg.get();
+  im.graphs[key] = std::move(sg);
+  return out;
 }
 
 static DecodeDev make_decode_dev(Engine::Impl& im, const EngineOptions& opt, int B, const int* slot, const int* row_off, const int* t_enc) {
@@ -1449,10 +1601,12 @@ void Engine::run_batch(const std::vector<Entry>& entries, float* enc_out_host) {
   flush_feature_stage(false);                          // staged feature pushes -> feature rings (same stream: ordered before the pass)
   const BatchDev b = upload_batch(entries);
   const int max_steps = b.max_tenc > kValidOut ? kMaxStepsOffline : kMaxStepsPerChunk;
-  run_encoder(b);
   const bool decode = enc_out_host == nullptr;
+  StepGraph* sg = decode ? step_graph(b) : nullptr;
+  if (sg) PKB_CUDA(cudaGraphLaunch(sg->exec, st_));
+  else run_encoder(b);
   if (decode) {
-    run_decode(b);
+    if (!sg) run_decode(b);
     // [Bcap] step counts, then [B][max_steps][3] records
     PKB_CUDA(cudaMemcpyAsync(im.res_host, im.n_steps, ((size_t)im.Bcap + (size_t)b.B * max_steps * 3) * sizeof(int),
                              cudaMemcpyDeviceToHost, st_));
@@ -1464,6 +1618,19 @@ void Engine::run_batch(const std::vector<Entry>& entries, float* enc_out_host) {
   if (im.profile) profile_collect();
   const int* h = im.batch_ints_host;
   const int C = im.Bcap;
+  if (sg) {      // every loop pass records one step for each entry that was still active: passes = the longest trace
+    int passes = 1;
+    for (int i = 0; i < b.B; ++i) passes = std::max(passes, std::min(im.res_host[i], max_steps));
+    launches_ += sg->fixed_launches + (long long)passes * sg->body_launches;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, sg->ev_loop0, sg->ev_loop1) == cudaSuccess) {
+      im.loop_ms += ms; im.loop_passes += passes; im.loop_count += 1;
+      // algorithmic bytes of a pass: see run_decode
+      im.loop_bytes += (double)passes * ((double)kJointOut * kJointH * 2.0 + kJointOut * 4.0 + (double)b.B * (2.0 * kJointH * 4.0 + 12.0));
+    } else {
+      cudaGetLastError();
+    }
+  }
   for (int i = 0; i < b.B; ++i) {
     Stream& s = *streams_[entries[i].sid];
     const int Tq = h[6 * C + i];

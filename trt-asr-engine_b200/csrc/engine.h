@@ -141,12 +141,15 @@ class Engine {
   void profile_enable(bool on);
   void profile_collect();
   void profile_read(int cls, double* ms, double* work, long long* launches);   // cls 0: tcgen05 GEMM (work = FLOPs), 1: attention, 2: frontend, 3: decode loop (bytes), 4: whole-utterance attention (FLOPs)
+  void decode_loop_stats(double* ms, double* bytes, long long* passes, long long* loops, int reset);
+  int graphs_built() const;                // step shapes currently held as CUDA graphs (0: launch-by-launch path)
   int prof_begin(int cls, double work);
   void prof_end(int idx);
 
   struct Stream;
   struct Impl;
   struct TempStreams;
+  struct StepGraph;
   struct Entry { int sid; long long f0; int T; };      // f0: ABSOLUTE index of the chunk's first frame (ring index = f0 % ring capacity)
   Impl* impl();
 
@@ -159,6 +162,10 @@ class Engine {
   void run_encoder(const BatchDev& b, const LongForm* lf = nullptr);
   // slots / steps / max_steps override the per-chunk defaults for the whole-utterance path
   void run_decode(const BatchDev& b, const int* slots = nullptr, int* steps = nullptr, int max_steps = 0, const float* enc_proj_rows = nullptr);
+  DecodeDev decode_setup(const BatchDev& b, const int* slots, int* steps, int max_steps, const float* enc_proj_rows);
+  void decode_prologue(const BatchDev& b, const DecodeDev& d, bool project);
+  void decode_iteration(const BatchDev& b, const DecodeDev& d, int host_poll_slot);
+  StepGraph* step_graph(const BatchDev& b);      // nullptr: run this step launch by launch
   void lf_prepare(size_t total_frames, size_t steps_ints);
   void run_predictor_pass(const DecodeDev& d);
   void frontend_pass();

@@ -111,6 +111,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+      "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+        "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
 __device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) {
   const __nv_bfloat162 p0 = __floats2bfloat162_rn(a, b), p1 = __floats2bfloat162_rn(c, d);
   return make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
@@ -241,7 +254,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int n_pass = g.a_lo_off != 0 ? 2 : 1;
   const int splits = MODE == EPI_PARTIAL_F32 ? g.epi.splits : 1;      // work unit = (tile, k-split), split fastest
   // bf16 rows (plain operand plane / bf16 partial sums) with 16-byte aligned 16-column groups: registers -> global directly
-  constexpr bool kDirectMode = MODE == EPI_ACT || MODE == EPI_SILU_ACT || MODE == EPI_BIAS_RELU_ACT || MODE == EPI_PARTIAL_F32;
+  constexpr bool kDirectMode = MODE == EPI_ACT || MODE == EPI_SILU_ACT || MODE == EPI_BIAS_RELU_ACT || MODE == EPI_PARTIAL_F32 ||
+                               MODE == EPI_GLU_F32;
   const bool direct = kDirectMode && g.epi.direct_bf16 != 0;
 
   if (warp == 0 && lane == 0) {
@@ -346,6 +360,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           drow = reinterpret_cast<__nv_bfloat16*>(g.epi.out_f32) + (size_t)epilogue_row_ctx<MODE>(g.epi, m_d, sp) * g.epi.ldo;
         else
           drow = g.epi.out_act + (size_t)m_d * g.epi.lda_out;
+      }
+      if constexpr (MODE == EPI_GLU_F32) {
+        if (direct) {
+          // GLU straight from the TMEM-load registers: 32 accumulator columns = 16 (value, gate) pairs of one row per lane ->
+          // 16 bf16 outputs = one full 32-byte sector, no shared-memory transpose (the transposed path made this launch
+          // epilogue-bound: 46 us for 25.8 GFLOP at 1024 streams)
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(taddr + (uint32_t)c0, v);
+            if (c0 + 32 == BN / 2) {
+              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            }
+            const int ncol = n0 + half * (BN / 2) + c0;
+            if (drow != nullptr && ncol < g.N) {
+              uint32_t o[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float a0 = __uint_as_float(v[4 * j]) * sigmoidf_(__uint_as_float(v[4 * j + 1]));
+                const float a1 = __uint_as_float(v[4 * j + 2]) * sigmoidf_(__uint_as_float(v[4 * j + 3]));
+                const __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
+                o[j] = *reinterpret_cast<const uint32_t*>(&h);
+              }
+              uint4* dst = reinterpret_cast<uint4*>(drow + (ncol >> 1));
+              dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+              dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            }
+          }
+          continue;
+        }
       }
 #pragma unroll 1
       for (int c0 = 0; c0 < BN / 2; c0 += 16) {
@@ -613,6 +659,36 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int m = m0 + q * 32 + rd_row + 8 * i;
         ctx[i] = m < M ? epilogue_row_ctx<MODE>(g.epi, m, sp) : -1;
       }
+      if constexpr (MODE == EPI_PARTIAL_F32) {
+        if (g.epi.direct_bf16) {
+          // bf16 partial sums straight from the TMEM-load registers: the lane keeps its own accumulator row, 32 columns per load
+          // = 64 contiguous bytes of the workspace row (see the single-CTA kernel's direct path)
+          const int m_d = m0 + q * 32 + lane;
+          __nv_bfloat16* drow = m_d < M ? reinterpret_cast<__nv_bfloat16*>(g.epi.out_f32) + (size_t)epilogue_row_ctx<MODE>(g.epi, m_d, sp) * g.epi.ldo
+                                        : nullptr;
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(taddr + (uint32_t)c0, v);
+            if (c0 + 32 == BN / 2) {
+              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) mbar_arrive_rank0(&tmem_empty_bar[acc]);
+            }
+            const int ncol = n0 + half * (BN / 2) + c0;
+            if (drow != nullptr && ncol < g.N) {
+              uint4* dst = reinterpret_cast<uint4*>(drow + ncol + g.epi.n_off);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint2 p0 = pack4_bf16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1]), __uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                const uint2 p1 = pack4_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]), __uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+                dst[j] = make_uint4(p0.x, p0.y, p1.x, p1.y);
+              }
+            }
+          }
+          continue;
+        }
+      }
 #pragma unroll 1
       for (int c0 = 0; c0 < BN / 2; c0 += 16) {
         uint32_t v[16];
@@ -767,7 +843,9 @@ void gemm_tc(const GemmArgs& g_in, const TensorMap& map_a, const TensorMap& map_
     static const bool allow = [] { const char* v = getenv("PARAKEET_B200_EPI_DIRECT"); return !(v && v[0] == '0'); }();
     const EpiParams& e = g.epi;
     bool ok = allow && g.N % 16 == 0 && e.n_off % 8 == 0 && g.out_col_stride % 8 == 0;
-    if (e.mode == EPI_PARTIAL_F32) ok = ok && e.part_bf16 && e.ldo % 8 == 0 && ((uintptr_t)e.out_f32 & 15) == 0;
+    if (e.mode == EPI_PARTIAL_F32) ok = ok && e.part_bf16 && e.ldo % 8 == 0 && ((uintptr_t)e.out_f32 & 15) == 0 && g.N % 32 == 0;
+    else if (e.mode == EPI_GLU_F32)
+      ok = ok && e.out_act != nullptr && g.N % 32 == 0 && e.n_off == 0 && g.batch == 1 && e.lda_out % 8 == 0 && ((uintptr_t)e.out_act & 15) == 0;
     else if (e.mode == EPI_ACT || e.mode == EPI_SILU_ACT || e.mode == EPI_BIAS_RELU_ACT)
       ok = ok && e.lo_off_out == 0 && e.lda_out % 8 == 0 && ((uintptr_t)e.out_act & 15) == 0 && (e.mode != EPI_BIAS_RELU_ACT || ((uintptr_t)e.bias & 15) == 0);
     else ok = false;
