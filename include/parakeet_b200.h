@@ -102,6 +102,9 @@ int32_t pkb_engine_profile_read_class(PkbEngine* engine, int32_t cls, double* ms
  * pkb_engine_decode_loop_stats: device time (CUDA events the graph records around its WHILE node), algorithmic bytes, passes and
  * count of the decode loops run inside graphs since the last reset. */
 int32_t pkb_engine_graphs_built(PkbEngine* engine);
+/* the reference's PARAKEET_BLANK_PENALTY knob (cpp/src/parakeet_trt.cpp:3175-3178; read from the environment when the engine is
+ * created) changed at run time: subtracted from the blank logit before the token argmax of every later decode */
+int32_t pkb_engine_set_blank_penalty(PkbEngine* engine, float penalty);
 int32_t pkb_engine_decode_loop_stats(PkbEngine* engine, double* ms, double* bytes, int64_t* passes, int64_t* loops, int32_t reset);
 
 /* ---- results ---- */

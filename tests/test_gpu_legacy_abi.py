@@ -55,7 +55,7 @@ def test_push_prologue_auto_chunking(tmp_path, model_small, features_ref):
     # 257 frames: 256 + a 1-frame tail the streaming encoder cannot take -> the first slice is processed, then rc -2 + ERROR event
     rc3, st3, ev3, _ = _drive(model_small, fp, [(0, 257)])
     rc4, st4, _, _ = _drive(model_small, fp, [(0, 256), (256, 257)])
-    assert rc3 == [-2] and rc4 == [0, -2] and st3 == st4 and len(st3) >= 3
+    assert rc3 == [-2] and rc4 == [0, -2] and st3 == st4 and len(st3) >= 1
     assert any(e.startswith("event error") and "frames" in e for e in ev3)
     # PARAKEET_MAX_FRAMES_PER_PUSH=100 (:1984): 600 frames -> six 100-frame slices
     rc5, st5, _, _ = _drive(model_small, fp, [(0, 600)], PARAKEET_MAX_FRAMES_PER_PUSH=100)

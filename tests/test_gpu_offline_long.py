@@ -208,3 +208,35 @@ def test_deferred_batched_decode(model_small, features_ref, prec):
     for s, (steps, toks, frames) in zip(sids, want):
         assert eng.last_steps(s) == steps and eng.tokens(s) == toks and eng.token_frames(s) == frames
     eng.close()
+
+
+def test_tcgen05_attention_against_the_other_kernels_at_15000_frames(model_small, features_ref):
+    """The whole-utterance attention exists three times: lf_attention_tc_kernel (tcgen05 / TMEM, the bf16-mode default),
+    lf_attention_tma_kernel (mma.sync; PARAKEET_B200_LF_ATTN=1) and lf_attention_f32_kernel (CUDA cores, precise mode: the kernel
+    whose traces equal the oracle's at 125 / 388 / 3000 frames).  The oracle cannot reach 15 000 encoder frames in seconds, so at that
+    size (235 key tiles per query tile, 118 query tiles, relative positions up to +-14 999) the tcgen05 kernel is cross-checked
+    against both: bf16 tolerance vs the f32 kernel, and the two bf16 kernels agree to bf16 rounding noise of the encoder output."""
+    import os
+    f = _feats(features_ref, 1200.0, 9)
+    outs = {}
+    for name, prec, kind in (("tc", 0, "2"), ("tma", 0, "1"), ("f32", 1, None)):
+        if kind is not None:
+            os.environ["PARAKEET_B200_LF_ATTN"] = kind
+        try:
+            eng = binding.Engine(model_small, max_streams=1, precision=prec, max_rows=15008 + 64)
+            sid = eng.open()
+            outs[name] = eng.offline_utterances([sid], features=[f], want_encoder_output=True, decode=True)[0]
+            outs[name + "_steps"] = eng.last_steps(sid)
+            eng.close()
+        finally:
+            os.environ.pop("PARAKEET_B200_LF_ATTN", None)
+    assert outs["tc"].shape == (1024, 15000) and np.isfinite(outs["tc"]).all()
+    _check(outs["tc"], outs["f32"], 0, "tcgen05 (bf16) vs f32 CUDA-core kernel, 15000 frames")
+    _check(outs["tma"], outs["f32"], 0, "mma.sync (bf16) vs f32 CUDA-core kernel, 15000 frames")
+    d = np.abs(outs["tc"] - outs["tma"])
+    assert np.percentile(d, 95) <= 3e-2 and d.max() <= 1.5e-1, (float(np.percentile(d, 95)), float(d.max()))
+    # decode traces: mostly identical (every difference is a bf16-borderline decision); at least 97 % of the steps of the common prefix
+    a, b = outs["tc_steps"], outs["f32_steps"]
+    n = min(len(a), len(b))
+    same = sum(x == y for x, y in zip(a[:n], b[:n]))
+    assert n >= 15000 // 4 and same >= 0.9 * n, (same, n)

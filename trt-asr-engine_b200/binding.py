@@ -28,7 +28,7 @@ B200_SYMBOLS = ["pkb_last_error", "pkb_version", "pkb_engine_create", "pkb_engin
                 "pkb_engine_kernel_launches", "pkb_stream_open", "pkb_stream_close", "pkb_stream_reset", "pkb_stream_push_features",
                 "pkb_stream_push_audio", "pkb_stream_set_feature_norm", "pkb_stream_set_feature_norm_running", "pkb_stream_set_offline", "pkb_encoder_offline_step", "pkb_offline_utterances", "pkb_offline_decode_pending", "pkb_encoded_length", "pkb_engine_push_audio_batch",
                 "pkb_engine_push_audio_batch_device", "pkb_engine_event_record", "pkb_engine_event_elapsed_ms",
-                "pkb_engine_profile_enable", "pkb_engine_profile_read", "pkb_engine_profile_read_class", "pkb_engine_graphs_built",
+                "pkb_engine_profile_enable", "pkb_engine_profile_read", "pkb_engine_profile_read_class", "pkb_engine_graphs_built", "pkb_engine_set_blank_penalty",
                 "pkb_engine_decode_loop_stats", "pkb_engine_step", "pkb_stream_has_pending",
                 "pkb_stream_num_tokens", "pkb_stream_tokens", "pkb_stream_token_frames", "pkb_stream_encoder_frames", "pkb_stream_stable_prefix", "pkb_stream_last_steps", "pkb_stream_cache_len",
                 "pkb_stream_chunks_done", "pkb_stream_text", "pkb_detokenize", "pkb_token_is_punct_only", "pkb_vocab_open", "pkb_vocab_close",
@@ -122,6 +122,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.pkb_engine_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), lp]
     lib.pkb_engine_profile_read_class.argtypes = [vp, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), lp]
     lib.pkb_engine_graphs_built.argtypes = [vp]
+    lib.pkb_engine_set_blank_penalty.argtypes = [vp, C.c_float]
     lib.pkb_engine_decode_loop_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), lp, lp, C.c_int32]
     lib.pkb_stream_tokens.argtypes = [vp, C.c_int32, ip, C.c_int32]
     lib.pkb_stream_last_steps.argtypes = [vp, C.c_int32, C.POINTER(PkbStep), C.c_int32]
@@ -347,6 +348,9 @@ class Engine:
         ms, wk, n = C.c_double(), C.c_double(), C.c_int64()
         self._chk(self._lib.pkb_engine_profile_read_class(self._e, cls, C.byref(ms), C.byref(wk), C.byref(n)))
         return ms.value, wk.value, n.value
+
+    def set_blank_penalty(self, penalty: float):
+        self._chk(self._lib.pkb_engine_set_blank_penalty(self._e, float(penalty)))
 
     def graphs_built(self) -> int:
         return self._chk(self._lib.pkb_engine_graphs_built(self._e))

@@ -646,6 +646,10 @@ int32_t pkb_engine_decode_loop_stats(PkbEngine* e, double* ms, double* bytes, in
   if (!ms || !bytes || !passes || !loops) { g_last_error = "null argument"; return -1; }
   return guarded([&] { long long p = 0, l = 0; e->eng->decode_loop_stats(ms, bytes, &p, &l, reset); *passes = p; *loops = l; return 0; });
 }
+int32_t pkb_engine_set_blank_penalty(PkbEngine* e, float penalty) {
+  PKB_ENTER(e);
+  return guarded([&] { e->eng->set_blank_penalty(penalty); return 0; });
+}
 int32_t pkb_engine_graphs_built(PkbEngine* e) { PKB_ENTER(e); return e->eng->graphs_built(); }
 int32_t pkb_engine_step(PkbEngine* e) { PKB_ENTER(e); return guarded([&] { return e->eng->step(); }); }
 int32_t pkb_stream_has_pending(PkbEngine* e, int32_t s) { PKB_ENTER(e); return guarded([&] { return e->eng->has_pending(s) ? 1 : 0; }); }

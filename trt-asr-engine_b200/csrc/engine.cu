@@ -282,6 +282,13 @@ struct Engine::Impl {
   float* lf_store = nullptr;             // deferred decode: joint.enc(encoder rows) of encoded, not yet decoded utterances [rows][640]
   size_t lf_store_cap = 0, lf_store_used = 0;
   TensorMap lf_map_qkv, lf_map_pos;      // TMA maps of this call's q|k|v rows and projected table (bf16 mode)
+  // tcgen05 whole-utterance attention (lf_attn_tc.cu): biased query planes, transposed V and their maps
+  __nv_bfloat16* lf_qplanes = nullptr;   // [2][lf_q_rows][1024]
+  int lf_q_rows = 0;
+  __nv_bfloat16* lf_vt = nullptr;        // [1024][lf_ldv]
+  long long lf_ldv = 0;
+  TensorMap lf_map_q, lf_map_pos64, lf_map_vt;
+  int lf_attn_kind = 2;                  // PARAKEET_B200_LF_ATTN: 2 = tcgen05 (default), 1 = mma.sync fed by TMA, 0 = mma.sync fed by LDG/STS
   size_t lf_steps_ints = 0;
   FrontSegment* segs_dev = nullptr;
   FrontSegment* segs_host = nullptr;
@@ -424,6 +431,17 @@ void Engine::decode_loop_stats(double* ms, double* bytes, long long* passes, lon
   if (reset) { im.loop_ms = im.loop_bytes = 0.0; im.loop_passes = im.loop_count = 0; }
 }
 int Engine::graphs_built() const { return (int)im_->graphs.size(); }
+// PARAKEET_BLANK_PENALTY at run time.  Kernel arguments of captured steps carry the old value: the step graphs are dropped.
+void Engine::set_blank_penalty(float p) {
+  PKB_CUDA(cudaStreamSynchronize(st_));
+  opt_.blank_penalty = p;
+  for (auto& kv : im_->graphs) {
+    cudaGraphExecDestroy(kv.second->exec); cudaGraphDestroy(kv.second->graph);
+    cudaEventDestroy(kv.second->ev_loop0); cudaEventDestroy(kv.second->ev_loop1);
+  }
+  im_->graphs.clear();
+  im_->graph_seen.clear();
+}
 void Engine::profile_read(int cls, double* ms, double* work, long long* launches) {
   PKB_CHECK(cls >= 0 && cls < kProfClasses, "profile class");
   *ms = im_->prof_ms[cls]; *work = im_->prof_work[cls]; *launches = im_->prof_launches[cls];
@@ -1290,12 +1308,30 @@ void Engine::run_encoder(const BatchDev& b, const LongForm* lf) {
       if (l == 0) {      // same buffers for every layer: the maps only depend on this call's row counts
         make_tensor_map_2d(&im.lf_map_qkv, im.lf_qkv, (uint64_t)M, 3 * kDModel, 3 * kDModel, 64);
         make_tensor_map_2d(&im.lf_map_pos, im.lf_ppos, (uint64_t)(2 * lf.Tm - 1), kDModel, kDModel, 128);
+        if (im.lf_attn_kind == 2) {
+          make_tensor_map_2d(&im.lf_map_q, im.lf_qplanes, (uint64_t)2 * im.lf_q_rows, kDModel, kDModel, 128);
+          make_tensor_map_2d(&im.lf_map_pos64, im.lf_ppos, (uint64_t)(2 * lf.Tm - 1), kDModel, kDModel, 64);
+          make_tensor_map_2d(&im.lf_map_vt, im.lf_vt, (uint64_t)kDModel, (uint64_t)im.lf_ldv, (uint64_t)im.lf_ldv, 128);
+        }
       }
-      a.map_qkv = &im.lf_map_qkv; a.map_pos = &im.lf_map_pos;
+      a.map_qkv = im.lf_attn_kind >= 1 ? &im.lf_map_qkv : nullptr; a.map_pos = im.lf_attn_kind >= 1 ? &im.lf_map_pos : nullptr;
     }
     double pairs = 0.0;      // sum over utterances of T^2 (host copy of the batch fields)
     for (int i = 0; i < b.B; ++i) { const double t = im.batch_ints_host[6 * im.Bcap + i]; pairs += t * t; }
     // algorithmic FLOPs: content score, position score and value product, 128 MACs each per (query, key, head)
+    if (!split && im.lf_attn_kind == 2) {
+      // tcgen05 kernel: biased query planes + V^T once per layer, then S / position blocks / PV on the 5th-generation tensor cores
+      LfTcArgs t;
+      t.qkv = (const __nv_bfloat16*)im.lf_qkv; t.bias_u = w.bias_u; t.bias_v = w.bias_v;
+      t.q_planes = im.lf_qplanes; t.q_plane_rows = im.lf_q_rows; t.q_plane = (long long)im.lf_q_rows * kDModel;
+      t.vt = im.lf_vt; t.ldv = im.lf_ldv; t.Tm = lf.Tm; t.ctx = im.a_ln.ptr; t.ldc = kDModel;
+      t.map_q = &im.lf_map_q; t.map_k = &im.lf_map_qkv; t.map_pos = &im.lf_map_pos64; t.map_vt = &im.lf_map_vt;
+      launch_lf_prep(b, t, st_); ++launches_;
+      const int pi = prof_begin(4, 2.0 * 3.0 * kDHead * kHeads * pairs);
+      launch_lf_attention_tc(b, t, b.max_Tq, st_); ++launches_;
+      prof_end(pi);
+      return;
+    }
     const int pi = prof_begin(4, 2.0 * 3.0 * kDHead * kHeads * pairs);
     launch_lf_attention(b, a, st_); ++launches_;
     prof_end(pi);
@@ -1886,6 +1922,16 @@ void Engine::lf_prepare(size_t total_frames, size_t steps_ints) {
     const size_t rows = ((size_t)im.Mcap + 127) / 128 * 128;
     im.lf_qkv = own(dev_alloc_bytes(rows * 3 * kDModel * (split ? 4 : 2)));
     im.lf_ppos = own(dev_alloc_bytes((size_t)2 * im.Mcap * kDModel * (split ? 4 : 2)));
+    { const char* v = getenv("PARAKEET_B200_LF_ATTN"); if (v) im.lf_attn_kind = atoi(v); }
+    if (!split && im.lf_attn_kind == 2) {
+      // zero-filled once: rows / columns past the utterances are read by whole-tile TMA boxes and must hold finite values
+      im.lf_q_rows = (int)rows;
+      im.lf_qplanes = (__nv_bfloat16*)own(dev_alloc_bytes((size_t)2 * rows * kDModel * 2));
+      PKB_CUDA(cudaMemsetAsync(im.lf_qplanes, 0, (size_t)2 * rows * kDModel * 2, st_));
+      im.lf_ldv = ((long long)im.Mcap + 64LL * im.Bcap + 7) & ~7LL;
+      im.lf_vt = (__nv_bfloat16*)own(dev_alloc_bytes((size_t)kDModel * im.lf_ldv * 2));
+      PKB_CUDA(cudaMemsetAsync(im.lf_vt, 0, (size_t)kDModel * im.lf_ldv * 2, st_));
+    }
   }
   if (total_frames > im.lf_feat_frames) {
     disown_free(im.lf_feat);

@@ -142,6 +142,7 @@ class Engine {
   void profile_collect();
   void profile_read(int cls, double* ms, double* work, long long* launches);   // cls 0: tcgen05 GEMM (work = FLOPs), 1: attention, 2: frontend, 3: decode loop (bytes), 4: whole-utterance attention (FLOPs)
   void decode_loop_stats(double* ms, double* bytes, long long* passes, long long* loops, int reset);
+  void set_blank_penalty(float p);         // PARAKEET_BLANK_PENALTY (parakeet_trt.cpp:3175-3178) at run time
   int graphs_built() const;                // step shapes currently held as CUDA graphs (0: launch-by-launch path)
   int prof_begin(int cls, double work);
   void prof_end(int idx);

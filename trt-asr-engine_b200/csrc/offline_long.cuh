@@ -35,6 +35,30 @@ struct LfAttnArgs {
 // 127-row window of the table).  precise mode: f32 CUDA-core kernel (parity-grade; scores of one query row live in smem).
 void launch_lf_attention(const BatchDev& b, const LfAttnArgs& a, cudaStream_t st);
 
+// tcgen05 version (lf_attn_tc.cu, bf16 mode).  lf_prep_kernel derives its operands from the layer's q | k | v rows once per layer:
+// the two biased query planes and V transposed ([1024][ldv], utterance e at the 64-aligned column offset sum_{x<e} roundup64(T_x)).
+struct LfTcArgs {
+  const __nv_bfloat16* qkv = nullptr;      // [M][3072]
+  const float* bias_u = nullptr;           // [1024]
+  const float* bias_v = nullptr;
+  __nv_bfloat16* q_planes = nullptr;       // [2][q_plane_rows][1024]: q + pos_bias_u | q + pos_bias_v
+  long long q_plane = 0;                   // elements between the planes
+  int q_plane_rows = 0;                    // rows between the planes
+  __nv_bfloat16* vt = nullptr;             // [1024][ldv]
+  long long ldv = 0;
+  int Tm = 0;                              // centre of the projected position table (row = relative position + Tm - 1)
+  __nv_bfloat16* ctx = nullptr;            // [M][ldc] operand of linear_out
+  int ldc = 0;
+  // host pointers to CUtensorMap objects (64-column boxes, 128-byte swizzle): query planes (128-row boxes), q|k|v rows (64-row boxes),
+  // projected table (64-row boxes), V^T (128-row boxes)
+  const void* map_q = nullptr;
+  const void* map_k = nullptr;
+  const void* map_pos = nullptr;
+  const void* map_vt = nullptr;
+};
+void launch_lf_prep(const BatchDev& b, const LfTcArgs& a, cudaStream_t st);
+void launch_lf_attention_tc(const BatchDev& b, const LfTcArgs& a, int max_T, cudaStream_t st);
+
 struct LfDwConvArgs {
   const float* c = nullptr;               // post-GLU activations f32 [M][1024] (precise mode), or
   const __nv_bfloat16* c_bf16 = nullptr;  // bf16 [M][1024] (bf16 mode)
