@@ -523,19 +523,31 @@ def longform(binding, model, precision, batch, seconds, blank_penalty=None):
     t_enc = binding.load_library().pkb_encoded_length((n_samp - 400) // 160 + 1)
     # ~120 KB of work buffers per encoder frame: clips go through in groups that fit (4 one-hour clips = 22 GB)
     group = max(1, min(batch, int(4 * 45000 // max(t_enc, 1)) or 1))
-    pen = 6.0 if blank_penalty is None else blank_penalty
-    old_env = os.environ.get("PARAKEET_BLANK_PENALTY")
-    os.environ["PARAKEET_BLANK_PENALTY"] = str(pen)
-    try:
-        eng = binding.Engine(model, max_streams=batch, precision=precision, max_rows=group * t_enc + 64, contract_cache=0)
-    finally:
-        if old_env is None:
-            del os.environ["PARAKEET_BLANK_PENALTY"]
-        else:
-            os.environ["PARAKEET_BLANK_PENALTY"] = old_env
+    eng = binding.Engine(model, max_streams=batch, precision=precision, max_rows=group * t_enc + 64, contract_cache=0)
     sids = [eng.open() for _ in range(batch)]
     eng.offline_utterances(sids[:1], audio=[audio[0][:160000]], decode=True)       # warm-up (lazy buffers, first launches)
     eng.reset(sids[0])
+    # blank penalty: bisect (on the first 10 minutes of clip 0, untimed) for 0.2 - 0.4 tokens per encoder frame = 2.5 - 5 tokens per second
+    cal = []
+    if blank_penalty is None:
+        lo_p, hi_p, pen = 0.0, 32.0, 16.0
+        probe = audio[0][: min(n_samp, 600 * 16000)]
+        for _ in range(8):
+            pen = 0.5 * (lo_p + hi_p)
+            eng.set_blank_penalty(pen)
+            eng.offline_utterances(sids[:1], audio=[probe], per_feature_norm=True, decode=True)
+            ratio = len(eng.tokens(sids[0])) / max(len(eng.last_steps(sids[0])), 1)
+            cal.append((round(pen, 3), round(ratio, 3)))
+            eng.reset(sids[0])
+            if 0.2 <= ratio <= 0.4:
+                break
+            if ratio < 0.2:
+                lo_p = pen
+            else:
+                hi_p = pen
+    else:
+        pen = blank_penalty
+    eng.set_blank_penalty(pen)
     eng.profile_enable(True)
     t0 = time.perf_counter()
     for lo in range(0, batch, group):      # encode group by group (decode = 2: rows parked), then ONE batched decode of all clips
@@ -551,7 +563,7 @@ def longform(binding, model, precision, batch, seconds, blank_penalty=None):
     return {"workload": f"{batch} clips x {seconds:.0f} s (each a different sequence of 10 s synthetic segments) encoded in groups of {group}, decoded in one "
                         f"batched pass; whole-utterance offline (config 5 shape), encoder frames per clip {t_enc}",
             "rtfx_e2e": batch * seconds / wall, "wall_s": wall, "tokens": n_tok, "tokens_per_hour": n_tok / max(batch * seconds / 3600.0, 1e-9),
-            "blank_penalty": pen, "gemm_ms": gemm_ms, "gemm_tflops": gemm_flops / max(gemm_ms, 1e-9) / 1e9,
+            "blank_penalty": pen, "blank_penalty_calibration": cal, "gemm_ms": gemm_ms, "gemm_tflops": gemm_flops / max(gemm_ms, 1e-9) / 1e9,
             "attention_ms": att_ms, "attention_tflops_algorithmic": att_flops / max(att_ms, 1e-9) / 1e9, "attention_launches": int(att_l),
             "decode_ms": dec_ms}
 
