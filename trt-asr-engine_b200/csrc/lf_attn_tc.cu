@@ -18,7 +18,10 @@
 //
 // TMEM (512 columns): O [0,128) | S double buffer [128,256) | position-block ring 4 x 64 [256,512).
 // Shared memory: Qu, Qv (2 x 32 KB, resident), 2 stages x (K_t 16 KB + Pblk_{t+1} 16 KB + V^T_t 16 KB), P_t 16 KB, S copy 34 KB.
-// Warps: 0 = TMA producer, 1 = MMA issuer (+ TMEM allocation), 4..7 = softmax (thread == query row; warp % 4 == TMEM lane quarter).
+// Warps: 0 = TMA producer, 1 = MMA issuer (+ TMEM allocation), 4..11 = softmax: thread == (query row, half of the tile's 64 rotated
+// key steps); warp % 4 == TMEM lane quarter.  The two threads of a row exchange their partial row maximum once per tile (named
+// barrier of their two warps) and their partial row sums once at the end.  (One softmax warp per scheduler was the bottleneck of the
+// first version: 472 TFLOP/s algorithmic at T = 45 000; see DESIGN.md.)
 // V is consumed K-major, i.e. transposed ([d][key]): lf_prep_kernel writes V^T (and the two biased query planes) once per layer.
 #include <cuda.h>
 
@@ -39,7 +42,9 @@ constexpr int kOffP = kOffStage + 2 * kStageBytes;      // 163840: probabilities
 constexpr int kOffScr = kOffP + kSubA;                  // 180224: f32 copy of S, [128][kScrPitch] (prologue: table block 0)
 constexpr int kScrPitch = 68;                           // floats per row: 16-byte aligned rows, conflict-free rotated reads (5 l + s mod 32)
 constexpr int kOffBar = kOffScr + kQT * kScrPitch * 4;  // 215040
-constexpr size_t kSmemTc = 1024 + kOffBar + 128;
+constexpr int kOffXch = kOffBar + 256;                  // float [2][128]: row maxima / row sums exchanged between the two column halves
+constexpr size_t kSmemTc = 1024 + kOffXch + 4 * kQT * 4;      // [0,2): maxima, [2,4): final row sums
+constexpr int kThreadsTc = 384;                         // warps 0 (TMA), 1 (MMA), 2-3 (idle), 4-11 (softmax: two column halves x four lane quarters)
 constexpr uint32_t kColO = 0, kColS = 128, kColG = 256;
 constexpr float kScale = 0.08838834764831845f;          // 1/sqrt(128)
 constexpr float kTau = 6.0f;                            // O is rescaled only when a row maximum grows by more than this
@@ -183,7 +188,7 @@ lf_prep_kernel(BatchDev b, LfTcArgs a, int n_q_blocks) {
 }
 
 // ------------------------------------------------------------------------------------------------ attention
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kThreadsTc, 1)
 lf_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                        const __grid_constant__ CUtensorMap map_pos, const __grid_constant__ CUtensorMap map_vt, BatchDev b, LfTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -205,8 +210,8 @@ lf_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_pos) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_vt) : "memory");
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 1); mbar_init(&sg_full[s], 1); mbar_init(&s_empty[s], 4); }
-    mbar_init(p_full, 4);
+    for (int s = 0; s < 2; ++s) { mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 1); mbar_init(&sg_full[s], 1); mbar_init(&s_empty[s], 8); }
+    mbar_init(p_full, 8);
     mbar_init(pv_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -290,101 +295,104 @@ lf_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       }
     }
   } else if (warp >= 4 && n_tiles > 0) {
-    // ===================================================== softmax: thread == query row r of the tile
-    const int q = warp - 4, r = 32 * q + lane;
+    // ===================================================== softmax: thread == (query row r of the tile, half of the rotated key steps)
+    const int q = (warp - 4) & 3, half = (warp - 4) >> 2, r = 32 * q + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16);
     float* scr = reinterpret_cast<float*>(base + kOffScr) + r * kScrPitch;
+    float* xch = reinterpret_cast<float*>(base + kOffXch);      // [2][128]
     uint8_t* prow = base + kOffP + r * 128;
-    float m_run = -INFINITY, l_run = 0.f;
+    const int s0 = 32 * half;                                    // this thread's steps: s0 .. s0 + 31
+    float m_run = -INFINITY, l_run = 0.f;                        // m_run: identical in both halves; l_run: this half's partial sum
 #pragma unroll 1
     for (int t = 0; t < n_tiles; ++t) {
       const int bsel = t & 1, j0 = kKT * t;
       mbar_wait(&sg_full[bsel], (t >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // ---- S row -> own row of the shared-memory copy (so that it can be read at a per-lane index)
+      // ---- S row -> the row's shared-memory copy (each half copies 32 columns), so that it can be read at a per-lane index
       {
         uint32_t v[32];
+        tmem_ld32(lane_addr + kColS + bsel * 64 + 32 * half, v);
 #pragma unroll
-        for (int hlf = 0; hlf < 2; ++hlf) {
-          tmem_ld32(lane_addr + kColS + bsel * 64 + 32 * hlf, v);
-#pragma unroll
-          for (int x = 0; x < 8; ++x)
-            *reinterpret_cast<uint4*>(scr + 32 * hlf + 4 * x) = make_uint4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
-        }
+        for (int x = 0; x < 8; ++x)
+          *reinterpret_cast<uint4*>(scr + 32 * half + 4 * x) = make_uint4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");      // both halves of the row copy are in place
         if (lane == 0) mbar_arrive(&s_empty[bsel]);
       }
       // ---- scores in the rotated key order c = (s + lane) mod 64; window column = 32 q + 63 - s (+ 64 once s + lane wraps)
       // window column w lives in ring slot (t + 2 - (w >> 6)) & 3 at column w & 63:  w < 64: block t+1,  < 128: block t,  else block t-1
-      float x[64];
+      float x[32];
       float mt = -INFINITY;
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        const int s0 = 32 * ch;
+      {
         const int wa = 32 * q + 32 - s0;               // first window column of the 32 loaded for the un-wrapped lanes
         uint32_t ga[32], gb[32];
         tmem_ld32(lane_addr + kColG + (((t + 2 - (wa >> 6)) & 3) << 6) + (wa & 63), ga);
-        if (ch == 1) {                                 // lanes with s + lane >= 64 (only possible for s >= 33)
+        if (half == 1) {                               // lanes with s + lane >= 64 (only possible for s >= 33)
           const int wb = wa + 64;
           tmem_ld32(lane_addr + kColG + (((t + 2 - (wb >> 6)) & 3) << 6) + (wb & 63), gb);
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int s = s0 + j;
-          const int cw = s + lane;
+          const int cw = s0 + j + lane;
           const int c = cw & 63;
           float g = __uint_as_float(ga[31 - j]);
-          if (ch == 1) g = cw >= 64 ? __uint_as_float(gb[31 - j]) : g;
+          if (half == 1) g = cw >= 64 ? __uint_as_float(gb[31 - j]) : g;
           const float sc = scr[c];
           const float v = (j0 + c < T) ? (sc + g) * kScale : -INFINITY;
-          x[s] = v;
+          x[j] = v;
           mt = fmaxf(mt, v);
         }
       }
+      // ---- row maximum over both halves
+      xch[half * kQT + r] = mt;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      mt = fmaxf(mt, xch[(half ^ 1) * kQT + r]);
       // ---- online softmax with a lazy rescale of O (the running maximum only moves when it grows by more than kTau)
       float alpha = 1.f;
       const bool grow = mt > m_run + kTau;             // first tile: m_run = -inf -> true (key j0 is always valid: mt is finite)
       if (grow) { alpha = __expf(m_run - mt); m_run = mt; }
       float rs = 0.f;
 #pragma unroll
-      for (int s = 0; s < 64; ++s) { x[s] = __expf(x[s] - m_run); rs += x[s]; }
+      for (int j = 0; j < 32; ++j) { x[j] = __expf(x[j] - m_run); rs += x[j]; }
       l_run = l_run * alpha + rs;
       if (t > 0) {
         mbar_wait(pv_done, (t - 1) & 1);               // PV_{t-1} complete: the P buffer is free and O is stable
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (__any_sync(0xffffffffu, grow)) {
+        if (__any_sync(0xffffffffu, grow)) {           // this half rescales O columns [64 half, 64 half + 64)
 #pragma unroll 1
-          for (int cc = 0; cc < 4; ++cc) {
+          for (int cc = 0; cc < 2; ++cc) {
             uint32_t o[32];
-            tmem_ld32(lane_addr + kColO + 32 * cc, o);
+            tmem_ld32(lane_addr + kColO + 64 * half + 32 * cc, o);
 #pragma unroll
             for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
-            tmem_st32(lane_addr + kColO + 32 * cc, o);
+            tmem_st32(lane_addr + kColO + 64 * half + 32 * cc, o);
           }
         }
       }
       // ---- P_t -> shared memory, bf16, K-major 128-byte-swizzled A tile [128 rows][64 keys]
 #pragma unroll
-      for (int s = 0; s < 64; ++s) {
-        const int c = (s + lane) & 63;
-        *reinterpret_cast<__nv_bfloat16*>(prow + ((((c >> 3) ^ (r & 7)) << 4) | ((c & 7) << 1))) = __float2bfloat16_rn(x[s]);
+      for (int j = 0; j < 32; ++j) {
+        const int c = (s0 + j + lane) & 63;
+        *reinterpret_cast<__nv_bfloat16*>(prow + ((((c >> 3) ^ (r & 7)) << 4) | ((c & 7) << 1))) = __float2bfloat16_rn(x[j]);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core's smem reads
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }
-    // ---- context rows -> bf16 operand of linear_out
+    // ---- row sums of the two halves, then the context rows -> bf16 operand of linear_out (each half stores 64 of the 128 columns)
+    xch[(2 + half) * kQT + r] = l_run;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+    l_run += xch[(2 + (half ^ 1)) * kQT + r];
     mbar_wait(pv_done, (n_tiles - 1) & 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
     const bool ok = i0 + r < T;
-    __nv_bfloat16* dst = a.ctx + (size_t)(row0 + i0 + r) * a.ldc + h * kDHead;
+    __nv_bfloat16* dst = a.ctx + (size_t)(row0 + i0 + r) * a.ldc + h * kDHead + 64 * half;
 #pragma unroll 1
-    for (int cc = 0; cc < 4; ++cc) {
+    for (int cc = 0; cc < 2; ++cc) {
       uint32_t o[32];
-      tmem_ld32(lane_addr + kColO + 32 * cc, o);
+      tmem_ld32(lane_addr + kColO + 64 * half + 32 * cc, o);
       if (ok) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -421,7 +429,7 @@ void launch_lf_attention_tc(const BatchDev& b, const LfTcArgs& a, int max_T, cud
     attr = true;
   }
   const dim3 grid((max_T + kQT - 1) / kQT, kHeads, b.B);
-  launch_k(lf_attention_tc_kernel, grid, dim3(256), kSmemTc, st, *reinterpret_cast<const CUtensorMap*>(a.map_q),
+  launch_k(lf_attention_tc_kernel, grid, dim3(kThreadsTc), kSmemTc, st, *reinterpret_cast<const CUtensorMap*>(a.map_q),
            *reinterpret_cast<const CUtensorMap*>(a.map_k), *reinterpret_cast<const CUtensorMap*>(a.map_pos),
            *reinterpret_cast<const CUtensorMap*>(a.map_vt), b, a);
   PKB_CUDA(cudaGetLastError());
