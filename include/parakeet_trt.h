@@ -61,7 +61,12 @@ void parakeet_reset_utterance(ParakeetSession* session);
 /* features: bins-major [128, num_frames] contiguous f32, features[m * num_frames + t]; borrowed for the call only.
  * One call == one encoder chunk (pushes above 256 frames are split at 256, reference :1982-2011); all decoding for
  * the pushed frames has completed on return.  Returns 0 ok (also for num_frames == 0), -1 NULL arguments,
- * -2 runtime error (an ERROR event carrying the message is queued) (reference :1967-1969, 3850-3857). */
+ * -2 runtime error (an ERROR event carrying the message is queued) (reference :1967-1969, 3850-3857).
+ * Streaming encoder (the default): a chunk must hold 33..256 frames -- 8x subsampling leaves 5 tokens of 33 frames, of which
+ * drop_extra_pre_encoded = 2 are dropped and valid_out_len = 3 are decoded; a shorter push returns -2 and processes nothing.
+ * All sessions of a process that share (model_dir, device, options) are streams of ONE engine (one copy of the weights); pushes
+ * that arrive together from several threads are served by one batched pass (PARAKEET_B200_MAX_SESSIONS slots per engine, default 8;
+ * PARAKEET_B200_COALESCE_US = how long a push waits for its siblings, default 200). */
 int parakeet_push_features(ParakeetSession* session, const float* features, size_t num_frames);
 
 /* NULL-safe; `id` is copied.  Context shows up in diagnostics only (reference :1951-1965). */

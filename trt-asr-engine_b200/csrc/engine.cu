@@ -488,17 +488,23 @@ void Engine::load_weights() {
                 wf.cfg("drop_extra_pre_encoded") == kDropPre,
             "weights.bin architecture constants do not match this build (Parakeet-TDT-0.6B-v3 shapes are compiled in)");
   Impl& im = *im_;
+  // every vector-shaped tensor is checked against the element count the kernels will read
+  auto F = [&](const std::string& name, size_t n) {
+    std::vector<float> v = wf.f32(name);
+    PKB_CHECK(v.size() == n, "weights.bin: tensor " + name + " has " + std::to_string(v.size()) + " elements, expected " + std::to_string(n));
+    return v;
+  };
   const std::string pe = "encoder.pre_encode.";
-  im.sub.w0 = dev_upload(wf.f32(pe + "conv.0.weight"));
-  im.sub.b0 = dev_upload(wf.f32(pe + "conv.0.bias"));
-  im.sub.w2 = dev_upload(wf.f32(pe + "conv.2.weight"));
-  im.sub.b2 = dev_upload(wf.f32(pe + "conv.2.bias"));
-  im.sub.w5 = dev_upload(wf.f32(pe + "conv.5.weight"));
-  im.sub.b5 = dev_upload(wf.f32(pe + "conv.5.bias"));
+  im.sub.w0 = dev_upload(F(pe + "conv.0.weight", (size_t)kSubCh * 9));
+  im.sub.b0 = dev_upload(F(pe + "conv.0.bias", kSubCh));
+  im.sub.w2 = dev_upload(F(pe + "conv.2.weight", (size_t)kSubCh * 9));
+  im.sub.b2 = dev_upload(F(pe + "conv.2.bias", kSubCh));
+  im.sub.w5 = dev_upload(F(pe + "conv.5.weight", (size_t)kSubCh * 9));
+  im.sub.b5 = dev_upload(F(pe + "conv.5.bias", kSubCh));
   im.sub_pw1 = upload_gemm_w(wf.bf16(pe + "conv.3.weight"), kSubCh, kSubCh);
-  im.sub_pw1_b = dev_upload(wf.f32(pe + "conv.3.bias"));
+  im.sub_pw1_b = dev_upload(F(pe + "conv.3.bias", kSubCh));
   im.sub_pw2 = upload_gemm_w(wf.bf16(pe + "conv.6.weight"), kSubCh, kSubCh);
-  im.sub_pw2_b = dev_upload(wf.f32(pe + "conv.6.bias"));
+  im.sub_pw2_b = dev_upload(F(pe + "conv.6.bias", kSubCh));
   {
     // Linear(4096 -> 1024): NeMo flattens [C=256, F=16] channel-major (c*16+f); our operand rows are (f*256+c)
     std::vector<uint16_t> w = wf.bf16(pe + "out.weight"), p(w.size());
@@ -506,17 +512,17 @@ void Engine::load_weights() {
       for (int c = 0; c < kSubCh; ++c)
         for (int f = 0; f < 16; ++f) p[(size_t)n * 4096 + f * kSubCh + c] = w[(size_t)n * 4096 + c * 16 + f];
     im.sub_out = upload_gemm_w(p, kDModel, 4096);
-    im.sub_out_b = dev_upload(wf.f32(pe + "out.bias"));
+    im.sub_out_b = dev_upload(F(pe + "out.bias", kDModel));
   }
   im.layers.resize(L_);
   for (int l = 0; l < L_; ++l) {
     const std::string p = "encoder.layers." + std::to_string(l) + ".";
     LayerW& w = im.layers[l];
-    w.n_ff1_g = dev_upload(wf.f32(p + "norm_feed_forward1.weight")); w.n_ff1_b = dev_upload(wf.f32(p + "norm_feed_forward1.bias"));
-    w.n_att_g = dev_upload(wf.f32(p + "norm_self_att.weight"));      w.n_att_b = dev_upload(wf.f32(p + "norm_self_att.bias"));
-    w.n_conv_g = dev_upload(wf.f32(p + "norm_conv.weight"));         w.n_conv_b = dev_upload(wf.f32(p + "norm_conv.bias"));
-    w.n_ff2_g = dev_upload(wf.f32(p + "norm_feed_forward2.weight")); w.n_ff2_b = dev_upload(wf.f32(p + "norm_feed_forward2.bias"));
-    w.n_out_g = dev_upload(wf.f32(p + "norm_out.weight"));           w.n_out_b = dev_upload(wf.f32(p + "norm_out.bias"));
+    w.n_ff1_g = dev_upload(F(p + "norm_feed_forward1.weight", kDModel)); w.n_ff1_b = dev_upload(F(p + "norm_feed_forward1.bias", kDModel));
+    w.n_att_g = dev_upload(F(p + "norm_self_att.weight", kDModel));      w.n_att_b = dev_upload(F(p + "norm_self_att.bias", kDModel));
+    w.n_conv_g = dev_upload(F(p + "norm_conv.weight", kDModel));         w.n_conv_b = dev_upload(F(p + "norm_conv.bias", kDModel));
+    w.n_ff2_g = dev_upload(F(p + "norm_feed_forward2.weight", kDModel)); w.n_ff2_b = dev_upload(F(p + "norm_feed_forward2.bias", kDModel));
+    w.n_out_g = dev_upload(F(p + "norm_out.weight", kDModel));           w.n_out_b = dev_upload(F(p + "norm_out.bias", kDModel));
     w.ff1_1 = upload_gemm_w(wf.bf16(p + "feed_forward1.linear1.weight"), kFF, kDModel);
     w.ff1_2 = upload_gemm_w(wf.bf16(p + "feed_forward1.linear2.weight"), kDModel, kFF);
     w.ff2_1 = upload_gemm_w(wf.bf16(p + "feed_forward2.linear1.weight"), kFF, kDModel);
@@ -545,9 +551,9 @@ void Engine::load_weights() {
     w.pw2 = upload_gemm_w(wf.bf16(p + "conv.pointwise_conv2.weight"), kDModel, kDModel);
     {
       // fold eval-mode BatchNorm1d into the depthwise kernel: y = dw*s + (beta - mean*s), s = gamma/sqrt(var+eps)
-      std::vector<float> dw = wf.f32(p + "conv.depthwise_conv.weight"), g = wf.f32(p + "conv.batch_norm.weight"),
-                         b = wf.f32(p + "conv.batch_norm.bias"), mu = wf.f32(p + "conv.batch_norm.running_mean"),
-                         var = wf.f32(p + "conv.batch_norm.running_var");
+      std::vector<float> dw = F(p + "conv.depthwise_conv.weight", (size_t)kDModel * kConvK), g = F(p + "conv.batch_norm.weight", kDModel),
+                         b = F(p + "conv.batch_norm.bias", kDModel), mu = F(p + "conv.batch_norm.running_mean", kDModel),
+                         var = F(p + "conv.batch_norm.running_var", kDModel);
       std::vector<float> off(kDModel);
       for (int c = 0; c < kDModel; ++c) {
         const float s = g[c] / sqrtf(var[c] + 1e-5f);
@@ -557,8 +563,8 @@ void Engine::load_weights() {
       w.dw_w = dev_upload(dw);
       w.dw_b = dev_upload(off);
     }
-    w.bias_u = dev_upload(wf.f32(p + "self_attn.pos_bias_u"));
-    w.bias_v = dev_upload(wf.f32(p + "self_attn.pos_bias_v"));
+    w.bias_u = dev_upload(F(p + "self_attn.pos_bias_u", kDModel));
+    w.bias_v = dev_upload(F(p + "self_attn.pos_bias_v", kDModel));
     w.ppos_t = nullptr;   // filled in alloc_state (needs work buffers)
     w.ppos_n = nullptr;
   }
@@ -576,17 +582,17 @@ void Engine::load_weights() {
         memcpy(&cat[(size_t)n * 2 * kPredH + kPredH], &hh[(size_t)n * kPredH], kPredH * 2);
       }
       im.lstm[l] = upload_gemm_w(cat, 4 * kPredH, 2 * kPredH);
-      std::vector<float> bi = wf.f32(p + "bias_ih_l" + std::to_string(l)), bh = wf.f32(p + "bias_hh_l" + std::to_string(l));
+      std::vector<float> bi = F(p + "bias_ih_l" + std::to_string(l), 4 * kPredH), bh = F(p + "bias_hh_l" + std::to_string(l), 4 * kPredH);
       for (size_t i = 0; i < bi.size(); ++i) bi[i] += bh[i];
       im.lstm_b[l] = dev_upload(bi);
     }
   }
   im.joint_enc = upload_gemm_w(wf.bf16("joint.enc.weight"), kJointH, kDModel);
-  im.joint_enc_b = dev_upload(wf.f32("joint.enc.bias"));
+  im.joint_enc_b = dev_upload(F("joint.enc.bias", kJointH));
   im.joint_pred = upload_gemm_w(wf.bf16("joint.pred.weight"), kJointH, kPredH);
-  im.joint_pred_b = dev_upload(wf.f32("joint.pred.bias"));
+  im.joint_pred_b = dev_upload(F("joint.pred.bias", kJointH));
   im.joint_out = upload_gemm_w(wf.bf16("joint.joint_net.2.weight"), kJointOut, kJointH);
-  im.joint_out_b = dev_upload(wf.f32("joint.joint_net.2.bias"));
+  im.joint_out_b = dev_upload(F("joint.joint_net.2.bias", kJointOut));
   im.punct_bits = dev_upload(punct_bits_);
   // keep the (host) linear_pos weights for alloc_state via a second open: cheap, mmap
 }

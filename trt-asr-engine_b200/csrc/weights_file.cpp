@@ -29,6 +29,16 @@ WeightsFile::WeightsFile(const std::string& path) {
   map_ = mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd, 0);
   ::close(fd);
   if (map_ == MAP_FAILED) { map_ = nullptr; throw std::runtime_error("mmap failed: " + path); }
+  try {
+    parse(path);
+  } catch (...) {      // a constructor that throws does not run the destructor: release the mapping here
+    munmap(map_, size_);
+    map_ = nullptr;
+    throw;
+  }
+}
+
+void WeightsFile::parse(const std::string& path) {
   const unsigned char* p = static_cast<const unsigned char*>(map_);
   Header h;
   memcpy(&h, p, sizeof(h));

@@ -39,6 +39,7 @@ class WeightsFile {
   std::vector<uint16_t> bf16(const std::string& name) const;
 
  private:
+  void parse(const std::string& path);
   void* map_ = nullptr;
   size_t size_ = 0;
   std::map<std::string, int64_t> cfg_;

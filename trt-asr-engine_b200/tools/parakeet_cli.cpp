@@ -5,7 +5,7 @@
 // frontend that replaces rust/features).  Inputs: WAV (PCM16 or float32, mono, 16 kHz), raw PCM (f32le), or a feature tap
 // (f32le raw + optional JSON sidecar: kind / format / layout / mel_bins / num_frames / shape, main.rs:132-165).
 //   parakeet_cli <input> --model-dir DIR [--stream-sim SEC] [--device-id N] [--raw-pcm] [--sample-rate HZ] [--features-input]
-//                [--n-mels N] [--verbose|-v] [--dump-features PATH] [--feature-norm none|per_feature] [--no-sleep] [--whole-utterance]
+//                [--n-mels N] [--verbose|-v] [--dump-features PATH] [--feature-norm none|per_feature] [--no-sleep] [--whole-utterance] [--stream-audio SECONDS]
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -30,6 +30,7 @@ struct Args {
   int device_id = 0, n_mels = -1;
   long sample_rate = -1;
   bool raw_pcm = false, features_input = false, verbose = false, no_sleep = false, whole_utterance = false;
+  double stream_audio = -1.0;      // additive: cache-aware streaming from audio (pkb_stream_push_audio), seconds per push
 };
 
 [[noreturn]] void die(const std::string& msg) {
@@ -189,11 +190,15 @@ int main(int argc, char** argv) {
     else if (s == "--dump-features") a.dump_features = need("--dump-features");
     else if (s == "--feature-norm") a.feature_norm = need("--feature-norm");
     else if (s == "--no-sleep") a.no_sleep = true;      // additive: stream simulation without the real-time sleeps
+    else if (s == "--stream-audio") a.stream_audio = std::atof(need("--stream-audio").c_str());
     else if (s == "--whole-utterance") a.whole_utterance = true;   // additive: one full-context pass over the whole file (pkb_offline_utterances)
     else if (s == "--help" || s == "-h") {
       std::printf("usage: parakeet_cli <input> --model-dir DIR [--stream-sim SEC] [--device-id N] [--raw-pcm] [--sample-rate HZ]\n"
                   "       [--features-input] [--n-mels N] [-v|--verbose] [--dump-features PATH] [--feature-norm none|per_feature] [--no-sleep]\n"
-                  "       [--whole-utterance]\n");
+                  "       [--whole-utterance] [--stream-audio SECONDS]\n"
+                  "  --stream-sim S     reference behaviour (rust/cli): every S seconds of audio become ONE independent push of its own frames\n"
+                  "  --stream-audio S   cache-aware streaming: audio is pushed S seconds at a time, the engine frames it and cuts the 41 / 57-frame\n"
+                  "                     chunk schedule itself (nothing is dropped between pushes); --feature-norm running = causal running statistics\n");
       return 0;
     } else if (!s.empty() && s[0] == '-') die("unknown option " + s);
     else a.input = s;
@@ -201,7 +206,7 @@ int main(int argc, char** argv) {
   if (a.input.empty() || a.model_dir.empty()) die("usage: parakeet_cli <input> --model-dir DIR [options]   (--help)");
   std::string norm = a.feature_norm;
   if (norm.empty()) { const char* e = std::getenv("PARAKEET_FEATURE_NORM"); norm = e ? e : "none"; }
-  if (norm != "none" && norm != "per_feature") die("Unsupported feature normalization: " + norm);
+  if (norm != "none" && norm != "per_feature" && !(norm == "running" && a.stream_audio > 0)) die("Unsupported feature normalization: " + norm);
   const bool per_feature = norm == "per_feature";
   const auto t_start = std::chrono::steady_clock::now();
   if (a.verbose) {
@@ -279,6 +284,60 @@ int main(int argc, char** argv) {
         std::fprintf(stderr, "[replay] Completed in %.2fs\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
       return 0;
     }
+    if (a.stream_audio > 0) {
+      // Additive mode: the reference CLI's --stream-sim makes every interval an independent push, of which the streaming
+      // encoder decodes only valid_out_len = 3 frames -- fine for replaying 48-frame chunks, lossy for anything else.  Here the audio goes
+      // through pkb_stream_push_audio: the engine keeps the sample / frame carry-over, cuts the cache-aware schedule (41 frames, then 57-frame
+      // slices shifted by 24) and decodes every encoder frame once.  The tail is flushed with up to one chunk of zero samples.
+      const size_t per_push = (size_t)(a.stream_audio * 16000.0);
+      if (per_push == 0) die("--stream-audio interval too small");
+      PkbEngineConfig ec{};
+      ec.model_dir = a.model_dir.c_str(); ec.device_id = a.device_id; ec.max_streams = 1; ec.precision = 0; ec.gemm_backend = 0;
+      ec.contract_cache = 0; ec.punct_suppression = 1; ec.max_rows = 0;
+      PkbEngine* eng = pkb_engine_create(&ec);
+      if (!eng) die(std::string("engine creation failed: ") + pkb_last_error());
+      const int32_t sid = pkb_stream_open(eng);
+      if (sid < 0) die(std::string("pkb_stream_open failed: ") + pkb_last_error());
+      if (norm == "running") {
+        if (pkb_stream_set_feature_norm_running(eng, sid, 1) != 0) die(std::string("running normalisation: ") + pkb_last_error());
+      } else if (per_feature) {      // whole-file statistics, like the reference's stream-sim (main.rs:398-405)
+        Frontend fe(a.device_id);
+        size_t T = 0;
+        std::vector<float> tc = fe.compute(audio.data(), audio.size(), &T);
+        std::vector<float> mean, stdv;
+        per_feature_stats(tc, T, &mean, &stdv);
+        if (pkb_stream_set_feature_norm(eng, sid, mean.data(), stdv.data()) != 0) die(std::string("feature norm: ") + pkb_last_error());
+      }
+      std::printf("Starting transcription (cache-aware streaming from audio)...\n");
+      std::vector<char> text;
+      auto drain_steps = [&](bool final_print) {
+        while (pkb_stream_has_pending(eng, sid) > 0) {
+          const int n = pkb_engine_step(eng);
+          if (n < 0) die(std::string("pkb_engine_step failed: ") + pkb_last_error());
+          if (n == 0) break;
+        }
+        text.assign((size_t)pkb_stream_text(eng, sid, nullptr, 0) + 1, 0);
+        pkb_stream_text(eng, sid, text.data(), (int32_t)text.size());
+        if (final_print) std::printf("\nFinal: %s\n", text.data());
+        else { std::printf("\rPartial: %s", text.data()); std::fflush(stdout); }
+      };
+      for (size_t pos = 0; pos < audio.size(); pos += per_push) {
+        const size_t n = std::min(per_push, audio.size() - pos);
+        if (pkb_stream_push_audio(eng, sid, audio.data() + pos, n) != 0) die(std::string("pkb_stream_push_audio failed: ") + pkb_last_error());
+        drain_steps(false);
+        if (!a.no_sleep) std::this_thread::sleep_for(std::chrono::duration<double>(a.stream_audio));
+      }
+      const std::vector<float> zeros((size_t)57 * 160 + 400, 0.0f);      // completes the last partial chunk of the schedule
+      if (pkb_stream_push_audio(eng, sid, zeros.data(), zeros.size()) != 0) die(std::string("flush failed: ") + pkb_last_error());
+      drain_steps(true);
+      if (a.verbose)
+        std::fprintf(stderr, "[replay] %lld chunks, %lld encoder frames, %d tokens\n", (long long)pkb_stream_chunks_done(eng, sid),
+                     (long long)pkb_stream_encoder_frames(eng, sid), pkb_stream_num_tokens(eng, sid));
+      pkb_engine_destroy(eng);
+      if (a.verbose)
+        std::fprintf(stderr, "[replay] Completed in %.2fs\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
+      return 0;
+    }
     Frontend fe(a.device_id);
     std::vector<float> mean, stdv;
     std::vector<float> whole_tc;
@@ -296,7 +355,10 @@ int main(int argc, char** argv) {
         const size_t n = std::min(per_chunk, audio.size() - pos);
         size_t T = 0;
         std::vector<float> tc = fe.compute(audio.data() + pos, n, &T);
-        if (T > 0) {
+        if (T > 0 && T < 33) {
+          // the streaming encoder needs 33 frames per push (8x subsampling, 2 dropped + 3 emitted tokens): a shorter tail is skipped
+          std::fprintf(stderr, "[replay] WARNING: chunk=%zu has %zu frames (< 33, the streaming encoder's minimum): skipped\n", idx, T);
+        } else if (T > 0) {
           if (per_feature) apply_norm(&tc, T, mean, stdv);
           const std::vector<float> bct = frames_major_to_bins_major(tc, kMels, T);
           if (!a.dump_features.empty()) all_bct.insert(all_bct.end(), bct.begin(), bct.end());
