@@ -149,3 +149,38 @@ def test_cli_replays_reference_written_taps(model_small):
     eng.step()
     assert outs[0][0] == "Transcript: " + eng.text(s)
     eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("norm", ["none", "running"])
+def test_cli_stream_audio(tmp_path, model_small, norm):
+    """--stream-audio: cache-aware streaming from audio (nothing dropped between pushes, tail flushed with zeros); the final transcript
+    equals the same audio pushed through pkb_stream_push_audio in other piece sizes (the schedule, not the push size, cuts the chunks).
+    A push interval below 0.33 s -- fatal for --stream-sim's one-push-one-chunk model -- is fine here; --stream-sim skips such tails."""
+    from synth_audio import synth_clip
+    _build()
+    pcm = _write_wav16(str(tmp_path / "a.wav"), synth_clip(5.3, 91))
+    run = subprocess.run([CLI, str(tmp_path / "a.wav"), "--model-dir", model_small, "--stream-audio", "0.2", "--no-sleep", "--feature-norm", norm, "-v"],
+                         capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stderr
+    finals = [ln[len("Final: "):] for ln in run.stdout.splitlines() if ln.startswith("Final: ")]
+    assert len(finals) == 1
+    eng = binding.Engine(model_small, max_streams=1, precision=0, contract_cache=0)
+    s = eng.open()
+    if norm == "running":
+        eng.set_feature_norm_running(s, True)
+    for pos in range(0, pcm.size, 5000):
+        eng.push_audio(s, pcm[pos:pos + 5000])
+        while eng.has_pending(s) and eng.step():
+            pass
+    eng.push_audio(s, np.zeros(57 * 160 + 400, np.float32))
+    while eng.has_pending(s) and eng.step():
+        pass
+    assert finals[0] == eng.text(s)
+    n_frames = (pcm.size + 57 * 160 + 400 - 400) // 160 + 1
+    assert f"{eng.chunks_done(s)} chunks" in run.stderr and eng.chunks_done(s) >= (n_frames - 41) // 24
+    eng.close()
+    # --stream-sim with a 0.2 s interval: every push has 18 frames (< 33): skipped with a warning, exit code 0
+    run = subprocess.run([CLI, str(tmp_path / "a.wav"), "--model-dir", model_small, "--stream-sim", "0.2", "--no-sleep"], capture_output=True,
+                         text=True, timeout=300)
+    assert run.returncode == 0 and "skipped" in run.stderr

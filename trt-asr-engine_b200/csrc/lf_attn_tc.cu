@@ -44,10 +44,9 @@ constexpr int kScrPitch = 68;                           // floats per row: 16-by
 constexpr int kOffBar = kOffScr + kQT * kScrPitch * 4;  // 215040
 constexpr int kOffXch = kOffBar + 256;                  // float [2][128]: row maxima / row sums exchanged between the two column halves
 constexpr size_t kSmemTc = 1024 + kOffXch + 4 * kQT * 4;      // [0,2): maxima, [2,4): final row sums
-constexpr int kThreadsTc = 384;                         // warps 0 (TMA), 1 (MMA), 2-3 (idle), 4-11 (softmax: two column halves x four lane quarters)
 constexpr uint32_t kColO = 0, kColS = 128, kColG = 256;
-constexpr float kScale = 0.08838834764831845f;          // 1/sqrt(128)
-constexpr float kTau = 6.0f;                            // O is rescaled only when a row maximum grows by more than this
+constexpr float kScale2 = 0.08838834764831845f * 1.4426950408889634f;      // log2(e) / sqrt(128): scores are kept in the exp2 domain
+constexpr float kTau2 = 8.0f;                           // O is rescaled only when a row maximum grows by more than this (factor 256)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -72,6 +71,41 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
   }
+}
+// waits of the two single-thread roles (TMA producer, MMA issuer): back off between polls so that the spin does not take issue
+// slots from the softmax warps that share their schedulers (the first version spent 18 % of its issued instructions in these loops)
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) break;
+    __nanosleep(40);
+  }
+}
+// explicit shared-window accesses with 32-bit addresses (through generic pointers the compiler emitted LD.E / ST.E with 64-bit
+// address arithmetic for every element of the rotated S reads and P writes: a quarter of the kernel's instructions)
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_b16(uint32_t addr, uint16_t v) { asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(v) : "memory"); }
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
@@ -188,7 +222,9 @@ lf_prep_kernel(BatchDev b, LfTcArgs a, int n_q_blocks) {
 }
 
 // ------------------------------------------------------------------------------------------------ attention
-__global__ void __launch_bounds__(kThreadsTc, 1)
+// NH = softmax warpgroups per CTA: 1 (thread == query row, all 64 rotated key steps of a tile) or 2 (two threads per row, 32 steps each)
+template <int NH>
+__global__ void __launch_bounds__(128 + 128 * NH, 1)
 lf_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                        const __grid_constant__ CUtensorMap map_pos, const __grid_constant__ CUtensorMap map_vt, BatchDev b, LfTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -210,8 +246,8 @@ lf_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_pos) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_vt) : "memory");
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 1); mbar_init(&sg_full[s], 1); mbar_init(&s_empty[s], 8); }
-    mbar_init(p_full, 8);
+    for (int s = 0; s < 2; ++s) { mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 1); mbar_init(&sg_full[s], 1); mbar_init(&s_empty[s], 4 * NH); }
+    mbar_init(p_full, 4 * NH);
     mbar_init(pv_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -249,7 +285,7 @@ lf_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       for (int t = 0; t < n_tiles; ++t) {
         const int s = t & 1;
         uint8_t* st = base + kOffStage + s * kStageBytes;
-        mbar_wait(&st_empty[s], ((t >> 1) & 1) ^ 1);
+        mbar_wait_backoff(&st_empty[s], ((t >> 1) & 1) ^ 1);
         mbar_expect_tx(&st_full[s], kStageBytes);
         tma_load_2d(st + kStageK, &map_k, &st_full[s], kDModel + col_h, row0 + kKT * t);
         tma_load_2d(st + kStageK + kSubB, &map_k, &st_full[s], kDModel + col_h + 64, row0 + kKT * t);
@@ -277,14 +313,14 @@ lf_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         if (t + 1 < n_tiles) {
           const int s1 = (t + 1) & 1;
           const uint32_t st1 = uSt + s1 * kStageBytes;
-          mbar_wait(&st_full[s1], ((t + 1) >> 1) & 1);
-          mbar_wait(&s_empty[s1], (((t + 1) >> 1) & 1) ^ 1);
+          mbar_wait_backoff(&st_full[s1], ((t + 1) >> 1) & 1);
+          mbar_wait_backoff(&s_empty[s1], (((t + 1) >> 1) & 1) ^ 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           issue_k128(tmem_base + kColS + s1 * 64, uQu, kSubA, st1 + kStageK, kSubB, IDesc<64>::value);                 // S_{t+1}
           issue_k128(tmem_base + kColG + ((t + 3) & 3) * 64, uQv, kSubA, st1 + kStageP, kSubB, IDesc<64>::value);      // block t + 2
           umma_commit(&sg_full[s1]);
         }
-        mbar_wait(p_full, t & 1);
+        mbar_wait_backoff(p_full, t & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t vt = uSt + (t & 1) * kStageBytes + kStageV;
 #pragma unroll
@@ -295,104 +331,126 @@ lf_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       }
     }
   } else if (warp >= 4 && n_tiles > 0) {
-    // ===================================================== softmax: thread == (query row r of the tile, half of the rotated key steps)
+    // ===================================================== softmax: thread == (query row r of the tile, 64 / NH of the rotated key steps)
+    constexpr int NS = 64 / NH;                                  // steps per thread
+    constexpr int OC = 128 / NH;                                 // O columns this thread rescales / stores
     const int q = (warp - 4) & 3, half = (warp - 4) >> 2, r = 32 * q + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16);
-    float* scr = reinterpret_cast<float*>(base + kOffScr) + r * kScrPitch;
-    float* xch = reinterpret_cast<float*>(base + kOffXch);      // [2][128]
-    uint8_t* prow = base + kOffP + r * 128;
-    const int s0 = 32 * half;                                    // this thread's steps: s0 .. s0 + 31
-    float m_run = -INFINITY, l_run = 0.f;                        // m_run: identical in both halves; l_run: this half's partial sum
+    const uint32_t scr_u = smem_u32(base + kOffScr) + (uint32_t)r * (kScrPitch * 4);      // this row of the f32 copy of S
+    const uint32_t p_u = smem_u32(base + kOffP) + (uint32_t)r * 128;                        // this row of the probability tile
+    const uint32_t xch_u = smem_u32(base + kOffXch);
+    const uint32_t lane4 = 4u * lane, lane2 = 2u * lane, swz = (uint32_t)(r & 7) << 4;
+    const int s0 = NS * half;                                    // this thread's steps: s0 .. s0 + NS - 1
+    float m_run = -INFINITY, l_run = 0.f;                        // exp2 domain; l_run: this thread's partial row sum
 #pragma unroll 1
     for (int t = 0; t < n_tiles; ++t) {
       const int bsel = t & 1, j0 = kKT * t;
       mbar_wait(&sg_full[bsel], (t >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // ---- S row -> the row's shared-memory copy (each half copies 32 columns), so that it can be read at a per-lane index
+      // ---- S row -> the row's shared-memory copy, so that it can be read at a per-lane index
       {
-        uint32_t v[32];
-        tmem_ld32(lane_addr + kColS + bsel * 64 + 32 * half, v);
 #pragma unroll
-        for (int x = 0; x < 8; ++x)
-          *reinterpret_cast<uint4*>(scr + 32 * half + 4 * x) = make_uint4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
+        for (int cc = 0; cc < NS / 32; ++cc) {
+          uint32_t v[32];
+          tmem_ld32(lane_addr + kColS + bsel * 64 + s0 + 32 * cc, v);
+#pragma unroll
+          for (int x = 0; x < 8; ++x) sts_v4(scr_u + 4 * (s0 + 32 * cc + 4 * x), v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
+        }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");      // both halves of the row copy are in place
+        if constexpr (NH == 2) asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");      // both halves of the row copy are in place
+        else __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[bsel]);
       }
       // ---- scores in the rotated key order c = (s + lane) mod 64; window column = 32 q + 63 - s (+ 64 once s + lane wraps)
       // window column w lives in ring slot (t + 2 - (w >> 6)) & 3 at column w & 63:  w < 64: block t+1,  < 128: block t,  else block t-1
-      float x[32];
+      float x[NS];
       float mt = -INFINITY;
-      {
-        const int wa = 32 * q + 32 - s0;               // first window column of the 32 loaded for the un-wrapped lanes
+      const bool full_tile = j0 + kKT <= T;            // warp-uniform: only the last tile of an utterance masks keys
+#pragma unroll
+      for (int cc = 0; cc < NS / 32; ++cc) {
+        const int sc0 = s0 + 32 * cc;                  // 0 or 32 (compile-time for NH == 1, warp-uniform for NH == 2)
+        const int wa = 32 * q + 32 - sc0;              // first window column of the 32 loaded for the un-wrapped lanes
         uint32_t ga[32], gb[32];
         tmem_ld32(lane_addr + kColG + (((t + 2 - (wa >> 6)) & 3) << 6) + (wa & 63), ga);
-        if (half == 1) {                               // lanes with s + lane >= 64 (only possible for s >= 33)
+        const bool wraps = sc0 == 32;                  // lanes with s + lane >= 64 exist only for s >= 33
+        if (wraps) {
           const int wb = wa + 64;
           tmem_ld32(lane_addr + kColG + (((t + 2 - (wb >> 6)) & 3) << 6) + (wb & 63), gb);
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int cw = s0 + j + lane;
-          const int c = cw & 63;
+          const uint32_t cw4 = lane4 + 4u * (uint32_t)(sc0 + j);          // 4 * (s + lane)
           float g = __uint_as_float(ga[31 - j]);
-          if (half == 1) g = cw >= 64 ? __uint_as_float(gb[31 - j]) : g;
-          const float sc = scr[c];
-          const float v = (j0 + c < T) ? (sc + g) * kScale : -INFINITY;
-          x[j] = v;
+          if (wraps) g = cw4 >= 256u ? __uint_as_float(gb[31 - j]) : g;
+          // (steps below 32 cannot wrap: base + immediate offset, no address arithmetic per element)
+          const float sc = wraps ? lds_f32(scr_u + (cw4 & 255u)) : lds_f32(scr_u + lane4 + 4u * (uint32_t)(sc0 + j));
+          const float v = (sc + g) * kScale2;
+          x[32 * cc + j] = v;
           mt = fmaxf(mt, v);
         }
       }
-      // ---- row maximum over both halves
-      xch[half * kQT + r] = mt;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-      mt = fmaxf(mt, xch[(half ^ 1) * kQT + r]);
-      // ---- online softmax with a lazy rescale of O (the running maximum only moves when it grows by more than kTau)
+      if (!full_tile) {                                // keys past the end of the utterance (last tile only)
+        mt = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          const int c = (int)(((lane4 + 4u * (uint32_t)(s0 + j)) & 255u) >> 2);
+          x[j] = j0 + c < T ? x[j] : -INFINITY;
+          mt = fmaxf(mt, x[j]);
+        }
+      }
+      if constexpr (NH == 2) {                         // row maximum over both halves
+        sts_f32(xch_u + 4 * (half * kQT + r), mt);
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        mt = fmaxf(mt, lds_f32(xch_u + 4 * ((half ^ 1) * kQT + r)));
+      }
+      // ---- online softmax with a lazy rescale of O (the running maximum only moves when it grows by more than kTau2)
       float alpha = 1.f;
-      const bool grow = mt > m_run + kTau;             // first tile: m_run = -inf -> true (key j0 is always valid: mt is finite)
-      if (grow) { alpha = __expf(m_run - mt); m_run = mt; }
+      const bool grow = mt > m_run + kTau2;            // first tile: m_run = -inf -> true (key j0 is always valid: mt is finite)
+      if (grow) { alpha = ex2f(m_run - mt); m_run = mt; }
       float rs = 0.f;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) { x[j] = __expf(x[j] - m_run); rs += x[j]; }
+      for (int j = 0; j < NS; ++j) { x[j] = ex2f(x[j] - m_run); rs += x[j]; }
       l_run = l_run * alpha + rs;
       if (t > 0) {
         mbar_wait(pv_done, (t - 1) & 1);               // PV_{t-1} complete: the P buffer is free and O is stable
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (__any_sync(0xffffffffu, grow)) {           // this half rescales O columns [64 half, 64 half + 64)
+        if (__any_sync(0xffffffffu, grow)) {
 #pragma unroll 1
-          for (int cc = 0; cc < 2; ++cc) {
+          for (int cc = 0; cc < OC / 32; ++cc) {
             uint32_t o[32];
-            tmem_ld32(lane_addr + kColO + 64 * half + 32 * cc, o);
+            tmem_ld32(lane_addr + kColO + OC * half + 32 * cc, o);
 #pragma unroll
             for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
-            tmem_st32(lane_addr + kColO + 64 * half + 32 * cc, o);
+            tmem_st32(lane_addr + kColO + OC * half + 32 * cc, o);
           }
         }
       }
-      // ---- P_t -> shared memory, bf16, K-major 128-byte-swizzled A tile [128 rows][64 keys]
+      // ---- P_t -> shared memory, bf16, K-major 128-byte-swizzled A tile [128 rows][64 keys]: byte (2 c) ^ ((r & 7) << 4) of the row
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int c = (s0 + j + lane) & 63;
-        *reinterpret_cast<__nv_bfloat16*>(prow + ((((c >> 3) ^ (r & 7)) << 4) | ((c & 7) << 1))) = __float2bfloat16_rn(x[j]);
+      for (int j = 0; j < NS; ++j) {
+        const uint32_t c2 = (lane2 + 2u * (uint32_t)(s0 + j)) & 127u;
+        sts_b16(p_u + (c2 ^ swz), __bfloat16_as_ushort(__float2bfloat16_rn(x[j])));
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core's smem reads
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }
-    // ---- row sums of the two halves, then the context rows -> bf16 operand of linear_out (each half stores 64 of the 128 columns)
-    xch[(2 + half) * kQT + r] = l_run;
-    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-    l_run += xch[(2 + (half ^ 1)) * kQT + r];
+    if constexpr (NH == 2) {                           // row sums of the two halves
+      sts_f32(xch_u + 4 * ((2 + half) * kQT + r), l_run);
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      l_run += lds_f32(xch_u + 4 * ((2 + (half ^ 1)) * kQT + r));
+    }
+    // ---- context rows -> bf16 operand of linear_out
     mbar_wait(pv_done, (n_tiles - 1) & 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
     const bool ok = i0 + r < T;
-    __nv_bfloat16* dst = a.ctx + (size_t)(row0 + i0 + r) * a.ldc + h * kDHead + 64 * half;
+    __nv_bfloat16* dst = a.ctx + (size_t)(row0 + i0 + r) * a.ldc + h * kDHead + OC * half;
 #pragma unroll 1
-    for (int cc = 0; cc < 2; ++cc) {
+    for (int cc = 0; cc < OC / 32; ++cc) {
       uint32_t o[32];
-      tmem_ld32(lane_addr + kColO + 64 * half + 32 * cc, o);
+      tmem_ld32(lane_addr + kColO + OC * half + 32 * cc, o);
       if (ok) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -425,13 +483,19 @@ void launch_lf_attention_tc(const BatchDev& b, const LfTcArgs& a, int max_T, cud
   if (b.B <= 0 || max_T <= 0) return;
   static bool attr = false;
   if (!attr) {
-    PKB_CUDA(cudaFuncSetAttribute(lf_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTc));
+    PKB_CUDA(cudaFuncSetAttribute(lf_attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTc));
+    PKB_CUDA(cudaFuncSetAttribute(lf_attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTc));
     attr = true;
   }
+  // PARAKEET_B200_LF_SPLIT: softmax warpgroups per CTA (1 or 2; A/B measurement knob)
+  static const int nh = [] { const char* v = getenv("PARAKEET_B200_LF_SPLIT"); return v ? atoi(v) : 1; }();
   const dim3 grid((max_T + kQT - 1) / kQT, kHeads, b.B);
-  launch_k(lf_attention_tc_kernel, grid, dim3(kThreadsTc), kSmemTc, st, *reinterpret_cast<const CUtensorMap*>(a.map_q),
-           *reinterpret_cast<const CUtensorMap*>(a.map_k), *reinterpret_cast<const CUtensorMap*>(a.map_pos),
-           *reinterpret_cast<const CUtensorMap*>(a.map_vt), b, a);
+  const CUtensorMap& mq = *reinterpret_cast<const CUtensorMap*>(a.map_q);
+  const CUtensorMap& mk = *reinterpret_cast<const CUtensorMap*>(a.map_k);
+  const CUtensorMap& mp = *reinterpret_cast<const CUtensorMap*>(a.map_pos);
+  const CUtensorMap& mv = *reinterpret_cast<const CUtensorMap*>(a.map_vt);
+  if (nh == 2) launch_k(lf_attention_tc_kernel<2>, grid, dim3(384), kSmemTc, st, mq, mk, mp, mv, b, a);
+  else launch_k(lf_attention_tc_kernel<1>, grid, dim3(256), kSmemTc, st, mq, mk, mp, mv, b, a);
   PKB_CUDA(cudaGetLastError());
 }
 
