@@ -255,7 +255,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int splits = MODE == EPI_PARTIAL_F32 ? g.epi.splits : 1;      // work unit = (tile, k-split), split fastest
   // bf16 rows (plain operand plane / bf16 partial sums) with 16-byte aligned 16-column groups: registers -> global directly
   constexpr bool kDirectMode = MODE == EPI_ACT || MODE == EPI_SILU_ACT || MODE == EPI_BIAS_RELU_ACT || MODE == EPI_PARTIAL_F32 ||
-                               MODE == EPI_GLU_F32;
+                               MODE == EPI_GLU_F32 || MODE == EPI_QKV;
   const bool direct = kDirectMode && g.epi.direct_bf16 != 0;
 
   if (warp == 0 && lane == 0) {
@@ -358,8 +358,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (direct && m_d < M) {
         if constexpr (MODE == EPI_PARTIAL_F32)
           drow = reinterpret_cast<__nv_bfloat16*>(g.epi.out_f32) + (size_t)epilogue_row_ctx<MODE>(g.epi, m_d, sp) * g.epi.ldo;
+        else if constexpr (MODE == EPI_QKV)
+          drow = g.epi.q_bf16 + (size_t)m_d * kDModel;
         else
           drow = g.epi.out_act + (size_t)m_d * g.epi.lda_out;
+      }
+      if constexpr (MODE == EPI_QKV) {
+        if (direct) {
+          // bf16 streaming mode: q leaves as the two biased planes, k and v go to the head-major rings, all straight from the TMEM-load
+          // registers -- a lane keeps its accumulator row, so each 32-column chunk is 64 contiguous bytes of one destination row
+          // (the staged path scattered 8-byte pieces through the smem transpose: 46 - 50 us for this launch at 1024 streams)
+          const int ctxd = m_d < M ? epilogue_row_ctx<MODE>(g.epi, m_d, sp) : 0;
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(taddr + (uint32_t)c0, v);
+            if (c0 + 32 == BN / 2) {
+              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            }
+            const int ncol = n0 + half * (BN / 2) + c0;
+            if (drow == nullptr || ncol >= g.N) continue;
+            if (ncol < kDModel) {
+              uint4* du = reinterpret_cast<uint4*>(drow + ncol);
+              uint4* dv = reinterpret_cast<uint4*>(drow + g.epi.q_plane + ncol);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 u0 = *reinterpret_cast<const float4*>(g.epi.bias_u + ncol + 8 * j), u1 = *reinterpret_cast<const float4*>(g.epi.bias_u + ncol + 8 * j + 4);
+                const float4 w0 = *reinterpret_cast<const float4*>(g.epi.bias_v + ncol + 8 * j), w1 = *reinterpret_cast<const float4*>(g.epi.bias_v + ncol + 8 * j + 4);
+                const float f0 = __uint_as_float(v[8 * j]), f1 = __uint_as_float(v[8 * j + 1]), f2 = __uint_as_float(v[8 * j + 2]), f3 = __uint_as_float(v[8 * j + 3]);
+                const float f4 = __uint_as_float(v[8 * j + 4]), f5 = __uint_as_float(v[8 * j + 5]), f6 = __uint_as_float(v[8 * j + 6]), f7 = __uint_as_float(v[8 * j + 7]);
+                const uint2 a0 = pack4_bf16(f0 + u0.x, f1 + u0.y, f2 + u0.z, f3 + u0.w), a1 = pack4_bf16(f4 + u1.x, f5 + u1.y, f6 + u1.z, f7 + u1.w);
+                const uint2 b0 = pack4_bf16(f0 + w0.x, f1 + w0.y, f2 + w0.z, f3 + w0.w), b1 = pack4_bf16(f4 + w1.x, f5 + w1.y, f6 + w1.z, f7 + w1.w);
+                du[j] = make_uint4(a0.x, a0.y, a1.x, a1.y);
+                dv[j] = make_uint4(b0.x, b0.y, b1.x, b1.y);
+              }
+            } else {
+              const int c = (ncol - kDModel) & (kDModel - 1), h = c >> 7, d = c & 127;
+              __nv_bfloat16* ring = reinterpret_cast<__nv_bfloat16*>(ncol < 2 * kDModel ? g.epi.kring : g.epi.vring);
+              uint4* dst = reinterpret_cast<uint4*>(ring + ((size_t)ctxd + (size_t)h * kRingCap) * kDHead + d);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint2 a0 = pack4_bf16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1]), __uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                const uint2 a1 = pack4_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]), __uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+                dst[j] = make_uint4(a0.x, a0.y, a1.x, a1.y);
+              }
+            }
+          }
+          continue;
+        }
       }
       if constexpr (MODE == EPI_GLU_F32) {
         if (direct) {
@@ -844,6 +892,10 @@ void gemm_tc(const GemmArgs& g_in, const TensorMap& map_a, const TensorMap& map_
     const EpiParams& e = g.epi;
     bool ok = allow && g.N % 16 == 0 && e.n_off % 8 == 0 && g.out_col_stride % 8 == 0;
     if (e.mode == EPI_PARTIAL_F32) ok = ok && e.part_bf16 && e.ldo % 8 == 0 && ((uintptr_t)e.out_f32 & 15) == 0 && g.N % 32 == 0;
+    else if (e.mode == EPI_QKV)
+      ok = ok && e.k_natural && !e.kv_f32 && e.q_bf16 != nullptr && e.n_off == 0 && g.batch == 1 && g.N == 3 * kDModel &&
+           ((uintptr_t)e.q_bf16 & 15) == 0 && ((uintptr_t)e.kring & 15) == 0 && ((uintptr_t)e.vring & 15) == 0 && (e.q_plane & 7) == 0 &&
+           ((uintptr_t)e.bias_u & 15) == 0 && ((uintptr_t)e.bias_v & 15) == 0;
     else if (e.mode == EPI_GLU_F32)
       ok = ok && e.out_act != nullptr && g.N % 32 == 0 && e.n_off == 0 && g.batch == 1 && e.lda_out % 8 == 0 && ((uintptr_t)e.out_act & 15) == 0;
     else if (e.mode == EPI_ACT || e.mode == EPI_SILU_ACT || e.mode == EPI_BIAS_RELU_ACT)

@@ -72,24 +72,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   }
 }
-// waits of the two single-thread roles (TMA producer, MMA issuer): back off between polls so that the spin does not take issue
-// slots from the softmax warps that share their schedulers (the first version spent 18 % of its issued instructions in these loops)
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
-  uint32_t ok = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (ok) break;
-    __nanosleep(40);
-  }
-}
 // explicit shared-window accesses with 32-bit addresses (through generic pointers the compiler emitted LD.E / ST.E with 64-bit
 // address arithmetic for every element of the rotated S reads and P writes: a quarter of the kernel's instructions)
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
@@ -231,13 +213,15 @@ lf_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + kOffBar);
   uint64_t* q_full = bars;            // prologue operands landed
-  uint64_t* st_full = bars + 1;       // [2] stage t: K_t, Pblk_{t+1}, V^T_t landed
-  uint64_t* st_empty = bars + 3;      // [2] PV_t has read the stage
+  uint64_t* kp_full = bars + 1;       // [2] stage t: K_t and table block t+1 landed
+  uint64_t* kp_empty = bars + 3;      // [2] S_t and position block t+1 have been computed: their operands are free (long before PV_t)
   uint64_t* sg_full = bars + 5;       // [2] S_t (buffer t & 1) and position block t+1 are in TMEM
   uint64_t* s_empty = bars + 7;       // [2] the softmax warps have copied S out of buffer t & 1
   uint64_t* p_full = bars + 9;        // P_t is in shared memory (and O has been rescaled)
   uint64_t* pv_done = bars + 10;      // PV_t has completed: O is readable, the P buffer is free
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* v_full = bars + 11;       // [2] V^T_t landed
+  uint64_t* v_empty = bars + 13;      // [2] PV_t has read V^T_t
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -246,7 +230,10 @@ lf_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_pos) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_vt) : "memory");
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 1); mbar_init(&sg_full[s], 1); mbar_init(&s_empty[s], 4 * NH); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kp_full[s], 1); mbar_init(&kp_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+      mbar_init(&sg_full[s], 1); mbar_init(&s_empty[s], 4 * NH);
+    }
     mbar_init(p_full, 4 * NH);
     mbar_init(pv_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -282,17 +269,22 @@ lf_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       tma_load_2d(base + kOffP + kSubB, &map_pos, q_full, col_h + 64, prow_m1);
       tma_load_2d(base + kOffScr, &map_pos, q_full, col_h, prow_0);
       tma_load_2d(base + kOffScr + kSubB, &map_pos, q_full, col_h + 64, prow_0);
+      // K / table-block operands are released as soon as S_t and its position block have been computed, V^T_t only when PV_t has
+      // run: two rings, so that the loads of tile t+2 start ~1.5 tiles before they are needed instead of right behind PV_t
       for (int t = 0; t < n_tiles; ++t) {
         const int s = t & 1;
         uint8_t* st = base + kOffStage + s * kStageBytes;
-        mbar_wait_backoff(&st_empty[s], ((t >> 1) & 1) ^ 1);
-        mbar_expect_tx(&st_full[s], kStageBytes);
-        tma_load_2d(st + kStageK, &map_k, &st_full[s], kDModel + col_h, row0 + kKT * t);
-        tma_load_2d(st + kStageK + kSubB, &map_k, &st_full[s], kDModel + col_h + 64, row0 + kKT * t);
+        const uint32_t ph = ((t >> 1) & 1) ^ 1;
+        mbar_wait(&kp_empty[s], ph);
+        mbar_expect_tx(&kp_full[s], 4 * kSubB);
+        tma_load_2d(st + kStageK, &map_k, &kp_full[s], kDModel + col_h, row0 + kKT * t);
+        tma_load_2d(st + kStageK + kSubB, &map_k, &kp_full[s], kDModel + col_h + 64, row0 + kKT * t);
         const int prow = i0 - kKT * (t + 1) + a.Tm;      // block t + 1
-        tma_load_2d(st + kStageP, &map_pos, &st_full[s], col_h, prow);
-        tma_load_2d(st + kStageP + kSubB, &map_pos, &st_full[s], col_h + 64, prow);
-        tma_load_2d(st + kStageV, &map_vt, &st_full[s], voff + kKT * t, col_h);
+        tma_load_2d(st + kStageP, &map_pos, &kp_full[s], col_h, prow);
+        tma_load_2d(st + kStageP + kSubB, &map_pos, &kp_full[s], col_h + 64, prow);
+        mbar_wait(&v_empty[s], ph);
+        mbar_expect_tx(&v_full[s], kSubA);
+        tma_load_2d(st + kStageV, &map_vt, &v_full[s], voff + kKT * t, col_h);
       }
     }
   } else if (warp == 1) {
@@ -301,7 +293,7 @@ lf_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       const uint32_t uQu = smem_u32(base + kOffQu), uQv = smem_u32(base + kOffQv), uP = smem_u32(base + kOffP), uScr = smem_u32(base + kOffScr);
       const uint32_t uSt = smem_u32(base + kOffStage);
       mbar_wait(q_full, 0);
-      mbar_wait(&st_full[0], 0);
+      mbar_wait(&kp_full[0], 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       // prologue: position blocks -1, 0 (ring slots 0, 1), S_0, position block 1 (slot 2)
       issue_k128(tmem_base + kColG + 0 * 64, uQv, kSubA, uP, kSubB, IDesc<64>::value);
@@ -309,24 +301,27 @@ lf_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       issue_k128(tmem_base + kColS, uQu, kSubA, uSt + kStageK, kSubB, IDesc<64>::value);
       issue_k128(tmem_base + kColG + 2 * 64, uQv, kSubA, uSt + kStageP, kSubB, IDesc<64>::value);
       umma_commit(&sg_full[0]);
+      umma_commit(&kp_empty[0]);
       for (int t = 0; t < n_tiles; ++t) {
         if (t + 1 < n_tiles) {
           const int s1 = (t + 1) & 1;
           const uint32_t st1 = uSt + s1 * kStageBytes;
-          mbar_wait_backoff(&st_full[s1], ((t + 1) >> 1) & 1);
-          mbar_wait_backoff(&s_empty[s1], (((t + 1) >> 1) & 1) ^ 1);
+          mbar_wait(&kp_full[s1], ((t + 1) >> 1) & 1);
+          mbar_wait(&s_empty[s1], (((t + 1) >> 1) & 1) ^ 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           issue_k128(tmem_base + kColS + s1 * 64, uQu, kSubA, st1 + kStageK, kSubB, IDesc<64>::value);                 // S_{t+1}
           issue_k128(tmem_base + kColG + ((t + 3) & 3) * 64, uQv, kSubA, st1 + kStageP, kSubB, IDesc<64>::value);      // block t + 2
           umma_commit(&sg_full[s1]);
+          umma_commit(&kp_empty[s1]);
         }
-        mbar_wait_backoff(p_full, t & 1);
+        mbar_wait(&v_full[t & 1], (t >> 1) & 1);
+        mbar_wait(p_full, t & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t vt = uSt + (t & 1) * kStageBytes + kStageV;
 #pragma unroll
         for (int k = 0; k < 4; ++k)      // O += P_t V_t : K = 64 keys
           umma(tmem_base + kColO, make_desc(uP) + (uint64_t)(2 * k), make_desc(vt) + (uint64_t)(2 * k), IDesc<128>::value, (t | k) != 0 ? 1u : 0u);
-        umma_commit(&st_empty[t & 1]);
+        umma_commit(&v_empty[t & 1]);
         umma_commit(pv_done);
       }
     }
