@@ -303,6 +303,7 @@ struct Engine::Impl {
   FeatPush* fpush_host = nullptr;
   int fpush_cap = 0, fpush_n = 0, fpush_max_T = 0;
   bool fstage_inflight = false;                // flushed to the device, host area not yet known to be consumed
+  bool frontend_inflight = false;              // frontend_pass() queued copies from its pinned descriptors, no synchronisation since
   // whole-step CUDA graphs, one per step shape (see Engine::step_graph)
   std::map<std::array<int, 6>, std::unique_ptr<Engine::StepGraph>> graphs;
   std::map<std::array<int, 6>, int> graph_seen;
@@ -1068,6 +1069,7 @@ void Engine::set_feature_norm_running(int sid, bool on) {
 // audio -> feature rings for every stream in audio mode (one launch); chunks are then cut by the schedule in step()
 void Engine::frontend_pass() {
   Impl& im = *im_;
+  if (im.frontend_inflight) { PKB_CUDA(cudaStreamSynchronize(st_)); im.frontend_inflight = false; }      // (only after a failed pass)
   // 1. top up device buffers from host overflow FIFOs (queue_audio path)
   for (int sid = 0; sid < (int)streams_.size(); ++sid) {
     Stream& s = *streams_[sid];
@@ -1124,9 +1126,9 @@ void Engine::frontend_pass() {
     s.dev_fill -= d.second * 160;
     s.frames_written += d.second;
   }
-  // segs_host / fprefix_host are rewritten only by the next frontend_pass, which run_batch's final sync precedes;
-  // when no chunk follows, sync here
-  PKB_CUDA(cudaStreamSynchronize(st_));
+  // segs_host / fprefix_host are rewritten only by the next frontend_pass; the batched pass that normally follows ends with a stream
+  // synchronisation, and step() synchronises itself when no chunk was ready (no host round trip in the middle of a step)
+  im.frontend_inflight = true;
 }
 
 // ------------------------------------------------------------------------------------------------ batching
@@ -1656,6 +1658,7 @@ void Engine::run_batch(const std::vector<Entry>& entries, float* enc_out_host) {
     PKB_CUDA(cudaMemcpyAsync(enc_out_host, im.enc_out, (size_t)b.B * kDModel * b.max_tenc * sizeof(float), cudaMemcpyDeviceToHost, st_));
   }
   PKB_CUDA(cudaStreamSynchronize(st_));
+  im.frontend_inflight = false;
   if (im.fstage_inflight) { im.fstage_inflight = false; im.fstage_used = 0; im.fpush_n = 0; im.fpush_max_T = 0; }
   if (im.profile) profile_collect();
   const int* h = im.batch_ints_host;
@@ -1743,6 +1746,10 @@ int Engine::step() {
     rows += Tq; t3 += T3; t2 += T2;
   }
   flush();
+  if (im.frontend_inflight) {      // no batched pass ran (or its last one did not follow the frontend): settle the frontend's copies
+    PKB_CUDA(cudaStreamSynchronize(st_));
+    im.frontend_inflight = false;
+  }
   return total;
 }
 

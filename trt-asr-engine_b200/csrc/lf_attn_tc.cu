@@ -72,18 +72,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   }
 }
-// explicit shared-window accesses with 32-bit addresses (through generic pointers the compiler emitted LD.E / ST.E with 64-bit
-// address arithmetic for every element of the rotated S reads and P writes: a quarter of the kernel's instructions)
-__device__ __forceinline__ float lds_f32(uint32_t addr) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
-__device__ __forceinline__ void sts_b16(uint32_t addr, uint16_t v) { asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(v) : "memory"); }
-__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
 __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -210,7 +198,9 @@ __global__ void __launch_bounds__(128 + 128 * NH, 1)
 lf_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                        const __grid_constant__ CUtensorMap map_pos, const __grid_constant__ CUtensorMap map_vt, BatchDev b, LfTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by OFFSET (a pointer rebuilt from an integer would be a generic pointer: every access through it became
+  // LD.E / ST.E with 64-bit address arithmetic in the first version)
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + kOffBar);
   uint64_t* q_full = bars;            // prologue operands landed
   uint64_t* kp_full = bars + 1;       // [2] stage t: K_t and table block t+1 landed
@@ -331,10 +321,10 @@ lf_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     constexpr int OC = 128 / NH;                                 // O columns this thread rescales / stores
     const int q = (warp - 4) & 3, half = (warp - 4) >> 2, r = 32 * q + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16);
-    const uint32_t scr_u = smem_u32(base + kOffScr) + (uint32_t)r * (kScrPitch * 4);      // this row of the f32 copy of S
-    const uint32_t p_u = smem_u32(base + kOffP) + (uint32_t)r * 128;                        // this row of the probability tile
-    const uint32_t xch_u = smem_u32(base + kOffXch);
-    const uint32_t lane4 = 4u * lane, lane2 = 2u * lane, swz = (uint32_t)(r & 7) << 4;
+    float* scr = reinterpret_cast<float*>(base + kOffScr) + r * kScrPitch;                  // this row of the f32 copy of S
+    uint8_t* p_row = base + kOffP + r * 128;                                                // this row of the probability tile
+    float* xch = reinterpret_cast<float*>(base + kOffXch);
+    const uint32_t lane2 = 2u * lane, swz = (uint32_t)(r & 7) << 4;
     const int s0 = NS * half;                                    // this thread's steps: s0 .. s0 + NS - 1
     float m_run = -INFINITY, l_run = 0.f;                        // exp2 domain; l_run: this thread's partial row sum
 #pragma unroll 1
@@ -349,7 +339,8 @@ lf_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
           uint32_t v[32];
           tmem_ld32(lane_addr + kColS + bsel * 64 + s0 + 32 * cc, v);
 #pragma unroll
-          for (int x = 0; x < 8; ++x) sts_v4(scr_u + 4 * (s0 + 32 * cc + 4 * x), v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
+          for (int x = 0; x < 8; ++x)
+            *reinterpret_cast<uint4*>(scr + s0 + 32 * cc + 4 * x) = make_uint4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         if constexpr (NH == 2) asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");      // both halves of the row copy are in place
@@ -374,11 +365,11 @@ lf_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const uint32_t cw4 = lane4 + 4u * (uint32_t)(sc0 + j);          // 4 * (s + lane)
+          const int cw = lane + sc0 + j;                                   // s + lane
           float g = __uint_as_float(ga[31 - j]);
-          if (wraps) g = cw4 >= 256u ? __uint_as_float(gb[31 - j]) : g;
+          if (wraps) g = cw >= 64 ? __uint_as_float(gb[31 - j]) : g;
           // (steps below 32 cannot wrap: base + immediate offset, no address arithmetic per element)
-          const float sc = wraps ? lds_f32(scr_u + (cw4 & 255u)) : lds_f32(scr_u + lane4 + 4u * (uint32_t)(sc0 + j));
+          const float sc = wraps ? scr[cw & 63] : scr[cw];
           const float v = (sc + g) * kScale2;
           x[32 * cc + j] = v;
           mt = fmaxf(mt, v);
@@ -388,24 +379,24 @@ lf_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         mt = -INFINITY;
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
-          const int c = (int)(((lane4 + 4u * (uint32_t)(s0 + j)) & 255u) >> 2);
+          const int c = (lane + s0 + j) & 63;
           x[j] = j0 + c < T ? x[j] : -INFINITY;
           mt = fmaxf(mt, x[j]);
         }
       }
       if constexpr (NH == 2) {                         // row maximum over both halves
-        sts_f32(xch_u + 4 * (half * kQT + r), mt);
+        xch[half * kQT + r] = mt;
         asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-        mt = fmaxf(mt, lds_f32(xch_u + 4 * ((half ^ 1) * kQT + r)));
+        mt = fmaxf(mt, xch[(half ^ 1) * kQT + r]);
       }
       // ---- online softmax with a lazy rescale of O (the running maximum only moves when it grows by more than kTau2)
       float alpha = 1.f;
       const bool grow = mt > m_run + kTau2;            // first tile: m_run = -inf -> true (key j0 is always valid: mt is finite)
       if (grow) { alpha = ex2f(m_run - mt); m_run = mt; }
-      float rs = 0.f;
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};             // four partial sums: no 64-deep dependent add chain
 #pragma unroll
-      for (int j = 0; j < NS; ++j) { x[j] = ex2f(x[j] - m_run); rs += x[j]; }
-      l_run = l_run * alpha + rs;
+      for (int j = 0; j < NS; ++j) { x[j] = ex2f(x[j] - m_run); rs4[j & 3] += x[j]; }
+      l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
       if (t > 0) {
         mbar_wait(pv_done, (t - 1) & 1);               // PV_{t-1} complete: the P buffer is free and O is stable
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -424,7 +415,7 @@ lf_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
         const uint32_t c2 = (lane2 + 2u * (uint32_t)(s0 + j)) & 127u;
-        sts_b16(p_u + (c2 ^ swz), __bfloat16_as_ushort(__float2bfloat16_rn(x[j])));
+        *reinterpret_cast<__nv_bfloat16*>(p_row + (c2 ^ swz)) = __float2bfloat16_rn(x[j]);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core's smem reads
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -432,9 +423,9 @@ lf_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       if (lane == 0) mbar_arrive(p_full);
     }
     if constexpr (NH == 2) {                           // row sums of the two halves
-      sts_f32(xch_u + 4 * ((2 + half) * kQT + r), l_run);
+      xch[(2 + half) * kQT + r] = l_run;
       asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-      l_run += lds_f32(xch_u + 4 * ((2 + (half ^ 1)) * kQT + r));
+      l_run += xch[(2 + (half ^ 1)) * kQT + r];
     }
     // ---- context rows -> bf16 operand of linear_out
     mbar_wait(pv_done, (n_tiles - 1) & 1);
