@@ -121,6 +121,34 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// two 32-column loads in flight behind ONE wait (each tcgen05.ld + wait pair exposes the full TMEM read latency)
+__device__ __forceinline__ void tmem_ld32x2(uint32_t taddr_a, uint32_t taddr_b, uint32_t (&a)[32], uint32_t (&b)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%64];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%65];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]), "=r"(a[16]), "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]), "=r"(a[24]), "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31]),
+        "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]), "=r"(b[8]), "=r"(b[9]), "=r"(b[10]), "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]), "=r"(b[15]), "=r"(b[16]), "=r"(b[17]), "=r"(b[18]), "=r"(b[19]), "=r"(b[20]), "=r"(b[21]), "=r"(b[22]), "=r"(b[23]), "=r"(b[24]), "=r"(b[25]), "=r"(b[26]), "=r"(b[27]), "=r"(b[28]), "=r"(b[29]), "=r"(b[30]), "=r"(b[31])
+      : "r"(taddr_a), "r"(taddr_b)
+      : "memory");
+}
+// polling with a suspend-time hint: the waiting thread is parked by the hardware until the phase completes (or the hint expires) instead
+// of spinning through issue slots that the softmax warps on the same scheduler need
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  if (hint_ns == 0) { mbar_wait(bar, parity); return; }
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+        : "memory");
+  }
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
@@ -265,14 +293,14 @@ lf_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         const int s = t & 1;
         uint8_t* st = base + kOffStage + s * kStageBytes;
         const uint32_t ph = ((t >> 1) & 1) ^ 1;
-        mbar_wait(&kp_empty[s], ph);
+        mbar_wait_hint(&kp_empty[s], ph, a.wait_hint_ns);
         mbar_expect_tx(&kp_full[s], 4 * kSubB);
         tma_load_2d(st + kStageK, &map_k, &kp_full[s], kDModel + col_h, row0 + kKT * t);
         tma_load_2d(st + kStageK + kSubB, &map_k, &kp_full[s], kDModel + col_h + 64, row0 + kKT * t);
         const int prow = i0 - kKT * (t + 1) + a.Tm;      // block t + 1
         tma_load_2d(st + kStageP, &map_pos, &kp_full[s], col_h, prow);
         tma_load_2d(st + kStageP + kSubB, &map_pos, &kp_full[s], col_h + 64, prow);
-        mbar_wait(&v_empty[s], ph);
+        mbar_wait_hint(&v_empty[s], ph, a.wait_hint_ns);
         mbar_expect_tx(&v_full[s], kSubA);
         tma_load_2d(st + kStageV, &map_vt, &v_full[s], voff + kKT * t, col_h);
       }
@@ -296,16 +324,16 @@ lf_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         if (t + 1 < n_tiles) {
           const int s1 = (t + 1) & 1;
           const uint32_t st1 = uSt + s1 * kStageBytes;
-          mbar_wait(&kp_full[s1], ((t + 1) >> 1) & 1);
-          mbar_wait(&s_empty[s1], (((t + 1) >> 1) & 1) ^ 1);
+          mbar_wait_hint(&kp_full[s1], ((t + 1) >> 1) & 1, a.wait_hint_ns);
+          mbar_wait_hint(&s_empty[s1], (((t + 1) >> 1) & 1) ^ 1, a.wait_hint_ns);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           issue_k128(tmem_base + kColS + s1 * 64, uQu, kSubA, st1 + kStageK, kSubB, IDesc<64>::value);                 // S_{t+1}
           issue_k128(tmem_base + kColG + ((t + 3) & 3) * 64, uQv, kSubA, st1 + kStageP, kSubB, IDesc<64>::value);      // block t + 2
           umma_commit(&sg_full[s1]);
           umma_commit(&kp_empty[s1]);
         }
-        mbar_wait(&v_full[t & 1], (t >> 1) & 1);
-        mbar_wait(p_full, t & 1);
+        mbar_wait_hint(&v_full[t & 1], (t >> 1) & 1, a.wait_hint_ns);
+        mbar_wait_hint(p_full, t & 1, a.wait_hint_ns);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t vt = uSt + (t & 1) * kStageBytes + kStageV;
 #pragma unroll
@@ -334,13 +362,20 @@ lf_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       // ---- S row -> the row's shared-memory copy, so that it can be read at a per-lane index
       {
+        if constexpr (NH == 1) {
+          uint32_t v[32], w[32];
+          tmem_ld32x2(lane_addr + kColS + bsel * 64, lane_addr + kColS + bsel * 64 + 32, v, w);
 #pragma unroll
-        for (int cc = 0; cc < NS / 32; ++cc) {
+          for (int x = 0; x < 8; ++x) {
+            *reinterpret_cast<uint4*>(scr + 4 * x) = make_uint4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
+            *reinterpret_cast<uint4*>(scr + 32 + 4 * x) = make_uint4(w[4 * x], w[4 * x + 1], w[4 * x + 2], w[4 * x + 3]);
+          }
+        } else {
           uint32_t v[32];
-          tmem_ld32(lane_addr + kColS + bsel * 64 + s0 + 32 * cc, v);
+          tmem_ld32(lane_addr + kColS + bsel * 64 + s0, v);
 #pragma unroll
           for (int x = 0; x < 8; ++x)
-            *reinterpret_cast<uint4*>(scr + s0 + 32 * cc + 4 * x) = make_uint4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
+            *reinterpret_cast<uint4*>(scr + s0 + 4 * x) = make_uint4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         if constexpr (NH == 2) asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");      // both halves of the row copy are in place
@@ -357,11 +392,13 @@ lf_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         const int sc0 = s0 + 32 * cc;                  // 0 or 32 (compile-time for NH == 1, warp-uniform for NH == 2)
         const int wa = 32 * q + 32 - sc0;              // first window column of the 32 loaded for the un-wrapped lanes
         uint32_t ga[32], gb[32];
-        tmem_ld32(lane_addr + kColG + (((t + 2 - (wa >> 6)) & 3) << 6) + (wa & 63), ga);
         const bool wraps = sc0 == 32;                  // lanes with s + lane >= 64 exist only for s >= 33
         if (wraps) {
           const int wb = wa + 64;
-          tmem_ld32(lane_addr + kColG + (((t + 2 - (wb >> 6)) & 3) << 6) + (wb & 63), gb);
+          tmem_ld32x2(lane_addr + kColG + (((t + 2 - (wa >> 6)) & 3) << 6) + (wa & 63),
+                      lane_addr + kColG + (((t + 2 - (wb >> 6)) & 3) << 6) + (wb & 63), ga, gb);
+        } else {
+          tmem_ld32(lane_addr + kColG + (((t + 2 - (wa >> 6)) & 3) << 6) + (wa & 63), ga);
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -475,13 +512,16 @@ void launch_lf_attention_tc(const BatchDev& b, const LfTcArgs& a, int max_T, cud
   }
   // PARAKEET_B200_LF_SPLIT: softmax warpgroups per CTA (1 or 2; A/B measurement knob)
   static const int nh = [] { const char* v = getenv("PARAKEET_B200_LF_SPLIT"); return v ? atoi(v) : 1; }();
+  static const int hint = [] { const char* v = getenv("PARAKEET_B200_LF_HINT_NS"); return v ? atoi(v) : 0; }();
+  LfTcArgs a2 = a;
+  a2.wait_hint_ns = hint;
   const dim3 grid((max_T + kQT - 1) / kQT, kHeads, b.B);
   const CUtensorMap& mq = *reinterpret_cast<const CUtensorMap*>(a.map_q);
   const CUtensorMap& mk = *reinterpret_cast<const CUtensorMap*>(a.map_k);
   const CUtensorMap& mp = *reinterpret_cast<const CUtensorMap*>(a.map_pos);
   const CUtensorMap& mv = *reinterpret_cast<const CUtensorMap*>(a.map_vt);
-  if (nh == 2) launch_k(lf_attention_tc_kernel<2>, grid, dim3(384), kSmemTc, st, mq, mk, mp, mv, b, a);
-  else launch_k(lf_attention_tc_kernel<1>, grid, dim3(256), kSmemTc, st, mq, mk, mp, mv, b, a);
+  if (nh == 2) launch_k(lf_attention_tc_kernel<2>, grid, dim3(384), kSmemTc, st, mq, mk, mp, mv, b, a2);
+  else launch_k(lf_attention_tc_kernel<1>, grid, dim3(256), kSmemTc, st, mq, mk, mp, mv, b, a2);
   PKB_CUDA(cudaGetLastError());
 }
 

@@ -55,6 +55,7 @@ struct LfTcArgs {
   const void* map_k = nullptr;
   const void* map_pos = nullptr;
   const void* map_vt = nullptr;
+  int wait_hint_ns = 0;                    // > 0: suspend-time hint of the single-thread roles' mbarrier polls (set by the launcher)
 };
 void launch_lf_prep(const BatchDev& b, const LfTcArgs& a, cudaStream_t st);
 void launch_lf_attention_tc(const BatchDev& b, const LfTcArgs& a, int max_T, cudaStream_t st);
