@@ -308,6 +308,9 @@ struct Engine::Impl {
   std::map<std::array<int, 6>, std::unique_ptr<Engine::StepGraph>> graphs;
   std::map<std::array<int, 6>, int> graph_seen;
   int graph_mode = 1, graph_pdl = 1;
+  cudaGraph_t lf_loop_graph = nullptr;         // decode-loop graph of the whole-utterance call in flight (run_decode_loop_graph)
+  cudaGraphExec_t lf_loop_exec = nullptr;
+  int lf_loop_body_launches = 0, lf_loop_prof_idx = -1, lf_loop_B = 0;
   double loop_ms = 0.0, loop_bytes = 0.0;      // decode loops run inside step graphs since the last decode_loop_stats(reset)
   long long loop_passes = 0, loop_count = 0;
   int* meta2 = nullptr;                        // device [2]: (slot, head) of a single-stream import / export
@@ -359,6 +362,7 @@ Engine::~Engine() {
       cudaGraphExecDestroy(kv.second->exec); cudaGraphDestroy(kv.second->graph);
       cudaEventDestroy(kv.second->ev_loop0); cudaEventDestroy(kv.second->ev_loop1);
     }
+    if (im_->lf_loop_exec) { cudaGraphExecDestroy(im_->lf_loop_exec); cudaGraphDestroy(im_->lf_loop_graph); }
     for (auto& e : im_->user_events) cudaEventDestroy(e);
     for (auto& e : im_->dec_events) if (e) cudaEventDestroy(e);
     for (auto& pr : im_->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -1462,12 +1466,82 @@ void Engine::decode_iteration(const BatchDev& b, const DecodeDev& d, int host_po
   run_predictor_pass(d);
 }
 
+// The decode loop of a whole-utterance call as a one-node CUDA graph: a device-side WHILE around one decode iteration (tens of
+// thousands of passes for an hour of audio: launched one by one each pass costs ~10 launches and a host poll).  Built per call
+// (capture + instantiation ~1 ms), destroyed by the caller after the stream has been synchronised.  Returns false (nothing
+// enqueued) when graphs are off or the build fails.
+bool Engine::run_decode_loop_graph(const BatchDev& b, DecodeDev d) {
+  Impl& im = *im_;
+  if (im.graph_mode <= 0) return false;
+  cudaGraph_t g = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  const long long l0 = launches_;
+  bool capturing = false;
+  try {
+    PKB_CUDA(cudaGraphCreate(&g, 0));
+    cudaGraphConditionalHandle handle;
+    PKB_CUDA(cudaGraphConditionalHandleCreate(&handle, g, 1, cudaGraphCondAssignDefault));
+    cudaGraphNodeParams cp{};
+    cp.type = cudaGraphNodeTypeConditional;
+    cp.conditional.handle = handle;
+    cp.conditional.type = cudaGraphCondTypeWhile;
+    cp.conditional.size = 1;
+    cudaGraphNode_t n_loop = nullptr;
+    PKB_CUDA(cudaGraphAddNode(&n_loop, g, nullptr, 0, &cp));
+    d.loop_handle = (unsigned long long)handle;
+    graph_pdl_suppressed() = true;
+    PKB_CUDA(cudaStreamBeginCaptureToGraph(st_, cp.conditional.phGraph_out[0], nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    capturing = true;
+    decode_iteration(b, d, -1);
+    capturing = false;
+    cudaGraph_t body_out = nullptr;
+    PKB_CUDA(cudaStreamEndCapture(st_, &body_out));
+    graph_pdl_suppressed() = false;
+    im.lf_loop_body_launches = (int)(launches_ - l0);
+    launches_ = l0;
+    PKB_CUDA(cudaGraphInstantiate(&exec, g, 0));
+    PKB_CUDA(cudaGraphLaunch(exec, st_));
+    im.lf_loop_graph = g;
+    im.lf_loop_exec = exec;
+    return true;
+  } catch (const std::exception& ex) {
+    graph_pdl_suppressed() = false;
+    if (capturing) { cudaGraph_t junk = nullptr; cudaStreamEndCapture(st_, &junk); }
+    if (exec) cudaGraphExecDestroy(exec);
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    launches_ = l0;
+    fprintf(stderr, "[parakeet_b200] decode-loop graph failed (%s); continuing launch by launch\n", ex.what());
+    return false;
+  }
+}
+
+// after the stream has been synchronised: kernels run by the loop graph, its algorithmic bytes (profile mode), release
+void Engine::finish_decode_loop_graph(long long passes) {
+  Impl& im = *im_;
+  if (!im.lf_loop_exec) return;
+  launches_ += passes * im.lf_loop_body_launches;
+  if (im.profile && im.lf_loop_prof_idx >= 0)
+    im.prof_flops[im.lf_loop_prof_idx] =
+        (double)passes * ((double)kJointOut * kJointH * 2.0 + kJointOut * 4.0 + (double)im.lf_loop_B * (2.0 * kJointH * 4.0 + 12.0));
+  cudaGraphExecDestroy(im.lf_loop_exec);
+  cudaGraphDestroy(im.lf_loop_graph);
+  im.lf_loop_exec = nullptr; im.lf_loop_graph = nullptr; im.lf_loop_prof_idx = -1;
+}
+
 void Engine::run_decode(const BatchDev& b, const int* slots, int* steps, int max_steps, const float* enc_proj_rows) {
   Impl& im = *im_;
   const DecodeDev d = decode_setup(b, slots, steps, max_steps, enc_proj_rows);
   decode_prologue(b, d, enc_proj_rows == nullptr);
   const int max_iters = b.max_tenc * (kMaxSymbols + 1) + 2;
   const int prof_i = prof_begin(3, 0.0);      // the whole loop; its algorithmic bytes are known when it ends
+  if (steps != nullptr && b.max_tenc > 4 * kMaxTq && run_decode_loop_graph(b, d)) {
+    // whole-utterance decode, device-side loop: passes (and with them the algorithmic bytes) are known once the traces are back
+    im.lf_loop_prof_idx = prof_i;
+    im.lf_loop_B = b.B;
+    if (prof_i >= 0) { im.prof_flops[prof_i] = 0.0; prof_end(prof_i); }
+    return;
+  }
   int iters_done = 0;
   for (int it = 0; it < max_iters; ++it) {
     ++iters_done;
@@ -2115,6 +2189,7 @@ void Engine::offline_utterances(int n, const int* sids, const float* const* pcm,
     PKB_CUDA(cudaMemcpyAsync(recs.data(), im.lf_steps, recs.size() * sizeof(int), cudaMemcpyDeviceToHost, st_));
   }
   PKB_CUDA(cudaStreamSynchronize(st_));
+  if (decode == 1) { long long passes = 1; for (int c : counts) passes = std::max<long long>(passes, std::min(c, steps_per)); finish_decode_loop_graph(passes); }
   if (im.profile) profile_collect();
   for (int i = 0; i < n; ++i) {
     Stream& s = *streams_[sids[i]];
@@ -2179,6 +2254,7 @@ int Engine::offline_decode_pending() {
   PKB_CUDA(cudaMemcpyAsync(counts.data(), im.n_steps, n * sizeof(int), cudaMemcpyDeviceToHost, st_));
   PKB_CUDA(cudaMemcpyAsync(recs.data(), im.lf_steps, recs.size() * sizeof(int), cudaMemcpyDeviceToHost, st_));
   PKB_CUDA(cudaStreamSynchronize(st_));
+  { long long passes = 1; for (int c : counts) passes = std::max<long long>(passes, std::min(c, steps_per)); finish_decode_loop_graph(passes); }
   if (im.profile) profile_collect();
   for (int i = 0; i < n; ++i) {
     Stream& s = *streams_[sids[i]];

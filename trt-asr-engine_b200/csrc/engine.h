@@ -167,6 +167,8 @@ class Engine {
   void decode_prologue(const BatchDev& b, const DecodeDev& d, bool project);
   void decode_iteration(const BatchDev& b, const DecodeDev& d, int host_poll_slot);
   StepGraph* step_graph(const BatchDev& b);      // nullptr: run this step launch by launch
+  bool run_decode_loop_graph(const BatchDev& b, DecodeDev d);
+  void finish_decode_loop_graph(long long passes);
   void lf_prepare(size_t total_frames, size_t steps_ints);
   void run_predictor_pass(const DecodeDev& d);
   void frontend_pass();
