@@ -707,13 +707,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int m = m0 + q * 32 + rd_row + 8 * i;
         ctx[i] = m < M ? epilogue_row_ctx<MODE>(g.epi, m, sp) : -1;
       }
-      if constexpr (MODE == EPI_PARTIAL_F32) {
+      if constexpr (MODE == EPI_PARTIAL_F32 || MODE == EPI_SILU_ACT || MODE == EPI_ACT) {
         if (g.epi.direct_bf16) {
-          // bf16 partial sums straight from the TMEM-load registers: the lane keeps its own accumulator row, 32 columns per load
-          // = 64 contiguous bytes of the workspace row (see the single-CTA kernel's direct path)
+          // bf16 rows straight from the TMEM-load registers: the lane keeps its own accumulator row, 32 columns per load
+          // = 64 contiguous bytes of the destination row (see the single-CTA kernel's direct path)
           const int m_d = m0 + q * 32 + lane;
-          __nv_bfloat16* drow = m_d < M ? reinterpret_cast<__nv_bfloat16*>(g.epi.out_f32) + (size_t)epilogue_row_ctx<MODE>(g.epi, m_d, sp) * g.epi.ldo
-                                        : nullptr;
+          __nv_bfloat16* drow = nullptr;
+          if (m_d < M) {
+            if constexpr (MODE == EPI_PARTIAL_F32)
+              drow = reinterpret_cast<__nv_bfloat16*>(g.epi.out_f32) + (size_t)epilogue_row_ctx<MODE>(g.epi, m_d, sp) * g.epi.ldo;
+            else
+              drow = g.epi.out_act + (size_t)m_d * g.epi.lda_out;
+          }
 #pragma unroll 1
           for (int c0 = 0; c0 < BN / 2; c0 += 32) {
             uint32_t v[32];
@@ -728,8 +733,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
               uint4* dst = reinterpret_cast<uint4*>(drow + ncol + g.epi.n_off);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const uint2 p0 = pack4_bf16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1]), __uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
-                const uint2 p1 = pack4_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]), __uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+                float f[8];
+#pragma unroll
+                for (int x = 0; x < 8; ++x) {
+                  f[x] = __uint_as_float(v[8 * j + x]);
+                  if constexpr (MODE == EPI_SILU_ACT) f[x] = silu(f[x]);
+                }
+                const uint2 p0 = pack4_bf16(f[0], f[1], f[2], f[3]), p1 = pack4_bf16(f[4], f[5], f[6], f[7]);
                 dst[j] = make_uint4(p0.x, p0.y, p1.x, p1.y);
               }
             }
@@ -906,8 +916,11 @@ void gemm_tc(const GemmArgs& g_in, const TensorMap& map_a, const TensorMap& map_
   const int sms = sm_count();
   if (g_force_bn < 0) { const char* v = getenv("PARAKEET_B200_GEMM_BN"); g_force_bn = v ? atoi(v) : 0; }
   if (g_two_cta < 0) { const char* v = getenv("PARAKEET_B200_GEMM_2CTA"); g_two_cta = v ? atoi(v) : 1; }
+  // PARAKEET_B200_PAIR_MODES: bit m set = epilogue mode m always takes the CTA-pair kernel when its shape allows (A/B knob)
+  static const int pair_modes = [] { const char* v = getenv("PARAKEET_B200_PAIR_MODES"); return v ? atoi(v) : 0; }();
+  const bool pair_forced = ((pair_modes >> g.epi.mode) & 1) && g.N % 256 == 0 && g.M >= 2048 && g.N % 32 == 0;
   const bool two_cta = g.epi.mode != EPI_ARGMAX && g.epi.mode != EPI_ACT && g.batch == 1 && !(g.epi.mode == EPI_PARTIAL_F32 && g.epi.splits > 1 && !g.epi.pair_split) &&
-                       (g_force_bn == 512 || (g_force_bn == 0 && g_two_cta != 0 && pick_two_cta(g.M, g.N, g.K, sms)));
+                       (g_force_bn == 512 || (g_force_bn == 0 && g_two_cta != 0 && (pair_forced || pick_two_cta(g.M, g.N, g.K, sms))));
   if (two_cta) {
     const int pair_tiles = ((g.M + 255) / 256) * ((g.N + 255) / 256) * (g.epi.mode == EPI_PARTIAL_F32 ? g.epi.splits : 1);
     const int pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;
