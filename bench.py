@@ -551,6 +551,10 @@ def longform(binding, model, precision, batch, seconds, blank_penalty=None):
             else:
                 hi_p = pen
         pen = best if best is not None else hi_p
+        if not any(0.2 <= r <= 0.4 for _, r in cal):
+            # no penalty lands inside the window (the transition is a step, and its position moves by a few tenths of a logit with the clip
+            # length): stay clear of the step, on the emitting side -- the decoder then emits on (nearly) every frame
+            pen += 1.5
     else:
         pen = blank_penalty
     eng.set_blank_penalty(pen)
