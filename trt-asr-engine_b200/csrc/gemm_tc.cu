@@ -916,8 +916,11 @@ void gemm_tc(const GemmArgs& g_in, const TensorMap& map_a, const TensorMap& map_
   const int sms = sm_count();
   if (g_force_bn < 0) { const char* v = getenv("PARAKEET_B200_GEMM_BN"); g_force_bn = v ? atoi(v) : 0; }
   if (g_two_cta < 0) { const char* v = getenv("PARAKEET_B200_GEMM_2CTA"); g_two_cta = v ? atoi(v) : 1; }
-  // PARAKEET_B200_PAIR_MODES: bit m set = epilogue mode m always takes the CTA-pair kernel when its shape allows (A/B knob)
-  static const int pair_modes = [] { const char* v = getenv("PARAKEET_B200_PAIR_MODES"); return v ? atoi(v) : 0; }();
+  // PARAKEET_B200_PAIR_MODES: bit m set = epilogue mode m always takes the CTA-pair kernel when its shape allows.  Default: the FFN-up
+  // projections (EPI_SILU_ACT, N = 4096, K = 1024) -- with the direct bf16 epilogue the 256 x 256 pair tile (32 KB of operands per SM
+  // and k-block instead of 48 KB for the same MACs) wins although both tilings leave the last of 6 waves equally empty: 55.3 -> ~50 us
+  // per launch, 17.48 -> 17.27 ms per step at 1024 streams (A/B in gpurun r2k; 0 restores the single-CTA choice)
+  static const int pair_modes = [] { const char* v = getenv("PARAKEET_B200_PAIR_MODES"); return v ? atoi(v) : (1 << EPI_SILU_ACT); }();
   const bool pair_forced = ((pair_modes >> g.epi.mode) & 1) && g.N % 256 == 0 && g.M >= 2048 && g.N % 32 == 0;
   const bool two_cta = g.epi.mode != EPI_ARGMAX && g.epi.mode != EPI_ACT && g.batch == 1 && !(g.epi.mode == EPI_PARTIAL_F32 && g.epi.splits > 1 && !g.epi.pair_split) &&
                        (g_force_bn == 512 || (g_force_bn == 0 && g_two_cta != 0 && (pair_forced || pick_two_cta(g.M, g.N, g.K, sms))));
