@@ -707,6 +707,64 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int m = m0 + q * 32 + rd_row + 8 * i;
         ctx[i] = m < M ? epilogue_row_ctx<MODE>(g.epi, m, sp) : -1;
       }
+      if constexpr (MODE == EPI_GLU_F32 || MODE == EPI_QKV) {
+        if (g.epi.direct_bf16) {      // same direct epilogues as the single-CTA kernel (see there)
+          const int m_d = m0 + q * 32 + lane;
+          const bool row_ok = m_d < M;
+          const int ctxd = (MODE == EPI_QKV && row_ok) ? epilogue_row_ctx<MODE>(g.epi, m_d, sp) : 0;
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(taddr + (uint32_t)c0, v);
+            if (c0 + 32 == BN / 2) {
+              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) mbar_arrive_rank0(&tmem_empty_bar[acc]);
+            }
+            const int ncol = n0 + half * (BN / 2) + c0;
+            if (!row_ok || ncol >= g.N) continue;
+            if constexpr (MODE == EPI_GLU_F32) {
+              uint32_t o[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float a0 = __uint_as_float(v[4 * j]) * sigmoidf_(__uint_as_float(v[4 * j + 1]));
+                const float a1 = __uint_as_float(v[4 * j + 2]) * sigmoidf_(__uint_as_float(v[4 * j + 3]));
+                const __nv_bfloat162 hh = __floats2bfloat162_rn(a0, a1);
+                o[j] = *reinterpret_cast<const uint32_t*>(&hh);
+              }
+              uint4* dst = reinterpret_cast<uint4*>(g.epi.out_act + (size_t)m_d * g.epi.lda_out + (ncol >> 1));
+              dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+              dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            } else if (ncol < kDModel) {
+              __nv_bfloat16* drow = g.epi.q_bf16 + (size_t)m_d * kDModel;
+              uint4* du = reinterpret_cast<uint4*>(drow + ncol);
+              uint4* dv = reinterpret_cast<uint4*>(drow + g.epi.q_plane + ncol);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 u0 = *reinterpret_cast<const float4*>(g.epi.bias_u + ncol + 8 * j), u1 = *reinterpret_cast<const float4*>(g.epi.bias_u + ncol + 8 * j + 4);
+                const float4 w0 = *reinterpret_cast<const float4*>(g.epi.bias_v + ncol + 8 * j), w1 = *reinterpret_cast<const float4*>(g.epi.bias_v + ncol + 8 * j + 4);
+                const float f0 = __uint_as_float(v[8 * j]), f1 = __uint_as_float(v[8 * j + 1]), f2 = __uint_as_float(v[8 * j + 2]), f3 = __uint_as_float(v[8 * j + 3]);
+                const float f4 = __uint_as_float(v[8 * j + 4]), f5 = __uint_as_float(v[8 * j + 5]), f6 = __uint_as_float(v[8 * j + 6]), f7 = __uint_as_float(v[8 * j + 7]);
+                const uint2 a0 = pack4_bf16(f0 + u0.x, f1 + u0.y, f2 + u0.z, f3 + u0.w), a1 = pack4_bf16(f4 + u1.x, f5 + u1.y, f6 + u1.z, f7 + u1.w);
+                const uint2 b0 = pack4_bf16(f0 + w0.x, f1 + w0.y, f2 + w0.z, f3 + w0.w), b1 = pack4_bf16(f4 + w1.x, f5 + w1.y, f6 + w1.z, f7 + w1.w);
+                du[j] = make_uint4(a0.x, a0.y, a1.x, a1.y);
+                dv[j] = make_uint4(b0.x, b0.y, b1.x, b1.y);
+              }
+            } else {
+              const int c = (ncol - kDModel) & (kDModel - 1), h = c >> 7, d = c & 127;
+              __nv_bfloat16* ring = reinterpret_cast<__nv_bfloat16*>(ncol < 2 * kDModel ? g.epi.kring : g.epi.vring);
+              uint4* dst = reinterpret_cast<uint4*>(ring + ((size_t)ctxd + (size_t)h * kRingCap) * kDHead + d);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint2 a0 = pack4_bf16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1]), __uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                const uint2 a1 = pack4_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]), __uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+                dst[j] = make_uint4(a0.x, a0.y, a1.x, a1.y);
+              }
+            }
+          }
+          continue;
+        }
+      }
       if constexpr (MODE == EPI_PARTIAL_F32 || MODE == EPI_SILU_ACT || MODE == EPI_ACT) {
         if (g.epi.direct_bf16) {
           // bf16 rows straight from the TMEM-load registers: the lane keeps its own accumulator row, 32 columns per load
