@@ -32,35 +32,52 @@ __global__ void __launch_bounds__(kWarps * 32, SPLIT ? 1 : 2)
 gemm_simt_kernel(const GemmArgs g) {
   constexpr int kPairs = kWarps / KS;                       // column pairs per CTA
   __shared__ float s_part[KS > 1 ? kWarps : 1][2 * kRows];
-  pdl_enter();
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = warp / KS, ks = warp % KS;
   const int n0 = (blockIdx.x * kPairs + pair) * 2;
   const int m0 = blockIdx.y * kRows;
+  const bool has1 = n0 + 1 < g.N;
+  const int kslice = ((g.K + KS - 1) / KS + 7) & ~7;
+  const int kb = ks * kslice, ke = min(g.K, kb + kslice);
+  const __nv_bfloat16* w0 = g.W + (size_t)min(n0, g.N - 1) * g.K;
+  const __nv_bfloat16* w1 = g.W + (size_t)(has1 ? n0 + 1 : min(n0, g.N - 1)) * g.K;
+  // The weights are constants: the first batch of loads is requested BEFORE waiting for the predecessor kernel, so that in a chain
+  // of dependent launches (one stream: ~370 per chunk) the HBM round trip of launch i+1 overlaps the execution of launch i.
+  uint4 wa[kInflight], wb[kInflight];
+  if (n0 < g.N) {
+#pragma unroll
+    for (int j = 0; j < kInflight; ++j) {
+      const int kk = kb + lane * 8 + 256 * j;
+      if (kk < ke) {
+        wa[j] = __ldg(reinterpret_cast<const uint4*>(w0 + kk));
+        wb[j] = __ldg(reinterpret_cast<const uint4*>(w1 + kk));
+      }
+    }
+  }
+  pdl_wait();
   const int M = g.M_dev ? min(*g.M_dev, g.M) : g.M;
   const bool live = n0 < g.N && m0 < M;                     // (dead warps still take part in the CTA barrier below)
-  const bool has1 = n0 + 1 < g.N;
   float acc0[kRows], acc1[kRows];
 #pragma unroll
   for (int r = 0; r < kRows; ++r) acc0[r] = acc1[r] = 0.0f;
   if (live) {
-    const int kslice = ((g.K + KS - 1) / KS + 7) & ~7;
-    const int kb = ks * kslice, ke = min(g.K, kb + kslice);
-    const __nv_bfloat16* w0 = g.W + (size_t)n0 * g.K;
-    const __nv_bfloat16* w1 = g.W + (size_t)(has1 ? n0 + 1 : n0) * g.K;
     int row_off[kRows];                                     // element offsets of the (clamped) activation rows
 #pragma unroll
     for (int r = 0; r < kRows; ++r) row_off[r] = min(m0 + r, M - 1) * g.lda;
+    bool first = true;
     for (int k = kb + lane * 8; k < ke; k += 256 * kInflight) {
-      uint4 wa[kInflight], wb[kInflight];
+      if (!first) {
 #pragma unroll
-      for (int j = 0; j < kInflight; ++j) {                 // every weight byte of this step is requested before any is consumed
-        const int kk = k + 256 * j;
-        if (kk < ke) {
-          wa[j] = __ldg(reinterpret_cast<const uint4*>(w0 + kk));
-          wb[j] = __ldg(reinterpret_cast<const uint4*>(w1 + kk));
+        for (int j = 0; j < kInflight; ++j) {               // every weight byte of this step is requested before any is consumed
+          const int kk = k + 256 * j;
+          if (kk < ke) {
+            wa[j] = __ldg(reinterpret_cast<const uint4*>(w0 + kk));
+            wb[j] = __ldg(reinterpret_cast<const uint4*>(w1 + kk));
+          }
         }
       }
+      first = false;
 #pragma unroll
       for (int j = 0; j < kInflight; ++j) {
         const int kk = k + 256 * j;

@@ -274,7 +274,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  pdl_enter();      // barrier init + TMEM allocation above overlap the previous kernel's tail; global data only from here on
+  // barrier init + TMEM allocation above overlap the previous kernel's tail.  The weight tiles are constants: the producer requests
+  // the W half of its first ring stages BEFORE waiting for the predecessor grid (the HBM round trip of this launch's weights overlaps
+  // the previous launch; only the A tiles -- the predecessor's output -- wait).  Not when the row count is read from device memory
+  // (decode GEMMs): the tile walk depends on it.
+  pdl_trigger();
+  int pre = 0;
+  if (warp == 0 && lane == 0 && g.M_dev == nullptr) {
+    const int tiles_m0 = (g.M + BM - 1) / BM, tiles_mn0 = tiles_m0 * ((g.N + BN - 1) / BN);
+    const int unit = blockIdx.x;
+    if (unit < tiles_mn0 * splits * g.batch) {
+      const int tile_b = unit / splits, sp = unit - tile_b * splits;
+      const int bt = tile_b / tiles_mn0, tile = tile_b - bt * tiles_mn0;
+      const int n0 = (tile / tiles_m0) * BN;
+      const int kb_lo = sp * kb_per_pass / splits, kbs = (sp + 1) * kb_per_pass / splits - kb_lo;
+      const int num_kb = kbs * n_pass;
+      const int w_row0 = bt * g.w_row_stride;
+      pre = num_kb < C::kStages ? num_kb : C::kStages;
+      for (int kb = 0; kb < pre; ++kb) {
+        mbar_expect_tx(&full_bar[kb], C::kStageBytes);
+        const int kk = (kb_lo + kb % kbs) * BK;
+#pragma unroll
+        for (int j = 0; j < BN / 128; ++j)
+          tma_load_2d(sB + kb * C::kTileBBytes + j * kTileABytes, &map_w, &full_bar[kb], kk, w_row0 + n0 + j * 128);
+      }
+    }
+  }
+  pdl_wait();
   const int M = g.M_dev ? min(*g.M_dev, g.M) : g.M;
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN;
   const int tiles_mn = tiles_m * tiles_n;
@@ -293,13 +319,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
+          const bool w_done = it < pre;      // stage armed and its W tiles requested before the dependency wait
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], C::kStageBytes);
+          if (!w_done) mbar_expect_tx(&full_bar[s], C::kStageBytes);
           const int pass = kb / kbs, kk = (kb_lo + kb % kbs) * BK;
           tma_load_2d(sA + s * kTileABytes, &map_a, &full_bar[s], a_col0 + kk, m0 + pass * lo_row_off);
+          if (!w_done) {
 #pragma unroll
-          for (int j = 0; j < BN / 128; ++j)
-            tma_load_2d(sB + s * C::kTileBBytes + j * kTileABytes, &map_w, &full_bar[s], kk, w_row0 + n0 + j * 128);
+            for (int j = 0; j < BN / 128; ++j)
+              tma_load_2d(sB + s * C::kTileBBytes + j * kTileABytes, &map_w, &full_bar[s], kk, w_row0 + n0 + j * 128);
+          }
         }
       }
     }
@@ -638,7 +667,24 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  pdl_enter();
+  // (as in the single-CTA kernel: the W halves of the first ring stages are requested before the dependency wait)
+  pdl_trigger();
+  int pre = 0;
+  if (warp == 0 && lane == 0 && g.M_dev == nullptr) {
+    const int tiles_m0 = (g.M + BM2 - 1) / BM2;
+    if (pair < tiles_m0 * ((g.N + BN - 1) / BN) * splits) {
+      const int tile = pair / splits, sp = pair - tile * splits;
+      const int n0 = (tile / tiles_m0) * BN + 128 * rank;
+      const int kb_lo = sp * kb_per_pass / splits, kbs = (sp + 1) * kb_per_pass / splits - kb_lo;
+      const int num_kb = kbs * n_pass;
+      pre = num_kb < kStages2 ? num_kb : kStages2;
+      for (int kb = 0; kb < pre; ++kb) {
+        if (rank == 0) mbar_expect_tx(&full_bar[kb], 2 * kStageBytes2);
+        tma_load_2d_2sm(sB + kb * kTileABytes, &map_w, smem_u32(&full_bar[kb]) & kPeerBitMask, (kb_lo + kb % kbs) * BK, n0);
+      }
+    }
+  }
+  pdl_wait();
   const int M = g.M_dev ? min(*g.M_dev, g.M) : g.M;
   const int tiles_m = (M + BM2 - 1) / BM2, tiles_n = (g.N + BN - 1) / BN;
   const int total_tiles = tiles_m * tiles_n * splits;
@@ -654,12 +700,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % kStages2;
           const uint32_t ph = (it / kStages2) & 1;
+          const bool w_done = it < pre;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * kStageBytes2);
+          if (rank == 0 && !w_done) mbar_expect_tx(&full_bar[s], 2 * kStageBytes2);
           const uint32_t leader_full = smem_u32(&full_bar[s]) & kPeerBitMask;
           const int pass = kb / kbs, kk = (kb_lo + kb % kbs) * BK;
           tma_load_2d_2sm(sA + s * kTileABytes, &map_a, leader_full, kk, m0 + pass * lo_row_off);
-          tma_load_2d_2sm(sB + s * kTileABytes, &map_w, leader_full, kk, n0);
+          if (!w_done) tma_load_2d_2sm(sB + s * kTileABytes, &map_w, leader_full, kk, n0);
         }
       }
     }
