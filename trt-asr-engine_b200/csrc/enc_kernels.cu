@@ -415,11 +415,196 @@ layernorm_kernel(float* __restrict__ x, int M, const float* __restrict__ g1, con
   for (int i = 0; i < 8; ++i)
     store_act4(a.ptr, row, a.lda, i * 128 + lane * 4, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), a.lo_off);
 }
+// ---- streaming LayerNorm for large batches (same arithmetic, lane <-> column mapping and summation order as layernorm_kernel: the
+// results are bit-identical; only the data movement differs).  layernorm_kernel keeps 24 warps per SM resident, each with ONE row
+// (4 KB of x + the partial sums) in flight between dependent phases: 1.6 TB/s of DRAM reads at 1024 streams (profiles/r02_misc...:
+// 38 - 50 MB in 23 - 29 us, 12 % of the step).  Here one persistent CTA per SM owns <= 16 warps; a warp walks rows
+// gw, gw + stride, ... and keeps `depth` rows in flight through cp.async.bulk copies (x row + partial-sum rows -> its private
+// shared-memory ring, one mbarrier per slot), so the loads of row k+depth overlap the arithmetic and stores of row k; gamma / beta
+// are staged in shared memory once per CTA, before the dependency wait.
+namespace {
+__device__ __forceinline__ uint32_t lns_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void lns_bulk(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(lns_u32(dst)), "l"(src),
+               "r"(bytes), "r"(lns_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void lns_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(lns_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+constexpr int kLnsParamBytes = 4 * kDModel * 4;      // gamma1 | beta1 | gamma2 | beta2
+constexpr int kLnsBarBytes = 1024;
+}  // namespace
+
+__global__ void __launch_bounds__(512, 1)
+layernorm_stream_kernel(float* __restrict__ x, int M, const float* __restrict__ g1, const float* __restrict__ b1,
+                        const float* __restrict__ g2, const float* __restrict__ b2, int write_x, ActOut a, AcacheOut ac, int has_ac,
+                        LnResidual res, int depth, int row_bytes) {
+  extern __shared__ __align__(128) uint8_t lns_raw[];
+  float* s_g1 = reinterpret_cast<float*>(lns_raw);
+  float* s_b1 = s_g1 + kDModel;
+  float* s_g2 = s_b1 + kDModel;
+  float* s_b2 = s_g2 + kDModel;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lns_raw + kLnsParamBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  uint8_t* mybuf = lns_raw + kLnsParamBytes + kLnsBarBytes + (size_t)warp * depth * row_bytes;
+  uint64_t* mybar = bars + warp * depth;
+  pdl_trigger();
+  for (int i = threadIdx.x; i < kDModel / 4; i += blockDim.x) {      // constants: staged before the dependency wait
+    reinterpret_cast<float4*>(s_g1)[i] = reinterpret_cast<const float4*>(g1)[i];
+    reinterpret_cast<float4*>(s_b1)[i] = reinterpret_cast<const float4*>(b1)[i];
+    if (g2 != nullptr) {
+      reinterpret_cast<float4*>(s_g2)[i] = reinterpret_cast<const float4*>(g2)[i];
+      reinterpret_cast<float4*>(s_b2)[i] = reinterpret_cast<const float4*>(b2)[i];
+    }
+  }
+  if (lane == 0) {
+    for (int d = 0; d < depth; ++d)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lns_u32(&mybar[d])), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  pdl_wait();
+  const int gw = warp * gridDim.x + blockIdx.x, stride = nw * gridDim.x;
+  const uint32_t part_bytes = res.part != nullptr ? (res.bf16 ? kDModel * 2u : kDModel * 4u) : 0u;
+  const int splits = res.part != nullptr ? res.splits : 0;
+  auto issue = [&](int row, int slot) {      // one lane: x row + the row of every partial-sum plane into ring slot `slot`
+    uint8_t* dst = mybuf + (size_t)slot * row_bytes;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lns_u32(&mybar[slot])), "r"(kDModel * 4u + splits * part_bytes)
+                 : "memory");
+    lns_bulk(dst, x + (size_t)row * kDModel, kDModel * 4u, &mybar[slot]);
+    for (int sp = 0; sp < splits; ++sp) {
+      const size_t off = (size_t)sp * res.split_stride + (size_t)row * kDModel;
+      const void* src = res.bf16 ? static_cast<const void*>(reinterpret_cast<const __nv_bfloat16*>(res.part) + off) : static_cast<const void*>(res.part + off);
+      lns_bulk(dst + kDModel * 4 + (size_t)sp * part_bytes, src, part_bytes, &mybar[slot]);
+    }
+  };
+  if (lane == 0) {
+    for (int d = 0; d < depth; ++d) {
+      const int row = gw + d * stride;
+      if (row < M) issue(row, d);
+    }
+  }
+  int k = 0;
+  for (int row = gw; row < M; row += stride, ++k) {
+    const int slot = k % depth;
+    lns_wait(&mybar[slot], (uint32_t)((k / depth) & 1));
+    const uint8_t* buf = mybuf + (size_t)slot * row_bytes;
+    float v[32];
+    float* xr = x + (size_t)row * kDModel;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 t = reinterpret_cast<const float4*>(buf)[i * 32 + lane];
+      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+    if (splits > 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int sp = 0; sp < splits; ++sp) {
+          const uint8_t* pb = buf + kDModel * 4 + (size_t)sp * part_bytes;
+          float4 t;
+          if (res.bf16) {
+            const uint2 raw = reinterpret_cast<const uint2*>(pb)[i * 32 + lane];
+            const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+            const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+            t = make_float4(lo.x, lo.y, hi.x, hi.y);
+          } else {
+            t = reinterpret_cast<const float4*>(pb)[i * 32 + lane];
+          }
+          acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+        v[4 * i] += res.scale * acc.x; v[4 * i + 1] += res.scale * acc.y; v[4 * i + 2] += res.scale * acc.z; v[4 * i + 3] += res.scale * acc.w;
+      }
+    }
+    // every lane holds its share of the row in registers: the slot can take the row `depth` iterations ahead
+    __syncwarp();
+    if (lane == 0) {
+      const int next = row + depth * stride;
+      if (next < M) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(next, slot);
+      }
+    }
+    if (splits > 0 && !write_x) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(xr + i * 128 + lane * 4) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+    ln_row(v, s_g1, s_b1, lane);
+    if (has_ac) {
+      const int e = ac.row_entry[row];
+      const int phys = (ac.entry_head[e] + kCacheS + ac.row_pos[row]) % kRingCap;
+      const size_t base = ((size_t)ac.entry_slot[e] * kRingCap + phys) * kDModel;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int col = i * 128 + lane * 4;
+        if (ac.is_f32) {
+          *reinterpret_cast<float4*>((float*)ac.ring + base + col) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+          store_act4((__nv_bfloat16*)ac.ring + base + col, 0, 0, 0, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), 0);
+        }
+      }
+    }
+    if (write_x) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(xr + i * 128 + lane * 4) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      if (g2 != nullptr) ln_row(v, s_g2, s_b2, lane);
+    }
+    if (a.ptr != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        store_act4(a.ptr, row, a.lda, i * 128 + lane * 4, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), a.lo_off);
+    }
+  }
+}
+
 void launch_layernorm(float* x, int M, const float* g1, const float* b1, const float* g2, const float* b2, int write_x, ActOut a,
                       const AcacheOut* ac, cudaStream_t st, const LnResidual* res) {
   if (M <= 0) return;
   AcacheOut z{};
   LnResidual r0{};
+  // large batches: the streaming kernel (PARAKEET_B200_LN_STREAM=0 keeps layernorm_kernel everywhere; the two are bit-identical)
+  static const int stream_min_rows = [] { const char* v = getenv("PARAKEET_B200_LN_STREAM"); return v ? (atoi(v) > 0 ? atoi(v) : 1 << 30) : 2048; }();
+  if (M >= stream_min_rows) {
+    static int sms = 0;
+    if (!sms) {
+      int dev = 0;
+      PKB_CUDA(cudaGetDevice(&dev));
+      PKB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int splits = (res && res->part) ? res->splits : 0;
+    const int row_bytes = kDModel * 4 + splits * ((res && res->bf16) ? kDModel * 2 : kDModel * 4);
+    constexpr int kBudget = 190 * 1024;
+    int nw = 16, depth = kBudget / (nw * row_bytes);
+    if (depth < 2) { nw = 8; depth = kBudget / (nw * row_bytes); }
+    if (depth >= 2) {
+      depth = depth > 3 ? 3 : depth;
+      const size_t smem = kLnsParamBytes + kLnsBarBytes + (size_t)nw * depth * row_bytes;
+      static bool attr = false;
+      if (!attr) {
+        PKB_CUDA(cudaFuncSetAttribute(layernorm_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr = true;
+      }
+      const int grid = (M + nw - 1) / nw < sms ? (M + nw - 1) / nw : sms;
+      launch_k(layernorm_stream_kernel, dim3(grid), dim3(nw * 32), smem, st, x, M, g1, b1, g2, b2, write_x, a, ac ? *ac : z, (int)(ac != nullptr),
+               res ? *res : r0, depth, row_bytes);
+      PKB_CUDA(cudaGetLastError());
+      return;
+    }
+  }
   launch_k(layernorm_kernel, dim3((M + kLnRowsPerCta - 1) / kLnRowsPerCta), dim3(kLnRowsPerCta * 32), 0, st, x, M, g1, b1, g2, b2, write_x, a, ac ? *ac : z, (int)(ac != nullptr),
            res ? *res : r0);
   PKB_CUDA(cudaGetLastError());
@@ -658,7 +843,98 @@ dwconv2_kernel(BatchDev b, DwConvArgs a) {
     *reinterpret_cast<float4*>(cache + kTimeCtx) = make_float4(nc[1][0], nc[1][1], nc[1][2], nc[1][3]);
   }
 }
+// bf16 mode, large batches: FOUR adjacent channels per thread, one CTA per entry.  dwconv2_kernel reads its 18 filter taps as scalars
+// 72 bytes apart across the lanes of a warp (11.3 M load sectors per launch at 1024 streams, the LSU-bound part of its 22 us:
+// profiles/r02_misc...); here the taps come from a transposed copy [9][1024] as float4 (one 512-byte run per warp and tap), are
+// requested before the dependency wait (constants), the activations move as 8-byte bf16 quads and the time cache as 64 contiguous
+// bytes per thread.  Per channel the arithmetic and its order are exactly those of dwconv_kernel.
+__global__ void __launch_bounds__(256)
+dwconv4_kernel(BatchDev b, DwConvArgs a) {
+  pdl_trigger();
+  const int e = blockIdx.x, ch = 4 * threadIdx.x;
+  float w[4][kConvK];
+#pragma unroll
+  for (int i = 0; i < kConvK; ++i) {
+    const float4 t = *reinterpret_cast<const float4*>(a.wt + (size_t)i * kDModel + ch);
+    w[0][i] = t.x; w[1][i] = t.y; w[2][i] = t.z; w[3][i] = t.w;
+  }
+  const float4 bias4 = *reinterpret_cast<const float4*>(a.bias + ch);
+  const float bias[4] = {bias4.x, bias4.y, bias4.z, bias4.w};
+  pdl_wait();
+  const int Tq = b.Tq[e], qlen = b.qlen[e], row0 = b.row_off[e];
+  float* cache = a.cache_tm + (size_t)b.slot[e] * a.slot_stride + (size_t)ch * kTimeCtx;
+  const bool offline = b.offline[e] != 0;
+  float cv[4][4];      // [channel][cache position]
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float4 t = offline ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(cache + c * kTimeCtx);
+    cv[c][0] = t.x; cv[c][1] = t.y; cv[c][2] = t.z; cv[c][3] = t.w;
+  }
+  auto ld_c = [&](int t, float (&o)[4]) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(a.c_bf16 + (size_t)(row0 + t) * kDModel + ch);
+    const float2 p0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+    const float2 p1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+    o[0] = p0.x; o[1] = p0.y; o[2] = p1.x; o[3] = p1.y;
+  };
+  float win[4][kConvK];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { win[c][0] = cv[c][0]; win[c][1] = cv[c][1]; win[c][2] = cv[c][2]; win[c][3] = cv[c][3]; }
+#pragma unroll
+  for (int i = 4; i < kConvK; ++i) {
+    const int t = i - 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (t < Tq && t < qlen) ld_c(t, v);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) win[c][i] = v[c];
+  }
+  float nc[4][4];      // [channel][new cache position]
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = Tq + 1 + i;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (idx < 4) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[c] = idx == 0 ? cv[c][0] : idx == 1 ? cv[c][1] : idx == 2 ? cv[c][2] : cv[c][3];
+    } else if (idx - 4 < Tq && idx - 4 < qlen) {
+      ld_c(idx - 4, v);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) nc[c][i] = v[c];
+  }
+  for (int t = 0; t < Tq; ++t) {
+    float o[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int i = 0; i < kConvK; ++i) acc = fmaf(w[c][i], win[c][i], acc);
+      o[c] = silu(acc + bias[c]);
+    }
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
+    *reinterpret_cast<uint2*>(a.out.ptr + (size_t)(row0 + t) * a.out.lda + ch) =
+        make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int i = 0; i < kConvK - 1; ++i) win[c][i] = win[c][i + 1];
+    const int tn = t + 5;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (tn < Tq && tn < qlen) ld_c(tn, v);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) win[c][kConvK - 1] = v[c];
+  }
+  if (!offline) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) *reinterpret_cast<float4*>(cache + c * kTimeCtx) = make_float4(nc[c][0], nc[c][1], nc[c][2], nc[c][3]);
+  }
+}
 void launch_dwconv(const BatchDev& b, const DwConvArgs& a, cudaStream_t st) {
+  static const bool quad = [] { const char* v = getenv("PARAKEET_B200_DWCONV4"); return !(v && v[0] == '0'); }();
+  if (quad && a.wt != nullptr && a.c_bf16 != nullptr && a.out.lo_off == 0 && b.B >= 64) {
+    launch_k(dwconv4_kernel, dim3(b.B), dim3(256), 0, st, b, a);
+    PKB_CUDA(cudaGetLastError());
+    return;
+  }
   if (b.B <= 0) return;
   static const bool pair = [] { const char* v = getenv("PARAKEET_B200_DWCONV2"); return !(v && v[0] == '0'); }();
   if (pair && a.c_bf16 != nullptr && a.out.lo_off == 0) launch_k(dwconv2_kernel, dim3(b.B, kDModel / 512), dim3(256), 0, st, b, a);

@@ -102,6 +102,7 @@ struct DwConvArgs {
   const float* w;          // [1024,9] depthwise weights with BN scale folded in
   const float* bias;       // [1024] folded BN offset
   ActOut out;              // [M,1024]
+  const float* wt = nullptr;   // optional transposed copy of w, [9][1024] (dwconv4_kernel: coalesced float4 tap loads)
 };
 void launch_dwconv(const BatchDev& b, const DwConvArgs& a, cudaStream_t st);
 

@@ -91,7 +91,7 @@ struct ActBuf {
 struct LayerW {
   float *n_ff1_g, *n_ff1_b, *n_att_g, *n_att_b, *n_conv_g, *n_conv_b, *n_ff2_g, *n_ff2_b, *n_out_g, *n_out_b;
   GemmW ff1_1, ff1_2, qkv, kv, out, pw1, pw2, ff2_1, ff2_2;
-  float *dw_w, *dw_b, *bias_u, *bias_v;
+  float *dw_w, *dw_wt, *dw_b, *bias_u, *bias_v;      // dw_wt: dw_w transposed to [9][1024]
   void* ppos_t;                 // precise mode: transposed table [head][128][kPosRows] f32
   __nv_bfloat16* ppos_n;        // bf16 mode: natural table [head][kPosRowsPad][128]
   TensorMap ppos_map;           //           TMA map over it as the W operand [8 * kPosRowsPad, 128] of the position-score GEMM
@@ -567,6 +567,10 @@ void Engine::load_weights() {
       }
       w.dw_w = dev_upload(dw);
       w.dw_b = dev_upload(off);
+      std::vector<float> dwt((size_t)kConvK * kDModel);
+      for (int c = 0; c < kDModel; ++c)
+        for (int k = 0; k < kConvK; ++k) dwt[(size_t)k * kDModel + c] = dw[(size_t)c * kConvK + k];
+      w.dw_wt = dev_upload(dwt);
     }
     w.bias_u = dev_upload(F(p + "self_attn.pos_bias_u", kDModel));
     w.bias_v = dev_upload(F(p + "self_attn.pos_bias_v", kDModel));
@@ -1386,7 +1390,7 @@ void Engine::run_encoder(const BatchDev& b, const LongForm* lf) {
     } else {
       DwConvArgs a; a.c = split ? im.cglu : nullptr; a.c_bf16 = split ? nullptr : reinterpret_cast<const __nv_bfloat16*>(im.cglu);
       a.cache_tm = im.cache_tm + (size_t)l * kDModel * kTimeCtx; a.slot_stride = (long long)L_ * kDModel * kTimeCtx;
-      a.w = w.dw_w; a.bias = w.dw_b; a.out = im.a_ln.out();
+      a.w = w.dw_w; a.wt = w.dw_wt; a.bias = w.dw_b; a.out = im.a_ln.out();
       launch_dwconv(b, a, st_); ++launches_;
     }
     g_tc_site = 2048;

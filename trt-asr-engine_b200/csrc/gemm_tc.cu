@@ -124,6 +124,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 
+// One 256-bit store (STG.E.256, sm_100): a lane writes a whole 32-byte sector in one request.  The direct epilogues used to write it
+// as two 16-byte halves -- twice the L1 -> L2 write transactions (3.1 M per FFN-up / QKV launch at 1024 streams, profiles/r02_gemm...).
+__device__ __forceinline__ void st_global_256(void* dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f, uint32_t g,
+                                              uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h)
+               : "memory");
+}
 __device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) {
   const __nv_bfloat162 p0 = __floats2bfloat162_rn(a, b), p1 = __floats2bfloat162_rn(c, d);
   return make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
@@ -413,25 +420,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               uint4* du = reinterpret_cast<uint4*>(drow + ncol);
               uint4* dv = reinterpret_cast<uint4*>(drow + g.epi.q_plane + ncol);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float4 u0 = *reinterpret_cast<const float4*>(g.epi.bias_u + ncol + 8 * j), u1 = *reinterpret_cast<const float4*>(g.epi.bias_u + ncol + 8 * j + 4);
-                const float4 w0 = *reinterpret_cast<const float4*>(g.epi.bias_v + ncol + 8 * j), w1 = *reinterpret_cast<const float4*>(g.epi.bias_v + ncol + 8 * j + 4);
-                const float f0 = __uint_as_float(v[8 * j]), f1 = __uint_as_float(v[8 * j + 1]), f2 = __uint_as_float(v[8 * j + 2]), f3 = __uint_as_float(v[8 * j + 3]);
-                const float f4 = __uint_as_float(v[8 * j + 4]), f5 = __uint_as_float(v[8 * j + 5]), f6 = __uint_as_float(v[8 * j + 6]), f7 = __uint_as_float(v[8 * j + 7]);
-                const uint2 a0 = pack4_bf16(f0 + u0.x, f1 + u0.y, f2 + u0.z, f3 + u0.w), a1 = pack4_bf16(f4 + u1.x, f5 + u1.y, f6 + u1.z, f7 + u1.w);
-                const uint2 b0 = pack4_bf16(f0 + w0.x, f1 + w0.y, f2 + w0.z, f3 + w0.w), b1 = pack4_bf16(f4 + w1.x, f5 + w1.y, f6 + w1.z, f7 + w1.w);
-                du[j] = make_uint4(a0.x, a0.y, a1.x, a1.y);
-                dv[j] = make_uint4(b0.x, b0.y, b1.x, b1.y);
+              for (int jj = 0; jj < 2; ++jj) {
+                uint2 pa[4], pb[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                  const int c = 16 * jj + 4 * x;
+                  const float4 u = *reinterpret_cast<const float4*>(g.epi.bias_u + ncol + c), w = *reinterpret_cast<const float4*>(g.epi.bias_v + ncol + c);
+                  const float f0 = __uint_as_float(v[c]), f1 = __uint_as_float(v[c + 1]), f2 = __uint_as_float(v[c + 2]), f3 = __uint_as_float(v[c + 3]);
+                  pa[x] = pack4_bf16(f0 + u.x, f1 + u.y, f2 + u.z, f3 + u.w);
+                  pb[x] = pack4_bf16(f0 + w.x, f1 + w.y, f2 + w.z, f3 + w.w);
+                }
+                st_global_256(du + 2 * jj, pa[0].x, pa[0].y, pa[1].x, pa[1].y, pa[2].x, pa[2].y, pa[3].x, pa[3].y);
+                st_global_256(dv + 2 * jj, pb[0].x, pb[0].y, pb[1].x, pb[1].y, pb[2].x, pb[2].y, pb[3].x, pb[3].y);
               }
             } else {
               const int c = (ncol - kDModel) & (kDModel - 1), h = c >> 7, d = c & 127;
               __nv_bfloat16* ring = reinterpret_cast<__nv_bfloat16*>(ncol < 2 * kDModel ? g.epi.kring : g.epi.vring);
               uint4* dst = reinterpret_cast<uint4*>(ring + ((size_t)ctxd + (size_t)h * kRingCap) * kDHead + d);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint2 a0 = pack4_bf16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1]), __uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
-                const uint2 a1 = pack4_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]), __uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
-                dst[j] = make_uint4(a0.x, a0.y, a1.x, a1.y);
+              for (int jj = 0; jj < 2; ++jj) {
+                uint2 pa[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                  const int c = 16 * jj + 4 * x;
+                  pa[x] = pack4_bf16(__uint_as_float(v[c]), __uint_as_float(v[c + 1]), __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+                }
+                st_global_256(dst + 2 * jj, pa[0].x, pa[0].y, pa[1].x, pa[1].y, pa[2].x, pa[2].y, pa[3].x, pa[3].y);
               }
             }
           }
@@ -463,8 +477,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 o[j] = *reinterpret_cast<const uint32_t*>(&h);
               }
               uint4* dst = reinterpret_cast<uint4*>(drow + (ncol >> 1));
-              dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-              dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+              st_global_256(dst, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
             }
           }
           continue;
@@ -502,8 +515,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint2 p0 = pack4_bf16(f[0], f[1], f[2], f[3]), p1 = pack4_bf16(f[4], f[5], f[6], f[7]);
             const uint2 p2 = pack4_bf16(f[8], f[9], f[10], f[11]), p3 = pack4_bf16(f[12], f[13], f[14], f[15]);
             uint4* dst = reinterpret_cast<uint4*>(drow + nn);
-            dst[0] = make_uint4(p0.x, p0.y, p1.x, p1.y);
-            dst[1] = make_uint4(p2.x, p2.y, p3.x, p3.y);
+            st_global_256(dst, p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y);
           }
           continue;
         }
@@ -780,32 +792,38 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 o[j] = *reinterpret_cast<const uint32_t*>(&hh);
               }
               uint4* dst = reinterpret_cast<uint4*>(g.epi.out_act + (size_t)m_d * g.epi.lda_out + (ncol >> 1));
-              dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-              dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+              st_global_256(dst, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
             } else if (ncol < kDModel) {
               __nv_bfloat16* drow = g.epi.q_bf16 + (size_t)m_d * kDModel;
               uint4* du = reinterpret_cast<uint4*>(drow + ncol);
               uint4* dv = reinterpret_cast<uint4*>(drow + g.epi.q_plane + ncol);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float4 u0 = *reinterpret_cast<const float4*>(g.epi.bias_u + ncol + 8 * j), u1 = *reinterpret_cast<const float4*>(g.epi.bias_u + ncol + 8 * j + 4);
-                const float4 w0 = *reinterpret_cast<const float4*>(g.epi.bias_v + ncol + 8 * j), w1 = *reinterpret_cast<const float4*>(g.epi.bias_v + ncol + 8 * j + 4);
-                const float f0 = __uint_as_float(v[8 * j]), f1 = __uint_as_float(v[8 * j + 1]), f2 = __uint_as_float(v[8 * j + 2]), f3 = __uint_as_float(v[8 * j + 3]);
-                const float f4 = __uint_as_float(v[8 * j + 4]), f5 = __uint_as_float(v[8 * j + 5]), f6 = __uint_as_float(v[8 * j + 6]), f7 = __uint_as_float(v[8 * j + 7]);
-                const uint2 a0 = pack4_bf16(f0 + u0.x, f1 + u0.y, f2 + u0.z, f3 + u0.w), a1 = pack4_bf16(f4 + u1.x, f5 + u1.y, f6 + u1.z, f7 + u1.w);
-                const uint2 b0 = pack4_bf16(f0 + w0.x, f1 + w0.y, f2 + w0.z, f3 + w0.w), b1 = pack4_bf16(f4 + w1.x, f5 + w1.y, f6 + w1.z, f7 + w1.w);
-                du[j] = make_uint4(a0.x, a0.y, a1.x, a1.y);
-                dv[j] = make_uint4(b0.x, b0.y, b1.x, b1.y);
+              for (int jj = 0; jj < 2; ++jj) {
+                uint2 pa[4], pb[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                  const int c = 16 * jj + 4 * x;
+                  const float4 u = *reinterpret_cast<const float4*>(g.epi.bias_u + ncol + c), w = *reinterpret_cast<const float4*>(g.epi.bias_v + ncol + c);
+                  const float f0 = __uint_as_float(v[c]), f1 = __uint_as_float(v[c + 1]), f2 = __uint_as_float(v[c + 2]), f3 = __uint_as_float(v[c + 3]);
+                  pa[x] = pack4_bf16(f0 + u.x, f1 + u.y, f2 + u.z, f3 + u.w);
+                  pb[x] = pack4_bf16(f0 + w.x, f1 + w.y, f2 + w.z, f3 + w.w);
+                }
+                st_global_256(du + 2 * jj, pa[0].x, pa[0].y, pa[1].x, pa[1].y, pa[2].x, pa[2].y, pa[3].x, pa[3].y);
+                st_global_256(dv + 2 * jj, pb[0].x, pb[0].y, pb[1].x, pb[1].y, pb[2].x, pb[2].y, pb[3].x, pb[3].y);
               }
             } else {
               const int c = (ncol - kDModel) & (kDModel - 1), h = c >> 7, d = c & 127;
               __nv_bfloat16* ring = reinterpret_cast<__nv_bfloat16*>(ncol < 2 * kDModel ? g.epi.kring : g.epi.vring);
               uint4* dst = reinterpret_cast<uint4*>(ring + ((size_t)ctxd + (size_t)h * kRingCap) * kDHead + d);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint2 a0 = pack4_bf16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1]), __uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
-                const uint2 a1 = pack4_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]), __uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
-                dst[j] = make_uint4(a0.x, a0.y, a1.x, a1.y);
+              for (int jj = 0; jj < 2; ++jj) {
+                uint2 pa[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                  const int c = 16 * jj + 4 * x;
+                  pa[x] = pack4_bf16(__uint_as_float(v[c]), __uint_as_float(v[c + 1]), __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+                }
+                st_global_256(dst + 2 * jj, pa[0].x, pa[0].y, pa[1].x, pa[1].y, pa[2].x, pa[2].y, pa[3].x, pa[3].y);
               }
             }
           }
@@ -837,15 +855,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             if (drow != nullptr && ncol < g.N) {
               uint4* dst = reinterpret_cast<uint4*>(drow + ncol + g.epi.n_off);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float f[8];
+              for (int jj = 0; jj < 2; ++jj) {
+                float f[16];
 #pragma unroll
-                for (int x = 0; x < 8; ++x) {
-                  f[x] = __uint_as_float(v[8 * j + x]);
+                for (int x = 0; x < 16; ++x) {
+                  f[x] = __uint_as_float(v[16 * jj + x]);
                   if constexpr (MODE == EPI_SILU_ACT) f[x] = silu(f[x]);
                 }
                 const uint2 p0 = pack4_bf16(f[0], f[1], f[2], f[3]), p1 = pack4_bf16(f[4], f[5], f[6], f[7]);
-                dst[j] = make_uint4(p0.x, p0.y, p1.x, p1.y);
+                const uint2 p2 = pack4_bf16(f[8], f[9], f[10], f[11]), p3 = pack4_bf16(f[12], f[13], f[14], f[15]);
+                st_global_256(dst + 2 * jj, p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y);
               }
             }
           }
@@ -1005,16 +1024,17 @@ void gemm_tc(const GemmArgs& g_in, const TensorMap& map_a, const TensorMap& map_
     // direct bf16 epilogue (single-CTA kernel): every 16-column group of an output row must be one aligned 32-byte run
     static const bool allow = [] { const char* v = getenv("PARAKEET_B200_EPI_DIRECT"); return !(v && v[0] == '0'); }();
     const EpiParams& e = g.epi;
-    bool ok = allow && g.N % 16 == 0 && e.n_off % 8 == 0 && g.out_col_stride % 8 == 0;
-    if (e.mode == EPI_PARTIAL_F32) ok = ok && e.part_bf16 && e.ldo % 8 == 0 && ((uintptr_t)e.out_f32 & 15) == 0 && g.N % 32 == 0;
+    // (every 16-column group of an output row is written as ONE 256-bit store: 32-byte aligned rows and column offsets)
+    bool ok = allow && g.N % 16 == 0 && e.n_off % 16 == 0 && g.out_col_stride % 16 == 0;
+    if (e.mode == EPI_PARTIAL_F32) ok = ok && e.part_bf16 && e.ldo % 16 == 0 && ((uintptr_t)e.out_f32 & 31) == 0 && g.N % 32 == 0;
     else if (e.mode == EPI_QKV)
       ok = ok && e.k_natural && !e.kv_f32 && e.q_bf16 != nullptr && e.n_off == 0 && g.batch == 1 && g.N == 3 * kDModel &&
-           ((uintptr_t)e.q_bf16 & 15) == 0 && ((uintptr_t)e.kring & 15) == 0 && ((uintptr_t)e.vring & 15) == 0 && (e.q_plane & 7) == 0 &&
+           ((uintptr_t)e.q_bf16 & 31) == 0 && ((uintptr_t)e.kring & 31) == 0 && ((uintptr_t)e.vring & 31) == 0 && (e.q_plane & 15) == 0 &&
            ((uintptr_t)e.bias_u & 15) == 0 && ((uintptr_t)e.bias_v & 15) == 0;
     else if (e.mode == EPI_GLU_F32)
-      ok = ok && e.out_act != nullptr && g.N % 32 == 0 && e.n_off == 0 && g.batch == 1 && e.lda_out % 8 == 0 && ((uintptr_t)e.out_act & 15) == 0;
+      ok = ok && e.out_act != nullptr && g.N % 32 == 0 && e.n_off == 0 && g.batch == 1 && e.lda_out % 16 == 0 && ((uintptr_t)e.out_act & 31) == 0;
     else if (e.mode == EPI_ACT || e.mode == EPI_SILU_ACT || e.mode == EPI_BIAS_RELU_ACT)
-      ok = ok && e.lo_off_out == 0 && e.lda_out % 8 == 0 && ((uintptr_t)e.out_act & 15) == 0 && (e.mode != EPI_BIAS_RELU_ACT || ((uintptr_t)e.bias & 15) == 0);
+      ok = ok && e.lo_off_out == 0 && e.lda_out % 16 == 0 && ((uintptr_t)e.out_act & 31) == 0 && (e.mode != EPI_BIAS_RELU_ACT || ((uintptr_t)e.bias & 15) == 0);
     else ok = false;
     g.epi.direct_bf16 = ok ? 1 : 0;
   }
