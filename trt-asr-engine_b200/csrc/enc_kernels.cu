@@ -325,37 +325,31 @@ void launch_subsample_stage2(const BatchDev& b, ActOut y1, const SubsampleWeight
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
-__device__ __forceinline__ void ln_row(float (&v)[32], const float* __restrict__ g, const float* __restrict__ bta, int lane) {
-  float s = 0.0f;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) s += v[i];
-  const float mean = warp_sum(s) * (1.0f / kDModel);
-  float q = 0.0f;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
-  const float var = warp_sum(q) * (1.0f / kDModel);
-  const float inv = 1.0f / sqrtf(var + 1e-5f);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int col = i * 128 + lane * 4;
-    const float4 gg = *reinterpret_cast<const float4*>(g + col);
-    const float4 bb = *reinterpret_cast<const float4*>(bta + col);
-    v[4 * i + 0] = (v[4 * i + 0] - mean) * inv * gg.x + bb.x;
-    v[4 * i + 1] = (v[4 * i + 1] - mean) * inv * gg.y + bb.y;
-    v[4 * i + 2] = (v[4 * i + 2] - mean) * inv * gg.z + bb.z;
-    v[4 * i + 3] = (v[4 * i + 3] - mean) * inv * gg.w + bb.w;
-  }
-}
-
+// (ln_row: enc_kernels.cuh -- shared with the LayerNorm-fused CUDA-core GEMM)
 constexpr int kLnRowsPerCta = 4;      // one warp per row; small CTAs balance 6144 rows over 148 SMs better than 8-row CTAs
 __global__ void __launch_bounds__(kLnRowsPerCta * 32)
 layernorm_kernel(float* __restrict__ x, int M, const float* __restrict__ g1, const float* __restrict__ b1,
                  const float* __restrict__ g2, const float* __restrict__ b2, int write_x, ActOut a, AcacheOut ac, int has_ac,
                  LnResidual res) {
-  pdl_enter();
+  // gamma / beta are constants: staged in shared memory BEFORE the dependency wait (in a chain of small dependent launches their
+  // round trip used to sit between the row statistics and the stores)
+  __shared__ __align__(16) float s_gb[4][kDModel];
+  pdl_trigger();
+  for (int i = threadIdx.x; i < kDModel / 4; i += kLnRowsPerCta * 32) {
+    reinterpret_cast<float4*>(s_gb[0])[i] = __ldg(reinterpret_cast<const float4*>(g1) + i);
+    reinterpret_cast<float4*>(s_gb[1])[i] = __ldg(reinterpret_cast<const float4*>(b1) + i);
+    if (g2 != nullptr) {
+      reinterpret_cast<float4*>(s_gb[2])[i] = __ldg(reinterpret_cast<const float4*>(g2) + i);
+      reinterpret_cast<float4*>(s_gb[3])[i] = __ldg(reinterpret_cast<const float4*>(b2) + i);
+    }
+  }
+  __syncthreads();
+  pdl_wait();
   const int row = blockIdx.x * kLnRowsPerCta + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
+  g1 = s_gb[0]; b1 = s_gb[1];
+  if (g2 != nullptr) { g2 = s_gb[2]; b2 = s_gb[3]; }
   float v[32];
   float* xr = x + (size_t)row * kDModel;
 #pragma unroll
@@ -447,6 +441,7 @@ constexpr int kLnsParamBytes = 4 * kDModel * 4;      // gamma1 | beta1 | gamma2 
 constexpr int kLnsBarBytes = 1024;
 }  // namespace
 
+template <int SPLITS, bool PBF16>      // partial-sum planes of the preceding split-K GEMM (0, 1 or 2), their element type
 __global__ void __launch_bounds__(512, 1)
 layernorm_stream_kernel(float* __restrict__ x, int M, const float* __restrict__ g1, const float* __restrict__ b1,
                         const float* __restrict__ g2, const float* __restrict__ b2, int write_x, ActOut a, AcacheOut ac, int has_ac,
@@ -477,16 +472,17 @@ layernorm_stream_kernel(float* __restrict__ x, int M, const float* __restrict__ 
   __syncthreads();
   pdl_wait();
   const int gw = warp * gridDim.x + blockIdx.x, stride = nw * gridDim.x;
-  const uint32_t part_bytes = res.part != nullptr ? (res.bf16 ? kDModel * 2u : kDModel * 4u) : 0u;
-  const int splits = res.part != nullptr ? res.splits : 0;
+  constexpr uint32_t part_bytes = SPLITS > 0 ? (PBF16 ? kDModel * 2u : kDModel * 4u) : 0u;
+  constexpr int splits = SPLITS;
   auto issue = [&](int row, int slot) {      // one lane: x row + the row of every partial-sum plane into ring slot `slot`
     uint8_t* dst = mybuf + (size_t)slot * row_bytes;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lns_u32(&mybar[slot])), "r"(kDModel * 4u + splits * part_bytes)
                  : "memory");
     lns_bulk(dst, x + (size_t)row * kDModel, kDModel * 4u, &mybar[slot]);
+#pragma unroll
     for (int sp = 0; sp < splits; ++sp) {
       const size_t off = (size_t)sp * res.split_stride + (size_t)row * kDModel;
-      const void* src = res.bf16 ? static_cast<const void*>(reinterpret_cast<const __nv_bfloat16*>(res.part) + off) : static_cast<const void*>(res.part + off);
+      const void* src = PBF16 ? static_cast<const void*>(reinterpret_cast<const __nv_bfloat16*>(res.part) + off) : static_cast<const void*>(res.part + off);
       lns_bulk(dst + kDModel * 4 + (size_t)sp * part_bytes, src, part_bytes, &mybar[slot]);
     }
   };
@@ -508,24 +504,30 @@ layernorm_stream_kernel(float* __restrict__ x, int M, const float* __restrict__ 
       const float4 t = reinterpret_cast<const float4*>(buf)[i * 32 + lane];
       v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
     }
-    if (splits > 0) {
+    if constexpr (SPLITS > 0) {
+      // x += scale * (p_0 + p_1): the same sums, in the same order, as layernorm_kernel (0 + p_0 is exact), on the packed f32x2 pipe
+      const float2 sc2 = make_float2(res.scale, res.scale);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int sp = 0; sp < splits; ++sp) {
+        float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int sp = 0; sp < SPLITS; ++sp) {
           const uint8_t* pb = buf + kDModel * 4 + (size_t)sp * part_bytes;
-          float4 t;
-          if (res.bf16) {
+          float2 t0, t1;
+          if constexpr (PBF16) {
             const uint2 raw = reinterpret_cast<const uint2*>(pb)[i * 32 + lane];
-            const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-            const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
-            t = make_float4(lo.x, lo.y, hi.x, hi.y);
+            t0 = make_float2(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u));
+            t1 = make_float2(__uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u));
           } else {
-            t = reinterpret_cast<const float4*>(pb)[i * 32 + lane];
+            const float4 t = reinterpret_cast<const float4*>(pb)[i * 32 + lane];
+            t0 = make_float2(t.x, t.y); t1 = make_float2(t.z, t.w);
           }
-          acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+          if (sp == 0) { a0 = t0; a1 = t1; }
+          else { a0 = __fadd2_rn(a0, t0); a1 = __fadd2_rn(a1, t1); }
         }
-        v[4 * i] += res.scale * acc.x; v[4 * i + 1] += res.scale * acc.y; v[4 * i + 2] += res.scale * acc.z; v[4 * i + 3] += res.scale * acc.w;
+        const float2 r0 = __ffma2_rn(sc2, a0, make_float2(v[4 * i], v[4 * i + 1]));
+        const float2 r1 = __ffma2_rn(sc2, a1, make_float2(v[4 * i + 2], v[4 * i + 3]));
+        v[4 * i] = r0.x; v[4 * i + 1] = r0.y; v[4 * i + 2] = r1.x; v[4 * i + 3] = r1.y;
       }
     }
     // every lane holds its share of the row in registers: the slot can take the row `depth` iterations ahead
@@ -537,7 +539,7 @@ layernorm_stream_kernel(float* __restrict__ x, int M, const float* __restrict__ 
         issue(next, slot);
       }
     }
-    if (splits > 0 && !write_x) {
+    if (SPLITS > 0 && !write_x) {
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         *reinterpret_cast<float4*>(xr + i * 128 + lane * 4) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -586,21 +588,30 @@ void launch_layernorm(float* x, int M, const float* g1, const float* b1, const f
       PKB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
     const int splits = (res && res->part) ? res->splits : 0;
-    const int row_bytes = kDModel * 4 + splits * ((res && res->bf16) ? kDModel * 2 : kDModel * 4);
-    constexpr int kBudget = 190 * 1024;
+    const bool pbf16 = res && res->bf16;
+    const int row_bytes = kDModel * 4 + splits * (pbf16 ? kDModel * 2 : kDModel * 4);
+    // 16 warps x 2 rows in flight where the rows are small enough (bf16 mode, one partial-sum plane: 6 KB per row), else 8 warps x 3:
+    // with 8 warps the kernel is bound by the latency of its own instruction chain (2 warps per scheduler: 23 us at 1024 streams,
+    // profiles/r02_ln_stream...), not by memory
+    static const int budget_kb = [] { const char* v = getenv("PARAKEET_B200_LN_SMEM_KB"); return v ? atoi(v) : 210; }();
+    const int kBudget = budget_kb * 1024;
     int nw = 16, depth = kBudget / (nw * row_bytes);
+    if (depth < 2) { nw = 12; depth = kBudget / (nw * row_bytes); }      // two bf16 partial-sum planes: 8 KB per row
     if (depth < 2) { nw = 8; depth = kBudget / (nw * row_bytes); }
-    if (depth >= 2) {
+    if (depth >= 2 && splits <= 2) {
       depth = depth > 3 ? 3 : depth;
       const size_t smem = kLnsParamBytes + kLnsBarBytes + (size_t)nw * depth * row_bytes;
-      static bool attr = false;
-      if (!attr) {
-        PKB_CUDA(cudaFuncSetAttribute(layernorm_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr = true;
-      }
       const int grid = (M + nw - 1) / nw < sms ? (M + nw - 1) / nw : sms;
-      launch_k(layernorm_stream_kernel, dim3(grid), dim3(nw * 32), smem, st, x, M, g1, b1, g2, b2, write_x, a, ac ? *ac : z, (int)(ac != nullptr),
-               res ? *res : r0, depth, row_bytes);
+      auto go = [&](auto kernel) {
+        PKB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        launch_k(kernel, dim3(grid), dim3(nw * 32), smem, st, x, M, g1, b1, g2, b2, write_x, a, ac ? *ac : z, (int)(ac != nullptr), res ? *res : r0, depth,
+                 row_bytes);
+      };
+      if (splits == 0) go(layernorm_stream_kernel<0, false>);
+      else if (splits == 1 && pbf16) go(layernorm_stream_kernel<1, true>);
+      else if (splits == 2 && pbf16) go(layernorm_stream_kernel<2, true>);
+      else if (splits == 1) go(layernorm_stream_kernel<1, false>);
+      else go(layernorm_stream_kernel<2, false>);
       PKB_CUDA(cudaGetLastError());
       return;
     }

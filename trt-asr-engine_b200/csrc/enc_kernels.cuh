@@ -64,6 +64,41 @@ struct LnResidual { const float* part; int splits; long long split_stride; float
 struct AcacheOut { void* ring; int is_f32; const int* row_entry; const int* row_pos; const int* entry_slot; const int* entry_head; };
 void launch_layernorm(float* x, int M, const float* g1, const float* b1, const float* g2, const float* b2, int write_x, ActOut a,
                       const AcacheOut* ac, cudaStream_t st, const LnResidual* res = nullptr);
+// LayerNorm folded into the A operand of the CUDA-core GEMM (gemm_simt_ln, one-stream latency path): A = LN(x) with gamma / beta
+struct LnFuse { const float* x; const float* gamma; const float* beta; AcacheOut ac; int has_ac; };
+#ifdef __CUDACC__
+// One LayerNorm row held by a warp: lane owns columns i*128 + lane*4 .. +3 (i = 0..7) in v[4i .. 4i+3]; two-pass mean / variance,
+// eps 1e-5.  Every LayerNorm in the library goes through this function (same summation order everywhere).  The elementwise passes
+// use the packed f32x2 instructions of sm_100 (FADD2 / FMUL2 / FFMA2: two IEEE round-to-nearest results per issue slot) -- the
+// row kernels are bound by instruction issue, not by memory (profiles/r02_ln_stream...).
+__device__ __forceinline__ void ln_row(float (&v)[32], const float* __restrict__ g, const float* __restrict__ bta, int lane) {
+  float2 s2 = make_float2(0.0f, 0.0f);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) s2 = __fadd2_rn(s2, make_float2(v[2 * j], v[2 * j + 1]));
+  const float mean = warp_sum(s2.x + s2.y) * (1.0f / kDModel);
+  const float2 nm = make_float2(-mean, -mean);
+  float2 q2 = make_float2(0.0f, 0.0f);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float2 d = __fadd2_rn(make_float2(v[2 * j], v[2 * j + 1]), nm);
+    q2 = __ffma2_rn(d, d, q2);
+  }
+  const float var = warp_sum(q2.x + q2.y) * (1.0f / kDModel);
+  const float inv = 1.0f / sqrtf(var + 1e-5f);
+  const float2 inv2 = make_float2(inv, inv);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int col = i * 128 + lane * 4;
+    const float4 gg = *reinterpret_cast<const float4*>(g + col);
+    const float4 bb = *reinterpret_cast<const float4*>(bta + col);
+    const float2 t0 = __fmul2_rn(__fadd2_rn(make_float2(v[4 * i + 0], v[4 * i + 1]), nm), inv2);
+    const float2 t1 = __fmul2_rn(__fadd2_rn(make_float2(v[4 * i + 2], v[4 * i + 3]), nm), inv2);
+    const float2 r0 = __ffma2_rn(t0, make_float2(gg.x, gg.y), make_float2(bb.x, bb.y));
+    const float2 r1 = __ffma2_rn(t1, make_float2(gg.z, gg.w), make_float2(bb.z, bb.w));
+    v[4 * i + 0] = r0.x; v[4 * i + 1] = r0.y; v[4 * i + 2] = r1.x; v[4 * i + 3] = r1.y;
+  }
+}
+#endif
 
 // Relative-position multi-head attention over [ring cache (256) || new rows (Tq)] for every (entry, head).
 struct AttnArgs {

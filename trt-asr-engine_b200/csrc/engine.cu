@@ -1279,12 +1279,24 @@ void Engine::run_encoder(const BatchDev& b, const LongForm* lf) {
     return LnResidual{nullptr, 0, 0, 0.f, 0};
   };
   // q | k | v projection + attention of one layer over [per-stream K/V ring (256 cached rows) || the chunk's rows]
-  auto attention_streaming = [&](int l, const LayerW& w, char* kr, char* vr) {
+  // One-stream latency path (M <= 16, bf16 mode, CUDA-core GEMMs): the LayerNorms that feed exactly one projection are computed
+  // inside that projection's kernel (gemm_simt_ln) instead of as launches of their own (PARAKEET_B200_LN_FUSE=0 restores them).
+  static const bool ln_fuse_allowed = [] { const char* v = getenv("PARAKEET_B200_LN_FUSE"); return !(v && v[0] == '0'); }();
+  const bool fuse_ln = ln_fuse_allowed && !split && !lf && M <= 16 && opt_.gemm_backend != 2;
+  auto gemm_ln = [&](const float* gamma, const float* beta, const AcacheOut* ac, const GemmW& wt, const EpiParams& e) {
+    GemmArgs g;
+    g.A = im.a_ln.ptr; g.lda = kDModel; g.W = wt.w; g.M = M; g.N = wt.N; g.K = wt.K; g.epi = e;
+    LnFuse f{im.x, gamma, beta, ac ? *ac : AcacheOut{}, ac ? 1 : 0};
+    ++launches_;
+    gemm_simt_ln(g, f, st_);
+  };
+  auto attention_streaming = [&](int l, const LayerW& w, char* kr, char* vr, const AcacheOut* fused_ac, bool fused) {
     { EpiParams e; e.mode = EPI_QKV; e.out_f32 = im.q; e.ldo = kDModel; e.row_entry = b.row_entry; e.row_pos = b.row_pos;
       e.entry_slot = b.slot; e.entry_head = b.head; e.kring = kr; e.vring = vr; e.kv_f32 = split ? 1 : 0;
       e.k_natural = im.attn_mma ? 1 : 0;
       if (im.attn_mma) { e.q_bf16 = im.q_bf16; e.q_plane = im.q_plane; e.bias_u = w.bias_u; e.bias_v = w.bias_v; }
-      RUN_GEMM(im.a_ln, w.qkv, M, nullptr, e); }
+      if (fused) gemm_ln(w.n_att_g, w.n_att_b, fused_ac, w.qkv, e);
+      else RUN_GEMM(im.a_ln, w.qkv, M, nullptr, e); }
     if (im.attn_mma) {
       // position scores for every (row, head): G[m][h][r] = (q_m + pos_bias_v)[h] . P_h[r] -- 8 batched [M,128] x [320,128]^T
       // problems in one tcgen05 launch (the table is the same for every stream, so this does not belong in the per-stream kernel)
@@ -1371,18 +1383,21 @@ void Engine::run_encoder(const BatchDev& b, const LongForm* lf) {
       ac.ring = (char*)im.acache + (size_t)l * im.ring_layer_elems * kv_elem; ac.is_f32 = split ? 1 : 0;
       ac.row_entry = b.row_entry; ac.row_pos = b.row_pos; ac.entry_slot = b.slot; ac.entry_head = b.head;
     }
-    launch_layernorm(im.x, M, w.n_att_g, w.n_att_b, nullptr, nullptr, 0, im.a_ln.out(), (im.acache && !lf) ? &ac : nullptr, st_, &res); ++launches_;
+    const bool fuse_att = fuse_ln && res.part == nullptr;
+    if (!fuse_att) { launch_layernorm(im.x, M, w.n_att_g, w.n_att_b, nullptr, nullptr, 0, im.a_ln.out(), (im.acache && !lf) ? &ac : nullptr, st_, &res); ++launches_; }
     g_tc_site = 256;
     if (lf) attention_whole_utterance(l, w, *lf);
-    else attention_streaming(l, w, kr, vr);
+    else attention_streaming(l, w, kr, vr, im.acache ? &ac : nullptr, fuse_att);
     g_tc_site = 512;
     res = residual_gemm(im.a_ln, w.out, 1.0f);
     // convolution module
-    launch_layernorm(im.x, M, w.n_conv_g, w.n_conv_b, nullptr, nullptr, 0, im.a_ln.out(), nullptr, st_, &res); ++launches_;
+    const bool fuse_conv = fuse_ln && res.part == nullptr;
+    if (!fuse_conv) { launch_layernorm(im.x, M, w.n_conv_g, w.n_conv_b, nullptr, nullptr, 0, im.a_ln.out(), nullptr, st_, &res); ++launches_; }
     g_tc_site = 1024;
     { EpiParams e; e.mode = EPI_GLU_F32; e.out_f32 = im.cglu; e.ldo = kDModel;
       if (!split) { e.out_act = reinterpret_cast<__nv_bfloat16*>(im.cglu); e.lda_out = kDModel; }      // bf16 mode: bf16 elements in the same buffer
-      RUN_GEMM(im.a_ln, w.pw1, M, nullptr, e); }
+      if (fuse_conv) gemm_ln(w.n_conv_g, w.n_conv_b, nullptr, w.pw1, e);
+      else RUN_GEMM(im.a_ln, w.pw1, M, nullptr, e); }
     if (lf) {      // whole utterance: symmetric (4,4) zero padding, no time cache
       LfDwConvArgs a; a.c = split ? im.cglu : nullptr; a.c_bf16 = split ? nullptr : reinterpret_cast<const __nv_bfloat16*>(im.cglu);
       a.w = w.dw_w; a.bias = w.dw_b; a.out = im.a_ln.out(); a.M = M;
@@ -1396,10 +1411,12 @@ void Engine::run_encoder(const BatchDev& b, const LongForm* lf) {
     g_tc_site = 2048;
     res = residual_gemm(im.a_ln, w.pw2, 1.0f);
     // FFN 2
-    launch_layernorm(im.x, M, w.n_ff2_g, w.n_ff2_b, nullptr, nullptr, 0, im.a_ln.out(), nullptr, st_, &res); ++launches_;
+    const bool fuse_ff2 = fuse_ln && res.part == nullptr;
+    if (!fuse_ff2) { launch_layernorm(im.x, M, w.n_ff2_g, w.n_ff2_b, nullptr, nullptr, 0, im.a_ln.out(), nullptr, st_, &res); ++launches_; }
     g_tc_site = 64;
     { EpiParams e; e.mode = EPI_SILU_ACT; e.out_act = im.a_ff.ptr; e.lda_out = kFF; e.lo_off_out = im.a_ff.lo_off;
-      RUN_GEMM(im.a_ln, w.ff2_1, M, nullptr, e); }
+      if (fuse_ff2) gemm_ln(w.n_ff2_g, w.n_ff2_b, nullptr, w.ff2_1, e);
+      else RUN_GEMM(im.a_ln, w.ff2_1, M, nullptr, e); }
     g_tc_site = 128;
     res = residual_gemm(im.a_ff, w.ff2_2, 0.5f);
     // norm_out (+ next layer's norm_feed_forward1; after the last layer: operand of the joint's encoder projection)

@@ -172,6 +172,10 @@ __device__ __forceinline__ void epilogue_pair(const EpiParams& p, int m, int n, 
 
 // CUDA-core backend (any M; efficient for M <= 16).
 void gemm_simt(const GemmArgs& g, cudaStream_t st);
+// ... with the LayerNorm that produces A folded in (A = LN(x) computed per CTA; g.A is not read).  K == 1024, bf16 mode, M <= 16.
+struct LnFuse;
+bool gemm_simt_ln_supported(const GemmArgs& g);
+void gemm_simt_ln(const GemmArgs& g, const LnFuse& f, cudaStream_t st);
 
 // tcgen05 backend.  `map_a` / `map_w` are CUtensorMap objects (128-byte opaque, 64-byte aligned) created by
 // make_tensor_map_2d for A [rows, lda] (hi plane then lo plane: lo rows start at a_lo_off / lda) and W [N, K],

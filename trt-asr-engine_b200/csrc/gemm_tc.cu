@@ -1051,7 +1051,10 @@ void gemm_tc(const GemmArgs& g_in, const TensorMap& map_a, const TensorMap& map_
                        (g_force_bn == 512 || (g_force_bn == 0 && g_two_cta != 0 && (pair_forced || pick_two_cta(g.M, g.N, g.K, sms))));
   if (two_cta) {
     const int pair_tiles = ((g.M + 255) / 256) * ((g.N + 255) / 256) * (g.epi.mode == EPI_PARTIAL_F32 ? g.epi.splits : 1);
-    const int pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;
+    // (PARAKEET_B200_GEMM_MAX_PAIRS: measurement aid -- fewer resident pairs show how much of a tile's time is L2 -> SM contention)
+    static const int max_pairs = [] { const char* v = getenv("PARAKEET_B200_GEMM_MAX_PAIRS"); return v ? atoi(v) : 1 << 30; }();
+    const int pair_cap = sms / 2 < max_pairs ? sms / 2 : max_pairs;
+    const int pairs = pair_tiles < pair_cap ? pair_tiles : pair_cap;
     const int lo_row_off2 = (int)(g.a_lo_off / g.lda);
     const CUtensorMap& ma2 = *reinterpret_cast<const CUtensorMap*>(&map_a);
     const CUtensorMap& mw2 = *reinterpret_cast<const CUtensorMap*>(&map_w);

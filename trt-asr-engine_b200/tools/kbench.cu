@@ -12,7 +12,29 @@ using namespace pkb;
 
 static float* dalloc_f(size_t n) { float* p; PKB_CUDA(cudaMalloc(&p, n * 4)); PKB_CUDA(cudaMemset(p, 0, n * 4)); return p; }
 
+// `kbench clusters`: how many thread-block clusters of 2 / 4 / 8 CTAs with a GEMM-sized shared-memory footprint (one CTA per SM) the
+// device can hold at once -- decides whether operand multicast over 4-CTA clusters can keep all 148 SMs busy.
+__global__ void probe_kernel(int* p) { if (p) *p = 0; }
+static int probe_clusters() {
+  PKB_CUDA(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  PKB_CUDA(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  for (int cs : {1, 2, 4, 8, 16}) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(cs * 64); cfg.blockDim = dim3(320); cfg.dynamicSmemBytes = 200 * 1024;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = -1;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, probe_kernel, &cfg);
+    printf("cluster size %2d: max active clusters %d (%d CTAs)%s\n", cs, n, n * cs, e == cudaSuccess ? "" : cudaGetErrorString(e));
+    if (e != cudaSuccess) cudaGetLastError();
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc >= 2 && strcmp(argv[1], "clusters") == 0) return probe_clusters();
   if (argc < 5 || strcmp(argv[1], "gemm") != 0) { printf("usage: kbench gemm M N K [iters] [epi: f32|resadd|silu|glu] [ln 0/1]\n"); return 1; }
   const int M = atoi(argv[2]), N = atoi(argv[3]), K = atoi(argv[4]);
   const int iters = argc > 5 ? atoi(argv[5]) : 50;
