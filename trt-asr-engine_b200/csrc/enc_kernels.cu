@@ -327,6 +327,10 @@ void launch_subsample_stage2(const BatchDev& b, ActOut y1, const SubsampleWeight
 // ------------------------------------------------------------------------------------------------ LayerNorm
 // (ln_row: enc_kernels.cuh -- shared with the LayerNorm-fused CUDA-core GEMM)
 constexpr int kLnRowsPerCta = 4;      // one warp per row; small CTAs balance 6144 rows over 148 SMs better than 8-row CTAs
+// SPLITS = partial-sum planes of the preceding split-K GEMM, a compile-time count so that ALL their loads are in flight together with
+// the x row (with a run-time loop over the planes each load waited for the previous one: 9.8 us per launch for 768 rows and three
+// planes, 20 % of the 128-stream step, profiles/r02_launch_summary_128.csv)
+template <int SPLITS>
 __global__ void __launch_bounds__(kLnRowsPerCta * 32)
 layernorm_kernel(float* __restrict__ x, int M, const float* __restrict__ g1, const float* __restrict__ b1,
                  const float* __restrict__ g2, const float* __restrict__ b2, int write_x, ActOut a, AcacheOut ac, int has_ac,
@@ -357,25 +361,39 @@ layernorm_kernel(float* __restrict__ x, int M, const float* __restrict__ g1, con
     const float4 t = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
     v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
   }
-  if (res.part != nullptr) {
+  if constexpr (SPLITS > 0) {
     // deferred residual of the preceding split-K GEMM: x += scale * (p_0 + p_1 + ...), splits added in index order
+    if (res.bf16) {
+      uint2 raw[SPLITS][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int sp = 0; sp < res.splits; ++sp) {
-        const size_t off = (size_t)sp * res.split_stride + (size_t)row * kDModel + i * 128 + lane * 4;
-        float4 t;
-        if (res.bf16) {
-          const uint2 raw = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(res.part) + off);
-          const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-          const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
-          t = make_float4(lo.x, lo.y, hi.x, hi.y);
-        } else {
-          t = *reinterpret_cast<const float4*>(res.part + off);
+      for (int sp = 0; sp < SPLITS; ++sp)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          raw[sp][i] = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(res.part) + (size_t)sp * res.split_stride +
+                                                       (size_t)row * kDModel + i * 128 + lane * 4);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int sp = 0; sp < SPLITS; ++sp) {
+          const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw[sp][i].x));
+          const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw[sp][i].y));
+          acc.x += lo.x; acc.y += lo.y; acc.z += hi.x; acc.w += hi.y;
         }
-        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        v[4 * i] += res.scale * acc.x; v[4 * i + 1] += res.scale * acc.y; v[4 * i + 2] += res.scale * acc.z; v[4 * i + 3] += res.scale * acc.w;
       }
-      v[4 * i] += res.scale * acc.x; v[4 * i + 1] += res.scale * acc.y; v[4 * i + 2] += res.scale * acc.z; v[4 * i + 3] += res.scale * acc.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 t[SPLITS];
+#pragma unroll
+        for (int sp = 0; sp < SPLITS; ++sp)
+          t[sp] = *reinterpret_cast<const float4*>(res.part + (size_t)sp * res.split_stride + (size_t)row * kDModel + i * 128 + lane * 4);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int sp = 0; sp < SPLITS; ++sp) { acc.x += t[sp].x; acc.y += t[sp].y; acc.z += t[sp].z; acc.w += t[sp].w; }
+        v[4 * i] += res.scale * acc.x; v[4 * i + 1] += res.scale * acc.y; v[4 * i + 2] += res.scale * acc.z; v[4 * i + 3] += res.scale * acc.w;
+      }
     }
     if (!write_x) {
 #pragma unroll
@@ -616,8 +634,19 @@ void launch_layernorm(float* x, int M, const float* g1, const float* b1, const f
       return;
     }
   }
-  launch_k(layernorm_kernel, dim3((M + kLnRowsPerCta - 1) / kLnRowsPerCta), dim3(kLnRowsPerCta * 32), 0, st, x, M, g1, b1, g2, b2, write_x, a, ac ? *ac : z, (int)(ac != nullptr),
-           res ? *res : r0);
+  const int nsp = (res && res->part) ? res->splits : 0;
+  PKB_CHECK(nsp >= 0 && nsp <= 4, "layernorm: at most 4 partial-sum planes");
+  auto go = [&](auto kernel) {
+    launch_k(kernel, dim3((M + kLnRowsPerCta - 1) / kLnRowsPerCta), dim3(kLnRowsPerCta * 32), 0, st, x, M, g1, b1, g2, b2, write_x, a, ac ? *ac : z,
+             (int)(ac != nullptr), res ? *res : r0);
+  };
+  switch (nsp) {
+    case 0: go(layernorm_kernel<0>); break;
+    case 1: go(layernorm_kernel<1>); break;
+    case 2: go(layernorm_kernel<2>); break;
+    case 3: go(layernorm_kernel<3>); break;
+    default: go(layernorm_kernel<4>); break;
+  }
   PKB_CUDA(cudaGetLastError());
 }
 
@@ -854,94 +883,83 @@ dwconv2_kernel(BatchDev b, DwConvArgs a) {
     *reinterpret_cast<float4*>(cache + kTimeCtx) = make_float4(nc[1][0], nc[1][1], nc[1][2], nc[1][3]);
   }
 }
-// bf16 mode, large batches: FOUR adjacent channels per thread, one CTA per entry.  dwconv2_kernel reads its 18 filter taps as scalars
-// 72 bytes apart across the lanes of a warp (11.3 M load sectors per launch at 1024 streams, the LSU-bound part of its 22 us:
-// profiles/r02_misc...); here the taps come from a transposed copy [9][1024] as float4 (one 512-byte run per warp and tap), are
-// requested before the dependency wait (constants), the activations move as 8-byte bf16 quads and the time cache as 64 contiguous
-// bytes per thread.  Per channel the arithmetic and its order are exactly those of dwconv_kernel.
+// bf16 mode, large batches of steady-state chunks (Tq <= 8 for every entry): FOUR adjacent channels per thread, one CTA per entry.
+// dwconv2_kernel reads its 18 filter taps as scalars 72 bytes apart across the lanes of a warp (11.3 M load sectors per launch at
+// 1024 streams) and slides its 9-tap window through register moves inside a loop over the rows: 10 M warp instructions, 22 us
+// (profiles/r02_misc...).  Here the taps come from a transposed copy [9][1024] as float4 (one 512-byte run per warp and tap,
+// requested before the dependency wait: constants), the extended signal [cache(4) | rows | 0000] of a channel pair lives in registers
+// at fixed positions (rows fully unrolled, no window shifting), the multiply-adds run on the packed f32x2 pipe (FFMA2: channel pairs),
+// activations move as 8-byte bf16 quads and the time cache as 64 contiguous bytes per thread.  Per channel the arithmetic and its
+// order are exactly those of dwconv_kernel.
 __global__ void __launch_bounds__(256)
 dwconv4_kernel(BatchDev b, DwConvArgs a) {
   pdl_trigger();
   const int e = blockIdx.x, ch = 4 * threadIdx.x;
-  float w[4][kConvK];
+  float2 w01[kConvK], w23[kConvK];
 #pragma unroll
   for (int i = 0; i < kConvK; ++i) {
     const float4 t = *reinterpret_cast<const float4*>(a.wt + (size_t)i * kDModel + ch);
-    w[0][i] = t.x; w[1][i] = t.y; w[2][i] = t.z; w[3][i] = t.w;
+    w01[i] = make_float2(t.x, t.y); w23[i] = make_float2(t.z, t.w);
   }
   const float4 bias4 = *reinterpret_cast<const float4*>(a.bias + ch);
-  const float bias[4] = {bias4.x, bias4.y, bias4.z, bias4.w};
   pdl_wait();
   const int Tq = b.Tq[e], qlen = b.qlen[e], row0 = b.row_off[e];
+  const int nv = Tq < qlen ? Tq : qlen;                   // rows past qlen are padding: zero (pad_mask)
   float* cache = a.cache_tm + (size_t)b.slot[e] * a.slot_stride + (size_t)ch * kTimeCtx;
   const bool offline = b.offline[e] != 0;
-  float cv[4][4];      // [channel][cache position]
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const float4 t = offline ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(cache + c * kTimeCtx);
-    cv[c][0] = t.x; cv[c][1] = t.y; cv[c][2] = t.z; cv[c][3] = t.w;
+  // ext[0..16) = [cache(4) | c rows 0..7 | 0 0 0 0] for the channel pairs (ch, ch+1) and (ch+2, ch+3)
+  float2 e01[16], e23[16];
+  {
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 c0 = offline ? z4 : *reinterpret_cast<const float4*>(cache);
+    const float4 c1 = offline ? z4 : *reinterpret_cast<const float4*>(cache + kTimeCtx);
+    const float4 c2 = offline ? z4 : *reinterpret_cast<const float4*>(cache + 2 * kTimeCtx);
+    const float4 c3 = offline ? z4 : *reinterpret_cast<const float4*>(cache + 3 * kTimeCtx);
+    e01[0] = make_float2(c0.x, c1.x); e01[1] = make_float2(c0.y, c1.y); e01[2] = make_float2(c0.z, c1.z); e01[3] = make_float2(c0.w, c1.w);
+    e23[0] = make_float2(c2.x, c3.x); e23[1] = make_float2(c2.y, c3.y); e23[2] = make_float2(c2.z, c3.z); e23[3] = make_float2(c2.w, c3.w);
   }
-  auto ld_c = [&](int t, float (&o)[4]) {
-    const uint2 raw = *reinterpret_cast<const uint2*>(a.c_bf16 + (size_t)(row0 + t) * kDModel + ch);
-    const float2 p0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-    const float2 p1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
-    o[0] = p0.x; o[1] = p0.y; o[2] = p1.x; o[3] = p1.y;
-  };
-  float win[4][kConvK];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) { win[c][0] = cv[c][0]; win[c][1] = cv[c][1]; win[c][2] = cv[c][2]; win[c][3] = cv[c][3]; }
-#pragma unroll
-  for (int i = 4; i < kConvK; ++i) {
-    const int t = i - 4;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (t < Tq && t < qlen) ld_c(t, v);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) win[c][i] = v[c];
+  for (int t = 0; t < 8; ++t) {
+    uint2 raw = make_uint2(0u, 0u);
+    if (t < nv) raw = *reinterpret_cast<const uint2*>(a.c_bf16 + (size_t)(row0 + t) * kDModel + ch);
+    e01[4 + t] = make_float2(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u));
+    e23[4 + t] = make_float2(__uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u));
   }
-  float nc[4][4];      // [channel][new cache position]
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int idx = Tq + 1 + i;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (idx < 4) {
+  for (int i = 12; i < 16; ++i) { e01[i] = make_float2(0.f, 0.f); e23[i] = make_float2(0.f, 0.f); }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) v[c] = idx == 0 ? cv[c][0] : idx == 1 ? cv[c][1] : idx == 2 ? cv[c][2] : cv[c][3];
-    } else if (idx - 4 < Tq && idx - 4 < qlen) {
-      ld_c(idx - 4, v);
+  for (int t = 0; t < 8; ++t) {
+    if (t < Tq) {
+      float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < kConvK; ++i) { a01 = __ffma2_rn(w01[i], e01[t + i], a01); a23 = __ffma2_rn(w23[i], e23[t + i], a23); }
+      const __nv_bfloat162 h0 = __floats2bfloat162_rn(silu(a01.x + bias4.x), silu(a01.y + bias4.y));
+      const __nv_bfloat162 h1 = __floats2bfloat162_rn(silu(a23.x + bias4.z), silu(a23.y + bias4.w));
+      *reinterpret_cast<uint2*>(a.out.ptr + (size_t)(row0 + t) * a.out.lda + ch) =
+          make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
     }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) nc[c][i] = v[c];
-  }
-  for (int t = 0; t < Tq; ++t) {
-    float o[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float acc = 0.0f;
-#pragma unroll
-      for (int i = 0; i < kConvK; ++i) acc = fmaf(w[c][i], win[c][i], acc);
-      o[c] = silu(acc + bias[c]);
-    }
-    const __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
-    *reinterpret_cast<uint2*>(a.out.ptr + (size_t)(row0 + t) * a.out.lda + ch) =
-        make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-#pragma unroll
-      for (int i = 0; i < kConvK - 1; ++i) win[c][i] = win[c][i + 1];
-    const int tn = t + 5;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (tn < Tq && tn < qlen) ld_c(tn, v);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) win[c][kConvK - 1] = v[c];
   }
   if (!offline) {
+    // new cache = ext[Tq+1 .. Tq+5)   (new_x[:-3][-4:], cache_drop_size 3); Tq is uniform over the CTA
+    float2 n01[4], n23[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) *reinterpret_cast<float4*>(cache + c * kTimeCtx) = make_float4(nc[c][0], nc[c][1], nc[c][2], nc[c][3]);
+    for (int i = 0; i < 4; ++i) { n01[i] = e01[1 + i]; n23[i] = e23[1 + i]; }
+#pragma unroll
+    for (int tt = 1; tt <= 8; ++tt) {
+      if (Tq == tt) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { n01[i] = e01[tt + 1 + i]; n23[i] = e23[tt + 1 + i]; }
+      }
+    }
+    *reinterpret_cast<float4*>(cache) = make_float4(n01[0].x, n01[1].x, n01[2].x, n01[3].x);
+    *reinterpret_cast<float4*>(cache + kTimeCtx) = make_float4(n01[0].y, n01[1].y, n01[2].y, n01[3].y);
+    *reinterpret_cast<float4*>(cache + 2 * kTimeCtx) = make_float4(n23[0].x, n23[1].x, n23[2].x, n23[3].x);
+    *reinterpret_cast<float4*>(cache + 3 * kTimeCtx) = make_float4(n23[0].y, n23[1].y, n23[2].y, n23[3].y);
   }
 }
 void launch_dwconv(const BatchDev& b, const DwConvArgs& a, cudaStream_t st) {
   static const bool quad = [] { const char* v = getenv("PARAKEET_B200_DWCONV4"); return !(v && v[0] == '0'); }();
-  if (quad && a.wt != nullptr && a.c_bf16 != nullptr && a.out.lo_off == 0 && b.B >= 64) {
+  if (quad && a.wt != nullptr && a.c_bf16 != nullptr && a.out.lo_off == 0 && b.B >= 64 && b.max_Tq <= 8) {
     launch_k(dwconv4_kernel, dim3(b.B), dim3(256), 0, st, b, a);
     PKB_CUDA(cudaGetLastError());
     return;

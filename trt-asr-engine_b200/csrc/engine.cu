@@ -77,7 +77,8 @@ inline int sub_len(int L) { return L <= 0 ? 0 : (L - 1) / 2 + 1; }   // floor((L
 struct GemmW {
   __nv_bfloat16* w = nullptr;
   int N = 0, K = 0;
-  TensorMap map;
+  TensorMap map;        // 128-row boxes
+  TensorMap map32;      // 32-row boxes (tail slices of the CTA-pair kernel)
 };
 
 struct ActBuf {
@@ -465,6 +466,7 @@ static GemmW upload_gemm_w(const std::vector<uint16_t>& bits, int N, int K) {
   PKB_CUDA(cudaMemcpy(g.w, bits.data(), bits.size() * 2, cudaMemcpyHostToDevice));   // synchronous: both are complete on return
   PKB_CUDA(cudaDeviceSynchronize());
   make_tensor_map_2d(&g.map, g.w, rows_pad, K, K, 128);
+  make_tensor_map_2d(&g.map32, g.w, rows_pad, K, K, 32);
   return g;
 }
 
@@ -1211,6 +1213,7 @@ static void run_gemm(Engine* eng, const EngineOptions& opt, cudaStream_t st, lon
   g.W = w.w;
   g.M = M; g.N = w.N; g.K = w.K;
   g.M_dev = M_dev;
+  g.map_w32 = &w.map32;
   g.epi = epi;
   ++*launches;
   bool want_tc = opt.gemm_backend == 2 || (opt.gemm_backend == 0 && M > 16);
@@ -2403,6 +2406,7 @@ void Engine::gemm_test(int backend, int M, int N, int K, const float* A, const u
   GemmArgs g;
   g.A = a.ptr; g.lda = K; g.a_lo_off = a.lo_off; g.W = w.w; g.M = M; g.N = N; g.K = K;
   g.epi.mode = EPI_F32; g.epi.out_f32 = d_C; g.epi.ldo = N;
+  g.map_w32 = &w.map32;
   (void)epi_silu;
   if (backend >= 1) {     // 1: heuristic, 2: 128-wide tiles, 3: 256-wide tiles, 4: CTA-pair 256 x 256 tiles (cta_group::2)
     PKB_CHECK(gemm_tc_supported(g), "gemm_test: shape not supported by the tensor-core backend");

@@ -83,6 +83,8 @@ struct GemmArgs {
   int batch = 1;
   int a_col_stride = 0, w_row_stride = 0, out_col_stride = 0;
   const int* M_dev = nullptr;   // optional device-side row count: effective M = min(*M_dev, M) (decode: rows known only on device)
+  const struct TensorMap* map_w32 = nullptr;   // host pointer, optional: W's tensor map with a 32-row box (CTA-pair kernel: column slices
+                                               // of the tiles of a partly filled last round)
   EpiParams epi;
 };
 

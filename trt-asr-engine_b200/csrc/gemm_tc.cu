@@ -639,8 +639,8 @@ __device__ __forceinline__ void mbar_arrive_rank0(uint64_t* bar) {
 
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const GemmArgs g,
-                const int lo_row_off) {
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                const __grid_constant__ CUtensorMap map_w32, const GemmArgs g, const int lo_row_off, const int tail_c, const int full_units) {
   constexpr int BN = 256, BM2 = 256;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -699,35 +699,55 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   pdl_wait();
   const int M = g.M_dev ? min(*g.M_dev, g.M) : g.M;
   const int tiles_m = (M + BM2 - 1) / BM2, tiles_n = (g.N + BN - 1) / BN;
-  const int total_tiles = tiles_m * tiles_n * splits;
+  // Work units.  v < full_units: one 256 x 256 tile (or k-split of one).  The tiles of the last, partly filled round are cut into
+  // tail_c column slices of 256 / tail_c columns each (tail_c = 1, 2 or 4, chosen by the host so that the slices fill the pairs
+  // better than the whole tiles would): v >= full_units walks (tile, slice) with the slice index fastest.  full_units is a multiple
+  // of the pair count, so `v += n_pairs` runs from the full rounds straight into the tail.
+  const int total_tiles = tail_c > 1 ? full_units + (tiles_m * tiles_n * splits - full_units) * tail_c : tiles_m * tiles_n * splits;
+  const int tail_shift = tail_c == 4 ? 2 : tail_c == 2 ? 1 : 0;
+  auto decode = [&](int v, int& unit, int& bn, int& ncol) {
+    if (v < full_units || tail_c <= 1) { unit = v; bn = BN; ncol = 0; }
+    else { const int sub = v - full_units; unit = full_units + (sub >> tail_shift); bn = BN >> tail_shift; ncol = (sub & (tail_c - 1)) * bn; }
+  };
 
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
-      for (int unit = pair; unit < total_tiles; unit += n_pairs) {
+      for (int v = pair; v < total_tiles; v += n_pairs) {
+        int unit, bn, ncol;
+        decode(v, unit, bn, ncol);
         const int tile = unit / splits, sp = unit - tile * splits;
-        const int m0 = (tile % tiles_m) * BM2 + 128 * rank, n0 = (tile / tiles_m) * BN + 128 * rank;
+        const int m0 = (tile % tiles_m) * BM2 + 128 * rank;
+        const int n0 = (tile / tiles_m) * BN + ncol + (bn >> 1) * rank;      // this CTA stages bn / 2 of the unit's W rows
         const int kb_lo = sp * kb_per_pass / splits, kbs = (sp + 1) * kb_per_pass / splits - kb_lo;
         const int num_kb = kbs * n_pass;
+        const uint32_t stage_tx = 2u * (uint32_t)(kTileABytes + (bn >> 1) * 128);
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % kStages2;
           const uint32_t ph = (it / kStages2) & 1;
           const bool w_done = it < pre;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          if (rank == 0 && !w_done) mbar_expect_tx(&full_bar[s], 2 * kStageBytes2);
+          if (rank == 0 && !w_done) mbar_expect_tx(&full_bar[s], stage_tx);
           const uint32_t leader_full = smem_u32(&full_bar[s]) & kPeerBitMask;
           const int pass = kb / kbs, kk = (kb_lo + kb % kbs) * BK;
           tma_load_2d_2sm(sA + s * kTileABytes, &map_a, leader_full, kk, m0 + pass * lo_row_off);
-          if (!w_done) tma_load_2d_2sm(sB + s * kTileABytes, &map_w, leader_full, kk, n0);
+          if (bn == BN) {
+            if (!w_done) tma_load_2d_2sm(sB + s * kTileABytes, &map_w, leader_full, kk, n0);
+          } else {      // column slice: 64 or 32 W rows per CTA through the 32-row box map
+            for (int j = 0; j < (bn >> 6); ++j) tma_load_2d_2sm(sB + s * kTileABytes + j * 4096, &map_w32, leader_full, kk, n0 + 32 * j);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
       int it = 0, tl = 0;
-      for (int unit = pair; unit < total_tiles; unit += n_pairs, ++tl) {
+      for (int v = pair; v < total_tiles; v += n_pairs, ++tl) {
+        int unit, bn, ncol;
+        decode(v, unit, bn, ncol);
         const int sp = unit % splits;
         const int num_kb = ((sp + 1) * kb_per_pass / splits - sp * kb_per_pass / splits) * n_pass;
+        const uint32_t idesc = (kIdesc2 & ~(0x3Fu << 17)) | ((uint32_t)(bn >> 3) << 17);      // N = bn
         const int acc = tl & 1;
         mbar_wait(&tmem_empty_bar[acc], ((tl >> 1) & 1) ^ 1);          // both CTAs' epilogues have drained this buffer
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -741,7 +761,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           const uint64_t db = make_smem_desc(smem_u32(sB + s * kTileABytes));
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            umma_bf16_2sm(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc2, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_2sm(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit_2sm(&empty_bar[s]);
         }
         umma_commit_2sm(&tmem_full_bar[acc]);
@@ -753,13 +773,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int rsel = lane >> 2, c4 = lane & 3;
     const int rd_row = (rsel & 1) * 4 + (rsel >> 1);
     int tl = 0;
-    for (int unit = pair; unit < total_tiles; unit += n_pairs, ++tl) {
+    for (int v = pair; v < total_tiles; v += n_pairs, ++tl) {
+      int unit, bn, ncol_u;
+      decode(v, unit, bn, ncol_u);
+      const int hb = bn >> 1;                                // columns per epilogue half (128, 64 or 32)
       const int tile = unit / splits, sp = unit - tile * splits;
-      const int m0 = (tile % tiles_m) * BM2 + 128 * rank, n0 = (tile / tiles_m) * BN;
+      const int m0 = (tile % tiles_m) * BM2 + 128 * rank, n0 = (tile / tiles_m) * BN + ncol_u;
       const int acc = tl & 1;
       mbar_wait(&tmem_full_bar[acc], (tl >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * hb);
       int ctx[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -772,15 +795,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           const bool row_ok = m_d < M;
           const int ctxd = (MODE == EPI_QKV && row_ok) ? epilogue_row_ctx<MODE>(g.epi, m_d, sp) : 0;
 #pragma unroll 1
-          for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+          for (int c0 = 0; c0 < hb; c0 += 32) {
             uint32_t v[32];
             tmem_ld32(taddr + (uint32_t)c0, v);
-            if (c0 + 32 == BN / 2) {
+            if (c0 + 32 == hb) {
               asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
               __syncwarp();
               if (lane == 0) mbar_arrive_rank0(&tmem_empty_bar[acc]);
             }
-            const int ncol = n0 + half * (BN / 2) + c0;
+            const int ncol = n0 + half * hb + c0;
             if (!row_ok || ncol >= g.N) continue;
             if constexpr (MODE == EPI_GLU_F32) {
               uint32_t o[8];
@@ -843,15 +866,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
               drow = g.epi.out_act + (size_t)m_d * g.epi.lda_out;
           }
 #pragma unroll 1
-          for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+          for (int c0 = 0; c0 < hb; c0 += 32) {
             uint32_t v[32];
             tmem_ld32(taddr + (uint32_t)c0, v);
-            if (c0 + 32 == BN / 2) {
+            if (c0 + 32 == hb) {
               asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
               __syncwarp();
               if (lane == 0) mbar_arrive_rank0(&tmem_empty_bar[acc]);
             }
-            const int ncol = n0 + half * (BN / 2) + c0;
+            const int ncol = n0 + half * hb + c0;
             if (drow != nullptr && ncol < g.N) {
               uint4* dst = reinterpret_cast<uint4*>(drow + ncol + g.epi.n_off);
 #pragma unroll
@@ -872,10 +895,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
       }
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN / 2; c0 += 16) {
+      for (int c0 = 0; c0 < hb; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(taddr + (uint32_t)c0, v);
-        if (c0 + 16 == BN / 2) {
+        if (c0 + 16 == hb) {
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive_rank0(&tmem_empty_bar[acc]);
@@ -886,7 +909,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           *reinterpret_cast<float4*>(stage + lane * kEpiPitch + 4 * j) =
               make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
         __syncwarp();
-        const int n = n0 + half * (BN / 2) + c0 + 4 * c4;
+        const int n = n0 + half * hb + c0 + 4 * c4;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int r = rd_row + 8 * i;
@@ -987,14 +1010,15 @@ void launch_cfg(int grid, const CUtensorMap& ma, const CUtensorMap& mw, const Ge
 }
 
 template <int MODE>
-void launch_cfg2(int pairs, const CUtensorMap& ma, const CUtensorMap& mw, const GemmArgs& g, int lo_row_off, cudaStream_t st) {
+void launch_cfg2(int pairs, const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mw32, const GemmArgs& g, int lo_row_off, int tail_c,
+                 int full_units, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
     PKB_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes2));
     attr = true;
   }
   // cluster size comes from __cluster_dims__; the launch adds the programmatic-dependent-launch attribute
-  launch_k(gemm_tc2_kernel<MODE>, dim3(2 * pairs), dim3(kThreads), kSmemBytes2, st, ma, mw, g, lo_row_off);
+  launch_k(gemm_tc2_kernel<MODE>, dim3(2 * pairs), dim3(kThreads), kSmemBytes2, st, ma, mw, mw32, g, lo_row_off, tail_c, full_units);
 }
 
 void gemm_tc_set_bn(int bn) { g_force_bn = bn; }
@@ -1058,8 +1082,30 @@ void gemm_tc(const GemmArgs& g_in, const TensorMap& map_a, const TensorMap& map_
     const int lo_row_off2 = (int)(g.a_lo_off / g.lda);
     const CUtensorMap& ma2 = *reinterpret_cast<const CUtensorMap*>(&map_a);
     const CUtensorMap& mw2 = *reinterpret_cast<const CUtensorMap*>(&map_w);
+    // Tail: the tiles of the last, partly filled round are cut into 2 or 4 column slices when that shortens the round
+    // (cost of a tail cut c ways = ceil(r c / pairs) / c full-tile times).  Needs the weight's 32-row box map.
+    // A slice is not proportionally cheaper than the tile: every slice re-reads the tile's 256 A rows and a narrow UMMA (N = 128 /
+    // 64) is bound by operand delivery, so a round of half-width slices costs ~0.6 and a round of quarter-width slices ~0.45 of a
+    // full-tile round (PARAKEET_B200_GEMM_TAIL_T2 / _T4, per mille; measured with tools/kbench.cu).  PARAKEET_B200_GEMM_TAIL = largest
+    // cut allowed (0 / 1: never, 2, 4).
+    // Measured (gpurun r2u, M = 6144): only the FFN-up shape gains (39.2 -> 38.0 us); k-split, GLU and QKV shapes lose 8 - 25 % and the
+    // 1024-stream step does not move (15.64 vs 15.65 ms) -- so the cut is OFF by default and kept as a tested option.
+    static const int tail_max = [] { const char* v = getenv("PARAKEET_B200_GEMM_TAIL"); return v ? atoi(v) : 0; }();
+    static const double t2 = [] { const char* v = getenv("PARAKEET_B200_GEMM_TAIL_T2"); return (v ? atoi(v) : 600) / 1000.0; }();
+    static const double t4 = [] { const char* v = getenv("PARAKEET_B200_GEMM_TAIL_T4"); return (v ? atoi(v) : 450) / 1000.0; }();
+    int tail_c = 1, full_units = pair_tiles;
+    if (tail_max >= 2 && g.map_w32 != nullptr && g.M_dev == nullptr && pair_tiles > pairs && pair_tiles % pairs != 0 && g.N % 256 == 0) {
+      const int r = pair_tiles % pairs;
+      double best = 1.0;
+      for (int c = 2; c <= tail_max && c <= 4; c *= 2) {
+        const double cost = (double)((r * c + pairs - 1) / pairs) * (c == 2 ? t2 : t4);
+        if (cost < best - 1e-9) { best = cost; tail_c = c; }
+      }
+      if (tail_c > 1) full_units = pair_tiles - r;
+    }
+    const CUtensorMap& mw32 = tail_c > 1 ? *reinterpret_cast<const CUtensorMap*>(g.map_w32) : mw2;
     switch (g.epi.mode) {
-#define PKB_GEMM_CASE2(MODE) case MODE: launch_cfg2<MODE>(pairs, ma2, mw2, g, lo_row_off2, st); break;
+#define PKB_GEMM_CASE2(MODE) case MODE: launch_cfg2<MODE>(pairs, ma2, mw2, mw32, g, lo_row_off2, tail_c, full_units, st); break;
       PKB_GEMM_CASE2(EPI_BIAS_F32) PKB_GEMM_CASE2(EPI_BIAS_RELU_F32) PKB_GEMM_CASE2(EPI_BIAS_RELU_ACT) PKB_GEMM_CASE2(EPI_BIAS_ROWMAP_F32)
       PKB_GEMM_CASE2(EPI_SILU_ACT) PKB_GEMM_CASE2(EPI_RESADD_F32) PKB_GEMM_CASE2(EPI_QKV) PKB_GEMM_CASE2(EPI_GLU_F32) PKB_GEMM_CASE2(EPI_F32)
       PKB_GEMM_CASE2(EPI_PARTIAL_F32)

@@ -60,9 +60,12 @@ int main(int argc, char** argv) {
   __nv_bfloat16* lnA;
   PKB_CUDA(cudaMalloc(&lnA, rows_a * 1024 * 2));
   TensorMap ma;
-  std::vector<TensorMap> mws(rot);
+  std::vector<TensorMap> mws(rot), mws32(rot);
   make_tensor_map_2d(&ma, A, rows_a, K, K, 128);
-  for (int r = 0; r < rot; ++r) make_tensor_map_2d(&mws[r], W + (size_t)r * rows_w * K, rows_w, K, K, 128);
+  for (int r = 0; r < rot; ++r) {
+    make_tensor_map_2d(&mws[r], W + (size_t)r * rows_w * K, rows_w, K, K, 128);
+    make_tensor_map_2d(&mws32[r], W + (size_t)r * rows_w * K, rows_w, K, K, 32);
+  }
   GemmArgs g;
   g.A = A; g.lda = K; g.W = W; g.M = M; g.N = N; g.K = K;
   if (!strcmp(epi, "resadd")) { g.epi.mode = EPI_RESADD_F32; g.epi.out_f32 = out; g.epi.ldo = N; g.epi.scale = 0.5f; }
@@ -86,6 +89,7 @@ int main(int argc, char** argv) {
     PKB_CUDA(cudaEventRecord(e0, st));
     for (int i = 0; i < iters; ++i) {
       g.W = W + (size_t)(i % rot) * rows_w * K;
+      g.map_w32 = &mws32[i % rot];
       gemm_tc(g, ma, mws[i % rot], st);
       if (with_ln) launch_layernorm(x, M, g1, g1, nullptr, nullptr, 0, ActOut{lnA, 1024, 0}, nullptr, st);
     }
