@@ -1,0 +1,17 @@
+# round 2: persistent cooperative decode loop: whole-utterance parity tests, config-5 shape A/B
+cd ${GRAFT_REPO_ROOT:-/root/repo}
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_offline_long.py -m gpu -q -x > gpurun_out/r2v_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2v_pytest.log; tail -5 gpurun_out/r2v_pytest.log
+timeout 600 python -m pytest tests/test_gpu_engine_api.py tests/test_gpu_decode_extras.py -m gpu -q -x > gpurun_out/r2v_pytest2.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2v_pytest2.log; tail -3 gpurun_out/r2v_pytest2.log
+BB="--no-cpu-baseline --no-config3 --no-latency --steps 5"
+timeout 900 python bench.py $BB > gpurun_out/r2v_bench_persist.json 2> gpurun_out/r2v_bench_persist.err
+PARAKEET_B200_DECODE_PERSIST=0 timeout 900 python bench.py $BB > gpurun_out/r2v_bench_graph.json 2> gpurun_out/r2v_bench_graph.err
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob('gpurun_out/r2v_bench_*.json')):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        print(f, 'ms/step', round(d['ms_per_step'],3), d.get('config5_longform'), d.get('config1_offline_10s'))
+    except Exception as e:
+        print(f, 'ERR', e, open(f.replace('.json','.err')).read()[-600:])
+PY

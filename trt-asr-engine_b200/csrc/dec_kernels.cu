@@ -222,4 +222,374 @@ void launch_force_token(const DecodeDev& d, const int* d_toks, cudaStream_t st) 
   PKB_CUDA(cudaGetLastError());
 }
 
+
+// ================================================================================================ persistent decode loop
+// Whole-utterance decode of a few utterances (<= kPersistMaxB): tens of thousands of passes, each a matrix-vector-sized problem.
+// As a chain of launches (or as the body of a WHILE graph node) a pass costs ~10 kernel boundaries = 32 - 39 us whatever the batch
+// (3.2 of the 5.7 s of BASELINE config 5's shape, 4 x 1 h).  Here ONE cooperative kernel runs the whole loop: a CTA per SM keeps ITS
+// slice of every decoder weight in shared memory for the lifetime of the loop -- 56 rows of the joint output layer [8198,640], the
+// four gate rows of 5 hidden units of each LSTM layer [2560,1280], 5 rows of joint.pred [640,640]: 180 KB per CTA, 24.5 MB over the
+// chip -- and the passes are separated by grid-wide barriers (a monotonic counter in global memory):
+//   phase 1  hidden = relu(E[t] + P) (every CTA, from L2), logits of the CTA's columns, per-entry (max, first argmax) -> global
+//   phase 2  CTA e finishes entry e: argmax over the CTAs' partials, TDT advance rules (tdt_select_kernel's), trace record,
+//            predictor input [emb(token); h0] for emitting entries
+//   phase 3/4  LSTM layers (only when some entry emitted): gate rows of the CTA's units, cell update, state + next input
+//   phase 5  joint.pred rows of the CTA -> P
+// Activations stay f32 (the launch-chain path feeds bf16 hi + lo planes: 16 mantissa bits), weights bf16, f32 accumulation.
+namespace {
+constexpr int kPdThreads = 256, kPdWarps = kPdThreads / 32;
+constexpr int kPdChunk = 8;                                     // entries processed together (register accumulators)
+constexpr int kPdColsMax = 56, kPdUnitsMax = 5;                 // per-CTA slice capacity: a grid of >= 147 CTAs (8198 / 56, 640 / 5)
+constexpr size_t kPdSmem = (size_t)kPdColsMax * kJointH * 2 + 2 * (size_t)kPdUnitsMax * 4 * 2 * kPredH * 2 + (size_t)kPdUnitsMax * kPredH * 2 +
+                           (size_t)kPdChunk * 2 * kPredH * 4;      // 221 440 B of the 227 KB a CTA may own
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// grid barrier number `k` (1-based): every CTA adds 1 to a monotonic counter and waits until k * G arrivals have been seen
+__device__ __forceinline__ bool pd_grid_sync(unsigned* bar, unsigned target, int* err) {
+  __syncthreads();
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    int ok = 1;
+    long long spins = 0;
+    while (ld_acquire_u32(bar) < target) {
+      if (++spins > (1ll << 27)) { ok = 0; atomicExch(err, 1); break; }      // watchdog: never hang the device
+      if ((spins & 1023) == 0 && *reinterpret_cast<volatile int*>(err) != 0) { ok = 0; break; }
+    }
+    __threadfence();
+    s_ok = ok;
+  }
+  __syncthreads();
+  return s_ok != 0;
+}
+// dot products of one bf16 weight row (shared memory) with the first NE of up to 8 f32 vectors (shared memory, pitch `ldx`), K % 128 == 0
+template <int K, int NE>
+__device__ __forceinline__ void pd_dot_ne(const __nv_bfloat16* __restrict__ w, const float* __restrict__ x, int ldx, int lane, float (&acc)[kPdChunk]) {
+#pragma unroll
+  for (int e = 0; e < kPdChunk; ++e) acc[e] = 0.0f;
+#pragma unroll
+  for (int k0 = 0; k0 < K; k0 += 128) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(w + k0 + lane * 4);
+    const float w0 = __uint_as_float(raw.x << 16), w1 = __uint_as_float(raw.x & 0xffff0000u);
+    const float w2 = __uint_as_float(raw.y << 16), w3 = __uint_as_float(raw.y & 0xffff0000u);
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const float4 v = *reinterpret_cast<const float4*>(x + (size_t)e * ldx + k0 + lane * 4);
+      acc[e] = fmaf(w0, v.x, acc[e]); acc[e] = fmaf(w1, v.y, acc[e]); acc[e] = fmaf(w2, v.z, acc[e]); acc[e] = fmaf(w3, v.w, acc[e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < NE; ++e) acc[e] = warp_sum(acc[e]);
+}
+// (the per-entry result does not depend on how many entries share the pass: same summation order for every NE)
+template <int K>
+__device__ __forceinline__ void pd_dot8(const __nv_bfloat16* __restrict__ w, const float* __restrict__ x, int ldx, int lane, int ne, float (&acc)[kPdChunk]) {
+  if (ne <= 1) pd_dot_ne<K, 1>(w, x, ldx, lane, acc);
+  else if (ne <= 2) pd_dot_ne<K, 2>(w, x, ldx, lane, acc);
+  else if (ne <= 4) pd_dot_ne<K, 4>(w, x, ldx, lane, acc);
+  else pd_dot_ne<K, 8>(w, x, ldx, lane, acc);
+}
+}  // namespace
+
+__global__ void __launch_bounds__(kPdThreads, 1)
+decode_persistent_kernel(DecPersistArgs a) {
+  extern __shared__ __align__(16) uint8_t pd_raw[];
+  const DecodeDev& d = a.d;
+  const int G = gridDim.x, cta = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cols_per = (kJointOut + G - 1) / G, units_per = (kPredH + G - 1) / G;
+  const int c0 = cta * cols_per, ncols = max(0, min(kJointOut, c0 + cols_per) - c0);
+  const int u0 = cta * units_per, nunits = max(0, min(kPredH, u0 + units_per) - u0);
+  __nv_bfloat16* s_wout = reinterpret_cast<__nv_bfloat16*>(pd_raw);                       // [ncols][640]
+  __nv_bfloat16* s_wl0 = s_wout + (size_t)kPdColsMax * kJointH;                           // [nunits][4][1280]
+  __nv_bfloat16* s_wl1 = s_wl0 + (size_t)kPdUnitsMax * 4 * 2 * kPredH;
+  __nv_bfloat16* s_wjp = s_wl1 + (size_t)kPdUnitsMax * 4 * 2 * kPredH;                    // [nunits][640]
+  float* s_x = reinterpret_cast<float*>(s_wjp + (size_t)kPdUnitsMax * kPredH);            // [8][1280] activations of the current chunk
+  __shared__ float s_red_v[kPdWarps][kPdChunk];
+  __shared__ int s_red_i[kPdWarps][kPdChunk];
+  __shared__ float s_gates[kPdUnitsMax * 4][kPdChunk];
+  __shared__ int s_flag[kPdChunk];
+
+  // ---- weights of this CTA -> shared memory (once)
+  for (int i = tid; i < ncols * (kJointH / 8); i += kPdThreads) {
+    const int r = i / (kJointH / 8), c = i % (kJointH / 8);
+    reinterpret_cast<uint4*>(s_wout + (size_t)r * kJointH)[c] = __ldg(reinterpret_cast<const uint4*>(a.w_out + (size_t)(c0 + r) * kJointH) + c);
+  }
+  for (int i = tid; i < nunits * 4 * (2 * kPredH / 8); i += kPdThreads) {
+    const int r = i / (2 * kPredH / 8), c = i % (2 * kPredH / 8);      // r = unit * 4 + gate
+    const size_t grow = (size_t)((r & 3) * kPredH + u0 + (r >> 2)) * (2 * kPredH);
+    reinterpret_cast<uint4*>(s_wl0 + (size_t)r * 2 * kPredH)[c] = __ldg(reinterpret_cast<const uint4*>(a.w_l0 + grow) + c);
+    reinterpret_cast<uint4*>(s_wl1 + (size_t)r * 2 * kPredH)[c] = __ldg(reinterpret_cast<const uint4*>(a.w_l1 + grow) + c);
+  }
+  for (int i = tid; i < nunits * (kPredH / 8); i += kPdThreads) {
+    const int r = i / (kPredH / 8), c = i % (kPredH / 8);
+    reinterpret_cast<uint4*>(s_wjp + (size_t)r * kPredH)[c] = __ldg(reinterpret_cast<const uint4*>(a.w_jp + (size_t)(u0 + r) * kPredH) + c);
+  }
+  __syncthreads();
+
+  unsigned nbar = 0;
+  int pass = 0;
+  for (; pass < a.max_passes; ++pass) {
+    int* flags = a.flags + 2 * (pass & 1);      // [0] any entry emitted in this pass, [1] entries still active after it
+    // ================= phase 1: joint output layer, columns [c0, c0 + ncols)
+    for (int e0 = 0; e0 < d.B; e0 += kPdChunk) {
+      const int ne = min(kPdChunk, d.B - e0);
+      if (tid < kPdChunk) s_flag[tid] = (tid < ne && __ldcg(d.active + e0 + tid) != 0) ? 1 : 0;
+      __syncthreads();
+      bool any = false;
+#pragma unroll
+      for (int e = 0; e < kPdChunk; ++e) any |= s_flag[e] != 0;
+      if (any) {
+        for (int i = tid; i < kPdChunk * (kJointH / 4); i += kPdThreads) {
+          const int e = i / (kJointH / 4), c = i % (kJointH / 4);
+          float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (s_flag[e]) {
+            const int ge = e0 + e;
+            const float4 E = __ldcg(reinterpret_cast<const float4*>(d.enc_proj + (size_t)(d.row_off[ge] + __ldcg(d.t_cur + ge)) * kJointH) + c);
+            const float4 P = __ldcg(reinterpret_cast<const float4*>(d.pred_proj + (size_t)d.slot[ge] * kJointH) + c);
+            h = make_float4(fmaxf(E.x + P.x, 0.f), fmaxf(E.y + P.y, 0.f), fmaxf(E.z + P.z, 0.f), fmaxf(E.w + P.w, 0.f));
+          }
+          reinterpret_cast<float4*>(s_x + (size_t)e * kJointH)[c] = h;
+        }
+        __syncthreads();
+        float best[kPdChunk];
+        int bidx[kPdChunk];
+#pragma unroll
+        for (int e = 0; e < kPdChunk; ++e) { best[e] = -INFINITY; bidx[e] = 0x7fffffff; }
+        for (int j = warp; j < ncols; j += kPdWarps) {      // ascending columns per warp: first maximum wins
+          float acc[kPdChunk];
+          pd_dot8<kJointH>(s_wout + (size_t)j * kJointH, s_x, kJointH, lane, ne, acc);
+          const int col = c0 + j;
+          const float bias = __ldg(a.b_out + col);
+#pragma unroll
+          for (int e = 0; e < kPdChunk; ++e) {
+            float y = acc[e] + bias;
+            if (y != y) y = -100.0f;                                      // NaN logits -> -100 (parakeet_trt.cpp:2971)
+            if (col == kBlank) y -= d.blank_penalty;                      // PARAKEET_BLANK_PENALTY (:3175-3178)
+            if (col < kVocab) { if (y > best[e]) { best[e] = y; bidx[e] = col; } }
+            else if (lane == 0 && e < ne) a.dur[(size_t)(e0 + e) * kNDur + (col - kVocab)] = y;
+          }
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int e = 0; e < kPdChunk; ++e) { s_red_v[warp][e] = best[e]; s_red_i[warp][e] = bidx[e]; }
+        }
+        __syncthreads();
+        if (tid < ne) {
+          float bv = s_red_v[0][tid];
+          int bi = s_red_i[0][tid];
+          for (int w = 1; w < kPdWarps; ++w)
+            if (s_red_v[w][tid] > bv || (s_red_v[w][tid] == bv && s_red_i[w][tid] < bi)) { bv = s_red_v[w][tid]; bi = s_red_i[w][tid]; }
+          a.part_val[(size_t)(e0 + tid) * G + cta] = bv;
+          a.part_idx[(size_t)(e0 + tid) * G + cta] = bi;
+        }
+      }
+      __syncthreads();
+    }
+    if (!pd_grid_sync(a.bar, ++nbar * G, a.err)) return;
+
+    // ================= phase 2: CTA e finishes entry e (greedy selection + TDT rules), predictor input for emitting entries
+    if (cta == 0 && tid == 0) { a.flags[2 * ((pass + 1) & 1)] = 0; a.flags[2 * ((pass + 1) & 1) + 1] = 0; }
+    for (int e = cta; e < d.B; e += G) {
+      __shared__ int s_tok;
+      if (tid == 0) s_tok = -1;
+      if (__ldcg(d.active + e) != 0) {
+        float best = -INFINITY;
+        int bidx = 0x7fffffff;
+        for (int i = tid; i < G; i += kPdThreads) {
+          const float v = __ldcg(a.part_val + (size_t)e * G + i);
+          const int ix = __ldcg(a.part_idx + (size_t)e * G + i);
+          if (v > best || (v == best && ix < bidx)) { best = v; bidx = ix; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+          if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+        }
+        if (lane == 0) { s_red_v[warp][0] = best; s_red_i[warp][0] = bidx; }
+        __syncthreads();
+        if (tid == 0) {
+          for (int w = 1; w < kPdWarps; ++w)
+            if (s_red_v[w][0] > best || (s_red_v[w][0] == best && s_red_i[w][0] < bidx)) { best = s_red_v[w][0]; bidx = s_red_i[w][0]; }
+          int tok = bidx;
+          const int slot = d.slot[e];
+          if (d.punct_suppress && d.n_emitted[slot] == 0 && tok < kBlank && ((d.punct_bits[tok >> 5] >> (tok & 31)) & 1u)) tok = kBlank;
+          int dbest = 0;
+          float dv = __ldcg(a.dur + (size_t)e * kNDur);
+          if (dv != dv) dv = -100.0f;
+          for (int i = 1; i < kNDur; ++i) {
+            float v = __ldcg(a.dur + (size_t)e * kNDur + i);
+            if (v != v) v = -100.0f;
+            if (v > dv) { dv = v; dbest = i; }
+          }
+          const int dur = dbest;
+          const int adv = (tok == kBlank && dur == 0) ? 1 : dur;
+          int t = d.t_cur[e], ns = d.n_sym[e];
+          const int k = d.n_steps[e];
+          if (k < d.max_steps) {
+            int* st = d.steps + ((size_t)e * d.max_steps + k) * 3;
+            st[0] = t; st[1] = tok; st[2] = dur;
+            d.n_steps[e] = k + 1;
+          }
+          if (tok != kBlank) {
+            d.n_emitted[slot] += 1;
+            d.y_id[slot] = tok;
+            d.emit_tok[e] = tok;
+            d.pred_rowmap[e] = slot;
+            atomicExch(flags, 1);
+            s_tok = tok;
+          } else {
+            d.emit_tok[e] = -1;
+            d.pred_rowmap[e] = -1;
+          }
+          ns += 1;
+          if (adv == 0) {
+            if (ns >= d.max_symbols) { t += 1; ns = 0; }
+          } else {
+            t += adv;
+            ns = 0;
+          }
+          d.t_cur[e] = t;
+          d.n_sym[e] = ns;
+          if (t >= d.t_enc[e]) d.active[e] = 0;
+          else atomicAdd(flags + 1, 1);
+        }
+        __syncthreads();
+        const int tok = s_tok;
+        if (tok >= 0) {      // layer-0 input [emb(tok) ; h0]
+          const float* h0 = d.pred_h + (size_t)d.slot[e] * kPredL * kPredH;
+          for (int c = tid; c < 2 * kPredH; c += kPdThreads)
+            a.xin[(size_t)e * 2 * kPredH + c] = c < kPredH ? __bfloat162float(d.embed[(size_t)tok * kPredH + c]) : __ldcg(h0 + c - kPredH);
+        }
+      } else if (tid == 0) {
+        d.emit_tok[e] = -1;
+        d.pred_rowmap[e] = -1;
+      }
+      __syncthreads();
+    }
+    if (!pd_grid_sync(a.bar, ++nbar * G, a.err)) return;
+    const int any_emit = __ldcg(flags), n_active = __ldcg(flags + 1);
+
+    if (any_emit) {
+      // ================= phases 3 and 4: LSTM layers, units [u0, u0 + nunits) of this CTA
+      for (int layer = 0; layer < kPredL; ++layer) {
+        const __nv_bfloat16* s_w = layer == 0 ? s_wl0 : s_wl1;
+        const float* bias = layer == 0 ? a.b_l0 : a.b_l1;
+        const float* xsrc = layer == 0 ? a.xin : a.x1;
+        for (int e0 = 0; e0 < d.B && nunits > 0; e0 += kPdChunk) {
+          const int ne = min(kPdChunk, d.B - e0);
+          if (tid < kPdChunk) s_flag[tid] = (tid < ne && __ldcg(d.emit_tok + e0 + tid) >= 0) ? 1 : 0;
+          __syncthreads();
+          bool any = false;
+#pragma unroll
+          for (int e = 0; e < kPdChunk; ++e) any |= s_flag[e] != 0;
+          if (any) {
+            for (int i = tid; i < kPdChunk * (2 * kPredH / 4); i += kPdThreads) {
+              const int e = i / (2 * kPredH / 4), c = i % (2 * kPredH / 4);
+              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (s_flag[e]) v = __ldcg(reinterpret_cast<const float4*>(xsrc + (size_t)(e0 + e) * 2 * kPredH) + c);
+              reinterpret_cast<float4*>(s_x + (size_t)e * 2 * kPredH)[c] = v;
+            }
+            __syncthreads();
+            for (int r = warp; r < nunits * 4; r += kPdWarps) {
+              float acc[kPdChunk];
+              pd_dot8<2 * kPredH>(s_w + (size_t)r * 2 * kPredH, s_x, 2 * kPredH, lane, ne, acc);
+              if (lane == 0) {
+                const float b = __ldg(bias + (r & 3) * kPredH + u0 + (r >> 2));
+#pragma unroll
+                for (int e = 0; e < kPdChunk; ++e) s_gates[r][e] = acc[e] + b;
+              }
+            }
+            __syncthreads();
+            if (tid < nunits * kPdChunk) {
+              const int u = tid / kPdChunk, e = tid % kPdChunk;
+              if (s_flag[e]) {
+                const int ge = e0 + e, j = u0 + u, slot = d.slot[ge];
+                float* h = d.pred_h + ((size_t)slot * kPredL + layer) * kPredH;
+                float* c = d.pred_c + ((size_t)slot * kPredL + layer) * kPredH;
+                const float ig = sigmoidf_acc(s_gates[u * 4 + 0][e]);
+                const float fg = sigmoidf_acc(s_gates[u * 4 + 1][e]);
+                const float gg = tanhf(s_gates[u * 4 + 2][e]);
+                const float og = sigmoidf_acc(s_gates[u * 4 + 3][e]);
+                const float cn = fg * __ldcg(c + j) + ig * gg;
+                const float hn = og * tanhf(cn);
+                c[j] = cn;
+                h[j] = hn;
+                if (layer == 0) {
+                  a.x1[(size_t)ge * 2 * kPredH + j] = hn;
+                  a.x1[(size_t)ge * 2 * kPredH + kPredH + j] = __ldcg(d.pred_h + ((size_t)slot * kPredL + 1) * kPredH + j);
+                } else {
+                  d.pred_g[(size_t)slot * kPredH + j] = hn;
+                  a.gvec[(size_t)ge * kPredH + j] = hn;
+                }
+              }
+            }
+          }
+          __syncthreads();
+        }
+        if (!pd_grid_sync(a.bar, ++nbar * G, a.err)) return;
+      }
+      // ================= phase 5: joint.pred rows [u0, u0 + nunits) -> P[slot]
+      for (int e0 = 0; e0 < d.B && nunits > 0; e0 += kPdChunk) {
+        const int ne = min(kPdChunk, d.B - e0);
+        if (tid < kPdChunk) s_flag[tid] = (tid < ne && __ldcg(d.emit_tok + e0 + tid) >= 0) ? 1 : 0;
+        __syncthreads();
+        bool any = false;
+#pragma unroll
+        for (int e = 0; e < kPdChunk; ++e) any |= s_flag[e] != 0;
+        if (any) {
+          for (int i = tid; i < kPdChunk * (kPredH / 4); i += kPdThreads) {
+            const int e = i / (kPredH / 4), c = i % (kPredH / 4);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s_flag[e]) v = __ldcg(reinterpret_cast<const float4*>(a.gvec + (size_t)(e0 + e) * kPredH) + c);
+            reinterpret_cast<float4*>(s_x + (size_t)e * kPredH)[c] = v;
+          }
+          __syncthreads();
+          for (int r = warp; r < nunits; r += kPdWarps) {
+            float acc[kPdChunk];
+            pd_dot8<kPredH>(s_wjp + (size_t)r * kPredH, s_x, kPredH, lane, ne, acc);
+            if (lane == 0) {
+              const float b = __ldg(a.b_jp + u0 + r);
+#pragma unroll
+              for (int e = 0; e < kPdChunk; ++e)
+                if (s_flag[e]) d.pred_proj[(size_t)d.slot[e0 + e] * kJointH + u0 + r] = acc[e] + b;
+            }
+          }
+        }
+        __syncthreads();
+      }
+      if (!pd_grid_sync(a.bar, ++nbar * G, a.err)) return;
+    }
+    if (n_active == 0) { ++pass; break; }
+  }
+  if (cta == 0 && tid == 0) { *a.passes_out = pass; *d.n_active = 0; *d.m_pred = 0; *d.m_joint = 0; }
+}
+
+size_t decode_persistent_smem() { return kPdSmem; }
+
+// Cooperative launch (all CTAs co-resident: the grid barrier needs it).  Returns false when the device cannot hold `grid` CTAs of
+// this kernel at once (the caller then takes the launch-chain path).
+bool launch_decode_persistent(const DecPersistArgs& a, int grid, cudaStream_t st) {
+  static int max_ctas = -1;
+  if (max_ctas < 0) {
+    PKB_CUDA(cudaFuncSetAttribute(decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPdSmem));
+    int per_sm = 0, dev = 0, sms = 0;
+    PKB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_persistent_kernel, kPdThreads, kPdSmem));
+    PKB_CUDA(cudaGetDevice(&dev));
+    PKB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    max_ctas = per_sm * sms;
+  }
+  const int cols_per = (kJointOut + grid - 1) / grid, units_per = (kPredH + grid - 1) / grid;
+  if (grid > max_ctas || cols_per > kPdColsMax || units_per > kPdUnitsMax || a.d.B > kPersistMaxB || a.d.B > grid) return false;
+  DecPersistArgs args = a;
+  void* params[] = {&args};
+  PKB_CUDA(cudaLaunchCooperativeKernel((const void*)decode_persistent_kernel, dim3(grid), dim3(kPdThreads), params, kPdSmem, st));
+  return true;
+}
+
 }  // namespace pkb

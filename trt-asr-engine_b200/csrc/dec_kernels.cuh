@@ -59,6 +59,27 @@ struct DecodeDev {
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 #endif
 
+// Persistent decode loop (dec_kernels.cu): one cooperative kernel runs every pass of a whole-utterance decode of <= kPersistMaxB entries
+constexpr int kPersistMaxB = 64;
+struct DecPersistArgs {
+  DecodeDev d;
+  const __nv_bfloat16* w_out; const float* b_out;     // joint output layer [8198,640], [8198]
+  const __nv_bfloat16* w_l0; const float* b_l0;       // LSTM layer 0 [2560,1280] = [weight_ih | weight_hh], [2560]
+  const __nv_bfloat16* w_l1; const float* b_l1;
+  const __nv_bfloat16* w_jp; const float* b_jp;       // joint.pred [640,640], [640]
+  unsigned* bar;            // grid-barrier counter (zeroed before the launch)
+  int* err;                 // set when a barrier times out (zeroed before the launch)
+  int* flags;               // [2][2] per-pass (any emission, still-active count), zeroed before the launch
+  float* part_val; int* part_idx;   // [B][grid] per-CTA (max, first argmax) of the token head
+  float* dur;               // [B][5]
+  float* xin; float* x1;    // [B][1280] LSTM layer inputs
+  float* gvec;              // [B][640]
+  int max_passes;
+  int* passes_out;
+};
+size_t decode_persistent_smem();
+bool launch_decode_persistent(const DecPersistArgs& a, int grid, cudaStream_t st);
+
 void launch_decode_begin(const DecodeDev& d, cudaStream_t st);
 void launch_decode_iter_reset(const DecodeDev& d, cudaStream_t st);
 void launch_joint_hidden(const DecodeDev& d, cudaStream_t st);

@@ -312,6 +312,11 @@ struct Engine::Impl {
   cudaGraph_t lf_loop_graph = nullptr;         // decode-loop graph of the whole-utterance call in flight (run_decode_loop_graph)
   cudaGraphExec_t lf_loop_exec = nullptr;
   int lf_loop_body_launches = 0, lf_loop_prof_idx = -1, lf_loop_B = 0;
+  // persistent decode loop (dec_kernels.cu): scratch for <= kPersistMaxB entries, allocated on first use
+  bool lf_persist_active = false;
+  unsigned* pd_bar = nullptr;      // [0] barrier counter, [1] error flag, [2..5] per-pass flags, [6] passes
+  float *pd_part_val = nullptr, *pd_dur = nullptr, *pd_xin = nullptr, *pd_x1 = nullptr, *pd_gvec = nullptr;
+  int* pd_part_idx = nullptr;
   double loop_ms = 0.0, loop_bytes = 0.0;      // decode loops run inside step graphs since the last decode_loop_stats(reset)
   long long loop_passes = 0, loop_count = 0;
   int* meta2 = nullptr;                        // device [2]: (slot, head) of a single-stream import / export
@@ -1543,6 +1548,18 @@ bool Engine::run_decode_loop_graph(const BatchDev& b, DecodeDev d) {
 // after the stream has been synchronised: kernels run by the loop graph, its algorithmic bytes (profile mode), release
 void Engine::finish_decode_loop_graph(long long passes) {
   Impl& im = *im_;
+  if (im.lf_persist_active) {      // the loop ran as one cooperative kernel
+    im.lf_persist_active = false;
+    unsigned st[7] = {0, 0, 0, 0, 0, 0, 0};
+    PKB_CUDA(cudaMemcpy(st, im.pd_bar, sizeof(st), cudaMemcpyDeviceToHost));
+    PKB_CHECK(st[1] == 0, "persistent decode loop: a grid barrier timed out");
+    launches_ += 1;
+    if (im.profile && im.lf_loop_prof_idx >= 0)
+      im.prof_flops[im.lf_loop_prof_idx] =
+          (double)st[6] * ((double)kJointOut * kJointH * 2.0 + kJointOut * 4.0 + (double)im.lf_loop_B * (2.0 * kJointH * 4.0 + 12.0));
+    im.lf_loop_prof_idx = -1;
+    return;
+  }
   if (!im.lf_loop_exec) return;
   launches_ += passes * im.lf_loop_body_launches;
   if (im.profile && im.lf_loop_prof_idx >= 0)
@@ -1559,6 +1576,40 @@ void Engine::run_decode(const BatchDev& b, const int* slots, int* steps, int max
   decode_prologue(b, d, enc_proj_rows == nullptr);
   const int max_iters = b.max_tenc * (kMaxSymbols + 1) + 2;
   const int prof_i = prof_begin(3, 0.0);      // the whole loop; its algorithmic bytes are known when it ends
+  // whole-utterance decode of a few utterances: the whole loop as ONE cooperative kernel with the decoder weights resident in shared
+  // memory (PARAKEET_B200_DECODE_PERSIST=0: WHILE-graph / launch chain instead)
+  static const bool persist_allowed = [] { const char* v = getenv("PARAKEET_B200_DECODE_PERSIST"); return !(v && v[0] == '0'); }();
+  if (persist_allowed && steps != nullptr && b.max_tenc > 4 * kMaxTq && b.B <= kPersistMaxB && b.B <= sm_count_) {
+    if (!im.pd_bar) {
+      im.pd_bar = dev_alloc<unsigned>(8);
+      im.pd_part_val = dev_alloc<float>((size_t)kPersistMaxB * sm_count_);
+      im.pd_part_idx = dev_alloc<int>((size_t)kPersistMaxB * sm_count_);
+      im.pd_dur = dev_alloc<float>((size_t)kPersistMaxB * kNDur);
+      im.pd_xin = dev_alloc<float>((size_t)kPersistMaxB * 2 * kPredH);
+      im.pd_x1 = dev_alloc<float>((size_t)kPersistMaxB * 2 * kPredH);
+      im.pd_gvec = dev_alloc<float>((size_t)kPersistMaxB * kPredH);
+      for (void* p : {(void*)im.pd_bar, (void*)im.pd_part_val, (void*)im.pd_part_idx, (void*)im.pd_dur, (void*)im.pd_xin, (void*)im.pd_x1, (void*)im.pd_gvec})
+        im.dev_allocs.push_back(p);      // released with the engine
+    }
+    PKB_CUDA(cudaMemsetAsync(im.pd_bar, 0, 8 * sizeof(unsigned), st_));
+    DecPersistArgs a{};
+    a.d = d;
+    a.w_out = im.joint_out.w; a.b_out = im.joint_out_b;
+    a.w_l0 = im.lstm[0].w; a.b_l0 = im.lstm_b[0];
+    a.w_l1 = im.lstm[1].w; a.b_l1 = im.lstm_b[1];
+    a.w_jp = im.joint_pred.w; a.b_jp = im.joint_pred_b;
+    a.bar = im.pd_bar; a.err = reinterpret_cast<int*>(im.pd_bar + 1); a.flags = reinterpret_cast<int*>(im.pd_bar + 2);
+    a.passes_out = reinterpret_cast<int*>(im.pd_bar + 6);
+    a.part_val = im.pd_part_val; a.part_idx = im.pd_part_idx; a.dur = im.pd_dur; a.xin = im.pd_xin; a.x1 = im.pd_x1; a.gvec = im.pd_gvec;
+    a.max_passes = max_iters;
+    if (launch_decode_persistent(a, sm_count_, st_)) {
+      im.lf_persist_active = true;
+      im.lf_loop_prof_idx = prof_i;
+      im.lf_loop_B = b.B;
+      if (prof_i >= 0) { im.prof_flops[prof_i] = 0.0; prof_end(prof_i); }
+      return;
+    }
+  }
   if (steps != nullptr && b.max_tenc > 4 * kMaxTq && run_decode_loop_graph(b, d)) {
     // whole-utterance decode, device-side loop: passes (and with them the algorithmic bytes) are known once the traces are back
     im.lf_loop_prof_idx = prof_i;
