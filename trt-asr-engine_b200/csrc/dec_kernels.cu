@@ -398,6 +398,15 @@ decode_persistent_kernel(DecPersistArgs a) {
       __shared__ int s_tok;
       if (tid == 0) s_tok = -1;
       if (__ldcg(d.active + e) != 0) {
+        // thread 0 requests the scalars of the advance rules now, so that their round trips overlap the reduction below
+        int p_slot = 0, p_nem = 0, p_t = 0, p_ns = 0, p_k = 0, p_tenc = 0;
+        float p_dl[kNDur] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        if (tid == 0) {
+          p_slot = d.slot[e]; p_t = d.t_cur[e]; p_ns = d.n_sym[e]; p_k = d.n_steps[e]; p_tenc = d.t_enc[e];
+#pragma unroll
+          for (int i = 0; i < kNDur; ++i) p_dl[i] = __ldcg(a.dur + (size_t)e * kNDur + i);
+          p_nem = d.n_emitted[p_slot];
+        }
         float best = -INFINITY;
         int bidx = 0x7fffffff;
         for (int i = tid; i < G; i += kPdThreads) {
@@ -417,27 +426,28 @@ decode_persistent_kernel(DecPersistArgs a) {
           for (int w = 1; w < kPdWarps; ++w)
             if (s_red_v[w][0] > best || (s_red_v[w][0] == best && s_red_i[w][0] < bidx)) { best = s_red_v[w][0]; bidx = s_red_i[w][0]; }
           int tok = bidx;
-          const int slot = d.slot[e];
-          if (d.punct_suppress && d.n_emitted[slot] == 0 && tok < kBlank && ((d.punct_bits[tok >> 5] >> (tok & 31)) & 1u)) tok = kBlank;
+          const int slot = p_slot;
+          if (d.punct_suppress && p_nem == 0 && tok < kBlank && ((d.punct_bits[tok >> 5] >> (tok & 31)) & 1u)) tok = kBlank;
           int dbest = 0;
-          float dv = __ldcg(a.dur + (size_t)e * kNDur);
+          float dv = p_dl[0];
           if (dv != dv) dv = -100.0f;
+#pragma unroll
           for (int i = 1; i < kNDur; ++i) {
-            float v = __ldcg(a.dur + (size_t)e * kNDur + i);
+            float v = p_dl[i];
             if (v != v) v = -100.0f;
             if (v > dv) { dv = v; dbest = i; }
           }
           const int dur = dbest;
           const int adv = (tok == kBlank && dur == 0) ? 1 : dur;
-          int t = d.t_cur[e], ns = d.n_sym[e];
-          const int k = d.n_steps[e];
+          int t = p_t, ns = p_ns;
+          const int k = p_k;
           if (k < d.max_steps) {
             int* st = d.steps + ((size_t)e * d.max_steps + k) * 3;
             st[0] = t; st[1] = tok; st[2] = dur;
             d.n_steps[e] = k + 1;
           }
           if (tok != kBlank) {
-            d.n_emitted[slot] += 1;
+            d.n_emitted[slot] = p_nem + 1;
             d.y_id[slot] = tok;
             d.emit_tok[e] = tok;
             d.pred_rowmap[e] = slot;
@@ -456,7 +466,7 @@ decode_persistent_kernel(DecPersistArgs a) {
           }
           d.t_cur[e] = t;
           d.n_sym[e] = ns;
-          if (t >= d.t_enc[e]) d.active[e] = 0;
+          if (t >= p_tenc) d.active[e] = 0;
           else atomicAdd(flags + 1, 1);
         }
         __syncthreads();
