@@ -8,7 +8,8 @@ import numpy as np
 import binding
 from make_synthetic_model import ensure_model
 from synth_audio import synth_clip
-model = ensure_model(os.path.join(ROOT, "models", "synth24"), n_layers=24, seed=0)
+_L = int(os.environ.get("LAYERS", "24"))
+model = ensure_model(os.path.join(ROOT, "models", f"synth{_L}"), n_layers=_L, seed=0)
 n = int(os.environ.get("STREAMS", "1"))
 eng = binding.Engine(model, max_streams=n, precision=int(os.environ.get("PREC", "0")))
 sids = np.array([eng.open() for _ in range(n)], np.int32)

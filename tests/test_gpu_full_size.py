@@ -22,6 +22,17 @@ N_STREAMS, N_DISTINCT, N_CHUNKS, TAU = 1024, 16, 10, 0.25
 
 @pytest.mark.parametrize("precision", [0, 1], ids=["bf16", "precise"])
 def test_1024_streams_duplicates_and_oracle(model_full, features_ref, precision):
+    _duplicates_and_oracle(model_full, features_ref, precision, N_STREAMS, N_DISTINCT, N_CHUNKS)
+
+
+@pytest.mark.parametrize("precision", [0, 1], ids=["bf16", "precise"])
+def test_128_streams_duplicates_and_oracle(model_full, features_ref, precision):
+    """The per-GPU batch of the 8-GPU configuration (768 packed rows): its own kernel choices -- 128 x 256 split-K tiles for the
+    residual GEMMs, the per-row LayerNorm with three / four partial-sum planes, single-CTA GEMMs everywhere."""
+    _duplicates_and_oracle(model_full, features_ref, precision, 128, 8, 6)
+
+
+def _duplicates_and_oracle(model_full, features_ref, precision, N_STREAMS, N_DISTINCT, N_CHUNKS):
     secs = 0.41 + 0.24 * N_CHUNKS + 0.5
     feats = []
     for i in range(N_DISTINCT):
@@ -60,7 +71,7 @@ def test_1024_streams_duplicates_and_oracle(model_full, features_ref, precision)
             if k == 0 and all(a > TAU and b_ > TAU for a, b_ in mg):
                 first_conf += 1
                 first_same += int(traces[d][k] == want)
-    print(f"\n[1024 streams precision={precision}] chunks identical to the oracle: {same}/{total}; confident first chunks {first_same}/{first_conf}")
+    print(f"\n[{N_STREAMS} streams precision={precision}] chunks identical to the oracle: {same}/{total}; confident first chunks {first_same}/{first_conf}")
     if precision == 1:
         assert same >= 0.99 * total, f"{same}/{total}"
     else:

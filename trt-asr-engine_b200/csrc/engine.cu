@@ -1267,6 +1267,17 @@ void Engine::run_encoder(const BatchDev& b, const LongForm* lf) {
     static const bool defer_all = [] { const char* v = getenv("PARAKEET_B200_DEFER"); return !(v && v[0] == '0'); }();
     splits = std::max(splits, 1);
     if (splits > 1 && M > im.part_rows_split) splits = 1;
+    // Small batches are bound by L2 -> SM operand traffic (a 128 x 128 tile moves 32 KB per k-block for 128 x 128 x 64 MACs; at 128
+    // streams a K = 4096 residual GEMM pulls 97 MB through L2 in ~10 us): 128 x 256 tiles move 48 KB for twice the MACs.  Taken when
+    // the wider tiles, split up to 4 ways, still give most SMs a unit (PARAKEET_B200_PART_WIDE=0: always 128-wide).
+    static const bool wide_allowed = [] { const char* v = getenv("PARAKEET_B200_PART_WIDE"); return !(v && v[0] == '0'); }();
+    int part_wide = 0;
+    if (tc && allow && wide_allowed && wt.N % 256 == 0 && M <= im.part_rows_split) {
+      const int tiles_w = ((M + 127) / 128) * (wt.N / 256);
+      int splits_w = std::max(1, std::min(4, sm_count_ / std::max(tiles_w, 1)));
+      splits_w = std::max(1, std::min(splits_w, wt.K / 64 / 2));
+      if (tiles_w * splits_w * 5 >= sm_count_ * 3) { part_wide = 1; splits = splits_w; }
+    }
     int stride_rows = im.part_rows, pair_split = 0;
     if (tc && allow && splits == 1) {      // large batch on the CTA-pair kernel: a 2-way k-split can fill its last wave
       const int ps = gemm_tc_pair_splits(M, wt.N, wt.K);
@@ -1275,6 +1286,7 @@ void Engine::run_encoder(const BatchDev& b, const LongForm* lf) {
     if (tc && allow && (splits >= 2 || defer_all) && wt.N == kDModel) {
       EpiParams e; e.mode = EPI_PARTIAL_F32; e.out_f32 = im.part_ws; e.ldo = kDModel; e.splits = splits; e.part_rows = stride_rows;
       e.pair_split = pair_split;
+      e.part_wide = (part_wide && !pair_split) ? 1 : 0;
       // bf16 mode keeps the deferred branch outputs in bf16 (they are O(|x|/3) and join a stream whose GEMM operands are
       // rounded to bf16 anyway; parity set unchanged at 256/256, 2 % less time per step); precise mode keeps f32
       static const bool pb = [] { const char* v = getenv("PARAKEET_B200_PART_BF16"); return !(v && v[0] == '0'); }();

@@ -982,7 +982,9 @@ bool pick_two_cta(int M, int N, int K, int sms) {
   const double eff1 = (double)t1 / (double)(((t1 + sms - 1) / sms) * sms);
   // (N = 1024, K = 1024, the attention-output and conv pointwise_conv2 projections: 16.9 vs 19.0 us although its 96 pair tiles
   // fill only 65 % of two rounds -- the 128 x 128 tiles of the single-CTA kernel are bound by operand delivery there)
-  return eff2 > eff1 + 0.05 || (K >= 4096 && M >= 4096) || (N == 1024 && K == 1024 && M >= 4096);
+  // (from 3072 rows = 512 streams: forcing the pair kernel for every projection takes the step 9.40 -> 8.82 ms at 512 streams and
+  // 11.09 -> 10.44 ms at 640, and loses below 2560 rows and, for QKV / GLU, above 4096: gpurun r2y)
+  return eff2 > eff1 + 0.05 || (K >= 4096 && M >= 3072) || (N == 1024 && K == 1024 && M >= 3072);
 }
 
 }  // namespace
@@ -1130,9 +1132,14 @@ void gemm_tc(const GemmArgs& g_in, const TensorMap& map_a, const TensorMap& map_
     PKB_GEMM_CASE(EPI_SILU_ACT) PKB_GEMM_CASE(EPI_RESADD_F32) PKB_GEMM_CASE(EPI_QKV) PKB_GEMM_CASE(EPI_GLU_F32) PKB_GEMM_CASE(EPI_F32)
     PKB_GEMM_CASE(EPI_ACT)
 #undef PKB_GEMM_CASE
-    case EPI_PARTIAL_F32: {   // split-K: 128-wide tiles, one work unit per (tile, split)
-      const int units = ((g.M + BM - 1) / BM) * ((g.N + 127) / 128) * g.epi.splits;
-      launch_cfg<128, EPI_PARTIAL_F32>(units < sms ? units : sms, ma, mw, g, lo_row_off, st);
+    case EPI_PARTIAL_F32: {   // split-K: one work unit per (tile, split); 128-wide tiles, or 256-wide ones when the caller found enough units
+      if (g.epi.part_wide && g.N % 256 == 0) {
+        const int units = ((g.M + BM - 1) / BM) * (g.N / 256) * g.epi.splits;
+        launch_cfg<256, EPI_PARTIAL_F32>(units < sms ? units : sms, ma, mw, g, lo_row_off, st);
+      } else {
+        const int units = ((g.M + BM - 1) / BM) * ((g.N + 127) / 128) * g.epi.splits;
+        launch_cfg<128, EPI_PARTIAL_F32>(units < sms ? units : sms, ma, mw, g, lo_row_off, st);
+      }
       break;
     }
     case EPI_ARGMAX: {      // slab geometry (kArgmaxParts) is defined for 256-wide tiles
