@@ -26,10 +26,12 @@ def test_1024_streams_duplicates_and_oracle(model_full, features_ref, precision)
 
 
 @pytest.mark.parametrize("precision", [0, 1], ids=["bf16", "precise"])
-def test_128_streams_duplicates_and_oracle(model_full, features_ref, precision):
-    """The per-GPU batch of the 8-GPU configuration (768 packed rows): its own kernel choices -- 128 x 256 split-K tiles for the
-    residual GEMMs, the per-row LayerNorm with three / four partial-sum planes, single-CTA GEMMs everywhere."""
-    _duplicates_and_oracle(model_full, features_ref, precision, 128, 8, 6)
+@pytest.mark.parametrize("n_streams", [128, 256])
+def test_mid_size_batches_duplicates_and_oracle(model_full, features_ref, precision, n_streams):
+    """The per-GPU batches of the 8- and 4-GPU configurations (768 / 1536 packed rows) have their own kernel choices: split-K
+    residual GEMMs on 128 x 128 (128 streams) or 128 x 256 tiles (256 streams), the per-row LayerNorm with three partial-sum
+    planes, single-CTA GEMMs everywhere."""
+    _duplicates_and_oracle(model_full, features_ref, precision, n_streams, 8, 6)
 
 
 def _duplicates_and_oracle(model_full, features_ref, precision, N_STREAMS, N_DISTINCT, N_CHUNKS):

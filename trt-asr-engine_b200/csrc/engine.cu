@@ -1276,7 +1276,9 @@ void Engine::run_encoder(const BatchDev& b, const LongForm* lf) {
       const int tiles_w = ((M + 127) / 128) * (wt.N / 256);
       int splits_w = std::max(1, std::min(4, sm_count_ / std::max(tiles_w, 1)));
       splits_w = std::max(1, std::min(splits_w, wt.K / 64 / 2));
-      if (tiles_w * splits_w * 5 >= sm_count_ * 3) { part_wide = 1; splits = splits_w; }
+      // (measured, gpurun r3a: 256 streams 5.87 -> 5.37 ms, 192 streams 4.69 -> 4.62; at 128 streams the wide tiling leaves 96 units
+      // against 144 narrow ones and loses 5 %: wide only when it does not shrink the unit count)
+      if (tiles_w * splits_w * 5 >= sm_count_ * 3 && tiles_w * splits_w >= tiles * splits) { part_wide = 1; splits = splits_w; }
     }
     int stride_rows = im.part_rows, pair_split = 0;
     if (tc && allow && splits == 1) {      // large batch on the CTA-pair kernel: a 2-way k-split can fill its last wave
