@@ -13,9 +13,4 @@ PARAKEET_B200_GRAPH=0 timeout 900 ncu --set full --clock-control none --import-s
 PARAKEET_B200_GRAPH=0 timeout 900 ncu --set full --clock-control none -k regex:"layernorm|dwconv|attention_mma" -s 3000 -c 8 -o gpurun_out/r02f_misc -f python bench.py $BA > gpurun_out/r3p_ncu3.log 2>&1; echo "ncu misc rc=$?"
 timeout 600 ncu --set full --clock-control none -k regex:"decode_persistent" -c 1 -o gpurun_out/r02f_decode_persistent -f python scripts/lf_decode_probe.py 120 2 4 > gpurun_out/r3p_ncu4.log 2>&1; echo "ncu persist rc=$?"
 for f in r02f_gemm r02f_misc r02f_decode_persistent; do python scripts/ncu_summary.py full gpurun_out/$f.ncu-rep > gpurun_out/${f}_ncu_full_summary.txt 2>&1; done
-# memory checker on the kernels added this round (2-layer model, short runs)
-LAYERS=2 STREAMS=384 CHUNKS=3 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/probe_1stream.py > gpurun_out/r3p_memcheck_stream.log 2>&1; echo "memcheck streaming rc=$?"
-LAYERS=2 STREAMS=1 CHUNKS=4 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/probe_1stream.py > gpurun_out/r3p_memcheck_1s.log 2>&1; echo "memcheck 1-stream rc=$?"
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/lf_decode_probe.py 30 2 3 > gpurun_out/r3p_memcheck_lf.log 2>&1; echo "memcheck whole-utterance rc=$?"
-tail -3 gpurun_out/r3p_memcheck_stream.log gpurun_out/r3p_memcheck_1s.log gpurun_out/r3p_memcheck_lf.log
 ls -la gpurun_out/r02f*.ncu-rep
