@@ -1281,6 +1281,17 @@ void Engine::run_encoder(const BatchDev& b, const LongForm* lf) {
       if (tiles_w * splits_w * 5 >= sm_count_ * 3 && tiles_w * splits_w >= tiles * splits) { part_wide = 1; splits = splits_w; }
     }
     int stride_rows = im.part_rows, pair_split = 0;
+    // Small batch, long K (the FFN-down projections): 256 x 256 pair tiles split up to 4 ways halve the operand bytes per MAC once
+    // more (M = 768: 12 tiles x 4 splits = 48 pairs, 49 MB through L2 instead of 97 MB) -- but leave a third of the SMs without a
+    // unit and make every unit's k-loop longer: measured slower at 128 ... 320 streams (3.99 vs 3.93, 4.67 vs 4.55, 5.60 vs 5.34,
+    // 6.03 vs 5.97 ms; gpurun r3b), so OFF unless PARAKEET_B200_PAIR_SMALL=1.
+    static const bool pair_small_allowed = [] { const char* v = getenv("PARAKEET_B200_PAIR_SMALL"); return v && v[0] == '1'; }();
+    if (tc && allow && pair_small_allowed && wt.N % 256 == 0 && wt.K >= 2048 && M >= 256 && M <= im.part_rows_split) {
+      const int tiles_p = ((M + 255) / 256) * (wt.N / 256), pairs = sm_count_ / 2;
+      int splits_p = std::max(1, std::min(4, pairs / std::max(tiles_p, 1)));
+      splits_p = std::max(1, std::min(splits_p, wt.K / 64 / 2));
+      if (splits_p >= 2 && tiles_p * splits_p * 5 >= pairs * 3) { splits = splits_p; pair_split = 2; part_wide = 0; }
+    }
     if (tc && allow && splits == 1) {      // large batch on the CTA-pair kernel: a 2-way k-split can fill its last wave
       const int ps = gemm_tc_pair_splits(M, wt.N, wt.K);
       if (ps == 2 && 2 * (size_t)im.Mcap <= (size_t)4 * im.part_rows) { splits = 2; stride_rows = im.Mcap; pair_split = 1; }

@@ -62,7 +62,8 @@ struct EpiParams {
   int splits = 1;                   // EPI_PARTIAL_F32: number of k-splits
   int part_rows = 0;                //                  rows per split in the workspace
   int part_bf16 = 0;                //                  1: partial sums stored as bf16 (bf16 mode; halves the workspace traffic)
-  int pair_split = 0;               //                  1: the split count was chosen for the CTA-pair kernel (256 x 256 tiles)
+  int pair_split = 0;               //                  1: the split count was chosen for the CTA-pair kernel (256 x 256 tiles); 2: ... and the
+                                    //                  pair kernel is to be used whatever its shape heuristic says (small batches, long K)
   int part_wide = 0;                //                  1: 128 x 256 tiles (single-CTA kernel) instead of 128 x 128: fewer operand bytes per MAC
   float* part_val = nullptr;        // EPI_ARGMAX: [M][kArgmaxParts]
   int* part_idx = nullptr;

@@ -1072,9 +1072,11 @@ void gemm_tc(const GemmArgs& g_in, const TensorMap& map_a, const TensorMap& map_
   // and k-block instead of 48 KB for the same MACs) wins although both tilings leave the last of 6 waves equally empty: 55.3 -> ~50 us
   // per launch, 17.48 -> 17.27 ms per step at 1024 streams (A/B in gpurun r2k; 0 restores the single-CTA choice)
   static const int pair_modes = [] { const char* v = getenv("PARAKEET_B200_PAIR_MODES"); return v ? atoi(v) : (1 << EPI_SILU_ACT); }();
-  const bool pair_forced = ((pair_modes >> g.epi.mode) & 1) && g.N % 256 == 0 && g.M >= 2048 && g.N % 32 == 0;
+  static const int pair_min_m = [] { const char* v = getenv("PARAKEET_B200_PAIR_MIN_M"); return v ? atoi(v) : 2048; }();
+  const bool pair_forced = ((pair_modes >> g.epi.mode) & 1) && g.N % 256 == 0 && g.M >= pair_min_m && g.N % 32 == 0;
   const bool two_cta = g.epi.mode != EPI_ARGMAX && g.epi.mode != EPI_ACT && g.batch == 1 && !(g.epi.mode == EPI_PARTIAL_F32 && g.epi.splits > 1 && !g.epi.pair_split) &&
-                       (g_force_bn == 512 || (g_force_bn == 0 && g_two_cta != 0 && (pair_forced || pick_two_cta(g.M, g.N, g.K, sms))));
+                       (g_force_bn == 512 || (g_force_bn == 0 && g_two_cta != 0 &&
+                                              (pair_forced || (g.epi.mode == EPI_PARTIAL_F32 && g.epi.pair_split == 2) || pick_two_cta(g.M, g.N, g.K, sms))));
   if (two_cta) {
     const int pair_tiles = ((g.M + 255) / 256) * ((g.N + 255) / 256) * (g.epi.mode == EPI_PARTIAL_F32 ? g.epi.splits : 1);
     // (PARAKEET_B200_GEMM_MAX_PAIRS: measurement aid -- fewer resident pairs show how much of a tile's time is L2 -> SM contention)
