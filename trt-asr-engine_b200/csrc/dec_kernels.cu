@@ -267,33 +267,71 @@ __device__ __forceinline__ bool pd_grid_sync(unsigned* bar, unsigned target, int
   __syncthreads();
   return s_ok != 0;
 }
-// dot products of one bf16 weight row (shared memory) with the first NE of up to 8 f32 vectors (shared memory, pitch `ldx`), K % 128 == 0
-template <int K, int NE>
-__device__ __forceinline__ void pd_dot_ne(const __nv_bfloat16* __restrict__ w, const float* __restrict__ x, int ldx, int lane, float (&acc)[kPdChunk]) {
+// Dot products of NR bf16 weight rows (shared memory; rows r0, r0 + rstep, ... below nrows) with the first NE of up to 8 f32 vectors
+// (shared memory, pitch ldx), K % 128 == 0.  The activations of a k-step are loaded ONCE per lane and reused for every row (one row
+// at a time re-read them per row: 8 LDS.128 per 32 FMAs, bound by the shared-memory pipe).  The 8 per-lane partial sums of a row
+// are reduced "transposed": after the xor-16 / 8 / 4 exchanges a lane keeps the sum of ONE entry, e = bits 4..2 of its lane index
+// (9 shuffles per row instead of 40); every entry still goes through the same xor-16, 8, 4, 2, 1 butterfly as warp_sum(), and
+// addition commutes, so the totals are bit-identical to the plain reduction and do not depend on NE.
+template <int K, int NE, int NR>
+__device__ __forceinline__ void pd_dot_rows_ne(const __nv_bfloat16* __restrict__ w, int ldw, int r0, int rstep, int nrows, const float* __restrict__ x,
+                                               int ldx, int lane, float (&tot)[NR]) {
+  float acc[NR][kPdChunk];
 #pragma unroll
-  for (int e = 0; e < kPdChunk; ++e) acc[e] = 0.0f;
+  for (int i = 0; i < NR; ++i)
 #pragma unroll
+    for (int e = 0; e < kPdChunk; ++e) acc[i][e] = 0.0f;
+#pragma unroll 2
   for (int k0 = 0; k0 < K; k0 += 128) {
-    const uint2 raw = *reinterpret_cast<const uint2*>(w + k0 + lane * 4);
-    const float w0 = __uint_as_float(raw.x << 16), w1 = __uint_as_float(raw.x & 0xffff0000u);
-    const float w2 = __uint_as_float(raw.y << 16), w3 = __uint_as_float(raw.y & 0xffff0000u);
+    float4 v[NE];
 #pragma unroll
-    for (int e = 0; e < NE; ++e) {
-      const float4 v = *reinterpret_cast<const float4*>(x + (size_t)e * ldx + k0 + lane * 4);
-      acc[e] = fmaf(w0, v.x, acc[e]); acc[e] = fmaf(w1, v.y, acc[e]); acc[e] = fmaf(w2, v.z, acc[e]); acc[e] = fmaf(w3, v.w, acc[e]);
+    for (int e = 0; e < NE; ++e) v[e] = *reinterpret_cast<const float4*>(x + (size_t)e * ldx + k0 + lane * 4);
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int r = r0 + i * rstep;
+      if (r < nrows) {
+        const uint2 raw = *reinterpret_cast<const uint2*>(w + (size_t)r * ldw + k0 + lane * 4);
+        const float w0 = __uint_as_float(raw.x << 16), w1 = __uint_as_float(raw.x & 0xffff0000u);
+        const float w2 = __uint_as_float(raw.y << 16), w3 = __uint_as_float(raw.y & 0xffff0000u);
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+          acc[i][e] = fmaf(w0, v[e].x, acc[i][e]); acc[i][e] = fmaf(w1, v[e].y, acc[i][e]);
+          acc[i][e] = fmaf(w2, v[e].z, acc[i][e]); acc[i][e] = fmaf(w3, v[e].w, acc[i][e]);
+        }
+      }
     }
   }
+  const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
 #pragma unroll
-  for (int e = 0; e < NE; ++e) acc[e] = warp_sum(acc[e]);
+  for (int i = 0; i < NR; ++i) {
+    float k4[4], k2[2];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {      // lanes with bit 4 clear keep entries 0..3, the others 4..7
+      const float give = b4 ? acc[i][q] : acc[i][q + 4], keep = b4 ? acc[i][q + 4] : acc[i][q];
+      k4[q] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float give = b3 ? k4[q] : k4[q + 2], keep = b3 ? k4[q + 2] : k4[q];
+      k2[q] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+    }
+    const float give = b2 ? k2[0] : k2[1], keep = b2 ? k2[1] : k2[0];
+    float t = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    tot[i] = t;      // the dot product of row r0 + i * rstep with entry (lane >> 2) & 7
+  }
 }
-// (the per-entry result does not depend on how many entries share the pass: same summation order for every NE)
-template <int K>
-__device__ __forceinline__ void pd_dot8(const __nv_bfloat16* __restrict__ w, const float* __restrict__ x, int ldx, int lane, int ne, float (&acc)[kPdChunk]) {
-  if (ne <= 1) pd_dot_ne<K, 1>(w, x, ldx, lane, acc);
-  else if (ne <= 2) pd_dot_ne<K, 2>(w, x, ldx, lane, acc);
-  else if (ne <= 4) pd_dot_ne<K, 4>(w, x, ldx, lane, acc);
-  else pd_dot_ne<K, 8>(w, x, ldx, lane, acc);
+template <int K, int NR>
+__device__ __forceinline__ void pd_dot_rows(const __nv_bfloat16* __restrict__ w, int ldw, int r0, int rstep, int nrows, const float* __restrict__ x, int ldx,
+                                            int lane, int ne, float (&tot)[NR]) {
+  if (ne <= 1) pd_dot_rows_ne<K, 1, NR>(w, ldw, r0, rstep, nrows, x, ldx, lane, tot);
+  else if (ne <= 2) pd_dot_rows_ne<K, 2, NR>(w, ldw, r0, rstep, nrows, x, ldx, lane, tot);
+  else if (ne <= 4) pd_dot_rows_ne<K, 4, NR>(w, ldw, r0, rstep, nrows, x, ldx, lane, tot);
+  else pd_dot_rows_ne<K, 8, NR>(w, ldw, r0, rstep, nrows, x, ldx, lane, tot);
 }
+constexpr int kPdColsPerWarp = (kPdColsMax + kPdWarps - 1) / kPdWarps;          // 7
+constexpr int kPdGateRowsPerWarp = (kPdUnitsMax * 4 + kPdWarps - 1) / kPdWarps; // 3
 }  // namespace
 
 __global__ void __launch_bounds__(kPdThreads, 1)
@@ -356,28 +394,25 @@ decode_persistent_kernel(DecPersistArgs a) {
           reinterpret_cast<float4*>(s_x + (size_t)e * kJointH)[c] = h;
         }
         __syncthreads();
-        float best[kPdChunk];
-        int bidx[kPdChunk];
+        // this lane's entry after the transposed reduction, and its running first maximum over the CTA's columns (ascending)
+        const int my_e = (lane >> 2) & 7;
+        float best = -INFINITY;
+        int bidx = 0x7fffffff;
+        float tot[kPdColsPerWarp];
+        pd_dot_rows<kJointH, kPdColsPerWarp>(s_wout, kJointH, warp, kPdWarps, ncols, s_x, kJointH, lane, ne, tot);
 #pragma unroll
-        for (int e = 0; e < kPdChunk; ++e) { best[e] = -INFINITY; bidx[e] = 0x7fffffff; }
-        for (int j = warp; j < ncols; j += kPdWarps) {      // ascending columns per warp: first maximum wins
-          float acc[kPdChunk];
-          pd_dot8<kJointH>(s_wout + (size_t)j * kJointH, s_x, kJointH, lane, ne, acc);
-          const int col = c0 + j;
-          const float bias = __ldg(a.b_out + col);
-#pragma unroll
-          for (int e = 0; e < kPdChunk; ++e) {
-            float y = acc[e] + bias;
+        for (int i = 0; i < kPdColsPerWarp; ++i) {
+          const int j = warp + i * kPdWarps;
+          if (j < ncols) {
+            const int col = c0 + j;
+            float y = tot[i] + __ldg(a.b_out + col);
             if (y != y) y = -100.0f;                                      // NaN logits -> -100 (parakeet_trt.cpp:2971)
             if (col == kBlank) y -= d.blank_penalty;                      // PARAKEET_BLANK_PENALTY (:3175-3178)
-            if (col < kVocab) { if (y > best[e]) { best[e] = y; bidx[e] = col; } }
-            else if (lane == 0 && e < ne) a.dur[(size_t)(e0 + e) * kNDur + (col - kVocab)] = y;
+            if (col < kVocab) { if (y > best) { best = y; bidx = col; } }
+            else if ((lane & 3) == 0 && my_e < ne) a.dur[(size_t)(e0 + my_e) * kNDur + (col - kVocab)] = y;
           }
         }
-        if (lane == 0) {
-#pragma unroll
-          for (int e = 0; e < kPdChunk; ++e) { s_red_v[warp][e] = best[e]; s_red_i[warp][e] = bidx[e]; }
-        }
+        if ((lane & 3) == 0) { s_red_v[warp][my_e] = best; s_red_i[warp][my_e] = bidx; }
         __syncthreads();
         if (tid < ne) {
           float bv = s_red_v[0][tid];
@@ -506,13 +541,16 @@ decode_persistent_kernel(DecPersistArgs a) {
               reinterpret_cast<float4*>(s_x + (size_t)e * 2 * kPredH)[c] = v;
             }
             __syncthreads();
-            for (int r = warp; r < nunits * 4; r += kPdWarps) {
-              float acc[kPdChunk];
-              pd_dot8<2 * kPredH>(s_w + (size_t)r * 2 * kPredH, s_x, 2 * kPredH, lane, ne, acc);
-              if (lane == 0) {
-                const float b = __ldg(bias + (r & 3) * kPredH + u0 + (r >> 2));
+            {
+              float tot[kPdGateRowsPerWarp];
+              pd_dot_rows<2 * kPredH, kPdGateRowsPerWarp>(s_w, 2 * kPredH, warp, kPdWarps, nunits * 4, s_x, 2 * kPredH, lane, ne, tot);
+              if ((lane & 3) == 0) {
+                const int my_e = (lane >> 2) & 7;
 #pragma unroll
-                for (int e = 0; e < kPdChunk; ++e) s_gates[r][e] = acc[e] + b;
+                for (int i = 0; i < kPdGateRowsPerWarp; ++i) {
+                  const int r = warp + i * kPdWarps;
+                  if (r < nunits * 4) s_gates[r][my_e] = tot[i] + __ldg(bias + (r & 3) * kPredH + u0 + (r >> 2));
+                }
               }
             }
             __syncthreads();
@@ -560,15 +598,12 @@ decode_persistent_kernel(DecPersistArgs a) {
             reinterpret_cast<float4*>(s_x + (size_t)e * kPredH)[c] = v;
           }
           __syncthreads();
-          for (int r = warp; r < nunits; r += kPdWarps) {
-            float acc[kPdChunk];
-            pd_dot8<kPredH>(s_wjp + (size_t)r * kPredH, s_x, kPredH, lane, ne, acc);
-            if (lane == 0) {
-              const float b = __ldg(a.b_jp + u0 + r);
-#pragma unroll
-              for (int e = 0; e < kPdChunk; ++e)
-                if (s_flag[e]) d.pred_proj[(size_t)d.slot[e0 + e] * kJointH + u0 + r] = acc[e] + b;
-            }
+          {
+            float tot[1];
+            pd_dot_rows<kPredH, 1>(s_wjp, kPredH, warp, kPdWarps, nunits, s_x, kPredH, lane, ne, tot);
+            const int my_e = (lane >> 2) & 7;
+            if ((lane & 3) == 0 && warp < nunits && s_flag[my_e])
+              d.pred_proj[(size_t)d.slot[e0 + my_e] * kJointH + u0 + warp] = tot[0] + __ldg(a.b_jp + u0 + warp);
           }
         }
         __syncthreads();

@@ -59,8 +59,10 @@ struct DecodeDev {
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 #endif
 
-// Persistent decode loop (dec_kernels.cu): one cooperative kernel runs every pass of a whole-utterance decode of <= kPersistMaxB entries
-constexpr int kPersistMaxB = 64;
+// Persistent decode loop (dec_kernels.cu): one cooperative kernel runs every pass of a whole-utterance decode of <= kPersistMaxB entries.
+// Its pass costs ~10 + 1.45 B us (CUDA cores, every CTA meets every entry); the WHILE-graph body with tensor-core GEMMs ~40 us flat:
+// measured 1.42 vs 3.24 s at 4 x 1 h, 5.09 vs 3.98 s at 32 x 1 h -- hence the limit.
+constexpr int kPersistMaxB = 16;
 struct DecPersistArgs {
   DecodeDev d;
   const __nv_bfloat16* w_out; const float* b_out;     // joint output layer [8198,640], [8198]

@@ -403,6 +403,10 @@ void Engine::profile_enable(bool on) {
 }
 // profile mode: bracket the next launch with two CUDA events on the engine stream
 int Engine::prof_begin(int cls, double work) {
+  if (im_->profile) {      // launches that are being captured into a graph have no timing of their own (their events would be graph nodes)
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st_, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) return -1;
+  }
   Impl& im = *im_;
   if (!im.profile) return -1;
   if (im.prof_used == im.prof_events.size()) {
