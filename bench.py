@@ -456,10 +456,10 @@ def main():
     }
     # the HBM-bound pieces, same method (CUDA events around each launch, algorithmic bytes / duration) vs the measured copy peak
     line["roofline_hbm"] = [
-        {"kernel": "attention_mma_kernel (K/V ring read, TMA + mma.sync)", "bound": "hbm", "achieved": attn_bytes / max(attn_ms, 1e-9) / 1e6,
+        {"kernel": "attention_mma_kernel (K/V ring read: valid 8-key groups only, TMA + mma.sync)", "bound": "hbm", "achieved": attn_bytes / max(attn_ms, 1e-9) / 1e6,
          "peak": peak_hbm, "unit": "GB/s", "frac": attn_bytes / max(attn_ms, 1e-9) / 1e6 / peak_hbm, "launches_timed": int(attn_launches),
          "algorithmic_bytes_per_launch": attn_bytes / max(attn_launches, 1)},
-        {"kernel": "logmel_kernel (frontend)", "bound": "hbm", "achieved": fe_bytes / max(fe_ms, 1e-9) / 1e6, "peak": peak_hbm, "unit": "GB/s",
+        {"kernel": "logmel_reg_kernel (frontend, register-resident FFT)", "bound": "hbm", "achieved": fe_bytes / max(fe_ms, 1e-9) / 1e6, "peak": peak_hbm, "unit": "GB/s",
          "frac": fe_bytes / max(fe_ms, 1e-9) / 1e6 / peak_hbm, "launches_timed": int(fe_launches),
          "algorithmic_bytes_per_launch": fe_bytes / max(fe_launches, 1),
          "note": "latency-bound at this size (24 new frames per stream per step); 0.3 % of the step"},
@@ -479,7 +479,7 @@ def main():
                  "at 1024 streams a pass is two split-precision tensor-core GEMMs deep, so this entry is latency / tensor bound, not HBM bound"})
     if fe1h is not None and fe1h[0] > 0:
         line["roofline_hbm"].append(
-            {"kernel": f"logmel_kernel, one 1 h clip ({(hour.size - 400) // 160 + 1} frames in one launch)", "bound": "hbm", "achieved": fe1h[1] / fe1h[0] / 1e6,
+            {"kernel": f"logmel_reg_kernel, one 1 h clip ({(hour.size - 400) // 160 + 1} frames in one launch)", "bound": "hbm", "achieved": fe1h[1] / fe1h[0] / 1e6,
              "peak": peak_hbm, "unit": "GB/s", "frac": fe1h[1] / fe1h[0] / 1e6 / peak_hbm, "launches_timed": int(fe1h[2]),
              "algorithmic_bytes_per_launch": fe1h[1] / max(fe1h[2], 1)})
     for e in engs:

@@ -10,6 +10,12 @@
 //     near 60 %); the slices are fetched with TMA (96-key x 64-dim boxes, 128-byte swizzle)
 //     by a dedicated producer warp into a 6-stage shared-memory ring (full/empty mbarriers): the producer runs a whole
 //     item ahead of the 8 consumer warps, so the loads of item i+1 overlap the math of item i.
+//   * only VALID ring slots are fetched: a 96-key block whose 12 groups of 8 keys are all valid is two 96-row boxes; a block that
+//     contains invalid slots (the 26 slots of the 288-slot ring outside [cache suffix || new rows] in steady state, most of the
+//     ring while a stream's cache is still filling) is fetched as its valid groups only, through 32-row / 8-row boxes of the same
+//     rings at the same shared-memory positions.  Rows that were not fetched hold stale data: their scores are masked by select
+//     and their V fragments are zeroed in registers, so nothing stale is ever consumed arithmetically.  (Round 1 fetched whole
+//     blocks: ncu dram__bytes_read 1.252 GB per launch against 1.099 GB of valid K / V rows at 1024 saturated streams.)
 //   * keys are walked in PHYSICAL ring order (the softmax sum does not care), so a wrapped FIFO needs no second copy and
 //     every box is one contiguous row range; validity and the relative position of slot p follow from the ring head.
 //   * the position term G = (q+v) P^T is NOT computed here: it is the same P for every stream, so one batched tcgen05 GEMM
@@ -110,9 +116,12 @@ struct Smem {
   static constexpr size_t kBytes = 1024 + (size_t)kStages * kStageBytes + kS + kG + 128;
 };
 
+constexpr int kGrpPerBlk = kBlkKeys / 8;          // 8-key groups per block
+constexpr int kNumGrp = kRingCap / 8;
 struct Item {
   int Tq, qlen, len, head, row0, ring_row0;
   unsigned need;      // bit k: 96-key block k holds at least one valid key
+  unsigned long long groups;      // bit q: the 8-key group of physical slots [8q, 8q+8) holds at least one valid key
 };
 __device__ __forceinline__ Item load_item(const BatchDev& b, const AttnMmaArgs& a, int e) {
   Item it;
@@ -120,12 +129,25 @@ __device__ __forceinline__ Item load_item(const BatchDev& b, const AttnMmaArgs& 
   it.ring_row0 = (a.layer * a.n_slots + b.slot[e]) * (kHeads * kRingCap);      // + head * kRingCap: rings are head-major
   // valid logical positions j in [256-len, 256+qlen) form one circular run of physical slots
   const int v_start = (it.head + kCacheS - it.len) % kRingCap, v_cnt = it.len + it.qlen;
+  // groups q0 .. q0 + n - 1 (circular over the kNumGrp groups of the ring) intersect the run
+  const int q0 = v_start >> 3;
+  int n = ((v_start + (v_cnt > 0 ? v_cnt : 1) - 1) >> 3) - q0 + 1;
+  n = n > kNumGrp ? kNumGrp : n;
+  const int hi = q0 + n < kNumGrp ? q0 + n : kNumGrp;
+  unsigned long long m = ((1ull << hi) - 1ull) & ~((1ull << q0) - 1ull);
+  if (q0 + n > kNumGrp) m |= (1ull << (q0 + n - kNumGrp)) - 1ull;
+  if (!a.trim) {      // whole blocks (A/B switch): every group of a needed block counts as valid
+    unsigned long long full = 0;
+#pragma unroll
+    for (int k = 0; k < kNumBlk; ++k)
+      if ((m >> (k * kGrpPerBlk)) & ((1ull << kGrpPerBlk) - 1ull)) full |= ((1ull << kGrpPerBlk) - 1ull) << (k * kGrpPerBlk);
+    m = full;
+  }
+  it.groups = m;
   it.need = 0;
 #pragma unroll
-  for (int k = 0; k < kNumBlk; ++k) {
-    const int lo = k * kBlkKeys;
-    if (((lo - v_start + kRingCap) % kRingCap) < v_cnt || ((v_start - lo + kRingCap) % kRingCap) < kBlkKeys) it.need |= 1u << k;
-  }
+  for (int k = 0; k < kNumBlk; ++k)
+    if ((m >> (k * kGrpPerBlk)) & ((1ull << kGrpPerBlk) - 1ull)) it.need |= 1u << k;
   return it;
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -139,7 +161,9 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;"
 // R = 8 (rows 8..15 of every m16 tile are identically zero and never loaded / stored), 16 or 32.
 template <int R, int CFG>
 __global__ void __launch_bounds__(Smem<R, CFG>::kThreads, Smem<R, CFG>::kCtasPerSm)
-attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v, BatchDev b, AttnMmaArgs a) {
+attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                     const __grid_constant__ CUtensorMap map_k32, const __grid_constant__ CUtensorMap map_v32,
+                     const __grid_constant__ CUtensorMap map_k8, const __grid_constant__ CUtensorMap map_v8, BatchDev b, AttnMmaArgs a) {
   constexpr int MT = R <= 16 ? 1 : 2;
   constexpr bool kHalf = R == 8;
   constexpr int kStages = Smem<R, CFG>::kStages;
@@ -160,6 +184,10 @@ attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
   if (tid == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k32) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v32) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k8) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v8) : "memory");
 #pragma unroll
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kConsumerWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -180,19 +208,58 @@ attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
 #pragma unroll
         for (int kv = 0; kv < 2; ++kv) {
           const CUtensorMap* map = kv ? &map_v : &map_k;
+          const CUtensorMap* map32 = kv ? &map_v32 : &map_k32;
+          const CUtensorMap* map8 = kv ? &map_v8 : &map_k8;
 #pragma unroll
           for (int k = 0; k < kNumBlk; ++k) {
             if (!((im.need >> k) & 1u)) continue;
+            const unsigned gm = (unsigned)(im.groups >> (k * kGrpPerBlk)) & ((1u << kGrpPerBlk) - 1u);
             const int s = it % kStages;
             mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
-            mbar_expect_tx(&full_bar[s], kStageBytes);
+            uint8_t* dst = s_ring + s * kStageBytes;
             const int row = im.ring_row0 + h * kRingCap + k * kBlkKeys;
-            if (hint) {
-              tma_load_2d_hint(s_ring + s * kStageBytes, map, &full_bar[s], 0, row, pol_stream);
-              tma_load_2d_hint(s_ring + s * kStageBytes + kBoxBytes, map, &full_bar[s], 64, row, pol_stream);
+            if (gm == (1u << kGrpPerBlk) - 1u) {
+              mbar_expect_tx(&full_bar[s], kStageBytes);
+              if (hint) {
+                tma_load_2d_hint(dst, map, &full_bar[s], 0, row, pol_stream);
+                tma_load_2d_hint(dst + kBoxBytes, map, &full_bar[s], 64, row, pol_stream);
+              } else {
+                tma_load_2d(dst, map, &full_bar[s], 0, row);
+                tma_load_2d(dst + kBoxBytes, map, &full_bar[s], 64, row);
+              }
             } else {
-              tma_load_2d(s_ring + s * kStageBytes, map, &full_bar[s], 0, row);
-              tma_load_2d(s_ring + s * kStageBytes + kBoxBytes, map, &full_bar[s], 64, row);
+              // valid groups only: aligned runs of four groups as one 32-row box, the rest as 8-row boxes; a group of 8 keys is
+              // 8 rows x 128 B = one 1024-byte swizzle atom of each 64-dim half, so partial boxes land exactly where the 96-row
+              // box would have put the same rows
+              mbar_expect_tx(&full_bar[s], (uint32_t)__popc(gm) * 2048u);
+#pragma unroll
+              for (int q4 = 0; q4 < kGrpPerBlk / 4; ++q4) {
+                const unsigned g4 = (gm >> (4 * q4)) & 15u;
+                if (g4 == 15u) {
+                  uint8_t* d = dst + q4 * 4096;
+                  if (hint) {
+                    tma_load_2d_hint(d, map32, &full_bar[s], 0, row + 32 * q4, pol_stream);
+                    tma_load_2d_hint(d + kBoxBytes, map32, &full_bar[s], 64, row + 32 * q4, pol_stream);
+                  } else {
+                    tma_load_2d(d, map32, &full_bar[s], 0, row + 32 * q4);
+                    tma_load_2d(d + kBoxBytes, map32, &full_bar[s], 64, row + 32 * q4);
+                  }
+                } else {
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    if (!((g4 >> q) & 1u)) continue;
+                    uint8_t* d = dst + (4 * q4 + q) * 1024;
+                    const int r8 = row + 8 * (4 * q4 + q);
+                    if (hint) {
+                      tma_load_2d_hint(d, map8, &full_bar[s], 0, r8, pol_stream);
+                      tma_load_2d_hint(d + kBoxBytes, map8, &full_bar[s], 64, r8, pol_stream);
+                    } else {
+                      tma_load_2d(d, map8, &full_bar[s], 0, r8);
+                      tma_load_2d(d + kBoxBytes, map8, &full_bar[s], 64, r8);
+                    }
+                  }
+                }
+              }
             }
             ++it;
           }
@@ -340,8 +407,11 @@ attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
       mbar_wait(&full_bar[s], (it / kStages) & 1);
       ++it;
       const uint32_t st = smem_u32(s_ring + s * kStageBytes);
+      const unsigned gm = (unsigned)(im.groups >> (k * kGrpPerBlk)) & ((1u << kGrpPerBlk) - 1u);
 #pragma unroll
       for (int kk = 0; kk < kBlkKeys / 16; ++kk) {
+        const bool lo_ok = (gm >> (2 * kk)) & 1u, hi_ok = (gm >> (2 * kk + 1)) & 1u;      // keys 0..7 / 8..15 of this step were fetched
+        if (!lo_ok && !hi_ok) continue;      // their probabilities are zero
         const int key0 = k * kBlkKeys + 16 * kk;
         uint32_t af[MT][4];
 #pragma unroll
@@ -363,6 +433,9 @@ attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
           const uint32_t addr = st + (chunk_g >> 3) * kBoxBytes + key_l * 128 + (((chunk_g & 7) ^ (key_l & 7)) << 4);
           uint32_t r0, r1, r2, r3;
           ldsm_x4_t(addr, r0, r1, r2, r3);
+          // rows that were not fetched hold stale bytes (possibly NaN patterns): 0 x NaN must not reach the accumulators
+          r0 = lo_ok ? r0 : 0u; r2 = lo_ok ? r2 : 0u;
+          r1 = hi_ok ? r1 : 0u; r3 = hi_ok ? r3 : 0u;
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
             if (kk & 1) { mma_bf16(ob[mt][2 * np], af[mt], r0, r1); mma_bf16(ob[mt][2 * np + 1], af[mt], r2, r3); }
@@ -401,7 +474,9 @@ void launch_r(const BatchDev& b, const AttnMmaArgs& a, int sms, cudaStream_t st)
   const int items = b.B * kHeads;
   const int ctas = sms * Smem<R, CFG>::kCtasPerSm;
   launch_k(attention_mma_kernel<R, CFG>, dim3(items < ctas ? items : ctas), dim3(Smem<R, CFG>::kThreads), Smem<R, CFG>::kBytes, st,
-           *reinterpret_cast<const CUtensorMap*>(a.map_k), *reinterpret_cast<const CUtensorMap*>(a.map_v), b, a);
+           *reinterpret_cast<const CUtensorMap*>(a.map_k), *reinterpret_cast<const CUtensorMap*>(a.map_v),
+           *reinterpret_cast<const CUtensorMap*>(a.map_k32), *reinterpret_cast<const CUtensorMap*>(a.map_v32),
+           *reinterpret_cast<const CUtensorMap*>(a.map_k8), *reinterpret_cast<const CUtensorMap*>(a.map_v8), b, a);
 }
 
 }  // namespace
@@ -410,8 +485,11 @@ void launch_attention_mma(const BatchDev& b, const AttnMmaArgs& a, cudaStream_t 
   if (b.B <= 0) return;
   PKB_CHECK(a.ctx.lo_off == 0, "attention_mma: bf16 mode only");
   static const int evict = [] { const char* v = getenv("PARAKEET_B200_ATTN_EVICT"); return (v && v[0] == '0') ? 0 : 1; }();
+  static const int trim = [] { const char* v = getenv("PARAKEET_B200_ATTN_TRIM"); return (v && v[0] == '0') ? 0 : 1; }();
   AttnMmaArgs a2 = a;
   a2.evict_first = evict;
+  a2.trim = (trim && a.map_k32 && a.map_v32 && a.map_k8 && a.map_v8) ? 1 : 0;
+  if (!a2.trim) { a2.map_k32 = a2.map_k8 = a.map_k; a2.map_v32 = a2.map_v8 = a.map_v; }      // never dereferenced by the kernel then
   static int sms = 0;
   if (!sms) {
     int dev = 0;

@@ -122,9 +122,14 @@ struct AttnMmaArgs {
   ActOut ctx;                    // [M,1024] bf16
   const void* map_k;             // host pointers to 128-byte CUtensorMap objects
   const void* map_v;
+  const void* map_k32 = nullptr; // the same rings with 32-row and 8-row boxes: blocks that hold invalid ring slots are fetched as their
+  const void* map_v32 = nullptr; // valid 8-key groups only (attn_mma.cu, PARAKEET_B200_ATTN_TRIM); null -> whole 96-key blocks
+  const void* map_k8 = nullptr;
+  const void* map_v8 = nullptr;
   int layer;
   int n_slots;
   int evict_first = 0;           // set by launch_attention_mma: K / V blocks are loaded with an L2 evict-first policy
+  int trim = 0;                  // set by launch_attention_mma: fetch the valid 8-key groups of partly valid blocks only
 };
 void launch_attention_mma(const BatchDev& b, const AttnMmaArgs& a, cudaStream_t st);
 

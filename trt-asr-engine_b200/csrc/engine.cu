@@ -225,6 +225,7 @@ struct Engine::Impl {
   void *kring = nullptr, *vring = nullptr, *acache = nullptr;
   bool attn_mma = false;                 // bf16 mode: natural-layout K ring + tensor-core attention (attn_mma.cu)
   TensorMap map_k, map_v;                // TMA maps over the K / V rings of all layers
+  TensorMap map_k32, map_v32, map_k8, map_v8;   // ... with 32-row / 8-row boxes (partly valid blocks: valid 8-key groups only)
   size_t ring_layer_elems = 0;           // elements per layer in each ring (slots * 288 * 1024)
   float* cache_tm = nullptr;             // [slots][L][1024][4]
   float* feat_ring = nullptr;            // [slots][kFeatRing][128]
@@ -633,6 +634,10 @@ void Engine::alloc_state() {
     // head-major rings [layer][slot][head][kRingCap][128]: a 2-D map over rows of 128 elements
     make_tensor_map_2d(&im.map_k, im.kring, (uint64_t)L_ * S * kHeads * kRingCap, kDHead, kDHead, 96);
     make_tensor_map_2d(&im.map_v, im.vring, (uint64_t)L_ * S * kHeads * kRingCap, kDHead, kDHead, 96);
+    make_tensor_map_2d(&im.map_k32, im.kring, (uint64_t)L_ * S * kHeads * kRingCap, kDHead, kDHead, 32);
+    make_tensor_map_2d(&im.map_v32, im.vring, (uint64_t)L_ * S * kHeads * kRingCap, kDHead, kDHead, 32);
+    make_tensor_map_2d(&im.map_k8, im.kring, (uint64_t)L_ * S * kHeads * kRingCap, kDHead, kDHead, 8);
+    make_tensor_map_2d(&im.map_v8, im.vring, (uint64_t)L_ * S * kHeads * kRingCap, kDHead, kDHead, 8);
   }
   if (opt_.contract_cache) {
     im.acache = dev_alloc_bytes(im.ring_layer_elems * L_ * kv_elem);
@@ -1344,6 +1349,7 @@ void Engine::run_encoder(const BatchDev& b, const LongForm* lf) {
         gemm_tc(g, im.map_qv, w.ppos_map, st_); ++launches_; }
       AttnMmaArgs a; a.q_bf16 = im.q_bf16; a.q_plane = im.q_plane; a.g_pos = im.g_pos; a.ctx = im.a_ln.out();
       a.map_k = &im.map_k; a.map_v = &im.map_v; a.layer = l; a.n_slots = opt_.max_streams;
+      a.map_k32 = &im.map_k32; a.map_v32 = &im.map_v32; a.map_k8 = &im.map_k8; a.map_v8 = &im.map_v8;
       // algorithmic bytes: the valid K and V rows of every (stream, head): 2 x (256 + Tq) x 128 x 2 B (steady state; early chunks less)
       const int pi = prof_begin(1, (double)b.B * kHeads * 2.0 * (kCacheS + b.max_Tq) * kDHead * 2.0);
       launch_attention_mma(b, a, st_); ++launches_;
