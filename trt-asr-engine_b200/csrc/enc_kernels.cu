@@ -74,8 +74,10 @@ subsample_stage1_kernel(BatchDev b, const float* __restrict__ feat_ring, int rin
     float k0[2][9], k2[2][9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
-      k0[0][i] = w.w0[c * 9 + i]; k0[1][i] = w.w0[(c + 1) * 9 + i];
-      k2[0][i] = w.w2[c * 9 + i]; k2[1][i] = w.w2[(c + 1) * 9 + i];
+      const float2 ka = __ldg(reinterpret_cast<const float2*>(w.w0t + i * kSubCh + c));      // transposed [9][256] copies: channels c, c+1
+      const float2 kb = __ldg(reinterpret_cast<const float2*>(w.w2t + i * kSubCh + c));
+      k0[0][i] = ka.x; k0[1][i] = ka.y;
+      k2[0][i] = kb.x; k2[1][i] = kb.y;
     }
     const float bias0[2] = {w.b0[c], w.b0[c + 1]}, bias2[2] = {w.b2[c], w.b2[c + 1]};
     __syncthreads();   // s_in ready (first iteration) / previous s_y0 consumers done
@@ -204,8 +206,8 @@ subsample_stage1_mma_kernel(BatchDev b, const float* __restrict__ feat_ring, int
     for (int nt = 0; nt < 2; ++nt) {
       const int cl = 16 * warp + 8 * nt;                      // channel offset inside the half
       const int cB = half * kS1Half + cl + gq;                 // B fragment: channel = n index = gq
-      const uint32_t b0 = pack_bf16x2_f(w.w0[cB * 9 + 2 * t], w.w0[cB * 9 + 2 * t + 1]);
-      const uint32_t b1 = t == 0 ? pack_bf16x2_f(w.w0[cB * 9 + 8], 0.0f) : 0u;
+      const uint32_t b0 = pack_bf16x2_f(w.w0t[(2 * t) * kSubCh + cB], w.w0t[(2 * t + 1) * kSubCh + cB]);
+      const uint32_t b1 = t == 0 ? pack_bf16x2_f(w.w0t[8 * kSubCh + cB], 0.0f) : 0u;
       const int cC = half * kS1Half + cl + 2 * t;              // C fragment: channels 2t, 2t+1
       const float bias0 = w.b0[cC], bias1 = w.b0[cC + 1];
 #pragma unroll
@@ -229,7 +231,10 @@ subsample_stage1_mma_kernel(BatchDev b, const float* __restrict__ feat_ring, int
       const int c = half * kS1Half + 2 * cp;
       float k2[2][9];
 #pragma unroll
-      for (int i = 0; i < 9; ++i) { k2[0][i] = w.w2[c * 9 + i]; k2[1][i] = w.w2[(c + 1) * 9 + i]; }
+      for (int i = 0; i < 9; ++i) {
+        const float2 kk = __ldg(reinterpret_cast<const float2*>(w.w2t + i * kSubCh + c));      // channels c, c+1 of tap i: 8 B per lane, coalesced
+        k2[0][i] = kk.x; k2[1][i] = kk.y;
+      }
       const float bias2[2] = {w.b2[c], w.b2[c + 1]};
 #pragma unroll 2
       for (int i = 0; i < 8; ++i) {
@@ -281,10 +286,13 @@ subsample_stage2_kernel(BatchDev b, ActOut y1, SubsampleWeights w, ActOut a2) {
   const int c = 4 * (threadIdx.x & 63), fq = threadIdx.x >> 6;      // channels c..c+3, output bins f3 = 4*fq .. 4*fq+3
   float k[4][9], bias[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-#pragma unroll
-    for (int i = 0; i < 9; ++i) k[j][i] = w.w5[(c + j) * 9 + i];
-    bias[j] = w.b5[c + j];
+  for (int i = 0; i < 9; ++i) {
+    const float4 kk = __ldg(reinterpret_cast<const float4*>(w.w5t + i * kSubCh + c));      // channels c..c+3 of tap i: 16 B per lane, coalesced
+    k[0][i] = kk.x; k[1][i] = kk.y; k[2][i] = kk.z; k[3][i] = kk.w;
+  }
+  {
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(w.b5 + c));
+    bias[0] = bb.x; bias[1] = bb.y; bias[2] = bb.z; bias[3] = bb.w;
   }
   const __nv_bfloat16* base = y1.ptr + (size_t)b.off2[e] * 32 * kSubCh;   // [T2][32][256]
 #pragma unroll

@@ -37,6 +37,9 @@ struct SubsampleWeights {
   const float* w0; const float* b0;   // conv.0  [256,1,3,3], [256]
   const float* w2; const float* b2;   // conv.2  depthwise
   const float* w5; const float* b5;   // conv.5  depthwise
+  // the three 3x3 filters transposed to [9 taps][256 channels]: lanes that own adjacent channels read adjacent words (with the
+  // [256][9] layout every weight request of a warp touched up to 32 sectors: 163 M load sectors per stage-1 launch at 1024 streams)
+  const float* w0t; const float* w2t; const float* w5t;
 };
 
 struct ActOut {             // destination of a GEMM-A operand (bf16 hi plane [+ lo plane])

@@ -518,6 +518,18 @@ void Engine::load_weights() {
   im.sub.b2 = dev_upload(F(pe + "conv.2.bias", kSubCh));
   im.sub.w5 = dev_upload(F(pe + "conv.5.weight", (size_t)kSubCh * 9));
   im.sub.b5 = dev_upload(F(pe + "conv.5.bias", kSubCh));
+  {
+    auto transposed = [&](const std::string& name) {
+      const std::vector<float> w = F(name, (size_t)kSubCh * 9);
+      std::vector<float> t((size_t)9 * kSubCh);
+      for (int c = 0; c < kSubCh; ++c)
+        for (int k = 0; k < 9; ++k) t[(size_t)k * kSubCh + c] = w[(size_t)c * 9 + k];
+      return dev_upload(t);
+    };
+    im.sub.w0t = transposed(pe + "conv.0.weight");
+    im.sub.w2t = transposed(pe + "conv.2.weight");
+    im.sub.w5t = transposed(pe + "conv.5.weight");
+  }
   im.sub_pw1 = upload_gemm_w(wf.bf16(pe + "conv.3.weight"), kSubCh, kSubCh);
   im.sub_pw1_b = dev_upload(F(pe + "conv.3.bias", kSubCh));
   im.sub_pw2 = upload_gemm_w(wf.bf16(pe + "conv.6.weight"), kSubCh, kSubCh);
