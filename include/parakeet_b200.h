@@ -175,6 +175,10 @@ int32_t pkb_offline_utterances(PkbEngine* engine, int32_t n, const int32_t* stre
                                const size_t* n_samples, int32_t per_feature_norm, const float* const* features,
                                const int32_t* n_frames, int32_t bins_major, float* const* encoder_output, int32_t decode);
 int32_t pkb_offline_decode_pending(PkbEngine* engine);
+/* Host restatement hook of the streaming attention's load schedule (no GPU needed): bit q of the result is set when the 8-slot group
+ * [8q, 8q+8) of a 288-slot K / V ring holds at least one valid key for an entry whose logical position 0 sits at physical slot `head`,
+ * with `len` cached rows and `qlen` new rows -- the groups the kernel fetches.  0 for arguments outside the ring geometry. */
+uint64_t pkb_debug_ring_valid_groups(int32_t head, int32_t len, int32_t qlen);
 /* encoder frames produced for T feature frames: three times floor((L-1)/2)+1 */
 int32_t pkb_encoded_length(int32_t n_frames);
 /* predictor: y [B,1] i64, h,c [2,B,640] -> g [B,640,1], h_out,c_out [2,B,640] */

@@ -26,7 +26,7 @@ TRT_ASR_SYMBOLS = ["trt_asr_create_session", "trt_asr_destroy_session", "trt_asr
                    "trt_asr_push_features_f32", "trt_asr_poll_event"]
 B200_SYMBOLS = ["pkb_last_error", "pkb_version", "pkb_engine_create", "pkb_engine_destroy", "pkb_engine_num_layers",
                 "pkb_engine_kernel_launches", "pkb_stream_open", "pkb_stream_close", "pkb_stream_reset", "pkb_stream_push_features",
-                "pkb_stream_push_audio", "pkb_stream_set_feature_norm", "pkb_stream_set_feature_norm_running", "pkb_stream_set_offline", "pkb_encoder_offline_step", "pkb_offline_utterances", "pkb_offline_decode_pending", "pkb_encoded_length", "pkb_engine_push_audio_batch",
+                "pkb_stream_push_audio", "pkb_stream_set_feature_norm", "pkb_stream_set_feature_norm_running", "pkb_stream_set_offline", "pkb_encoder_offline_step", "pkb_offline_utterances", "pkb_offline_decode_pending", "pkb_encoded_length", "pkb_debug_ring_valid_groups", "pkb_engine_push_audio_batch",
                 "pkb_engine_push_audio_batch_device", "pkb_engine_event_record", "pkb_engine_event_elapsed_ms",
                 "pkb_engine_profile_enable", "pkb_engine_profile_read", "pkb_engine_profile_read_class", "pkb_engine_graphs_built", "pkb_engine_set_blank_penalty",
                 "pkb_engine_decode_loop_stats", "pkb_engine_step", "pkb_stream_has_pending",
@@ -151,6 +151,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.pkb_offline_utterances.argtypes = [vp, C.c_int32, ip, C.POINTER(fp), C.POINTER(C.c_size_t), C.c_int32, C.POINTER(fp), ip, C.c_int32,
                                            C.POINTER(fp), C.c_int32]
     lib.pkb_encoded_length.argtypes = [C.c_int32]
+    lib.pkb_debug_ring_valid_groups.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    lib.pkb_debug_ring_valid_groups.restype = C.c_uint64
     lib.pkb_offline_decode_pending.argtypes = [vp]
     lib.pkb_predictor_step.argtypes = [vp, C.c_int32, lp, fp, fp, fp, fp, fp]
     lib.pkb_joint_step.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, fp, fp, fp]

@@ -117,7 +117,6 @@ struct Smem {
 };
 
 constexpr int kGrpPerBlk = kBlkKeys / 8;          // 8-key groups per block
-constexpr int kNumGrp = kRingCap / 8;
 struct Item {
   int Tq, qlen, len, head, row0, ring_row0;
   unsigned need;      // bit k: 96-key block k holds at least one valid key
@@ -128,14 +127,7 @@ __device__ __forceinline__ Item load_item(const BatchDev& b, const AttnMmaArgs& 
   it.Tq = b.Tq[e]; it.qlen = b.qlen[e]; it.len = b.len[e]; it.head = b.head[e]; it.row0 = b.row_off[e];
   it.ring_row0 = (a.layer * a.n_slots + b.slot[e]) * (kHeads * kRingCap);      // + head * kRingCap: rings are head-major
   // valid logical positions j in [256-len, 256+qlen) form one circular run of physical slots
-  const int v_start = (it.head + kCacheS - it.len) % kRingCap, v_cnt = it.len + it.qlen;
-  // groups q0 .. q0 + n - 1 (circular over the kNumGrp groups of the ring) intersect the run
-  const int q0 = v_start >> 3;
-  int n = ((v_start + (v_cnt > 0 ? v_cnt : 1) - 1) >> 3) - q0 + 1;
-  n = n > kNumGrp ? kNumGrp : n;
-  const int hi = q0 + n < kNumGrp ? q0 + n : kNumGrp;
-  unsigned long long m = ((1ull << hi) - 1ull) & ~((1ull << q0) - 1ull);
-  if (q0 + n > kNumGrp) m |= (1ull << (q0 + n - kNumGrp)) - 1ull;
+  unsigned long long m = ring_valid_groups(it.head, it.len, it.qlen);      // common.cuh
   if (!a.trim) {      // whole blocks (A/B switch): every group of a needed block counts as valid
     unsigned long long full = 0;
 #pragma unroll

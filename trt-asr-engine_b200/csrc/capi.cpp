@@ -778,6 +778,10 @@ int32_t pkb_offline_decode_pending(PkbEngine* e) {
   PKB_ENTER(e);
   return guarded([&] { return e->eng->offline_decode_pending(); });
 }
+uint64_t pkb_debug_ring_valid_groups(int32_t head, int32_t len, int32_t qlen) {
+  if (head < 0 || head >= pkb::kRingCap || len < 0 || len > pkb::kCacheS || qlen < 0 || qlen > pkb::kMaxTq) return 0;
+  return pkb::ring_valid_groups(head, len, qlen);
+}
 int32_t pkb_encoded_length(int32_t L) {
   for (int i = 0; i < 3; ++i) L = L <= 0 ? 0 : (L - 1) / 2 + 1;
   return L;

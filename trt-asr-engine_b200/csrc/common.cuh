@@ -38,6 +38,25 @@ constexpr int kPosRows = kCacheS + 2 * kMaxTq;  // relative positions -(kMaxTq-1
 constexpr int kPosNeg = kMaxTq - 1;             // table row of relative position r is (r + kPosNeg)
 constexpr int kPosRowsPad = 320;                // rows of the natural-layout table (multiple of 8, zero padded)
 
+// Valid 8-slot groups of a K / V ring (attn_mma.cu fetches only these).  The valid logical positions of an entry -- the cache suffix
+// [256 - len, 256) and the qlen new rows [256, 256 + qlen) -- are ONE circular run of physical slots starting at
+// (head + 256 - len) mod kRingCap; bit q of the result is set when group q = slots [8q, 8q + 8) intersects that run.
+// Host-callable so that the bit algebra is checked exhaustively on the CPU (pkb_debug_ring_valid_groups, tests/test_ring_groups.py).
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline unsigned long long ring_valid_groups(int head, int len, int qlen) {
+  constexpr int kGroups = kRingCap / 8;
+  const int v_start = (head + kCacheS - len) % kRingCap, v_cnt = len + qlen;
+  const int q0 = v_start >> 3;
+  int n = ((v_start + (v_cnt > 0 ? v_cnt : 1) - 1) >> 3) - q0 + 1;      // groups q0 .. q0 + n - 1, circular
+  n = n > kGroups ? kGroups : n;
+  const int hi = q0 + n < kGroups ? q0 + n : kGroups;
+  unsigned long long m = ((1ull << hi) - 1ull) & ~((1ull << q0) - 1ull);
+  if (q0 + n > kGroups) m |= (1ull << (q0 + n - kGroups)) - 1ull;
+  return m;
+}
+
 struct CudaError : std::runtime_error {
   using std::runtime_error::runtime_error;
 };
