@@ -19,3 +19,11 @@ for f in sorted(glob.glob('gpurun_out/${T}_bench_*.json')):
     except Exception as e:
         print(f, 'ERR', e)
 PY
+if [ "${LF32:-0}" = "1" ]; then
+timeout 1500 python bench.py --no-cpu-baseline --no-config3 --steps 5 --longform 32 > gpurun_out/${T}_bench_lf32.json 2> gpurun_out/${T}_bench_lf32.err; echo "lf32 rc=$?"
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/${T}_bench_lf32.json').read().strip().splitlines()[-1])
+print('lf32', {k:v for k,v in d['config5_longform'].items() if k not in ('blank_penalty_calibration','workload')})
+PY
+fi
