@@ -31,7 +31,9 @@ typedef struct PkbEngine PkbEngine;
 
 typedef struct {
   const char* model_dir;    /* holds weights.bin + vocab.txt */
-  int32_t device_id;
+  int32_t device_id;        /* one process per GPU (the deployment north_star names): every entry point selects this device for the
+                               call, but the kernels' opt-in to > 48 KB of shared memory is configured once per PROCESS, on the
+                               device of the first engine -- engines on several devices of one process are not supported */
   int32_t max_streams;      /* stream slots (state is preallocated: ~45 MB per stream in bf16 mode) */
   int32_t precision;        /* 0 = bf16 tensor-core operands; 1 = split bf16 hi+lo operands (fp32-grade) */
   int32_t gemm_backend;     /* 0 = auto (tcgen05 above 16 rows, weight-streaming CUDA-core kernel below), 1 = CUDA cores only,
