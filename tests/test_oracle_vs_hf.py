@@ -114,3 +114,48 @@ def test_first_streaming_chunk_equals_full_context(features_ref):
     assert float((enc_s - enc_o[:, :, : m.valid_out]).abs().max()) < 1e-5
     # and the caches it hands on are what the next chunk needs: cache_len = tokens kept, time cache = last 4 kept GLU columns
     assert int(cl1) == 8 - m.drop
+
+
+@pytest.mark.parametrize("cache_len", [0, 5, 97, 256])
+def test_cache_aware_attention_step_matches_hf_attention(features_ref, cache_len):
+    """Pins the part of the streaming step the full-context comparison cannot reach -- attention with Tq != Tk over
+    [cache_last_channel || chunk], the 256 + Tq relative-position table, the validity mask of a partly filled cache and the FIFO cache
+    update -- against Hugging Face's ParakeetEncoderAttention, an implementation that knows nothing about caches.
+
+    Identity used: NeMo caches the attention INPUT (the norm_self_att output), so the chunk's attention output rows are the LAST Tq rows
+    of plain full self-attention over the sequence [valid cache rows ; chunk rows] (scores depend on content and on the distance
+    i - j only).  The oracle is made attention-only by zeroing the second linear of both FFNs and pointwise_conv2 (each layer becomes
+    norm_out(x + MHA(norm_self_att(x)))); stream_step() then runs through its public contract with a random cache whose INVALID prefix
+    holds garbage, and HF's attention module is driven layer by layer on the concatenated sequences."""
+    m = ModelRef(model_dir(2))
+    hf = _hf_encoder(m)
+    for l in range(m.L):
+        p = f"encoder.layers.{l}."
+        for n in ("feed_forward1.linear2.weight", "feed_forward2.linear2.weight", "conv.pointwise_conv2.weight"):
+            m.w[p + n] = torch.zeros_like(m.w[p + n])
+    f = normalized_features(features_ref, 1.0, 31)[:, :57]
+    f[0] = 0.0
+    x_in = torch.from_numpy(f[None])
+    torch.manual_seed(11 + cache_len)
+    cc = torch.randn(1, m.L, m.S, m.D)                       # rows [S - cache_len, S) are the valid suffix; the rest must be ignored
+    ct = torch.zeros(1, m.L, m.D, m.KT)
+    enc, enc_len, cc_out, _, len_out = m.stream_step(x_in, torch.tensor([57]), cc, ct, torch.tensor([cache_len]))
+
+    x, _ = m.pre_encode(x_in.transpose(1, 2), torch.tensor([57]))
+    x = x[:, m.drop_pre:, :]
+    Tq = x.size(1)
+    keep = Tq - m.drop
+    assert Tq == 6 and int(len_out) == min(cache_len + keep, m.S) and int(enc_len) == m.valid_out
+    with torch.no_grad():
+        for l in range(m.L):
+            p = f"encoder.layers.{l}."
+            a = torch.nn.functional.layer_norm(x, (m.D,), m.w[p + "norm_self_att.weight"], m.w[p + "norm_self_att.bias"], 1e-5)
+            seq = torch.cat([cc[:, l, m.S - cache_len:, :], a], dim=1)                 # [1, cache_len + Tq, D]
+            att, _ = hf.layers[l].self_attn(hidden_states=seq, position_embeddings=hf.encode_positions(seq), attention_mask=None)
+            x = torch.nn.functional.layer_norm(x + att[:, -Tq:, :], (m.D,), m.w[p + "norm_out.weight"], m.w[p + "norm_out.bias"], 1e-5)
+            # FIFO update: oldest `keep` rows leave, the chunk's first `keep` attention inputs enter at the END
+            want_cache = torch.cat([cc[:, l, keep:, :], a[:, :keep, :]], dim=1)
+            assert float((cc_out[:, l] - want_cache).abs().max()) < 1e-5
+    d = (enc - x.transpose(1, 2)[:, :, : m.valid_out]).abs()
+    assert float(d.max()) < 2e-5, float(d.max())
+    assert float(enc.abs().mean()) > 0.1
