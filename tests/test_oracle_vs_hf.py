@@ -159,3 +159,50 @@ def test_cache_aware_attention_step_matches_hf_attention(features_ref, cache_len
     d = (enc - x.transpose(1, 2)[:, :, : m.valid_out]).abs()
     assert float(d.max()) < 2e-5, float(d.max())
     assert float(enc.abs().mean()) > 0.1
+
+
+def test_cached_convolution_step_matches_hf_convolution_module(features_ref):
+    """The other streaming-specific piece: the conv module with its time cache.  NeMo's CausalConv1D with a cache convolves
+    [cache_last_time(4) | chunk | 0000] without further padding and hands on new_x[..., :-cache_drop][..., -4:].  The cached columns are
+    post-GLU activations of earlier frames, so for cached columns GLU(pointwise_conv1(h_prev)) the chunk's outputs are the LAST Tq rows of
+    Hugging Face's ParakeetEncoderConvolutionModule (symmetric (4,4) zero padding, no notion of a cache) applied to the sequence
+    [h_prev ; norm_conv(x)].  The oracle is made conv-only (attention linear_out and both FFN second linears zeroed: each layer is
+    norm_out(x + Conv(norm_conv(x)))) and run through stream_step()'s contract."""
+    m = ModelRef(model_dir(2))
+    hf = _hf_encoder(m)
+    for l in range(m.L):
+        p = f"encoder.layers.{l}."
+        for n in ("feed_forward1.linear2.weight", "feed_forward2.linear2.weight", "self_attn.linear_out.weight"):
+            m.w[p + n] = torch.zeros_like(m.w[p + n])
+    f = normalized_features(features_ref, 1.0, 32)[:, :57]
+    f[0] = 0.0
+    x_in = torch.from_numpy(f[None])
+    torch.manual_seed(5)
+    h_prev = torch.randn(m.L, 1, m.KT, m.D)                       # norm_conv outputs of the 4 frames before the chunk, per layer
+    ct = torch.zeros(1, m.L, m.D, m.KT)
+    for l in range(m.L):
+        pw1 = m.w[f"encoder.layers.{l}.conv.pointwise_conv1.weight"]
+        pw1 = pw1[:, :, 0] if pw1.dim() == 3 else pw1
+        ct[0, l] = torch.nn.functional.glu(torch.nn.functional.linear(h_prev[l], pw1), dim=-1)[0].transpose(0, 1)
+    cc = torch.zeros(1, m.L, m.S, m.D)
+    enc, _, _, ct_out, _ = m.stream_step(x_in, torch.tensor([57]), cc, ct, torch.tensor([0]))
+
+    x, _ = m.pre_encode(x_in.transpose(1, 2), torch.tensor([57]))
+    x = x[:, m.drop_pre:, :]
+    Tq = x.size(1)
+    with torch.no_grad():
+        for l in range(m.L):
+            p = f"encoder.layers.{l}."
+            c_in = torch.nn.functional.layer_norm(x, (m.D,), m.w[p + "norm_conv.weight"], m.w[p + "norm_conv.bias"], 1e-5)
+            out = hf.layers[l].conv(torch.cat([h_prev[l], c_in], dim=1))[:, -Tq:, :]
+            # time cache handed on: [x3, x4, x5, 0] of the chunk's post-GLU columns (docs/VALIDATION_REPORT_TRACE.md:212: last slot is zero)
+            pw1 = m.w[p + "conv.pointwise_conv1.weight"]
+            pw1 = pw1[:, :, 0] if pw1.dim() == 3 else pw1
+            glu = torch.nn.functional.glu(torch.nn.functional.linear(c_in, pw1), dim=-1)[0].transpose(0, 1)      # [D, Tq]
+            want_ct = torch.cat([glu, torch.zeros(m.D, 4 - m.drop)], dim=1)[:, -m.KT:]      # [..|chunk|0000] minus its last cache_drop columns
+            assert want_ct.shape == (m.D, m.KT) and float((ct_out[0, l] - want_ct).abs().max()) < 1e-5
+            assert float(ct_out[0, l, :, -1].abs().max()) == 0.0
+            x = torch.nn.functional.layer_norm(x + out, (m.D,), m.w[p + "norm_out.weight"], m.w[p + "norm_out.bias"], 1e-5)
+    d = (enc - x.transpose(1, 2)[:, :, : m.valid_out]).abs()
+    assert float(d.max()) < 2e-5, float(d.max())
+    assert float(enc.abs().mean()) > 0.1
